@@ -1,0 +1,76 @@
+"""TEST INFRASTRUCTURE ONLY -- generates `tests/golden/*.npz` from the UNMODIFIED reference.
+
+Run in the build container (needs `/root/reference`):   python oracle/make_golden.py
+
+For each case: seeded synthetic scenes (`trafficbots_b200.synthetic.make_batch`) and seeded parameters
+(`trafficbots_b200.weights.init_state_dict`) are loaded into the reference `WaymoMotion` (strict
+`load_state_dict`), the reference's own `pre_processing -> encode_input_features -> latent_encoder -> pred_goal ->
+reactive_replay -> joint_future_pred(K)` is executed (`oracle/ref_run.py`), and its outputs are stored.  Inputs and
+parameters are NOT stored -- they are regenerated from the seeds (a checksum of both is stored and verified).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import ref_loader  # noqa: E402
+import ref_run  # noqa: E402
+from trafficbots_b200 import synthetic, weights  # noqa: E402
+
+CASES = {
+    # name: (n_scene, n_agent, n_pl, K, scene_seed, weight_seed, sample_seed)
+    "cfg1_s1_a8_p64_k1": (1, 8, 64, 1, 11, 2023, 7),  # BASELINE.json configs[0] shape (parity gate)
+    "s3_a8_p64_k2": (3, 8, 64, 2, 100, 2023, 7),  # + zero-TL scene, single-valid-agent scene, K>1 sampling
+    "s1_a64_p1024_k1": (1, 64, 1024, 1, 500, 2023, 7),  # BASELINE.json configs[1] per-scene shape
+}
+
+KEEP = (
+    "enc/map_feature", "enc/map_feature_valid", "enc/agent_feature", "enc/tl_feature", "dest/probs",
+    "latent_prior/mean", "latent_post/mean", "jfp/goal_sample", "jfp/goal_log_probs", "jfp/latent_sample",
+    "jfp/hidden", "replay/hidden",
+)
+BUF = ("preds", "valid", "override_masks", "diffbar_rewards", "diffbar_rewards_valid", "latent_log_probs",
+       "action_log_probs", "violations/outside_map", "violations/outside_map_this_step", "violations/goal_reached",
+       "violations/goal_reached_this_step", "violations/dest_reached", "violations/dest_reached_this_step")
+
+
+def checksum(tensors) -> float:
+    """order-dependent fp64 checksum of a dict of tensors (inputs / parameters are regenerated, not stored)."""
+    acc = 0.0
+    for i, (k, v) in enumerate(sorted(tensors.items())):
+        acc += (i + 1) * float(v.double().sum()) + 1e-3 * float(v.double().abs().sum())
+    return acc
+
+
+def main() -> None:
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for name, (S, A, P, K, seed, wseed, sseed) in CASES.items():
+        model = ref_loader.build_reference(n_agent=A, n_pl=P, n_joint_future=K)
+        sd = weights.init_state_dict(wseed)
+        model.load_state_dict(sd, strict=True)
+        batch = synthetic.make_batch(S, n_agent=A, n_pl=P, seed=seed)
+        res = ref_run.run_reference(model, batch, k_futures=K, sample_seed=sseed)
+        keep = {k: res[k] for k in KEEP}
+        for leg in ("jfp", "replay"):
+            for b in BUF:
+                keep[f"{leg}/{b}"] = res[f"{leg}/{b}"]
+        arrays = {k.replace("/", "__"): v.numpy() for k, v in keep.items()}
+        arrays["meta__case"] = np.array([S, A, P, K, seed, wseed, sseed], dtype=np.int64)
+        arrays["meta__checksum_batch"] = np.array(checksum(batch))
+        arrays["meta__checksum_weights"] = np.array(checksum(sd))
+        path = os.path.join(out_dir, name + ".npz")
+        np.savez_compressed(path, **arrays)
+        print(name, "->", path, f"{os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()
