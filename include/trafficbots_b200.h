@@ -1,0 +1,228 @@
+/*
+ * trafficbots_b200 -- C ABI of the B200-native TrafficBots hot path (scene encoding + closed-loop rollout).
+ *
+ * The reference (zhejz/TrafficBots) is pure Python/PyTorch and has NO C/FFI boundary; its "plugin API" for this
+ * path is a set of nn.Module methods selected through Hydra `_target_`s.  Each entry point below
+ * names the reference method(s) it replaces (paths relative to the reference's `src/`); the Python mirror of
+ * those methods (trafficbots_b200/pl_modules, trafficbots_b200/models) binds this library with ctypes, and
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless it says "host"; all tensors are dense, row-major, in the
+ *     reference's batch schema (`data_modules/data_h5_womd.py:85-173`); `bool` tensors are 1 byte per element.
+ *   - the caller owns and allocates every buffer; the library keeps no global mutable state and never
+ *     allocates device memory; every call is asynchronous on the `stream` argument (a `cudaStream_t`).
+ *   - return value: TB_OK or a negative tb_status; nothing is thrown across the ABI.
+ *   - all arithmetic is fp32 (the reference's eval-mode dtype).
+ */
+#ifndef TRAFFICBOTS_B200_H_
+#define TRAFFICBOTS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum tb_status {
+  TB_OK = 0,
+  TB_ERR_BAD_SHAPE = -1,   /* a dimension is out of the supported range */
+  TB_ERR_NULL = -2,        /* a required pointer is NULL */
+  TB_ERR_LAUNCH = -3,      /* a CUDA launch failed (cudaGetLastError) */
+  TB_ERR_UNSUPPORTED = -4, /* configuration outside the default `configs/model/traffic_bots.yaml` surface */
+  TB_ERR_ALIGN = -5        /* a float buffer is not 16-byte aligned */
+} tb_status;
+
+/* Fixed by the default model config (configs/model/traffic_bots.yaml): hidden_dim 128, n_head 4,
+ * d_feedforward 128, pe_dim 96, 3 GRU layers, latent_dim 16; data: 20 nodes per polyline, 11 polyline types,
+ * 5 traffic-light states. */
+#define TB_HIDDEN 128
+#define TB_LATENT 16
+#define TB_PL_NODE 20
+#define TB_PL_TYPE 11
+#define TB_TL_STATE 5
+#define TB_N_VIOLATION 6 /* outside_map, outside_map_this_step, goal_reached, goal_reached_this_step,
+                            dest_reached, dest_reached_this_step (utils/traffic_rule_checker.py:499-515) */
+
+typedef struct TbDims {
+  int32_t n_scene;     /* S: scenes in the batch */
+  int32_t n_mode;      /* K: joint futures per scene; scene-mode b = s*K + k (waymo_motion.py:487-548) */
+  int32_t n_agent;     /* A */
+  int32_t n_pl;        /* P: map polylines */
+  int32_t n_tl;        /* TL: traffic-light stop points */
+  int32_t n_step_hist; /* history frames = time_step_current + 1 (11); also the number of TL frames */
+  int32_t n_step_gt;   /* frames in the GT tensors used for overriding: 91 (train/val) or 11 (test) */
+  int32_t n_step;      /* decode steps stored in the outputs = time_step_end (90) */
+} TbDims;
+
+/* ---------------------------------------------------------------- parameters ------------------------- */
+
+/* Number of tensors in the packed parameter blob, and for tensor i its reference state_dict key, shape
+ * (cols == 0 for 1-D tensors) -- the order in which tb_pack_weights expects its pointers. */
+int32_t tb_weight_count(void);
+const char* tb_weight_name(int32_t i);
+int32_t tb_weight_rows(int32_t i);
+int32_t tb_weight_cols(int32_t i);
+size_t tb_packed_weight_bytes(void);
+
+/* Re-lays the reference's fp32 parameters (host array of `tb_weight_count()` device pointers, each a
+ * contiguous tensor exactly as in `WaymoMotion.state_dict()`) into the kernel layout.  Replaces
+ * `load_state_dict` (run.py:40-44).  `packed`: tb_packed_weight_bytes() bytes. */
+int32_t tb_pack_weights(const float* const* params_host_array, float* packed, void* stream);
+
+/* ---------------------------------------------------------------- scene encoding ---------------------- */
+
+typedef struct TbSceneIn { /* raw batch tensors (what SceneCentricInput consumes, data_modules/sc_input.py:98-140) */
+  const uint8_t* map_valid;      /* [S,P,20]      map/valid   */
+  const uint8_t* map_type;       /* [S,P,11]      map/type    */
+  const float* map_pos;          /* [S,P,20,2]    map/pos     */
+  const float* map_dir;          /* [S,P,20,2]    map/dir     */
+  const uint8_t* agent_valid;    /* [S,Th,A]      history/agent/valid */
+  const float* agent_pos;        /* [S,Th,A,2]    */
+  const float* agent_yaw;        /* [S,Th,A,1]    history/agent/yaw_bbox */
+  const float* agent_vel;        /* [S,Th,A,2]    */
+  const float* agent_spd;        /* [S,Th,A,1]    */
+  const float* agent_yaw_rate;   /* [S,Th,A,1]    */
+  const float* agent_acc;        /* [S,Th,A,1]    */
+  const float* agent_size;       /* [S,A,3]       */
+  const uint8_t* agent_type;     /* [S,A,3]       */
+  const uint8_t* tl_valid;       /* [S,Th,TL]     history/tl_stop/valid */
+  const uint8_t* tl_state;       /* [S,Th,TL,5]   */
+  const float* tl_pos;           /* [S,Th,TL,2]   */
+  const float* tl_dir;           /* [S,Th,TL,2]   */
+} TbSceneIn;
+
+typedef struct TbSceneOut { /* == the dict returned by TrafficBots.encode_input_features (traffic_bots.py:146-151) */
+  float* map_feature;            /* [S,P,128]     */
+  uint8_t* map_feature_valid;    /* [S,P]         */
+  float* agent_feature;          /* [S,Th,A,128]  */
+  float* tl_feature;             /* [S,Th,TL,128] */
+  /* loop-invariant attention operands, projected once per scene (the reference re-projects them at every
+   * decode step and layer, attention.py:86): K|V = LN_tgt(tgt) W_kv + b for the 3 agent->map layers and the
+   * 3 agent->traffic-light layers of the policy (traffic_bots.py:205-219). */
+  float* kv_map;                 /* [3,S,P,256]      */
+  float* kv_tl;                  /* [3,S,Th,TL,256]  */
+} TbSceneOut;
+
+/* scratch needed by tb_encode_scene */
+size_t tb_encode_workspace_bytes(const TbDims* dims);
+
+/* SceneCentricInput.forward + TrafficBots.encode_input_features (data_modules/sc_input.py:98-140,
+ * models/traffic_bots.py:109-151, models/modules/map_encoder.py:58-115, input_pe_encoder.py:41-61). */
+int32_t tb_encode_scene(const TbDims* dims, const TbSceneIn* in, const float* packed, const TbSceneOut* out,
+                        void* workspace, void* stream);
+
+/* ---------------------------------------------------------------- building blocks --------------------- */
+
+/* Identifies one TransformerBlock of the reference (models/modules/transformer.py:53-95). */
+typedef enum tb_block {
+  TB_BLOCK_MAP_DENSETNT = 0,   /* model.map_encoder.transformer_densetnt (3 layers)   */
+  TB_BLOCK_MAP_SELF_ATTN = 1,  /* model.map_encoder.transformer_self_attn (1 layer)   */
+  TB_BLOCK_AS2PL = 2,          /* model.transformer_as2pl (3)                          */
+  TB_BLOCK_AS2TL = 3,          /* model.transformer_as2tl (3)                          */
+  TB_BLOCK_INTERACTION = 4,    /* model.agent_interaction.transformer (3)              */
+  TB_BLOCK_LATENT_PRIOR_INT = 5, /* model.latent_encoder.agent_interaction_prior.transformer (3) */
+  TB_BLOCK_LATENT_POST_INT = 6   /* model.latent_encoder.agent_interaction_post.transformer (3)  */
+} tb_block;
+
+/* K|V projection of one layer: kv[row] = LN_tgt(tgt[row]) W_kv^T + b_kv  (transformer.py:192 + attention.py:86).
+ * tgt [n_row,128] -> kv [n_row,256]. */
+int32_t tb_kv_project(int32_t block, int32_t layer, const float* tgt, int64_t n_row, const float* packed,
+                      float* kv, void* stream);
+
+/* One pre-LN cross-attention layer, TransformerCrossAttention.forward (transformer.py:186-237) with
+ * Attention.forward (attention.py:79-146), K|V given by tb_kv_project.
+ *   src [n_batch,n_src,128], src_valid [n_batch,n_src]; the keys of batch element b are
+ *   kv[(b / kv_share) ...]: kv [n_batch/kv_share, n_key, 256], key_valid [n_batch/kv_share, n_key];
+ *   mask_self != 0 additionally disables key j for query j (the eye attn_mask of agent_interaction.py:57-59).
+ * Rows without any enabled key get a zero attention output (attention.py:101-107,144-146); rows with
+ * src_valid == 0 are zeroed at the end (transformer.py:236-237).  dst may alias src. */
+int32_t tb_xlayer(int32_t block, int32_t layer, const float* src, const uint8_t* src_valid, int32_t n_batch,
+                  int32_t n_src, const float* kv, const uint8_t* key_valid, int32_t n_key, int32_t kv_share,
+                  int32_t mask_self, const float* packed, float* dst, void* stream);
+
+/* ---------------------------------------------------------------- closed-loop rollout ----------------- */
+
+typedef struct TbRolloutIn {
+  /* per scene (shared by the K modes of the scene) */
+  const float* map_feature;        /* [S,P,128]   TbSceneOut.map_feature (destination feature gather) */
+  const uint8_t* map_feature_valid;/* [S,P]       */
+  const float* kv_map;             /* [3,S,P,256] */
+  const float* kv_tl;              /* [3,S,Th,TL,256] */
+  const uint8_t* tl_valid;         /* [S,Th,TL]   */
+  const uint8_t* gt_valid;         /* [S,Tg,A]    agent/valid   (Tg = n_step_gt) */
+  const float* gt_pos;             /* [S,Tg,A,2]  agent/pos      */
+  const float* gt_yaw;             /* [S,Tg,A,1]  agent/yaw_bbox */
+  const float* gt_spd;             /* [S,Tg,A,1]  agent/spd      */
+  const float* gt_vel;             /* [S,Tg,A,2]  agent/vel      */
+  const float* gt_acc;             /* [S,Tg,A,1]  agent/acc      */
+  const float* gt_yaw_rate;        /* [S,Tg,A,1]  agent/yaw_rate */
+  const uint8_t* tf_mask;          /* [S,Tg,A]    TeacherForcing.get (utils/teacher_forcing.py:33-74) */
+  const uint8_t* agent_type;       /* [S,A,3]     */
+  const float* agent_size;         /* [S,A,3]     */
+  const float* map_boundary;       /* [S,4]  xmin,xmax,ymin,ymax */
+  const uint8_t* map_valid;        /* [S,P,20]    raw map (destination polyline nodes, traffic_rule_checker.py:82-98) */
+  const uint8_t* map_type;         /* [S,P,11]    */
+  const float* map_pos;            /* [S,P,20,2]  */
+  const float* map_dir;            /* [S,P,20,2]  */
+  const float* goal_gt;            /* [S,A,4] agent/goal, or NULL (test mode: no goal_reached check) */
+  /* per scene-mode (B = S*K) */
+  const float* latent_sample;      /* [B,A,16]   sampled once per rollout (traffic_bots.py:196-199) */
+  const float* latent_logp;        /* [B,A]      */
+  const int64_t* dest;             /* [B,A]      destination polyline index */
+  const uint8_t* goal_valid;       /* [B,A]      */
+} TbRolloutIn;
+
+typedef struct TbRolloutOut { /* == RolloutBuffer after finish() (utils/buffer.py:72-90), T = n_step */
+  float* preds;                    /* [B,A,T,4]  x,y,yaw,spd (pre-override prediction) */
+  uint8_t* valid;                  /* [B,A,T]    */
+  uint8_t* override_masks;         /* [B,A,T]    */
+  float* diffbar_rewards;          /* [B,A,T]    */
+  uint8_t* diffbar_rewards_valid;  /* [B,A,T]    */
+  float* action_log_probs;         /* [B,A,T]    */
+  float* latent_log_probs;         /* [B,A,T]    */
+  uint8_t* violations;             /* [6,B,A,T]  order: see TB_N_VIOLATION */
+  float* trace_policy_feature;     /* optional [B,A,T,128] (NULL to skip): input of the action head */
+  float* trace_action_mean;        /* optional [B,A,T,2] */
+} TbRolloutOut;
+
+/* The simulation state that the reference keeps on `Dynamics`, `TrafficBots.hidden`, `TrafficRuleChecker` and
+ * `goal_valid` between decode steps lives in one caller-owned buffer.  Field offsets (bytes) for host-side
+ * views: */
+typedef enum tb_state_field {
+  TB_STATE_AGENT_STATE = 0, /* float [B,A,4]  dynamics.agent_state                 */
+  TB_STATE_VALID = 1,       /* u8 [2,B,A]     dynamics.agent_valid, double-buffered by step parity (t&1) */
+  TB_STATE_KILLED = 2,      /* u8 [B,A]       */
+  TB_STATE_VEL = 3,         /* float [B,A,2]  dynamics.vel (only changed by overrides) */
+  TB_STATE_ACC = 4,         /* float [B,A]    */
+  TB_STATE_YAW_RATE = 5,    /* float [B,A]    */
+  TB_STATE_GOAL_VALID = 6,  /* u8 [B,A]       */
+  TB_STATE_STICKY = 7,      /* u8 [3,B,A]     outside_map, goal_reached, dest_reached */
+  TB_STATE_HIDDEN = 8,      /* float [3,B*A,128]  TrafficBots.hidden (GRU) */
+  TB_STATE_N_FIELD = 9
+} tb_state_field;
+size_t tb_rollout_state_bytes(const TbDims* dims);     /* includes private scratch behind the fields */
+size_t tb_rollout_state_offset(const TbDims* dims, int32_t field);
+
+/* rollout set-up: Dynamics.init with frame 0 (waymo_motion.py:251-259), TrafficBots.init (traffic_bots.py:153-161),
+ * TrafficRuleChecker.__init__ (traffic_rule_checker.py:45-98), get_goal_feature (goal_manager.py:83-139), and the
+ * loop-invariant `mlp_in` halves of add_goal / add_latent (add_latent_goal.py:57). */
+int32_t tb_rollout_init(const TbDims* dims, const TbRolloutIn* in, const float* packed, void* state, void* stream);
+
+/* decode steps t_first..t_last (1-based, inclusive; WaymoMotion.rollout's loop body, waymo_motion.py:269-343,
+ * with WaymoMotion.forward :108-203).  Step t writes slot t-1 of the outputs. */
+int32_t tb_rollout_steps(const TbDims* dims, const TbRolloutIn* in, const float* packed, void* state,
+                         const TbRolloutOut* out, int32_t t_first, int32_t t_last, void* stream);
+
+/* tb_rollout_init + tb_rollout_steps(1..n_step) == WaymoMotion.rollout (waymo_motion.py:205-354). */
+int32_t tb_rollout(const TbDims* dims, const TbRolloutIn* in, const float* packed, void* state,
+                   const TbRolloutOut* out, void* stream);
+
+/* Kernels this library launches on a call path, for accounting (`gpu_launches` in bench.py). */
+int64_t tb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRAFFICBOTS_B200_H_ */

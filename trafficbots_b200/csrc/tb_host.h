@@ -1,0 +1,22 @@
+// Host-side helpers shared by the translation units of libtrafficbots_b200.so.
+#pragma once
+#include <atomic>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/trafficbots_b200.h"
+#include "tb_device.cuh"
+
+namespace tb {
+
+constexpr int ROW_TILE = 16;  // feature rows per CTA in the row-tile kernels
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern std::atomic<long long> g_launches;  // diagnostics only (tb_launch_count)
+inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+inline int launch_status() { return cudaGetLastError() == cudaSuccess ? TB_OK : TB_ERR_LAUNCH; }
+
+int check_dims_host(const TbDims* d);
+
+}  // namespace tb

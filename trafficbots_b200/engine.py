@@ -1,0 +1,261 @@
+"""Host-side driver of the CUDA hot path: owns the packed parameters and the device buffers, and exposes the two
+operations the reference's training / eval loop needs -- scene encoding and the closed-loop rollout -- on torch
+CUDA tensors in the reference's batch schema.  All arithmetic happens in `libtrafficbots_b200.so`; torch is used
+for device memory and streams only.
+
+Reference methods replaced (paths under the reference's `src/`):
+  `Engine.encode_scene`  -> `SceneCentricInput.forward` + `TrafficBots.encode_input_features`
+                            (data_modules/sc_input.py:98-140, models/traffic_bots.py:109-151)
+  `Engine.rollout`       -> `WaymoMotion.rollout` with `WaymoMotion.forward` as the loop body
+                            (pl_modules/waymo_motion.py:108-354)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Mapping, Optional
+
+import torch
+from torch import Tensor
+
+from . import _native as nt
+
+VIOLATION_KEYS = ("outside_map", "outside_map_this_step", "goal_reached", "goal_reached_this_step", "dest_reached",
+                  "dest_reached_this_step")
+# the four checks that are off in the default config report their (all-False) sticky state (traffic_rule_checker.py:426-472)
+DISABLED_VIOLATION_KEYS = ("collided", "collided_this_step", "run_road_edge", "run_road_edge_this_step",
+                           "run_red_light", "run_red_light_this_step", "passive", "passive_this_step")
+
+
+class SceneFeatures(dict):
+    """dict returned by `encode_scene`: the reference's feature dict (`agent_feature(_valid)`, `map_feature(_valid)`,
+    `tl_feature(_valid)`) plus the projected K|V caches under private keys (`_kv_map`, `_kv_tl`)."""
+
+
+class Engine:
+    def __init__(self, state_dict: Mapping[str, Tensor], device: Optional[torch.device] = None):
+        self.lib = nt.lib()
+        if not torch.cuda.is_available():
+            raise nt.TbError("no CUDA device: trafficbots_b200 has no CPU implementation of the hot path")
+        self.device = torch.device(device if device is not None else "cuda")
+        self.packed = torch.empty(self.lib.tb_packed_weight_bytes() // 4, dtype=torch.float32, device=self.device)
+        self.load_state_dict(state_dict)
+        self._enc_ws: Optional[Tensor] = None
+        self._state: Optional[Tensor] = None
+        self._state_dims = None
+        self.last_t = 0
+
+    # ------------------------------------------------------------------------------------------------ parameters
+    def load_state_dict(self, state_dict: Mapping[str, Tensor]) -> None:
+        """re-lays a reference `WaymoMotion.state_dict()` (fp32) into the kernel layout (`tb_pack_weights`)."""
+        n = self.lib.tb_weight_count()
+        keep = []
+        ptrs = (C.c_void_p * n)()
+        for i in range(n):
+            name = self.lib.tb_weight_name(i).decode()
+            rows, cols = self.lib.tb_weight_rows(i), self.lib.tb_weight_cols(i)
+            if name not in state_dict:
+                raise nt.TbError(f"state_dict is missing {name}")
+            t = state_dict[name].detach().to(device=self.device, dtype=torch.float32).contiguous()
+            want = (rows,) if cols == 0 else (rows, cols)
+            if tuple(t.shape) != want:
+                raise nt.TbError(f"{name}: shape {tuple(t.shape)}, expected {want}")
+            keep.append(t)
+            ptrs[i] = t.data_ptr()
+        with torch.cuda.device(self.device):
+            nt.check(self.lib.tb_pack_weights(ptrs, self.packed.data_ptr(), nt.current_stream_ptr()), "tb_pack_weights")
+            torch.cuda.current_stream().synchronize()  # `keep` may be freed after this
+
+    # ------------------------------------------------------------------------------------------------ encoding
+    @staticmethod
+    def _dims(S, K, A, P, TL, Th, Tg, T) -> nt.TbDims:
+        return nt.TbDims(S, K, A, P, TL, Th, Tg, T)
+
+    def encode_scene(self, batch: Mapping[str, Tensor], prefix: str = "history/") -> SceneFeatures:
+        """batch: reference batch dict (CUDA tensors). Uses map/* and `{prefix}agent/*`, `{prefix}tl_stop/*`."""
+        mv = batch["map/valid"]
+        S, P, N = mv.shape
+        if N != 20:
+            raise nt.TbError("n_pl_node must be 20")
+        av = batch[prefix + "agent/valid"]
+        Th, A = av.shape[1], av.shape[2]
+        TL = batch[prefix + "tl_stop/valid"].shape[2]
+        dims = self._dims(S, 1, A, P, TL, Th, Th, 1)
+        g = lambda k: batch[k]  # noqa: E731
+        a = prefix + "agent/"
+        tl = prefix + "tl_stop/"
+        sin = nt.TbSceneIn(
+            nt.dev_ptr(mv, "u8", (S, P, 20), "map/valid"), nt.dev_ptr(g("map/type"), "u8", (S, P, 11), "map/type"),
+            nt.dev_ptr(g("map/pos"), "f32", (S, P, 20, 2), "map/pos"), nt.dev_ptr(g("map/dir"), "f32", (S, P, 20, 2), "map/dir"),
+            nt.dev_ptr(av, "u8", (S, Th, A), a + "valid"), nt.dev_ptr(g(a + "pos"), "f32", (S, Th, A, 2), a + "pos"),
+            nt.dev_ptr(g(a + "yaw_bbox"), "f32", (S, Th, A, 1), a + "yaw_bbox"),
+            nt.dev_ptr(g(a + "vel"), "f32", (S, Th, A, 2), a + "vel"), nt.dev_ptr(g(a + "spd"), "f32", (S, Th, A, 1), a + "spd"),
+            nt.dev_ptr(g(a + "yaw_rate"), "f32", (S, Th, A, 1), a + "yaw_rate"),
+            nt.dev_ptr(g(a + "acc"), "f32", (S, Th, A, 1), a + "acc"), nt.dev_ptr(g(a + "size"), "f32", (S, A, 3), a + "size"),
+            nt.dev_ptr(g(a + "type"), "u8", (S, A, 3), a + "type"), nt.dev_ptr(g(tl + "valid"), "u8", (S, Th, TL), tl + "valid"),
+            nt.dev_ptr(g(tl + "state"), "u8", (S, Th, TL, 5), tl + "state"),
+            nt.dev_ptr(g(tl + "pos"), "f32", (S, Th, TL, 2), tl + "pos"), nt.dev_ptr(g(tl + "dir"), "f32", (S, Th, TL, 2), tl + "dir"))
+        dev = self.device
+        f = SceneFeatures()
+        f["map_feature"] = torch.empty(S, P, 128, device=dev)
+        f["map_feature_valid"] = torch.empty(S, P, dtype=torch.bool, device=dev)
+        f["agent_feature"] = torch.empty(S, Th, A, 128, device=dev)
+        f["agent_feature_valid"] = av
+        f["tl_feature"] = torch.empty(S, Th, TL, 128, device=dev)
+        f["tl_feature_valid"] = batch[tl + "valid"]
+        f["_kv_map"] = torch.empty(3, S, P, 256, device=dev)
+        f["_kv_tl"] = torch.empty(3, S, Th, TL, 256, device=dev)
+        sout = nt.TbSceneOut(f["map_feature"].data_ptr(), f["map_feature_valid"].data_ptr(), f["agent_feature"].data_ptr(),
+                             f["tl_feature"].data_ptr(), f["_kv_map"].data_ptr(), f["_kv_tl"].data_ptr())
+        need = self.lib.tb_encode_workspace_bytes(C.byref(dims))
+        if self._enc_ws is None or self._enc_ws.numel() < need:
+            self._enc_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            nt.check(self.lib.tb_encode_scene(C.byref(dims), C.byref(sin), self.packed.data_ptr(), C.byref(sout),
+                                              self._enc_ws.data_ptr(), nt.current_stream_ptr()), "tb_encode_scene")
+        return f
+
+    # ------------------------------------------------------------------------------------------------ building blocks
+    def kv_project(self, block: int, layer: int, tgt: Tensor) -> Tensor:
+        rows = tgt.numel() // 128
+        kv = torch.empty(*tgt.shape[:-1], 256, device=self.device)
+        with torch.cuda.device(self.device):
+            nt.check(self.lib.tb_kv_project(block, layer, nt.dev_ptr(tgt, "f32", name="tgt"), rows, self.packed.data_ptr(),
+                                            kv.data_ptr(), nt.current_stream_ptr()), "tb_kv_project")
+        return kv
+
+    def xlayer(self, block: int, layer: int, src: Tensor, src_valid: Tensor, kv: Tensor, key_valid: Tensor,
+               kv_share: int = 1, mask_self: bool = False) -> Tensor:
+        nb, ns, _ = src.shape
+        nk = kv.shape[-2]
+        dst = torch.empty_like(src)
+        with torch.cuda.device(self.device):
+            nt.check(self.lib.tb_xlayer(block, layer, nt.dev_ptr(src, "f32", name="src"),
+                                        nt.dev_ptr(src_valid, "u8", (nb, ns), "src_valid"), nb, ns,
+                                        nt.dev_ptr(kv, "f32", (nb // kv_share, nk, 256), "kv"),
+                                        nt.dev_ptr(key_valid, "u8", (nb // kv_share, nk), "key_valid"), nk, kv_share,
+                                        int(mask_self), self.packed.data_ptr(), dst.data_ptr(), nt.current_stream_ptr()),
+                     "tb_xlayer")
+        return dst
+
+    # ------------------------------------------------------------------------------------------------ rollout
+    def _rollout_structs(self, feat, gt, tf_mask, agent_type, agent_size, raw_map, latent_sample, latent_logp, dest,
+                         goal_valid, goal_gt, n_mode, n_step):
+        S, P, _ = feat["map_feature"].shape
+        Th, TL = feat["tl_feature_valid"].shape[1:]
+        Tg, A = gt["valid"].shape[1:]
+        B = S * n_mode
+        dims = self._dims(S, n_mode, A, P, TL, Th, Tg, n_step)
+        p = nt.dev_ptr
+        rin = nt.TbRolloutIn(
+            p(feat["map_feature"], "f32", (S, P, 128), "map_feature"), p(feat["map_feature_valid"], "u8", (S, P), "map_feature_valid"),
+            p(feat["_kv_map"], "f32", (3, S, P, 256), "_kv_map"), p(feat["_kv_tl"], "f32", (3, S, Th, TL, 256), "_kv_tl"),
+            p(feat["tl_feature_valid"], "u8", (S, Th, TL), "tl_feature_valid"),
+            p(gt["valid"], "u8", (S, Tg, A), "gt valid"), p(gt["pos"], "f32", (S, Tg, A, 2), "gt pos"),
+            p(gt["yaw_bbox"], "f32", (S, Tg, A, 1), "gt yaw_bbox"), p(gt["spd"], "f32", (S, Tg, A, 1), "gt spd"),
+            p(gt["vel"], "f32", (S, Tg, A, 2), "gt vel"), p(gt["acc"], "f32", (S, Tg, A, 1), "gt acc"),
+            p(gt["yaw_rate"], "f32", (S, Tg, A, 1), "gt yaw_rate"), p(tf_mask, "u8", (S, Tg, A), "tf_mask"),
+            p(agent_type, "u8", (S, A, 3), "agent_type"), p(agent_size, "f32", (S, A, 3), "agent_size"),
+            p(raw_map["boundary"], "f32", (S, 4), "map/boundary"), p(raw_map["valid"], "u8", (S, P, 20), "map/valid"),
+            p(raw_map["type"], "u8", (S, P, 11), "map/type"), p(raw_map["pos"], "f32", (S, P, 20, 2), "map/pos"),
+            p(raw_map["dir"], "f32", (S, P, 20, 2), "map/dir"), p(goal_gt, "f32", (S, A, 4), "goal_gt", optional=True),
+            p(latent_sample, "f32", (B, A, 16), "latent_sample"), p(latent_logp, "f32", (B, A), "latent_logp"),
+            p(dest, "i64", (B, A), "dest"), p(goal_valid, "u8", (B, A), "goal_valid"))
+        return dims, rin
+
+    def _ensure_state(self, dims: nt.TbDims) -> Tensor:
+        need = self.lib.tb_rollout_state_bytes(C.byref(dims))
+        if self._state is None or self._state.numel() < need:
+            self._state = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self._state_dims = dims
+        return self._state
+
+    def alloc_outputs(self, B: int, A: int, T: int, trace: bool = False) -> Dict[str, Tensor]:
+        dev = self.device
+        o = {
+            "preds": torch.empty(B, A, T, 4, device=dev), "valid": torch.empty(B, A, T, dtype=torch.bool, device=dev),
+            "override_masks": torch.empty(B, A, T, dtype=torch.bool, device=dev),
+            "diffbar_rewards": torch.empty(B, A, T, device=dev),
+            "diffbar_rewards_valid": torch.empty(B, A, T, dtype=torch.bool, device=dev),
+            "action_log_probs": torch.empty(B, A, T, device=dev), "latent_log_probs": torch.empty(B, A, T, device=dev),
+            "_violations": torch.empty(6, B, A, T, dtype=torch.bool, device=dev),
+        }
+        if trace:
+            o["trace/policy_feature"] = torch.empty(B, A, T, 128, device=dev)
+            o["trace/action_mean"] = torch.empty(B, A, T, 2, device=dev)
+        return o
+
+    @staticmethod
+    def _out_struct(o: Dict[str, Tensor]) -> nt.TbRolloutOut:
+        tp = o.get("trace/policy_feature")
+        ta = o.get("trace/action_mean")
+        return nt.TbRolloutOut(o["preds"].data_ptr(), o["valid"].data_ptr(), o["override_masks"].data_ptr(),
+                               o["diffbar_rewards"].data_ptr(), o["diffbar_rewards_valid"].data_ptr(),
+                               o["action_log_probs"].data_ptr(), o["latent_log_probs"].data_ptr(),
+                               o["_violations"].data_ptr(), tp.data_ptr() if tp is not None else None,
+                               ta.data_ptr() if ta is not None else None)
+
+    def rollout(self, feat: Mapping[str, Tensor], gt: Mapping[str, Tensor], tf_mask: Tensor, agent_type: Tensor,
+                agent_size: Tensor, raw_map: Mapping[str, Tensor], latent_sample: Tensor, latent_logp: Tensor,
+                dest: Tensor, goal_valid: Tensor, goal_gt: Optional[Tensor], n_mode: int = 1, n_step: int = 90,
+                trace: bool = False, out: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+        """Full closed-loop rollout (t = 1..n_step).  Per-scene tensors have leading dim S, per-scene-mode tensors
+        (`latent_sample`, `latent_logp`, `dest`, `goal_valid`) have leading dim B = S * n_mode (scene-major).
+        gt: dict with valid/pos/yaw_bbox/spd/vel/acc/yaw_rate, [S,Tg,A,.].  Returns the RolloutBuffer fields,
+        `[B,A,T,.]`, violations as `violations/<key>`."""
+        dims, rin = self._rollout_structs(feat, gt, tf_mask, agent_type, agent_size, raw_map, latent_sample,
+                                          latent_logp, dest, goal_valid, goal_gt, n_mode, n_step)
+        B, A = dims.n_scene * dims.n_mode, dims.n_agent
+        if out is None:
+            out = self.alloc_outputs(B, A, n_step, trace)
+        state = self._ensure_state(dims)
+        rout = self._out_struct(out)
+        with torch.cuda.device(self.device):
+            nt.check(self.lib.tb_rollout(C.byref(dims), C.byref(rin), self.packed.data_ptr(), state.data_ptr(),
+                                         C.byref(rout), nt.current_stream_ptr()), "tb_rollout")
+        self.last_t = n_step
+        return self._finish(out)
+
+    def _finish(self, out: Dict[str, Tensor]) -> Dict[str, Tensor]:
+        res = {k: v for k, v in out.items() if not k.startswith("_")}
+        for i, k in enumerate(VIOLATION_KEYS):
+            res[f"violations/{k}"] = out["_violations"][i]
+        res["hidden"] = self.state_field(nt.STATE_HIDDEN)
+        res["final_state"] = self.state_field(nt.STATE_AGENT_STATE)
+        res["final_valid"] = self.state_field(nt.STATE_VALID)
+        return res
+
+    def state_field(self, field: int) -> Tensor:
+        """typed view into the simulation-state buffer (see `tb_state_field` in the header)."""
+        d = self._state_dims
+        B, A = d.n_scene * d.n_mode, d.n_agent
+        off = self.lib.tb_rollout_state_offset(C.byref(d), field)
+        raw = self._state
+        f32 = lambda n: raw[off: off + 4 * n].view(torch.float32)  # noqa: E731
+        u8 = lambda n: raw[off: off + n].view(torch.bool)  # noqa: E731
+        if field == nt.STATE_AGENT_STATE:
+            return f32(B * A * 4).view(B, A, 4)
+        if field == nt.STATE_VALID:
+            return u8(2 * B * A).view(2, B, A)[(self.last_t + 1) & 1]
+        if field in (nt.STATE_KILLED, nt.STATE_GOAL_VALID):
+            return u8(B * A).view(B, A)
+        if field == nt.STATE_VEL:
+            return f32(B * A * 2).view(B, A, 2)
+        if field in (nt.STATE_ACC, nt.STATE_YAW_RATE):
+            return f32(B * A).view(B, A)
+        if field == nt.STATE_STICKY:
+            return u8(3 * B * A).view(3, B, A)
+        if field == nt.STATE_HIDDEN:
+            return f32(3 * B * A * 128).view(3, B * A, 128)
+        raise nt.TbError(f"unknown state field {field}")
+
+
+def gt_from_batch(batch: Mapping[str, Tensor], n_frame: Optional[int] = None, prefix: str = "agent/") -> Dict[str, Tensor]:
+    """the GT tensors the rollout overrides with (waymo_motion.py:434-466,523-548); `n_frame=11` gives test mode."""
+    keys = ("valid", "pos", "yaw_bbox", "spd", "vel", "acc", "yaw_rate")
+    if n_frame is None:
+        return {k: batch[prefix + k] for k in keys}
+    return {k: batch[prefix + k][:, :n_frame].contiguous() for k in keys}
+
+
+def raw_map_from_batch(batch: Mapping[str, Tensor]) -> Dict[str, Tensor]:
+    return {k: batch["map/" + k] for k in ("boundary", "valid", "type", "pos", "dir")}
