@@ -215,6 +215,17 @@ int32_t tb_rollout_init(const TbDims* dims, const TbRolloutIn* in, const float* 
 int32_t tb_rollout_steps(const TbDims* dims, const TbRolloutIn* in, const float* packed, void* state,
                          const TbRolloutOut* out, int32_t t_first, int32_t t_last, void* stream);
 
+/* The two halves of one decode step, separately launchable (tb_rollout_steps(t,t) == front(t); back(t)):
+ *   front: get_agent_attr_and_pe + agent_encoder + transformer_as2pl + transformer_as2tl (waymo_motion.py:140-155,
+ *          traffic_bots.py:205-219) and the K|V projection of the agent<->agent layers;
+ *   back:  agent_interaction, agent_temporal, add_goal, add_latent, action head, Dynamics.update/override_states,
+ *          TrafficRuleChecker.check, Dynamics.kill, disable_goal_reached, DifferentiableReward.get, buffer write
+ *          (traffic_bots.py:228-241, waymo_motion.py:171-203,311-343). */
+int32_t tb_step_front(const TbDims* dims, const TbRolloutIn* in, const float* packed, void* state, int32_t t,
+                      void* stream);
+int32_t tb_step_back(const TbDims* dims, const TbRolloutIn* in, const float* packed, void* state,
+                     const TbRolloutOut* out, int32_t t, void* stream);
+
 /* tb_rollout_init + tb_rollout_steps(1..n_step) == WaymoMotion.rollout (waymo_motion.py:205-354). */
 int32_t tb_rollout(const TbDims* dims, const TbRolloutIn* in, const float* packed, void* state,
                    const TbRolloutOut* out, void* stream);

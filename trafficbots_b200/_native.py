@@ -35,7 +35,7 @@ BLOCK_MAP_DENSETNT, BLOCK_MAP_SELF_ATTN, BLOCK_AS2PL, BLOCK_AS2TL, BLOCK_INTERAC
 EXPORTS = (
     "tb_weight_count", "tb_weight_name", "tb_weight_rows", "tb_weight_cols", "tb_packed_weight_bytes",
     "tb_pack_weights", "tb_encode_workspace_bytes", "tb_encode_scene", "tb_kv_project", "tb_xlayer",
-    "tb_rollout_state_bytes", "tb_rollout_state_offset", "tb_rollout_init", "tb_rollout_steps", "tb_rollout",
+    "tb_rollout_state_bytes", "tb_rollout_state_offset", "tb_rollout_init", "tb_rollout_steps", "tb_step_front", "tb_step_back", "tb_rollout",
     "tb_launch_count",
 )
 
@@ -141,6 +141,11 @@ def lib() -> C.CDLL:
     L.tb_rollout_steps.restype = C.c_int32
     L.tb_rollout_steps.argtypes = [C.POINTER(TbDims), C.POINTER(TbRolloutIn), C.c_void_p, C.c_void_p,
                                    C.POINTER(TbRolloutOut), C.c_int32, C.c_int32, C.c_void_p]
+    L.tb_step_front.restype = C.c_int32
+    L.tb_step_front.argtypes = [C.POINTER(TbDims), C.POINTER(TbRolloutIn), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.tb_step_back.restype = C.c_int32
+    L.tb_step_back.argtypes = [C.POINTER(TbDims), C.POINTER(TbRolloutIn), C.c_void_p, C.c_void_p,
+                               C.POINTER(TbRolloutOut), C.c_int32, C.c_void_p]
     L.tb_rollout.restype = C.c_int32
     L.tb_rollout.argtypes = [C.POINTER(TbDims), C.POINTER(TbRolloutIn), C.c_void_p, C.c_void_p,
                              C.POINTER(TbRolloutOut), C.c_void_p]

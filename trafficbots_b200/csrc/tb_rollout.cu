@@ -625,17 +625,22 @@ extern "C" int32_t tb_rollout_init(const TbDims* dims, const TbRolloutIn* in, co
   return launch_status();
 }
 
-extern "C" int32_t tb_rollout_steps(const TbDims* dims, const TbRolloutIn* in, const float* packed, void* state,
-                                    const TbRolloutOut* out, int32_t t_first, int32_t t_last, void* stream) {
+// which: 1 = front half only, 2 = back half only, 3 = both
+static int rollout_steps_impl(const TbDims* dims, const TbRolloutIn* in, const float* packed, void* state,
+                              const TbRolloutOut* out, int32_t t_first, int32_t t_last, void* stream, int which) {
   int rc = check_dims_host(dims);
   if (rc != TB_OK) return rc;
   rc = check_rollout_in(in);
   if (rc != TB_OK) return rc;
-  if (!packed || !state || !out) return TB_ERR_NULL;
-  if (!out->preds || !out->valid || !out->override_masks || !out->diffbar_rewards || !out->diffbar_rewards_valid ||
-      !out->action_log_probs || !out->latent_log_probs || !out->violations)
-    return TB_ERR_NULL;
-  if (!aligned16(packed) || !aligned16(out->preds) || (reinterpret_cast<uintptr_t>(state) & 255u)) return TB_ERR_ALIGN;
+  if (!packed || !state) return TB_ERR_NULL;
+  if (which & 2) {
+    if (!out) return TB_ERR_NULL;
+    if (!out->preds || !out->valid || !out->override_masks || !out->diffbar_rewards || !out->diffbar_rewards_valid ||
+        !out->action_log_probs || !out->latent_log_probs || !out->violations)
+      return TB_ERR_NULL;
+    if (!aligned16(out->preds)) return TB_ERR_ALIGN;
+  }
+  if (!aligned16(packed) || (reinterpret_cast<uintptr_t>(state) & 255u)) return TB_ERR_ALIGN;
   if (t_first < 1 || t_last > dims->n_step || t_first > t_last) return TB_ERR_BAD_SHAPE;
   constexpr int R = ROW_TILE;
   set_rollout_attrs<R>();
@@ -644,12 +649,29 @@ extern "C" int32_t tb_rollout_steps(const TbDims* dims, const TbRolloutIn* in, c
   dim3 grid((d.n_agent + R - 1) / R, d.n_scene * d.n_mode);
   cudaStream_t st = (cudaStream_t)stream;
   for (int t = t_first; t <= t_last; ++t) {
-    k_step_front<R><<<grid, NT, sizeof(TileSmem<R>), st>>>(d, *in, packed, sv, t);
-    k_step_back<R><<<grid, NT, sizeof(BackSmem<R>), st>>>(d, *in, packed, sv, *out, t);
-    count_launch();
-    count_launch();
+    if (which & 1) {
+      k_step_front<R><<<grid, NT, sizeof(TileSmem<R>), st>>>(d, *in, packed, sv, t);
+      count_launch();
+    }
+    if (which & 2) {
+      k_step_back<R><<<grid, NT, sizeof(BackSmem<R>), st>>>(d, *in, packed, sv, *out, t);
+      count_launch();
+    }
   }
   return launch_status();
+}
+
+extern "C" int32_t tb_rollout_steps(const TbDims* dims, const TbRolloutIn* in, const float* packed, void* state,
+                                    const TbRolloutOut* out, int32_t t_first, int32_t t_last, void* stream) {
+  return rollout_steps_impl(dims, in, packed, state, out, t_first, t_last, stream, 3);
+}
+extern "C" int32_t tb_step_front(const TbDims* dims, const TbRolloutIn* in, const float* packed, void* state, int32_t t,
+                                 void* stream) {
+  return rollout_steps_impl(dims, in, packed, state, nullptr, t, t, stream, 1);
+}
+extern "C" int32_t tb_step_back(const TbDims* dims, const TbRolloutIn* in, const float* packed, void* state,
+                                const TbRolloutOut* out, int32_t t, void* stream) {
+  return rollout_steps_impl(dims, in, packed, state, out, t, t, stream, 2);
 }
 
 extern "C" int32_t tb_rollout(const TbDims* dims, const TbRolloutIn* in, const float* packed, void* state,

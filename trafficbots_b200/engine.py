@@ -215,6 +215,33 @@ class Engine:
         self.last_t = n_step
         return self._finish(out)
 
+    def profile_rollout(self, *args, n_mode: int = 1, n_step: int = 90, out=None, **kw):
+        """Instrumented replay of `rollout` with the two halves of every step launched separately and bracketed by CUDA
+        events on the launching stream; returns (avg front-half ms, avg back-half ms).  Measurement aid for bench.py."""
+        dims, rin = self._rollout_structs(*args, n_mode, n_step, **kw)
+        B, A = dims.n_scene * dims.n_mode, dims.n_agent
+        if out is None:
+            out = self.alloc_outputs(B, A, n_step)
+        state = self._ensure_state(dims)
+        rout = self._out_struct(out)
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_step)]
+        with torch.cuda.device(self.device):
+            st = nt.current_stream_ptr()
+            nt.check(self.lib.tb_rollout_init(C.byref(dims), C.byref(rin), self.packed.data_ptr(), state.data_ptr(), st), "init")
+            for t in range(1, n_step + 1):
+                e = ev[t - 1]
+                e[0].record()
+                nt.check(self.lib.tb_step_front(C.byref(dims), C.byref(rin), self.packed.data_ptr(), state.data_ptr(), t, st), "front")
+                e[1].record()
+                nt.check(self.lib.tb_step_back(C.byref(dims), C.byref(rin), self.packed.data_ptr(), state.data_ptr(),
+                                               C.byref(rout), t, st), "back")
+                e[2].record()
+            torch.cuda.current_stream().synchronize()
+        self.last_t = n_step
+        front = sum(e[0].elapsed_time(e[1]) for e in ev) / n_step
+        back = sum(e[1].elapsed_time(e[2]) for e in ev) / n_step
+        return front, back
+
     def _finish(self, out: Dict[str, Tensor]) -> Dict[str, Tensor]:
         res = {k: v for k, v in out.items() if not k.startswith("_")}
         for i, k in enumerate(VIOLATION_KEYS):
