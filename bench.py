@@ -131,12 +131,22 @@ USED_KEYS = ("map/valid", "map/type", "map/pos", "map/dir", "map/boundary", "age
 
 
 def run_step(eng, cb, ex, n_mode, n_step, out=None):
+    """device-resident step through the thin C-ABI driver"""
     from trafficbots_b200 import engine as E, host
     feat = eng.encode_scene(cb)
     gt = E.gt_from_batch(cb)
     tf = host.teacher_forcing_mask(gt["valid"], 10, 10)
     return eng.rollout(feat, gt, tf, cb["agent/type"], cb["agent/size"], E.raw_map_from_batch(cb), ex["latent_sample"],
                        ex["latent_logp"], ex["dest"], ex["goal_valid"], cb["agent/goal"], n_mode=n_mode, n_step=n_step, out=out)
+
+
+def run_step_public(module, cb, ex):
+    """the call a user of the reference makes (validation_step's hot path): encode_input_features + reactive_replay-style
+    rollout through the `WaymoMotion` surface; returns the RolloutBuffer."""
+    feat = module.model.encode_input_features(cb)
+    tf = module.teacher_forcing_joint_future_pred.get(cb["agent/valid"], 0)
+    return module.reactive_replay(cb, feat, tf, ex["latent_sample"], ex["dest"], ex["goal_valid"], deterministic_latent=True,
+                                  deterministic_action=True, require_vis_dict=False)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -219,8 +229,6 @@ def run_ours(args):
     out = eng.alloc_outputs(S * K, A, T)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     h2d = sum(v.numel() * v.element_size() for v in host_batch.values()) + sum(v.numel() * v.element_size() for v in host_ex.values())
-    host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
-    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
 
     def barrier():
         if world > 1:
@@ -246,13 +254,30 @@ def run_ours(args):
     ms = sum(a.elapsed_time(b) for a, b in ev)
 
     # ---- end to end: pinned host buffers in, results back to the host, through the same public call ---------
+    from trafficbots_b200 import config as tb_config, parallel
+    from trafficbots_b200.pl_modules.waymo_motion import WaymoMotion
+    module = WaymoMotion(**tb_config.default_config(n_joint_future=K))
+    module.load_state_dict(sd)
+    module = module.to(dev).eval()
+    host_res = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items() if not k.startswith("_")}
+    host_res["violations"] = torch.empty(6, S * K, A, T, dtype=torch.bool).pin_memory()
+    d2h = sum(v.numel() * v.element_size() for v in host_res.values())
+
     def e2e_step():
         cbe = host.batch_to_device(host_batch, dev)
         cexe = host.batch_to_device(host_ex, dev)
-        o = run_step(eng, cbe, cexe, K, T, out)
-        for k2, v in host_out.items():
-            v.copy_(out[k2], non_blocking=True)
-        return o
+        buf = run_step_public(module, cbe, cexe)
+        for name in ("preds", "valid", "override_masks", "diffbar_rewards", "diffbar_rewards_valid", "action_log_probs",
+                     "latent_log_probs"):
+            host_res[name].copy_(getattr(buf, name), non_blocking=True)
+        for i, name in enumerate(E.VIOLATION_KEYS):
+            host_res["violations"][i].copy_(buf.violations[name], non_blocking=True)
+        if world > 1:  # the metrics reduction: one packed all-gather per step
+            fr = lambda x: x.unsqueeze(2)  # noqa: E731  K = 1
+            local = parallel.pack_scene_metrics(fr(buf.preds), fr(buf.valid), {k2: fr(v) for k2, v in buf.violations.items()},
+                                                fr(buf.diffbar_rewards), cbe["agent/pos"], cbe["agent/valid"])
+            parallel.all_gather_scenes(local, world * S)
+        return buf
     for _ in range(2):
         e2e_step()
     barrier()

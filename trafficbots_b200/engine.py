@@ -215,6 +215,26 @@ class Engine:
         self.last_t = n_step
         return self._finish(out)
 
+    def begin_rollout(self, *args, n_mode: int = 1, n_step: int = 90, **kw) -> Dict:
+        """`tb_rollout_init` only; the steps are then driven one by one with `step(ctx)` (per-step `forward` use)."""
+        dims, rin = self._rollout_structs(*args, n_mode, n_step, **kw)
+        out = self.alloc_outputs(dims.n_scene * dims.n_mode, dims.n_agent, n_step)
+        state = self._ensure_state(dims)
+        with torch.cuda.device(self.device):
+            nt.check(self.lib.tb_rollout_init(C.byref(dims), C.byref(rin), self.packed.data_ptr(), state.data_ptr(),
+                                              nt.current_stream_ptr()), "tb_rollout_init")
+        self.last_t = 0
+        return {"dims": dims, "rin": rin, "out": out, "rout": self._out_struct(out), "keep": (args, kw), "n_step": n_step}
+
+    def step(self, ctx: Dict) -> int:
+        t = self.last_t + 1
+        with torch.cuda.device(self.device):
+            nt.check(self.lib.tb_rollout_steps(C.byref(ctx["dims"]), C.byref(ctx["rin"]), self.packed.data_ptr(),
+                                               self._state.data_ptr(), C.byref(ctx["rout"]), t, t, nt.current_stream_ptr()),
+                     "tb_rollout_steps")
+        self.last_t = t
+        return t
+
     def profile_rollout(self, *args, n_mode: int = 1, n_step: int = 90, out=None, **kw):
         """Instrumented replay of `rollout` with the two halves of every step launched separately and bracketed by CUDA
         events on the launching stream; returns (avg front-half ms, avg back-half ms).  Measurement aid for bench.py."""

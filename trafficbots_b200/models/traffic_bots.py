@@ -1,0 +1,94 @@
+"""`TrafficBots` -- mirror of the reference world model's interface (`src/models/traffic_bots.py:19-247`) on top of the
+CUDA library.  Parameters are registered under the reference's `state_dict` keys (`model.*`), so a reference
+checkpoint loads with `load_state_dict` unchanged; they are re-laid into the kernel layout lazily
+(`tb_pack_weights`) whenever they change.  The per-step `forward` of the reference is fused into the rollout kernels
+(`tb_step_front` / `tb_step_back`); what remains here is what the outer loop calls directly:
+`encode_input_features`, `init`, the `hidden` / `latent_sample` attributes and `goal_manager` / `latent_encoder` handles.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Dict, Mapping, Optional, Union
+
+import torch
+from torch import Tensor, nn
+
+from .. import _native as nt
+from .. import config as tb_config
+from .. import weights
+from ..engine import Engine, SceneFeatures
+from .distributions import DiagGaussian
+
+
+def register_param_tree(root: nn.Module, spec: Mapping[str, tuple], prefix: str, buffers: bool = False) -> None:
+    """creates nested container modules so that `root.state_dict()` has exactly the keys of `spec` below `prefix`."""
+    for key, shape in spec.items():
+        if not key.startswith(prefix):
+            continue
+        parts = key[len(prefix):].split(".")
+        mod = root
+        for p in parts[:-1]:
+            if not hasattr(mod, p):
+                mod.add_module(p, nn.Module())
+            mod = getattr(mod, p)
+        t = torch.zeros(shape)
+        if buffers:
+            mod.register_buffer(parts[-1], t)
+        else:
+            mod.register_parameter(parts[-1], nn.Parameter(t, requires_grad=False))
+
+
+class TrafficBots(nn.Module):
+    def __init__(self, hidden_dim: int = 128, **cfg) -> None:
+        super().__init__()
+        tb_config.check_supported({"hidden_dim": hidden_dim, "model": dict(cfg, hidden_dim=hidden_dim)})
+        self.hidden_dim = hidden_dim
+        spec = weights.state_dict_spec()
+        register_param_tree(self, {k: v for k, v in spec.items() if weights._alias_of(k) is None}, "model.")
+        # shared modules: the latent encoder re-exports the policy's cross-attention blocks (latent_encoder.py:39-41)
+        self.latent_encoder.add_module("transformer_as2pl", self.transformer_as2pl)
+        self.latent_encoder.add_module("transformer_as2tl", self.transformer_as2tl)
+        gm = cfg.get("goal_manager", {}) or {}
+        self.goal_manager.dummy = False
+        self.goal_manager.update_goal = False
+        self.goal_manager.goal_attr_mode = gm.get("goal_attr_mode", "dest")
+        self.latent_sample: Optional[Tensor] = None
+        self.latent_logp: Optional[Tensor] = None
+        self.__dict__["_owner"] = None  # weak handle on the WaymoMotion shell that holds the Engine (not a submodule)
+
+    # the Engine (packed parameters + device buffers) lives on the LightningModule shell
+    def _engine(self) -> Engine:
+        owner = self.__dict__["_owner"]() if self.__dict__["_owner"] is not None else None
+        if owner is None:
+            raise nt.TbError("TrafficBots must be owned by a trafficbots_b200 WaymoMotion module")
+        return owner.engine()
+
+    def set_owner(self, owner) -> None:
+        import weakref
+        self.__dict__["_owner"] = weakref.ref(owner)
+
+    def encode_input_features(self, batch: Mapping[str, Tensor] = None, prefix: str = "history/", **kw) -> SceneFeatures:
+        """SceneCentricInput + encode_input_features (sc_input.py:98-140, traffic_bots.py:109-151) fused: consumes the
+        RAW scene tensors (`map/*`, `{prefix}agent/*`, `{prefix}tl_stop/*`); positional encodings are computed inside the
+        kernels instead of being materialised (`input/map_pe` alone is 252 MB at 32 scenes in the reference).
+        Returns the reference's feature dict (+ private K|V caches)."""
+        if batch is None:
+            batch = kw
+        return self._engine().encode_scene(batch, prefix)
+
+    def init(self, latent: Union[DiagGaussian, Tensor], deterministic: Union[bool, Tensor]) -> None:
+        """traffic_bots.py:153-161,196-199 -- the latent is sampled once per rollout; GRU hidden restarts at zero."""
+        if isinstance(latent, Tensor):
+            self.latent_sample = latent
+            self.latent_logp = torch.zeros(latent.shape[:-1], device=latent.device)
+        else:
+            self.latent_sample = latent.sample(deterministic).contiguous()
+            self.latent_logp = latent.log_prob(self.latent_sample).contiguous()
+
+    @property
+    def hidden(self) -> Optional[Tensor]:
+        eng = self._engine()
+        return None if eng._state is None else eng.state_field(nt.STATE_HIDDEN)
+
+    def forward(self, *a, **kw):
+        raise nt.TbError("TrafficBots.forward is fused into the rollout kernels: call WaymoMotion.forward / rollout")

@@ -1,0 +1,227 @@
+"""`WaymoMotion` -- drop-in shell with the constructor kwargs, method names and return types of the reference's
+LightningModule (`src/pl_modules/waymo_motion.py:27-572`) for the hot path: `forward` (one decode step), `rollout`,
+`reactive_replay`, `joint_future_pred`, plus `encode` helpers.  Select it with
+`model._target_=trafficbots_b200.pl_modules.waymo_motion.WaymoMotion` (`configs/model/traffic_bots_b200.yaml`).
+
+All model arithmetic runs in `libtrafficbots_b200.so` (see `include/trafficbots_b200.h`); this file is tensor plumbing.
+Differences to the reference, all deliberate and documented in DESIGN.md:
+  * scene-level tensors are NOT `repeat_interleave`d per joint future; the kernels index scene = scene_mode // K.
+  * `rollout()` runs all steps inside the library; the traffic-rule checks, kill, goal disabling and the imitation
+    reward are part of the fused step, so the `rule_checker` argument only carries the raw tensors they need.
+  * `require_vis_dict=True` / `need_weights` (attention maps for videos) are not provided by the fused path and raise.
+If pytorch_lightning is importable the class derives from `LightningModule`, otherwise from `nn.Module`.
+"""
+from __future__ import annotations
+
+from typing import Dict, Mapping, Optional, Tuple, Union
+
+import torch
+from torch import Tensor, nn
+
+from .. import _native as nt
+from .. import config as tb_config
+from .. import host, weights
+from ..engine import Engine, gt_from_batch, raw_map_from_batch
+from ..models.distributions import DestCategorical, DiagGaussian
+from ..models.traffic_bots import TrafficBots, register_param_tree
+from ..utils.buffer import RolloutBuffer
+
+try:  # pragma: no cover - Lightning is optional in this image
+    from pytorch_lightning import LightningModule as _Base
+except Exception:  # noqa: BLE001
+    _Base = nn.Module
+
+
+class TeacherForcing:
+    """utils/teacher_forcing.py:9-74 without the (default-off) schedules."""
+
+    def __init__(self, step_spawn_agent: int = 10, step_warm_start: int = 10, step_horizon: int = 0,
+                 step_horizon_decrease_per_epoch: int = 0, prob_forcing_agent: float = 0,
+                 prob_forcing_agent_decrease_per_epoch: float = 0) -> None:
+        if step_horizon or prob_forcing_agent:
+            raise tb_config.UnsupportedConfig("teacher-forcing schedules (step_horizon / prob_forcing_agent) are not supported")
+        self.step_spawn_agent, self.step_warm_start = step_spawn_agent, step_warm_start
+
+    def get(self, as_valid: Tensor, current_epoch: int = 0) -> Tensor:
+        return host.teacher_forcing_mask(as_valid, self.step_spawn_agent, self.step_warm_start)
+
+
+class TrafficRuleChecker:
+    """Carrier of the raw tensors the fused rule checks read (constructor signature of
+    utils/traffic_rule_checker.py:16-44; the checks themselves run inside `tb_step_back`)."""
+
+    def __init__(self, map_boundary, map_valid, map_type, map_pos, map_dir, tl_valid=None, tl_pos=None, tl_state=None,
+                 agent_type=None, agent_size=None, agent_goal=None, agent_dest=None, enable_check_collided=False,
+                 enable_check_run_road_edge=False, enable_check_run_red_light=False, enable_check_passive=False) -> None:
+        if enable_check_collided or enable_check_run_road_edge or enable_check_run_red_light or enable_check_passive:
+            raise tb_config.UnsupportedConfig("optional traffic-rule checks are not implemented in the fused step (SURVEY 8f-2)")
+        self.raw_map = {"boundary": map_boundary, "valid": map_valid, "type": map_type, "pos": map_pos, "dir": map_dir}
+        self.agent_goal, self.agent_dest = agent_goal, agent_dest
+
+
+class WaymoMotion(_Base):
+    def __init__(self, time_step_current: int = 10, time_step_gt: int = 90, time_step_end: int = 90,
+                 time_step_sim_start: int = 1, hidden_dim: int = 128, data_size: Optional[Mapping] = None,
+                 pre_processing: Optional[Mapping] = None, step_detach_hidden: int = -1, model: Optional[Mapping] = None,
+                 p_training_rollout_prior: float = 0.1, detach_state_policy: bool = True,
+                 training_deterministic_action: bool = True, differentiable_reward: Optional[Mapping] = None,
+                 p_drop_hidden: float = -1.0, n_video_batch: int = 3, n_joint_future: int = 6,
+                 waymo_post_processing: Optional[Mapping] = None, dynamics: Optional[Mapping] = None,
+                 action_head: Optional[Mapping] = None, teacher_forcing_training: Optional[Mapping] = None,
+                 teacher_forcing_reactive_replay: Optional[Mapping] = None,
+                 teacher_forcing_joint_future_pred: Optional[Mapping] = None, training_metrics: Optional[Mapping] = None,
+                 traffic_rule_checker: Optional[Mapping] = None, optimizer: Optional[Mapping] = None,
+                 lr_scheduler: Optional[Mapping] = None, lr_goal: float = 3e-4,
+                 sub_womd_reactive_replay: Optional[Mapping] = None, sub_womd_joint_future_pred: Optional[Mapping] = None,
+                 interactive_challenge: bool = False, wb_artifact: Optional[str] = None) -> None:
+        super().__init__()
+        cfg = dict(hidden_dim=hidden_dim, time_step_sim_start=time_step_sim_start, pre_processing=pre_processing or {},
+                   model=model or {}, differentiable_reward=differentiable_reward or {}, dynamics=dynamics or {},
+                   action_head=action_head or {}, traffic_rule_checker=traffic_rule_checker or {})
+        tb_config.check_supported(cfg)
+        if not detach_state_policy:
+            raise tb_config.UnsupportedConfig("detach_state_policy=False")
+        self.tb_hparams = dict(time_step_current=time_step_current, time_step_gt=time_step_gt, time_step_end=time_step_end,
+                               time_step_sim_start=time_step_sim_start, n_joint_future=n_joint_future,
+                               traffic_rule_checker=dict(traffic_rule_checker or {}))
+        spec = weights.state_dict_spec()
+        self.pre_processing = nn.Module()
+        register_param_tree(self.pre_processing, spec, "pre_processing.", buffers=True)
+        for pp in ("input", "latent"):
+            m = getattr(self.pre_processing, pp)
+            m.pl_node_ohe.copy_(torch.eye(weights.N_PL_NODE))
+            for who in ("agent", "map", "tl"):
+                pe = getattr(m, f"pose_pe_{who}")
+                pe.pe_xy.freqs.copy_(weights.pe_freqs_xy())
+                pe.pe_yaw.freqs.copy_(weights.pe_freqs_yaw())
+        mcfg = {k: v for k, v in dict(model or {}).items() if k not in ("_target_", "hidden_dim")}
+        self.model = TrafficBots(hidden_dim=hidden_dim, **mcfg)
+        self.model.set_owner(self)
+        self.action_head = nn.Module()
+        register_param_tree(self.action_head, spec, "action_head.")
+        self.teacher_forcing_training = TeacherForcing(**(teacher_forcing_training or {}))
+        self.teacher_forcing_reactive_replay = TeacherForcing(**(teacher_forcing_reactive_replay or {"step_spawn_agent": 90}))
+        self.teacher_forcing_joint_future_pred = TeacherForcing(**(teacher_forcing_joint_future_pred or {}))
+        self._eng: Optional[Engine] = None
+        self._packed_version = None
+        self._step_ctx = None
+
+    # ------------------------------------------------------------------------------------------------ engine / parameters
+    def _param_version(self):
+        return tuple((p.data_ptr(), p._version) for p in self.state_dict(keep_vars=True).values())
+
+    def engine(self) -> Engine:
+        """the CUDA engine with the CURRENT parameters packed (re-packs after load_state_dict / optimizer steps / .to())."""
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise nt.TbError("trafficbots_b200.WaymoMotion must live on a CUDA device (no CPU implementation of the hot path)")
+        ver = self._param_version()
+        if self._eng is None or self._eng.device != dev:
+            self._eng = Engine(self.state_dict(), dev)
+            self._packed_version = ver
+        elif ver != self._packed_version:
+            self._eng.load_state_dict(self.state_dict())
+            self._packed_version = ver
+        return self._eng
+
+    # ------------------------------------------------------------------------------------------------ encoding
+    def encode(self, batch: Mapping[str, Tensor]):
+        """`pre_processing` + `model.encode_input_features` of validation_step / test_step (waymo_motion.py:576-583)."""
+        return self.model.encode_input_features(batch)
+
+    # ------------------------------------------------------------------------------------------------ rollout
+    def rollout(self, features: Mapping[str, Tensor], latent: Union[DiagGaussian, Tensor], goal: Tensor, goal_valid: Tensor,
+                mask_teacher_forcing: Tensor, rule_checker: TrafficRuleChecker,
+                deterministic_latent: Union[bool, Tensor], deterministic_action: bool, step_end: int, step_start: int,
+                require_vis_dict: bool = False, gt_sdc=None) -> RolloutBuffer:
+        """waymo_motion.py:205-354.  `features`: the reference's keys (`map_valid`, `map_feature`, `tl_valid`, `tl_feature`,
+        `agent_valid`, `agent_state`, `agent_type`, `agent_size`, `vel`, `acc`, `yaw_rate`) with leading dim n_scene, plus
+        the K|V caches of `encode` (`_kv_map`, `_kv_tl`) and optionally `_n_mode` (joint futures per scene);
+        `goal` [n_scene*n_mode, n_agent] int64 destination index; latent / goal_valid per scene-mode."""
+        if require_vis_dict or gt_sdc is not None or not deterministic_action:
+            raise tb_config.UnsupportedConfig("require_vis_dict / gt_sdc / stochastic actions are not supported by the fused rollout")
+        if step_start != 1:
+            raise tb_config.UnsupportedConfig("step_start must be 1")
+        n_mode = int(features.get("_n_mode", 1))
+        self.model.init(latent, deterministic_latent)
+        eng = self.engine()
+        if "_gt" in features:  # un-concatenated GT tensors straight from the batch (no copies)
+            gt = features["_gt"]
+        else:
+            st = features["agent_state"]
+            gt = {"valid": features["agent_valid"], "pos": st[..., :2].contiguous(), "yaw_bbox": st[..., 2:3].contiguous(),
+                  "spd": st[..., 3:4].contiguous(), "vel": features["vel"], "acc": features["acc"], "yaw_rate": features["yaw_rate"]}
+        feat = {"map_feature": features["map_feature"], "map_feature_valid": features["map_valid"],
+                "tl_feature_valid": features["tl_valid"], "_kv_map": features["_kv_map"], "_kv_tl": features["_kv_tl"]}
+        args = (feat, gt, mask_teacher_forcing, features["agent_type"], features["agent_size"], rule_checker.raw_map,
+                self.model.latent_sample, self.model.latent_logp, goal.contiguous(), goal_valid.contiguous(), rule_checker.agent_goal)
+        if features.get("_stepwise", False):  # caller drives the steps through forward()
+            self._step_ctx = eng.begin_rollout(*args, n_mode=n_mode, n_step=step_end)
+            return None
+        out = eng.rollout(*args, n_mode=n_mode, n_step=step_end)
+        return RolloutBuffer(step_start, step_end, self.tb_hparams["time_step_current"], out)
+
+    def forward(self, *args, **kwargs):
+        """One decode step (waymo_motion.py:108-203) of the rollout opened with `rollout(features | {"_stepwise": True}, ...)`.
+        The reference passes the step's map / traffic-light features, goal feature and state overrides as arguments; in the
+        fused path they are bound when the rollout is opened (K|V caches, GT tensors and the teacher-forcing mask), so the
+        arguments are accepted for signature compatibility and ignored.  Returns (state [B,A,4], valid [B,A], train_dict,
+        vis_dict) like the reference; `train_dict` holds this step's pre-override prediction."""
+        if self._step_ctx is None:
+            raise nt.TbError("forward(): open a rollout first (features['_stepwise'] = True)")
+        eng = self.engine()
+        t = eng.step(self._step_ctx)
+        o = self._step_ctx["out"]
+        train = {"pred_state": o["preds"][:, :, t - 1], "pred_valid": o["valid"][:, :, t - 1],
+                 "latent_logp": o["latent_log_probs"][:, :, t - 1], "action_logp": o["action_log_probs"][:, :, t - 1]}
+        return eng.state_field(nt.STATE_AGENT_STATE), eng.state_field(nt.STATE_VALID), train, {}
+
+    def finish_rollout(self) -> RolloutBuffer:
+        ctx, self._step_ctx = self._step_ctx, None
+        eng = self.engine()
+        return RolloutBuffer(1, ctx["n_step"], self.tb_hparams["time_step_current"], eng._finish(ctx["out"]))
+
+    def _features(self, batch: Mapping[str, Tensor], f: Mapping[str, Tensor], n_mode: int, n_gt: Optional[int] = None) -> Dict:
+        gt = gt_from_batch(batch, n_gt)
+        return {"map_valid": f["map_feature_valid"], "map_feature": f["map_feature"], "tl_valid": f["tl_feature_valid"],
+                "tl_feature": f["tl_feature"], "agent_type": batch["history/agent/type"], "agent_size": batch["history/agent/size"],
+                "agent_valid": gt["valid"], "vel": gt["vel"], "acc": gt["acc"], "yaw_rate": gt["yaw_rate"], "agent_state": None,
+                "_gt": gt, "_kv_map": f["_kv_map"], "_kv_tl": f["_kv_tl"], "_n_mode": n_mode}
+
+    def reactive_replay(self, batch: Mapping[str, Tensor], input_feature_dict: Mapping[str, Tensor], mask_teacher_forcing: Tensor,
+                        latent, goal: Optional[Tensor], goal_valid: Optional[Tensor], deterministic_latent: bool,
+                        deterministic_action: bool, require_vis_dict: bool = False) -> RolloutBuffer:
+        """waymo_motion.py:420-476: one rollout per scene with GT destination, spawning over the whole episode."""
+        rc = TrafficRuleChecker(batch["map/boundary"], batch["map/valid"], batch["map/type"], batch["map/pos"], batch["map/dir"],
+                                agent_goal=batch.get("agent/goal"), agent_dest=batch.get("agent/dest"),
+                                **self.tb_hparams["traffic_rule_checker"])
+        feats = self._features(batch, input_feature_dict, 1)
+        return self.rollout(feats, latent=latent, goal=goal, goal_valid=goal_valid, mask_teacher_forcing=mask_teacher_forcing,
+                            rule_checker=rc, step_start=self.tb_hparams["time_step_sim_start"],
+                            step_end=self.tb_hparams["time_step_end"], deterministic_latent=deterministic_latent,
+                            deterministic_action=deterministic_action, require_vis_dict=require_vis_dict)
+
+    def joint_future_pred(self, batch: Mapping[str, Tensor], input_feature_dict: Mapping[str, Tensor], latent: DiagGaussian,
+                          goal: DestCategorical, goal_valid: Tensor, require_vis_dict: bool = False
+                          ) -> Tuple[RolloutBuffer, Tensor, Tensor]:
+        """waymo_motion.py:478-572: K joint futures per scene; mode 0 is deterministic (prior mean, arg-max destination).
+        Test mode (only the 11 history frames as GT, no goal check) is selected like in the reference's `test_step` by
+        a batch whose `agent/valid` has 11 frames (waymo_motion.py:923-924)."""
+        K = self.tb_hparams["n_joint_future"]
+        S, A = batch["history/agent/valid"].shape[0], batch["history/agent/valid"].shape[2]
+        det = torch.zeros(S * K, A, dtype=torch.bool, device=goal_valid.device)
+        det[::K] = True
+        latent.repeat_interleave_(K, 0)
+        goal.repeat_interleave_(K, 0)
+        goal_sample = goal.sample(det)
+        goal_log_probs = goal.log_prob(goal_sample)
+        gvalid = goal_valid.repeat_interleave(K, 0)
+        rc = TrafficRuleChecker(batch["map/boundary"], batch["map/valid"], batch["map/type"], batch["map/pos"], batch["map/dir"],
+                                agent_goal=batch.get("agent/goal"), agent_dest=goal_sample, **self.tb_hparams["traffic_rule_checker"])
+        feats = self._features(batch, input_feature_dict, K)
+        tf = self.teacher_forcing_joint_future_pred.get(feats["agent_valid"], 0)
+        buf = self.rollout(feats, latent=latent, goal=goal_sample, goal_valid=gvalid, mask_teacher_forcing=tf, rule_checker=rc,
+                           step_start=self.tb_hparams["time_step_sim_start"], step_end=self.tb_hparams["time_step_end"],
+                           deterministic_latent=det, deterministic_action=True, require_vis_dict=require_vis_dict)
+        buf.flatten_repeat(K)
+        return buf, goal_sample.view(S, K, A).transpose(1, 2), goal_log_probs.view(S, K, A).transpose(1, 2)
