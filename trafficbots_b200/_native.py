@@ -36,7 +36,7 @@ EXPORTS = (
     "tb_weight_count", "tb_weight_name", "tb_weight_rows", "tb_weight_cols", "tb_packed_weight_bytes",
     "tb_pack_weights", "tb_encode_workspace_bytes", "tb_encode_scene", "tb_kv_project", "tb_xlayer",
     "tb_rollout_state_bytes", "tb_rollout_state_offset", "tb_rollout_init", "tb_rollout_steps", "tb_step_front", "tb_step_back", "tb_rollout",
-    "tb_launch_count",
+    "tb_launch_count", "tb_tc_block_count", "tb_tc_first_block", "tb_tc_selftest",
 )
 
 
@@ -150,6 +150,11 @@ def lib() -> C.CDLL:
     L.tb_rollout.argtypes = [C.POINTER(TbDims), C.POINTER(TbRolloutIn), C.c_void_p, C.c_void_p,
                              C.POINTER(TbRolloutOut), C.c_void_p]
     L.tb_launch_count.restype = C.c_int64
+    L.tb_tc_block_count.restype = C.c_int32
+    L.tb_tc_first_block.restype = C.c_int32
+    L.tb_tc_first_block.argtypes = [C.c_int32]
+    L.tb_tc_selftest.restype = C.c_int32
+    L.tb_tc_selftest.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 

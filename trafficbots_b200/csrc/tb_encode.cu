@@ -22,6 +22,25 @@ __global__ void k_pack_weight(const float* __restrict__ src, float* __restrict__
   dst[i] = k < cols ? src[(size_t)n * cols + k] : 0.f;
 }
 
+// tensor-core copy of W[N,K] (N, K multiples of 128): 128x128 blocks, each [hi kb0 | hi kb1 | lo kb0 | lo kb1] x 16 KB,
+// rows = output features (the UMMA B operand is N x K, K-major), 128-byte swizzle (tb_tc.cuh)
+__global__ void k_pack_weight_tc(const float* __restrict__ src, unsigned char* __restrict__ dst, int rows, int cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk (8 bf16) of either the hi or the lo plane
+  const int chunks_per_plane = rows * cols / 8;
+  if (i >= 2 * chunks_per_plane) return;
+  const int plane = i / chunks_per_plane, j = i % chunks_per_plane;
+  const int n = j / (cols / 8), k8 = j % (cols / 8);  // row n, elements k8*8 .. +7
+  const int nb = n >> 7, r = n & 127, kblk128 = (k8 * 8) >> 7, kin = (k8 * 8) & 127;
+  const int kb = kin >> 6, c16 = (kin & 63) >> 3;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = src[(size_t)n * cols + k8 * 8 + e];
+  uint4 hi, lo;
+  tc::split8(v, hi, lo);
+  unsigned char* blk = dst + (size_t)(nb * (cols >> 7) + kblk128) * tc::BLOCK_BYTES;
+  *reinterpret_cast<uint4*>(blk + plane * 2 * tc::KB_BYTES_128 + kb * tc::KB_BYTES_128 + tc::sw128_off(r, c16)) = plane ? lo : hi;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // InputPeEncoder on a row tile (input_pe_encoder.py:41-61, pe_mode "cat"): x[r] = valid ? [MLP(attr) | PE] : 0.
 // Expects attr (zero padded to 4*K4) in sm.t rows, pose in pose[r] = (x, y, yaw), validity in sm.row_valid.
@@ -336,7 +355,13 @@ extern "C" int32_t tb_weight_count(void) { return TB_N_WEIGHTS; }
 extern "C" const char* tb_weight_name(int32_t i) { return (i >= 0 && i < TB_N_WEIGHTS) ? TB_WEIGHT_TABLE[i].name : nullptr; }
 extern "C" int32_t tb_weight_rows(int32_t i) { return (i >= 0 && i < TB_N_WEIGHTS) ? TB_WEIGHT_TABLE[i].rows : -1; }
 extern "C" int32_t tb_weight_cols(int32_t i) { return (i >= 0 && i < TB_N_WEIGHTS) ? TB_WEIGHT_TABLE[i].cols : -1; }
-extern "C" size_t tb_packed_weight_bytes(void) { return (size_t)TB_PACKED_FLOATS * sizeof(float); }
+extern "C" int32_t tb_tc_block_count(void) { return TB_N_TC_BLOCKS; }
+extern "C" int32_t tb_tc_first_block(int32_t i) {
+  for (int j = 0; j < TB_N_TC_WEIGHTS; ++j)
+    if (TB_TC_TABLE[j].weight == i) return TB_TC_TABLE[j].first_block;
+  return -1;
+}
+extern "C" size_t tb_packed_weight_bytes(void) { return tc_blob_offset_bytes() + (size_t)TB_N_TC_BLOCKS * tc::BLOCK_BYTES; }
 
 extern "C" int32_t tb_pack_weights(const float* const* params, float* packed, void* stream_) {
   if (!params || !packed) return TB_ERR_NULL;
@@ -347,6 +372,15 @@ extern "C" int32_t tb_pack_weights(const float* const* params, float* packed, vo
     if (!params[i]) return TB_ERR_NULL;
     const int n = d.cols == 0 ? (d.rows + 3) / 4 * 4 : (d.cols + 3) / 4 * d.rows * 4;
     k_pack_weight<<<(n + 255) / 256, 256, 0, st>>>(params[i], packed + d.offset, d.rows, d.cols);
+    count_launch();
+  }
+  // tensor-core copies: bf16 hi / lo blocks in the swizzled UMMA layout
+  unsigned char* tcb = reinterpret_cast<unsigned char*>(packed) + tc_blob_offset_bytes();
+  for (int j = 0; j < TB_N_TC_WEIGHTS; ++j) {
+    const TbWeightDesc& d = TB_WEIGHT_TABLE[TB_TC_TABLE[j].weight];
+    const int chunks = d.rows * d.cols / 8 * 2;  // 16-byte chunks, hi and lo
+    k_pack_weight_tc<<<(chunks + 255) / 256, 256, 0, st>>>(params[TB_TC_TABLE[j].weight],
+                                                             tcb + (size_t)TB_TC_TABLE[j].first_block * tc::BLOCK_BYTES, d.rows, d.cols);
     count_launch();
   }
   return launch_status();

@@ -6,6 +6,7 @@
 
 #include "../../include/trafficbots_b200.h"
 #include "tb_device.cuh"
+#include "tb_tc.cuh"
 
 namespace tb {
 
@@ -18,5 +19,9 @@ inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed);
 inline int launch_status() { return cudaGetLastError() == cudaSuccess ? TB_OK : TB_ERR_LAUNCH; }
 
 int check_dims_host(const TbDims* d);
+
+// the packed parameter buffer = [fp32 blob | pad to 1 KB | tensor-core blocks]
+inline size_t tc_blob_offset_bytes() { return ((size_t)TB_PACKED_FLOATS * sizeof(float) + 1023) & ~(size_t)1023; }
+inline const unsigned char* tc_blob(const float* packed) { return reinterpret_cast<const unsigned char*>(packed) + tc_blob_offset_bytes(); }
 
 }  // namespace tb
