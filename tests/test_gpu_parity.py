@@ -49,7 +49,7 @@ def test_pack_weights_layout():
             ref[: w.numel()] = w
         assert torch.equal(packed[off: off + ref.numel()], ref), name
         off += ref.numel()
-    assert off == packed.numel()
+    assert off <= packed.numel()  # the tensor-core blocks follow the fp32 blob (checked by tests/test_gpu_tc.py)
 
 
 @pytest.mark.parametrize("block,prefix", [(2, "model.transformer_as2pl"), (4, "model.agent_interaction.transformer"),

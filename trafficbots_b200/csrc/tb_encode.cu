@@ -2,6 +2,7 @@
 // stand-alone cross-attention layer.  See include/trafficbots_b200.h for the reference methods each replaces.
 #define TB_WEIGHT_TABLE_IMPL
 #include "tb_host.h"
+#include <stdlib.h>
 
 namespace tb {
 
@@ -399,7 +400,8 @@ int tb::check_dims_host(const TbDims* d) { return check_dims(d); }
 extern "C" size_t tb_encode_workspace_bytes(const TbDims* d) {
   if (check_dims(d) != TB_OK) return 0;
   const size_t rows = (size_t)d->n_scene * d->n_pl;
-  return rows * D * sizeof(float) + rows * 256 * sizeof(float);  // pooled polyline features + self-attention K|V
+  // pooled polyline features + self-attention K|V + per-CTA scratch of the tensor-core polyline encoder
+  return rows * D * sizeof(float) + rows * 256 * sizeof(float) + map_tc_scratch_bytes(MAP_TC_MAX_CTA);
 }
 
 template <int R>
@@ -472,10 +474,16 @@ extern "C" int32_t tb_encode_scene(const TbDims* dims, const TbSceneIn* in, cons
     cudaFuncSetAttribute(k_encode_tl<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<R>));
     attr_set = true;
   }
-  // 1. polyline encoder
-  k_map_polyline<<<(unsigned)((n_pl + MAP_NP - 1) / MAP_NP), NT, sizeof(MapSmem), st>>>(d, *in, packed, pl_feature,
-                                                                                      out->map_feature_valid);
-  count_launch();
+  // 1. polyline encoder: tcgen05 kernel; TB_DISABLE_TC=1 selects the fp32 CUDA-core kernel (verification aid)
+  static const bool use_tc = !(getenv("TB_DISABLE_TC") && getenv("TB_DISABLE_TC")[0] == '1');
+  if (use_tc) {
+    rc = launch_map_polyline_tc(d, *in, packed, kv_self + n_pl * 256, MAP_TC_MAX_CTA, pl_feature, out->map_feature_valid, st);
+    if (rc != TB_OK) return rc;
+  } else {
+    k_map_polyline<<<(unsigned)((n_pl + MAP_NP - 1) / MAP_NP), NT, sizeof(MapSmem), st>>>(d, *in, packed, pl_feature,
+                                                                                        out->map_feature_valid);
+    count_launch();
+  }
   // 2. global self-attention over the polylines of a scene (map_encoder.py:108-114)
   rc = tb_kv_project(TB_BLOCK_MAP_SELF_ATTN, 0, pl_feature, n_pl, packed, kv_self, stream);
   if (rc != TB_OK) return rc;

@@ -20,6 +20,12 @@ inline int launch_status() { return cudaGetLastError() == cudaSuccess ? TB_OK : 
 
 int check_dims_host(const TbDims* d);
 
+// tensor-core polyline encoder (tb_tc_kernels.cu)
+constexpr int MAP_TC_MAX_CTA = 148;
+size_t map_tc_scratch_bytes(int n_cta);
+int launch_map_polyline_tc(const TbDims& d, const TbSceneIn& in, const float* packed, float* x0_scratch, int n_cta,
+                           float* pl_feature, uint8_t* pl_valid, cudaStream_t st);
+
 // the packed parameter buffer = [fp32 blob | pad to 1 KB | tensor-core blocks]
 inline size_t tc_blob_offset_bytes() { return ((size_t)TB_PACKED_FLOATS * sizeof(float) + 1023) & ~(size_t)1023; }
 inline const unsigned char* tc_blob(const float* packed) { return reinterpret_cast<const unsigned char*>(packed) + tc_blob_offset_bytes(); }
