@@ -231,10 +231,11 @@ int32_t tb_rollout(const TbDims* dims, const TbRolloutIn* in, const float* packe
                    const TbRolloutOut* out, void* stream);
 
 /* Self-test of the tensor-core GEMM machinery (tcgen05.mma, TMEM, bulk-async weight staging, bf16x3 operand split):
- * d[128,128] = a[128,128] @ W^T for packed tensor-core weight block `block` (0 <= block < tb_tc_block_count()). */
+ * d[128,128] = a[128,128] @ W^T for packed tensor-core weight block `block` (0 <= block < tb_tc_block_count());
+ * mode 0: A operand staged in shared memory, mode 1: A operand in tensor memory. */
 int32_t tb_tc_block_count(void);
 int32_t tb_tc_first_block(int32_t weight_index); /* -1 if weight i has no tensor-core copy (N or K not multiple of 128) */
-int32_t tb_tc_selftest(const float* a, int32_t block, const float* packed, float* d, void* stream);
+int32_t tb_tc_selftest(const float* a, int32_t block, const float* packed, float* d, int32_t mode, void* stream);
 
 /* Kernels this library launches on a call path, for accounting (`gpu_launches` in bench.py). */
 int64_t tb_launch_count(void);

@@ -6,7 +6,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def test_tc_selftest_gemm_matches_fp64():
+@pytest.mark.parametrize("mode", [0, 1])
+def test_tc_selftest_gemm_matches_fp64(mode):
     from trafficbots_b200 import _native as nt, weights
     from trafficbots_b200.engine import Engine
     sd = weights.init_state_dict(4)
@@ -25,7 +26,7 @@ def test_tc_selftest_gemm_matches_fp64():
         blk = first + nb * (w.shape[1] // 128) + kb
         a = (torch.randn(128, 128, generator=g) * 3).cuda()
         d = torch.empty(128, 128, device="cuda")
-        nt.check(lib.tb_tc_selftest(a.data_ptr(), blk, eng.packed.data_ptr(), d.data_ptr(), nt.current_stream_ptr()), "selftest")
+        nt.check(lib.tb_tc_selftest(a.data_ptr(), blk, eng.packed.data_ptr(), d.data_ptr(), mode, nt.current_stream_ptr()), "selftest")
         torch.cuda.synchronize()
         wsub = w[nb * 128:(nb + 1) * 128, kb * 128:(kb + 1) * 128].double()
         ref = a.cpu().double() @ wsub.t()

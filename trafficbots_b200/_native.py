@@ -154,7 +154,7 @@ def lib() -> C.CDLL:
     L.tb_tc_first_block.restype = C.c_int32
     L.tb_tc_first_block.argtypes = [C.c_int32]
     L.tb_tc_selftest.restype = C.c_int32
-    L.tb_tc_selftest.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.tb_tc_selftest.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     _lib = L
     return L
 

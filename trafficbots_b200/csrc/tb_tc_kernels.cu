@@ -12,8 +12,9 @@ struct SelftestSmem {
 };
 
 // d[128,128] = a[128,128] @ W_block^T with W_block = one packed 128x128 tensor-core weight block
+// mode 0: A operand from shared memory (SS); mode 1: A operand from tensor memory (TS)
 __global__ void __launch_bounds__(128) k_tc_selftest(const float* __restrict__ a, const unsigned char* __restrict__ wblock,
-                                                     float* __restrict__ d) {
+                                                     float* __restrict__ d, int mode) {
   extern __shared__ unsigned char smem_raw[];
   SelftestSmem& sm = *reinterpret_cast<SelftestSmem*>(
       smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));  // SWIZZLE_128B tiles need 1 KB alignment
@@ -23,7 +24,7 @@ __global__ void __launch_bounds__(128) k_tc_selftest(const float* __restrict__ a
     tc::mbar_init(&sm.bar_mma, 1);
     tc::fence_mbar_init();
   }
-  if (warp == 0) tc::tmem_alloc(&sm.tmem_base, 128);
+  if (warp == 0) tc::tmem_alloc(&sm.tmem_base, 256);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -38,17 +39,33 @@ __global__ void __launch_bounds__(128) k_tc_selftest(const float* __restrict__ a
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = a[tid * 128 + k0 + i];
     tc::store_row32_split(sm.a_hi, sm.a_lo, tid, k0, v);
+    // TS mode: the same operand as packed bf16 pairs in TMEM, hi at columns [128,192), lo at [192,256)
+    float ph[16], pl[16];
+    tc::split32_packed(v, ph, pl);
+    tc::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + 128 + k0 / 2, ph);
+    tc::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + 192 + k0 / 2, pl);
   }
+  tc::tmem_st_wait();
   tc::fence_proxy_async();
+  tc::tc_fence_before();
   __syncthreads();
   if (tid == 0) {
     tc::mbar_wait(&sm.bar_w, 0);
     tc::tc_fence_after();
     const uint32_t idesc = tc::make_idesc_bf16(128, 128);
     const uint32_t ah = tc::smem_u32(sm.a_hi), al = tc::smem_u32(sm.a_lo), wh = tc::smem_u32(sm.w), wl = wh + 2 * tc::KB_BYTES_128;
-    tc::mma_tile(tmem, ah, tc::KB_BYTES_128, wh, tc::KB_BYTES_128, 128, idesc, false);
-    tc::mma_tile(tmem, al, tc::KB_BYTES_128, wh, tc::KB_BYTES_128, 128, idesc, true);
-    tc::mma_tile(tmem, ah, tc::KB_BYTES_128, wl, tc::KB_BYTES_128, 128, idesc, true);
+    if (mode == 0) {
+      tc::mma_tile(tmem, ah, tc::KB_BYTES_128, wh, tc::KB_BYTES_128, 128, idesc, false);
+      tc::mma_tile(tmem, al, tc::KB_BYTES_128, wh, tc::KB_BYTES_128, 128, idesc, true);
+      tc::mma_tile(tmem, ah, tc::KB_BYTES_128, wl, tc::KB_BYTES_128, 128, idesc, true);
+    } else {
+      for (int term = 0; term < 3; ++term) {
+        const uint32_t ta = tmem + (term == 1 ? 192 : 128), wb = term == 2 ? wl : wh;
+        for (int k = 0; k < 128; k += 16)
+          tc::mma_bf16_ts(tmem, ta + k / 2, tc::make_desc_sw128(wb + (k >> 6) * tc::KB_BYTES_128 + (k & 63) * 2), idesc,
+                          (term > 0 || k > 0) ? 1u : 0u);
+      }
+    }
     tc::mma_commit(&sm.bar_mma);
   }
   tc::mbar_wait(&sm.bar_mma, 0);
@@ -62,7 +79,7 @@ __global__ void __launch_bounds__(128) k_tc_selftest(const float* __restrict__ a
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 128);
+  if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
 
@@ -423,7 +440,7 @@ __global__ void __launch_bounds__(128, 1) k_map_polyline_tc(TbDims dm, TbSceneIn
 
 using namespace tb;
 
-extern "C" int32_t tb_tc_selftest(const float* a, int32_t block, const float* packed, float* d, void* stream) {
+extern "C" int32_t tb_tc_selftest(const float* a, int32_t block, const float* packed, float* d, int32_t mode, void* stream) {
   if (!a || !packed || !d) return TB_ERR_NULL;
   if (block < 0 || block >= TB_N_TC_BLOCKS) return TB_ERR_BAD_SHAPE;
   if (!aligned16(a) || !aligned16(packed) || !aligned16(d)) return TB_ERR_ALIGN;
@@ -432,7 +449,7 @@ extern "C" int32_t tb_tc_selftest(const float* a, int32_t block, const float* pa
     cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelftestSmem) + 1024);
     attr_set = true;
   }
-  k_tc_selftest<<<1, 128, sizeof(SelftestSmem) + 1024, (cudaStream_t)stream>>>(a, tc_blob(packed) + (size_t)block * tc::BLOCK_BYTES, d);
+  k_tc_selftest<<<1, 128, sizeof(SelftestSmem) + 1024, (cudaStream_t)stream>>>(a, tc_blob(packed) + (size_t)block * tc::BLOCK_BYTES, d, mode);
   count_launch();
   return launch_status();
 }
