@@ -103,7 +103,16 @@ typedef struct TbSceneOut { /* == the dict returned by TrafficBots.encode_input_
    * 3 agent->traffic-light layers of the policy (traffic_bots.py:205-219). */
   float* kv_map;                 /* [3,S,P,256]      */
   float* kv_tl;                  /* [3,S,Th,TL,256]  */
+  /* the same K|V as tensor-core operand blocks (see tb_kv_tc_bytes): only the VALID keys, compacted, in 64-key tiles of
+   * 64 KB = bf16 [K hi | K lo | V^T hi | V^T lo] in the 128-byte-swizzled K-major UMMA layout, plus the key counts. */
+  uint8_t* kv_map_tc;            /* [3,S,ceil(P/64)] x 64 KB      */
+  uint8_t* kv_tl_tc;             /* [3,S,Th,ceil(TL/64)] x 64 KB  */
+  int32_t* n_key_map;            /* [S]     valid polylines per scene          */
+  int32_t* n_key_tl;             /* [S,Th]  valid traffic lights per scene-frame */
 } TbSceneOut;
+
+/* bytes of kv_map_tc (which = 0) / kv_tl_tc (which = 1) for these dims */
+size_t tb_kv_tc_bytes(const TbDims* dims, int32_t which);
 
 /* scratch needed by tb_encode_scene */
 size_t tb_encode_workspace_bytes(const TbDims* dims);
@@ -172,6 +181,11 @@ typedef struct TbRolloutIn {
   const float* latent_logp;        /* [B,A]      */
   const int64_t* dest;             /* [B,A]      destination polyline index */
   const uint8_t* goal_valid;       /* [B,A]      */
+  /* tensor-core K|V blocks and key counts from TbSceneOut (may be NULL: the decode step then runs on the CUDA cores) */
+  const uint8_t* kv_map_tc;
+  const uint8_t* kv_tl_tc;
+  const int32_t* n_key_map;
+  const int32_t* n_key_tl;
 } TbRolloutIn;
 
 typedef struct TbRolloutOut { /* == RolloutBuffer after finish() (utils/buffer.py:72-90), T = n_step */

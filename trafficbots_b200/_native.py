@@ -36,7 +36,7 @@ EXPORTS = (
     "tb_weight_count", "tb_weight_name", "tb_weight_rows", "tb_weight_cols", "tb_packed_weight_bytes",
     "tb_pack_weights", "tb_encode_workspace_bytes", "tb_encode_scene", "tb_kv_project", "tb_xlayer",
     "tb_rollout_state_bytes", "tb_rollout_state_offset", "tb_rollout_init", "tb_rollout_steps", "tb_step_front", "tb_step_back", "tb_rollout",
-    "tb_launch_count", "tb_tc_block_count", "tb_tc_first_block", "tb_tc_selftest",
+    "tb_launch_count", "tb_kv_tc_bytes", "tb_tc_block_count", "tb_tc_first_block", "tb_tc_selftest",
 )
 
 
@@ -56,11 +56,12 @@ def _ptr_struct(name, fields):
 SCENE_IN_FIELDS = ("map_valid", "map_type", "map_pos", "map_dir", "agent_valid", "agent_pos", "agent_yaw", "agent_vel",
                    "agent_spd", "agent_yaw_rate", "agent_acc", "agent_size", "agent_type", "tl_valid", "tl_state",
                    "tl_pos", "tl_dir")
-SCENE_OUT_FIELDS = ("map_feature", "map_feature_valid", "agent_feature", "tl_feature", "kv_map", "kv_tl")
+SCENE_OUT_FIELDS = ("map_feature", "map_feature_valid", "agent_feature", "tl_feature", "kv_map", "kv_tl", "kv_map_tc", "kv_tl_tc",
+                    "n_key_map", "n_key_tl")
 ROLLOUT_IN_FIELDS = ("map_feature", "map_feature_valid", "kv_map", "kv_tl", "tl_valid", "gt_valid", "gt_pos", "gt_yaw",
                      "gt_spd", "gt_vel", "gt_acc", "gt_yaw_rate", "tf_mask", "agent_type", "agent_size", "map_boundary",
                      "map_valid", "map_type", "map_pos", "map_dir", "goal_gt", "latent_sample", "latent_logp", "dest",
-                     "goal_valid")
+                     "goal_valid", "kv_map_tc", "kv_tl_tc", "n_key_map", "n_key_tl")
 ROLLOUT_OUT_FIELDS = ("preds", "valid", "override_masks", "diffbar_rewards", "diffbar_rewards_valid",
                       "action_log_probs", "latent_log_probs", "violations", "trace_policy_feature",
                       "trace_action_mean")
@@ -150,6 +151,8 @@ def lib() -> C.CDLL:
     L.tb_rollout.argtypes = [C.POINTER(TbDims), C.POINTER(TbRolloutIn), C.c_void_p, C.c_void_p,
                              C.POINTER(TbRolloutOut), C.c_void_p]
     L.tb_launch_count.restype = C.c_int64
+    L.tb_kv_tc_bytes.restype = C.c_size_t
+    L.tb_kv_tc_bytes.argtypes = [C.POINTER(TbDims), C.c_int32]
     L.tb_tc_block_count.restype = C.c_int32
     L.tb_tc_first_block.restype = C.c_int32
     L.tb_tc_first_block.argtypes = [C.c_int32]

@@ -475,8 +475,7 @@ extern "C" int32_t tb_encode_scene(const TbDims* dims, const TbSceneIn* in, cons
     attr_set = true;
   }
   // 1. polyline encoder: tcgen05 kernel; TB_DISABLE_TC=1 selects the fp32 CUDA-core kernel (verification aid)
-  static const bool use_tc = !(getenv("TB_DISABLE_TC") && getenv("TB_DISABLE_TC")[0] == '1');
-  if (use_tc) {
+  if (tc_enabled()) {
     rc = launch_map_polyline_tc(d, *in, packed, kv_self + n_pl * 256, MAP_TC_MAX_CTA, pl_feature, out->map_feature_valid, st);
     if (rc != TB_OK) return rc;
   } else {
@@ -495,6 +494,10 @@ extern "C" int32_t tb_encode_scene(const TbDims* dims, const TbSceneIn* in, cons
     rc = tb_kv_project(TB_BLOCK_AS2PL, L, out->map_feature, n_pl, packed, out->kv_map + (size_t)L * n_pl * 256, stream);
     if (rc != TB_OK) return rc;
   }
+  if (out->kv_map_tc && out->n_key_map) {  // tensor-core operand blocks of the same K|V (valid keys only)
+    rc = launch_pack_kv_tc(out->kv_map, out->map_feature_valid, 3 * d.n_scene, d.n_scene, d.n_pl, out->kv_map_tc, out->n_key_map, st);
+    if (rc != TB_OK) return rc;
+  }
   // 4. agent / traffic-light history encoders
   const long n_ag = (long)d.n_scene * d.n_step_hist * d.n_agent;
   k_encode_agent_hist<R><<<(unsigned)((n_ag + R - 1) / R), NT, sizeof(TileSmem<R>), st>>>(d, *in, packed, out->agent_feature);
@@ -505,6 +508,11 @@ extern "C" int32_t tb_encode_scene(const TbDims* dims, const TbSceneIn* in, cons
   // 5. K|V of the agent->traffic-light layers for every history frame
   for (int L = 0; L < 3; ++L) {
     rc = tb_kv_project(TB_BLOCK_AS2TL, L, out->tl_feature, n_tl, packed, out->kv_tl + (size_t)L * n_tl * 256, stream);
+    if (rc != TB_OK) return rc;
+  }
+  if (out->kv_tl_tc && out->n_key_tl) {
+    rc = launch_pack_kv_tc(out->kv_tl, in->tl_valid, 3 * d.n_scene * d.n_step_hist, d.n_scene * d.n_step_hist, d.n_tl, out->kv_tl_tc,
+                           out->n_key_tl, st);
     if (rc != TB_OK) return rc;
   }
   return launch_status();

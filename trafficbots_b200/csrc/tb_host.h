@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/trafficbots_b200.h"
 #include "tb_device.cuh"
@@ -20,11 +21,40 @@ inline int launch_status() { return cudaGetLastError() == cudaSuccess ? TB_OK : 
 
 int check_dims_host(const TbDims* d);
 
+struct StateView {
+  float* agent_state;  // [B,A,4]
+  uint8_t* valid;      // [2,B,A]
+  uint8_t* killed;     // [B,A]
+  float* vel;          // [B,A,2]
+  float* acc;          // [B,A]
+  float* yaw_rate;     // [B,A]
+  uint8_t* goal_valid; // [B,A]
+  uint8_t* sticky;     // [3,B,A]
+  float* hidden;       // [3,B*A,128]
+  // private scratch
+  float* x0;           // [B,A,128]  map/traffic-light aware agent feature of the current step
+  float* kv_int;       // [3,B,A,256] interaction K|V of the current step
+  float* goal_in;      // [B,A,128]  add_goal.mlp_in(goal_feature) before mask/ReLU (loop invariant)
+  float* latent_in;    // [B,A,128]  add_latent.mlp_in(latent_sample) before mask/ReLU (loop invariant)
+};
+
+StateView state_view(const TbDims& d, void* base);
+
 // tensor-core polyline encoder (tb_tc_kernels.cu)
 constexpr int MAP_TC_MAX_CTA = 148;
 size_t map_tc_scratch_bytes(int n_cta);
 int launch_map_polyline_tc(const TbDims& d, const TbSceneIn& in, const float* packed, float* x0_scratch, int n_cta,
                            float* pl_feature, uint8_t* pl_valid, cudaStream_t st);
+
+// tensor-core decode step (tb_tc_rollout.cu)
+int launch_pack_kv_tc(const float* kv, const uint8_t* key_valid, int n_set, int n_set_valid, int T, unsigned char* blocks,
+                      int32_t* n_key, cudaStream_t st);
+bool front_tc_supported(const TbDims& d, const TbRolloutIn& in);
+int launch_step_front_tc(const TbDims& d, const TbRolloutIn& in, const float* packed, const StateView& sv, int t, cudaStream_t st);
+inline bool tc_enabled() {
+  static const bool on = !(getenv("TB_DISABLE_TC") && getenv("TB_DISABLE_TC")[0] == '1');
+  return on;
+}
 
 // the packed parameter buffer = [fp32 blob | pad to 1 KB | tensor-core blocks]
 inline size_t tc_blob_offset_bytes() { return ((size_t)TB_PACKED_FLOATS * sizeof(float) + 1023) & ~(size_t)1023; }

@@ -12,23 +12,6 @@
 
 namespace tb {
 
-struct StateView {
-  float* agent_state;  // [B,A,4]
-  uint8_t* valid;      // [2,B,A]
-  uint8_t* killed;     // [B,A]
-  float* vel;          // [B,A,2]
-  float* acc;          // [B,A]
-  float* yaw_rate;     // [B,A]
-  uint8_t* goal_valid; // [B,A]
-  uint8_t* sticky;     // [3,B,A]
-  float* hidden;       // [3,B*A,128]
-  // private scratch
-  float* x0;           // [B,A,128]  map/traffic-light aware agent feature of the current step
-  float* kv_int;       // [3,B,A,256] interaction K|V of the current step
-  float* goal_in;      // [B,A,128]  add_goal.mlp_in(goal_feature) before mask/ReLU (loop invariant)
-  float* latent_in;    // [B,A,128]  add_latent.mlp_in(latent_sample) before mask/ReLU (loop invariant)
-};
-
 static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct StateLayout {
@@ -62,7 +45,7 @@ static StateLayout state_layout(const TbDims& d) {
   return L;
 }
 
-static StateView state_view(const TbDims& d, void* base) {
+StateView state_view(const TbDims& d, void* base) {
   const StateLayout L = state_layout(d);
   char* p = reinterpret_cast<char*>(base);
   StateView v;
@@ -650,8 +633,13 @@ static int rollout_steps_impl(const TbDims* dims, const TbRolloutIn* in, const f
   cudaStream_t st = (cudaStream_t)stream;
   for (int t = t_first; t <= t_last; ++t) {
     if (which & 1) {
-      k_step_front<R><<<grid, NT, sizeof(TileSmem<R>), st>>>(d, *in, packed, sv, t);
-      count_launch();
+      if (tc_enabled() && front_tc_supported(d, *in)) {
+        const int rc2 = launch_step_front_tc(d, *in, packed, sv, t, st);
+        if (rc2 != TB_OK) return rc2;
+      } else {
+        k_step_front<R><<<grid, NT, sizeof(TileSmem<R>), st>>>(d, *in, packed, sv, t);
+        count_launch();
+      }
     }
     if (which & 2) {
       k_step_back<R><<<grid, NT, sizeof(BackSmem<R>), st>>>(d, *in, packed, sv, *out, t);

@@ -104,8 +104,14 @@ class Engine:
         f["tl_feature_valid"] = batch[tl + "valid"]
         f["_kv_map"] = torch.empty(3, S, P, 256, device=dev)
         f["_kv_tl"] = torch.empty(3, S, Th, TL, 256, device=dev)
+        f["_kv_map_tc"] = torch.empty(self.lib.tb_kv_tc_bytes(C.byref(dims), 0), dtype=torch.uint8, device=dev)
+        f["_kv_tl_tc"] = torch.empty(self.lib.tb_kv_tc_bytes(C.byref(dims), 1), dtype=torch.uint8, device=dev)
+        f["_n_key_map"] = torch.empty(S, dtype=torch.int32, device=dev)
+        f["_n_key_tl"] = torch.empty(S, Th, dtype=torch.int32, device=dev)
         sout = nt.TbSceneOut(f["map_feature"].data_ptr(), f["map_feature_valid"].data_ptr(), f["agent_feature"].data_ptr(),
-                             f["tl_feature"].data_ptr(), f["_kv_map"].data_ptr(), f["_kv_tl"].data_ptr())
+                             f["tl_feature"].data_ptr(), f["_kv_map"].data_ptr(), f["_kv_tl"].data_ptr(),
+                             f["_kv_map_tc"].data_ptr(), f["_kv_tl_tc"].data_ptr(), f["_n_key_map"].data_ptr(),
+                             f["_n_key_tl"].data_ptr())
         need = self.lib.tb_encode_workspace_bytes(C.byref(dims))
         if self._enc_ws is None or self._enc_ws.numel() < need:
             self._enc_ws = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -159,7 +165,11 @@ class Engine:
             p(raw_map["type"], "u8", (S, P, 11), "map/type"), p(raw_map["pos"], "f32", (S, P, 20, 2), "map/pos"),
             p(raw_map["dir"], "f32", (S, P, 20, 2), "map/dir"), p(goal_gt, "f32", (S, A, 4), "goal_gt", optional=True),
             p(latent_sample, "f32", (B, A, 16), "latent_sample"), p(latent_logp, "f32", (B, A), "latent_logp"),
-            p(dest, "i64", (B, A), "dest"), p(goal_valid, "u8", (B, A), "goal_valid"))
+            p(dest, "i64", (B, A), "dest"), p(goal_valid, "u8", (B, A), "goal_valid"),
+            feat["_kv_map_tc"].data_ptr() if "_kv_map_tc" in feat else None,
+            feat["_kv_tl_tc"].data_ptr() if "_kv_tl_tc" in feat else None,
+            feat["_n_key_map"].data_ptr() if "_n_key_map" in feat else None,
+            feat["_n_key_tl"].data_ptr() if "_n_key_tl" in feat else None)
         return dims, rin
 
     def _ensure_state(self, dims: nt.TbDims) -> Tensor:

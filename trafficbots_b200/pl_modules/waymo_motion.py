@@ -153,6 +153,9 @@ class WaymoMotion(_Base):
                   "spd": st[..., 3:4].contiguous(), "vel": features["vel"], "acc": features["acc"], "yaw_rate": features["yaw_rate"]}
         feat = {"map_feature": features["map_feature"], "map_feature_valid": features["map_valid"],
                 "tl_feature_valid": features["tl_valid"], "_kv_map": features["_kv_map"], "_kv_tl": features["_kv_tl"]}
+        for k in ("_kv_map_tc", "_kv_tl_tc", "_n_key_map", "_n_key_tl"):
+            if k in features:
+                feat[k] = features[k]
         args = (feat, gt, mask_teacher_forcing, features["agent_type"], features["agent_size"], rule_checker.raw_map,
                 self.model.latent_sample, self.model.latent_logp, goal.contiguous(), goal_valid.contiguous(), rule_checker.agent_goal)
         if features.get("_stepwise", False):  # caller drives the steps through forward()
@@ -186,7 +189,8 @@ class WaymoMotion(_Base):
         return {"map_valid": f["map_feature_valid"], "map_feature": f["map_feature"], "tl_valid": f["tl_feature_valid"],
                 "tl_feature": f["tl_feature"], "agent_type": batch["history/agent/type"], "agent_size": batch["history/agent/size"],
                 "agent_valid": gt["valid"], "vel": gt["vel"], "acc": gt["acc"], "yaw_rate": gt["yaw_rate"], "agent_state": None,
-                "_gt": gt, "_kv_map": f["_kv_map"], "_kv_tl": f["_kv_tl"], "_n_mode": n_mode}
+                "_gt": gt, "_kv_map": f["_kv_map"], "_kv_tl": f["_kv_tl"], "_n_mode": n_mode,
+                **{k: f[k] for k in ("_kv_map_tc", "_kv_tl_tc", "_n_key_map", "_n_key_tl") if k in f}}
 
     def reactive_replay(self, batch: Mapping[str, Tensor], input_feature_dict: Mapping[str, Tensor], mask_teacher_forcing: Tensor,
                         latent, goal: Optional[Tensor], goal_valid: Optional[Tensor], deterministic_latent: bool,
