@@ -119,6 +119,12 @@ struct FrontArgs {
   int t;
 };
 
+// MUFU.EX2 (max relative error 2^-22), without exp2f's denormal-range scaling
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
@@ -461,12 +467,15 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_step_front_tc(FrontArgs a)
           float sv_[32];
           tc::tmem_ld32(sbase + 32 * h, sv_);
           tc::tmem_ld_wait();
-          float mx = -INFINITY;
+          if (key0 + SUB_KEYS > nkey) {  // only the last sub-tile of a layer has padding keys
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            sv_[j] = (key0 + j < nkey) ? sv_[j] * sc : -INFINITY;
-            mx = fmaxf(mx, sv_[j]);
+            for (int j = 0; j < 32; ++j)
+              if (key0 + j >= nkey) sv_[j] = -INFINITY;
           }
+          float mx = sv_[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) mx = fmaxf(mx, sv_[j]);
+          mx *= sc;  // sc > 0: scale after the max
           // lazy rescaling: keep the reference maximum unless the new maximum exceeds it by more than 8 (factor 256)
           if (mx > m_ref[hh] + 8.0f) {
             alpha[hh] = (m_ref[hh] == -INFINITY) ? 0.f : exp2f(m_ref[hh] - mx);
@@ -475,9 +484,10 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_step_front_tc(FrontArgs a)
             need_rescale = need_rescale || (u > 0);
           }
           float psum = 0.f;
+          const float neg_m = -m_ref[hh];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            sv_[j] = exp2f(sv_[j] - m_ref[hh]);  // masked keys: exp2(-inf) = 0
+            sv_[j] = ex2_approx(fmaf(sv_[j], sc, neg_m));  // masked keys: ex2(-inf) = 0
             psum += sv_[j];
           }
           l_sum[hh] += psum;
