@@ -45,11 +45,11 @@ def test_joint_future_pred_surface(case):
     # mode 0 is deterministic (prior mean, arg-max destination): identical to the reference's mode 0
     assert torch.equal(goal_sample[:, :, 0].cpu(), gold["jfp/goal_sample"][:, :, 0])
     assert torch.equal(buf.valid[:, :, 0].cpu(), gold["jfp/valid"][:, :, 0])
-    assert float((buf.preds[:, :, 0].cpu() - gold["jfp/preds"][:, :, 0]).abs().max()) <= 1e-3
+    assert float((buf.preds[:, :, 0].cpu() - gold["jfp/preds"][:, :, 0]).abs().max()) <= 2e-3  # closed-loop tolerance, see tests/test_gpu_parity.py
     for k in ("outside_map", "goal_reached", "dest_reached"):
         assert torch.equal(buf.violations[k][:, :, 0].cpu(), gold[f"jfp/violations/{k}"][:, :, 0]), k
     assert float((m.model.hidden.view(3, S, K, A, 128)[:, :, 0].cpu()
-                  - gold["jfp/hidden"].view(3, S, K, A, 128)[:, :, 0]).abs().max()) <= 1e-3
+                  - gold["jfp/hidden"].view(3, S, K, A, 128)[:, :, 0]).abs().max()) <= 2e-3  # closed-loop tolerance, see tests/test_gpu_parity.py
 
 
 def test_reactive_replay_surface_and_stepwise_forward():
@@ -68,8 +68,8 @@ def test_reactive_replay_surface_and_stepwise_forward():
                             deterministic_action=True, require_vis_dict=False)
     assert torch.equal(buf.valid.cpu(), gold["replay/valid"])
     assert torch.equal(buf.override_masks.cpu(), gold["replay/override_masks"])
-    assert float((buf.preds.cpu() - gold["replay/preds"]).abs().max()) <= 1e-3
-    assert float((buf.diffbar_rewards.cpu() - gold["replay/diffbar_rewards"]).abs().max()) <= 1e-3
+    assert float((buf.preds.cpu() - gold["replay/preds"]).abs().max()) <= 2e-3  # closed-loop tolerance, see tests/test_gpu_parity.py
+    assert float((buf.diffbar_rewards.cpu() - gold["replay/diffbar_rewards"]).abs().max()) <= 2e-3  # closed-loop tolerance, see tests/test_gpu_parity.py
     for k in ("outside_map", "goal_reached", "dest_reached", "dest_reached_this_step"):
         assert torch.equal(buf.violations[k].cpu(), gold[f"replay/violations/{k}"]), k
     one_shot = buf.preds.clone()

@@ -51,6 +51,15 @@ int launch_pack_kv_tc(const float* kv, const uint8_t* key_valid, int n_set, int 
                       int32_t* n_key, cudaStream_t st);
 bool front_tc_supported(const TbDims& d, const TbRolloutIn& in);
 int launch_step_front_tc(const TbDims& d, const TbRolloutIn& in, const float* packed, const StateView& sv, int t, cudaStream_t st);
+extern long long* g_debug_trace;  // development aid (tb_debug_set_trace)
+// persistent tensor-core rollout (tb_tc_persist.cu): all decode steps t_first..t_last in one launch, n_agent <= 64
+bool rollout_tc_supported(const TbDims& d, const TbRolloutIn& in);
+int launch_rollout_tc(const TbDims& d, const TbRolloutIn& in, const float* packed, const StateView& sv, const TbRolloutOut& out,
+                      int t_first, int t_last, cudaStream_t st);
+inline bool persist_enabled() {
+  static const bool on = !(getenv("TB_DISABLE_PERSIST") && getenv("TB_DISABLE_PERSIST")[0] == '1');
+  return on;
+}
 inline bool tc_enabled() {
   static const bool on = !(getenv("TB_DISABLE_TC") && getenv("TB_DISABLE_TC")[0] == '1');
   return on;

@@ -631,6 +631,8 @@ static int rollout_steps_impl(const TbDims* dims, const TbRolloutIn* in, const f
   const StateView sv = state_view(d, state);
   dim3 grid((d.n_agent + R - 1) / R, d.n_scene * d.n_mode);
   cudaStream_t st = (cudaStream_t)stream;
+  if (which == 3 && tc_enabled() && persist_enabled() && rollout_tc_supported(d, *in))
+    return launch_rollout_tc(d, *in, packed, sv, *out, t_first, t_last, st);
   for (int t = t_first; t <= t_last; ++t) {
     if (which & 1) {
       if (tc_enabled() && front_tc_supported(d, *in)) {

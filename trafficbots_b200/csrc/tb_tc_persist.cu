@@ -1,0 +1,1212 @@
+// Persistent tensor-core rollout (tcgen05): the WHOLE decode step of WaymoMotion.rollout (reference
+// src/pl_modules/waymo_motion.py:108-354) for ONE scene-mode per CTA, looping over the decode steps t_first..t_last
+// without returning to the host: state embedding -> 3 agent->map layers -> 3 agent->traffic-light layers -> 3
+// agent<->agent layers -> 3 GRU layers -> add_goal -> add_latent -> action head -> dynamics / override / rule checks /
+// kill / reward -> outputs in the final [B,A,T,.] layout.  Supports n_agent <= 64 (larger scenes use the two-kernel path).
+//
+// Roles (320 threads):
+//   warps 0..7  row workers.  TMEM lane l = 32 * (warp % 4) + lane; agent a = l % 64; `upper` = l / 64; `half` = warp / 4.
+//               Every Linear is evaluated for 128 rows = the 64 agents TWICE (rows a and a + 64 hold the same values), which
+//               costs nothing (M = 128 is the tensor-core tile height) and lets the attention run "head-stacked":
+//   warp  8     issuer: one lane issues every tcgen05.mma and commits completion to mbarriers.
+//   warp  9     loader: one lane streams the 64 KB operand blocks (weights, compacted K|V key blocks) into a 2-slot ring
+//               with bulk-async copies, 32 KB halves with their own full / free barriers.
+//
+// Head-stacked attention (n_agent <= 64): for head pair hp = {2hp, 2hp+1} the A operand row l holds the query of agent a
+// for head 2hp + upper in that head's 32 dims of the 64-dim K-block and zeros in the other head's dims, so ONE N = 64 MMA
+// chain against the K-block [64 keys x 64 dims] yields S[l, key] = q_{2hp+upper}(a) . k_{2hp+upper}(key): all 128 lanes
+// carry useful logits.  PV uses the same trick with N = 64 dims: D[l, 0:32] = P V_{2hp}, D[l, 32:64] = P V_{2hp+1}; lane l
+// keeps columns 32 * upper .. +32.  Worker group `half` = hp owns pass hp, so the two groups alternate on the tensor pipe
+// (one does its softmax while the other's QK^T / PV run).
+//
+// TMEM (512 columns):  [0,128) ACC0 (S buffers of pass 0 / 1 at [0,64) / [64,128) during attention)   [128,256) ACC1
+//                      [256,384) ACC2 | second A operand (GRU hidden, goal / latent feature) | O accumulators of the 2 passes
+//                      [384,512) A operand (bf16x2 packed: hi [384,448), lo [448,512))
+// Numerics: every contraction is bf16x3 (hi*hi + lo*hi + hi*lo, fp32 accumulate), see tb_tc.cuh.
+#include "tb_host.h"
+
+namespace tb {
+namespace pr {
+
+constexpr int WORKERS = 256;
+constexpr int THREADS = WORKERS + 64;
+constexpr int MAXA = 64;
+constexpr uint32_t BLK = 65536, HALF = 32768;
+constexpr uint32_t T_ACC0 = 0, T_ACC1 = 128, T_ACC2 = 256, T_A2 = 256, T_O = 256, T_A = 384;
+constexpr int N_PHASE = 15;  // parameter-vector sets: 9 attention layers, 3 GRU layers, add_goal, add_latent, head
+
+struct Smem {
+  unsigned char ring[2][BLK];
+  float xs[128 * MAXA];  // residual stream, [col][agent]
+  float xo[128 * MAXA];  // exchange buffer, [col][agent] (attention output; scratch of the state embedding)
+  float lp[2][16][128];  // parameter vectors of the current / next phase
+  float emb_w1[384], emb_w2[1024], emb_b1[32], emb_b2[32], f_xy[24], f_yaw[48];
+  float2 red[2][2][128];  // LayerNorm partials {sum, M2} [buffer][half][lane]
+  float mean_part[2][MAXA][2];
+  // simulation state of the scene-mode
+  float4 pose[MAXA];  // x, y, yaw, spd
+  float2 vel[MAXA];
+  float acc[MAXA], yaw_rate[MAXA];
+  uint8_t valid[MAXA], killed[MAXA], goal_valid[MAXA], sticky[3][MAXA], type[MAXA][4];
+  // barriers
+  uint64_t full[2][2], free_[2][2], grant, wfill, ready, mma, cfg, s[2], p[2], o[2];
+  uint32_t tmem_base;
+  int n_valid, kvi_slot;
+};
+
+struct Args {
+  TbDims dm;
+  TbRolloutIn in;
+  const float* packed;
+  const unsigned char* tcw;
+  StateView sv;
+  TbRolloutOut out;
+  int t_first, t_last;
+  long long* trace;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float smooth_l1(float d) {
+  const float a = fabsf(d);
+  return a < 1.0f ? 0.5f * d * d : a - 0.5f;
+}
+
+// offset (floats, in the packed blob) of parameter vector i of phase p, or -1
+__device__ __forceinline__ int phase_vec(int p, int i) {
+  if (p < 9) {
+    const int kind = p / 3, L = p % 3;
+    const int base = (kind == 0   ? tbw::model_transformer_as2pl_layers_0_norm1_weight
+                      : kind == 1 ? tbw::model_transformer_as2tl_layers_0_norm1_weight
+                                  : tbw::model_agent_interaction_transformer_layers_0_norm1_weight) +
+                     L * tfl::STRIDE;
+    switch (i) {
+      case 0: return base + tfl::NORM1_W;
+      case 1: return base + tfl::NORM1_B;
+      case 2: return base + tfl::IN_B;
+      case 3: return base + tfl::OUT_B;
+      case 4: return base + tfl::NORM2_W;
+      case 5: return base + tfl::NORM2_B;
+      case 6: return base + tfl::L1_B;
+      case 7: return base + tfl::L2_B;
+      case 8: return kind == 2 ? base + tfl::NORMT_W : -1;
+      case 9: return kind == 2 ? base + tfl::NORMT_B : -1;
+      case 10: return kind == 2 ? base + tfl::IN_B + 128 : -1;
+      case 11: return kind == 2 ? base + tfl::IN_B + 256 : -1;
+    }
+    return -1;
+  }
+  if (p < 12) {
+    const int base = gru::BASE + (p - 9) * gru::STRIDE;
+    if (i < 3) return base + gru::B_IH + 128 * i;
+    if (i < 6) return base + gru::B_HH + 128 * (i - 3);
+    return -1;
+  }
+  if (p == 12) return i == 0 ? tbw::model_add_goal_mlp_out_fc_layers_0_bias : i == 1 ? tbw::model_add_goal_mlp_out_fc_layers_3_bias : -1;
+  if (p == 13) return i == 0 ? tbw::model_add_latent_mlp_out_fc_layers_0_bias : i == 1 ? tbw::model_add_latent_mlp_out_fc_layers_3_bias : -1;
+  switch (i) {  // head
+    case 0: return tbw::action_head_mlp_mean_0_fc_layers_0_bias;
+    case 1: return tbw::action_head_mlp_mean_1_fc_layers_0_bias;
+    case 2: return tbw::action_head_mlp_mean_2_fc_layers_0_bias;
+    case 3: return tbw::action_head_mlp_mean_0_fc_layers_2_weight;  // Wt4[32][2][4] = 256 floats
+    case 4: return tbw::action_head_mlp_mean_0_fc_layers_2_weight + 128;
+    case 5: return tbw::action_head_mlp_mean_1_fc_layers_2_weight;
+    case 6: return tbw::action_head_mlp_mean_1_fc_layers_2_weight + 128;
+    case 7: return tbw::action_head_mlp_mean_2_fc_layers_2_weight;
+    case 8: return tbw::action_head_mlp_mean_2_fc_layers_2_weight + 128;
+  }
+  return -1;
+}
+
+// ---- the operand-block sequence of one decode step, shared by the loader and the issuer ---------------------------------
+struct StepCfg {
+  int nblk_map, nblk_tl;
+  const unsigned char* kv_map;  // + (L * S) * nT_map * BLK per layer
+  const unsigned char* kv_tl;
+  size_t kv_map_layer_stride, kv_tl_layer_stride;
+};
+
+template <class R>
+__device__ __forceinline__ void enumerate_step(const Args& a, const StepCfg& c, R& r) {
+  auto W = [&](int first, int idx) { return a.tcw + (size_t)(first + idx) * BLK; };
+  bool bypass = false;
+  int nblk_int = 0;
+#pragma unroll 1
+  for (int Lx = 0; Lx < 9; ++Lx) {
+    const int kind = Lx / 3, L = Lx % 3;
+    if (Lx == 6) {
+      const int nv = r.wait_cfg();
+      bypass = nv == 1;
+      nblk_int = nv > 0 ? 1 : 0;
+    }
+    if (kind == 2 && bypass) break;
+    const int w0 = (kind == 0   ? tbb::model_transformer_as2pl_layers_0_attn_in_proj_weight
+                    : kind == 1 ? tbb::model_transformer_as2tl_layers_0_attn_in_proj_weight
+                                : tbb::model_agent_interaction_transformer_layers_0_attn_in_proj_weight) +
+                   6 * L;
+    const int nblk = kind == 0 ? c.nblk_map : kind == 1 ? c.nblk_tl : nblk_int;
+    if (nblk > 0) {
+      if (kind == 2) {
+        r.gemm_begin();
+        r.chain(W(w0, 1), T_ACC0, T_A, false);
+        r.chain(W(w0, 2), T_ACC1, T_A, false);
+        r.gemm_end();
+        r.kvi();
+      }
+      r.gemm_begin();
+      r.chain(W(w0, 0), T_ACC0, T_A, false);
+      r.gemm_end();
+      r.att(kind == 2, nblk, kind == 0 ? c.kv_map + L * c.kv_map_layer_stride : c.kv_tl + L * c.kv_tl_layer_stride);
+      r.gemm_begin();
+      r.chain(W(w0, 3), T_ACC0, T_A, false);
+      r.gemm_end();
+    }
+    r.gemm_begin();
+    r.chain(W(w0, 4), T_ACC0, T_A, false);
+    r.gemm_end();
+    r.gemm_begin();
+    r.chain(W(w0, 5), T_ACC0, T_A, false);
+    r.gemm_end();
+  }
+#pragma unroll 1
+  for (int L = 0; L < 3; ++L) {  // GRU: gate blocks r, z, n of weight_ih / weight_hh
+    const int wi = tbb::model_agent_temporal_rnn_weight_ih_l0 + 6 * L, wh = tbb::model_agent_temporal_rnn_weight_hh_l0 + 6 * L;
+    r.gemm_begin();
+    r.chain(W(wi, 0), T_ACC0, T_A, false);
+    r.chain(W(wh, 0), T_ACC0, T_A2, true);
+    r.chain(W(wh, 2), T_ACC1, T_A2, false);
+    r.gemm_end();
+    r.gemm_begin();
+    r.chain(W(wi, 1), T_ACC0, T_A, false);
+    r.chain(W(wh, 1), T_ACC0, T_A2, true);
+    r.chain(W(wi, 2), T_ACC1, T_A, false);
+    r.gemm_end();
+  }
+  {
+    const int w[2][2] = {{tbb::model_add_goal_mlp_out_fc_layers_0_weight, tbb::model_add_goal_mlp_out_fc_layers_3_weight},
+                         {tbb::model_add_latent_mlp_out_fc_layers_0_weight, tbb::model_add_latent_mlp_out_fc_layers_3_weight}};
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {
+      r.gemm_begin();
+      r.chain(W(w[j][0], 0), T_ACC0, T_A, false);
+      r.chain(W(w[j][0], 1), T_ACC0, T_A2, true);
+      r.gemm_end();
+      r.gemm_begin();
+      r.chain(W(w[j][1], 0), T_ACC0, T_A, false);
+      r.gemm_end();
+    }
+  }
+  r.gemm_begin();
+  r.chain(W(tbb::action_head_mlp_mean_0_fc_layers_0_weight, 0), T_ACC0, T_A, false);
+  r.chain(W(tbb::action_head_mlp_mean_1_fc_layers_0_weight, 0), T_ACC1, T_A, false);
+  r.chain(W(tbb::action_head_mlp_mean_2_fc_layers_0_weight, 0), T_ACC2, T_A, false);
+  r.gemm_end();
+}
+
+struct Loader {
+  Smem& sm;
+  uint32_t g = 0, n_cfg = 0;
+  __device__ Loader(Smem& s) : sm(s) {}
+  __device__ __forceinline__ void wait_free(uint32_t slot, uint32_t half) {
+    const uint32_t use = g >> 1;
+    if (use > 0) tc::mbar_wait(&sm.free_[slot][half], (use - 1) & 1);
+  }
+  __device__ __forceinline__ void load(const unsigned char* ptr) {
+    const uint32_t slot = g & 1;
+#pragma unroll
+    for (uint32_t h = 0; h < 2; ++h) {
+      wait_free(slot, h);
+      tc::mbar_expect_tx(&sm.full[slot][h], HALF);
+      tc::bulk_g2s(sm.ring[slot] + h * HALF, ptr + h * HALF, HALF, &sm.full[slot][h]);
+    }
+    ++g;
+  }
+  __device__ __forceinline__ int wait_cfg() {
+    tc::mbar_wait(&sm.cfg, n_cfg & 1);
+    ++n_cfg;
+    return *reinterpret_cast<volatile int*>(&sm.n_valid);
+  }
+  __device__ __forceinline__ void gemm_begin() {}
+  __device__ __forceinline__ void gemm_end() {}
+  __device__ __forceinline__ void chain(const unsigned char* w, uint32_t, uint32_t, bool) { load(w); }
+  __device__ __forceinline__ void kvi() {
+    const uint32_t slot = g & 1;
+    wait_free(slot, 0);
+    wait_free(slot, 1);
+    *reinterpret_cast<volatile int*>(&sm.kvi_slot) = (int)slot;
+    __threadfence_block();
+    mbar_arrive(&sm.grant);
+    ++g;
+  }
+  __device__ __forceinline__ void att(bool kvi_keys, int nblk, const unsigned char* blocks) {
+    if (kvi_keys) return;
+    for (int j = 0; j < nblk; ++j) load(blocks + (size_t)j * BLK);
+  }
+};
+
+struct Issuer {
+  Smem& sm;
+  uint32_t tm0;
+  uint32_t g = 0, nf[2] = {0, 0}, n_ready = 0, n_cfg = 0, n_p[2] = {0, 0}, n_kvi = 0, kvi_slot = 0;
+  __device__ Issuer(Smem& s, uint32_t t) : sm(s), tm0(t) {}
+  __device__ __forceinline__ int wait_cfg() {
+    tc::mbar_wait(&sm.cfg, n_cfg & 1);
+    ++n_cfg;
+    return *reinterpret_cast<volatile int*>(&sm.n_valid);
+  }
+  __device__ __forceinline__ void wait_ready() {
+    tc::mbar_wait(&sm.ready, n_ready & 1);
+    ++n_ready;
+    tc::tc_fence_after();
+  }
+  __device__ __forceinline__ void gemm_begin() { wait_ready(); }
+  __device__ __forceinline__ void gemm_end() { tc::mma_commit(&sm.mma); }
+  __device__ __forceinline__ void chain(const unsigned char*, uint32_t dcol, uint32_t acol, bool accum) {
+    const uint32_t slot = g & 1;
+    tc::mbar_wait(&sm.full[slot][0], nf[slot] & 1);
+    tc::mbar_wait(&sm.full[slot][1], nf[slot] & 1);
+    ++nf[slot];
+    tc::tc_fence_after();
+    const uint32_t wh = tc::smem_u32(sm.ring[slot]);
+    const uint64_t dh = tc::make_desc_sw128(wh), dl = tc::make_desc_sw128(wh + 2 * tc::KB_BYTES_128);
+    const uint32_t idesc = tc::make_idesc_bf16(128, 128);
+#pragma unroll
+    for (int term = 0; term < 3; ++term) {
+      const uint32_t ta = tm0 + acol + (term == 1 ? 64 : 0);
+      const uint64_t db = term == 2 ? dl : dh;
+#pragma unroll
+      for (int k = 0; k < 128; k += 16)
+        tc::mma_bf16_ts(tm0 + dcol, ta + k / 2, db + (uint64_t)(((k >> 6) * tc::KB_BYTES_128 + (k & 63) * 2) >> 4), idesc,
+                        (accum || term > 0 || k > 0) ? 1u : 0u);
+    }
+    tc::mma_commit(&sm.free_[slot][0]);
+    tc::mma_commit(&sm.free_[slot][1]);
+    ++g;
+  }
+  __device__ __forceinline__ void kvi() {
+    kvi_slot = g & 1;
+    ++g;
+  }
+  // QK^T of pass hp against the K half of the block in `slot`:  S_hp[128 x 64 keys] = A_hp[128 x 64 dims] K_hp^T
+  __device__ __forceinline__ void issue_qk(uint32_t slot, int hp) {
+    const uint32_t kb = tc::smem_u32(sm.ring[slot]) + hp * 8192;
+    const uint64_t dh = tc::make_desc_sw128(kb), dl = tc::make_desc_sw128(kb + 16384);
+    const uint32_t idesc = tc::make_idesc_bf16(128, 64);
+#pragma unroll
+    for (int term = 0; term < 3; ++term) {
+      const uint32_t ta = tm0 + T_A + (term == 1 ? 64 : 0) + 32 * hp;
+      const uint64_t db = term == 2 ? dl : dh;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        tc::mma_bf16_ts(tm0 + T_ACC0 + 64 * hp, ta + 8 * ks, db + (uint64_t)(2 * ks), idesc, (term > 0 || ks > 0) ? 1u : 0u);
+    }
+    tc::mma_commit(&sm.s[hp]);
+  }
+  // PV of pass hp:  O_hp[128 x 64 dims] (+)= P_hp[128 x 64 keys] V_hp   (P = bf16 hi | lo packed over the S columns)
+  __device__ __forceinline__ void issue_pv(uint32_t slot, int hp, bool accum) {
+    const uint32_t vb = tc::smem_u32(sm.ring[slot]) + HALF + hp * 8192;
+    const uint64_t dh = tc::make_desc_sw128(vb), dl = tc::make_desc_sw128(vb + 16384);
+    const uint32_t idesc = tc::make_idesc_bf16(128, 64);
+    const uint32_t sp = tm0 + T_ACC0 + 64 * hp;
+#pragma unroll
+    for (int term = 0; term < 3; ++term) {
+      const uint32_t ta = sp + (term == 1 ? 32 : 0);
+      const uint64_t db = term == 2 ? dl : dh;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        tc::mma_bf16_ts(tm0 + T_O + 64 * hp, ta + 8 * ks, db + (uint64_t)(2 * ks), idesc, (accum || term > 0 || ks > 0) ? 1u : 0u);
+    }
+  }
+  __device__ __forceinline__ void att(bool kvi_keys, int nblk, const unsigned char*) {
+    wait_ready();  // stacked queries written
+    const uint32_t g0 = kvi_keys ? kvi_slot : g;  // slot parity of block jb = (g0 + jb) & 1
+    if (kvi_keys) {
+      tc::mbar_wait(&sm.wfill, n_kvi & 1);
+      ++n_kvi;
+    } else {
+      tc::mbar_wait(&sm.full[g0 & 1][0], nf[g0 & 1] & 1);
+    }
+    tc::tc_fence_after();
+    issue_qk(g0 & 1, 0);
+    issue_qk(g0 & 1, 1);
+    tc::mma_commit(&sm.free_[g0 & 1][0]);
+    for (int jb = 0; jb < nblk; ++jb) {
+      const uint32_t slot = (g0 + jb) & 1, slotn = slot ^ 1;
+#pragma unroll
+      for (int hp = 0; hp < 2; ++hp) {
+        tc::mbar_wait(&sm.p[hp], n_p[hp] & 1);
+        ++n_p[hp];
+        tc::tc_fence_after();
+        if (hp == 0 && !kvi_keys) {
+          tc::mbar_wait(&sm.full[slot][1], nf[slot] & 1);
+          ++nf[slot];
+          tc::tc_fence_after();
+        }
+        issue_pv(slot, hp, jb > 0);
+        if (hp == 1) tc::mma_commit(&sm.free_[slot][1]);
+        if (jb + 1 < nblk) {
+          if (hp == 0) {
+            tc::mbar_wait(&sm.full[slotn][0], nf[slotn] & 1);
+            tc::tc_fence_after();
+          }
+          issue_qk(slotn, hp);
+          if (hp == 1) tc::mma_commit(&sm.free_[slotn][0]);
+        } else {
+          tc::mma_commit(&sm.o[hp]);
+        }
+      }
+    }
+    if (!kvi_keys) g += nblk;
+  }
+};
+
+// =============================================================================================================================
+__global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
+  extern __shared__ unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
+  const TbDims& dm = a.dm;
+  const TbRolloutIn& in = a.in;
+  const float* __restrict__ packed = a.packed;
+  const int A = dm.n_agent, K = dm.n_mode, S = dm.n_scene, B = S * K, Th = dm.n_step_hist, T = dm.n_step, Tg = dm.n_step_gt;
+  const int nT_map = (dm.n_pl + 63) / 64, nT_tl = (dm.n_tl + 63) / 64;
+  const int b = blockIdx.x, s = b / K;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t BA = (size_t)B * A;
+  const int nkey_map = in.n_key_map[s];
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 2; ++j) {
+        tc::mbar_init(&sm.full[i][j], 1);
+        tc::mbar_init(&sm.free_[i][j], 1);
+      }
+    tc::mbar_init(&sm.grant, 1);
+    tc::mbar_init(&sm.wfill, 8);
+    tc::mbar_init(&sm.ready, 8);
+    tc::mbar_init(&sm.mma, 1);
+    tc::mbar_init(&sm.cfg, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&sm.s[i], 1);
+      tc::mbar_init(&sm.p[i], 4);
+      tc::mbar_init(&sm.o[i], 1);
+    }
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&sm.tmem_base, 512);
+  // persistent tables: state-embedding MLP (agent_encoder) and the positional-encoding frequencies
+  for (int i = tid; i < 384; i += THREADS) sm.emb_w1[i] = __ldg(packed + tbw::model_agent_encoder_mlp_fc_layers_0_weight + i);
+  for (int i = tid; i < 1024; i += THREADS) sm.emb_w2[i] = __ldg(packed + tbw::model_agent_encoder_mlp_fc_layers_3_weight + i);
+  if (tid < 32) {
+    sm.emb_b1[tid] = __ldg(packed + tbw::model_agent_encoder_mlp_fc_layers_0_bias + tid);
+    sm.emb_b2[tid] = __ldg(packed + tbw::model_agent_encoder_mlp_fc_layers_3_bias + tid);
+  }
+  if (tid < 24) sm.f_xy[tid] = __ldg(packed + tbw::pre_processing_input_pose_pe_agent_pe_xy_freqs + tid);
+  if (tid < 48) sm.f_yaw[tid] = __ldg(packed + tbw::pre_processing_input_pose_pe_agent_pe_yaw_freqs + tid);
+  // simulation state -> shared memory
+  if (tid < MAXA) {
+    const int ag = tid;
+    const bool live = ag < A;
+    const size_t ba = (size_t)b * A + (live ? ag : 0), sa = (size_t)s * A + (live ? ag : 0);
+    sm.pose[ag] = live ? *reinterpret_cast<const float4*>(a.sv.agent_state + ba * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sm.vel[ag] = live ? make_float2(a.sv.vel[ba * 2], a.sv.vel[ba * 2 + 1]) : make_float2(0.f, 0.f);
+    sm.acc[ag] = live ? a.sv.acc[ba] : 0.f;
+    sm.yaw_rate[ag] = live ? a.sv.yaw_rate[ba] : 0.f;
+    sm.valid[ag] = live ? a.sv.valid[(size_t)(a.t_first & 1) * BA + ba] : (uint8_t)0;
+    sm.killed[ag] = live ? a.sv.killed[ba] : (uint8_t)0;
+    sm.goal_valid[ag] = live ? a.sv.goal_valid[ba] : (uint8_t)0;
+    for (int i = 0; i < 3; ++i) {
+      sm.sticky[i][ag] = live ? a.sv.sticky[(size_t)i * BA + ba] : (uint8_t)0;
+      sm.type[ag][i] = live ? in.agent_type[sa * 3 + i] : (uint8_t)0;
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tm0 = sm.tmem_base;
+
+  StepCfg cfg;
+  cfg.nblk_map = (nkey_map + 63) / 64;
+  cfg.kv_map = in.kv_map_tc + (size_t)s * nT_map * BLK;
+  cfg.kv_map_layer_stride = (size_t)S * nT_map * BLK;
+  cfg.kv_tl_layer_stride = (size_t)S * Th * nT_tl * BLK;
+
+  if (warp == 9) {
+    // ========================================================================================================== loader
+    if (lane == 0) {
+      Loader ld(sm);
+      for (int t = a.t_first; t <= a.t_last; ++t) {
+        const int tl_t = min(t - 1, Th - 1);
+        cfg.nblk_tl = (in.n_key_tl[(size_t)s * Th + tl_t] + 63) / 64;
+        cfg.kv_tl = in.kv_tl_tc + ((size_t)s * Th + tl_t) * nT_tl * BLK;
+        enumerate_step(a, cfg, ld);
+      }
+    }
+  } else if (warp == 8) {
+    // ========================================================================================================== issuer
+    if (lane == 0) {
+      Issuer is(sm, tm0);
+      for (int t = a.t_first; t <= a.t_last; ++t) {
+        const int tl_t = min(t - 1, Th - 1);
+        cfg.nblk_tl = (in.n_key_tl[(size_t)s * Th + tl_t] + 63) / 64;
+        cfg.kv_tl = nullptr;
+        enumerate_step(a, cfg, is);
+      }
+    }
+  } else {
+    // ========================================================================================================== workers
+    const int quad = warp & 3, half = warp >> 2;
+    const int l = quad * 32 + lane;  // TMEM lane
+    const int ag = l & 63, upper = l >> 6;
+    const int c0 = half * 64;
+    const bool live = ag < A;
+    const bool writer = upper == 0 && live;  // the lane that owns global side effects of agent `ag`
+    const size_t ba = (size_t)b * A + (live ? ag : 0), sa = (size_t)s * A + (live ? ag : 0);
+    const uint32_t tm = tm0 + ((uint32_t)(quad * 32) << 16);
+    uint32_t n_mma = 0, n_s = 0, n_o = 0, n_grant = 0, n_ln = 0, n_lp = 0;
+    int n_mark = 0;
+    auto mark = [&]() {
+      if (a.trace && b == 0 && tid == 0 && n_mark < 1000) a.trace[n_mark++] = clock64();
+    };
+    int n_dmark = 0, t_cur = 0;
+    auto dmark = [&](int id) {  // detailed (id, clock) pairs of one warm step, both softmax groups' leaders
+      if (a.trace && b == 0 && (tid == 0 || tid == 128) && t_cur == a.t_first + 3 && n_dmark < 700) {
+        long long* dst = a.trace + 1024 + (tid == 128 ? 1400 : 0) + 2 * n_dmark++;
+        dst[0] = id;
+        dst[1] = clock64();
+      }
+    };
+
+    auto signal_ready = [&]() {  // TMEM operand written / accumulator consumed -> issuer
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.ready);
+    };
+    auto wait_gemm = [&]() {
+      tc::mbar_wait(&sm.mma, n_mma & 1);
+      tc::tc_fence_after();
+      ++n_mma;
+    };
+    auto xs_at = [&](int c) -> float& { return sm.xs[c * MAXA + ag]; };
+    auto load_x = [&](float (&v)[64]) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = xs_at(c0 + i);
+    };
+    auto store_x = [&](const float (&v)[64]) {  // rows a and a + 64 hold the same values: the lower lane writes
+      if (upper == 0) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) xs_at(c0 + i) = v[i];
+      }
+    };
+    auto write_A = [&](uint32_t col, const float (&v)[64]) {  // columns c0 .. c0+63 of a K = 128 operand
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float ph[16], pl[16];
+        tc::split32_packed(*reinterpret_cast<const float(*)[32]>(&v[32 * j]), ph, pl);
+        tc::tmem_st16(tm + col + (c0 + 32 * j) / 2, ph);
+        tc::tmem_st16(tm + col + 64 + (c0 + 32 * j) / 2, pl);
+      }
+    };
+    auto load_acc = [&](uint32_t col, float (&v)[64]) {
+      tc::tmem_ld32(tm + col + c0, *reinterpret_cast<float(*)[32]>(&v[0]));
+      tc::tmem_ld32(tm + col + c0 + 32, *reinterpret_cast<float(*)[32]>(&v[32]));
+      tc::tmem_ld_wait();
+    };
+    // LayerNorm over the 128 columns of a row held by the thread pair (l, half 0 / 1): one exchange of {sum, M2}
+    auto layernorm64 = [&](float (&v)[64], const float* g, const float* bt) {
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) sum += v[i];
+      const float mloc = sum * (1.0f / 64);
+      float m2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float d = v[i] - mloc;
+        m2 = fmaf(d, d, m2);
+      }
+      const int buf = n_ln & 1;
+      ++n_ln;
+      sm.red[buf][half][l] = make_float2(sum, m2);
+      worker_sync();
+      const float2 o = sm.red[buf][half ^ 1][l];
+      const float mean = (sum + o.x) * (1.0f / 128);
+      const float dm_ = (o.x - sum) * (1.0f / 64);  // difference of the two half means
+      const float var = (m2 + o.y + dm_ * dm_ * 32.0f) * (1.0f / 128);  // Chan: + n_a n_b / (n_a + n_b) * delta^2
+      const float rstd = 1.0f / sqrtf(var + LN_EPS);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = (v[i] - mean) * rstd * g[c0 + i] + bt[c0 + i];
+    };
+    // parameter vectors: the set of phase `p` is fetched into registers, committed to lp[n_lp & 1] later in the same phase
+    float4 pf0 = make_float4(0.f, 0.f, 0.f, 0.f), pf1 = pf0;
+    auto fetch_params = [&](int p) {
+      const int o0 = phase_vec(p, warp), o1 = phase_vec(p, warp + 8);
+      if (o0 >= 0) pf0 = __ldg(reinterpret_cast<const float4*>(packed + o0) + lane);
+      if (o1 >= 0) pf1 = __ldg(reinterpret_cast<const float4*>(packed + o1) + lane);
+    };
+    auto commit_params = [&]() {  // into the buffer that the NEXT phase reads
+      float (*dst)[128] = sm.lp[(n_lp + 1) & 1];
+      reinterpret_cast<float4*>(dst[warp])[lane] = pf0;
+      reinterpret_cast<float4*>(dst[warp + 8])[lane] = pf1;
+    };
+    fetch_params(0);
+    {
+      float (*dst)[128] = sm.lp[0];
+      reinterpret_cast<float4*>(dst[warp])[lane] = pf0;
+      reinterpret_cast<float4*>(dst[warp + 8])[lane] = pf1;
+    }
+    worker_sync();
+
+    const float sc = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e): softmax in base 2
+
+#pragma unroll 1
+    for (int t = a.t_first; t <= a.t_last; ++t) {
+      const int tl_t = min(t - 1, Th - 1);
+      const int nkey_tl = in.n_key_tl[(size_t)s * Th + tl_t];
+      t_cur = t;
+      mark();
+      // ---- validity of this step; interaction bypass decision -> issuer / loader ----------------------------------------
+      const bool valid = sm.valid[ag] != 0;
+      const unsigned vm_lo = __ballot_sync(0xffffffffu, sm.valid[lane] != 0);
+      const unsigned vm_hi = __ballot_sync(0xffffffffu, sm.valid[lane + 32] != 0);
+      const unsigned long long vmask = ((unsigned long long)vm_hi << 32) | vm_lo;
+      const int n_valid = __popc(vm_lo) + __popc(vm_hi);
+      if (tid == 0) {
+        *reinterpret_cast<volatile int*>(&sm.n_valid) = n_valid;
+        __threadfence_block();
+        mbar_arrive(&sm.cfg);  // loader and issuer both wait for this phase
+      }
+      // ---- state embedding: get_agent_attr_and_pe + agent_encoder (sc_input.py:142-165, input_pe_encoder.py:41-61) -----------
+      {
+        const int part = tid >> 6;  // features [32 part, 32 part + 32) of agent ag
+        const float4 st = sm.pose[ag];
+        if (part == 0) {
+          float at[12];
+          at[0] = sm.vel[ag].x, at[1] = sm.vel[ag].y, at[2] = st.w, at[3] = sm.yaw_rate[ag], at[4] = sm.acc[ag];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            at[5 + i] = in.agent_size[sa * 3 + i];
+            at[8 + i] = sm.type[ag][i] ? 1.f : 0.f;
+          }
+          at[11] = 0.f;
+          float h[32];
+#pragma unroll
+          for (int o = 0; o < 32; ++o) {
+            float acc = sm.emb_b1[o];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) acc = fmaf(at[k], sm.emb_w1[((k >> 2) * 32 + o) * 4 + (k & 3)], acc);
+            h[o] = fmaxf(acc, 0.f);
+          }
+#pragma unroll 4
+          for (int o = 0; o < 32; ++o) {
+            float acc = sm.emb_b2[o];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc = fmaf(h[k], sm.emb_w2[((k >> 2) * 32 + o) * 4 + (k & 3)], acc);
+            sm.xs[o * MAXA + ag] = valid ? acc : 0.f;
+          }
+        } else {
+#pragma unroll 4
+          for (int i = 0; i < 32; ++i) {
+            const int j = 32 * (part - 1) + i;  // PE element 0..95
+            float v;
+            if (j < 12) v = cosf(st.x * sm.f_xy[2 * j]);
+            else if (j < 24) v = sinf(st.x * sm.f_xy[2 * (j - 12) + 1]);
+            else if (j < 36) v = cosf(st.y * sm.f_xy[2 * (j - 24)]);
+            else if (j < 48) v = sinf(st.y * sm.f_xy[2 * (j - 36) + 1]);
+            else if (j < 72) v = cosf(st.z * sm.f_yaw[2 * (j - 48)]);
+            else v = sinf(st.z * sm.f_yaw[2 * (j - 72) + 1]);
+            sm.xs[(32 + j) * MAXA + ag] = valid ? v : 0.f;
+          }
+        }
+      }
+      mark();
+
+      // ---- 9 pre-LN cross-attention layers ------------------------------------------------------------------------------------
+      const bool bypass = n_valid == 1;
+#pragma unroll 1
+      for (int Lx = 0; Lx < 9; ++Lx) {
+        const int kind = Lx / 3;
+        if (kind == 2 && bypass) break;
+        const int nkey = kind == 0 ? nkey_map : kind == 1 ? nkey_tl : (n_valid > 0 ? MAXA : 0);
+        const int nblk = (nkey + 63) / 64;
+        worker_sync();  // xs / lp of this phase complete
+        dmark(100 + Lx * 10);
+        const float (*lp)[128] = sm.lp[n_lp & 1];
+        {  // next phase's parameters
+          int pn = Lx + 1;
+          if (pn == 6 && bypass) pn = 9;
+          fetch_params(pn);
+        }
+        float v[64];
+        if (nblk > 0) {
+          if (kind == 2) {
+            // K|V of the block input x0 (agent_interaction.py:52: tgt = attn_to_map_aware_feature for all 3 layers)
+            float tg[64];
+            if (Lx == 6) {
+              load_x(tg);
+              if (writer) {
+                float* dst = a.sv.x0 + ba * D + c0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  reinterpret_cast<float4*>(dst)[i] = make_float4(tg[4 * i], tg[4 * i + 1], tg[4 * i + 2], tg[4 * i + 3]);
+              }
+            } else {
+              const float* src = a.sv.x0 + ba * D + c0;  // written by this thread (or its twin lane) at Lx == 6
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float4 q = reinterpret_cast<const float4*>(src)[i];
+                tg[4 * i] = q.x, tg[4 * i + 1] = q.y, tg[4 * i + 2] = q.z, tg[4 * i + 3] = q.w;
+              }
+            }
+            layernorm64(tg, lp[8], lp[9]);
+            write_A(T_A, tg);
+            signal_ready();  // -> Wk (ACC0), Wv (ACC1)
+            wait_gemm();
+            tc::mbar_wait(&sm.grant, n_grant & 1);
+            ++n_grant;
+            unsigned char* blk = sm.ring[*reinterpret_cast<volatile int*>(&sm.kvi_slot)];
+            load_acc(T_ACC0, tg);  // K[ag, c0 .. c0+63]: key row ag of K-block `half`
+            if (upper == 0) {
+#pragma unroll
+              for (int i = 0; i < 64; ++i) tg[i] += lp[10][c0 + i];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                uint4 hi, lo;
+                tc::split8(tg + 8 * c, hi, lo);
+                const uint32_t off = half * 8192 + tc::sw128_off(ag, c);
+                *reinterpret_cast<uint4*>(blk + off) = hi;
+                *reinterpret_cast<uint4*>(blk + 16384 + off) = lo;
+              }
+            }
+            load_acc(T_ACC1, tg);  // V[ag, c0 .. c0+63] -> V^T rows d = c0 + i, key column ag
+            if (upper == 0) {
+#pragma unroll
+              for (int i = 0; i < 64; ++i) {
+                const float val = tg[i] + lp[11][c0 + i];
+                const __nv_bfloat16 h = __float2bfloat16_rn(val);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(val - __bfloat162float(h));
+                const int d = c0 + i;
+                const uint32_t off = tc::sw128_off(d, ag >> 3) + (ag & 7) * 2;
+                *reinterpret_cast<__nv_bfloat16*>(blk + HALF + off) = h;
+                *reinterpret_cast<__nv_bfloat16*>(blk + HALF + 16384 + off) = lo;
+              }
+            }
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.wfill);
+          }
+          load_x(v);
+          layernorm64(v, lp[0], lp[1]);
+          write_A(T_A, v);
+          signal_ready();  // -> Wq
+          dmark(101 + Lx * 10);
+          commit_params();
+          wait_gemm();
+          dmark(102 + Lx * 10);
+          {  // stacked query operand of pass `half`: own head's 32 dims, zeros in the twin head's dims
+            float q[32];
+            tc::tmem_ld32(tm + T_ACC0 + c0 + 32 * upper, q);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) q[i] = (q[i] + lp[2][c0 + 32 * upper + i]) * sc;
+            float ph[16], pl[16], zz[16];
+            tc::split32_packed(q, ph, pl);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) zz[i] = 0.f;
+            tc::tmem_st16(tm + T_A + 32 * half + 16 * upper, ph);
+            tc::tmem_st16(tm + T_A + 64 + 32 * half + 16 * upper, pl);
+            tc::tmem_st16(tm + T_A + 32 * half + 16 * (1 - upper), zz);
+            tc::tmem_st16(tm + T_A + 64 + 32 * half + 16 * (1 - upper), zz);
+          }
+          signal_ready();  // -> QK^T(0, .)
+          dmark(103 + Lx * 10);
+          // ---- online softmax of pass `half` over the key blocks (lazy rescaling) -----------------------------------------------
+          float m_ref = -INFINITY, l_sum = 0.f;
+          const uint32_t sbase = tm + T_ACC0 + 64 * half;
+          const uint32_t obase = tm + T_O + 64 * half + 32 * upper;
+#pragma unroll 1
+          for (int jb = 0; jb < nblk; ++jb) {
+            tc::mbar_wait(&sm.s[half], n_s & 1);
+            ++n_s;
+            tc::tc_fence_after();
+            if (Lx == 0 && jb < 8) dmark(1000 + jb * 4);
+            float sv_[64];
+            tc::tmem_ld32(sbase, *reinterpret_cast<float(*)[32]>(&sv_[0]));
+            tc::tmem_ld32(sbase + 32, *reinterpret_cast<float(*)[32]>(&sv_[32]));
+            tc::tmem_ld_wait();
+            if (Lx == 0 && jb < 8) dmark(1001 + jb * 4);
+            if (kind == 2) {
+              const unsigned long long en = vmask & ~(1ull << ag);
+#pragma unroll
+              for (int j = 0; j < 64; ++j)
+                if (!((en >> j) & 1ull)) sv_[j] = -INFINITY;
+            } else if (jb * 64 + 64 > nkey) {
+#pragma unroll
+              for (int j = 0; j < 64; ++j)
+                if (jb * 64 + j >= nkey) sv_[j] = -INFINITY;
+            }
+            float mx = sv_[0];
+#pragma unroll
+            for (int j = 1; j < 64; ++j) mx = fmaxf(mx, sv_[j]);
+            float alpha = 1.f;
+            bool resc = false;
+            if (mx > m_ref + 8.0f) {
+              alpha = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - mx);
+              m_ref = mx;
+              l_sum *= alpha;
+              resc = jb > 0;
+            }
+            const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+            float psum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+              sv_[j] = ex2_approx(sv_[j] + neg_m);
+              psum += sv_[j];
+            }
+            l_sum += psum;
+            {
+              float ph[16], pl[16];
+              tc::split32_packed(*reinterpret_cast<const float(*)[32]>(&sv_[0]), ph, pl);
+              tc::tmem_st16(sbase, ph);
+              tc::tmem_st16(sbase + 32, pl);
+              tc::split32_packed(*reinterpret_cast<const float(*)[32]>(&sv_[32]), ph, pl);
+              tc::tmem_st16(sbase + 16, ph);
+              tc::tmem_st16(sbase + 48, pl);
+            }
+            if (__any_sync(0xffffffffu, resc)) {  // PV(jb-1) is complete (its commit precedes QK^T(jb)'s): O is quiescent
+              float o[32];
+              tc::tmem_ld32(obase, o);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] *= alpha;
+              tc::tmem_st32(obase, o);
+            }
+            if (Lx == 0 && jb < 8) dmark(1002 + jb * 4);
+            tc::tmem_st_wait();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.p[half]);  // -> PV(jb, half), QK^T(jb+1, half)
+            if (Lx == 0 && jb < 8) dmark(1003 + jb * 4);
+          }
+          dmark(104 + Lx * 10);
+          {
+            tc::mbar_wait(&sm.o[half], n_o & 1);
+            ++n_o;
+            tc::tc_fence_after();
+            float o[32];
+            tc::tmem_ld32(obase, o);
+            tc::tmem_ld_wait();
+            const float inv = l_sum > 0.f ? 1.0f / l_sum : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sm.xo[(c0 + 32 * upper + j) * MAXA + ag] = o[j] * inv;
+          }
+          worker_sync();
+#pragma unroll
+          for (int i = 0; i < 64; ++i) v[i] = sm.xo[(c0 + i) * MAXA + ag];
+          write_A(T_A, v);
+          signal_ready();  // -> Wo
+          dmark(105 + Lx * 10);
+          wait_gemm();
+          dmark(106 + Lx * 10);
+          load_acc(T_ACC0, v);
+          {
+            float x[64];
+            load_x(x);
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] += x[i] + lp[3][c0 + i];
+          }
+          store_x(v);
+        } else {
+          load_x(v);
+          commit_params();
+        }
+        {
+          float x2[64];
+#pragma unroll
+          for (int i = 0; i < 64; ++i) x2[i] = v[i];
+          layernorm64(x2, lp[4], lp[5]);
+          write_A(T_A, x2);
+        }
+        signal_ready();  // -> W1
+        dmark(107 + Lx * 10);
+        wait_gemm();
+        dmark(108 + Lx * 10);
+        {
+          float h1[64];
+          load_acc(T_ACC0, h1);
+#pragma unroll
+          for (int i = 0; i < 64; ++i) h1[i] = fmaxf(h1[i] + lp[6][c0 + i], 0.f);
+          write_A(T_A, h1);
+        }
+        signal_ready();  // -> W2
+        dmark(109 + Lx * 10);
+        wait_gemm();
+        dmark(190 + Lx);
+        {
+          float y[64];
+          load_acc(T_ACC0, y);
+          float x[64];
+          load_x(x);
+#pragma unroll
+          for (int i = 0; i < 64; ++i) y[i] = valid ? x[i] + y[i] + lp[7][c0 + i] : 0.f;
+          store_x(y);
+        }
+        ++n_lp;
+      }
+      mark();
+
+      // ---- agent_temporal: 3-layer GRU, one time step (agent_temporal.py:147-153) -------------------------------------------------
+#pragma unroll 1
+      for (int L = 0; L < 3; ++L) {
+        worker_sync();
+        const float (*lp)[128] = sm.lp[n_lp & 1];
+        dmark(200 + L * 10);
+        fetch_params(10 + L);  // 10, 11 = GRU layers 1, 2; 12 = add_goal
+        float* hid = a.sv.hidden + ((size_t)L * BA + ba) * D + c0;
+        {
+          float x[64];
+          load_x(x);
+          write_A(T_A, x);
+          if (live) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float4 q = reinterpret_cast<const float4*>(hid)[i];
+              x[4 * i] = q.x, x[4 * i + 1] = q.y, x[4 * i + 2] = q.z, x[4 * i + 3] = q.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) x[i] = 0.f;
+          }
+          write_A(T_A2, x);
+        }
+        signal_ready();  // -> r (ACC0), W_hn h (ACC1)
+        dmark(201 + L * 10);
+        commit_params();
+        wait_gemm();
+        dmark(202 + L * 10);
+        float rh[64];
+        {
+          float r[64];
+          load_acc(T_ACC0, r);
+          load_acc(T_ACC1, rh);
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const float rg = sigmoidf_(r[i] + lp[0][c0 + i] + lp[3][c0 + i]);
+            rh[i] = rg * (rh[i] + lp[5][c0 + i]);
+          }
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.ready);  // accumulators consumed -> z (ACC0), W_in x (ACC1)
+        dmark(203 + L * 10);
+        wait_gemm();
+        dmark(204 + L * 10);
+#pragma unroll 1
+        for (int jj = 0; jj < 2; ++jj) {
+          float z[32], n[32];
+          tc::tmem_ld32(tm + T_ACC0 + c0 + 32 * jj, z);
+          tc::tmem_ld32(tm + T_ACC1 + c0 + 32 * jj, n);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 hp4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) hp4 = reinterpret_cast<const float4*>(hid)[8 * jj + i];
+            const float hp_[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
+            float hn_[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = 32 * jj + 4 * i + e;
+              const float zg = sigmoidf_(z[4 * i + e] + lp[1][c0 + c] + lp[4][c0 + c]);
+              const float ng = tanhf(n[4 * i + e] + lp[2][c0 + c] + rh[c]);
+              hn_[e] = (1.0f - zg) * ng + zg * hp_[e];
+            }
+            // h[:, ~valid] = 0; the next GRU layer sees the unmasked output, after the last layer x[~valid] = 0
+            if (writer)
+              reinterpret_cast<float4*>(hid)[8 * jj + i] = valid ? make_float4(hn_[0], hn_[1], hn_[2], hn_[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (upper == 0) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) xs_at(c0 + 32 * jj + 4 * i + e) = (L == 2 && !valid) ? 0.f : hn_[e];
+            }
+          }
+        }
+        ++n_lp;
+      }
+      mark();
+
+      // ---- add_goal, add_latent (add_latent_goal.py:57-77, mode cat, res_add) ---------------------------------------------------------
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j) {
+        worker_sync();
+        const float (*lp)[128] = sm.lp[n_lp & 1];
+        fetch_params(13 + j);  // 13 = add_latent, 14 = head
+        const bool zv = j == 0 ? (sm.goal_valid[ag] != 0) : valid;
+        const float* zin = (j == 0 ? a.sv.goal_in : a.sv.latent_in) + ba * D + c0;
+        float x[64];
+        load_x(x);
+        write_A(T_A, x);
+        {
+          float z[64];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live && zv) q = __ldg(reinterpret_cast<const float4*>(zin) + i);
+            z[4 * i] = fmaxf(q.x, 0.f), z[4 * i + 1] = fmaxf(q.y, 0.f), z[4 * i + 2] = fmaxf(q.z, 0.f), z[4 * i + 3] = fmaxf(q.w, 0.f);
+          }
+          write_A(T_A2, z);
+        }
+        signal_ready();
+        commit_params();
+        wait_gemm();
+        {
+          float h1[64];
+          load_acc(T_ACC0, h1);
+#pragma unroll
+          for (int i = 0; i < 64; ++i) h1[i] = fmaxf(h1[i] + lp[0][c0 + i], 0.f);
+          write_A(T_A, h1);
+        }
+        signal_ready();
+        wait_gemm();
+        {
+          float h2[64];
+          load_acc(T_ACC0, h2);
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const float hz = fmaxf(h2[i] + lp[1][c0 + i], 0.f);
+            x[i] = valid ? (zv ? hz : 0.f) + x[i] : 0.f;
+          }
+          store_x(x);
+        }
+        ++n_lp;
+      }
+      // ---- action head (action_head.py:70-87): per-type MLP 128 -> 128 -> 2, masked by type & valid, summed -------------------------------
+      {
+        worker_sync();
+        const float (*lp)[128] = sm.lp[n_lp & 1];
+        fetch_params(0);
+        float x[64];
+        load_x(x);
+        write_A(T_A, x);
+        signal_ready();
+        if (a.out.trace_policy_feature && writer) {
+          float* dst = a.out.trace_policy_feature + ((ba * T) + (t - 1)) * D + c0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+        }
+        commit_params();
+        wait_gemm();
+        float m0 = 0.f, m1 = 0.f;
+#pragma unroll 1
+        for (int c3 = 0; c3 < 3; ++c3) {
+          float hdn[64];
+          load_acc(128 * c3, hdn);
+          if (sm.type[ag][c3] && valid) {
+            const float* w2 = &lp[3 + 2 * c3][0];  // Wt4[32][2][4]: (k, d) at ((k >> 2) * 2 + d) * 4 + (k & 3); 256 contiguous floats
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+              const float hv = fmaxf(hdn[i] + lp[c3][c0 + i], 0.f);
+              const int k = c0 + i;
+              s0 = fmaf(hv, w2[((k >> 2) * 2 + 0) * 4 + (k & 3)], s0);
+              s1 = fmaf(hv, w2[((k >> 2) * 2 + 1) * 4 + (k & 3)], s1);
+            }
+            m0 += s0;
+            m1 += s1;
+          }
+        }
+        if (upper == 0) {
+          sm.mean_part[half][ag][0] = m0;
+          sm.mean_part[half][ag][1] = m1;
+        }
+        ++n_lp;
+        worker_sync();
+      }
+      mark();
+
+      dmark(400);
+      // ---- per-agent tail: dynamics, override, rule checks, kill, goal_valid, reward, outputs ----------------------------------------------
+      if (half == 0 && writer) {
+        const bool ty0 = sm.type[ag][0], ty1 = sm.type[ag][1], ty2 = sm.type[ag][2];
+        float mean0 = sm.mean_part[0][ag][0] + sm.mean_part[1][ag][0], mean1 = sm.mean_part[0][ag][1] + sm.mean_part[1][ag][1];
+        if (valid) {
+          if (ty0) mean0 += __ldg(packed + tbw::action_head_mlp_mean_0_fc_layers_2_bias), mean1 += __ldg(packed + tbw::action_head_mlp_mean_0_fc_layers_2_bias + 1);
+          if (ty1) mean0 += __ldg(packed + tbw::action_head_mlp_mean_1_fc_layers_2_bias), mean1 += __ldg(packed + tbw::action_head_mlp_mean_1_fc_layers_2_bias + 1);
+          if (ty2) mean0 += __ldg(packed + tbw::action_head_mlp_mean_2_fc_layers_2_bias), mean1 += __ldg(packed + tbw::action_head_mlp_mean_2_fc_layers_2_bias + 1);
+        }
+        // DiagGaussian log-prob of the deterministic sample (= mean), dynamics.py:77-80
+        float logp = 0.f;
+        if (valid) {
+          for (int d = 0; d < 2; ++d) {
+            float ls = 0.f;
+            if (ty0) ls += __ldg(packed + tbw::action_head_log_std_0 + d);
+            if (ty1) ls += __ldg(packed + tbw::action_head_log_std_1 + d);
+            if (ty2) ls += __ldg(packed + tbw::action_head_log_std_2 + d);
+            logp += -logf(expf(ls)) - 0.91893853320467267f;
+          }
+        }
+        // MultiPathPP.process_action / update (dynamics.py:187-228); type order of the parameter tuples: veh, ped, cyc
+        const float max_acc = (ty0 ? 5.0f : 0.f) + (ty1 ? 7.0f : 0.f) + (ty2 ? 6.0f : 0.f);
+        const float max_yr = (ty0 ? 1.5f : 0.f) + (ty1 ? 7.0f : 0.f) + (ty2 ? 3.0f : 0.f);
+        const float a_acc = valid ? tanhf(mean0) * max_acc : 0.f;
+        const float a_yr = valid ? tanhf(mean1) * max_yr : 0.f;
+        const float4 st = sm.pose[ag];
+        const float v_t = st.w + 0.05f * a_acc, th_t = st.z + 0.05f * a_yr;
+        const bool has_type = ty0 || ty1 || ty2;
+        float4 pred = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && has_type) {
+          pred.x = st.x + 0.1f * (v_t * cosf(th_t));
+          pred.y = st.y + 0.1f * (v_t * sinf(th_t));
+          pred.z = st.z + 0.1f * a_yr;
+          pred.w = st.w + 0.1f * a_acc;
+        }
+        const size_t o = ba * T + (t - 1);
+        *reinterpret_cast<float4*>(a.out.preds + o * 4) = pred;
+        a.out.valid[o] = valid;
+        a.out.action_log_probs[o] = logp;
+        a.out.latent_log_probs[o] = in.latent_logp[ba];
+        if (a.out.trace_action_mean) {
+          a.out.trace_action_mean[o * 2] = mean0;
+          a.out.trace_action_mean[o * 2 + 1] = mean1;
+        }
+        // Dynamics.override_states (dynamics.py:121-149)
+        const bool has_gt = t < Tg;
+        const size_t g = ((size_t)s * Tg + (has_gt ? t : 0)) * A + ag;
+        const bool ovr = has_gt && in.tf_mask[g] != 0;
+        const bool gt_valid = has_gt && in.gt_valid[g] != 0;
+        bool killed = sm.killed[ag] != 0;
+        const bool m = ovr && !killed;
+        bool nvalid = valid || m;
+        float4 ns = pred;
+        float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_gt) gs = make_float4(in.gt_pos[g * 2], in.gt_pos[g * 2 + 1], in.gt_yaw[g], in.gt_spd[g]);
+        if (m) {
+          ns = gs;
+          sm.vel[ag] = make_float2(in.gt_vel[g * 2], in.gt_vel[g * 2 + 1]);
+          sm.acc[ag] = in.gt_acc[g];
+          sm.yaw_rate[ag] = in.gt_yaw_rate[g];
+        }
+        a.out.override_masks[o] = ovr;
+        // TrafficRuleChecker.check, always-on subset (traffic_rule_checker.py:101-119,338-410,423-424,474-496)
+        const float* mb = in.map_boundary + (size_t)s * 4;
+        const bool out_t = nvalid && (ns.x > mb[1] || ns.x < mb[0] || ns.y > mb[3] || ns.y < mb[2]);
+        bool outside = sm.sticky[0][ag] != 0, goal_r = sm.sticky[1][ag] != 0, dest_r = sm.sticky[2][ag] != 0;
+        outside |= out_t;
+        bool goal_t = false;
+        if (in.goal_gt) {
+          const float* gg = in.goal_gt + sa * 4;
+          const float dx = ns.x - gg[0], dy = ns.y - gg[1];
+          const bool pos_ok = sqrtf(dx * dx + dy * dy) < in.agent_size[sa * 3] * 8.0f;
+          // cast_rad (transform_utils.py:10-12): (a + pi) % (2 pi) - pi with Python's sign-of-divisor modulo
+          const float PI_F = 3.14159265358979323846f, TWO_PI_F = 6.28318530717958647692f;
+          float w = fmodf(ns.z - gg[2] + PI_F, TWO_PI_F);
+          if (w < 0.f) w += TWO_PI_F;
+          const bool rot_ok = fabsf(w - PI_F) < 0.26179938779914943654f;
+          goal_t = pos_ok && rot_ok && nvalid && !goal_r;
+        }
+        goal_r |= goal_t;
+        long dst = in.dest[ba];
+        dst = dst < 0 ? 0 : (dst >= dm.n_pl ? dm.n_pl - 1 : dst);
+        const size_t dp = (size_t)s * dm.n_pl + dst;
+        const uint8_t* dtype = in.map_type + dp * TB_PL_TYPE;
+        const bool lane_t = dtype[0] || dtype[1] || dtype[2] || dtype[3], edge_t = dtype[4] != 0;
+        const float thresh = 50.0f * (1.0f - (edge_t ? 1.0f : 0.f) * 0.8f);
+        bool pos_reached = false, rot_reached = false;
+        const float hx = cosf(ns.z), hy = sinf(ns.z);
+        for (int n = 0; n < TB_PL_NODE; ++n) {
+          const size_t nd = dp * TB_PL_NODE + n;
+          if (!in.map_valid[nd]) continue;
+          const float dx = ns.x - in.map_pos[nd * 2], dy = ns.y - in.map_pos[nd * 2 + 1];
+          pos_reached |= sqrtf(dx * dx + dy * dy) < thresh;
+          const float ux = in.map_dir[nd * 2], uy = in.map_dir[nd * 2 + 1];
+          const float nrm = sqrtf(ux * ux + uy * uy);
+          rot_reached |= (hx * (ux / nrm) + hy * (uy / nrm)) > 0.86602540378443864676f;  // NaN (zero-length dir) compares false
+        }
+        const bool dest_t = !dest_r && nvalid && ((lane_t && pos_reached && rot_reached) || (edge_t && pos_reached));
+        dest_r |= dest_t;
+        const size_t vs = BA * T;
+        a.out.violations[0 * vs + o] = outside;
+        a.out.violations[1 * vs + o] = out_t;
+        a.out.violations[2 * vs + o] = goal_r;
+        a.out.violations[3 * vs + o] = goal_t;
+        a.out.violations[4 * vs + o] = dest_r;
+        a.out.violations[5 * vs + o] = dest_t;
+        // Dynamics.kill (dynamics.py:151-167): outside_map_this_step & ~gt_valid
+        const bool kill = out_t && !gt_valid;
+        killed |= kill;
+        nvalid = nvalid && !kill;
+        // disable_goal_reached (goal_manager.py:155-161)
+        const bool gv = sm.goal_valid[ag] && nvalid && !dest_r;
+        // DifferentiableReward.get, imitation part (rewards.py:117-131)
+        float reward = 0.f;
+        bool rv = valid;
+        if (has_gt) {
+          rv = valid && gt_valid;
+          if (rv) {
+            const float e_pos = smooth_l1(gs.x - pred.x) + smooth_l1(gs.y - pred.y);
+            const float e_rot = 0.5f * (1.0f - cosf(gs.z - pred.z));
+            const float e_spd = smooth_l1(gs.w - pred.w);
+            reward = 0.0f - (0.1f * e_pos + 10.0f * e_rot + 0.1f * e_spd);
+          }
+        }
+        a.out.diffbar_rewards[o] = reward;
+        a.out.diffbar_rewards_valid[o] = rv;
+        // state for the next step
+        sm.pose[ag] = ns;
+        sm.valid[ag] = nvalid;
+        sm.killed[ag] = killed;
+        sm.goal_valid[ag] = gv;
+        sm.sticky[0][ag] = outside;
+        sm.sticky[1][ag] = goal_r;
+        sm.sticky[2][ag] = dest_r;
+      }
+      dmark(401);
+      worker_sync();
+      dmark(402);
+    }
+    mark();
+    // ---- simulation state back to global memory (chunked stepping, final-state outputs) -------------------------------------------
+    if (half == 0 && writer) {
+      *reinterpret_cast<float4*>(a.sv.agent_state + ba * 4) = sm.pose[ag];
+      a.sv.vel[ba * 2] = sm.vel[ag].x;
+      a.sv.vel[ba * 2 + 1] = sm.vel[ag].y;
+      a.sv.acc[ba] = sm.acc[ag];
+      a.sv.yaw_rate[ba] = sm.yaw_rate[ag];
+      a.sv.valid[(size_t)((a.t_last + 1) & 1) * BA + ba] = sm.valid[ag];
+      a.sv.killed[ba] = sm.killed[ag];
+      a.sv.goal_valid[ba] = sm.goal_valid[ag];
+      for (int i = 0; i < 3; ++i) a.sv.sticky[(size_t)i * BA + ba] = sm.sticky[i][ag];
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(sm.tmem_base, 512);
+}
+
+}  // namespace pr
+}  // namespace tb
+
+using namespace tb;
+
+bool tb::rollout_tc_supported(const TbDims& d, const TbRolloutIn& in) {
+  if (!in.kv_map_tc || !in.kv_tl_tc || !in.n_key_map || !in.n_key_tl) return false;
+  return d.n_agent <= pr::MAXA;
+}
+
+int tb::launch_rollout_tc(const TbDims& d, const TbRolloutIn& in, const float* packed, const StateView& sv, const TbRolloutOut& out,
+                          int t_first, int t_last, cudaStream_t st) {
+  static bool attr_set = false;
+  const int smem = (int)sizeof(pr::Smem) + 1024;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(pr::k_rollout_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return TB_ERR_LAUNCH;
+    attr_set = true;
+  }
+  pr::Args a{d, in, packed, tc_blob(packed), sv, out, t_first, t_last, g_debug_trace};
+  pr::k_rollout_tc<<<d.n_scene * d.n_mode, pr::THREADS, smem, st>>>(a);
+  count_launch();
+  return launch_status();
+}

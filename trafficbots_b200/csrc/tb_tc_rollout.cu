@@ -117,6 +117,7 @@ struct FrontArgs {
   const unsigned char* tcw;
   StateView sv;
   int t;
+  long long* trace;  // development aid: clock64 marks of CTA 0 / worker thread 0 (NULL = off)
 };
 
 // MUFU.EX2 (max relative error 2^-22), without exp2f's denormal-range scaling
@@ -317,6 +318,11 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_step_front_tc(FrontArgs a)
     const size_t ba = (size_t)b * A + (live ? r : 0), sa = (size_t)s * A + (live ? r : 0);
     const uint32_t tm = tm0 + ((uint32_t)(quad * 32) << 16);
     uint32_t n_mma = 0, n_s[2] = {0, 0}, n_pv = 0;
+    int n_mark = 0;
+    auto mark = [&]() {
+      if (a.trace && b == 0 && tid == 0 && n_mark < 500) a.trace[n_mark++] = clock64();
+    };
+    mark();
 
     // operand written (tcgen05.st) -> tell the issuer
     auto signal_ready = [&]() {
@@ -433,6 +439,7 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_step_front_tc(FrontArgs a)
       if (half == 0) sm.row_valid[r] = valid;
     }
     worker_sync();
+    mark();
 
     // ---- one pre-LN cross-attention layer against `nkey` compacted keys ---------------------------------------------------
     auto xlayer = [&](const float* __restrict__ lw, int nkey) {
@@ -441,13 +448,16 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_step_front_tc(FrontArgs a)
       layernorm64(v, lw + tfl::NORM1_W, lw + tfl::NORM1_B);
       write_A(v);
       signal_ready();  // -> Wq
+      mark();
       wait_gemm();
+      mark();
       load_acc(T_S0, v);
 #pragma unroll
       for (int i = 0; i < 64; ++i) v[i] += __ldg(lw + tfl::IN_B + c0 + i);
       write_A(v);
       const int n_sub = (nkey + SUB_KEYS - 1) / SUB_KEYS;
       if (n_sub > 0) signal_ready();  // Q ready -> QK^T(0), QK^T(1)
+      mark();
 
       const float sc = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e): softmax in base 2
       float m_ref[2] = {-INFINITY, -INFINITY}, l_sum[2] = {0.f, 0.f};
@@ -457,6 +467,7 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_step_front_tc(FrontArgs a)
         tc::mbar_wait(&sm.bar_s[bsel], n_s[bsel] & 1);
         tc::tc_fence_after();
         ++n_s[bsel];
+        if (u < 8) mark();
         const uint32_t sbase = tm + (bsel ? T_S1 : T_S0);
         const int key0 = u * SUB_KEYS;
         bool need_rescale = false;
@@ -496,6 +507,7 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_step_front_tc(FrontArgs a)
           tc::tmem_st16(sbase + 32 * h, ph);
           tc::tmem_st16(sbase + 32 * h + 16, pl);
         }
+        if (u < 8) mark();
         if (u > 0) {  // PV(u-1) must be complete before O is rescaled
           tc::mbar_wait(&sm.bar_pv, n_pv & 1);
           tc::tc_fence_after();
@@ -513,8 +525,11 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_step_front_tc(FrontArgs a)
             tc::tmem_st32(tm + T_O + 32 * h, o);
           }
         }
+        if (u < 8) mark();
         signal_ready();  // -> PV(u), QK^T(u+2)
+        if (u < 8) mark();
       }
+      mark();
       {
         float o[64];
         if (n_sub > 0) {
@@ -535,7 +550,9 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_step_front_tc(FrontArgs a)
         write_A(o);
       }
       signal_ready();  // -> Wo
+      mark();
       wait_gemm();
+      mark();
       load_acc(T_S0, v);
       {
         float x[64];
@@ -550,19 +567,24 @@ __global__ void __launch_bounds__(FRONT_THREADS, 1) k_step_front_tc(FrontArgs a)
         write_A(x);
       }
       signal_ready();  // -> W1
+      mark();
       wait_gemm();
+      mark();
       load_acc(T_S0, v);
 #pragma unroll
       for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i] + __ldg(lw + tfl::L1_B + c0 + i), 0.f);
       write_A(v);
       signal_ready();  // -> W2
+      mark();
       wait_gemm();
+      mark();
       load_acc(T_S0, v);
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
         const float y = xs_at(c0 + i) + v[i] + __ldg(lw + tfl::L2_B + c0 + i);
         xs_at(c0 + i) = valid ? y : 0.f;
       }
+      mark();
     };
 
 #pragma unroll 1
@@ -630,6 +652,9 @@ int tb::launch_pack_kv_tc(const float* kv, const uint8_t* key_valid, int n_set, 
   return launch_status();
 }
 
+long long* tb::g_debug_trace = nullptr;
+extern "C" void tb_debug_set_trace(void* dev_ptr) { tb::g_debug_trace = reinterpret_cast<long long*>(dev_ptr); }
+
 bool tb::front_tc_supported(const TbDims& d, const TbRolloutIn& in) {
   if (!in.kv_map_tc || !in.kv_tl_tc || !in.n_key_map || !in.n_key_tl) return false;
   if (d.n_agent > 128) return false;
@@ -645,7 +670,7 @@ int tb::launch_step_front_tc(const TbDims& d, const TbRolloutIn& in, const float
     cudaFuncSetAttribute(k_step_front_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_set = true;
   }
-  FrontArgs a{d, in, packed, tc_blob(packed), sv, t};
+  FrontArgs a{d, in, packed, tc_blob(packed), sv, t, g_debug_trace};
   k_step_front_tc<<<d.n_scene * d.n_mode, FRONT_THREADS, smem, st>>>(a);
   count_launch();
   return launch_status();

@@ -245,32 +245,28 @@ class Engine:
         self.last_t = t
         return t
 
-    def profile_rollout(self, *args, n_mode: int = 1, n_step: int = 90, out=None, **kw):
-        """Instrumented replay of `rollout` with the two halves of every step launched separately and bracketed by CUDA
-        events on the launching stream; returns (avg front-half ms, avg back-half ms).  Measurement aid for bench.py."""
+    def profile_rollout(self, *args, n_mode: int = 1, n_step: int = 90, out=None, repeats: int = 3, **kw):
+        """Times the decode loop alone (`tb_rollout_steps(1..n_step)`: ONE launch of the persistent tensor-core kernel when
+        n_agent <= 64) with CUDA events on the launching stream; `tb_rollout_init` runs outside the timed region.
+        Returns the average ms per call.  Measurement aid for bench.py."""
         dims, rin = self._rollout_structs(*args, n_mode, n_step, **kw)
         B, A = dims.n_scene * dims.n_mode, dims.n_agent
         if out is None:
             out = self.alloc_outputs(B, A, n_step)
         state = self._ensure_state(dims)
         rout = self._out_struct(out)
-        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_step)]
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(repeats)]
         with torch.cuda.device(self.device):
             st = nt.current_stream_ptr()
-            nt.check(self.lib.tb_rollout_init(C.byref(dims), C.byref(rin), self.packed.data_ptr(), state.data_ptr(), st), "init")
-            for t in range(1, n_step + 1):
-                e = ev[t - 1]
-                e[0].record()
-                nt.check(self.lib.tb_step_front(C.byref(dims), C.byref(rin), self.packed.data_ptr(), state.data_ptr(), t, st), "front")
-                e[1].record()
-                nt.check(self.lib.tb_step_back(C.byref(dims), C.byref(rin), self.packed.data_ptr(), state.data_ptr(),
-                                               C.byref(rout), t, st), "back")
-                e[2].record()
+            for e0, e1 in ev:
+                nt.check(self.lib.tb_rollout_init(C.byref(dims), C.byref(rin), self.packed.data_ptr(), state.data_ptr(), st), "init")
+                e0.record()
+                nt.check(self.lib.tb_rollout_steps(C.byref(dims), C.byref(rin), self.packed.data_ptr(), state.data_ptr(),
+                                                   C.byref(rout), 1, n_step, st), "steps")
+                e1.record()
             torch.cuda.current_stream().synchronize()
         self.last_t = n_step
-        front = sum(e[0].elapsed_time(e[1]) for e in ev) / n_step
-        back = sum(e[1].elapsed_time(e[2]) for e in ev) / n_step
-        return front, back
+        return sum(e0.elapsed_time(e1) for e0, e1 in ev) / repeats
 
     def _finish(self, out: Dict[str, Tensor]) -> Dict[str, Tensor]:
         res = {k: v for k, v in out.items() if not k.startswith("_")}
