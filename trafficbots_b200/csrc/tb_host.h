@@ -36,6 +36,7 @@ struct StateView {
   float* kv_int;       // [3,B,A,256] interaction K|V of the current step
   float* goal_in;      // [B,A,128]  add_goal.mlp_in(goal_feature) before mask/ReLU (loop invariant)
   float* latent_in;    // [B,A,128]  add_latent.mlp_in(latent_sample) before mask/ReLU (loop invariant)
+  float4* dest_nodes;  // [B,A,20]   destination polyline nodes (x, y, unit direction), invalid nodes at 1e30
 };
 
 StateView state_view(const TbDims& d, void* base);

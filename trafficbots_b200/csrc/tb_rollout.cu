@@ -16,7 +16,7 @@ static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct StateLayout {
   size_t off[TB_STATE_N_FIELD];
-  size_t x0, kv_int, goal_in, latent_in, total;
+  size_t x0, kv_int, goal_in, latent_in, dest_nodes, total;
 };
 
 static StateLayout state_layout(const TbDims& d) {
@@ -41,6 +41,7 @@ static StateLayout state_layout(const TbDims& d) {
   L.kv_int = put(3 * BA * 256 * sizeof(float));
   L.goal_in = put(BA * D * sizeof(float));
   L.latent_in = put(BA * D * sizeof(float));
+  L.dest_nodes = put(BA * TB_PL_NODE * 4 * sizeof(float));
   L.total = o;
   return L;
 }
@@ -62,6 +63,7 @@ StateView state_view(const TbDims& d, void* base) {
   v.kv_int = reinterpret_cast<float*>(p + L.kv_int);
   v.goal_in = reinterpret_cast<float*>(p + L.goal_in);
   v.latent_in = reinterpret_cast<float*>(p + L.latent_in);
+  v.dest_nodes = reinterpret_cast<float4*>(p + L.dest_nodes);
   return v;
 }
 
@@ -116,6 +118,21 @@ __global__ void __launch_bounds__(NT) k_rollout_init(TbDims dm, TbRolloutIn in, 
     sv.sticky[ba] = 0;
     sv.sticky[BA + ba] = 0;
     sv.sticky[2 * BA + ba] = 0;
+    // destination polyline nodes (traffic_rule_checker.py:82-98) as (x, y, unit dir): loop-invariant operand of the
+    // dest_reached check; invalid nodes are placed at 1e30 with a zero direction, so they never test true
+    long dst = in.dest[ba];
+    dst = dst < 0 ? 0 : (dst >= dm.n_pl ? dm.n_pl - 1 : dst);
+    const size_t dp = (size_t)s * dm.n_pl + dst;
+    for (int n = 0; n < TB_PL_NODE; ++n) {
+      const size_t nd = dp * TB_PL_NODE + n;
+      float4 o = make_float4(1e30f, 1e30f, 0.f, 0.f);
+      if (in.map_valid[nd]) {
+        const float ux = in.map_dir[nd * 2], uy = in.map_dir[nd * 2 + 1];
+        const float nrm = sqrtf(ux * ux + uy * uy);
+        o = make_float4(in.map_pos[nd * 2], in.map_pos[nd * 2 + 1], ux / nrm, uy / nrm);  // zero-length dir -> NaN (compares false)
+      }
+      sv.dest_nodes[ba * TB_PL_NODE + n] = o;
+    }
   }
   // GRU hidden starts at zero (agent_temporal.py:131, traffic_bots.py:159)
   for (int L = 0; L < 3; ++L)

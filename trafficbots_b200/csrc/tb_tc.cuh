@@ -25,6 +25,22 @@ constexpr int KB_BYTES_128 = 16384; // one K-block (64 bf16 wide) of a 128-row t
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// ---- warp-uniform issue ---------------------------------------------------------------------------------------------
+// tcgen05.mma / tcgen05.commit take their descriptors and addresses in UNIFORM registers.  If the issuing code runs under
+// `if (threadIdx.x == 0)` the compiler cannot prove the operands warp-uniform and wraps every instruction in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~14 instructions, ~90 cycles per MMA).  Instead the whole warp runs the issue
+// code on values marked uniform with `uniform()` and one elected lane executes the instruction: 2 instructions per MMA.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ---- mbarrier -----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

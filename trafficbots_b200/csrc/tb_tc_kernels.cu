@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(128, 1) k_map_polyline_tc(TbDims dm, TbSceneIn
   extern __shared__ unsigned char smem_raw[];
   MapTcSmem& sm = *reinterpret_cast<MapTcSmem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
   constexpr int N = TB_PL_NODE;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tc::uniform(tid >> 5);
   const long n_pl_total = (long)dm.n_scene * dm.n_pl;
 
   if (tid == 0) {
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(128, 1) k_map_polyline_tc(TbDims dm, TbSceneIn
   tc::tc_fence_after();
   const uint32_t tm = sm.tmem_base + ((uint32_t)(warp * 32) << 16);  // this warp's lane quadrant
   const uint32_t TX = tm, TQ = tm + 128, TK = tm + 256, TV = tm + 384;
-  const uint32_t tm0 = sm.tmem_base;
+  const uint32_t tm0 = (uint32_t)tc::uniform((int)sm.tmem_base);
   const uint32_t idesc = tc::make_idesc_bf16(128, 128);
   const uint32_t ah = tc::smem_u32(sm.a_hi), al = tc::smem_u32(sm.a_lo);
 
@@ -188,25 +188,30 @@ __global__ void __launch_bounds__(128, 1) k_map_polyline_tc(TbDims dm, TbSceneIn
       ++wp.loaded;
     }
   };
-  // issue the three bf16x3 MMAs of weight stage `s` into TMEM columns `dst` (thread 0 only)
+  // issue the three bf16x3 MMAs of weight stage `s` into TMEM columns `dst`: warp 0 runs this converged (operands stay
+  // warp-uniform, see tc::elect_one), one elected lane issues
   auto issue = [&](uint32_t s, uint32_t dst_col) {
     const uint32_t buf = s & 1;
     tc::mbar_wait(&sm.bar_w[buf], (s >> 1) & 1);
     tc::tc_fence_after();
     const uint32_t wh = tc::smem_u32(sm.w[buf]), wl = wh + 2 * tc::KB_BYTES_128;
-    tc::mma_tile(tm0 + dst_col, ah, tc::KB_BYTES_128, wh, tc::KB_BYTES_128, 128, idesc, false);
-    tc::mma_tile(tm0 + dst_col, al, tc::KB_BYTES_128, wh, tc::KB_BYTES_128, 128, idesc, true);
-    tc::mma_tile(tm0 + dst_col, ah, tc::KB_BYTES_128, wl, tc::KB_BYTES_128, 128, idesc, true);
+    if (tc::elect_one()) {
+      tc::mma_tile(tm0 + dst_col, ah, tc::KB_BYTES_128, wh, tc::KB_BYTES_128, 128, idesc, false);
+      tc::mma_tile(tm0 + dst_col, al, tc::KB_BYTES_128, wh, tc::KB_BYTES_128, 128, idesc, true);
+      tc::mma_tile(tm0 + dst_col, ah, tc::KB_BYTES_128, wl, tc::KB_BYTES_128, 128, idesc, true);
+    }
+    __syncwarp();
   };
   // A operand complete -> MMAs of `n_stage` consecutive weight stages -> wait for completion (all threads)
   auto run_gemm = [&](int n_stage, uint32_t dst_col0) {
     tc::fence_proxy_async();
     tc::tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc::tc_fence_after();
       for (int j = 0; j < n_stage; ++j) issue(wp.consumed + j, dst_col0 + 128 * j);
-      tc::mma_commit(&sm.bar_mma);
+      if (tc::elect_one()) tc::mma_commit(&sm.bar_mma);
+      __syncwarp();
     }
     tc::mbar_wait(&sm.bar_mma, wp.mma_count & 1);
     tc::tc_fence_after();

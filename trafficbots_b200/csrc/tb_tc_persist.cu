@@ -48,11 +48,17 @@ struct Smem {
   float2 vel[MAXA];
   float acc[MAXA], yaw_rate[MAXA];
   uint8_t valid[MAXA], killed[MAXA], goal_valid[MAXA], sticky[3][MAXA], type[MAXA][4];
+  // per-rollout constants of the tail: [field][agent]; fields: b2.x, b2.y, logp, latent logp, goal x, y, yaw, goal thresh, dest thresh
+  float tailc[9][MAXA];
+  float map_boundary[4];
+  uint8_t tflag[MAXA];  // bit 0: destination is a lane (types 0-3), bit 1: destination is a road edge (type 4)
   // barriers
   uint64_t full[2][2], free_[2][2], grant, wfill, ready, mma, cfg, s[2], p[2], o[2];
   uint32_t tmem_base;
   int n_valid, kvi_slot;
 };
+
+static_assert(sizeof(Smem) + 1024 <= 232448, "shared memory budget (227 KB per CTA)");
 
 struct Args {
   TbDims dm;
@@ -70,6 +76,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// sigmoid / tanh through MUFU.EX2 + MUFU.RCP: ~2^-21 relative error, far inside the bf16x3 error of their arguments
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  return __fdividef(1.0f, 1.0f + ex2_approx(-1.4426950408889634f * x));
+}
+__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.0f, fast_sigmoid(2.0f * x), -1.0f); }
+using tc::elect_one;
+using tc::uniform;
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
@@ -259,7 +272,7 @@ struct Issuer {
   __device__ __forceinline__ int wait_cfg() {
     tc::mbar_wait(&sm.cfg, n_cfg & 1);
     ++n_cfg;
-    return *reinterpret_cast<volatile int*>(&sm.n_valid);
+    return uniform(*reinterpret_cast<volatile int*>(&sm.n_valid));
   }
   __device__ __forceinline__ void wait_ready() {
     tc::mbar_wait(&sm.ready, n_ready & 1);
@@ -267,7 +280,10 @@ struct Issuer {
     tc::tc_fence_after();
   }
   __device__ __forceinline__ void gemm_begin() { wait_ready(); }
-  __device__ __forceinline__ void gemm_end() { tc::mma_commit(&sm.mma); }
+  __device__ __forceinline__ void gemm_end() {
+    if (elect_one()) tc::mma_commit(&sm.mma);
+    __syncwarp();
+  }
   __device__ __forceinline__ void chain(const unsigned char*, uint32_t dcol, uint32_t acol, bool accum) {
     const uint32_t slot = g & 1;
     tc::mbar_wait(&sm.full[slot][0], nf[slot] & 1);
@@ -277,17 +293,20 @@ struct Issuer {
     const uint32_t wh = tc::smem_u32(sm.ring[slot]);
     const uint64_t dh = tc::make_desc_sw128(wh), dl = tc::make_desc_sw128(wh + 2 * tc::KB_BYTES_128);
     const uint32_t idesc = tc::make_idesc_bf16(128, 128);
+    if (elect_one()) {
 #pragma unroll
-    for (int term = 0; term < 3; ++term) {
-      const uint32_t ta = tm0 + acol + (term == 1 ? 64 : 0);
-      const uint64_t db = term == 2 ? dl : dh;
+      for (int term = 0; term < 3; ++term) {
+        const uint32_t ta = tm0 + acol + (term == 1 ? 64 : 0);
+        const uint64_t db = term == 2 ? dl : dh;
 #pragma unroll
-      for (int k = 0; k < 128; k += 16)
-        tc::mma_bf16_ts(tm0 + dcol, ta + k / 2, db + (uint64_t)(((k >> 6) * tc::KB_BYTES_128 + (k & 63) * 2) >> 4), idesc,
-                        (accum || term > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 128; k += 16)
+          tc::mma_bf16_ts(tm0 + dcol, ta + k / 2, db + (uint64_t)(((k >> 6) * tc::KB_BYTES_128 + (k & 63) * 2) >> 4), idesc,
+                          (accum || term > 0 || k > 0) ? 1u : 0u);
+      }
+      tc::mma_commit(&sm.free_[slot][0]);
+      tc::mma_commit(&sm.free_[slot][1]);
     }
-    tc::mma_commit(&sm.free_[slot][0]);
-    tc::mma_commit(&sm.free_[slot][1]);
+    __syncwarp();
     ++g;
   }
   __device__ __forceinline__ void kvi() {
@@ -334,9 +353,12 @@ struct Issuer {
       tc::mbar_wait(&sm.full[g0 & 1][0], nf[g0 & 1] & 1);
     }
     tc::tc_fence_after();
-    issue_qk(g0 & 1, 0);
-    issue_qk(g0 & 1, 1);
-    tc::mma_commit(&sm.free_[g0 & 1][0]);
+    if (elect_one()) {
+      issue_qk(g0 & 1, 0);
+      issue_qk(g0 & 1, 1);
+      tc::mma_commit(&sm.free_[g0 & 1][0]);
+    }
+    __syncwarp();
     for (int jb = 0; jb < nblk; ++jb) {
       const uint32_t slot = (g0 + jb) & 1, slotn = slot ^ 1;
 #pragma unroll
@@ -349,18 +371,22 @@ struct Issuer {
           ++nf[slot];
           tc::tc_fence_after();
         }
-        issue_pv(slot, hp, jb > 0);
-        if (hp == 1) tc::mma_commit(&sm.free_[slot][1]);
-        if (jb + 1 < nblk) {
-          if (hp == 0) {
-            tc::mbar_wait(&sm.full[slotn][0], nf[slotn] & 1);
-            tc::tc_fence_after();
-          }
-          issue_qk(slotn, hp);
-          if (hp == 1) tc::mma_commit(&sm.free_[slotn][0]);
-        } else {
-          tc::mma_commit(&sm.o[hp]);
+        const bool more = jb + 1 < nblk;
+        if (more && hp == 0) {
+          tc::mbar_wait(&sm.full[slotn][0], nf[slotn] & 1);
+          tc::tc_fence_after();
         }
+        if (elect_one()) {
+          issue_pv(slot, hp, jb > 0);
+          if (hp == 1) tc::mma_commit(&sm.free_[slot][1]);
+          if (more) {
+            issue_qk(slotn, hp);
+            if (hp == 1) tc::mma_commit(&sm.free_[slotn][0]);
+          } else {
+            tc::mma_commit(&sm.o[hp]);
+          }
+        }
+        __syncwarp();
       }
     }
     if (!kvi_keys) g += nblk;
@@ -377,9 +403,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
   const int A = dm.n_agent, K = dm.n_mode, S = dm.n_scene, B = S * K, Th = dm.n_step_hist, T = dm.n_step, Tg = dm.n_step_gt;
   const int nT_map = (dm.n_pl + 63) / 64, nT_tl = (dm.n_tl + 63) / 64;
   const int b = blockIdx.x, s = b / K;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform(tid >> 5), lane = tid & 31;
   const size_t BA = (size_t)B * A;
-  const int nkey_map = in.n_key_map[s];
+  const int nkey_map = uniform(in.n_key_map[s]);
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i)
@@ -429,7 +455,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tm0 = sm.tmem_base;
+  const uint32_t tm0 = (uint32_t)uniform((int)sm.tmem_base);
 
   StepCfg cfg;
   cfg.nblk_map = (nkey_map + 63) / 64;
@@ -450,11 +476,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
     }
   } else if (warp == 8) {
     // ========================================================================================================== issuer
-    if (lane == 0) {
+    {  // the whole warp runs the issue program (so that every operand is provably warp-uniform); one elected lane issues
       Issuer is(sm, tm0);
       for (int t = a.t_first; t <= a.t_last; ++t) {
         const int tl_t = min(t - 1, Th - 1);
-        cfg.nblk_tl = (in.n_key_tl[(size_t)s * Th + tl_t] + 63) / 64;
+        cfg.nblk_tl = (uniform(in.n_key_tl[(size_t)s * Th + tl_t]) + 63) / 64;
         cfg.kv_tl = nullptr;
         enumerate_step(a, cfg, is);
       }
@@ -467,6 +493,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
     const int c0 = half * 64;
     const bool live = ag < A;
     const bool writer = upper == 0 && live;  // the lane that owns global side effects of agent `ag`
+    // Rows a + 64 duplicate rows a.  Only the query projection needs the duplicate (head-stacked attention), so the warps of
+    // the upper lanes skip every other epilogue and just keep the barrier / mbarrier arrival counts.
+    const bool lo_w = upper == 0;
     const size_t ba = (size_t)b * A + (live ? ag : 0), sa = (size_t)s * A + (live ? ag : 0);
     const uint32_t tm = tm0 + ((uint32_t)(quad * 32) << 16);
     uint32_t n_mma = 0, n_s = 0, n_o = 0, n_grant = 0, n_ln = 0, n_lp = 0;
@@ -520,7 +549,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
       tc::tmem_ld_wait();
     };
     // LayerNorm over the 128 columns of a row held by the thread pair (l, half 0 / 1): one exchange of {sum, M2}
-    auto layernorm64 = [&](float (&v)[64], const float* g, const float* bt) {
+    auto layernorm64 = [&](float (&v)[64], const float* g, const float* bt, bool active = true) {
+      if (!active) {  // a warp that skips this LayerNorm still takes part in the exchange barrier
+        ++n_ln;
+        worker_sync();
+        return;
+      }
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < 64; ++i) sum += v[i];
@@ -565,10 +599,41 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
 
     const float sc = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e): softmax in base 2
 
+    // per-rollout constants of the tail -> shared memory
+    if (half == 0 && writer) {
+      const int b2o[3] = {tbw::action_head_mlp_mean_0_fc_layers_2_bias, tbw::action_head_mlp_mean_1_fc_layers_2_bias,
+                          tbw::action_head_mlp_mean_2_fc_layers_2_bias};
+      const int lso[3] = {tbw::action_head_log_std_0, tbw::action_head_log_std_1, tbw::action_head_log_std_2};
+      float b2x = 0.f, b2y = 0.f, ls[2] = {0.f, 0.f};
+      for (int c3 = 0; c3 < 3; ++c3)
+        if (sm.type[ag][c3]) {
+          b2x += __ldg(packed + b2o[c3]);
+          b2y += __ldg(packed + b2o[c3] + 1);
+          ls[0] += __ldg(packed + lso[c3]);
+          ls[1] += __ldg(packed + lso[c3] + 1);
+        }
+      float logp = 0.f;
+      for (int d = 0; d < 2; ++d) logp += -logf(expf(ls[d])) - 0.91893853320467267f;
+      sm.tailc[0][ag] = b2x;
+      sm.tailc[1][ag] = b2y;
+      sm.tailc[2][ag] = logp;
+      sm.tailc[3][ag] = in.latent_logp[ba];
+      for (int i = 0; i < 3; ++i) sm.tailc[4 + i][ag] = in.goal_gt ? in.goal_gt[sa * 4 + i] : 0.f;
+      sm.tailc[7][ag] = in.agent_size[sa * 3] * 8.0f;
+      long dst = in.dest[ba];
+      dst = dst < 0 ? 0 : (dst >= dm.n_pl ? dm.n_pl - 1 : dst);
+      const uint8_t* dtype = in.map_type + ((size_t)s * dm.n_pl + dst) * TB_PL_TYPE;
+      const bool lane_t = dtype[0] || dtype[1] || dtype[2] || dtype[3], edge_t = dtype[4] != 0;
+      sm.tailc[8][ag] = 50.0f * (1.0f - (edge_t ? 1.0f : 0.f) * 0.8f);
+      sm.tflag[ag] = (uint8_t)((lane_t ? 1 : 0) | (edge_t ? 2 : 0));
+      if (ag == 0)
+        for (int i = 0; i < 4; ++i) sm.map_boundary[i] = in.map_boundary[(size_t)s * 4 + i];
+    }
+
 #pragma unroll 1
     for (int t = a.t_first; t <= a.t_last; ++t) {
       const int tl_t = min(t - 1, Th - 1);
-      const int nkey_tl = in.n_key_tl[(size_t)s * Th + tl_t];
+      const int nkey_tl = uniform(in.n_key_tl[(size_t)s * Th + tl_t]);
       t_cur = t;
       mark();
       // ---- validity of this step; interaction bypass decision -> issuer / loader ----------------------------------------
@@ -648,31 +713,39 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
           if (kind == 2) {
             // K|V of the block input x0 (agent_interaction.py:52: tgt = attn_to_map_aware_feature for all 3 layers)
             float tg[64];
-            if (Lx == 6) {
-              load_x(tg);
-              if (writer) {
-                float* dst = a.sv.x0 + ba * D + c0;
+            if (lo_w) {
+              if (Lx == 6) {
+                load_x(tg);
+                if (writer) {
+                  float* dst = a.sv.x0 + ba * D + c0;
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  reinterpret_cast<float4*>(dst)[i] = make_float4(tg[4 * i], tg[4 * i + 1], tg[4 * i + 2], tg[4 * i + 3]);
-              }
-            } else {
-              const float* src = a.sv.x0 + ba * D + c0;  // written by this thread (or its twin lane) at Lx == 6
+                  for (int i = 0; i < 16; ++i)
+                    reinterpret_cast<float4*>(dst)[i] = make_float4(tg[4 * i], tg[4 * i + 1], tg[4 * i + 2], tg[4 * i + 3]);
+                }
+              } else if (live) {
+                const float* src = a.sv.x0 + ba * D + c0;  // written by this thread at Lx == 6
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float4 q = reinterpret_cast<const float4*>(src)[i];
-                tg[4 * i] = q.x, tg[4 * i + 1] = q.y, tg[4 * i + 2] = q.z, tg[4 * i + 3] = q.w;
+                for (int i = 0; i < 16; ++i) {
+                  const float4 q = reinterpret_cast<const float4*>(src)[i];
+                  tg[4 * i] = q.x, tg[4 * i + 1] = q.y, tg[4 * i + 2] = q.z, tg[4 * i + 3] = q.w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) tg[i] = 0.f;
               }
             }
-            layernorm64(tg, lp[8], lp[9]);
-            write_A(T_A, tg);
+            layernorm64(tg, lp[8], lp[9], lo_w);
+            if (lo_w) write_A(T_A, tg);
             signal_ready();  // -> Wk (ACC0), Wv (ACC1)
+            dmark(500 + Lx);
             wait_gemm();
-            tc::mbar_wait(&sm.grant, n_grant & 1);
+            dmark(510 + Lx);
+            if (lo_w) tc::mbar_wait(&sm.grant, n_grant & 1);
             ++n_grant;
-            unsigned char* blk = sm.ring[*reinterpret_cast<volatile int*>(&sm.kvi_slot)];
-            load_acc(T_ACC0, tg);  // K[ag, c0 .. c0+63]: key row ag of K-block `half`
-            if (upper == 0) {
+            dmark(520 + Lx);
+            if (lo_w) {
+              unsigned char* blk = sm.ring[*reinterpret_cast<volatile int*>(&sm.kvi_slot)];
+              load_acc(T_ACC0, tg);  // K[ag, c0 .. c0+63]: key row ag of K-block `half`
 #pragma unroll
               for (int i = 0; i < 64; ++i) tg[i] += lp[10][c0 + i];
 #pragma unroll
@@ -683,23 +756,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
                 *reinterpret_cast<uint4*>(blk + off) = hi;
                 *reinterpret_cast<uint4*>(blk + 16384 + off) = lo;
               }
-            }
-            load_acc(T_ACC1, tg);  // V[ag, c0 .. c0+63] -> V^T rows d = c0 + i, key column ag
-            if (upper == 0) {
+              dmark(530 + Lx);
+              load_acc(T_ACC1, tg);  // V[ag, c0 .. c0+63] -> V^T rows d = c0 + i, key column ag
+              unsigned char* vt = blk + HALF + (ag & 7) * 2;
+              const uint32_t kc = (uint32_t)(ag >> 3);
 #pragma unroll
-              for (int i = 0; i < 64; ++i) {
-                const float val = tg[i] + lp[11][c0 + i];
-                const __nv_bfloat16 h = __float2bfloat16_rn(val);
-                const __nv_bfloat16 lo = __float2bfloat16_rn(val - __bfloat162float(h));
-                const int d = c0 + i;
-                const uint32_t off = tc::sw128_off(d, ag >> 3) + (ag & 7) * 2;
-                *reinterpret_cast<__nv_bfloat16*>(blk + HALF + off) = h;
-                *reinterpret_cast<__nv_bfloat16*>(blk + HALF + 16384 + off) = lo;
+              for (int i = 0; i < 64; i += 2) {
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(tg[i] + lp[11][c0 + i], tg[i + 1] + lp[11][c0 + i + 1]);
+                const float2 hf = __bfloat1622float2(hh);
+                const __nv_bfloat162 ll = __floats2bfloat162_rn(tg[i] + lp[11][c0 + i] - hf.x, tg[i + 1] + lp[11][c0 + i + 1] - hf.y);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int d = c0 + i + e;
+                  const uint32_t off = (uint32_t)((d >> 3) * 1024 + (d & 7) * 128) + ((kc ^ (uint32_t)(d & 7)) << 4);
+                  *reinterpret_cast<__nv_bfloat16*>(vt + off) = e ? hh.y : hh.x;
+                  *reinterpret_cast<__nv_bfloat16*>(vt + 16384 + off) = e ? ll.y : ll.x;
+                }
               }
+              tc::fence_proxy_async();
             }
-            tc::fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.wfill);
+            dmark(540 + Lx);
           }
           load_x(v);
           layernorm64(v, lp[0], lp[1]);
@@ -807,37 +885,39 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
             for (int j = 0; j < 32; ++j) sm.xo[(c0 + 32 * upper + j) * MAXA + ag] = o[j] * inv;
           }
           worker_sync();
+          if (lo_w) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i) v[i] = sm.xo[(c0 + i) * MAXA + ag];
-          write_A(T_A, v);
+            for (int i = 0; i < 64; ++i) v[i] = sm.xo[(c0 + i) * MAXA + ag];
+            write_A(T_A, v);
+          }
           signal_ready();  // -> Wo
           dmark(105 + Lx * 10);
           wait_gemm();
           dmark(106 + Lx * 10);
-          load_acc(T_ACC0, v);
-          {
-            float x[64];
-            load_x(x);
+          if (lo_w) {  // x += attention output (all rows have at least one enabled key here)
+#pragma unroll 1
+            for (int jj = 0; jj < 2; ++jj) {
+              float o32[32];
+              tc::tmem_ld32(tm + T_ACC0 + c0 + 32 * jj, o32);
+              tc::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] += x[i] + lp[3][c0 + i];
+              for (int i = 0; i < 32; ++i) xs_at(c0 + 32 * jj + i) += o32[i] + lp[3][c0 + 32 * jj + i];
+            }
           }
-          store_x(v);
         } else {
-          load_x(v);
           commit_params();
         }
         {
           float x2[64];
-#pragma unroll
-          for (int i = 0; i < 64; ++i) x2[i] = v[i];
-          layernorm64(x2, lp[4], lp[5]);
-          write_A(T_A, x2);
+          if (lo_w) load_x(x2);
+          layernorm64(x2, lp[4], lp[5], lo_w);
+          if (lo_w) write_A(T_A, x2);
         }
         signal_ready();  // -> W1
         dmark(107 + Lx * 10);
         wait_gemm();
         dmark(108 + Lx * 10);
-        {
+        if (lo_w) {
           float h1[64];
           load_acc(T_ACC0, h1);
 #pragma unroll
@@ -848,13 +928,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         dmark(109 + Lx * 10);
         wait_gemm();
         dmark(190 + Lx);
-        {
+        if (lo_w) {  // x = valid ? x + FFN : 0
           float y[64];
           load_acc(T_ACC0, y);
-          float x[64];
-          load_x(x);
 #pragma unroll
-          for (int i = 0; i < 64; ++i) y[i] = valid ? x[i] + y[i] + lp[7][c0 + i] : 0.f;
+          for (int i = 0; i < 64; ++i) y[i] = valid ? xs_at(c0 + i) + y[i] + lp[7][c0 + i] : 0.f;
           store_x(y);
         }
         ++n_lp;
@@ -869,7 +947,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         dmark(200 + L * 10);
         fetch_params(10 + L);  // 10, 11 = GRU layers 1, 2; 12 = add_goal
         float* hid = a.sv.hidden + ((size_t)L * BA + ba) * D + c0;
-        {
+        if (lo_w) {
           float x[64];
           load_x(x);
           write_A(T_A, x);
@@ -890,15 +968,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         commit_params();
         wait_gemm();
         dmark(202 + L * 10);
-        float rh[64];
-        {
-          float r[64];
+        if (lo_w) {  // r * (W_hn h + b_hn) parked in the exchange buffer (free during the GRU; same thread reads it back)
+          float r[64], rh[64];
           load_acc(T_ACC0, r);
           load_acc(T_ACC1, rh);
 #pragma unroll
           for (int i = 0; i < 64; ++i) {
-            const float rg = sigmoidf_(r[i] + lp[0][c0 + i] + lp[3][c0 + i]);
-            rh[i] = rg * (rh[i] + lp[5][c0 + i]);
+            const float rg = fast_sigmoid(r[i] + lp[0][c0 + i] + lp[3][c0 + i]);
+            sm.xo[(c0 + i) * MAXA + ag] = rg * (rh[i] + lp[5][c0 + i]);
           }
         }
         tc::tc_fence_before();
@@ -907,29 +984,29 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         dmark(203 + L * 10);
         wait_gemm();
         dmark(204 + L * 10);
+        if (lo_w) {
 #pragma unroll 1
-        for (int jj = 0; jj < 2; ++jj) {
-          float z[32], n[32];
-          tc::tmem_ld32(tm + T_ACC0 + c0 + 32 * jj, z);
-          tc::tmem_ld32(tm + T_ACC1 + c0 + 32 * jj, n);
-          tc::tmem_ld_wait();
+          for (int jj = 0; jj < 2; ++jj) {
+            float z[32], n[32];
+            tc::tmem_ld32(tm + T_ACC0 + c0 + 32 * jj, z);
+            tc::tmem_ld32(tm + T_ACC1 + c0 + 32 * jj, n);
+            tc::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 hp4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) hp4 = reinterpret_cast<const float4*>(hid)[8 * jj + i];
-            const float hp_[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
-            float hn_[4];
+            for (int i = 0; i < 8; ++i) {
+              float4 hp4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (live) hp4 = reinterpret_cast<const float4*>(hid)[8 * jj + i];
+              const float hp_[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
+              float hn_[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = 32 * jj + 4 * i + e;
-              const float zg = sigmoidf_(z[4 * i + e] + lp[1][c0 + c] + lp[4][c0 + c]);
-              const float ng = tanhf(n[4 * i + e] + lp[2][c0 + c] + rh[c]);
-              hn_[e] = (1.0f - zg) * ng + zg * hp_[e];
-            }
-            // h[:, ~valid] = 0; the next GRU layer sees the unmasked output, after the last layer x[~valid] = 0
-            if (writer)
-              reinterpret_cast<float4*>(hid)[8 * jj + i] = valid ? make_float4(hn_[0], hn_[1], hn_[2], hn_[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (upper == 0) {
+              for (int e = 0; e < 4; ++e) {
+                const int c = 32 * jj + 4 * i + e;
+                const float zg = fast_sigmoid(z[4 * i + e] + lp[1][c0 + c] + lp[4][c0 + c]);
+                const float ng = fast_tanh(n[4 * i + e] + lp[2][c0 + c] + sm.xo[(c0 + c) * MAXA + ag]);
+                hn_[e] = (1.0f - zg) * ng + zg * hp_[e];
+              }
+              // h[:, ~valid] = 0; the next GRU layer sees the unmasked output, after the last layer x[~valid] = 0
+              if (live)
+                reinterpret_cast<float4*>(hid)[8 * jj + i] = valid ? make_float4(hn_[0], hn_[1], hn_[2], hn_[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
               for (int e = 0; e < 4; ++e) xs_at(c0 + 32 * jj + 4 * i + e) = (L == 2 && !valid) ? 0.f : hn_[e];
             }
@@ -944,14 +1021,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
       for (int j = 0; j < 2; ++j) {
         worker_sync();
         const float (*lp)[128] = sm.lp[n_lp & 1];
+        dmark(300 + j * 10);
         fetch_params(13 + j);  // 13 = add_latent, 14 = head
         const bool zv = j == 0 ? (sm.goal_valid[ag] != 0) : valid;
         const float* zin = (j == 0 ? a.sv.goal_in : a.sv.latent_in) + ba * D + c0;
-        float x[64];
-        load_x(x);
-        write_A(T_A, x);
-        {
-          float z[64];
+        if (lo_w) {
+          float x[64], z[64];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -959,11 +1034,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
             z[4 * i] = fmaxf(q.x, 0.f), z[4 * i + 1] = fmaxf(q.y, 0.f), z[4 * i + 2] = fmaxf(q.z, 0.f), z[4 * i + 3] = fmaxf(q.w, 0.f);
           }
           write_A(T_A2, z);
+          load_x(x);
+          write_A(T_A, x);
         }
         signal_ready();
+        dmark(301 + j * 10);
         commit_params();
         wait_gemm();
-        {
+        dmark(302 + j * 10);
+        if (lo_w) {
           float h1[64];
           load_acc(T_ACC0, h1);
 #pragma unroll
@@ -971,41 +1050,66 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
           write_A(T_A, h1);
         }
         signal_ready();
+        dmark(303 + j * 10);
         wait_gemm();
-        {
+        dmark(304 + j * 10);
+        if (lo_w) {
           float h2[64];
           load_acc(T_ACC0, h2);
 #pragma unroll
           for (int i = 0; i < 64; ++i) {
             const float hz = fmaxf(h2[i] + lp[1][c0 + i], 0.f);
-            x[i] = valid ? (zv ? hz : 0.f) + x[i] : 0.f;
+            h2[i] = valid ? (zv ? hz : 0.f) + xs_at(c0 + i) : 0.f;
           }
-          store_x(x);
+          store_x(h2);
         }
         ++n_lp;
       }
       // ---- action head (action_head.py:70-87): per-type MLP 128 -> 128 -> 2, masked by type & valid, summed -------------------------------
+      // the tail's ground-truth operands of this step are fetched now, so that their latency hides behind the head GEMMs
+      const bool tail_thread = half == 0 && writer;
+      const bool has_gt = t < Tg;
+      const size_t gidx = ((size_t)s * Tg + (has_gt ? t : 0)) * A + ag;
+      float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
+      float2 g_vel = make_float2(0.f, 0.f);
+      float g_acc = 0.f, g_yr = 0.f;
+      bool ovr = false, gt_valid = false;
       {
         worker_sync();
         const float (*lp)[128] = sm.lp[n_lp & 1];
+        dmark(320);
         fetch_params(0);
-        float x[64];
-        load_x(x);
-        write_A(T_A, x);
-        signal_ready();
-        if (a.out.trace_policy_feature && writer) {
-          float* dst = a.out.trace_policy_feature + ((ba * T) + (t - 1)) * D + c0;
+        if (lo_w) {
+          float x[64];
+          load_x(x);
+          write_A(T_A, x);
+          if (a.out.trace_policy_feature && writer) {
+            float* dst = a.out.trace_policy_feature + ((ba * T) + (t - 1)) * D + c0;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+            for (int i = 0; i < 16; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+          }
+        }
+        signal_ready();
+        dmark(321);
+        if (tail_thread && has_gt) {
+          ovr = in.tf_mask[gidx] != 0;
+          gt_valid = in.gt_valid[gidx] != 0;
+          gs = make_float4(in.gt_pos[gidx * 2], in.gt_pos[gidx * 2 + 1], in.gt_yaw[gidx], in.gt_spd[gidx]);
+          g_vel = make_float2(in.gt_vel[gidx * 2], in.gt_vel[gidx * 2 + 1]);
+          g_acc = in.gt_acc[gidx];
+          g_yr = in.gt_yaw_rate[gidx];
         }
         commit_params();
         wait_gemm();
-        float m0 = 0.f, m1 = 0.f;
+        dmark(322);
+        if (lo_w) {
+          float m0 = 0.f, m1 = 0.f;
+          // tcgen05.ld is warp-collective: every lane loads all three accumulators and masks the contribution
 #pragma unroll 1
-        for (int c3 = 0; c3 < 3; ++c3) {
-          float hdn[64];
-          load_acc(128 * c3, hdn);
-          if (sm.type[ag][c3] && valid) {
+          for (int c3 = 0; c3 < 3; ++c3) {
+            float hdn[64];
+            load_acc(128 * c3, hdn);
+            const bool on = sm.type[ag][c3] && valid;
             const float* w2 = &lp[3 + 2 * c3][0];  // Wt4[32][2][4]: (k, d) at ((k >> 2) * 2 + d) * 4 + (k & 3); 256 contiguous floats
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
@@ -1015,11 +1119,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
               s0 = fmaf(hv, w2[((k >> 2) * 2 + 0) * 4 + (k & 3)], s0);
               s1 = fmaf(hv, w2[((k >> 2) * 2 + 1) * 4 + (k & 3)], s1);
             }
-            m0 += s0;
-            m1 += s1;
+            if (on) {
+              m0 += s0;
+              m1 += s1;
+            }
           }
-        }
-        if (upper == 0) {
           sm.mean_part[half][ag][0] = m0;
           sm.mean_part[half][ag][1] = m1;
         }
@@ -1030,35 +1134,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
 
       dmark(400);
       // ---- per-agent tail: dynamics, override, rule checks, kill, goal_valid, reward, outputs ----------------------------------------------
-      if (half == 0 && writer) {
-        const bool ty0 = sm.type[ag][0], ty1 = sm.type[ag][1], ty2 = sm.type[ag][2];
+      if (tail_thread) {
         float mean0 = sm.mean_part[0][ag][0] + sm.mean_part[1][ag][0], mean1 = sm.mean_part[0][ag][1] + sm.mean_part[1][ag][1];
         if (valid) {
-          if (ty0) mean0 += __ldg(packed + tbw::action_head_mlp_mean_0_fc_layers_2_bias), mean1 += __ldg(packed + tbw::action_head_mlp_mean_0_fc_layers_2_bias + 1);
-          if (ty1) mean0 += __ldg(packed + tbw::action_head_mlp_mean_1_fc_layers_2_bias), mean1 += __ldg(packed + tbw::action_head_mlp_mean_1_fc_layers_2_bias + 1);
-          if (ty2) mean0 += __ldg(packed + tbw::action_head_mlp_mean_2_fc_layers_2_bias), mean1 += __ldg(packed + tbw::action_head_mlp_mean_2_fc_layers_2_bias + 1);
-        }
-        // DiagGaussian log-prob of the deterministic sample (= mean), dynamics.py:77-80
-        float logp = 0.f;
-        if (valid) {
-          for (int d = 0; d < 2; ++d) {
-            float ls = 0.f;
-            if (ty0) ls += __ldg(packed + tbw::action_head_log_std_0 + d);
-            if (ty1) ls += __ldg(packed + tbw::action_head_log_std_1 + d);
-            if (ty2) ls += __ldg(packed + tbw::action_head_log_std_2 + d);
-            logp += -logf(expf(ls)) - 0.91893853320467267f;
-          }
+          mean0 += sm.tailc[0][ag];
+          mean1 += sm.tailc[1][ag];
         }
         // MultiPathPP.process_action / update (dynamics.py:187-228); type order of the parameter tuples: veh, ped, cyc
-        const float max_acc = (ty0 ? 5.0f : 0.f) + (ty1 ? 7.0f : 0.f) + (ty2 ? 6.0f : 0.f);
-        const float max_yr = (ty0 ? 1.5f : 0.f) + (ty1 ? 7.0f : 0.f) + (ty2 ? 3.0f : 0.f);
-        const float a_acc = valid ? tanhf(mean0) * max_acc : 0.f;
-        const float a_yr = valid ? tanhf(mean1) * max_yr : 0.f;
+        const bool ty0 = sm.type[ag][0], ty1 = sm.type[ag][1], ty2 = sm.type[ag][2];
+        const bool k_has_type = ty0 || ty1 || ty2;
+        const float k_max_acc = (ty0 ? 5.0f : 0.f) + (ty1 ? 7.0f : 0.f) + (ty2 ? 6.0f : 0.f);
+        const float k_max_yr = (ty0 ? 1.5f : 0.f) + (ty1 ? 7.0f : 0.f) + (ty2 ? 3.0f : 0.f);
+        const float a_acc = valid ? tanhf(mean0) * k_max_acc : 0.f;
+        const float a_yr = valid ? tanhf(mean1) * k_max_yr : 0.f;
         const float4 st = sm.pose[ag];
         const float v_t = st.w + 0.05f * a_acc, th_t = st.z + 0.05f * a_yr;
-        const bool has_type = ty0 || ty1 || ty2;
         float4 pred = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid && has_type) {
+        if (valid && k_has_type) {
           pred.x = st.x + 0.1f * (v_t * cosf(th_t));
           pred.y = st.y + 0.1f * (v_t * sinf(th_t));
           pred.z = st.z + 0.1f * a_yr;
@@ -1067,66 +1159,58 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         const size_t o = ba * T + (t - 1);
         *reinterpret_cast<float4*>(a.out.preds + o * 4) = pred;
         a.out.valid[o] = valid;
-        a.out.action_log_probs[o] = logp;
-        a.out.latent_log_probs[o] = in.latent_logp[ba];
+        a.out.action_log_probs[o] = valid ? sm.tailc[2][ag] : 0.f;  // DiagGaussian log-prob of the deterministic sample, dynamics.py:77-80
+        a.out.latent_log_probs[o] = sm.tailc[3][ag];
         if (a.out.trace_action_mean) {
           a.out.trace_action_mean[o * 2] = mean0;
           a.out.trace_action_mean[o * 2 + 1] = mean1;
         }
         // Dynamics.override_states (dynamics.py:121-149)
-        const bool has_gt = t < Tg;
-        const size_t g = ((size_t)s * Tg + (has_gt ? t : 0)) * A + ag;
-        const bool ovr = has_gt && in.tf_mask[g] != 0;
-        const bool gt_valid = has_gt && in.gt_valid[g] != 0;
         bool killed = sm.killed[ag] != 0;
         const bool m = ovr && !killed;
         bool nvalid = valid || m;
         float4 ns = pred;
-        float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_gt) gs = make_float4(in.gt_pos[g * 2], in.gt_pos[g * 2 + 1], in.gt_yaw[g], in.gt_spd[g]);
         if (m) {
           ns = gs;
-          sm.vel[ag] = make_float2(in.gt_vel[g * 2], in.gt_vel[g * 2 + 1]);
-          sm.acc[ag] = in.gt_acc[g];
-          sm.yaw_rate[ag] = in.gt_yaw_rate[g];
+          sm.vel[ag] = g_vel;
+          sm.acc[ag] = g_acc;
+          sm.yaw_rate[ag] = g_yr;
         }
         a.out.override_masks[o] = ovr;
         // TrafficRuleChecker.check, always-on subset (traffic_rule_checker.py:101-119,338-410,423-424,474-496)
-        const float* mb = in.map_boundary + (size_t)s * 4;
-        const bool out_t = nvalid && (ns.x > mb[1] || ns.x < mb[0] || ns.y > mb[3] || ns.y < mb[2]);
+        const bool out_t = nvalid && (ns.x > sm.map_boundary[1] || ns.x < sm.map_boundary[0] || ns.y > sm.map_boundary[3] || ns.y < sm.map_boundary[2]);
         bool outside = sm.sticky[0][ag] != 0, goal_r = sm.sticky[1][ag] != 0, dest_r = sm.sticky[2][ag] != 0;
         outside |= out_t;
         bool goal_t = false;
         if (in.goal_gt) {
-          const float* gg = in.goal_gt + sa * 4;
-          const float dx = ns.x - gg[0], dy = ns.y - gg[1];
-          const bool pos_ok = sqrtf(dx * dx + dy * dy) < in.agent_size[sa * 3] * 8.0f;
+          const float dx = ns.x - sm.tailc[4][ag], dy = ns.y - sm.tailc[5][ag];
+          const bool pos_ok = sqrtf(dx * dx + dy * dy) < sm.tailc[7][ag];
           // cast_rad (transform_utils.py:10-12): (a + pi) % (2 pi) - pi with Python's sign-of-divisor modulo
           const float PI_F = 3.14159265358979323846f, TWO_PI_F = 6.28318530717958647692f;
-          float w = fmodf(ns.z - gg[2] + PI_F, TWO_PI_F);
+          float w = fmodf(ns.z - sm.tailc[6][ag] + PI_F, TWO_PI_F);
           if (w < 0.f) w += TWO_PI_F;
           const bool rot_ok = fabsf(w - PI_F) < 0.26179938779914943654f;
           goal_t = pos_ok && rot_ok && nvalid && !goal_r;
         }
         goal_r |= goal_t;
-        long dst = in.dest[ba];
-        dst = dst < 0 ? 0 : (dst >= dm.n_pl ? dm.n_pl - 1 : dst);
-        const size_t dp = (size_t)s * dm.n_pl + dst;
-        const uint8_t* dtype = in.map_type + dp * TB_PL_TYPE;
-        const bool lane_t = dtype[0] || dtype[1] || dtype[2] || dtype[3], edge_t = dtype[4] != 0;
-        const float thresh = 50.0f * (1.0f - (edge_t ? 1.0f : 0.f) * 0.8f);
         bool pos_reached = false, rot_reached = false;
+        const float k_dest_thresh = sm.tailc[8][ag];
+        const bool k_lane_t = (sm.tflag[ag] & 1) != 0, k_edge_t = (sm.tflag[ag] & 2) != 0;
         const float hx = cosf(ns.z), hy = sinf(ns.z);
-        for (int n = 0; n < TB_PL_NODE; ++n) {
-          const size_t nd = dp * TB_PL_NODE + n;
-          if (!in.map_valid[nd]) continue;
-          const float dx = ns.x - in.map_pos[nd * 2], dy = ns.y - in.map_pos[nd * 2 + 1];
-          pos_reached |= sqrtf(dx * dx + dy * dy) < thresh;
-          const float ux = in.map_dir[nd * 2], uy = in.map_dir[nd * 2 + 1];
-          const float nrm = sqrtf(ux * ux + uy * uy);
-          rot_reached |= (hx * (ux / nrm) + hy * (uy / nrm)) > 0.86602540378443864676f;  // NaN (zero-length dir) compares false
+        const float4* dn = a.sv.dest_nodes + ba * TB_PL_NODE;
+#pragma unroll
+        for (int n0 = 0; n0 < TB_PL_NODE; n0 += 10) {
+          float4 nd[10];
+#pragma unroll
+          for (int n = 0; n < 10; ++n) nd[n] = __ldg(dn + n0 + n);
+#pragma unroll
+          for (int n = 0; n < 10; ++n) {
+            const float dx = ns.x - nd[n].x, dy = ns.y - nd[n].y;
+            pos_reached |= sqrtf(dx * dx + dy * dy) < k_dest_thresh;
+            rot_reached |= (hx * nd[n].z + hy * nd[n].w) > 0.86602540378443864676f;  // NaN (zero-length dir) compares false
+          }
         }
-        const bool dest_t = !dest_r && nvalid && ((lane_t && pos_reached && rot_reached) || (edge_t && pos_reached));
+        const bool dest_t = !dest_r && nvalid && ((k_lane_t && pos_reached && rot_reached) || (k_edge_t && pos_reached));
         dest_r |= dest_t;
         const size_t vs = BA * T;
         a.out.violations[0 * vs + o] = outside;
