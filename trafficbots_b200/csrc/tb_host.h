@@ -36,6 +36,8 @@ struct StateView {
   float* kv_int;       // [3,B,A,256] interaction K|V of the current step
   float* goal_in;      // [B,A,128]  add_goal.mlp_in(goal_feature) before mask/ReLU (loop invariant)
   float* latent_in;    // [B,A,128]  add_latent.mlp_in(latent_sample) before mask/ReLU (loop invariant)
+  float* hidden_x;     // [n_cluster-1][3,B*A,128] private GRU hidden copies of the cluster ranks > 0 (persistent kernel)
+  float* x0_x;         // [n_cluster-1][B,A,128]
   float4* dest_nodes;  // [B,A,20]   destination polyline nodes (x, y, unit direction), invalid nodes at 1e30
 };
 
@@ -55,6 +57,7 @@ int launch_step_front_tc(const TbDims& d, const TbRolloutIn& in, const float* pa
 extern long long* g_debug_trace;  // development aid (tb_debug_set_trace)
 // persistent tensor-core rollout (tb_tc_persist.cu): all decode steps t_first..t_last in one launch, n_agent <= 64
 bool rollout_tc_supported(const TbDims& d, const TbRolloutIn& in);
+int rollout_tc_cluster_size(const TbDims& d);  // CTAs per scene-mode (1, 2 or 4)
 int launch_rollout_tc(const TbDims& d, const TbRolloutIn& in, const float* packed, const StateView& sv, const TbRolloutOut& out,
                       int t_first, int t_last, cudaStream_t st);
 inline bool persist_enabled() {

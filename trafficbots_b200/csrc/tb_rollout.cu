@@ -16,7 +16,7 @@ static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct StateLayout {
   size_t off[TB_STATE_N_FIELD];
-  size_t x0, kv_int, goal_in, latent_in, dest_nodes, total;
+  size_t x0, kv_int, goal_in, latent_in, dest_nodes, hidden_x, x0_x, total;
 };
 
 static StateLayout state_layout(const TbDims& d) {
@@ -42,6 +42,9 @@ static StateLayout state_layout(const TbDims& d) {
   L.goal_in = put(BA * D * sizeof(float));
   L.latent_in = put(BA * D * sizeof(float));
   L.dest_nodes = put(BA * TB_PL_NODE * 4 * sizeof(float));
+  const size_t n_extra = (size_t)(rollout_tc_cluster_size(d) - 1);
+  L.hidden_x = put(n_extra * 3 * BA * D * sizeof(float));
+  L.x0_x = put(n_extra * BA * D * sizeof(float));
   L.total = o;
   return L;
 }
@@ -64,6 +67,8 @@ StateView state_view(const TbDims& d, void* base) {
   v.goal_in = reinterpret_cast<float*>(p + L.goal_in);
   v.latent_in = reinterpret_cast<float*>(p + L.latent_in);
   v.dest_nodes = reinterpret_cast<float4*>(p + L.dest_nodes);
+  v.hidden_x = reinterpret_cast<float*>(p + L.hidden_x);
+  v.x0_x = reinterpret_cast<float*>(p + L.x0_x);
   return v;
 }
 

@@ -83,6 +83,46 @@ __device__ __forceinline__ float fast_sigmoid(float x) {
 __device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.0f, fast_sigmoid(2.0f * x), -1.0f); }
 using tc::elect_one;
 using tc::uniform;
+
+// ---- thread-block cluster helpers (split of the agent->map attention over the CTAs of a cluster) -----------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_sync_relaxed() {  // rendezvous only: the caller publishes no data
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t cta_smem_addr, uint32_t rank) {  // same offset in CTA `rank`'s shared memory
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float ld_cluster_f32(uint32_t cluster_addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_cluster_f32x4(uint32_t cluster_addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(cluster_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 ld_cluster_f32x2(uint32_t cluster_addr) {
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(cluster_addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
@@ -140,7 +180,8 @@ __device__ __forceinline__ int phase_vec(int p, int i) {
 
 // ---- the operand-block sequence of one decode step, shared by the loader and the issuer ---------------------------------
 struct StepCfg {
-  int nblk_map, nblk_tl;
+  int nblk_map, nblk_tl;  // nblk_map: key blocks of the scene; this CTA takes blocks rank, rank + n_cta, ...
+  int rank, n_cta;
   const unsigned char* kv_map;  // + (L * S) * nT_map * BLK per layer
   const unsigned char* kv_tl;
   size_t kv_map_layer_stride, kv_tl_layer_stride;
@@ -165,6 +206,8 @@ __device__ __forceinline__ void enumerate_step(const Args& a, const StepCfg& c, 
                                 : tbb::model_agent_interaction_transformer_layers_0_attn_in_proj_weight) +
                    6 * L;
     const int nblk = kind == 0 ? c.nblk_map : kind == 1 ? c.nblk_tl : nblk_int;
+    // blocks of this CTA: the agent->map attention is split over the cluster (online-softmax partials merged by the workers)
+    const int nblk_my = kind == 0 ? (c.nblk_map > c.rank ? (c.nblk_map - c.rank + c.n_cta - 1) / c.n_cta : 0) : nblk;
     if (nblk > 0) {
       if (kind == 2) {
         r.gemm_begin();
@@ -176,10 +219,14 @@ __device__ __forceinline__ void enumerate_step(const Args& a, const StepCfg& c, 
       r.gemm_begin();
       r.chain(W(w0, 0), T_ACC0, T_A, false);
       r.gemm_end();
-      r.att(kind == 2, nblk, kind == 0 ? c.kv_map + L * c.kv_map_layer_stride : c.kv_tl + L * c.kv_tl_layer_stride);
+      r.att(kind == 2, nblk_my, kind == 0 ? c.kv_map + L * c.kv_map_layer_stride + (size_t)c.rank * BLK : c.kv_tl + L * c.kv_tl_layer_stride,
+            kind == 0 ? (size_t)c.n_cta * BLK : (size_t)BLK);
+      const bool split = kind == 0 && c.n_cta > 1;
+      if (split) r.csync_before_wo();
       r.gemm_begin();
       r.chain(W(w0, 3), T_ACC0, T_A, false);
       r.gemm_end();
+      if (split) r.csync_after_wo();
     }
     r.gemm_begin();
     r.chain(W(w0, 4), T_ACC0, T_A, false);
@@ -223,7 +270,7 @@ __device__ __forceinline__ void enumerate_step(const Args& a, const StepCfg& c, 
   r.gemm_end();
 }
 
-struct Loader {
+struct Loader {  // run by a whole (converged) warp; one elected lane issues the copies
   Smem& sm;
   uint32_t g = 0, n_cfg = 0;
   __device__ Loader(Smem& s) : sm(s) {}
@@ -236,15 +283,18 @@ struct Loader {
 #pragma unroll
     for (uint32_t h = 0; h < 2; ++h) {
       wait_free(slot, h);
-      tc::mbar_expect_tx(&sm.full[slot][h], HALF);
-      tc::bulk_g2s(sm.ring[slot] + h * HALF, ptr + h * HALF, HALF, &sm.full[slot][h]);
+      if (elect_one()) {
+        tc::mbar_expect_tx(&sm.full[slot][h], HALF);
+        tc::bulk_g2s(sm.ring[slot] + h * HALF, ptr + h * HALF, HALF, &sm.full[slot][h]);
+      }
+      __syncwarp();
     }
     ++g;
   }
   __device__ __forceinline__ int wait_cfg() {
     tc::mbar_wait(&sm.cfg, n_cfg & 1);
     ++n_cfg;
-    return *reinterpret_cast<volatile int*>(&sm.n_valid);
+    return uniform(*reinterpret_cast<volatile int*>(&sm.n_valid));
   }
   __device__ __forceinline__ void gemm_begin() {}
   __device__ __forceinline__ void gemm_end() {}
@@ -253,14 +303,23 @@ struct Loader {
     const uint32_t slot = g & 1;
     wait_free(slot, 0);
     wait_free(slot, 1);
-    *reinterpret_cast<volatile int*>(&sm.kvi_slot) = (int)slot;
-    __threadfence_block();
-    mbar_arrive(&sm.grant);
+    if (elect_one()) {
+      *reinterpret_cast<volatile int*>(&sm.kvi_slot) = (int)slot;
+      __threadfence_block();
+      mbar_arrive(&sm.grant);
+    }
+    __syncwarp();
     ++g;
   }
-  __device__ __forceinline__ void att(bool kvi_keys, int nblk, const unsigned char* blocks) {
+  __device__ __forceinline__ void att(bool kvi_keys, int nblk, const unsigned char* blocks, size_t stride) {
     if (kvi_keys) return;
-    for (int j = 0; j < nblk; ++j) load(blocks + (size_t)j * BLK);
+    for (int j = 0; j < nblk; ++j) load(blocks + (size_t)j * stride);
+  }
+  // the two cluster barriers of a split layer's merge: the loader joins them after the Wo block is on its way
+  __device__ __forceinline__ void csync_before_wo() {}
+  __device__ __forceinline__ void csync_after_wo() {
+    cluster_sync_relaxed();
+    cluster_sync_relaxed();
   }
 };
 
@@ -313,6 +372,11 @@ struct Issuer {
     kvi_slot = g & 1;
     ++g;
   }
+  __device__ __forceinline__ void csync_before_wo() {  // the issuer joins the merge's two cluster barriers right away
+    cluster_sync_relaxed();
+    cluster_sync_relaxed();
+  }
+  __device__ __forceinline__ void csync_after_wo() {}
   // QK^T of pass hp against the K half of the block in `slot`:  S_hp[128 x 64 keys] = A_hp[128 x 64 dims] K_hp^T
   __device__ __forceinline__ void issue_qk(uint32_t slot, int hp) {
     const uint32_t kb = tc::smem_u32(sm.ring[slot]) + hp * 8192;
@@ -343,8 +407,9 @@ struct Issuer {
         tc::mma_bf16_ts(tm0 + T_O + 64 * hp, ta + 8 * ks, db + (uint64_t)(2 * ks), idesc, (accum || term > 0 || ks > 0) ? 1u : 0u);
     }
   }
-  __device__ __forceinline__ void att(bool kvi_keys, int nblk, const unsigned char*) {
+  __device__ __forceinline__ void att(bool kvi_keys, int nblk, const unsigned char*, size_t) {
     wait_ready();  // stacked queries written
+    if (nblk == 0) return;  // (a cluster rank without key blocks of its own)
     const uint32_t g0 = kvi_keys ? kvi_slot : g;  // slot parity of block jb = (g0 + jb) & 1
     if (kvi_keys) {
       tc::mbar_wait(&sm.wfill, n_kvi & 1);
@@ -402,7 +467,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
   const float* __restrict__ packed = a.packed;
   const int A = dm.n_agent, K = dm.n_mode, S = dm.n_scene, B = S * K, Th = dm.n_step_hist, T = dm.n_step, Tg = dm.n_step_gt;
   const int nT_map = (dm.n_pl + 63) / 64, nT_tl = (dm.n_tl + 63) / 64;
-  const int b = blockIdx.x, s = b / K;
+  const int rank = (int)cluster_ctarank(), n_cta = (int)cluster_nctarank();  // CTAs of a cluster share one scene-mode
+  const int b = blockIdx.x / n_cta, s = b / K;
   const int tid = threadIdx.x, warp = uniform(tid >> 5), lane = tid & 31;
   const size_t BA = (size_t)B * A;
   const int nkey_map = uniform(in.n_key_map[s]);
@@ -452,24 +518,37 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
       sm.type[ag][i] = live ? in.agent_type[sa * 3 + i] : (uint8_t)0;
     }
   }
+  // cluster ranks > 0 run the same program on private copies of the mutable global scratch (GRU hidden state, x0)
+  float* const hidden_base = rank == 0 ? a.sv.hidden : a.sv.hidden_x + (size_t)(rank - 1) * 3 * BA * D;
+  float* const x0_base = rank == 0 ? a.sv.x0 : a.sv.x0_x + (size_t)(rank - 1) * BA * D;
+  if (rank > 0) {
+    for (int L = 0; L < 3; ++L) {
+      const float4* src = reinterpret_cast<const float4*>(a.sv.hidden + ((size_t)L * BA + (size_t)b * A) * D);
+      float4* dst = reinterpret_cast<float4*>(hidden_base + ((size_t)L * BA + (size_t)b * A) * D);
+      for (int i = tid; i < A * (D / 4); i += THREADS) dst[i] = src[i];
+    }
+  }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
+  cluster_sync_all();  // barriers initialised and hidden copies taken in every CTA of the cluster
   const uint32_t tm0 = (uint32_t)uniform((int)sm.tmem_base);
 
   StepCfg cfg;
   cfg.nblk_map = (nkey_map + 63) / 64;
+  cfg.rank = rank;
+  cfg.n_cta = n_cta;
   cfg.kv_map = in.kv_map_tc + (size_t)s * nT_map * BLK;
   cfg.kv_map_layer_stride = (size_t)S * nT_map * BLK;
   cfg.kv_tl_layer_stride = (size_t)S * Th * nT_tl * BLK;
 
   if (warp == 9) {
     // ========================================================================================================== loader
-    if (lane == 0) {
+    {
       Loader ld(sm);
       for (int t = a.t_first; t <= a.t_last; ++t) {
         const int tl_t = min(t - 1, Th - 1);
-        cfg.nblk_tl = (in.n_key_tl[(size_t)s * Th + tl_t] + 63) / 64;
+        cfg.nblk_tl = (uniform(in.n_key_tl[(size_t)s * Th + tl_t]) + 63) / 64;
         cfg.kv_tl = in.kv_tl_tc + ((size_t)s * Th + tl_t) * nT_tl * BLK;
         enumerate_step(a, cfg, ld);
       }
@@ -492,7 +571,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
     const int ag = l & 63, upper = l >> 6;
     const int c0 = half * 64;
     const bool live = ag < A;
-    const bool writer = upper == 0 && live;  // the lane that owns global side effects of agent `ag`
+    const bool writer = upper == 0 && live && rank == 0;  // the lane that owns the global outputs of agent `ag`
+    const bool scratch_writer = upper == 0 && live;       // ... and this CTA's private scratch (x0)
     // Rows a + 64 duplicate rows a.  Only the query projection needs the duplicate (head-stacked attention), so the warps of
     // the upper lanes skip every other epilogue and just keep the barrier / mbarrier arrival counts.
     const bool lo_w = upper == 0;
@@ -501,11 +581,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
     uint32_t n_mma = 0, n_s = 0, n_o = 0, n_grant = 0, n_ln = 0, n_lp = 0;
     int n_mark = 0;
     auto mark = [&]() {
-      if (a.trace && b == 0 && tid == 0 && n_mark < 1000) a.trace[n_mark++] = clock64();
+      if (a.trace && blockIdx.x == 0 && tid == 0 && n_mark < 1000) a.trace[n_mark++] = clock64();
     };
     int n_dmark = 0, t_cur = 0;
     auto dmark = [&](int id) {  // detailed (id, clock) pairs of one warm step, both softmax groups' leaders
-      if (a.trace && b == 0 && (tid == 0 || tid == 128) && t_cur == a.t_first + 3 && n_dmark < 700) {
+      if (a.trace && blockIdx.x == 0 && (tid == 0 || tid == 128) && t_cur == a.t_first + 3 && n_dmark < 700) {
         long long* dst = a.trace + 1024 + (tid == 128 ? 1400 : 0) + 2 * n_dmark++;
         dst[0] = id;
         dst[1] = clock64();
@@ -599,8 +679,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
 
     const float sc = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e): softmax in base 2
 
-    // per-rollout constants of the tail -> shared memory
-    if (half == 0 && writer) {
+    // per-rollout constants of the tail -> shared memory (in every CTA of the cluster)
+    if (half == 0 && upper == 0 && live) {
       const int b2o[3] = {tbw::action_head_mlp_mean_0_fc_layers_2_bias, tbw::action_head_mlp_mean_1_fc_layers_2_bias,
                           tbw::action_head_mlp_mean_2_fc_layers_2_bias};
       const int lso[3] = {tbw::action_head_log_std_0, tbw::action_head_log_std_1, tbw::action_head_log_std_2};
@@ -716,14 +796,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
             if (lo_w) {
               if (Lx == 6) {
                 load_x(tg);
-                if (writer) {
-                  float* dst = a.sv.x0 + ba * D + c0;
+                if (scratch_writer) {
+                  float* dst = x0_base + ba * D + c0;
 #pragma unroll
                   for (int i = 0; i < 16; ++i)
                     reinterpret_cast<float4*>(dst)[i] = make_float4(tg[4 * i], tg[4 * i + 1], tg[4 * i + 2], tg[4 * i + 3]);
                 }
               } else if (live) {
-                const float* src = a.sv.x0 + ba * D + c0;  // written by this thread at Lx == 6
+                const float* src = x0_base + ba * D + c0;  // written by this thread at Lx == 6
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                   const float4 q = reinterpret_cast<const float4*>(src)[i];
@@ -808,8 +888,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
           float m_ref = -INFINITY, l_sum = 0.f;
           const uint32_t sbase = tm + T_ACC0 + 64 * half;
           const uint32_t obase = tm + T_O + 64 * half + 32 * upper;
+          // the agent->map attention is split over the cluster: this CTA owns key blocks rank, rank + n_cta, ...
+          const bool split = kind == 0 && n_cta > 1;
+          const int nblk_my = kind == 0 ? (nblk > rank ? (nblk - rank + n_cta - 1) / n_cta : 0) : nblk;
 #pragma unroll 1
-          for (int jb = 0; jb < nblk; ++jb) {
+          for (int jb = 0; jb < nblk_my; ++jb) {
+            const int key0 = (kind == 0 ? rank + jb * n_cta : jb) * 64;  // first key of this block
             tc::mbar_wait(&sm.s[half], n_s & 1);
             ++n_s;
             tc::tc_fence_after();
@@ -824,14 +908,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
 #pragma unroll
               for (int j = 0; j < 64; ++j)
                 if (!((en >> j) & 1ull)) sv_[j] = -INFINITY;
-            } else if (jb * 64 + 64 > nkey) {
+            } else if (key0 + 64 > nkey) {
 #pragma unroll
               for (int j = 0; j < 64; ++j)
-                if (jb * 64 + j >= nkey) sv_[j] = -INFINITY;
+                if (key0 + j >= nkey) sv_[j] = -INFINITY;
             }
-            float mx = sv_[0];
+            float mx4[4] = {sv_[0], sv_[1], sv_[2], sv_[3]};
 #pragma unroll
-            for (int j = 1; j < 64; ++j) mx = fmaxf(mx, sv_[j]);
+            for (int j = 4; j < 64; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], sv_[j]);
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
             float alpha = 1.f;
             bool resc = false;
             if (mx > m_ref + 8.0f) {
@@ -841,13 +926,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
               resc = jb > 0;
             }
             const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
-            float psum = 0.f;
+            float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int j = 0; j < 64; ++j) {
               sv_[j] = ex2_approx(sv_[j] + neg_m);
-              psum += sv_[j];
+              ps4[j & 3] += sv_[j];
             }
-            l_sum += psum;
+            l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
             {
               float ph[16], pl[16];
               tc::split32_packed(*reinterpret_cast<const float(*)[32]>(&sv_[0]), ph, pl);
@@ -874,15 +959,73 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
           }
           dmark(104 + Lx * 10);
           {
-            tc::mbar_wait(&sm.o[half], n_o & 1);
-            ++n_o;
-            tc::tc_fence_after();
             float o[32];
-            tc::tmem_ld32(obase, o);
-            tc::tmem_ld_wait();
-            const float inv = l_sum > 0.f ? 1.0f / l_sum : 0.f;
+            if (nblk_my > 0) {
+              tc::mbar_wait(&sm.o[half], n_o & 1);
+              ++n_o;
+              tc::tc_fence_after();
+              tc::tmem_ld32(obase, o);
+              tc::tmem_ld_wait();
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sm.xo[(c0 + 32 * upper + j) * MAXA + ag] = o[j] * inv;
+              for (int j = 0; j < 32; ++j) o[j] = 0.f;
+            }
+            float* xo_mine = &sm.xo[(c0 + 32 * upper) * MAXA + ag];  // this thread's 32 outputs: stride MAXA
+            if (split) {
+              // merge the online-softmax partials (O, m, l) of the cluster's CTAs; every CTA combines them in rank order, so
+              // all CTAs continue with bit-identical activations
+              float2* ml = reinterpret_cast<float2*>(&sm.red[0][0][0]);  // [256] (m, l) per worker thread (no LayerNorm in flight)
+              float4* xp = reinterpret_cast<float4*>(sm.xo);              // partial O as [8][256] float4: conflict-free 16-byte accesses
+#pragma unroll
+              for (int q = 0; q < 8; ++q) xp[q * WORKERS + tid] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+              ml[tid] = make_float2(m_ref, l_sum);
+              cluster_sync_all();  // every thread of the cluster (the issuer and loader warps join from their own programs)
+              float m_all = m_ref;
+              float2 mlr[4];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                mlr[r] = make_float2(-INFINITY, 0.f);
+                if (r < n_cta) {
+                  mlr[r] = r == rank ? make_float2(m_ref, l_sum) : ld_cluster_f32x2(mapa(tc::smem_u32(&ml[tid]), (uint32_t)r));
+                  m_all = fmaxf(m_all, mlr[r].x);
+                }
+              }
+              float acc[32], l_all = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+              const uint32_t xp_addr = tc::smem_u32(&xp[tid]);
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                if (r < n_cta) {
+                  const float w = mlr[r].x == -INFINITY ? 0.f : exp2f(mlr[r].x - m_all);
+                  l_all = fmaf(w, mlr[r].y, l_all);
+                  if (r == rank) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] = fmaf(w, o[j], acc[j]);
+                  } else {
+                    const uint32_t ra = mapa(xp_addr, (uint32_t)r);
+                    float4 pr_[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) pr_[q] = ld_cluster_f32x4(ra + q * WORKERS * 16);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                      acc[4 * q] = fmaf(w, pr_[q].x, acc[4 * q]);
+                      acc[4 * q + 1] = fmaf(w, pr_[q].y, acc[4 * q + 1]);
+                      acc[4 * q + 2] = fmaf(w, pr_[q].z, acc[4 * q + 2]);
+                      acc[4 * q + 3] = fmaf(w, pr_[q].w, acc[4 * q + 3]);
+                    }
+                  }
+                }
+              }
+              cluster_sync_relaxed();  // every CTA has consumed this CTA's partials (loads retired): xo may be overwritten
+              const float inv = l_all > 0.f ? 1.0f / l_all : 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) xo_mine[j * MAXA] = acc[j] * inv;
+            } else {
+              const float inv = l_sum > 0.f ? 1.0f / l_sum : 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) xo_mine[j * MAXA] = o[j] * inv;
+            }
           }
           worker_sync();
           if (lo_w) {
@@ -946,7 +1089,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         const float (*lp)[128] = sm.lp[n_lp & 1];
         dmark(200 + L * 10);
         fetch_params(10 + L);  // 10, 11 = GRU layers 1, 2; 12 = add_goal
-        float* hid = a.sv.hidden + ((size_t)L * BA + ba) * D + c0;
+        float* hid = hidden_base + ((size_t)L * BA + ba) * D + c0;
         if (lo_w) {
           float x[64];
           load_x(x);
@@ -1067,7 +1210,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
       }
       // ---- action head (action_head.py:70-87): per-type MLP 128 -> 128 -> 2, masked by type & valid, summed -------------------------------
       // the tail's ground-truth operands of this step are fetched now, so that their latency hides behind the head GEMMs
-      const bool tail_thread = half == 0 && writer;
+      const bool tail_thread = half == 0 && upper == 0 && live;  // runs in every CTA of the cluster (state stays replicated)
+      const bool out_w = rank == 0;                              // ... but only rank 0 writes the global outputs
       const bool has_gt = t < Tg;
       const size_t gidx = ((size_t)s * Tg + (has_gt ? t : 0)) * A + ag;
       float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1157,13 +1301,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
           pred.w = st.w + 0.1f * a_acc;
         }
         const size_t o = ba * T + (t - 1);
-        *reinterpret_cast<float4*>(a.out.preds + o * 4) = pred;
-        a.out.valid[o] = valid;
-        a.out.action_log_probs[o] = valid ? sm.tailc[2][ag] : 0.f;  // DiagGaussian log-prob of the deterministic sample, dynamics.py:77-80
-        a.out.latent_log_probs[o] = sm.tailc[3][ag];
-        if (a.out.trace_action_mean) {
-          a.out.trace_action_mean[o * 2] = mean0;
-          a.out.trace_action_mean[o * 2 + 1] = mean1;
+        if (out_w) {
+          *reinterpret_cast<float4*>(a.out.preds + o * 4) = pred;
+          a.out.valid[o] = valid;
+          a.out.action_log_probs[o] = valid ? sm.tailc[2][ag] : 0.f;  // DiagGaussian log-prob of the deterministic sample, dynamics.py:77-80
+          a.out.latent_log_probs[o] = sm.tailc[3][ag];
+          if (a.out.trace_action_mean) {
+            a.out.trace_action_mean[o * 2] = mean0;
+            a.out.trace_action_mean[o * 2 + 1] = mean1;
+          }
         }
         // Dynamics.override_states (dynamics.py:121-149)
         bool killed = sm.killed[ag] != 0;
@@ -1176,7 +1322,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
           sm.acc[ag] = g_acc;
           sm.yaw_rate[ag] = g_yr;
         }
-        a.out.override_masks[o] = ovr;
+        if (out_w) a.out.override_masks[o] = ovr;
         // TrafficRuleChecker.check, always-on subset (traffic_rule_checker.py:101-119,338-410,423-424,474-496)
         const bool out_t = nvalid && (ns.x > sm.map_boundary[1] || ns.x < sm.map_boundary[0] || ns.y > sm.map_boundary[3] || ns.y < sm.map_boundary[2]);
         bool outside = sm.sticky[0][ag] != 0, goal_r = sm.sticky[1][ag] != 0, dest_r = sm.sticky[2][ag] != 0;
@@ -1212,13 +1358,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         }
         const bool dest_t = !dest_r && nvalid && ((k_lane_t && pos_reached && rot_reached) || (k_edge_t && pos_reached));
         dest_r |= dest_t;
-        const size_t vs = BA * T;
-        a.out.violations[0 * vs + o] = outside;
-        a.out.violations[1 * vs + o] = out_t;
-        a.out.violations[2 * vs + o] = goal_r;
-        a.out.violations[3 * vs + o] = goal_t;
-        a.out.violations[4 * vs + o] = dest_r;
-        a.out.violations[5 * vs + o] = dest_t;
+        if (out_w) {
+          const size_t vs = BA * T;
+          a.out.violations[0 * vs + o] = outside;
+          a.out.violations[1 * vs + o] = out_t;
+          a.out.violations[2 * vs + o] = goal_r;
+          a.out.violations[3 * vs + o] = goal_t;
+          a.out.violations[4 * vs + o] = dest_r;
+          a.out.violations[5 * vs + o] = dest_t;
+        }
         // Dynamics.kill (dynamics.py:151-167): outside_map_this_step & ~gt_valid
         const bool kill = out_t && !gt_valid;
         killed |= kill;
@@ -1237,8 +1385,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
             reward = 0.0f - (0.1f * e_pos + 10.0f * e_rot + 0.1f * e_spd);
           }
         }
-        a.out.diffbar_rewards[o] = reward;
-        a.out.diffbar_rewards_valid[o] = rv;
+        if (out_w) {
+          a.out.diffbar_rewards[o] = reward;
+          a.out.diffbar_rewards_valid[o] = rv;
+        }
         // state for the next step
         sm.pose[ag] = ns;
         sm.valid[ag] = nvalid;
@@ -1269,6 +1419,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(sm.tmem_base, 512);
+  cluster_sync_all();  // no CTA leaves while a peer may still read its shared memory or arrive on its barrier
 }
 
 }  // namespace pr
@@ -1281,6 +1432,16 @@ bool tb::rollout_tc_supported(const TbDims& d, const TbRolloutIn& in) {
   return d.n_agent <= pr::MAXA;
 }
 
+int tb::rollout_tc_cluster_size(const TbDims& d) {
+  // One CTA per scene-mode leaves most of the 148 SMs idle for small batches; the agent->map attention (the largest part of
+  // a step) is then split over a cluster of 2 or 4 CTAs per scene-mode.
+  if (d.n_agent > pr::MAXA) return 1;
+  static const int forced = getenv("TB_CLUSTER") ? atoi(getenv("TB_CLUSTER")) : 0;
+  if (forced == 1 || forced == 2 || forced == 4) return forced;
+  const int B = d.n_scene * d.n_mode;
+  return B * 4 <= 148 ? 4 : (B * 2 <= 148 ? 2 : 1);
+}
+
 int tb::launch_rollout_tc(const TbDims& d, const TbRolloutIn& in, const float* packed, const StateView& sv, const TbRolloutOut& out,
                           int t_first, int t_last, cudaStream_t st) {
   static bool attr_set = false;
@@ -1290,7 +1451,20 @@ int tb::launch_rollout_tc(const TbDims& d, const TbRolloutIn& in, const float* p
     attr_set = true;
   }
   pr::Args a{d, in, packed, tc_blob(packed), sv, out, t_first, t_last, g_debug_trace};
-  pr::k_rollout_tc<<<d.n_scene * d.n_mode, pr::THREADS, smem, st>>>(a);
+  const int n_cta = rollout_tc_cluster_size(d);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(d.n_scene * d.n_mode * n_cta);
+  cfg.blockDim = dim3(pr::THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = n_cta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, pr::k_rollout_tc, a) != cudaSuccess) return TB_ERR_LAUNCH;
   count_launch();
   return launch_status();
 }
