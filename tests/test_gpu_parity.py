@@ -230,3 +230,27 @@ def test_abi_rejects_bad_arguments():
     assert L.tb_kv_project(9, 0, 16, 1, 16, 16, None) == -1
     assert L.tb_kv_project(2, 0, None, 1, 16, 16, None) == -2
     assert L.tb_kv_project(2, 0, 8, 1, 16, 16, None) == -5
+
+
+@pytest.mark.parametrize("n_cta", ["1", "2", "4"])
+def test_rollout_cluster_sizes_agree(n_cta, monkeypatch):
+    """The persistent decode kernel splits the agent->map attention over a cluster of 1 / 2 / 4 CTAs per scene-mode
+    (`rollout_tc_cluster_size`); every setting must reproduce the oracle (all boolean outputs bit-exact)."""
+    from golden_util import load_case
+    monkeypatch.setenv("TB_CLUSTER", n_cta)
+    gold, sd, batch, meta = load_case("s1_a64_p1024_k1")
+    eng = _engine(sd)
+    feat = eng.encode_scene(_cuda(batch))
+    out, ref = _run_jfp(eng, sd, batch, meta, feat)
+    _compare_rollout(out, ref, meta["S"], meta["K"])
+
+
+def test_rollout_two_kernel_path_agrees(monkeypatch):
+    """`TB_DISABLE_PERSIST=1` selects the per-step front / back kernels (the path used for more than 64 agents)."""
+    from golden_util import load_case
+    monkeypatch.setenv("TB_DISABLE_PERSIST", "1")
+    gold, sd, batch, meta = load_case("s3_a8_p64_k2")
+    eng = _engine(sd)
+    feat = eng.encode_scene(_cuda(batch))
+    out, ref = _run_jfp(eng, sd, batch, meta, feat)
+    _compare_rollout(out, ref, meta["S"], meta["K"])

@@ -60,9 +60,9 @@ bool rollout_tc_supported(const TbDims& d, const TbRolloutIn& in);
 int rollout_tc_cluster_size(const TbDims& d);  // CTAs per scene-mode (1, 2 or 4)
 int launch_rollout_tc(const TbDims& d, const TbRolloutIn& in, const float* packed, const StateView& sv, const TbRolloutOut& out,
                       int t_first, int t_last, cudaStream_t st);
-inline bool persist_enabled() {
-  static const bool on = !(getenv("TB_DISABLE_PERSIST") && getenv("TB_DISABLE_PERSIST")[0] == '1');
-  return on;
+inline bool persist_enabled() {  // read per call: tests toggle it
+  const char* e = getenv("TB_DISABLE_PERSIST");
+  return !(e && e[0] == '1');
 }
 inline bool tc_enabled() {
   static const bool on = !(getenv("TB_DISABLE_TC") && getenv("TB_DISABLE_TC")[0] == '1');

@@ -33,7 +33,7 @@ constexpr int THREADS = WORKERS + 64;
 constexpr int MAXA = 64;
 constexpr uint32_t BLK = 65536, HALF = 32768;
 constexpr uint32_t T_ACC0 = 0, T_ACC1 = 128, T_ACC2 = 256, T_A2 = 256, T_O = 256, T_A = 384;
-constexpr int N_PHASE = 15;  // parameter-vector sets: 9 attention layers, 3 GRU layers, add_goal, add_latent, head
+// parameter-vector sets ("phases"): 0-8 attention layers, 9-11 GRU layers, 12 add_goal, 13 add_latent, 14 head
 
 struct Smem {
   unsigned char ring[2][BLK];
@@ -107,6 +107,15 @@ __device__ __forceinline__ uint32_t mapa(uint32_t cta_smem_addr, uint32_t rank) 
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_smem_addr), "r"(rank));
   return r;
+}
+__device__ __forceinline__ void st_cluster_f32x4(uint32_t cluster_addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float2 v) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ float ld_cluster_f32(uint32_t cluster_addr) {
   float v;
@@ -318,8 +327,8 @@ struct Loader {  // run by a whole (converged) warp; one elected lane issues the
   // the two cluster barriers of a split layer's merge: the loader joins them after the Wo block is on its way
   __device__ __forceinline__ void csync_before_wo() {}
   __device__ __forceinline__ void csync_after_wo() {
-    cluster_sync_relaxed();
-    cluster_sync_relaxed();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cluster_sync_relaxed();
   }
 };
 
@@ -372,9 +381,9 @@ struct Issuer {
     kvi_slot = g & 1;
     ++g;
   }
-  __device__ __forceinline__ void csync_before_wo() {  // the issuer joins the merge's two cluster barriers right away
-    cluster_sync_relaxed();
-    cluster_sync_relaxed();
+  __device__ __forceinline__ void csync_before_wo() {  // the issuer joins the merge's four cluster barriers right away
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cluster_sync_relaxed();
   }
   __device__ __forceinline__ void csync_after_wo() {}
   // QK^T of pass hp against the K half of the block in `slot`:  S_hp[128 x 64 keys] = A_hp[128 x 64 dims] K_hp^T
@@ -583,6 +592,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
     auto mark = [&]() {
       if (a.trace && blockIdx.x == 0 && tid == 0 && n_mark < 1000) a.trace[n_mark++] = clock64();
     };
+#ifdef TB_TRACE_DETAIL
     int n_dmark = 0, t_cur = 0;
     auto dmark = [&](int id) {  // detailed (id, clock) pairs of one warm step, both softmax groups' leaders
       if (a.trace && blockIdx.x == 0 && (tid == 0 || tid == 128) && t_cur == a.t_first + 3 && n_dmark < 700) {
@@ -591,6 +601,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         dst[1] = clock64();
       }
     };
+#else
+    auto dmark = [](int) {};  // (build with -DTB_TRACE_DETAIL for per-phase marks, tools/trace_rollout.py)
+#endif
 
     auto signal_ready = [&]() {  // TMEM operand written / accumulator consumed -> issuer
       tc::tmem_st_wait();
@@ -714,7 +727,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
     for (int t = a.t_first; t <= a.t_last; ++t) {
       const int tl_t = min(t - 1, Th - 1);
       const int nkey_tl = uniform(in.n_key_tl[(size_t)s * Th + tl_t]);
+#ifdef TB_TRACE_DETAIL
       t_cur = t;
+#endif
       mark();
       // ---- validity of this step; interaction bypass decision -> issuer / loader ----------------------------------------
       const bool valid = sm.valid[ag] != 0;
@@ -864,7 +879,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
           write_A(T_A, v);
           signal_ready();  // -> Wq
           dmark(101 + Lx * 10);
-          commit_params();
+          // (layers whose attention is split over the cluster use the next-phase parameter buffer as merge scratch first)
+          const bool split_layer = kind == 0 && n_cta > 1;
+          if (!split_layer) commit_params();
           wait_gemm();
           dmark(102 + Lx * 10);
           {  // stacked query operand of pass `half`: own head's 32 dims, zeros in the twin head's dims
@@ -972,55 +989,85 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
             }
             float* xo_mine = &sm.xo[(c0 + 32 * upper) * MAXA + ag];  // this thread's 32 outputs: stride MAXA
             if (split) {
-              // merge the online-softmax partials (O, m, l) of the cluster's CTAs; every CTA combines them in rank order, so
-              // all CTAs continue with bit-identical activations
-              float2* ml = reinterpret_cast<float2*>(&sm.red[0][0][0]);  // [256] (m, l) per worker thread (no LayerNorm in flight)
-              float4* xp = reinterpret_cast<float4*>(sm.xo);              // partial O as [8][256] float4: conflict-free 16-byte accesses
+              // Merge of the online-softmax partials (O, m, l) of the cluster's CTAs, all traffic as remote STORES into
+              // distributed shared memory: reduce-scatter (CTA r receives everyone's partial of column range r and merges it),
+              // then all-gather of the merged, normalised ranges straight into every CTA's exchange buffer.
+              const int nq = 8 / n_cta;  // float4 per thread and range (the 32 outputs of a thread = 8 float4)
+              float4* xp = reinterpret_cast<float4*>(sm.xo);                        // slots [src rank][nq][256] float4
+              float2* mls = reinterpret_cast<float2*>(&sm.lp[(n_lp + 1) & 1][0][0]);  // [src rank][256] (m, l)
+              const uint32_t xp_addr = tc::smem_u32(xp), mls_addr = tc::smem_u32(mls), xo_addr = tc::smem_u32(sm.xo);
+              dmark(600 + Lx);
+              cluster_sync_relaxed();  // every CTA is done with its previous use of the exchange buffer
+              dmark(610 + Lx);
 #pragma unroll
-              for (int q = 0; q < 8; ++q) xp[q * WORKERS + tid] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-              ml[tid] = make_float2(m_ref, l_sum);
-              cluster_sync_all();  // every thread of the cluster (the issuer and loader warps join from their own programs)
-              float m_all = m_ref;
+              for (int q = 0; q < 8; ++q) {
+                const int dst = q / nq, qq = q % nq;
+                const float4 val = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                const uint32_t off = (uint32_t)(((rank * nq + qq) * WORKERS + tid) * 16);
+                if (dst == rank) xp[(rank * nq + qq) * WORKERS + tid] = val;
+                else st_cluster_f32x4(mapa(xp_addr, (uint32_t)dst) + off, val);
+              }
+              for (int dst = 0; dst < n_cta; ++dst) {
+                if (dst == rank) mls[rank * WORKERS + tid] = make_float2(m_ref, l_sum);
+                else st_cluster_f32x2(mapa(mls_addr, (uint32_t)dst) + (uint32_t)((rank * WORKERS + tid) * 8), make_float2(m_ref, l_sum));
+              }
+              dmark(620 + Lx);
+              cluster_sync_all();  // release / acquire: all partials of my range have landed
+              dmark(630 + Lx);
+              float m_all = -INFINITY;
               float2 mlr[4];
 #pragma unroll
               for (int r = 0; r < 4; ++r) {
-                mlr[r] = make_float2(-INFINITY, 0.f);
-                if (r < n_cta) {
-                  mlr[r] = r == rank ? make_float2(m_ref, l_sum) : ld_cluster_f32x2(mapa(tc::smem_u32(&ml[tid]), (uint32_t)r));
-                  m_all = fmaxf(m_all, mlr[r].x);
-                }
+                mlr[r] = r < n_cta ? mls[r * WORKERS + tid] : make_float2(-INFINITY, 0.f);
+                m_all = fmaxf(m_all, mlr[r].x);
               }
-              float acc[32], l_all = 0.f;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-              const uint32_t xp_addr = tc::smem_u32(&xp[tid]);
+              float l_all = 0.f, w[4];
 #pragma unroll
               for (int r = 0; r < 4; ++r) {
-                if (r < n_cta) {
-                  const float w = mlr[r].x == -INFINITY ? 0.f : exp2f(mlr[r].x - m_all);
-                  l_all = fmaf(w, mlr[r].y, l_all);
-                  if (r == rank) {
+                w[r] = mlr[r].x == -INFINITY ? 0.f : exp2f(mlr[r].x - m_all);
+                l_all = fmaf(w[r], mlr[r].y, l_all);
+              }
+              const float inv = l_all > 0.f ? 1.0f / l_all : 0.f;
+              float4 mg[4];  // merged outputs 4 * (rank * nq + qq) + e of this thread's (lane, pass)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[j] = fmaf(w, o[j], acc[j]);
-                  } else {
-                    const uint32_t ra = mapa(xp_addr, (uint32_t)r);
-                    float4 pr_[8];
+              for (int qq = 0; qq < 4; ++qq) {
+                mg[qq] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (qq < nq) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) pr_[q] = ld_cluster_f32x4(ra + q * WORKERS * 16);
+                  for (int r = 0; r < 4; ++r) {
+                    if (r < n_cta) {
+                      const float4 pv = xp[(r * nq + qq) * WORKERS + tid];
+                      mg[qq].x = fmaf(w[r], pv.x, mg[qq].x);
+                      mg[qq].y = fmaf(w[r], pv.y, mg[qq].y);
+                      mg[qq].z = fmaf(w[r], pv.z, mg[qq].z);
+                      mg[qq].w = fmaf(w[r], pv.w, mg[qq].w);
+                    }
+                  }
+                  mg[qq].x *= inv, mg[qq].y *= inv, mg[qq].z *= inv, mg[qq].w *= inv;
+                }
+              }
+              dmark(640 + Lx);
+              cluster_sync_relaxed();  // every CTA has consumed its slots: the exchange buffer becomes the [col][agent] output
+              dmark(650 + Lx);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                      acc[4 * q] = fmaf(w, pr_[q].x, acc[4 * q]);
-                      acc[4 * q + 1] = fmaf(w, pr_[q].y, acc[4 * q + 1]);
-                      acc[4 * q + 2] = fmaf(w, pr_[q].z, acc[4 * q + 2]);
-                      acc[4 * q + 3] = fmaf(w, pr_[q].w, acc[4 * q + 3]);
+              for (int qq = 0; qq < 4; ++qq) {
+                if (qq < nq) {
+                  const float e4[4] = {mg[qq].x, mg[qq].y, mg[qq].z, mg[qq].w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int j = 4 * (rank * nq + qq) + e;
+                    const uint32_t off = (uint32_t)(((c0 + 32 * upper + j) * MAXA + ag) * 4);
+                    for (int dst = 0; dst < n_cta; ++dst) {
+                      if (dst == rank) xo_mine[j * MAXA] = e4[e];
+                      else st_cluster_f32(mapa(xo_addr, (uint32_t)dst) + off, e4[e]);
                     }
                   }
                 }
               }
-              cluster_sync_relaxed();  // every CTA has consumed this CTA's partials (loads retired): xo may be overwritten
-              const float inv = l_all > 0.f ? 1.0f / l_all : 0.f;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) xo_mine[j * MAXA] = acc[j] * inv;
+              dmark(660 + Lx);
+              cluster_sync_all();  // release / acquire: the merged attention output is complete in every CTA
+              dmark(670 + Lx);
+              commit_params();
             } else {
               const float inv = l_sum > 0.f ? 1.0f / l_sum : 0.f;
 #pragma unroll
@@ -1436,7 +1483,8 @@ int tb::rollout_tc_cluster_size(const TbDims& d) {
   // One CTA per scene-mode leaves most of the 148 SMs idle for small batches; the agent->map attention (the largest part of
   // a step) is then split over a cluster of 2 or 4 CTAs per scene-mode.
   if (d.n_agent > pr::MAXA) return 1;
-  static const int forced = getenv("TB_CLUSTER") ? atoi(getenv("TB_CLUSTER")) : 0;
+  const char* env = getenv("TB_CLUSTER");  // development / test override
+  const int forced = env ? atoi(env) : 0;
   if (forced == 1 || forced == 2 || forced == 4) return forced;
   const int B = d.n_scene * d.n_mode;
   return B * 4 <= 148 ? 4 : (B * 2 <= 148 ? 2 : 1);
