@@ -215,6 +215,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     W = WORKLOAD
@@ -340,7 +343,10 @@ def run_ours(args):
             "roofline": {"kernel": "k_rollout_tc (persistent decode kernel: 90 steps x (embed, 9 attention layers, 3 GRU layers, "
                                    "add_goal, add_latent, action head, dynamics/rule-check tail), one CTA per scene-mode)",
                          "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                         "traffic": None, "peak_source": peak_src, "flops_per_launch": f_roll,
+                         "traffic": 11.24e9 if (world == 1 and S == 32) else None,
+                         "traffic_note": "dram read 9.78 GB + write 1.46 GB per launch, ncu --set full (profiles/r1d_k_rollout_tc.txt): "
+                                         "the 100 MB of key blocks stream from HBM at every one of the 90 steps",
+                         "peak_source": peak_src, "flops_per_launch": f_roll,
                          "avg_launch_ms": rollout_ms, "whole_step_tflops": f_total / (ms / args.steps * 1e-3) / 1e12,
                          "note": "algorithmic fp32-equivalent FLOPs (SURVEY 8d); the kernel issues 3 bf16 MMAs per logical "
                                  "product (bf16x3) on M=128 tiles holding 64 agents, and runs on B of the 148 SMs"},

@@ -42,7 +42,7 @@ struct Smem {
   float lp[2][16][128];  // parameter vectors of the current / next phase
   float emb_w1[384], emb_w2[1024], emb_b1[32], emb_b2[32], f_xy[24], f_yaw[48];
   float2 red[2][2][128];  // LayerNorm partials {sum, M2} [buffer][half][lane]
-  float mean_part[2][MAXA][2];
+  float mean_part[4][MAXA][2];  // action-mean partial sums of the 4 column quarters
   // simulation state of the scene-mode
   float4 pose[MAXA];  // x, y, yaw, spd
   float2 vel[MAXA];
@@ -585,6 +585,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
     // Rows a + 64 duplicate rows a.  Only the query projection needs the duplicate (head-stacked attention), so the warps of
     // the upper lanes skip every other epilogue and just keep the barrier / mbarrier arrival counts.
     const bool lo_w = upper == 0;
+    const int cs = c0 + 32 * upper;  // first of the 32 columns this thread owns in split epilogues
     const size_t ba = (size_t)b * A + (live ? ag : 0), sa = (size_t)s * A + (live ? ag : 0);
     const uint32_t tm = tm0 + ((uint32_t)(quad * 32) << 16);
     uint32_t n_mma = 0, n_s = 0, n_o = 0, n_grant = 0, n_ln = 0, n_lp = 0;
@@ -621,12 +622,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
 #pragma unroll
       for (int i = 0; i < 64; ++i) v[i] = xs_at(c0 + i);
     };
-    auto store_x = [&](const float (&v)[64]) {  // rows a and a + 64 hold the same values: the lower lane writes
-      if (upper == 0) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i) xs_at(c0 + i) = v[i];
-      }
-    };
     auto write_A = [&](uint32_t col, const float (&v)[64]) {  // columns c0 .. c0+63 of a K = 128 operand
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -648,16 +643,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         worker_sync();
         return;
       }
-      float sum = 0.f;
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < 64; ++i) sum += v[i];
+      for (int i = 0; i < 64; ++i) s4[i & 3] += v[i];
+      const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
       const float mloc = sum * (1.0f / 64);
-      float m2 = 0.f;
+      float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
         const float d = v[i] - mloc;
-        m2 = fmaf(d, d, m2);
+        q4[i & 3] = fmaf(d, d, q4[i & 3]);
       }
+      const float m2 = (q4[0] + q4[1]) + (q4[2] + q4[3]);
       const int buf = n_ln & 1;
       ++n_ln;
       sm.red[buf][half][l] = make_float2(sum, m2);
@@ -744,9 +741,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
       }
       // ---- state embedding: get_agent_attr_and_pe + agent_encoder (sc_input.py:142-165, input_pe_encoder.py:41-61) -----------
       {
-        const int part = tid >> 6;  // features [32 part, 32 part + 32) of agent ag
+        // the 4 threads of an agent (part = 0..3) each produce 8 of the 32 MLP outputs and 24 of the 96 PE values
+        const int part = tid >> 6;
         const float4 st = sm.pose[ag];
-        if (part == 0) {
+        {
           float at[12];
           at[0] = sm.vel[ag].x, at[1] = sm.vel[ag].y, at[2] = st.w, at[3] = sm.yaw_rate[ag], at[4] = sm.acc[ag];
 #pragma unroll
@@ -755,7 +753,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
             at[8 + i] = sm.type[ag][i] ? 1.f : 0.f;
           }
           at[11] = 0.f;
-          float h[32];
+          float h[32];  // hidden layer (computed by all 4 threads: 352 FMAs)
 #pragma unroll
           for (int o = 0; o < 32; ++o) {
             float acc = sm.emb_b1[o];
@@ -763,26 +761,35 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
             for (int k = 0; k < 12; ++k) acc = fmaf(at[k], sm.emb_w1[((k >> 2) * 32 + o) * 4 + (k & 3)], acc);
             h[o] = fmaxf(acc, 0.f);
           }
-#pragma unroll 4
-          for (int o = 0; o < 32; ++o) {
+#pragma unroll
+          for (int oo = 0; oo < 8; ++oo) {
+            const int o = 8 * part + oo;
             float acc = sm.emb_b2[o];
 #pragma unroll
             for (int k = 0; k < 32; ++k) acc = fmaf(h[k], sm.emb_w2[((k >> 2) * 32 + o) * 4 + (k & 3)], acc);
             sm.xs[o * MAXA + ag] = valid ? acc : 0.f;
           }
-        } else {
-#pragma unroll 4
-          for (int i = 0; i < 32; ++i) {
-            const int j = 32 * (part - 1) + i;  // PE element 0..95
-            float v;
-            if (j < 12) v = cosf(st.x * sm.f_xy[2 * j]);
-            else if (j < 24) v = sinf(st.x * sm.f_xy[2 * (j - 12) + 1]);
-            else if (j < 36) v = cosf(st.y * sm.f_xy[2 * (j - 24)]);
-            else if (j < 48) v = sinf(st.y * sm.f_xy[2 * (j - 36) + 1]);
-            else if (j < 72) v = cosf(st.z * sm.f_yaw[2 * (j - 48)]);
-            else v = sinf(st.z * sm.f_yaw[2 * (j - 72) + 1]);
-            sm.xs[(32 + j) * MAXA + ag] = valid ? v : 0.f;
+        }
+#pragma unroll 2
+        for (int i = 0; i < 24; ++i) {
+          // PE element j of [cos(x f_2k) k<12 | sin(x f_2k+1) | cos(y ..) | sin(y ..) | cos(yaw g_2k) k<24 | sin(yaw g_2k+1)]
+          const int j = 24 * part + i;
+          float base, f;
+          bool is_cos;
+          if (j < 48) {
+            const int jj = j < 24 ? j : j - 24;
+            base = j < 24 ? st.x : st.y;
+            is_cos = jj < 12;
+            f = sm.f_xy[2 * (is_cos ? jj : jj - 12) + (is_cos ? 0 : 1)];
+          } else {
+            const int jj = j - 48;
+            base = st.z;
+            is_cos = jj < 24;
+            f = sm.f_yaw[2 * (is_cos ? jj : jj - 24) + (is_cos ? 0 : 1)];
           }
+          float sn, cs_;
+          sincosf(base * f, &sn, &cs_);  // full-range path: arguments reach hundreds of radians
+          sm.xs[(32 + j) * MAXA + ag] = valid ? (is_cos ? cs_ : sn) : 0.f;
         }
       }
       mark();
@@ -1075,39 +1082,38 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
             }
           }
           worker_sync();
-          if (lo_w) {
+          // From here to the end of the layer the two lanes of an agent (rows a and a + 64) both write complete A operands, so
+          // both accumulator rows are valid and the epilogues that end in shared memory are split between them: the thread of
+          // lane l handles the 32 columns cs .. cs + 31 of its column half.
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = sm.xo[(c0 + i) * MAXA + ag];
-            write_A(T_A, v);
-          }
+          for (int i = 0; i < 64; ++i) v[i] = sm.xo[(c0 + i) * MAXA + ag];
+          write_A(T_A, v);
           signal_ready();  // -> Wo
           dmark(105 + Lx * 10);
           wait_gemm();
           dmark(106 + Lx * 10);
-          if (lo_w) {  // x += attention output (all rows have at least one enabled key here)
-#pragma unroll 1
-            for (int jj = 0; jj < 2; ++jj) {
-              float o32[32];
-              tc::tmem_ld32(tm + T_ACC0 + c0 + 32 * jj, o32);
-              tc::tmem_ld_wait();
+          {  // x += attention output (all rows have at least one enabled key here)
+            float o32[32];
+            tc::tmem_ld32(tm + T_ACC0 + cs, o32);
+            tc::tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) xs_at(c0 + 32 * jj + i) += o32[i] + lp[3][c0 + 32 * jj + i];
-            }
+            for (int i = 0; i < 32; ++i) xs_at(cs + i) += o32[i] + lp[3][cs + i];
           }
+          worker_sync();
         } else {
           commit_params();
         }
         {
           float x2[64];
-          if (lo_w) load_x(x2);
-          layernorm64(x2, lp[4], lp[5], lo_w);
-          if (lo_w) write_A(T_A, x2);
+          load_x(x2);
+          layernorm64(x2, lp[4], lp[5]);
+          write_A(T_A, x2);
         }
         signal_ready();  // -> W1
         dmark(107 + Lx * 10);
         wait_gemm();
         dmark(108 + Lx * 10);
-        if (lo_w) {
+        {
           float h1[64];
           load_acc(T_ACC0, h1);
 #pragma unroll
@@ -1118,12 +1124,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         dmark(109 + Lx * 10);
         wait_gemm();
         dmark(190 + Lx);
-        if (lo_w) {  // x = valid ? x + FFN : 0
-          float y[64];
-          load_acc(T_ACC0, y);
+        {  // x = valid ? x + FFN : 0
+          float y[32];
+          tc::tmem_ld32(tm + T_ACC0 + cs, y);
+          tc::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 64; ++i) y[i] = valid ? xs_at(c0 + i) + y[i] + lp[7][c0 + i] : 0.f;
-          store_x(y);
+          for (int i = 0; i < 32; ++i) xs_at(cs + i) = valid ? xs_at(cs + i) + y[i] + lp[7][cs + i] : 0.f;
         }
         ++n_lp;
       }
@@ -1136,15 +1142,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         const float (*lp)[128] = sm.lp[n_lp & 1];
         dmark(200 + L * 10);
         fetch_params(10 + L);  // 10, 11 = GRU layers 1, 2; 12 = add_goal
-        float* hid = hidden_base + ((size_t)L * BA + ba) * D + c0;
-        if (lo_w) {
+        float* hid = hidden_base + ((size_t)L * BA + ba) * D;
+        {  // both lanes of an agent write the operands x and h (valid accumulator rows for the split epilogues)
           float x[64];
           load_x(x);
           write_A(T_A, x);
           if (live) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float4 q = reinterpret_cast<const float4*>(hid)[i];
+              const float4 q = reinterpret_cast<const float4*>(hid + c0)[i];
               x[4 * i] = q.x, x[4 * i + 1] = q.y, x[4 * i + 2] = q.z, x[4 * i + 3] = q.w;
             }
           } else {
@@ -1158,14 +1164,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         commit_params();
         wait_gemm();
         dmark(202 + L * 10);
-        if (lo_w) {  // r * (W_hn h + b_hn) parked in the exchange buffer (free during the GRU; same thread reads it back)
-          float r[64], rh[64];
-          load_acc(T_ACC0, r);
-          load_acc(T_ACC1, rh);
+        {  // r * (W_hn h + b_hn) of this thread's 32 columns, parked in the exchange buffer (free during the GRU)
+          float r[32], rh[32];
+          tc::tmem_ld32(tm + T_ACC0 + cs, r);
+          tc::tmem_ld32(tm + T_ACC1 + cs, rh);
+          tc::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            const float rg = fast_sigmoid(r[i] + lp[0][c0 + i] + lp[3][c0 + i]);
-            sm.xo[(c0 + i) * MAXA + ag] = rg * (rh[i] + lp[5][c0 + i]);
+          for (int i = 0; i < 32; ++i) {
+            const float rg = fast_sigmoid(r[i] + lp[0][cs + i] + lp[3][cs + i]);
+            sm.xo[(cs + i) * MAXA + ag] = rg * (rh[i] + lp[5][cs + i]);
           }
         }
         tc::tc_fence_before();
@@ -1174,32 +1181,29 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         dmark(203 + L * 10);
         wait_gemm();
         dmark(204 + L * 10);
-        if (lo_w) {
-#pragma unroll 1
-          for (int jj = 0; jj < 2; ++jj) {
-            float z[32], n[32];
-            tc::tmem_ld32(tm + T_ACC0 + c0 + 32 * jj, z);
-            tc::tmem_ld32(tm + T_ACC1 + c0 + 32 * jj, n);
-            tc::tmem_ld_wait();
+        {
+          float z[32], n[32];
+          tc::tmem_ld32(tm + T_ACC0 + cs, z);
+          tc::tmem_ld32(tm + T_ACC1 + cs, n);
+          tc::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 hp4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (live) hp4 = reinterpret_cast<const float4*>(hid)[8 * jj + i];
-              const float hp_[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
-              float hn_[4];
+          for (int i = 0; i < 8; ++i) {
+            float4 hp4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) hp4 = reinterpret_cast<const float4*>(hid + cs)[i];
+            const float hp_[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
+            float hn_[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int c = 32 * jj + 4 * i + e;
-                const float zg = fast_sigmoid(z[4 * i + e] + lp[1][c0 + c] + lp[4][c0 + c]);
-                const float ng = fast_tanh(n[4 * i + e] + lp[2][c0 + c] + sm.xo[(c0 + c) * MAXA + ag]);
-                hn_[e] = (1.0f - zg) * ng + zg * hp_[e];
-              }
-              // h[:, ~valid] = 0; the next GRU layer sees the unmasked output, after the last layer x[~valid] = 0
-              if (live)
-                reinterpret_cast<float4*>(hid)[8 * jj + i] = valid ? make_float4(hn_[0], hn_[1], hn_[2], hn_[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) xs_at(c0 + 32 * jj + 4 * i + e) = (L == 2 && !valid) ? 0.f : hn_[e];
+            for (int e = 0; e < 4; ++e) {
+              const int c = cs + 4 * i + e;
+              const float zg = fast_sigmoid(z[4 * i + e] + lp[1][c] + lp[4][c]);
+              const float ng = fast_tanh(n[4 * i + e] + lp[2][c] + sm.xo[c * MAXA + ag]);
+              hn_[e] = (1.0f - zg) * ng + zg * hp_[e];
             }
+            // h[:, ~valid] = 0; the next GRU layer sees the unmasked output, after the last layer x[~valid] = 0
+            if (live)
+              reinterpret_cast<float4*>(hid + cs)[i] = valid ? make_float4(hn_[0], hn_[1], hn_[2], hn_[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) xs_at(cs + 4 * i + e) = (L == 2 && !valid) ? 0.f : hn_[e];
           }
         }
         ++n_lp;
@@ -1215,7 +1219,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         fetch_params(13 + j);  // 13 = add_latent, 14 = head
         const bool zv = j == 0 ? (sm.goal_valid[ag] != 0) : valid;
         const float* zin = (j == 0 ? a.sv.goal_in : a.sv.latent_in) + ba * D + c0;
-        if (lo_w) {
+        {
           float x[64], z[64];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -1232,7 +1236,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         commit_params();
         wait_gemm();
         dmark(302 + j * 10);
-        if (lo_w) {
+        {
           float h1[64];
           load_acc(T_ACC0, h1);
 #pragma unroll
@@ -1243,15 +1247,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         dmark(303 + j * 10);
         wait_gemm();
         dmark(304 + j * 10);
-        if (lo_w) {
-          float h2[64];
-          load_acc(T_ACC0, h2);
+        {  // split epilogue: this thread's 32 columns
+          float h2[32];
+          tc::tmem_ld32(tm + T_ACC0 + cs, h2);
+          tc::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            const float hz = fmaxf(h2[i] + lp[1][c0 + i], 0.f);
-            h2[i] = valid ? (zv ? hz : 0.f) + xs_at(c0 + i) : 0.f;
+          for (int i = 0; i < 32; ++i) {
+            const float hz = fmaxf(h2[i] + lp[1][cs + i], 0.f);
+            xs_at(cs + i) = valid ? (zv ? hz : 0.f) + xs_at(cs + i) : 0.f;
           }
-          store_x(h2);
         }
         ++n_lp;
       }
@@ -1270,7 +1274,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         const float (*lp)[128] = sm.lp[n_lp & 1];
         dmark(320);
         fetch_params(0);
-        if (lo_w) {
+        {
           float x[64];
           load_x(x);
           write_A(T_A, x);
@@ -1293,20 +1297,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         commit_params();
         wait_gemm();
         dmark(322);
-        if (lo_w) {
+        {  // split epilogue: partial dot products of this thread's 32 hidden columns (tcgen05.ld is warp-collective: every
+           // lane loads all three accumulators and masks the contribution)
           float m0 = 0.f, m1 = 0.f;
-          // tcgen05.ld is warp-collective: every lane loads all three accumulators and masks the contribution
 #pragma unroll 1
           for (int c3 = 0; c3 < 3; ++c3) {
-            float hdn[64];
-            load_acc(128 * c3, hdn);
+            float hdn[32];
+            tc::tmem_ld32(tm + 128 * c3 + cs, hdn);
+            tc::tmem_ld_wait();
             const bool on = sm.type[ag][c3] && valid;
             const float* w2 = &lp[3 + 2 * c3][0];  // Wt4[32][2][4]: (k, d) at ((k >> 2) * 2 + d) * 4 + (k & 3); 256 contiguous floats
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 64; ++i) {
-              const float hv = fmaxf(hdn[i] + lp[c3][c0 + i], 0.f);
-              const int k = c0 + i;
+            for (int i = 0; i < 32; ++i) {
+              const float hv = fmaxf(hdn[i] + lp[c3][cs + i], 0.f);
+              const int k = cs + i;
               s0 = fmaf(hv, w2[((k >> 2) * 2 + 0) * 4 + (k & 3)], s0);
               s1 = fmaf(hv, w2[((k >> 2) * 2 + 1) * 4 + (k & 3)], s1);
             }
@@ -1315,8 +1320,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
               m1 += s1;
             }
           }
-          sm.mean_part[half][ag][0] = m0;
-          sm.mean_part[half][ag][1] = m1;
+          sm.mean_part[2 * half + upper][ag][0] = m0;
+          sm.mean_part[2 * half + upper][ag][1] = m1;
         }
         ++n_lp;
         worker_sync();
@@ -1326,7 +1331,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
       dmark(400);
       // ---- per-agent tail: dynamics, override, rule checks, kill, goal_valid, reward, outputs ----------------------------------------------
       if (tail_thread) {
-        float mean0 = sm.mean_part[0][ag][0] + sm.mean_part[1][ag][0], mean1 = sm.mean_part[0][ag][1] + sm.mean_part[1][ag][1];
+        float mean0 = (sm.mean_part[0][ag][0] + sm.mean_part[1][ag][0]) + (sm.mean_part[2][ag][0] + sm.mean_part[3][ag][0]);
+        float mean1 = (sm.mean_part[0][ag][1] + sm.mean_part[1][ag][1]) + (sm.mean_part[2][ag][1] + sm.mean_part[3][ag][1]);
         if (valid) {
           mean0 += sm.tailc[0][ag];
           mean1 += sm.tailc[1][ag];
