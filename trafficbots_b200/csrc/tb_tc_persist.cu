@@ -584,7 +584,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
     const bool scratch_writer = upper == 0 && live;       // ... and this CTA's private scratch (x0)
     // Rows a + 64 duplicate rows a.  Only the query projection needs the duplicate (head-stacked attention), so the warps of
     // the upper lanes skip every other epilogue and just keep the barrier / mbarrier arrival counts.
-    const bool lo_w = upper == 0;
     const int cs = c0 + 32 * upper;  // first of the 32 columns this thread owns in split epilogues
     const size_t ba = (size_t)b * A + (live ? ag : 0), sa = (size_t)s * A + (live ? ag : 0);
     const uint32_t tm = tm0 + ((uint32_t)(quad * 32) << 16);
@@ -741,10 +740,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
       }
       // ---- state embedding: get_agent_attr_and_pe + agent_encoder (sc_input.py:142-165, input_pe_encoder.py:41-61) -----------
       {
-        // the 4 threads of an agent (part = 0..3) each produce 8 of the 32 MLP outputs and 24 of the 96 PE values
-        const int part = tid >> 6;
+        const int part = tid >> 6;  // features [32 part, 32 part + 32) of agent ag
         const float4 st = sm.pose[ag];
-        {
+        if (part == 0) {
           float at[12];
           at[0] = sm.vel[ag].x, at[1] = sm.vel[ag].y, at[2] = st.w, at[3] = sm.yaw_rate[ag], at[4] = sm.acc[ag];
 #pragma unroll
@@ -753,7 +751,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
             at[8 + i] = sm.type[ag][i] ? 1.f : 0.f;
           }
           at[11] = 0.f;
-          float h[32];  // hidden layer (computed by all 4 threads: 352 FMAs)
+          float h[32];
 #pragma unroll
           for (int o = 0; o < 32; ++o) {
             float acc = sm.emb_b1[o];
@@ -761,35 +759,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
             for (int k = 0; k < 12; ++k) acc = fmaf(at[k], sm.emb_w1[((k >> 2) * 32 + o) * 4 + (k & 3)], acc);
             h[o] = fmaxf(acc, 0.f);
           }
-#pragma unroll
-          for (int oo = 0; oo < 8; ++oo) {
-            const int o = 8 * part + oo;
+#pragma unroll 4
+          for (int o = 0; o < 32; ++o) {
             float acc = sm.emb_b2[o];
 #pragma unroll
             for (int k = 0; k < 32; ++k) acc = fmaf(h[k], sm.emb_w2[((k >> 2) * 32 + o) * 4 + (k & 3)], acc);
             sm.xs[o * MAXA + ag] = valid ? acc : 0.f;
           }
-        }
-#pragma unroll 2
-        for (int i = 0; i < 24; ++i) {
-          // PE element j of [cos(x f_2k) k<12 | sin(x f_2k+1) | cos(y ..) | sin(y ..) | cos(yaw g_2k) k<24 | sin(yaw g_2k+1)]
-          const int j = 24 * part + i;
-          float base, f;
-          bool is_cos;
-          if (j < 48) {
-            const int jj = j < 24 ? j : j - 24;
-            base = j < 24 ? st.x : st.y;
-            is_cos = jj < 12;
-            f = sm.f_xy[2 * (is_cos ? jj : jj - 12) + (is_cos ? 0 : 1)];
-          } else {
-            const int jj = j - 48;
-            base = st.z;
-            is_cos = jj < 24;
-            f = sm.f_yaw[2 * (is_cos ? jj : jj - 24) + (is_cos ? 0 : 1)];
+        } else {
+#pragma unroll 4
+          for (int i = 0; i < 32; ++i) {
+            const int j = 32 * (part - 1) + i;  // PE element 0..95
+            float v;
+            if (j < 12) v = cosf(st.x * sm.f_xy[2 * j]);
+            else if (j < 24) v = sinf(st.x * sm.f_xy[2 * (j - 12) + 1]);
+            else if (j < 36) v = cosf(st.y * sm.f_xy[2 * (j - 24)]);
+            else if (j < 48) v = sinf(st.y * sm.f_xy[2 * (j - 36) + 1]);
+            else if (j < 72) v = cosf(st.z * sm.f_yaw[2 * (j - 48)]);
+            else v = sinf(st.z * sm.f_yaw[2 * (j - 72) + 1]);
+            sm.xs[(32 + j) * MAXA + ag] = valid ? v : 0.f;
           }
-          float sn, cs_;
-          sincosf(base * f, &sn, &cs_);  // full-range path: arguments reach hundreds of radians
-          sm.xs[(32 + j) * MAXA + ag] = valid ? (is_cos ? cs_ : sn) : 0.f;
         }
       }
       mark();
@@ -814,62 +803,66 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         if (nblk > 0) {
           if (kind == 2) {
             // K|V of the block input x0 (agent_interaction.py:52: tgt = attn_to_map_aware_feature for all 3 layers)
+            // (both lanes of an agent write the operand, so both accumulator rows are valid and each lane converts 32 of the
+            // agent's 64 columns of its column half into the key block)
             float tg[64];
-            if (lo_w) {
-              if (Lx == 6) {
-                load_x(tg);
-                if (scratch_writer) {
-                  float* dst = x0_base + ba * D + c0;
+            if (Lx == 6) {
+              load_x(tg);
+              if (scratch_writer) {
+                float* dst = x0_base + ba * D + c0;
 #pragma unroll
-                  for (int i = 0; i < 16; ++i)
-                    reinterpret_cast<float4*>(dst)[i] = make_float4(tg[4 * i], tg[4 * i + 1], tg[4 * i + 2], tg[4 * i + 3]);
-                }
-              } else if (live) {
-                const float* src = x0_base + ba * D + c0;  // written by this thread at Lx == 6
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const float4 q = reinterpret_cast<const float4*>(src)[i];
-                  tg[4 * i] = q.x, tg[4 * i + 1] = q.y, tg[4 * i + 2] = q.z, tg[4 * i + 3] = q.w;
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 64; ++i) tg[i] = 0.f;
+                for (int i = 0; i < 16; ++i)
+                  reinterpret_cast<float4*>(dst)[i] = make_float4(tg[4 * i], tg[4 * i + 1], tg[4 * i + 2], tg[4 * i + 3]);
               }
+            } else if (live) {
+              const float* src = x0_base + ba * D + c0;  // written at Lx == 6 by the lower lane of this agent (barriers since)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float4 q = __ldcg(reinterpret_cast<const float4*>(src) + i);  // L2: written by another warp of this CTA
+                tg[4 * i] = q.x, tg[4 * i + 1] = q.y, tg[4 * i + 2] = q.z, tg[4 * i + 3] = q.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 64; ++i) tg[i] = 0.f;
             }
-            layernorm64(tg, lp[8], lp[9], lo_w);
-            if (lo_w) write_A(T_A, tg);
+            layernorm64(tg, lp[8], lp[9]);
+            write_A(T_A, tg);
             signal_ready();  // -> Wk (ACC0), Wv (ACC1)
             dmark(500 + Lx);
             wait_gemm();
             dmark(510 + Lx);
-            if (lo_w) tc::mbar_wait(&sm.grant, n_grant & 1);
+            tc::mbar_wait(&sm.grant, n_grant & 1);
             ++n_grant;
             dmark(520 + Lx);
-            if (lo_w) {
+            {
               unsigned char* blk = sm.ring[*reinterpret_cast<volatile int*>(&sm.kvi_slot)];
-              load_acc(T_ACC0, tg);  // K[ag, c0 .. c0+63]: key row ag of K-block `half`
+              float kk[32];
+              tc::tmem_ld32(tm + T_ACC0 + cs, kk);  // K[ag, cs .. cs+31]: key row ag of K-block `half`
+              tc::tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 64; ++i) tg[i] += lp[10][c0 + i];
+              for (int i = 0; i < 32; ++i) kk[i] += lp[10][cs + i];
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
+              for (int c = 0; c < 4; ++c) {
                 uint4 hi, lo;
-                tc::split8(tg + 8 * c, hi, lo);
-                const uint32_t off = half * 8192 + tc::sw128_off(ag, c);
+                tc::split8(kk + 8 * c, hi, lo);
+                const uint32_t off = half * 8192 + tc::sw128_off(ag, 4 * upper + c);
                 *reinterpret_cast<uint4*>(blk + off) = hi;
                 *reinterpret_cast<uint4*>(blk + 16384 + off) = lo;
               }
               dmark(530 + Lx);
-              load_acc(T_ACC1, tg);  // V[ag, c0 .. c0+63] -> V^T rows d = c0 + i, key column ag
+              tc::tmem_ld32(tm + T_ACC1 + cs, kk);  // V[ag, cs .. cs+31] -> V^T rows d = cs + i, key column ag
+              tc::tmem_ld_wait();
               unsigned char* vt = blk + HALF + (ag & 7) * 2;
               const uint32_t kc = (uint32_t)(ag >> 3);
 #pragma unroll
-              for (int i = 0; i < 64; i += 2) {
-                const __nv_bfloat162 hh = __floats2bfloat162_rn(tg[i] + lp[11][c0 + i], tg[i + 1] + lp[11][c0 + i + 1]);
+              for (int i = 0; i < 32; i += 2) {
+                const float v0 = kk[i] + lp[11][cs + i], v1 = kk[i + 1] + lp[11][cs + i + 1];
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
                 const float2 hf = __bfloat1622float2(hh);
-                const __nv_bfloat162 ll = __floats2bfloat162_rn(tg[i] + lp[11][c0 + i] - hf.x, tg[i + 1] + lp[11][c0 + i + 1] - hf.y);
+                const __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                  const int d = c0 + i + e;
+                  const int d = cs + i + e;
                   const uint32_t off = (uint32_t)((d >> 3) * 1024 + (d & 7) * 128) + ((kc ^ (uint32_t)(d & 7)) << 4);
                   *reinterpret_cast<__nv_bfloat16*>(vt + off) = e ? hh.y : hh.x;
                   *reinterpret_cast<__nv_bfloat16*>(vt + 16384 + off) = e ? ll.y : ll.x;
@@ -1054,20 +1047,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
                 }
               }
               dmark(640 + Lx);
-              cluster_sync_relaxed();  // every CTA has consumed its slots: the exchange buffer becomes the [col][agent] output
+              cluster_sync_relaxed();  // every CTA has consumed its slots: the exchange buffer becomes the merged output
               dmark(650 + Lx);
+              // merged output of (lane, pass) thread `tid`, float4 q, at xp[q * 256 + tid] in EVERY CTA (16-byte remote stores)
 #pragma unroll
               for (int qq = 0; qq < 4; ++qq) {
                 if (qq < nq) {
-                  const float e4[4] = {mg[qq].x, mg[qq].y, mg[qq].z, mg[qq].w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const int j = 4 * (rank * nq + qq) + e;
-                    const uint32_t off = (uint32_t)(((c0 + 32 * upper + j) * MAXA + ag) * 4);
-                    for (int dst = 0; dst < n_cta; ++dst) {
-                      if (dst == rank) xo_mine[j * MAXA] = e4[e];
-                      else st_cluster_f32(mapa(xo_addr, (uint32_t)dst) + off, e4[e]);
-                    }
+                  const uint32_t off = (uint32_t)((((rank * nq + qq) * WORKERS) + tid) * 16);
+                  for (int dst = 0; dst < n_cta; ++dst) {
+                    if (dst == rank) xp[(rank * nq + qq) * WORKERS + tid] = mg[qq];
+                    else st_cluster_f32x4(mapa(xp_addr, (uint32_t)dst) + off, mg[qq]);
                   }
                 }
               }
@@ -1085,8 +1074,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
           // From here to the end of the layer the two lanes of an agent (rows a and a + 64) both write complete A operands, so
           // both accumulator rows are valid and the epilogues that end in shared memory are split between them: the thread of
           // lane l handles the 32 columns cs .. cs + 31 of its column half.
+          if (split) {  // merged outputs live as [float4 q][worker thread]: heads 2 half / 2 half + 1 of agent ag
+            const float4* xp = reinterpret_cast<const float4*>(sm.xo);
 #pragma unroll
-          for (int i = 0; i < 64; ++i) v[i] = sm.xo[(c0 + i) * MAXA + ag];
+            for (int which = 0; which < 2; ++which) {
+              const int src_tid = half * 128 + 64 * which + ag;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 t4 = xp[q * WORKERS + src_tid];
+                v[32 * which + 4 * q] = t4.x, v[32 * which + 4 * q + 1] = t4.y, v[32 * which + 4 * q + 2] = t4.z, v[32 * which + 4 * q + 3] = t4.w;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = sm.xo[(c0 + i) * MAXA + ag];
+          }
           write_A(T_A, v);
           signal_ready();  // -> Wo
           dmark(105 + Lx * 10);
