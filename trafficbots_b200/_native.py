@@ -89,7 +89,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    extra = os.environ.get("TB_NVCC_FLAGS", "").split()  # e.g. -DTB_TRACE_DETAIL (tools/trace_rollout.py)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise TbError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

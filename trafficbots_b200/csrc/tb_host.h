@@ -36,9 +36,13 @@ struct StateView {
   float* kv_int;       // [3,B,A,256] interaction K|V of the current step
   float* goal_in;      // [B,A,128]  add_goal.mlp_in(goal_feature) before mask/ReLU (loop invariant)
   float* latent_in;    // [B,A,128]  add_latent.mlp_in(latent_sample) before mask/ReLU (loop invariant)
-  float* hidden_x;     // [n_cluster-1][3,B*A,128] private GRU hidden copies of the cluster ranks > 0 (persistent kernel)
-  float* x0_x;         // [n_cluster-1][B,A,128]
-  float4* dest_nodes;  // [B,A,20]   destination polyline nodes (x, y, unit direction), invalid nodes at 1e30
+  // Scratch of the persistent kernel in "agent-minor" layout [.., 32 column quads, A] float4 (the 32 lanes of a warp = 32
+  // consecutive agents read 512 contiguous bytes), one copy per CTA of a cluster:
+  float4* hidden_t;    // [n_cluster][3][B][32][A]  working copy of the GRU hidden state (converted from / to `hidden`)
+  float4* x0_t;        // [n_cluster][B][32][A]     input of the interaction block
+  float4* goal_in_t;   // [B][32][A]   = goal_in
+  float4* latent_in_t; // [B][32][A]   = latent_in
+  float4* dest_nodes;  // [B][20][A]   destination polyline nodes (x, y, unit direction), invalid nodes at 1e30
 };
 
 StateView state_view(const TbDims& d, void* base);

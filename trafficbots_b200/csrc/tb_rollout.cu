@@ -16,7 +16,7 @@ static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct StateLayout {
   size_t off[TB_STATE_N_FIELD];
-  size_t x0, kv_int, goal_in, latent_in, dest_nodes, hidden_x, x0_x, total;
+  size_t x0, kv_int, goal_in, latent_in, dest_nodes, hidden_t, x0_t, goal_in_t, latent_in_t, total;
 };
 
 static StateLayout state_layout(const TbDims& d) {
@@ -42,9 +42,11 @@ static StateLayout state_layout(const TbDims& d) {
   L.goal_in = put(BA * D * sizeof(float));
   L.latent_in = put(BA * D * sizeof(float));
   L.dest_nodes = put(BA * TB_PL_NODE * 4 * sizeof(float));
-  const size_t n_extra = (size_t)(rollout_tc_cluster_size(d) - 1);
-  L.hidden_x = put(n_extra * 3 * BA * D * sizeof(float));
-  L.x0_x = put(n_extra * BA * D * sizeof(float));
+  const size_t n_cta = d.n_agent <= 64 ? (size_t)rollout_tc_cluster_size(d) : 0;  // persistent-kernel scratch
+  L.hidden_t = put(n_cta * 3 * BA * D * sizeof(float));
+  L.x0_t = put(n_cta * BA * D * sizeof(float));
+  L.goal_in_t = put(BA * D * sizeof(float));
+  L.latent_in_t = put(BA * D * sizeof(float));
   L.total = o;
   return L;
 }
@@ -67,8 +69,10 @@ StateView state_view(const TbDims& d, void* base) {
   v.goal_in = reinterpret_cast<float*>(p + L.goal_in);
   v.latent_in = reinterpret_cast<float*>(p + L.latent_in);
   v.dest_nodes = reinterpret_cast<float4*>(p + L.dest_nodes);
-  v.hidden_x = reinterpret_cast<float*>(p + L.hidden_x);
-  v.x0_x = reinterpret_cast<float*>(p + L.x0_x);
+  v.hidden_t = reinterpret_cast<float4*>(p + L.hidden_t);
+  v.x0_t = reinterpret_cast<float4*>(p + L.x0_t);
+  v.goal_in_t = reinterpret_cast<float4*>(p + L.goal_in_t);
+  v.latent_in_t = reinterpret_cast<float4*>(p + L.latent_in_t);
   return v;
 }
 
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(NT) k_rollout_init(TbDims dm, TbRolloutIn in, 
         const float nrm = sqrtf(ux * ux + uy * uy);
         o = make_float4(in.map_pos[nd * 2], in.map_pos[nd * 2 + 1], ux / nrm, uy / nrm);  // zero-length dir -> NaN (compares false)
       }
-      sv.dest_nodes[ba * TB_PL_NODE + n] = o;
+      sv.dest_nodes[((size_t)b * TB_PL_NODE + n) * A + a] = o;
     }
   }
   // GRU hidden starts at zero (agent_temporal.py:131, traffic_bots.py:159)
@@ -176,6 +180,10 @@ __global__ void __launch_bounds__(NT) k_rollout_init(TbDims dm, TbRolloutIn in, 
     }
   }
   store_tile<R>(sm.x, sv.goal_in + ((size_t)b * A + a0) * D, nrow);
+  for (int i = tid; i < R * (D / 4); i += NT) {  // agent-minor copy for the persistent kernel
+    const int r = i % R, c4 = i / R;
+    if (r < nrow) sv.goal_in_t[((size_t)b * (D / 4) + c4) * A + a0 + r] = reinterpret_cast<const float4*>(sm.x + r * D)[c4];
+  }
   __syncthreads();
 
   // ---- add_latent.mlp_in(latent_sample): Linear(16,128)-ReLU-Linear(128,128) -----------------------------------------
@@ -193,6 +201,10 @@ __global__ void __launch_bounds__(NT) k_rollout_init(TbDims dm, TbRolloutIn in, 
   });
   __syncthreads();
   store_tile<R>(sm.x, sv.latent_in + ((size_t)b * A + a0) * D, nrow);
+  for (int i = tid; i < R * (D / 4); i += NT) {
+    const int r = i % R, c4 = i / R;
+    if (r < nrow) sv.latent_in_t[((size_t)b * (D / 4) + c4) * A + a0 + r] = reinterpret_cast<const float4*>(sm.x + r * D)[c4];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------

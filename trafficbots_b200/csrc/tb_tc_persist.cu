@@ -527,20 +527,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
       sm.type[ag][i] = live ? in.agent_type[sa * 3 + i] : (uint8_t)0;
     }
   }
-  // cluster ranks > 0 run the same program on private copies of the mutable global scratch (GRU hidden state, x0)
-  float* const hidden_base = rank == 0 ? a.sv.hidden : a.sv.hidden_x + (size_t)(rank - 1) * 3 * BA * D;
-  float* const x0_base = rank == 0 ? a.sv.x0 : a.sv.x0_x + (size_t)(rank - 1) * BA * D;
-  if (rank > 0) {
-    for (int L = 0; L < 3; ++L) {
-      const float4* src = reinterpret_cast<const float4*>(a.sv.hidden + ((size_t)L * BA + (size_t)b * A) * D);
-      float4* dst = reinterpret_cast<float4*>(hidden_base + ((size_t)L * BA + (size_t)b * A) * D);
-      for (int i = tid; i < A * (D / 4); i += THREADS) dst[i] = src[i];
+  // Mutable global scratch (GRU hidden state, x0) is private to every CTA of a cluster and kept in agent-minor layout
+  // [32 column quads][A] float4: lane = agent, so a warp reads / writes 512 contiguous bytes per instruction.
+  float4* const hid_t = a.sv.hidden_t + ((size_t)rank * 3 * B + b) * 32 * A;  // + L * B * 32 * A per layer
+  float4* const x0_t = a.sv.x0_t + ((size_t)rank * B + b) * 32 * A;
+  const float4* const goal_in_t = a.sv.goal_in_t + (size_t)b * 32 * A;
+  const float4* const latent_in_t = a.sv.latent_in_t + (size_t)b * 32 * A;
+  for (int L = 0; L < 3; ++L) {  // hidden state of the previous launch (or zeros after tb_rollout_init) -> working copy
+    const float4* src = reinterpret_cast<const float4*>(a.sv.hidden + ((size_t)L * BA + (size_t)b * A) * D);
+    float4* dst = hid_t + (size_t)L * B * 32 * A;
+    for (int i = tid; i < A * 32; i += THREADS) {
+      const int ag_ = i % A, c4 = i / A;
+      dst[c4 * A + ag_] = src[ag_ * 32 + c4];
     }
   }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  cluster_sync_all();  // barriers initialised and hidden copies taken in every CTA of the cluster
+  cluster_sync_all();  // barriers initialised and working copies taken in every CTA of the cluster
   const uint32_t tm0 = (uint32_t)uniform((int)sm.tmem_base);
 
   StepCfg cfg;
@@ -809,16 +813,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
             if (Lx == 6) {
               load_x(tg);
               if (scratch_writer) {
-                float* dst = x0_base + ba * D + c0;
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  reinterpret_cast<float4*>(dst)[i] = make_float4(tg[4 * i], tg[4 * i + 1], tg[4 * i + 2], tg[4 * i + 3]);
+                for (int i = 0; i < 16; ++i) x0_t[(c0 / 4 + i) * A + ag] = make_float4(tg[4 * i], tg[4 * i + 1], tg[4 * i + 2], tg[4 * i + 3]);
               }
             } else if (live) {
-              const float* src = x0_base + ba * D + c0;  // written at Lx == 6 by the lower lane of this agent (barriers since)
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float4 q = __ldcg(reinterpret_cast<const float4*>(src) + i);  // L2: written by another warp of this CTA
+              for (int i = 0; i < 16; ++i) {  // written at Lx == 6 by the lower lane of this agent (CTA barriers since)
+                const float4 q = x0_t[(c0 / 4 + i) * A + ag];
                 tg[4 * i] = q.x, tg[4 * i + 1] = q.y, tg[4 * i + 2] = q.z, tg[4 * i + 3] = q.w;
               }
             } else {
@@ -1144,7 +1145,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         const float (*lp)[128] = sm.lp[n_lp & 1];
         dmark(200 + L * 10);
         fetch_params(10 + L);  // 10, 11 = GRU layers 1, 2; 12 = add_goal
-        float* hid = hidden_base + ((size_t)L * BA + ba) * D;
+        float4* hid = hid_t + (size_t)L * B * 32 * A + ag;  // column quad c4 of this agent at hid[c4 * A]
         {  // both lanes of an agent write the operands x and h (valid accumulator rows for the split epilogues)
           float x[64];
           load_x(x);
@@ -1152,7 +1153,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
           if (live) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float4 q = reinterpret_cast<const float4*>(hid + c0)[i];
+              const float4 q = hid[(c0 / 4 + i) * A];
               x[4 * i] = q.x, x[4 * i + 1] = q.y, x[4 * i + 2] = q.z, x[4 * i + 3] = q.w;
             }
           } else {
@@ -1191,7 +1192,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4 hp4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) hp4 = reinterpret_cast<const float4*>(hid + cs)[i];
+            if (live) hp4 = hid[(cs / 4 + i) * A];
             const float hp_[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
             float hn_[4];
 #pragma unroll
@@ -1203,7 +1204,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
             }
             // h[:, ~valid] = 0; the next GRU layer sees the unmasked output, after the last layer x[~valid] = 0
             if (live)
-              reinterpret_cast<float4*>(hid + cs)[i] = valid ? make_float4(hn_[0], hn_[1], hn_[2], hn_[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+              hid[(cs / 4 + i) * A] = valid ? make_float4(hn_[0], hn_[1], hn_[2], hn_[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int e = 0; e < 4; ++e) xs_at(cs + 4 * i + e) = (L == 2 && !valid) ? 0.f : hn_[e];
           }
@@ -1220,13 +1221,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         dmark(300 + j * 10);
         fetch_params(13 + j);  // 13 = add_latent, 14 = head
         const bool zv = j == 0 ? (sm.goal_valid[ag] != 0) : valid;
-        const float* zin = (j == 0 ? a.sv.goal_in : a.sv.latent_in) + ba * D + c0;
+        const float4* zin = (j == 0 ? goal_in_t : latent_in_t) + (c0 / 4) * A + ag;
         {
           float x[64], z[64];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live && zv) q = __ldg(reinterpret_cast<const float4*>(zin) + i);
+            if (live && zv) q = __ldg(zin + i * A);
             z[4 * i] = fmaxf(q.x, 0.f), z[4 * i + 1] = fmaxf(q.y, 0.f), z[4 * i + 2] = fmaxf(q.z, 0.f), z[4 * i + 3] = fmaxf(q.w, 0.f);
           }
           write_A(T_A2, z);
@@ -1398,12 +1399,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
         const float k_dest_thresh = sm.tailc[8][ag];
         const bool k_lane_t = (sm.tflag[ag] & 1) != 0, k_edge_t = (sm.tflag[ag] & 2) != 0;
         const float hx = cosf(ns.z), hy = sinf(ns.z);
-        const float4* dn = a.sv.dest_nodes + ba * TB_PL_NODE;
+        const float4* dn = a.sv.dest_nodes + (size_t)b * TB_PL_NODE * A + ag;
 #pragma unroll
         for (int n0 = 0; n0 < TB_PL_NODE; n0 += 10) {
           float4 nd[10];
 #pragma unroll
-          for (int n = 0; n < 10; ++n) nd[n] = __ldg(dn + n0 + n);
+          for (int n = 0; n < 10; ++n) nd[n] = __ldg(dn + (n0 + n) * A);
 #pragma unroll
           for (int n = 0; n < 10; ++n) {
             const float dx = ns.x - nd[n].x, dy = ns.y - nd[n].y;
@@ -1459,6 +1460,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
     }
     mark();
     // ---- simulation state back to global memory (chunked stepping, final-state outputs) -------------------------------------------
+    worker_sync();
+    if (rank == 0) {  // GRU hidden state: working copy -> the ABI's [3, B*A, 128] layout
+      for (int L = 0; L < 3; ++L) {
+        float4* dst = reinterpret_cast<float4*>(a.sv.hidden + ((size_t)L * BA + (size_t)b * A) * D);
+        const float4* src = hid_t + (size_t)L * B * 32 * A;
+        for (int i = tid; i < A * 32; i += WORKERS) {
+          const int ag_ = i / 32, c4 = i % 32;
+          dst[ag_ * 32 + c4] = __ldcg(src + c4 * A + ag_);
+        }
+      }
+    }
     if (half == 0 && writer) {
       *reinterpret_cast<float4*>(a.sv.agent_state + ba * 4) = sm.pose[ag];
       a.sv.vel[ba * 2] = sm.vel[ag].x;
