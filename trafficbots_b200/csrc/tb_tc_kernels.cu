@@ -133,16 +133,17 @@ __device__ __forceinline__ void st_row128(uint32_t taddr, const float (&v)[128])
 // LayerNorm of a register row, written as the bf16 hi / lo A operand (row r of the 128-row tiles)
 __device__ __forceinline__ void ln_row_to_A(const float (&v)[128], const float* __restrict__ g, const float* __restrict__ b,
                                             unsigned char* a_hi, unsigned char* a_lo, int r) {
-  float s = 0.f;
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < 128; ++i) s += v[i];
-  const float mean = s * (1.0f / 128);
-  float q = 0.f;
+  for (int i = 0; i < 128; ++i) s4[i & 3] += v[i];
+  const float mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / 128);
+  float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < 128; ++i) {
     const float d = v[i] - mean;
-    q = fmaf(d, d, q);
+    q4[i & 3] = fmaf(d, d, q4[i & 3]);
   }
+  const float q = (q4[0] + q4[1]) + (q4[2] + q4[3]);
   const float rstd = 1.0f / sqrtf(q * (1.0f / 128) + LN_EPS);
 #pragma unroll
   for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -277,9 +278,10 @@ __global__ void __launch_bounds__(128, 1) k_map_polyline_tc(TbDims dm, TbSceneIn
       sm.row_valid[r] = valid;
     }
     st_row128(TX, v);
-    float* x0row = x0_scratch + ((size_t)blockIdx.x * 128 + r) * 128;
+    // per-CTA scratch in row-minor layout [32 column quads][128 rows] float4: a warp touches 512 contiguous bytes
+    float4* x0col = reinterpret_cast<float4*>(x0_scratch) + (size_t)blockIdx.x * 32 * 128 + r;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) reinterpret_cast<float4*>(x0row)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    for (int i = 0; i < 32; ++i) x0col[i * 128] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     __syncthreads();
     if (tid < 8) {
       bool any = false;
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(128, 1) k_map_polyline_tc(TbDims dm, TbSceneIn
       if (L > 0) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float4 t = reinterpret_cast<const float4*>(x0row)[i];
+          const float4 t = x0col[i * 128];
           v[4 * i] = t.x, v[4 * i + 1] = t.y, v[4 * i + 2] = t.z, v[4 * i + 3] = t.w;
         }
       }
