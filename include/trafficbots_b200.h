@@ -244,6 +244,46 @@ int32_t tb_step_back(const TbDims* dims, const TbRolloutIn* in, const float* pac
 int32_t tb_rollout(const TbDims* dims, const TbRolloutIn* in, const float* packed, void* state,
                    const TbRolloutOut* out, void* stream);
 
+/* ---------------------------------------------------------------- pre-rollout heads ----- */
+
+typedef enum tb_gru {
+  TB_GRU_POLICY = 0,        /* model.agent_temporal.rnn                                   */
+  TB_GRU_LATENT_PRIOR = 1,  /* model.latent_encoder.agent_temporal_prior.rnn              */
+  TB_GRU_LATENT_POST = 2,   /* model.latent_encoder.agent_temporal_post.rnn               */
+  TB_GRU_DEST = 3           /* model.goal_manager.goal_predictor.gru_as.rnn               */
+} tb_gru;
+
+/* `MultiAgentGRULoop.forward`, 3-D branch (models/modules/agent_temporal.py:133-146: 3-layer GRU over the frames, hidden
+ * state of invalid agents zeroed after every frame, outputs zeroed where invalid) fused with the temporal aggregation
+ * that follows it in the reference:
+ *   mode 0: `TemporalAggregate` max_valid (agent_temporal.py:31-32,43-44)            -> latent encoder (latent_encoder.py:131-137)
+ *   mode 1: last valid frame of (GRU output + input)  (goal_manager.py:298-300, last_valid)  -> destination predictor
+ * x [n_batch, n_frame, n_agent, 128], valid [n_batch, n_frame, n_agent]; every t_stride-th frame is used.
+ * out [n_batch, n_agent, 128], out_valid [n_batch, n_agent] = valid.any(frames). */
+int32_t tb_gru_sequence(int32_t which, int32_t mode, const float* x, const uint8_t* valid, int32_t n_batch, int32_t n_frame,
+                        int32_t n_agent, int32_t t_stride, const float* packed, float* out, uint8_t* out_valid, void* stream);
+
+typedef enum tb_mlp {
+  TB_MLP_LATENT_PRIOR_MEAN = 0, /* model.latent_encoder.latent_prior_dist.mlp_mean : 128 -> 128 -> 16 */
+  TB_MLP_LATENT_POST_MEAN = 1   /* model.latent_encoder.latent_post_dist.mlp_mean                     */
+} tb_mlp;
+
+/* `MLP.forward` Linear-ReLU-Linear with the valid mask (models/modules/mlp.py:66-85; latent mean: latent_encoder.py:195-199).
+ * x [n_row,128], valid [n_row] -> y [n_row, n_out]. */
+int32_t tb_mlp_head(int32_t which, const float* x, const uint8_t* valid, int64_t n_row, const float* packed, float* y,
+                    void* stream);
+
+/* `DestPredictor.forward`, mode mlp (models/goal_manager.py:228-246,301-307,328-333) after the GRU (tb_gru_sequence
+ * TB_GRU_DEST mode 1 gives `tgt`, `tgt_valid`): logits over the P polylines of every agent from the pairwise MLP
+ * [map_feature[p], tgt[a]] -> 128 -> 128 -> 1 (LayerNorm + ReLU), polyline-type masks, and the normalisation of
+ * `Categorical(logits=)` (models/modules/distributions.py:161-165).
+ * map_feature [S,P,128], map_feature_valid [S,P], map_type [S,P,11], tgt [S,A,128], tgt_valid [S,A], agent_type [S,A,3]
+ * -> logp [S,A,P], probs [S,A,P].  workspace: tb_dest_workspace_bytes, 256-byte aligned. */
+size_t tb_dest_workspace_bytes(int32_t n_scene, int32_t n_agent, int32_t n_pl);
+int32_t tb_dest_logits(int32_t n_scene, int32_t n_agent, int32_t n_pl, const float* map_feature,
+                       const uint8_t* map_feature_valid, const uint8_t* map_type, const float* tgt, const uint8_t* tgt_valid,
+                       const uint8_t* agent_type, const float* packed, void* workspace, float* logp, float* probs, void* stream);
+
 /* Self-test of the tensor-core GEMM machinery (tcgen05.mma, TMEM, bulk-async weight staging, bf16x3 operand split):
  * d[128,128] = a[128,128] @ W^T for packed tensor-core weight block `block` (0 <= block < tb_tc_block_count());
  * mode 0: A operand staged in shared memory, mode 1: A operand in tensor memory. */

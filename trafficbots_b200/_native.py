@@ -28,6 +28,9 @@ STATUS = {0: "TB_OK", -1: "TB_ERR_BAD_SHAPE", -2: "TB_ERR_NULL", -3: "TB_ERR_LAU
 # tb_block
 BLOCK_MAP_DENSETNT, BLOCK_MAP_SELF_ATTN, BLOCK_AS2PL, BLOCK_AS2TL, BLOCK_INTERACTION, BLOCK_LATENT_PRIOR_INT, \
     BLOCK_LATENT_POST_INT = range(7)
+# tb_gru / tb_mlp
+GRU_POLICY, GRU_LATENT_PRIOR, GRU_LATENT_POST, GRU_DEST = range(4)
+MLP_LATENT_PRIOR_MEAN, MLP_LATENT_POST_MEAN = range(2)
 # tb_state_field
 (STATE_AGENT_STATE, STATE_VALID, STATE_KILLED, STATE_VEL, STATE_ACC, STATE_YAW_RATE, STATE_GOAL_VALID, STATE_STICKY,
  STATE_HIDDEN) = range(9)
@@ -37,6 +40,7 @@ EXPORTS = (
     "tb_pack_weights", "tb_encode_workspace_bytes", "tb_encode_scene", "tb_kv_project", "tb_xlayer",
     "tb_rollout_state_bytes", "tb_rollout_state_offset", "tb_rollout_init", "tb_rollout_steps", "tb_step_front", "tb_step_back", "tb_rollout",
     "tb_launch_count", "tb_kv_tc_bytes", "tb_tc_block_count", "tb_tc_first_block", "tb_tc_selftest",
+    "tb_gru_sequence", "tb_mlp_head", "tb_dest_workspace_bytes", "tb_dest_logits",
 )
 
 
@@ -159,6 +163,15 @@ def lib() -> C.CDLL:
     L.tb_tc_first_block.argtypes = [C.c_int32]
     L.tb_tc_selftest.restype = C.c_int32
     L.tb_tc_selftest.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.tb_gru_sequence.restype = C.c_int32
+    L.tb_gru_sequence.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.tb_mlp_head.restype = C.c_int32
+    L.tb_mlp_head.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.tb_dest_workspace_bytes.restype = C.c_size_t
+    L.tb_dest_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    L.tb_dest_logits.restype = C.c_int32
+    L.tb_dest_logits.argtypes = [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 11
     _lib = L
     return L
 

@@ -143,6 +143,76 @@ class Engine:
                      "tb_xlayer")
         return dst
 
+    # ------------------------------------------------------------------------------------------------ pre-rollout heads
+    def gru_sequence(self, which: int, mode: int, x: Tensor, valid: Tensor, t_stride: int = 1):
+        """`MultiAgentGRULoop` over the frames + temporal aggregation (`tb_gru_sequence`).  x [B,T,A,128], valid [B,T,A]
+        -> (out [B,A,128], out_valid [B,A])."""
+        B, T, A, _ = x.shape
+        out = torch.empty(B, A, 128, device=self.device)
+        ov = torch.empty(B, A, dtype=torch.bool, device=self.device)
+        with torch.cuda.device(self.device):
+            nt.check(self.lib.tb_gru_sequence(which, mode, nt.dev_ptr(x, "f32", (B, T, A, 128), "x"),
+                                              nt.dev_ptr(valid, "u8", (B, T, A), "valid"), B, T, A, t_stride,
+                                              self.packed.data_ptr(), out.data_ptr(), ov.data_ptr(), nt.current_stream_ptr()),
+                     "tb_gru_sequence")
+        return out, ov
+
+    def latent_encoder(self, feat: Mapping[str, Tensor], posterior: bool = False, temporal_down_sample_rate: int = 5):
+        """`LatentEncoder.forward` (models/latent_encoder.py:95-147): every `temporal_down_sample_rate`-th frame of the
+        agent features through the policy's agent->map / agent->traffic-light blocks (shared weights), the latent encoder's
+        own interaction block and GRU, max over the valid frames, and the mean MLP.  Returns (mean [S,A,16], valid [S,A]);
+        the std is the constant `exp(log_std)` parameter.  `feat`: the dict of `encode_scene` (posterior: encoded with the
+        full-horizon tensors)."""
+        d = temporal_down_sample_rate
+        av = feat["agent_feature_valid"][:, ::d].contiguous()
+        x = feat["agent_feature"][:, ::d].contiguous()
+        tv = feat["tl_feature_valid"][:, ::d].contiguous()
+        S, T, A, _ = x.shape
+        TL = tv.shape[2]
+        kv_tl = feat["_kv_tl"][:, :, ::d].contiguous()  # [3,S,T,TL,256]
+        x = x.view(S, T * A, 128)
+        avf = av.view(S, T * A)
+        for L in range(3):
+            x = self.xlayer(nt.BLOCK_AS2PL, L, x, avf, feat["_kv_map"][L], feat["map_feature_valid"])
+        x = x.view(S * T, A, 128)
+        avb = av.view(S * T, A)
+        for L in range(3):
+            x = self.xlayer(nt.BLOCK_AS2TL, L, x, avb, kv_tl[L].reshape(S * T, TL, 256), tv.view(S * T, TL))
+        block = nt.BLOCK_LATENT_POST_INT if posterior else nt.BLOCK_LATENT_PRIOR_INT
+        x0 = x
+        for L in range(3):  # tgt = the block input for all layers (agent_interaction.py:52), eye mask
+            kv = self.kv_project(block, L, x0)
+            x = self.xlayer(block, L, x, avb, kv, avb, mask_self=True)
+        single = avb.sum(-1, keepdim=True) == 1  # scenes with exactly one valid agent bypass the block (:61-77)
+        x = torch.where(single.unsqueeze(-1), x0, x)
+        agg, v = self.gru_sequence(nt.GRU_LATENT_POST if posterior else nt.GRU_LATENT_PRIOR, 0, x.view(S, T, A, 128), av)
+        mean = torch.empty(S, A, 16, device=self.device)
+        with torch.cuda.device(self.device):
+            nt.check(self.lib.tb_mlp_head(nt.MLP_LATENT_POST_MEAN if posterior else nt.MLP_LATENT_PRIOR_MEAN, agg.data_ptr(),
+                                          v.data_ptr(), S * A, self.packed.data_ptr(), mean.data_ptr(), nt.current_stream_ptr()),
+                     "tb_mlp_head")
+        return mean, v
+
+    def dest_predictor(self, feat: Mapping[str, Tensor], agent_type: Tensor, map_type: Tensor):
+        """`DestPredictor.forward`, mode mlp (models/goal_manager.py:228-246,294-333).  Returns (probs [S,A,P],
+        logp [S,A,P], valid [S,A])."""
+        af, av = feat["agent_feature"], feat["agent_feature_valid"]
+        S, T, A, _ = af.shape
+        P = feat["map_feature"].shape[1]
+        tgt, v = self.gru_sequence(nt.GRU_DEST, 1, af, av)
+        need = self.lib.tb_dest_workspace_bytes(S, A, P)
+        ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        logp = torch.empty(S, A, P, device=self.device)
+        probs = torch.empty(S, A, P, device=self.device)
+        p = nt.dev_ptr
+        with torch.cuda.device(self.device):
+            nt.check(self.lib.tb_dest_logits(S, A, P, p(feat["map_feature"], "f32", (S, P, 128), "map_feature"),
+                                             p(feat["map_feature_valid"], "u8", (S, P), "map_feature_valid"),
+                                             p(map_type, "u8", (S, P, 11), "map/type"), tgt.data_ptr(), v.data_ptr(),
+                                             p(agent_type, "u8", (S, A, 3), "agent/type"), self.packed.data_ptr(), ws.data_ptr(),
+                                             logp.data_ptr(), probs.data_ptr(), nt.current_stream_ptr()), "tb_dest_logits")
+        return probs, logp, v
+
     # ------------------------------------------------------------------------------------------------ rollout
     def _rollout_structs(self, feat, gt, tf_mask, agent_type, agent_size, raw_map, latent_sample, latent_logp, dest,
                          goal_valid, goal_gt, n_mode, n_step):
