@@ -2,8 +2,9 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one pass of the hot path over one batch of synthetic scenes: scene encoding (`tb_encode_scene`)
-followed by the 90-step closed-loop rollout of every scene-mode (`tb_rollout`).  Workload at N=1 = BASELINE.json
+One "step" = one pass of the hot path over one batch of synthetic scenes (a "scene" = encode + prior
+latent + destination prediction + K rollouts): scene encoding (`tb_encode_scene`), the pre-rollout heads (prior latent
+encoder, destination predictor) and the 90-step closed-loop rollout of every scene-mode (`tb_rollout`).  Workload at N=1 = BASELINE.json
 configs[1]: 32 scenes, 64 agents, 1024 map polylines, 91 frames, K=1.  With N>1 GPUs every rank processes its
 own batch of 32 scenes (scene sharding, weak scaling, no data-path collective).
 
@@ -108,19 +109,10 @@ class ClockSampler:
 
 
 def make_inputs(n_scene, n_agent, n_pl, n_mode, seed):
-    """synthetic batch + the per-mode rollout inputs that the pre-rollout heads would provide (prior latent sample
-    and destination; those heads are SURVEY 8f "next" rows): latent ~ N(0, 0.37^2) (= exp(log_std -1)), GT destinations."""
+    """synthetic batch (trafficbots_b200.synthetic)."""
     from trafficbots_b200 import synthetic
     batch = synthetic.make_batch(n_scene, n_agent=n_agent, n_pl=n_pl, seed=seed)
-    g = torch.Generator().manual_seed(seed + 99)
-    B = n_scene * n_mode
-    extra = {
-        "latent_sample": torch.randn(B, n_agent, 16, generator=g) * 0.37,
-        "latent_logp": torch.zeros(B, n_agent),
-        "dest": batch["agent/dest"].repeat_interleave(n_mode, 0).contiguous(),
-        "goal_valid": batch["history/agent/valid"].any(1).repeat_interleave(n_mode, 0).contiguous(),
-    }
-    return batch, extra
+    return batch, {}
 
 
 USED_KEYS = ("map/valid", "map/type", "map/pos", "map/dir", "map/boundary", "agent/valid", "agent/pos", "agent/yaw_bbox",
@@ -131,41 +123,47 @@ USED_KEYS = ("map/valid", "map/type", "map/pos", "map/dir", "map/boundary", "age
 
 
 def run_step(eng, cb, ex, n_mode, n_step, out=None):
-    """device-resident step through the thin C-ABI driver"""
+    """device-resident step through the thin C-ABI driver: encode -> prior latent -> destination -> rollout.  With K = 1
+    the single mode is the deterministic one (prior mean, arg-max destination: waymo_motion.py:489-500)."""
     from trafficbots_b200 import engine as E, host
     feat = eng.encode_scene(cb)
+    lat_mean, _ = eng.latent_encoder(feat)
+    probs, _logp, _ = eng.dest_predictor(feat, cb["agent/type"], cb["map/type"])
+    dest = probs.argmax(-1)
     gt = E.gt_from_batch(cb)
     tf = host.teacher_forcing_mask(gt["valid"], 10, 10)
-    return eng.rollout(feat, gt, tf, cb["agent/type"], cb["agent/size"], E.raw_map_from_batch(cb), ex["latent_sample"],
-                       ex["latent_logp"], ex["dest"], ex["goal_valid"], cb["agent/goal"], n_mode=n_mode, n_step=n_step, out=out)
+    goal_valid = cb["history/agent/valid"].any(1)
+    lat_logp = ex["latent_logp"]
+    return eng.rollout(feat, gt, tf, cb["agent/type"], cb["agent/size"], E.raw_map_from_batch(cb), lat_mean, lat_logp, dest,
+                       goal_valid, cb["agent/goal"], n_mode=n_mode, n_step=n_step, out=out)
 
 
 def run_step_public(module, cb, ex):
-    """the call a user of the reference makes (validation_step's hot path): encode_input_features + reactive_replay-style
-    rollout through the `WaymoMotion` surface; returns the RolloutBuffer."""
+    """the call sequence a user of the reference makes (validation_step's joint_future_pred leg, waymo_motion.py:581-598)
+    through the `WaymoMotion` surface: encode_input_features -> latent_encoder -> pred_goal -> joint_future_pred."""
     feat = module.model.encode_input_features(cb)
-    tf = module.teacher_forcing_joint_future_pred.get(cb["agent/valid"], 0)
-    return module.reactive_replay(cb, feat, tf, ex["latent_sample"], ex["dest"], ex["goal_valid"], deterministic_latent=True,
-                                  deterministic_action=True, require_vis_dict=False)
+    latent = module.model.latent_encoder(**feat)
+    goal = module.model.goal_manager.pred_goal(agent_type=cb["agent/type"], map_type=cb["map/type"], agent_state=None, **feat)
+    goal_valid = cb["history/agent/valid"].any(1)
+    buf, _goal_sample, _goal_logp = module.joint_future_pred(cb, feat, latent, goal, goal_valid, require_vis_dict=False)
+    return buf
 
 
 # ----------------------------------------------------------------------------------------------------------
 def cpu_reference_rate(n_scene, repeats=1, seed=1234):
-    """the oracle port of the reference's CPU path (encode_scene + rollout as the reference implements them:
-    K|V re-projected every step) on `n_scene` scenes of the bench workload; returns scenes/s and seconds."""
+    """the oracle port of the reference's CPU path (encode_scene + latent prior + destination predictor + rollout as the
+    reference implements them: K|V re-projected every step) on `n_scene` scenes of the bench workload; returns scenes/s
+    and seconds."""
     import trafficbots_oracle as orc
     from trafficbots_b200 import weights
     W = WORKLOAD
     sd = weights.init_state_dict(2023)
-    batch, ex = make_inputs(n_scene, W["n_agent"], W["n_pl"], 1, seed)
+    batch, _ = make_inputs(n_scene, W["n_agent"], W["n_pl"], 1, seed)
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        feat = orc.encode_scene(sd, batch)
-        rin = orc.rollout_inputs(batch, feat, 1)
-        tf = orc.teacher_forcing_mask(rin["gt_valid"], 10, 10)
-        orc.rollout(sd, **rin, tf_mask=tf, latent_sample=ex["latent_sample"], latent_logp=ex["latent_logp"], dest=ex["dest"],
-                    goal_valid=ex["goal_valid"], goal_gt=batch["agent/goal"], step_end=W["n_step"])
+        with torch.no_grad():  # encode -> prior latent -> destination predictor -> rollout (K = 1: the deterministic mode)
+            orc.joint_future_pred(sd, batch, k=1, sample_seed=0, step_end=W["n_step"])
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return n_scene / best, best
@@ -194,7 +192,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{n} scenes/step (bounded sample of the 32-scene batch), 64 agents, 1024 polylines, K=1, "
-                               "encode + 90-step closed-loop rollout, reference CPU algorithm (oracle port)"},
+                               "encode + prior latent + destination predictor + 90-step closed-loop rollout, reference CPU algorithm (oracle port)"},
         "cpu_baseline": {"value": value, "unit": "scenes/s", "cores": cores, "kind": "port",
                          "sample": f"{n} scenes x {args.steps} steps, torch {torch.__version__} CPU fp32, {cores} threads"},
         "e2e": {"value": value, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -226,12 +224,11 @@ def run_ours(args):
     eng = E.Engine(sd, dev)
     batch, ex = make_inputs(S, A, P, K, seed=1000 + 100 * rank)
     host_batch = host.pin_batch({k: batch[k] for k in USED_KEYS})
-    host_ex = host.pin_batch(ex)
     cb = host.batch_to_device(host_batch, dev)
-    cex = host.batch_to_device(host_ex, dev)
+    cex = {"latent_logp": torch.zeros(S * K, A, device=dev)}  # log-prob of the deterministic latent: not part of the timed math
     out = eng.alloc_outputs(S * K, A, T)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    h2d = sum(v.numel() * v.element_size() for v in host_batch.values()) + sum(v.numel() * v.element_size() for v in host_ex.values())
+    h2d = sum(v.numel() * v.element_size() for v in host_batch.values())
 
     def barrier():
         if world > 1:
@@ -268,17 +265,15 @@ def run_ours(args):
 
     def e2e_step():
         cbe = host.batch_to_device(host_batch, dev)
-        cexe = host.batch_to_device(host_ex, dev)
-        buf = run_step_public(module, cbe, cexe)
+        buf = run_step_public(module, cbe, None)  # RolloutBuffer after flatten_repeat: [S, A, K, T, ...]
         for name in ("preds", "valid", "override_masks", "diffbar_rewards", "diffbar_rewards_valid", "action_log_probs",
                      "latent_log_probs"):
-            host_res[name].copy_(getattr(buf, name), non_blocking=True)
+            host_res[name].copy_(getattr(buf, name).squeeze(2), non_blocking=True)
         for i, name in enumerate(E.VIOLATION_KEYS):
-            host_res["violations"][i].copy_(buf.violations[name], non_blocking=True)
+            host_res["violations"][i].copy_(buf.violations[name].squeeze(2), non_blocking=True)
         if world > 1:  # the metrics reduction: one packed all-gather per step
-            fr = lambda x: x.unsqueeze(2)  # noqa: E731  K = 1
-            local = parallel.pack_scene_metrics(fr(buf.preds), fr(buf.valid), {k2: fr(v) for k2, v in buf.violations.items()},
-                                                fr(buf.diffbar_rewards), cbe["agent/pos"], cbe["agent/valid"])
+            local = parallel.pack_scene_metrics(buf.preds, buf.valid, buf.violations, buf.diffbar_rewards, cbe["agent/pos"],
+                                                cbe["agent/valid"])
             parallel.all_gather_scenes(local, world * S)
         return buf
     for _ in range(2):
@@ -300,8 +295,10 @@ def run_ours(args):
     feat = eng.encode_scene(cb)
     gt = E.gt_from_batch(cb)
     tf = host.teacher_forcing_mask(gt["valid"], 10, 10)
+    lat_mean, _ = eng.latent_encoder(feat)
+    dest = eng.dest_predictor(feat, cb["agent/type"], cb["map/type"])[0].argmax(-1)
     rollout_ms = eng.profile_rollout(feat, gt, tf, cb["agent/type"], cb["agent/size"], E.raw_map_from_batch(cb),
-                                     cex["latent_sample"], cex["latent_logp"], cex["dest"], cex["goal_valid"],
+                                     lat_mean, cex["latent_logp"], dest, cb["history/agent/valid"].any(1),
                                      cb["agent/goal"], n_mode=K, n_step=T, out=out)
     torch.cuda.synchronize()
 
@@ -333,8 +330,8 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (bf16x3 split operands on tcgen05, fp32 accumulate)", "data": "synthetic",
             "config": {"workload": f"{S} scenes/GPU/step, {A} agents, {P} map polylines, 40 TL, K={K}, encode_scene + {T}-step "
-                                   "closed-loop rollout (BASELINE.json configs[1]); latent sample and destination are inputs "
-                                   "(pre-rollout heads = SURVEY 8f)",
+                                   "closed-loop rollout (BASELINE.json configs[1]), incl. the pre-rollout heads (prior latent encoder, "
+                                   "destination predictor; the K = 1 mode is the deterministic one)",
                        "l2": "256 MiB flush write between timed iterations", "timing": "CUDA events per step, summed, max over ranks",
                        "weights": "seeded random init (no checkpoint distributable)"},
             "e2e": {"value": world * S * args.steps / (ms_e2e * 1e-3), "unit": "scenes/s", "h2d_bytes_per_step": h2d,

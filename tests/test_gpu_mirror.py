@@ -1,6 +1,7 @@
 """GPU: the reference-shaped Python surface (`WaymoMotion.joint_future_pred / reactive_replay / forward`) drives the CUDA
-library and reproduces the oracle / golden vectors.  The prior latent and the destination distribution (SURVEY 8f "next"
-heads) are taken from the oracle and handed over as the distribution objects the reference's methods expect."""
+library and reproduces the oracle / golden vectors.  The first tests take the prior latent and the destination distribution
+from the oracle (as the distribution objects the reference's methods expect); the last one runs the library's own
+pre-rollout heads (`model.latent_encoder`, `model.goal_manager.pred_goal`)."""
 import pytest
 import torch
 
@@ -100,3 +101,26 @@ def test_repack_after_parameter_update():
     f2 = m.model.encode_input_features(cb)["map_feature"]
     valid = gold["enc/map_feature_valid"].cuda()
     assert float(((f2 - f1)[valid] - 1.0).abs().max()) <= 1e-5  # the bias shift shows up: weights were re-packed
+
+
+@pytest.mark.parametrize("case", ["cfg1_s1_a8_p64_k1", "s3_a8_p64_k2"])
+def test_full_pipeline_with_library_heads(case):
+    """validation_step's joint_future_pred leg entirely on the library: encode_input_features -> model.latent_encoder ->
+    model.goal_manager.pred_goal -> joint_future_pred (reference src/pl_modules/waymo_motion.py:581-598); the deterministic
+    mode 0 (prior mean, arg-max destination) reproduces the unmodified reference."""
+    from golden_util import load_case
+    gold, sd, batch, meta = load_case(case)
+    K, S = meta["K"], meta["S"]
+    m = _module(sd, K)
+    cb = {k: v.cuda() for k, v in batch.items()}
+    feat = m.model.encode_input_features(cb)
+    latent = m.model.latent_encoder(**feat)
+    goal = m.model.goal_manager.pred_goal(agent_type=cb["agent/type"], map_type=cb["map/type"], agent_state=None, **feat)
+    assert float((latent.mean.cpu() - gold["latent_prior/mean"]).abs().max()) <= 1e-4
+    assert float((goal.probs.cpu() - gold["dest/probs"]).abs().max()) <= 2e-5
+    goal_valid = cb["history/agent/valid"].any(1)
+    torch.manual_seed(0)
+    buf, goal_sample, _ = m.joint_future_pred(cb, feat, latent, goal, goal_valid, require_vis_dict=False)
+    assert torch.equal(goal_sample[:, :, 0].cpu(), gold["jfp/goal_sample"][:, :, 0])
+    assert torch.equal(buf.valid[:, :, 0].cpu(), gold["jfp/valid"][:, :, 0])
+    assert float((buf.preds[:, :, 0].cpu() - gold["jfp/preds"][:, :, 0]).abs().max()) <= 2e-3  # closed-loop tolerance

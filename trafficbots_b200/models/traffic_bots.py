@@ -17,7 +17,7 @@ from .. import _native as nt
 from .. import config as tb_config
 from .. import weights
 from ..engine import Engine, SceneFeatures
-from .distributions import DiagGaussian
+from .distributions import DestCategorical, DiagGaussian
 
 
 def register_param_tree(root: nn.Module, spec: Mapping[str, tuple], prefix: str, buffers: bool = False) -> None:
@@ -38,11 +38,46 @@ def register_param_tree(root: nn.Module, spec: Mapping[str, tuple], prefix: str,
             mod.register_parameter(parts[-1], nn.Parameter(t, requires_grad=False))
 
 
+class _Head(nn.Module):
+    """parameter container of a pre-rollout head that calls back into the owning `TrafficBots` (not a submodule link)."""
+
+    def _model(self) -> "TrafficBots":
+        return self.__dict__["_tb"]()
+
+
+class LatentEncoder(_Head):
+    def forward(self, agent_feature: Tensor = None, agent_feature_valid: Tensor = None, map_feature: Tensor = None,
+                map_feature_valid: Tensor = None, tl_feature: Tensor = None, tl_feature_valid: Tensor = None,
+                posterior: bool = False, **private) -> DiagGaussian:
+        """`LatentEncoder.forward` (src/models/latent_encoder.py:70-147): called like the reference with the dict of
+        `encode_input_features` (`model.latent_encoder(posterior=True, **feat)`), whose private `_kv_*` entries carry the
+        projected K|V caches.  Returns the diagonal Gaussian with the learned constant log_std (:195-199)."""
+        if "_kv_map" not in private or "_kv_tl" not in private:
+            raise nt.TbError("latent_encoder expects the feature dict returned by encode_input_features (with its K|V caches)")
+        feat = dict(private, agent_feature=agent_feature, agent_feature_valid=agent_feature_valid, map_feature=map_feature,
+                    map_feature_valid=map_feature_valid, tl_feature=tl_feature, tl_feature_valid=tl_feature_valid)
+        mean, valid = self._model()._engine().latent_encoder(feat, posterior=posterior)
+        dist = self.latent_post_dist if posterior else self.latent_prior_dist
+        return DiagGaussian(mean, dist.log_std.detach(), valid=valid)
+
+
+class GoalManager(_Head):
+    def pred_goal(self, agent_type: Tensor, map_type: Tensor, agent_state: Tensor = None, **feat) -> DestCategorical:
+        """`GoalManager.pred_goal` -> `DestPredictor.forward`, mode mlp (src/models/goal_manager.py:77-81,202-333)."""
+        probs, _logp, valid = self._model()._engine().dest_predictor(feat, agent_type, map_type)
+        return DestCategorical(probs=probs, valid=valid)
+
+
 class TrafficBots(nn.Module):
     def __init__(self, hidden_dim: int = 128, **cfg) -> None:
         super().__init__()
         tb_config.check_supported({"hidden_dim": hidden_dim, "model": dict(cfg, hidden_dim=hidden_dim)})
         self.hidden_dim = hidden_dim
+        import weakref
+        self.latent_encoder = LatentEncoder()
+        self.goal_manager = GoalManager()
+        for head in (self.latent_encoder, self.goal_manager):
+            head.__dict__["_tb"] = weakref.ref(self)
         spec = weights.state_dict_spec()
         register_param_tree(self, {k: v for k, v in spec.items() if weights._alias_of(k) is None}, "model.")
         # shared modules: the latent encoder re-exports the policy's cross-attention blocks (latent_encoder.py:39-41)
