@@ -151,6 +151,14 @@ int32_t tb_xlayer(int32_t block, int32_t layer, const float* src, const uint8_t*
                   int32_t n_src, const float* kv, const uint8_t* key_valid, int32_t n_key, int32_t kv_share,
                   int32_t mask_self, const float* packed, float* dst, void* stream);
 
+/* The same layer with the keys given as compacted tensor-core key blocks (TbSceneOut.kv_map_tc / kv_tl_tc layout: 64 keys per
+ * 64 KB block, `n_key[i]` valid keys in set i, ceil(n_key_max / 64) blocks per set) and evaluated on the tensor pipe (bf16x3).
+ * No self-mask (compaction drops the key index).  Blocks: TB_BLOCK_MAP_SELF_ATTN, TB_BLOCK_AS2PL, TB_BLOCK_AS2TL,
+ * TB_BLOCK_INTERACTION.  Used for the map self-attention inside tb_encode_scene and for the latent encoder. */
+int32_t tb_xlayer_tc(int32_t block, int32_t layer, const float* src, const uint8_t* src_valid, int32_t n_batch, int32_t n_src,
+                     const uint8_t* key_blocks, const int32_t* n_key, int32_t n_key_max, int32_t kv_share, const float* packed,
+                     float* dst, void* stream);
+
 /* ---------------------------------------------------------------- closed-loop rollout ----------------- */
 
 typedef struct TbRolloutIn {

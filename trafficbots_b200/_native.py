@@ -40,7 +40,7 @@ EXPORTS = (
     "tb_pack_weights", "tb_encode_workspace_bytes", "tb_encode_scene", "tb_kv_project", "tb_xlayer",
     "tb_rollout_state_bytes", "tb_rollout_state_offset", "tb_rollout_init", "tb_rollout_steps", "tb_step_front", "tb_step_back", "tb_rollout",
     "tb_launch_count", "tb_kv_tc_bytes", "tb_tc_block_count", "tb_tc_first_block", "tb_tc_selftest",
-    "tb_gru_sequence", "tb_mlp_head", "tb_dest_workspace_bytes", "tb_dest_logits",
+    "tb_gru_sequence", "tb_mlp_head", "tb_dest_workspace_bytes", "tb_dest_logits", "tb_xlayer_tc",
 )
 
 
@@ -163,6 +163,9 @@ def lib() -> C.CDLL:
     L.tb_tc_first_block.argtypes = [C.c_int32]
     L.tb_tc_selftest.restype = C.c_int32
     L.tb_tc_selftest.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.tb_xlayer_tc.restype = C.c_int32
+    L.tb_xlayer_tc.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                               C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.tb_gru_sequence.restype = C.c_int32
     L.tb_gru_sequence.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -181,7 +184,7 @@ def check(rc: int, what: str) -> None:
         raise TbError(f"{what} failed: {STATUS.get(rc, rc)}")
 
 
-_DT = {"f32": torch.float32, "u8": (torch.bool, torch.uint8), "i64": torch.int64}
+_DT = {"f32": torch.float32, "u8": (torch.bool, torch.uint8), "i64": torch.int64, "i32": torch.int32}
 
 
 def dev_ptr(t: Optional[torch.Tensor], kind: str, shape=None, name: str = "tensor", optional: bool = False) -> Optional[int]:

@@ -400,8 +400,11 @@ int tb::check_dims_host(const TbDims* d) { return check_dims(d); }
 extern "C" size_t tb_encode_workspace_bytes(const TbDims* d) {
   if (check_dims(d) != TB_OK) return 0;
   const size_t rows = (size_t)d->n_scene * d->n_pl;
-  // pooled polyline features + self-attention K|V + per-CTA scratch of the tensor-core polyline encoder
-  return rows * D * sizeof(float) + rows * 256 * sizeof(float) + map_tc_scratch_bytes(MAP_TC_MAX_CTA);
+  // pooled polyline features + self-attention K|V + per-CTA scratch of the tensor-core polyline encoder + the tensor-core
+  // key blocks and key counts of the map self-attention layer
+  const size_t nT = (d->n_pl + 63) / 64;
+  return rows * D * sizeof(float) + rows * 256 * sizeof(float) + map_tc_scratch_bytes(MAP_TC_MAX_CTA) + 1024 +
+         (size_t)d->n_scene * nT * tc::BLOCK_BYTES + (size_t)d->n_scene * sizeof(int32_t) + 256;
 }
 
 template <int R>
@@ -486,8 +489,19 @@ extern "C" int32_t tb_encode_scene(const TbDims* dims, const TbSceneIn* in, cons
   // 2. global self-attention over the polylines of a scene (map_encoder.py:108-114)
   rc = tb_kv_project(TB_BLOCK_MAP_SELF_ATTN, 0, pl_feature, n_pl, packed, kv_self, stream);
   if (rc != TB_OK) return rc;
-  rc = tb_xlayer(TB_BLOCK_MAP_SELF_ATTN, 0, pl_feature, out->map_feature_valid, d.n_scene, d.n_pl, kv_self,
-                 out->map_feature_valid, d.n_pl, 1, 0, packed, out->map_feature, stream);
+  if (tc_enabled()) {  // tensor-core layer on compacted key blocks (tb_tc_xlayer.cu)
+    unsigned char* ws_end = reinterpret_cast<unsigned char*>(kv_self + n_pl * 256) + map_tc_scratch_bytes(MAP_TC_MAX_CTA);
+    unsigned char* self_blocks = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ws_end) + 1023) & ~(uintptr_t)1023);
+    const size_t nT = (d.n_pl + 63) / 64;
+    int32_t* n_key_self = reinterpret_cast<int32_t*>(self_blocks + (size_t)d.n_scene * nT * tc::BLOCK_BYTES);
+    rc = launch_pack_kv_tc(kv_self, out->map_feature_valid, d.n_scene, d.n_scene, d.n_pl, self_blocks, n_key_self, st);
+    if (rc != TB_OK) return rc;
+    rc = launch_xlayer_tc(TB_BLOCK_MAP_SELF_ATTN, 0, pl_feature, out->map_feature_valid, d.n_scene, d.n_pl, self_blocks, n_key_self,
+                          d.n_pl, 1, packed, out->map_feature, st);
+  } else {
+    rc = tb_xlayer(TB_BLOCK_MAP_SELF_ATTN, 0, pl_feature, out->map_feature_valid, d.n_scene, d.n_pl, kv_self,
+                   out->map_feature_valid, d.n_pl, 1, 0, packed, out->map_feature, stream);
+  }
   if (rc != TB_OK) return rc;
   // 3. loop-invariant K|V of the policy's agent->map layers
   for (int L = 0; L < 3; ++L) {

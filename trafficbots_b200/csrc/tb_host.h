@@ -53,6 +53,11 @@ size_t map_tc_scratch_bytes(int n_cta);
 int launch_map_polyline_tc(const TbDims& d, const TbSceneIn& in, const float* packed, float* x0_scratch, int n_cta,
                            float* pl_feature, uint8_t* pl_valid, cudaStream_t st);
 
+// generic tensor-core cross-attention layer on compacted key blocks (tb_tc_xlayer.cu)
+int launch_xlayer_tc(int block, int layer, const float* src, const uint8_t* src_valid, int n_batch, int n_src,
+                     const unsigned char* blocks, const int32_t* n_key, int n_key_max, int kv_share, const float* packed, float* dst,
+                     cudaStream_t st);
+
 // tensor-core decode step (tb_tc_rollout.cu)
 int launch_pack_kv_tc(const float* kv, const uint8_t* key_valid, int n_set, int n_set_valid, int T, unsigned char* blocks,
                       int32_t* n_key, cudaStream_t st);

@@ -1,0 +1,465 @@
+// One pre-LN cross-attention layer (`TransformerCrossAttention.forward`, reference src/models/modules/transformer.py:186-237)
+// on the tensor pipe for ANY number of query rows: a CTA owns a tile of up to 128 rows of one batch element and runs
+//   LN1 -> Wq -> flash attention against the compacted tensor-core key blocks of the element -> Wo -> residual -> LN2 -> FFN.
+// Used for the map encoder's global self-attention over the polylines of a scene (map_encoder.py:108-114) and for the
+// latent encoder's agent->map / agent->traffic-light layers (latent_encoder.py:108-122).  Same machinery as the decode
+// kernels: A operands in tensor memory (bf16x3), weights and key blocks streamed through a 2 x 64 KB ring by bulk-async
+// copies, online softmax with lazy rescaling; the issuer warp runs converged and one elected lane issues (tc::elect_one).
+//   TMEM: [0,128) S0 / GEMM accumulator | [128,256) S1 | [256,384) O | [384,512) A operand (hi | lo)
+#include "tb_host.h"
+
+namespace tb {
+namespace xl {
+
+constexpr int KVT_KEYS = 64, SUB_KEYS = 32;
+constexpr int MAX_STAGE = 160;
+constexpr int THREADS = 288;
+constexpr uint32_t T_S0 = 0, T_S1 = 128, T_O = 256, T_A = 384;
+
+struct Smem {
+  unsigned char ring[2][tc::BLOCK_BYTES];
+  float xs[128 * 128];  // residual stream, [col][row]
+  float red[2][128];
+  const unsigned char* sched[MAX_STAGE];
+  uint64_t bar_ring[2], bar_free[2], bar_ready, bar_mma, bar_s[2], bar_pv;
+  uint32_t tmem_base;
+  int n_stage;
+};
+
+struct Args {
+  const float* src;            // [n_batch, n_src, 128]
+  const uint8_t* src_valid;    // [n_batch, n_src]
+  float* dst;
+  int n_src;
+  const unsigned char* blocks; // [n_batch / kv_share][nT] x 64 KB
+  const int32_t* n_key;        // [n_batch / kv_share]
+  int nT, kv_share;
+  const float* lw;             // fp32 parameters of the layer (tfl:: offsets)
+  const unsigned char* tcw;    // tensor-core weight blocks of the layer: q, k, v, out, linear1, linear2
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_xlayer_tc(Args a) {
+  extern __shared__ unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int b = blockIdx.y, r0 = blockIdx.x * 128;
+  const int kb = b / a.kv_share;
+  const int tid = threadIdx.x, warp = tc::uniform(tid >> 5), lane = tid & 31;
+  const int nkey = tc::uniform(a.n_key[kb]);
+  const int nblk = (nkey + KVT_KEYS - 1) / KVT_KEYS;
+
+  if (tid == 0) {
+    tc::mbar_init(&sm.bar_ring[0], 1);
+    tc::mbar_init(&sm.bar_ring[1], 1);
+    tc::mbar_init(&sm.bar_free[0], 1);
+    tc::mbar_init(&sm.bar_free[1], 1);
+    tc::mbar_init(&sm.bar_ready, 8);
+    tc::mbar_init(&sm.bar_mma, 1);
+    tc::mbar_init(&sm.bar_s[0], 1);
+    tc::mbar_init(&sm.bar_s[1], 1);
+    tc::mbar_init(&sm.bar_pv, 1);
+    tc::fence_mbar_init();
+    int n = 0;
+    sm.sched[n++] = a.tcw;  // Wq
+    for (int j = 0; j < nblk; ++j) sm.sched[n++] = a.blocks + ((size_t)kb * a.nT + j) * tc::BLOCK_BYTES;
+    sm.sched[n++] = a.tcw + 3 * (size_t)tc::BLOCK_BYTES;  // Wo
+    sm.sched[n++] = a.tcw + 4 * (size_t)tc::BLOCK_BYTES;  // W1
+    sm.sched[n++] = a.tcw + 5 * (size_t)tc::BLOCK_BYTES;  // W2
+    sm.n_stage = n;
+  }
+  if (warp == 0) tc::tmem_alloc(&sm.tmem_base, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tm0 = (uint32_t)tc::uniform((int)sm.tmem_base);
+  const uint32_t idesc128 = tc::make_idesc_bf16(128, 128), idesc32 = tc::make_idesc_bf16(128, 32);
+
+  if (warp == 8) {
+    // ================================================================================================ issuer (converged warp)
+    uint32_t loaded = 0, n_ready = 0;
+    const int n_stage = tc::uniform(sm.n_stage);
+    auto ensure_loaded = [&](uint32_t upto) {
+      while (loaded <= upto && (int)loaded < n_stage) {
+        const uint32_t slot = loaded & 1;
+        if (loaded >= 2) tc::mbar_wait(&sm.bar_free[slot], ((loaded >> 1) - 1) & 1);
+        if (tc::elect_one()) {
+          tc::mbar_expect_tx(&sm.bar_ring[slot], tc::BLOCK_BYTES);
+          tc::bulk_g2s(sm.ring[slot], sm.sched[loaded], tc::BLOCK_BYTES, &sm.bar_ring[slot]);
+        }
+        __syncwarp();
+        ++loaded;
+      }
+    };
+    auto ring_wait = [&](uint32_t g) {
+      ensure_loaded(g);
+      tc::mbar_wait(&sm.bar_ring[g & 1], (g >> 1) & 1);
+      tc::tc_fence_after();
+    };
+    auto wait_ready = [&]() {
+      tc::mbar_wait(&sm.bar_ready, n_ready & 1);
+      ++n_ready;
+      tc::tc_fence_after();
+    };
+    uint32_t g = 0;
+    ensure_loaded(1);
+    auto gemm = [&]() {  // ACC0 = A(tmem) W_g^T
+      wait_ready();
+      ring_wait(g);
+      const uint32_t wh = tc::smem_u32(sm.ring[g & 1]);
+      const uint64_t dh = tc::make_desc_sw128(wh), dl = tc::make_desc_sw128(wh + 2 * tc::KB_BYTES_128);
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t ta = tm0 + T_A + (term == 1 ? 64 : 0);
+          const uint64_t db = term == 2 ? dl : dh;
+#pragma unroll
+          for (int k = 0; k < 128; k += 16)
+            tc::mma_bf16_ts(tm0 + T_S0, ta + k / 2, db + (uint64_t)(((k >> 6) * tc::KB_BYTES_128 + (k & 63) * 2) >> 4), idesc128,
+                            (term > 0 || k > 0) ? 1u : 0u);
+        }
+        tc::mma_commit(&sm.bar_free[g & 1]);
+        tc::mma_commit(&sm.bar_mma);
+      }
+      __syncwarp();
+      ++g;
+      ensure_loaded(g + 1);
+    };
+    auto attention = [&]() {
+      const int n_sub = (nkey + SUB_KEYS - 1) / SUB_KEYS;
+      const uint32_t blk0 = g;
+      auto issue_qk = [&](int u) {
+        const uint32_t gb = blk0 + (u >> 1);
+        if ((u & 1) == 0) ring_wait(gb);
+        const uint32_t kbase = tc::smem_u32(sm.ring[gb & 1]) + (u & 1) * 4096;
+        const uint64_t dh = tc::make_desc_sw128(kbase), dl = tc::make_desc_sw128(kbase + 16384);
+        const uint32_t sd = tm0 + ((u & 1) ? T_S1 : T_S0);
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int h = 0; h < NHEAD; ++h) {
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {
+              const uint32_t ta = tm0 + T_A + (term == 1 ? 64 : 0) + 16 * h;
+              const uint64_t db = (term == 2 ? dl : dh) + (uint64_t)(((h >> 1) * 8192 + (h & 1) * 64) >> 4);
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)
+                tc::mma_bf16_ts(sd + 32 * h, ta + 8 * ks, db + (uint64_t)(2 * ks), idesc32, (term > 0 || ks > 0) ? 1u : 0u);
+            }
+          }
+          tc::mma_commit(&sm.bar_s[u & 1]);
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](int u) {
+        const uint32_t gb = blk0 + (u >> 1);
+        const uint32_t vb = tc::smem_u32(sm.ring[gb & 1]) + 32768 + (u & 1) * 64;
+        const uint64_t dh = tc::make_desc_sw128(vb), dl = tc::make_desc_sw128(vb + 16384);
+        const uint32_t sp = tm0 + ((u & 1) ? T_S1 : T_S0);
+        const bool last_of_block = (u & 1) == 1 || u == n_sub - 1;
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int h = 0; h < NHEAD; ++h) {
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {
+              const uint32_t ta = sp + 32 * h + (term == 1 ? 16 : 0);
+              const uint64_t db = (term == 2 ? dl : dh) + (uint64_t)((h * 4096) >> 4);
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)
+                tc::mma_bf16_ts(tm0 + T_O + 32 * h, ta + 8 * ks, db + (uint64_t)(2 * ks), idesc32, (u > 0 || term > 0 || ks > 0) ? 1u : 0u);
+            }
+          }
+          tc::mma_commit(&sm.bar_pv);
+          if (last_of_block) tc::mma_commit(&sm.bar_free[gb & 1]);
+        }
+        __syncwarp();
+      };
+      if (n_sub > 0) {
+        wait_ready();  // Q packed in the A region
+        issue_qk(0);
+        if (n_sub > 1) issue_qk(1);
+      }
+      for (int u = 0; u < n_sub; ++u) {
+        wait_ready();  // P(u) written, O rescaled
+        issue_pv(u);
+        if (u + 2 < n_sub) issue_qk(u + 2);
+        if ((u & 1) == 1 || u == n_sub - 1) ensure_loaded(blk0 + (u >> 1) + 2);
+      }
+      g = blk0 + (n_sub + 1) / 2;
+    };
+    gemm();       // Wq
+    attention();
+    gemm();       // Wo
+    gemm();       // W1
+    gemm();       // W2
+  } else {
+    // ================================================================================================ row workers
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane;
+    const int c0 = half * 64;
+    const bool live = r0 + r < a.n_src;
+    const size_t row = (size_t)b * a.n_src + r0 + (live ? r : 0);
+    const uint32_t tm = tm0 + ((uint32_t)(quad * 32) << 16);
+    uint32_t n_mma = 0, n_s[2] = {0, 0}, n_pv = 0;
+    const float* __restrict__ lw = a.lw;
+
+    auto signal_ready = [&]() {
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.bar_ready);
+    };
+    auto wait_gemm = [&]() {
+      tc::mbar_wait(&sm.bar_mma, n_mma & 1);
+      tc::tc_fence_after();
+      ++n_mma;
+    };
+    auto xs_at = [&](int c) -> float& { return sm.xs[c * 128 + r]; };
+    auto write_A = [&](const float (&v)[64]) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float ph[16], pl[16];
+        tc::split32_packed(*reinterpret_cast<const float(*)[32]>(&v[32 * j]), ph, pl);
+        tc::tmem_st16(tm + T_A + (c0 + 32 * j) / 2, ph);
+        tc::tmem_st16(tm + T_A + 64 + (c0 + 32 * j) / 2, pl);
+      }
+    };
+    auto layernorm64 = [&](float (&v)[64], const float* __restrict__ g, const float* __restrict__ bt) {
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 64; ++i) s4[i & 3] += v[i];
+      sm.red[half][r] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      worker_sync();
+      const float mean = (sm.red[0][r] + sm.red[1][r]) * (1.0f / 128);
+      worker_sync();
+      float q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float d = v[i] - mean;
+        q4[i & 3] = fmaf(d, d, q4[i & 3]);
+      }
+      sm.red[half][r] = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+      worker_sync();
+      const float rstd = 1.0f / sqrtf((sm.red[0][r] + sm.red[1][r]) * (1.0f / 128) + LN_EPS);
+      worker_sync();
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = (v[i] - mean) * rstd * __ldg(g + c0 + i) + __ldg(bt + c0 + i);
+    };
+    auto load_x = [&](float (&v)[64]) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = xs_at(c0 + i);
+    };
+    auto load_acc = [&](uint32_t col, float (&v)[64]) {
+      tc::tmem_ld32(tm + col + c0, *reinterpret_cast<float(*)[32]>(&v[0]));
+      tc::tmem_ld32(tm + col + c0 + 32, *reinterpret_cast<float(*)[32]>(&v[32]));
+      tc::tmem_ld_wait();
+    };
+
+    const bool valid = live && a.src_valid[row] != 0;
+    {
+      float v[64];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) q = __ldg(reinterpret_cast<const float4*>(a.src + row * D + c0) + i);
+        v[4 * i] = q.x, v[4 * i + 1] = q.y, v[4 * i + 2] = q.z, v[4 * i + 3] = q.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 64; ++i) xs_at(c0 + i) = v[i];
+      layernorm64(v, lw + tfl::NORM1_W, lw + tfl::NORM1_B);
+      write_A(v);
+      signal_ready();  // -> Wq
+      wait_gemm();
+      load_acc(T_S0, v);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] += __ldg(lw + tfl::IN_B + c0 + i);
+      write_A(v);
+    }
+    const int n_sub = (nkey + SUB_KEYS - 1) / SUB_KEYS;
+    if (n_sub > 0) signal_ready();  // Q ready
+    const float sc = 0.17677669529663687f * 1.4426950408889634f;
+    float m_ref[2] = {-INFINITY, -INFINITY}, l_sum[2] = {0.f, 0.f};
+#pragma unroll 1
+    for (int u = 0; u < n_sub; ++u) {
+      const int bsel = u & 1;
+      tc::mbar_wait(&sm.bar_s[bsel], n_s[bsel] & 1);
+      tc::tc_fence_after();
+      ++n_s[bsel];
+      const uint32_t sbase = tm + (bsel ? T_S1 : T_S0);
+      const int key0 = u * SUB_KEYS;
+      bool need_rescale = false;
+      float alpha[2] = {1.f, 1.f};
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int h = 2 * half + hh;
+        float sv_[32];
+        tc::tmem_ld32(sbase + 32 * h, sv_);
+        tc::tmem_ld_wait();
+        if (key0 + SUB_KEYS > nkey) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (key0 + j >= nkey) sv_[j] = -INFINITY;
+        }
+        float mx = sv_[0];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, sv_[j]);
+        mx *= sc;
+        if (mx > m_ref[hh] + 8.0f) {
+          alpha[hh] = (m_ref[hh] == -INFINITY) ? 0.f : exp2f(m_ref[hh] - mx);
+          m_ref[hh] = mx;
+          l_sum[hh] *= alpha[hh];
+          need_rescale = need_rescale || (u > 0);
+        }
+        float psum = 0.f;
+        const float neg_m = -m_ref[hh];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          sv_[j] = ex2_approx(fmaf(sv_[j], sc, neg_m));
+          psum += sv_[j];
+        }
+        l_sum[hh] += psum;
+        float ph[16], pl[16];
+        tc::split32_packed(sv_, ph, pl);
+        tc::tmem_st16(sbase + 32 * h, ph);
+        tc::tmem_st16(sbase + 32 * h + 16, pl);
+      }
+      if (u > 0) {
+        tc::mbar_wait(&sm.bar_pv, n_pv & 1);
+        tc::tc_fence_after();
+        ++n_pv;
+      }
+      if (__any_sync(0xffffffffu, need_rescale)) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int h = 2 * half + hh;
+          float o[32];
+          tc::tmem_ld32(tm + T_O + 32 * h, o);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] *= alpha[hh];
+          tc::tmem_st32(tm + T_O + 32 * h, o);
+        }
+      }
+      signal_ready();
+    }
+    {
+      float o[64];
+      if (n_sub > 0) {
+        tc::mbar_wait(&sm.bar_pv, n_pv & 1);
+        tc::tc_fence_after();
+        ++n_pv;
+        load_acc(T_O, o);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const float inv = l_sum[hh] > 0.f ? 1.0f / l_sum[hh] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[32 * hh + j] *= inv;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) o[i] = 0.f;
+      }
+      write_A(o);
+    }
+    signal_ready();  // -> Wo
+    wait_gemm();
+    {
+      float v[64], x[64];
+      load_acc(T_S0, v);
+      load_x(x);
+      if (nkey > 0) {  // rows without any key: zero attention output (attention.py:144-146)
+#pragma unroll
+        for (int i = 0; i < 64; ++i) x[i] += v[i] + __ldg(lw + tfl::OUT_B + c0 + i);
+      }
+#pragma unroll
+      for (int i = 0; i < 64; ++i) xs_at(c0 + i) = x[i];
+      layernorm64(x, lw + tfl::NORM2_W, lw + tfl::NORM2_B);
+      write_A(x);
+    }
+    signal_ready();  // -> W1
+    wait_gemm();
+    {
+      float v[64];
+      load_acc(T_S0, v);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i] + __ldg(lw + tfl::L1_B + c0 + i), 0.f);
+      write_A(v);
+    }
+    signal_ready();  // -> W2
+    wait_gemm();
+    {
+      float v[64];
+      load_acc(T_S0, v);
+      if (live) {
+        float* out = a.dst + row * D + c0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float4 q;
+          q.x = valid ? xs_at(c0 + 4 * i) + v[4 * i] + __ldg(lw + tfl::L2_B + c0 + 4 * i) : 0.f;
+          q.y = valid ? xs_at(c0 + 4 * i + 1) + v[4 * i + 1] + __ldg(lw + tfl::L2_B + c0 + 4 * i + 1) : 0.f;
+          q.z = valid ? xs_at(c0 + 4 * i + 2) + v[4 * i + 2] + __ldg(lw + tfl::L2_B + c0 + 4 * i + 2) : 0.f;
+          q.w = valid ? xs_at(c0 + 4 * i + 3) + v[4 * i + 3] + __ldg(lw + tfl::L2_B + c0 + 4 * i + 3) : 0.f;
+          reinterpret_cast<float4*>(out)[i] = q;
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(sm.tmem_base, 512);
+}
+
+}  // namespace xl
+}  // namespace tb
+
+using namespace tb;
+
+static int tc_layer_first_block(int block, int layer) {
+  switch (block) {
+    case TB_BLOCK_MAP_SELF_ATTN: return tbb::model_map_encoder_transformer_self_attn_layers_0_attn_in_proj_weight;
+    case TB_BLOCK_AS2PL: return tbb::model_transformer_as2pl_layers_0_attn_in_proj_weight + 6 * layer;
+    case TB_BLOCK_AS2TL: return tbb::model_transformer_as2tl_layers_0_attn_in_proj_weight + 6 * layer;
+    case TB_BLOCK_INTERACTION: return tbb::model_agent_interaction_transformer_layers_0_attn_in_proj_weight + 6 * layer;
+  }
+  return -1;
+}
+
+int tb::launch_xlayer_tc(int block, int layer, const float* src, const uint8_t* src_valid, int n_batch, int n_src,
+                         const unsigned char* blocks, const int32_t* n_key, int n_key_max, int kv_share, const float* packed, float* dst,
+                         cudaStream_t st) {
+  const int first = tc_layer_first_block(block, layer);
+  if (first < 0) return TB_ERR_UNSUPPORTED;
+  const int nT = (n_key_max + xl::KVT_KEYS - 1) / xl::KVT_KEYS;
+  if (nT + 4 > xl::MAX_STAGE) return TB_ERR_BAD_SHAPE;
+  static bool attr_set = false;
+  const int smem = (int)sizeof(xl::Smem) + 1024;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(xl::k_xlayer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return TB_ERR_LAUNCH;
+    attr_set = true;
+  }
+  xl::Args a{src, src_valid, dst, n_src, blocks, n_key, nT, kv_share, packed + block_base(block) + layer * tfl::STRIDE,
+             tc_blob(packed) + (size_t)first * tc::BLOCK_BYTES};
+  dim3 grid((n_src + 127) / 128, n_batch);
+  xl::k_xlayer_tc<<<grid, xl::THREADS, smem, st>>>(a);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int32_t tb_xlayer_tc(int32_t block, int32_t layer, const float* src, const uint8_t* src_valid, int32_t n_batch,
+                                int32_t n_src, const uint8_t* key_blocks, const int32_t* n_key, int32_t n_key_max,
+                                int32_t kv_share, const float* packed, float* dst, void* stream) {
+  if (!src || !src_valid || !key_blocks || !n_key || !packed || !dst) return TB_ERR_NULL;
+  if (block_base(block) < 0 || layer < 0 || layer >= block_layers(block) || n_batch < 1 || n_batch > 65535 || n_src < 1 ||
+      n_key_max < 1 || kv_share < 1 || n_batch % kv_share != 0)
+    return TB_ERR_BAD_SHAPE;
+  if (!aligned16(src) || !aligned16(packed) || !aligned16(dst) || (reinterpret_cast<uintptr_t>(key_blocks) & 127u)) return TB_ERR_ALIGN;
+  return launch_xlayer_tc(block, layer, src, src_valid, n_batch, n_src, key_blocks, n_key, n_key_max, kv_share, packed, dst,
+                          (cudaStream_t)stream);
+}

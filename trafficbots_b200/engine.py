@@ -143,6 +143,21 @@ class Engine:
                      "tb_xlayer")
         return dst
 
+    def xlayer_tc(self, block: int, layer: int, src: Tensor, src_valid: Tensor, key_blocks: Tensor, n_key: Tensor,
+                  n_key_max: int, kv_share: int = 1) -> Tensor:
+        """`tb_xlayer_tc`: the layer on the tensor pipe against compacted key blocks.  src [nb, ns, 128]; key_blocks uint8
+        [nb / kv_share, ceil(n_key_max / 64), 65536]; n_key int32 [nb / kv_share]."""
+        nb, ns, _ = src.shape
+        nT = (n_key_max + 63) // 64
+        dst = torch.empty_like(src)
+        with torch.cuda.device(self.device):
+            nt.check(self.lib.tb_xlayer_tc(block, layer, nt.dev_ptr(src, "f32", name="src"),
+                                           nt.dev_ptr(src_valid, "u8", (nb, ns), "src_valid"), nb, ns,
+                                           nt.dev_ptr(key_blocks, "u8", (nb // kv_share, nT, 65536), "key_blocks"),
+                                           nt.dev_ptr(n_key, "i32", (nb // kv_share,), "n_key"), n_key_max, kv_share,
+                                           self.packed.data_ptr(), dst.data_ptr(), nt.current_stream_ptr()), "tb_xlayer_tc")
+        return dst
+
     # ------------------------------------------------------------------------------------------------ pre-rollout heads
     def gru_sequence(self, which: int, mode: int, x: Tensor, valid: Tensor, t_stride: int = 1):
         """`MultiAgentGRULoop` over the frames + temporal aggregation (`tb_gru_sequence`).  x [B,T,A,128], valid [B,T,A]
@@ -172,12 +187,25 @@ class Engine:
         kv_tl = feat["_kv_tl"][:, :, ::d].contiguous()  # [3,S,T,TL,256]
         x = x.view(S, T * A, 128)
         avf = av.view(S, T * A)
-        for L in range(3):
-            x = self.xlayer(nt.BLOCK_AS2PL, L, x, avf, feat["_kv_map"][L], feat["map_feature_valid"])
-        x = x.view(S * T, A, 128)
         avb = av.view(S * T, A)
-        for L in range(3):
-            x = self.xlayer(nt.BLOCK_AS2TL, L, x, avb, kv_tl[L].reshape(S * T, TL, 256), tv.view(S * T, TL))
+        if "_kv_map_tc" in feat:  # tensor-core layers on the compacted key blocks of encode_scene
+            P = feat["map_feature"].shape[1]
+            nT_map, nT_tl = (P + 63) // 64, (TL + 63) // 64
+            Th = feat["tl_feature_valid"].shape[1]
+            kmap = feat["_kv_map_tc"].view(3, S, nT_map, 65536)
+            ktl = feat["_kv_tl_tc"].view(3, S, Th, nT_tl, 65536)[:, :, ::d].contiguous()
+            nk_tl = feat["_n_key_tl"][:, ::d].contiguous().view(S * T)
+            for L in range(3):
+                x = self.xlayer_tc(nt.BLOCK_AS2PL, L, x, avf, kmap[L], feat["_n_key_map"], P)
+            x = x.view(S * T, A, 128)
+            for L in range(3):
+                x = self.xlayer_tc(nt.BLOCK_AS2TL, L, x, avb, ktl[L].reshape(S * T, nT_tl, 65536), nk_tl, TL)
+        else:
+            for L in range(3):
+                x = self.xlayer(nt.BLOCK_AS2PL, L, x, avf, feat["_kv_map"][L], feat["map_feature_valid"])
+            x = x.view(S * T, A, 128)
+            for L in range(3):
+                x = self.xlayer(nt.BLOCK_AS2TL, L, x, avb, kv_tl[L].reshape(S * T, TL, 256), tv.view(S * T, TL))
         block = nt.BLOCK_LATENT_POST_INT if posterior else nt.BLOCK_LATENT_PRIOR_INT
         x0 = x
         for L in range(3):  # tgt = the block input for all layers (agent_interaction.py:52), eye mask
