@@ -319,14 +319,19 @@ extern "C" int32_t tb_dest_logits(int32_t n_scene, int32_t n_agent, int32_t n_pl
   count_launch();
   k_row_linear<HR><<<(unsigned)((rows_v + HR - 1) / HR), NT, 0, st>>>(tgt, rows_v, w0, D, nullptr, V);
   count_launch();
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_dest_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairSmem));
-    attr_set = true;
+  if (tc_enabled()) {  // pairwise MLP on the tensor pipe (tb_tc_xlayer.cu); raw logits staged in `logp`
+    const int rc = launch_dest_pairs_tc(U, V, n_scene, n_agent, n_pl, packed, logp, st);
+    if (rc != TB_OK) return rc;
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_dest_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairSmem));
+      attr_set = true;
+    }
+    dim3 grid((n_pl + PR - 1) / PR, n_agent, n_scene);
+    k_dest_pairs<<<grid, NT, sizeof(PairSmem), st>>>(U, V, n_pl, n_agent, packed, logp);
+    count_launch();
   }
-  dim3 grid((n_pl + PR - 1) / PR, n_agent, n_scene);
-  k_dest_pairs<<<grid, NT, sizeof(PairSmem), st>>>(U, V, n_pl, n_agent, packed, logp);  // raw logits staged in `logp`
-  count_launch();
   const int rows = n_scene * n_agent;
   k_dest_finish<<<(rows + NWARP - 1) / NWARP, NT, 0, st>>>(logp, map_feature_valid, map_type, agent_type, tgt_valid, n_scene, n_agent, n_pl,
                                                          logp, probs);

@@ -58,6 +58,9 @@ int launch_xlayer_tc(int block, int layer, const float* src, const uint8_t* src_
                      const unsigned char* blocks, const int32_t* n_key, int n_key_max, int kv_share, const float* packed, float* dst,
                      cudaStream_t st);
 
+int launch_dest_pairs_tc(const float* U, const float* V, int n_scene, int n_agent, int n_pl, const float* packed, float* logits,
+                         cudaStream_t st);
+
 // tensor-core decode step (tb_tc_rollout.cu)
 int launch_pack_kv_tc(const float* kv, const uint8_t* key_valid, int n_set, int n_set_valid, int T, unsigned char* blocks,
                       int32_t* n_key, cudaStream_t st);

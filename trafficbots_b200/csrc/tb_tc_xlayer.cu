@@ -463,3 +463,182 @@ extern "C" int32_t tb_xlayer_tc(int32_t block, int32_t layer, const float* src, 
   return launch_xlayer_tc(block, layer, src, src_valid, n_batch, n_src, key_blocks, n_key, n_key_max, kv_share, packed, dst,
                           (cudaStream_t)stream);
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Pairwise destination MLP on the tensor pipe (DestPredictor, mode mlp: reference src/models/goal_manager.py:301-307).
+// A tile = 128 consecutive polylines of one (scene, agent) pair; persistent CTAs, the 128x128 weight block of the second
+// Linear stays resident in shared memory:   h1 = relu(LN1(U[p] + V[a]))  -> [128 x 128] bf16x3 GEMM -> relu(LN2(. + b3)) . w6 + b6
+// ------------------------------------------------------------------------------------------------------------
+namespace tb {
+namespace dp {
+
+constexpr int THREADS = 288;
+struct Smem {
+  unsigned char w[tc::BLOCK_BYTES];
+  float red[2][128];
+  float dot[2][128];
+  uint64_t bar_w, bar_ready, bar_mma;
+  uint32_t tmem_base;
+};
+constexpr uint32_t T_ACC = 0, T_A = 128;
+
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 2) k_dest_pairs_tc(const float* __restrict__ U, const float* __restrict__ V, int P, int A,
+                                                              int n_sa, const float* __restrict__ packed,
+                                                              const unsigned char* __restrict__ w3_block, float* __restrict__ logits) {
+  extern __shared__ unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tc::uniform(tid >> 5), lane = tid & 31;
+  const int tiles_per_sa = (P + 127) / 128;
+  const int n_tile = n_sa * tiles_per_sa;
+  if (tid == 0) {
+    tc::mbar_init(&sm.bar_w, 1);
+    tc::mbar_init(&sm.bar_ready, 8);
+    tc::mbar_init(&sm.bar_mma, 1);
+    tc::fence_mbar_init();
+    tc::mbar_expect_tx(&sm.bar_w, tc::BLOCK_BYTES);
+    tc::bulk_g2s(sm.w, w3_block, tc::BLOCK_BYTES, &sm.bar_w);
+  }
+  if (warp == 0) tc::tmem_alloc(&sm.tmem_base, 256);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tm0 = (uint32_t)tc::uniform((int)sm.tmem_base);
+
+  if (warp == 8) {
+    tc::mbar_wait(&sm.bar_w, 0);
+    const uint32_t wh = tc::smem_u32(sm.w);
+    const uint64_t dh = tc::make_desc_sw128(wh), dl = tc::make_desc_sw128(wh + 2 * tc::KB_BYTES_128);
+    const uint32_t idesc = tc::make_idesc_bf16(128, 128);
+    uint32_t n_ready = 0;
+    for (int tile = blockIdx.x; tile < n_tile; tile += gridDim.x) {
+      tc::mbar_wait(&sm.bar_ready, n_ready & 1);
+      ++n_ready;
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t ta = tm0 + T_A + (term == 1 ? 64 : 0);
+          const uint64_t db = term == 2 ? dl : dh;
+#pragma unroll
+          for (int k = 0; k < 128; k += 16)
+            tc::mma_bf16_ts(tm0 + T_ACC, ta + k / 2, db + (uint64_t)(((k >> 6) * tc::KB_BYTES_128 + (k & 63) * 2) >> 4), idesc,
+                            (term > 0 || k > 0) ? 1u : 0u);
+        }
+        tc::mma_commit(&sm.bar_mma);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane, c0 = half * 64;
+    const uint32_t tm = tm0 + ((uint32_t)(quad * 32) << 16);
+    uint32_t n_mma = 0;
+    const float* ln1w = packed + tbw::model_goal_manager_goal_predictor_mlp_fc_layers_1_weight;
+    const float* ln1b = packed + tbw::model_goal_manager_goal_predictor_mlp_fc_layers_1_bias;
+    const float* b3 = packed + tbw::model_goal_manager_goal_predictor_mlp_fc_layers_3_bias;
+    const float* ln2w = packed + tbw::model_goal_manager_goal_predictor_mlp_fc_layers_4_weight;
+    const float* ln2b = packed + tbw::model_goal_manager_goal_predictor_mlp_fc_layers_4_bias;
+    const float* w6 = packed + tbw::model_goal_manager_goal_predictor_mlp_fc_layers_6_weight;
+    const float b6 = __ldg(packed + tbw::model_goal_manager_goal_predictor_mlp_fc_layers_6_bias);
+    // LayerNorm statistics of a row held by the thread pair (r, half 0 / 1): exchange of {sum, M2} halves (Chan)
+    auto ln_stats = [&](const float (&v)[64], float& mean, float& rstd) {
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 64; ++i) s4[i & 3] += v[i];
+      const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      const float mloc = sum * (1.0f / 64);
+      float q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float d = v[i] - mloc;
+        q4[i & 3] = fmaf(d, d, q4[i & 3]);
+      }
+      const float m2 = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+      sm.red[half][r] = sum;
+      sm.dot[half][r] = m2;
+      worker_sync();
+      const float os = sm.red[half ^ 1][r], om = sm.dot[half ^ 1][r];
+      worker_sync();
+      mean = (sum + os) * (1.0f / 128);
+      const float dm = (os - sum) * (1.0f / 64);
+      rstd = 1.0f / sqrtf((m2 + om + dm * dm * 32.0f) * (1.0f / 128) + LN_EPS);
+    };
+    for (int tile = blockIdx.x; tile < n_tile; tile += gridDim.x) {
+      const int sa = tile / tiles_per_sa, p0 = (tile % tiles_per_sa) * 128;
+      const int s = sa / A;
+      const int p = p0 + r;
+      const bool live = p < P;
+      float v[64];
+      {
+        const float4* u4 = reinterpret_cast<const float4*>(U + ((size_t)s * P + (live ? p : 0)) * D + c0);
+        const float4* v4 = reinterpret_cast<const float4*>(V + (size_t)sa * D + c0);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 a4 = __ldg(u4 + i), b4 = __ldg(v4 + i);
+          v[4 * i] = a4.x + b4.x, v[4 * i + 1] = a4.y + b4.y, v[4 * i + 2] = a4.z + b4.z, v[4 * i + 3] = a4.w + b4.w;
+        }
+      }
+      float mean, rstd;
+      ln_stats(v, mean, rstd);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = fmaxf((v[i] - mean) * rstd * __ldg(ln1w + c0 + i) + __ldg(ln1b + c0 + i), 0.f);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float ph[16], pl[16];
+        tc::split32_packed(*reinterpret_cast<const float(*)[32]>(&v[32 * j]), ph, pl);
+        tc::tmem_st16(tm + T_A + (c0 + 32 * j) / 2, ph);
+        tc::tmem_st16(tm + T_A + 64 + (c0 + 32 * j) / 2, pl);
+      }
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.bar_ready);
+      tc::mbar_wait(&sm.bar_mma, n_mma & 1);
+      ++n_mma;
+      tc::tc_fence_after();
+      tc::tmem_ld32(tm + T_ACC + c0, *reinterpret_cast<float(*)[32]>(&v[0]));
+      tc::tmem_ld32(tm + T_ACC + c0 + 32, *reinterpret_cast<float(*)[32]>(&v[32]));
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] += __ldg(b3 + c0 + i);
+      ln_stats(v, mean, rstd);
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i)
+        d = fmaf(fmaxf((v[i] - mean) * rstd * __ldg(ln2w + c0 + i) + __ldg(ln2b + c0 + i), 0.f), __ldg(w6 + c0 + i), d);
+      sm.dot[half][r] = d;
+      worker_sync();
+      if (half == 0 && live) logits[(size_t)sa * P + p] = sm.dot[0][r] + sm.dot[1][r] + b6;
+      worker_sync();
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(sm.tmem_base, 256);
+}
+
+}  // namespace dp
+}  // namespace tb
+
+int tb::launch_dest_pairs_tc(const float* U, const float* V, int n_scene, int n_agent, int n_pl, const float* packed, float* logits,
+                             cudaStream_t st) {
+  static bool attr_set = false;
+  const int smem = (int)sizeof(dp::Smem) + 1024;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(dp::k_dest_pairs_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return TB_ERR_LAUNCH;
+    attr_set = true;
+  }
+  const int n_sa = n_scene * n_agent;
+  const long n_tile = (long)n_sa * ((n_pl + 127) / 128);
+  const int grid = (int)(n_tile < 2 * 148 ? n_tile : 2 * 148);  // 2 CTAs per SM (66 KB shared memory, 256 TMEM columns each)
+  dp::k_dest_pairs_tc<<<grid, dp::THREADS, smem, st>>>(
+      U, V, n_pl, n_agent, n_sa, packed,
+      tc_blob(packed) + (size_t)tbb::model_goal_manager_goal_predictor_mlp_fc_layers_3_weight * tc::BLOCK_BYTES, logits);
+  count_launch();
+  return launch_status();
+}
