@@ -22,14 +22,15 @@ def main():
     S = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     sd = weights.init_state_dict(2023)
     eng = E.Engine(sd, "cuda")
-    batch, ex = bench.make_inputs(S, 64, 1024, 1, seed=1000)
+    batch, _ = bench.make_inputs(S, 64, 1024, 1, seed=1000)
     cb = host.batch_to_device(batch, "cuda")
-    cex = host.batch_to_device(ex, "cuda")
     feat = eng.encode_scene(cb)
     gt = E.gt_from_batch(cb)
     tf = host.teacher_forcing_mask(gt["valid"], 10, 10)
-    args = (feat, gt, tf, cb["agent/type"], cb["agent/size"], E.raw_map_from_batch(cb), cex["latent_sample"],
-            cex["latent_logp"], cex["dest"], cex["goal_valid"], cb["agent/goal"])
+    lat_mean, _ = eng.latent_encoder(feat)
+    dest = eng.dest_predictor(feat, cb["agent/type"], cb["map/type"])[0].argmax(-1)
+    args = (feat, gt, tf, cb["agent/type"], cb["agent/size"], E.raw_map_from_batch(cb), lat_mean,
+            torch.zeros(S, 64, device="cuda"), dest, cb["history/agent/valid"].any(1), cb["agent/goal"])
     for _ in range(2):
         eng.rollout(*args, n_mode=1, n_step=90)
     torch.cuda.synchronize()

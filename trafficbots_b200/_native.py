@@ -15,7 +15,7 @@ import torch
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
-LIB_PATH = os.path.join(PKG_DIR, "libtrafficbots_b200.so")
+LIB_PATH = os.environ.get("TB_LIB_PATH") or os.path.join(PKG_DIR, "libtrafficbots_b200.so")  # TB_LIB_PATH: A/B builds
 CSRC = os.path.join(PKG_DIR, "csrc")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",

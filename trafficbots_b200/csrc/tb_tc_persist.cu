@@ -84,6 +84,14 @@ __device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.0f, fast_sig
 using tc::elect_one;
 using tc::uniform;
 
+// Issuer / loader primitives are inlined into the step program: measured 3 % faster than out-of-line copies (A/B on one box,
+// -DTB_NOINLINE_ISSUER), although the latter shrink the kernel by ~5 k instructions.
+#ifdef TB_NOINLINE_ISSUER
+#define TB_ROLE_FN __noinline__
+#else
+#define TB_ROLE_FN __forceinline__
+#endif
+
 // ---- thread-block cluster helpers (split of the agent->map attention over the CTAs of a cluster) -----------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -287,7 +295,7 @@ struct Loader {  // run by a whole (converged) warp; one elected lane issues the
     const uint32_t use = g >> 1;
     if (use > 0) tc::mbar_wait(&sm.free_[slot][half], (use - 1) & 1);
   }
-  __device__ __forceinline__ void load(const unsigned char* ptr) {
+  __device__ TB_ROLE_FN void load(const unsigned char* ptr) {
     const uint32_t slot = g & 1;
 #pragma unroll
     for (uint32_t h = 0; h < 2; ++h) {
@@ -352,7 +360,7 @@ struct Issuer {
     if (elect_one()) tc::mma_commit(&sm.mma);
     __syncwarp();
   }
-  __device__ __forceinline__ void chain(const unsigned char*, uint32_t dcol, uint32_t acol, bool accum) {
+  __device__ TB_ROLE_FN void chain(const unsigned char*, uint32_t dcol, uint32_t acol, bool accum) {
     const uint32_t slot = g & 1;
     tc::mbar_wait(&sm.full[slot][0], nf[slot] & 1);
     tc::mbar_wait(&sm.full[slot][1], nf[slot] & 1);
@@ -387,7 +395,7 @@ struct Issuer {
   }
   __device__ __forceinline__ void csync_after_wo() {}
   // QK^T of pass hp against the K half of the block in `slot`:  S_hp[128 x 64 keys] = A_hp[128 x 64 dims] K_hp^T
-  __device__ __forceinline__ void issue_qk(uint32_t slot, int hp) {
+  __device__ TB_ROLE_FN void issue_qk(uint32_t slot, int hp) {
     const uint32_t kb = tc::smem_u32(sm.ring[slot]) + hp * 8192;
     const uint64_t dh = tc::make_desc_sw128(kb), dl = tc::make_desc_sw128(kb + 16384);
     const uint32_t idesc = tc::make_idesc_bf16(128, 64);
@@ -402,7 +410,7 @@ struct Issuer {
     tc::mma_commit(&sm.s[hp]);
   }
   // PV of pass hp:  O_hp[128 x 64 dims] (+)= P_hp[128 x 64 keys] V_hp   (P = bf16 hi | lo packed over the S columns)
-  __device__ __forceinline__ void issue_pv(uint32_t slot, int hp, bool accum) {
+  __device__ TB_ROLE_FN void issue_pv(uint32_t slot, int hp, bool accum) {
     const uint32_t vb = tc::smem_u32(sm.ring[slot]) + HALF + hp * 8192;
     const uint64_t dh = tc::make_desc_sw128(vb), dl = tc::make_desc_sw128(vb + 16384);
     const uint32_t idesc = tc::make_idesc_bf16(128, 64);
