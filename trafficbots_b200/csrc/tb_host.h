@@ -61,6 +61,10 @@ int launch_xlayer_tc(int block, int layer, const float* src, const uint8_t* src_
 int launch_dest_pairs_tc(const float* U, const float* V, int n_scene, int n_agent, int n_pl, const float* packed, float* logits,
                          cudaStream_t st);
 
+// second version of the tensor-core polyline encoder: 4 threads per node row (tb_tc_polyline.cu)
+int launch_map_polyline_tc2(const TbDims& d, const TbSceneIn& in, const float* packed, float* x0_scratch, int n_cta,
+                            float* pl_feature, uint8_t* pl_valid, cudaStream_t st);
+
 // tensor-core decode step (tb_tc_rollout.cu)
 int launch_pack_kv_tc(const float* kv, const uint8_t* key_valid, int n_set, int n_set_valid, int T, unsigned char* blocks,
                       int32_t* n_key, cudaStream_t st);

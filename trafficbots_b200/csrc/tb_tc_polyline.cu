@@ -1,0 +1,373 @@
+// Polyline encoder on the tensor pipe, second version (map_encoder.py:72-106): 512 threads, FOUR threads per node row.
+// The first version (tb_tc_kernels.cu, one thread per row, 4 warps) was bound by dependent-issue latency with one warp per
+// scheduler (issue active 17 %, tensor pipe 8 %: profiles/r1d_k_map_polyline_tc.txt).  Here thread (row, q4) owns the 32
+// columns [32 q4, 32 q4 + 32) of its row -- which is exactly attention head q4 -- so 16 warps share the LayerNorm / epilogue
+// work and each thread runs the 20-key attention of ONE head:
+//   tile = 6 polylines x 20 nodes (120 rows), persistent over tiles; residual stream in registers (32 per thread);
+//   TMEM: Q [0,128) (also Wo / W1 / W2 accumulator) | K [128,256) | V [256,384) | A operand [384,512) (bf16x2 hi | lo);
+//   every Linear = bf16x3 tcgen05 GEMM with the A operand in tensor memory, weights through a 2 x 64 KB bulk-copy ring;
+//   K of all 4 heads is staged in shared memory for the logits, then V in the same buffer for the weighted sum.
+#include "tb_host.h"
+
+namespace tb {
+namespace pl2 {
+
+constexpr int THREADS = 512;
+constexpr int NP = 6, N = TB_PL_NODE, ROWS = NP * N;  // 120
+constexpr int KVS = 132;                              // staging row stride (floats)
+constexpr uint32_t TQ = 0, TK = 128, TV = 256, TA = 384;
+
+struct Smem {
+  unsigned char w[2][tc::BLOCK_BYTES];
+  float kv[ROWS * KVS];
+  float2 red[2][4][128];  // LayerNorm partials {sum, M2} [buffer][column quarter][row]
+  uint64_t bar_w[2], bar_mma;
+  uint32_t tmem_base;
+  uint8_t row_valid[128];
+  uint8_t pl_valid[8];
+};
+
+__device__ __forceinline__ int stage_block(uint32_t s) {  // stage s of the repeating 18-stage weight schedule
+  const int L = (s % 18) / 6, j = s % 6;
+  const int blk[6] = {1, 2, 0, 3, 4, 5};  // order inside a layer: Wk, Wv, Wq, Wo, W1, W2 (blocks: q,k,v,out,linear1,linear2)
+  return tbb::model_map_encoder_transformer_densetnt_layers_0_attn_in_proj_weight + L * 6 + blk[j];
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSceneIn in, const float* __restrict__ packed,
+                                                                 const unsigned char* __restrict__ tcw, float* __restrict__ x0_scratch,
+                                                                 float* __restrict__ pl_feature, uint8_t* __restrict__ pl_valid_out,
+                                                                 int n_tiles) {
+  extern __shared__ unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tc::uniform(tid >> 5), lane = tid & 31;
+  const int quad = warp & 3, q4 = warp >> 2;
+  const int r = quad * 32 + lane, c0 = 32 * q4;
+  const long n_pl_total = (long)dm.n_scene * dm.n_pl;
+
+  if (tid == 0) {
+    tc::mbar_init(&sm.bar_w[0], 1);
+    tc::mbar_init(&sm.bar_w[1], 1);
+    tc::mbar_init(&sm.bar_mma, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&sm.tmem_base, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tm0 = (uint32_t)tc::uniform((int)sm.tmem_base);
+  const uint32_t tm = tm0 + ((uint32_t)(quad * 32) << 16);
+  const uint32_t idesc = tc::make_idesc_bf16(128, 128);
+
+  uint32_t w_loaded = 0, w_consumed = 0, n_mma = 0, n_ln = 0;
+  auto prefetch = [&]() {  // thread 0: keep two weight stages in flight
+    while (w_loaded < w_consumed + 2) {
+      const uint32_t buf = w_loaded & 1;
+      tc::mbar_expect_tx(&sm.bar_w[buf], tc::BLOCK_BYTES);
+      tc::bulk_g2s(sm.w[buf], tcw + (size_t)stage_block(w_loaded) * tc::BLOCK_BYTES, tc::BLOCK_BYTES, &sm.bar_w[buf]);
+      ++w_loaded;
+    }
+  };
+  // A operand complete -> MMAs of `n_stage` consecutive weight stages into TMEM columns dst0, dst0 + 128, .. -> wait
+  auto run_gemm = [&](int n_stage, uint32_t dst0) {
+    tc::tmem_st_wait();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {  // converged warp, one elected lane issues (operands stay warp-uniform)
+      tc::tc_fence_after();
+      for (int j = 0; j < n_stage; ++j) {
+        const uint32_t s = w_consumed + j, buf = s & 1;
+        tc::mbar_wait(&sm.bar_w[buf], (s >> 1) & 1);
+        tc::tc_fence_after();
+        const uint32_t wh = tc::smem_u32(sm.w[buf]);
+        const uint64_t dh = tc::make_desc_sw128(wh), dl = tc::make_desc_sw128(wh + 2 * tc::KB_BYTES_128);
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {
+            const uint32_t ta = tm0 + TA + (term == 1 ? 64 : 0);
+            const uint64_t db = term == 2 ? dl : dh;
+#pragma unroll
+            for (int k = 0; k < 128; k += 16)
+              tc::mma_bf16_ts(tm0 + dst0 + 128 * j, ta + k / 2, db + (uint64_t)(((k >> 6) * tc::KB_BYTES_128 + (k & 63) * 2) >> 4), idesc,
+                              (term > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+      }
+      if (tc::elect_one()) tc::mma_commit(&sm.bar_mma);
+      __syncwarp();
+    }
+    tc::mbar_wait(&sm.bar_mma, n_mma & 1);
+    tc::tc_fence_after();
+    ++n_mma;
+    w_consumed += n_stage;
+    if (tid == 0) prefetch();
+  };
+  // LayerNorm over the 128 columns of a row held by 4 threads (32 columns each): one exchange of {sum, M2}
+  auto ln32 = [&](float (&v)[32], const float* __restrict__ g, const float* __restrict__ bt) {
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s4[i & 3] += v[i];
+    const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    const float mloc = sum * (1.0f / 32);
+    float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float d = v[i] - mloc;
+      q[i & 3] = fmaf(d, d, q[i & 3]);
+    }
+    const int buf = n_ln & 1;
+    ++n_ln;
+    sm.red[buf][q4][r] = make_float2(sum, (q[0] + q[1]) + (q[2] + q[3]));
+    __syncthreads();
+    const float2 p0 = sm.red[buf][0][r], p1 = sm.red[buf][1][r], p2 = sm.red[buf][2][r], p3 = sm.red[buf][3][r];
+    const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.0f / 128);
+    const float d0 = p0.x * (1.0f / 32) - mean, d1 = p1.x * (1.0f / 32) - mean, d2 = p2.x * (1.0f / 32) - mean, d3 = p3.x * (1.0f / 32) - mean;
+    const float m2 = ((p0.y + p1.y) + (p2.y + p3.y)) + 32.0f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));  // Chan
+    const float rstd = 1.0f / sqrtf(m2 * (1.0f / 128) + LN_EPS);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd * __ldg(g + c0 + i) + __ldg(bt + c0 + i);
+  };
+  auto write_A = [&](const float (&v)[32]) {
+    float ph[16], pl[16];
+    tc::split32_packed(v, ph, pl);
+    tc::tmem_st16(tm + TA + c0 / 2, ph);
+    tc::tmem_st16(tm + TA + 64 + c0 / 2, pl);
+  };
+  auto load_acc = [&](uint32_t col, float (&v)[32]) {
+    tc::tmem_ld32(tm + col + c0, v);
+    tc::tmem_ld_wait();
+  };
+  if (tid == 0) prefetch();
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long pl0 = (long)tile * NP;
+    const int p = r / N, n = r % N;
+    const long pl = pl0 + p;
+    const bool live = r < ROWS && pl < n_pl_total;
+    float x[32];  // residual stream: columns c0 .. c0+31 of row r
+    // ---- node features: InputPeEncoder([type | onehot(node)], PE(pos, atan2(dir)))  (sc_input.py:124-134) ---------
+    bool valid = false;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = 0.f;
+    if (live) {
+      const long node = pl * N + n;
+      valid = in.map_valid[node] != 0;
+      if (valid) {
+        if (q4 == 0) {
+          const float* w1 = packed + tbw::model_map_encoder_input_pe_encoder_mlp_fc_layers_0_weight;  // Wt4[8][32][4]
+          float h[32];
+#pragma unroll
+          for (int o = 0; o < 32; ++o) h[o] = __ldg(packed + tbw::model_map_encoder_input_pe_encoder_mlp_fc_layers_0_bias + o);
+          for (int k = 0; k < TB_PL_TYPE + N; ++k) {
+            const bool on = k < TB_PL_TYPE ? (in.map_type[pl * TB_PL_TYPE + k] != 0) : (k - TB_PL_TYPE == n);
+            if (!on) continue;
+#pragma unroll
+            for (int o = 0; o < 32; ++o) h[o] += __ldg(w1 + ((k >> 2) * 32 + o) * 4 + (k & 3));
+          }
+#pragma unroll
+          for (int o = 0; o < 32; ++o) h[o] = fmaxf(h[o], 0.f);
+          const float* w2 = packed + tbw::model_map_encoder_input_pe_encoder_mlp_fc_layers_3_weight;  // Wt4[8][32][4]
+#pragma unroll
+          for (int o = 0; o < 32; ++o) {
+            float acc = __ldg(packed + tbw::model_map_encoder_input_pe_encoder_mlp_fc_layers_3_bias + o);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc = fmaf(h[k], __ldg(w2 + ((k >> 2) * 32 + o) * 4 + (k & 3)), acc);
+            x[o] = acc;
+          }
+        } else {
+          const float px = in.map_pos[node * 2], py = in.map_pos[node * 2 + 1];
+          const float yaw = atan2f(in.map_dir[node * 2 + 1], in.map_dir[node * 2]);
+          const float* fxy = packed + tbw::pre_processing_input_pose_pe_map_pe_xy_freqs;
+          const float* fyaw = packed + tbw::pre_processing_input_pose_pe_map_pe_yaw_freqs;
+#pragma unroll 4
+          for (int i = 0; i < 32; ++i) {
+            const int j = 32 * (q4 - 1) + i;  // PE element: [cos(x f) 12 | sin(x f) 12 | cos(y f) 12 | sin(y f) 12 | cos(yaw g) 24 | sin(yaw g) 24]
+            float v;
+            if (j < 12) v = cosf(px * __ldg(fxy + 2 * j));
+            else if (j < 24) v = sinf(px * __ldg(fxy + 2 * (j - 12) + 1));
+            else if (j < 36) v = cosf(py * __ldg(fxy + 2 * (j - 24)));
+            else if (j < 48) v = sinf(py * __ldg(fxy + 2 * (j - 36) + 1));
+            else if (j < 72) v = cosf(yaw * __ldg(fyaw + 2 * (j - 48)));
+            else v = sinf(yaw * __ldg(fyaw + 2 * (j - 72) + 1));
+            x[i] = v;
+          }
+        }
+      }
+    }
+    if (q4 == 0) sm.row_valid[r] = valid;
+    // initial node features = the attention target of all 3 layers: per-CTA scratch, row-minor [32 column quads][128 rows]
+    float4* x0col = reinterpret_cast<float4*>(x0_scratch) + (size_t)blockIdx.x * 32 * 128 + (size_t)(8 * q4) * 128 + r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x0col[i * 128] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+    __syncthreads();
+    if (tid < 8) {
+      bool any = false;
+      if (tid < NP)
+        for (int j = 0; j < N; ++j) any |= sm.row_valid[tid * N + j] != 0;
+      sm.pl_valid[tid] = any;
+    }
+    __syncthreads();
+    const bool pvalid = sm.pl_valid[p < 8 ? p : 7] != 0;
+
+#pragma unroll 1
+    for (int L = 0; L < 3; ++L) {
+      const float* lw = packed + tbw::model_map_encoder_transformer_densetnt_layers_0_norm1_weight + L * tfl::STRIDE;
+      float t[32];
+      // ---- K | V = LN_tgt(x0) Wkv  (tgt = the INITIAL node features in every layer, map_encoder.py:78-84) -----------
+      if (L == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) t[i] = x[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 q = x0col[i * 128];
+          t[4 * i] = q.x, t[4 * i + 1] = q.y, t[4 * i + 2] = q.z, t[4 * i + 3] = q.w;
+        }
+      }
+      ln32(t, lw + tfl::NORMT_W, lw + tfl::NORMT_B);
+      write_A(t);
+      run_gemm(2, TK);  // -> K, V
+      // ---- Q = LN1(x) Wq ------------------------------------------------------------------------------------------------
+#pragma unroll
+      for (int i = 0; i < 32; ++i) t[i] = x[i];
+      ln32(t, lw + tfl::NORM1_W, lw + tfl::NORM1_B);
+      write_A(t);
+      run_gemm(1, TQ);
+      // ---- attention inside each polyline: thread (row, q4) = head q4 of the row ------------------------------------------
+      load_acc(TK, t);
+      if (r < ROWS) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          reinterpret_cast<float4*>(sm.kv + r * KVS + c0)[i] =
+              make_float4(t[4 * i] + __ldg(lw + tfl::IN_B + D + c0 + 4 * i), t[4 * i + 1] + __ldg(lw + tfl::IN_B + D + c0 + 4 * i + 1),
+                          t[4 * i + 2] + __ldg(lw + tfl::IN_B + D + c0 + 4 * i + 2), t[4 * i + 3] + __ldg(lw + tfl::IN_B + D + c0 + 4 * i + 3));
+      }
+      __syncthreads();
+      float pj[N];
+      float inv = 0.f;
+      load_acc(TQ, t);
+      if (r < ROWS) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) t[i] += __ldg(lw + tfl::IN_B + c0 + i);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const float* kr = sm.kv + (p * N + j) * KVS + c0;
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const float4 k4 = reinterpret_cast<const float4*>(kr)[i], k5 = reinterpret_cast<const float4*>(kr)[i + 1];
+            a0 = fmaf(t[4 * i + 3], k4.w, fmaf(t[4 * i + 2], k4.z, fmaf(t[4 * i + 1], k4.y, fmaf(t[4 * i], k4.x, a0))));
+            a1 = fmaf(t[4 * i + 7], k5.w, fmaf(t[4 * i + 6], k5.z, fmaf(t[4 * i + 5], k5.y, fmaf(t[4 * i + 4], k5.x, a1))));
+          }
+          pj[j] = sm.row_valid[p * N + j] ? (a0 + a1) * 0.17677669529663687f : -INFINITY;
+          mx = fmaxf(mx, pj[j]);
+        }
+        if (mx != -INFINITY) {
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            pj[j] = (pj[j] == -INFINITY) ? 0.f : expf(pj[j] - mx);
+            sum += pj[j];
+          }
+          inv = 1.0f / sum;
+        } else {
+#pragma unroll
+          for (int j = 0; j < N; ++j) pj[j] = 0.f;
+        }
+      }
+      __syncthreads();  // every thread is done with K
+      load_acc(TV, t);
+      if (r < ROWS) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          reinterpret_cast<float4*>(sm.kv + r * KVS + c0)[i] =
+              make_float4(t[4 * i] + __ldg(lw + tfl::IN_B + 2 * D + c0 + 4 * i), t[4 * i + 1] + __ldg(lw + tfl::IN_B + 2 * D + c0 + 4 * i + 1),
+                          t[4 * i + 2] + __ldg(lw + tfl::IN_B + 2 * D + c0 + 4 * i + 2), t[4 * i + 3] + __ldg(lw + tfl::IN_B + 2 * D + c0 + 4 * i + 3));
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) t[i] = 0.f;
+      if (r < ROWS) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const float* vr = sm.kv + (p * N + j) * KVS + c0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 v4 = reinterpret_cast<const float4*>(vr)[i];
+            t[4 * i] = fmaf(pj[j], v4.x, t[4 * i]);
+            t[4 * i + 1] = fmaf(pj[j], v4.y, t[4 * i + 1]);
+            t[4 * i + 2] = fmaf(pj[j], v4.z, t[4 * i + 2]);
+            t[4 * i + 3] = fmaf(pj[j], v4.w, t[4 * i + 3]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) t[i] *= inv;
+      }
+      write_A(t);
+      // ---- out-proj, residual (dead rows = polylines without a valid node get no attention update) ----------------------
+      run_gemm(1, TQ);
+      load_acc(TQ, t);
+      if (pvalid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] += t[i] + __ldg(lw + tfl::OUT_B + c0 + i);
+      }
+      // ---- FFN ------------------------------------------------------------------------------------------------------------
+#pragma unroll
+      for (int i = 0; i < 32; ++i) t[i] = x[i];
+      ln32(t, lw + tfl::NORM2_W, lw + tfl::NORM2_B);
+      write_A(t);
+      run_gemm(1, TQ);
+      load_acc(TQ, t);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) t[i] = fmaxf(t[i] + __ldg(lw + tfl::L1_B + c0 + i), 0.f);
+      write_A(t);
+      run_gemm(1, TQ);
+      load_acc(TQ, t);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = valid ? x[i] + t[i] + __ldg(lw + tfl::L2_B + c0 + i) : 0.f;
+    }
+    // ---- masked max-pool over the valid nodes of each polyline (map_encoder.py:95-97,105-106) ------------------------------
+    {
+      float* stage = sm.kv;  // [col][row], 128 x 120 floats
+      __syncthreads();
+      if (r < ROWS) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) stage[(c0 + i) * ROWS + r] = x[i];
+      }
+      __syncthreads();
+      for (int idx = tid; idx < NP * 128; idx += THREADS) {
+        const int pp = idx >> 7, c = idx & 127;
+        if (pl0 + pp >= n_pl_total) continue;
+        float mx = -INFINITY;
+        for (int j = 0; j < N; ++j)
+          if (sm.row_valid[pp * N + j]) mx = fmaxf(mx, stage[c * ROWS + pp * N + j]);
+        pl_feature[(pl0 + pp) * 128 + c] = sm.pl_valid[pp] ? mx : 0.f;
+      }
+      if (tid < NP && pl0 + tid < n_pl_total) pl_valid_out[pl0 + tid] = sm.pl_valid[tid];
+      __syncthreads();
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(sm.tmem_base, 512);
+}
+
+}  // namespace pl2
+}  // namespace tb
+
+int tb::launch_map_polyline_tc2(const TbDims& d, const TbSceneIn& in, const float* packed, float* x0_scratch, int n_cta,
+                                float* pl_feature, uint8_t* pl_valid, cudaStream_t st) {
+  static bool attr_set = false;
+  const int smem = (int)sizeof(pl2::Smem) + 1024;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(pl2::k_map_polyline_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return TB_ERR_LAUNCH;
+    attr_set = true;
+  }
+  const long n_pl = (long)d.n_scene * d.n_pl;
+  const int n_tiles = (int)((n_pl + pl2::NP - 1) / pl2::NP);
+  const int grid = n_tiles < n_cta ? n_tiles : n_cta;
+  pl2::k_map_polyline_tc2<<<grid, pl2::THREADS, smem, st>>>(d, in, packed, tc_blob(packed), x0_scratch, pl_feature, pl_valid, n_tiles);
+  count_launch();
+  return launch_status();
+}
