@@ -21,6 +21,7 @@ struct Smem {
   unsigned char w[2][tc::BLOCK_BYTES];
   float kv[ROWS * KVS];
   float2 red[2][4][128];  // LayerNorm partials {sum, M2} [buffer][column quarter][row]
+  float lp[2][12][128];   // per-layer bias / LayerNorm vectors (double-buffered by layer parity)
   uint64_t bar_w[2], bar_mma;
   uint32_t tmem_base;
   uint8_t row_valid[128];
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
     if (tid == 0) prefetch();
   };
   // LayerNorm over the 128 columns of a row held by 4 threads (32 columns each): one exchange of {sum, M2}
-  auto ln32 = [&](float (&v)[32], const float* __restrict__ g, const float* __restrict__ bt) {
+  auto ln32 = [&](float (&v)[32], const float* g, const float* bt) {  // g, bt: shared-memory vectors, read after the barrier
     float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 32; ++i) s4[i & 3] += v[i];
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
     const float m2 = ((p0.y + p1.y) + (p2.y + p3.y)) + 32.0f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));  // Chan
     const float rstd = 1.0f / sqrtf(m2 * (1.0f / 128) + LN_EPS);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd * __ldg(g + c0 + i) + __ldg(bt + c0 + i);
+    for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd * g[c0 + i] + bt[c0 + i];
   };
   auto write_A = [&](const float (&v)[32]) {
     float ph[16], pl[16];
@@ -212,6 +213,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
 #pragma unroll 1
     for (int L = 0; L < 3; ++L) {
       const float* lw = packed + tbw::model_map_encoder_transformer_densetnt_layers_0_norm1_weight + L * tfl::STRIDE;
+      // the layer's bias / LayerNorm vectors -> shared memory (visible after the barrier inside the first LayerNorm)
+      float (*lp)[128] = sm.lp[L & 1];
+      {
+        const int off[12] = {tfl::NORMT_W, tfl::NORMT_B, tfl::NORM1_W, tfl::NORM1_B, tfl::IN_B, tfl::IN_B + 128, tfl::IN_B + 256,
+                             tfl::OUT_B, tfl::NORM2_W, tfl::NORM2_B, tfl::L1_B, tfl::L2_B};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int i = tid + k * THREADS;
+          lp[i >> 7][i & 127] = __ldg(lw + off[i >> 7] + (i & 127));
+        }
+      }
+      enum { P_NT_W, P_NT_B, P_N1_W, P_N1_B, P_BQ, P_BK, P_BV, P_BO, P_N2_W, P_N2_B, P_B1, P_B2 };
       float t[32];
       // ---- K | V = LN_tgt(x0) Wkv  (tgt = the INITIAL node features in every layer, map_encoder.py:78-84) -----------
       if (L == 0) {
@@ -224,13 +237,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
           t[4 * i] = q.x, t[4 * i + 1] = q.y, t[4 * i + 2] = q.z, t[4 * i + 3] = q.w;
         }
       }
-      ln32(t, lw + tfl::NORMT_W, lw + tfl::NORMT_B);
+      ln32(t, lp[P_NT_W], lp[P_NT_B]);
       write_A(t);
       run_gemm(2, TK);  // -> K, V
       // ---- Q = LN1(x) Wq ------------------------------------------------------------------------------------------------
 #pragma unroll
       for (int i = 0; i < 32; ++i) t[i] = x[i];
-      ln32(t, lw + tfl::NORM1_W, lw + tfl::NORM1_B);
+      ln32(t, lp[P_N1_W], lp[P_N1_B]);
       write_A(t);
       run_gemm(1, TQ);
       // ---- attention inside each polyline: thread (row, q4) = head q4 of the row ------------------------------------------
@@ -239,8 +252,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           reinterpret_cast<float4*>(sm.kv + r * KVS + c0)[i] =
-              make_float4(t[4 * i] + __ldg(lw + tfl::IN_B + D + c0 + 4 * i), t[4 * i + 1] + __ldg(lw + tfl::IN_B + D + c0 + 4 * i + 1),
-                          t[4 * i + 2] + __ldg(lw + tfl::IN_B + D + c0 + 4 * i + 2), t[4 * i + 3] + __ldg(lw + tfl::IN_B + D + c0 + 4 * i + 3));
+              make_float4(t[4 * i] + lp[P_BK][c0 + 4 * i], t[4 * i + 1] + lp[P_BK][c0 + 4 * i + 1], t[4 * i + 2] + lp[P_BK][c0 + 4 * i + 2],
+                          t[4 * i + 3] + lp[P_BK][c0 + 4 * i + 3]);
       }
       __syncthreads();
       float pj[N];
@@ -248,7 +261,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
       load_acc(TQ, t);
       if (r < ROWS) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) t[i] += __ldg(lw + tfl::IN_B + c0 + i);
+        for (int i = 0; i < 32; ++i) t[i] += lp[P_BQ][c0 + i];
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < N; ++j) {
@@ -282,8 +295,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           reinterpret_cast<float4*>(sm.kv + r * KVS + c0)[i] =
-              make_float4(t[4 * i] + __ldg(lw + tfl::IN_B + 2 * D + c0 + 4 * i), t[4 * i + 1] + __ldg(lw + tfl::IN_B + 2 * D + c0 + 4 * i + 1),
-                          t[4 * i + 2] + __ldg(lw + tfl::IN_B + 2 * D + c0 + 4 * i + 2), t[4 * i + 3] + __ldg(lw + tfl::IN_B + 2 * D + c0 + 4 * i + 3));
+              make_float4(t[4 * i] + lp[P_BV][c0 + 4 * i], t[4 * i + 1] + lp[P_BV][c0 + 4 * i + 1], t[4 * i + 2] + lp[P_BV][c0 + 4 * i + 2],
+                          t[4 * i + 3] + lp[P_BV][c0 + 4 * i + 3]);
       }
       __syncthreads();
 #pragma unroll
@@ -310,22 +323,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
       load_acc(TQ, t);
       if (pvalid) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] += t[i] + __ldg(lw + tfl::OUT_B + c0 + i);
+        for (int i = 0; i < 32; ++i) x[i] += t[i] + lp[P_BO][c0 + i];
       }
       // ---- FFN ------------------------------------------------------------------------------------------------------------
 #pragma unroll
       for (int i = 0; i < 32; ++i) t[i] = x[i];
-      ln32(t, lw + tfl::NORM2_W, lw + tfl::NORM2_B);
+      ln32(t, lp[P_N2_W], lp[P_N2_B]);
       write_A(t);
       run_gemm(1, TQ);
       load_acc(TQ, t);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) t[i] = fmaxf(t[i] + __ldg(lw + tfl::L1_B + c0 + i), 0.f);
+      for (int i = 0; i < 32; ++i) t[i] = fmaxf(t[i] + lp[P_B1][c0 + i], 0.f);
       write_A(t);
       run_gemm(1, TQ);
       load_acc(TQ, t);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) x[i] = valid ? x[i] + t[i] + __ldg(lw + tfl::L2_B + c0 + i) : 0.f;
+      for (int i = 0; i < 32; ++i) x[i] = valid ? x[i] + t[i] + lp[P_B2][c0 + i] : 0.f;
     }
     // ---- masked max-pool over the valid nodes of each polyline (map_encoder.py:95-97,105-106) ------------------------------
     {
