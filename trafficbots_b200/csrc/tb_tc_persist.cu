@@ -287,10 +287,11 @@ __device__ __forceinline__ void enumerate_step(const Args& a, const StepCfg& c, 
   r.gemm_end();
 }
 
-struct Loader {  // run by a whole (converged) warp; one elected lane issues the copies
-  Smem& sm;
+template <class SM>
+struct LoaderT {  // run by a whole (converged) warp; one elected lane issues the copies
+  SM& sm;
   uint32_t g = 0, n_cfg = 0;
-  __device__ Loader(Smem& s) : sm(s) {}
+  __device__ LoaderT(SM& s) : sm(s) {}
   __device__ __forceinline__ void wait_free(uint32_t slot, uint32_t half) {
     const uint32_t use = g >> 1;
     if (use > 0) tc::mbar_wait(&sm.free_[slot][half], (use - 1) & 1);
@@ -340,11 +341,12 @@ struct Loader {  // run by a whole (converged) warp; one elected lane issues the
   }
 };
 
-struct Issuer {
-  Smem& sm;
+template <class SM>
+struct IssuerT {
+  SM& sm;
   uint32_t tm0;
   uint32_t g = 0, nf[2] = {0, 0}, n_ready = 0, n_cfg = 0, n_p[2] = {0, 0}, n_kvi = 0, kvi_slot = 0;
-  __device__ Issuer(Smem& s, uint32_t t) : sm(s), tm0(t) {}
+  __device__ IssuerT(SM& s, uint32_t t) : sm(s), tm0(t) {}
   __device__ __forceinline__ int wait_cfg() {
     tc::mbar_wait(&sm.cfg, n_cfg & 1);
     ++n_cfg;
@@ -566,7 +568,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
   if (warp == 9) {
     // ========================================================================================================== loader
     {
-      Loader ld(sm);
+      LoaderT<Smem> ld(sm);
       for (int t = a.t_first; t <= a.t_last; ++t) {
         const int tl_t = min(t - 1, Th - 1);
         cfg.nblk_tl = (uniform(in.n_key_tl[(size_t)s * Th + tl_t]) + 63) / 64;
@@ -577,7 +579,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
   } else if (warp == 8) {
     // ========================================================================================================== issuer
     {  // the whole warp runs the issue program (so that every operand is provably warp-uniform); one elected lane issues
-      Issuer is(sm, tm0);
+      IssuerT<Smem> is(sm, tm0);
       for (int t = a.t_first; t <= a.t_last; ++t) {
         const int tl_t = min(t - 1, Th - 1);
         cfg.nblk_tl = (uniform(in.n_key_tl[(size_t)s * Th + tl_t]) + 63) / 64;
@@ -1497,6 +1499,953 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
   cluster_sync_all();  // no CTA leaves while a peer may still read its shared memory or arrive on its barrier
 }
 
+// =============================================================================================================================
+// 16-worker-warp variant: FOUR threads per TMEM lane.  Thread (lane l, part 0..3) owns columns [32 part, 32 part + 32) of
+// lane l in every operand write (both lanes of an agent write complete A operands), and 16 columns [32 part + 16 upper, +16)
+// of the agent in the epilogues that end in shared / global memory.  In the attention the pass of a lane is shared by the
+// two threads part = 2 hp, 2 hp + 1: each takes 32 of the block's 64 keys, and they agree on the running maximum through
+// shared memory (one 64-thread named barrier per key block).  Same issuer / loader programs as the 8-warp kernel.
+// =============================================================================================================================
+constexpr int WORKERS16 = 512;
+constexpr int THREADS16 = WORKERS16 + 64;
+
+struct Smem16 {
+  unsigned char ring[2][BLK];
+  float xs[128 * MAXA];  // residual stream, [col][agent]
+  float xo[128 * MAXA];  // exchange buffer
+  float lp[2][12][128];  // parameter vectors of the current / next phase
+  float emb_w1[384], emb_b1[32], emb_b2[32], f_xy[24], f_yaw[48];
+  float2 red[2][4][128];  // LayerNorm partials {sum, M2} [buffer][part][lane]
+  float mxs[4][128];      // softmax exchange between the two threads of a (lane, pass): block max / final sum
+  float mean_part[8][MAXA][2];
+  float4 pose[MAXA];
+  float2 vel[MAXA];
+  float acc[MAXA], yaw_rate[MAXA];
+  uint8_t valid[MAXA], killed[MAXA], goal_valid[MAXA], sticky[3][MAXA], type[MAXA][4];
+  float tailc[9][MAXA];
+  float map_boundary[4];
+  uint8_t tflag[MAXA];
+  uint64_t full[2][2], free_[2][2], grant, wfill, ready, mma, cfg, s[2], p[2], o[2];
+  uint32_t tmem_base;
+  int n_valid, kvi_slot;
+};
+static_assert(sizeof(Smem16) + 1024 <= 232448, "shared memory budget (227 KB per CTA)");
+
+__device__ __forceinline__ void worker_sync16() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
+  extern __shared__ unsigned char smem_raw[];
+  Smem16& sm = *reinterpret_cast<Smem16*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
+  const TbDims& dm = a.dm;
+  const TbRolloutIn& in = a.in;
+  const float* __restrict__ packed = a.packed;
+  const int A = dm.n_agent, K = dm.n_mode, S = dm.n_scene, B = S * K, Th = dm.n_step_hist, T = dm.n_step, Tg = dm.n_step_gt;
+  const int nT_map = (dm.n_pl + 63) / 64, nT_tl = (dm.n_tl + 63) / 64;
+  const int rank = (int)cluster_ctarank(), n_cta = (int)cluster_nctarank();
+  const int b = blockIdx.x / n_cta, s = b / K;
+  const int tid = threadIdx.x, warp = uniform(tid >> 5), lane = tid & 31;
+  const size_t BA = (size_t)B * A;
+  const int nkey_map = uniform(in.n_key_map[s]);
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 2; ++j) {
+        tc::mbar_init(&sm.full[i][j], 1);
+        tc::mbar_init(&sm.free_[i][j], 1);
+      }
+    tc::mbar_init(&sm.grant, 1);
+    tc::mbar_init(&sm.wfill, 16);
+    tc::mbar_init(&sm.ready, 16);
+    tc::mbar_init(&sm.mma, 1);
+    tc::mbar_init(&sm.cfg, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&sm.s[i], 1);
+      tc::mbar_init(&sm.p[i], 8);
+      tc::mbar_init(&sm.o[i], 1);
+    }
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&sm.tmem_base, 512);
+  for (int i = tid; i < 384; i += THREADS16) sm.emb_w1[i] = __ldg(packed + tbw::model_agent_encoder_mlp_fc_layers_0_weight + i);
+  if (tid < 32) {
+    sm.emb_b1[tid] = __ldg(packed + tbw::model_agent_encoder_mlp_fc_layers_0_bias + tid);
+    sm.emb_b2[tid] = __ldg(packed + tbw::model_agent_encoder_mlp_fc_layers_3_bias + tid);
+  }
+  if (tid < 24) sm.f_xy[tid] = __ldg(packed + tbw::pre_processing_input_pose_pe_agent_pe_xy_freqs + tid);
+  if (tid < 48) sm.f_yaw[tid] = __ldg(packed + tbw::pre_processing_input_pose_pe_agent_pe_yaw_freqs + tid);
+  if (tid < MAXA) {
+    const int ag = tid;
+    const bool live = ag < A;
+    const size_t ba = (size_t)b * A + (live ? ag : 0), sa = (size_t)s * A + (live ? ag : 0);
+    sm.pose[ag] = live ? *reinterpret_cast<const float4*>(a.sv.agent_state + ba * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sm.vel[ag] = live ? make_float2(a.sv.vel[ba * 2], a.sv.vel[ba * 2 + 1]) : make_float2(0.f, 0.f);
+    sm.acc[ag] = live ? a.sv.acc[ba] : 0.f;
+    sm.yaw_rate[ag] = live ? a.sv.yaw_rate[ba] : 0.f;
+    sm.valid[ag] = live ? a.sv.valid[(size_t)(a.t_first & 1) * BA + ba] : (uint8_t)0;
+    sm.killed[ag] = live ? a.sv.killed[ba] : (uint8_t)0;
+    sm.goal_valid[ag] = live ? a.sv.goal_valid[ba] : (uint8_t)0;
+    for (int i = 0; i < 3; ++i) {
+      sm.sticky[i][ag] = live ? a.sv.sticky[(size_t)i * BA + ba] : (uint8_t)0;
+      sm.type[ag][i] = live ? in.agent_type[sa * 3 + i] : (uint8_t)0;
+    }
+  }
+  float4* const hid_t = a.sv.hidden_t + ((size_t)rank * 3 * B + b) * 32 * A;
+  float4* const x0_t = a.sv.x0_t + ((size_t)rank * B + b) * 32 * A;
+  const float4* const goal_in_t = a.sv.goal_in_t + (size_t)b * 32 * A;
+  const float4* const latent_in_t = a.sv.latent_in_t + (size_t)b * 32 * A;
+  for (int L = 0; L < 3; ++L) {
+    const float4* src = reinterpret_cast<const float4*>(a.sv.hidden + ((size_t)L * BA + (size_t)b * A) * D);
+    float4* dst = hid_t + (size_t)L * B * 32 * A;
+    for (int i = tid; i < A * 32; i += THREADS16) {
+      const int ag_ = i % A, c4 = i / A;
+      dst[c4 * A + ag_] = src[ag_ * 32 + c4];
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  cluster_sync_all();
+  const uint32_t tm0 = (uint32_t)uniform((int)sm.tmem_base);
+
+  StepCfg cfg;
+  cfg.nblk_map = (nkey_map + 63) / 64;
+  cfg.rank = rank;
+  cfg.n_cta = n_cta;
+  cfg.kv_map = in.kv_map_tc + (size_t)s * nT_map * BLK;
+  cfg.kv_map_layer_stride = (size_t)S * nT_map * BLK;
+  cfg.kv_tl_layer_stride = (size_t)S * Th * nT_tl * BLK;
+
+  if (warp == 17) {
+    LoaderT<Smem16> ld(sm);
+    for (int t = a.t_first; t <= a.t_last; ++t) {
+      const int tl_t = min(t - 1, Th - 1);
+      cfg.nblk_tl = (uniform(in.n_key_tl[(size_t)s * Th + tl_t]) + 63) / 64;
+      cfg.kv_tl = in.kv_tl_tc + ((size_t)s * Th + tl_t) * nT_tl * BLK;
+      enumerate_step(a, cfg, ld);
+    }
+  } else if (warp == 16) {
+    IssuerT<Smem16> is(sm, tm0);
+    for (int t = a.t_first; t <= a.t_last; ++t) {
+      const int tl_t = min(t - 1, Th - 1);
+      cfg.nblk_tl = (uniform(in.n_key_tl[(size_t)s * Th + tl_t]) + 63) / 64;
+      cfg.kv_tl = nullptr;
+      enumerate_step(a, cfg, is);
+    }
+  } else {
+    // ========================================================================================================== workers
+    const int quad = warp & 3, part = warp >> 2, half = part >> 1, sub = part & 1;
+    const int l = quad * 32 + lane;  // TMEM lane
+    const int ag = l & 63, upper = l >> 6;
+    const int cq = 32 * part;             // operand columns of this thread
+    const int ce = cq + 16 * upper;       // epilogue columns of this thread (16)
+    const bool live = ag < A;
+    const bool writer = upper == 0 && live && rank == 0;
+    const size_t ba = (size_t)b * A + (live ? ag : 0), sa = (size_t)s * A + (live ? ag : 0);
+    const uint32_t tm = tm0 + ((uint32_t)(quad * 32) << 16);
+    const int pair_id = 2 + quad * 2 + half;  // named barrier of the two warps (quad, 2 half) and (quad, 2 half + 1)
+    uint32_t n_mma = 0, n_s = 0, n_o = 0, n_grant = 0, n_ln = 0, n_lp = 0;
+    int n_mark = 0;
+    auto mark = [&]() {
+      if (a.trace && blockIdx.x == 0 && tid == 0 && n_mark < 1000) a.trace[n_mark++] = clock64();
+    };
+    auto signal_ready = [&]() {
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.ready);
+    };
+    auto wait_gemm = [&]() {
+      tc::mbar_wait(&sm.mma, n_mma & 1);
+      tc::tc_fence_after();
+      ++n_mma;
+    };
+    auto xs_at = [&](int c) -> float& { return sm.xs[c * MAXA + ag]; };
+    auto load_x = [&](float (&v)[32]) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = xs_at(cq + i);
+    };
+    auto write_A = [&](uint32_t col, const float (&v)[32]) {  // columns cq .. cq+31 of a K = 128 operand
+      float ph[16], pl[16];
+      tc::split32_packed(v, ph, pl);
+      tc::tmem_st16(tm + col + cq / 2, ph);
+      tc::tmem_st16(tm + col + 64 + cq / 2, pl);
+    };
+    auto load_acc = [&](uint32_t col, float (&v)[32]) {
+      tc::tmem_ld32(tm + col + cq, v);
+      tc::tmem_ld_wait();
+    };
+    auto load_acc16 = [&](uint32_t col, float (&v)[16]) {  // this thread's 16 epilogue columns
+      tc::tmem_ld16(tm + col + ce, v);
+      tc::tmem_ld_wait();
+    };
+    auto ln32 = [&](float (&v)[32], const float* g, const float* bt) {
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 32; ++i) s4[i & 3] += v[i];
+      const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      const float mloc = sum * (1.0f / 32);
+      float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float d = v[i] - mloc;
+        q[i & 3] = fmaf(d, d, q[i & 3]);
+      }
+      const int buf = n_ln & 1;
+      ++n_ln;
+      sm.red[buf][part][l] = make_float2(sum, (q[0] + q[1]) + (q[2] + q[3]));
+      worker_sync16();
+      const float2 p0 = sm.red[buf][0][l], p1 = sm.red[buf][1][l], p2 = sm.red[buf][2][l], p3 = sm.red[buf][3][l];
+      const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.0f / 128);
+      const float d0 = p0.x * (1.0f / 32) - mean, d1 = p1.x * (1.0f / 32) - mean, d2 = p2.x * (1.0f / 32) - mean, d3 = p3.x * (1.0f / 32) - mean;
+      const float m2 = ((p0.y + p1.y) + (p2.y + p3.y)) + 32.0f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+      const float rstd = 1.0f / sqrtf(m2 * (1.0f / 128) + LN_EPS);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd * g[cq + i] + bt[cq + i];
+    };
+    float4 pf0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch_params = [&](int p) {
+      const int o0 = warp < 12 ? phase_vec(p, warp) : -1;
+      if (o0 >= 0) pf0 = __ldg(reinterpret_cast<const float4*>(packed + o0) + lane);
+    };
+    auto commit_params = [&]() {
+      if (warp < 12) reinterpret_cast<float4*>(sm.lp[(n_lp + 1) & 1][warp])[lane] = pf0;
+    };
+    fetch_params(0);
+    if (warp < 12) reinterpret_cast<float4*>(sm.lp[0][warp])[lane] = pf0;
+    worker_sync16();
+
+    const float sc = 0.17677669529663687f * 1.4426950408889634f;
+
+    if (part == 0 && upper == 0 && live) {  // per-rollout constants of the tail
+      const int b2o[3] = {tbw::action_head_mlp_mean_0_fc_layers_2_bias, tbw::action_head_mlp_mean_1_fc_layers_2_bias,
+                          tbw::action_head_mlp_mean_2_fc_layers_2_bias};
+      const int lso[3] = {tbw::action_head_log_std_0, tbw::action_head_log_std_1, tbw::action_head_log_std_2};
+      float b2x = 0.f, b2y = 0.f, ls[2] = {0.f, 0.f};
+      for (int c3 = 0; c3 < 3; ++c3)
+        if (sm.type[ag][c3]) {
+          b2x += __ldg(packed + b2o[c3]);
+          b2y += __ldg(packed + b2o[c3] + 1);
+          ls[0] += __ldg(packed + lso[c3]);
+          ls[1] += __ldg(packed + lso[c3] + 1);
+        }
+      float logp = 0.f;
+      for (int d = 0; d < 2; ++d) logp += -logf(expf(ls[d])) - 0.91893853320467267f;
+      sm.tailc[0][ag] = b2x;
+      sm.tailc[1][ag] = b2y;
+      sm.tailc[2][ag] = logp;
+      sm.tailc[3][ag] = in.latent_logp[ba];
+      for (int i = 0; i < 3; ++i) sm.tailc[4 + i][ag] = in.goal_gt ? in.goal_gt[sa * 4 + i] : 0.f;
+      sm.tailc[7][ag] = in.agent_size[sa * 3] * 8.0f;
+      long dst = in.dest[ba];
+      dst = dst < 0 ? 0 : (dst >= dm.n_pl ? dm.n_pl - 1 : dst);
+      const uint8_t* dtype = in.map_type + ((size_t)s * dm.n_pl + dst) * TB_PL_TYPE;
+      const bool lane_t = dtype[0] || dtype[1] || dtype[2] || dtype[3], edge_t = dtype[4] != 0;
+      sm.tailc[8][ag] = 50.0f * (1.0f - (edge_t ? 1.0f : 0.f) * 0.8f);
+      sm.tflag[ag] = (uint8_t)((lane_t ? 1 : 0) | (edge_t ? 2 : 0));
+      if (ag == 0)
+        for (int i = 0; i < 4; ++i) sm.map_boundary[i] = in.map_boundary[(size_t)s * 4 + i];
+    }
+
+#pragma unroll 1
+    for (int t = a.t_first; t <= a.t_last; ++t) {
+      const int tl_t = min(t - 1, Th - 1);
+      const int nkey_tl = uniform(in.n_key_tl[(size_t)s * Th + tl_t]);
+      mark();
+      const bool valid = sm.valid[ag] != 0;
+      const unsigned vm_lo = __ballot_sync(0xffffffffu, sm.valid[lane] != 0);
+      const unsigned vm_hi = __ballot_sync(0xffffffffu, sm.valid[lane + 32] != 0);
+      const unsigned long long vmask = ((unsigned long long)vm_hi << 32) | vm_lo;
+      const int n_valid = __popc(vm_lo) + __popc(vm_hi);
+      if (tid == 0) {
+        *reinterpret_cast<volatile int*>(&sm.n_valid) = n_valid;
+        __threadfence_block();
+        mbar_arrive(&sm.cfg);
+      }
+      // ---- state embedding: 8 threads per agent, 16 of the 128 features each (32 MLP outputs, then 96 PE values) --------
+      {
+        const int fidx = 2 * part + upper;
+        const float4 st = sm.pose[ag];
+        if (fidx < 2) {
+          float at[12];
+          at[0] = sm.vel[ag].x, at[1] = sm.vel[ag].y, at[2] = st.w, at[3] = sm.yaw_rate[ag], at[4] = sm.acc[ag];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            at[5 + i] = in.agent_size[sa * 3 + i];
+            at[8 + i] = sm.type[ag][i] ? 1.f : 0.f;
+          }
+          at[11] = 0.f;
+          float h[32];
+#pragma unroll
+          for (int o = 0; o < 32; ++o) {
+            float acc = sm.emb_b1[o];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) acc = fmaf(at[k], sm.emb_w1[((k >> 2) * 32 + o) * 4 + (k & 3)], acc);
+            h[o] = fmaxf(acc, 0.f);
+          }
+          const float* w2 = packed + tbw::model_agent_encoder_mlp_fc_layers_3_weight;  // Wt4[8][32][4], through L1
+#pragma unroll 4
+          for (int oo = 0; oo < 16; ++oo) {
+            const int o = 16 * fidx + oo;
+            float acc = sm.emb_b2[o];
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+              const float4 w = __ldg(reinterpret_cast<const float4*>(w2) + k4 * 32 + o);
+              acc = fmaf(h[4 * k4 + 3], w.w, fmaf(h[4 * k4 + 2], w.z, fmaf(h[4 * k4 + 1], w.y, fmaf(h[4 * k4], w.x, acc))));
+            }
+            sm.xs[o * MAXA + ag] = valid ? acc : 0.f;
+          }
+        } else {
+#pragma unroll 4
+          for (int i = 0; i < 16; ++i) {
+            const int j = 16 * (fidx - 2) + i;  // PE element 0..95
+            float v;
+            if (j < 12) v = cosf(st.x * sm.f_xy[2 * j]);
+            else if (j < 24) v = sinf(st.x * sm.f_xy[2 * (j - 12) + 1]);
+            else if (j < 36) v = cosf(st.y * sm.f_xy[2 * (j - 24)]);
+            else if (j < 48) v = sinf(st.y * sm.f_xy[2 * (j - 36) + 1]);
+            else if (j < 72) v = cosf(st.z * sm.f_yaw[2 * (j - 48)]);
+            else v = sinf(st.z * sm.f_yaw[2 * (j - 72) + 1]);
+            sm.xs[(32 + j) * MAXA + ag] = valid ? v : 0.f;
+          }
+        }
+      }
+      mark();
+
+      // ---- 9 pre-LN cross-attention layers ------------------------------------------------------------------------------------
+      const bool bypass = n_valid == 1;
+#pragma unroll 1
+      for (int Lx = 0; Lx < 9; ++Lx) {
+        const int kind = Lx / 3;
+        if (kind == 2 && bypass) break;
+        const int nkey = kind == 0 ? nkey_map : kind == 1 ? nkey_tl : (n_valid > 0 ? MAXA : 0);
+        const int nblk = (nkey + 63) / 64;
+        worker_sync16();
+        const float (*lp)[128] = sm.lp[n_lp & 1];
+        {
+          int pn = Lx + 1;
+          if (pn == 6 && bypass) pn = 9;
+          fetch_params(pn);
+        }
+        float v[32];
+        if (nblk > 0) {
+          if (kind == 2) {
+            if (Lx == 6) {
+              load_x(v);
+              if (upper == 0 && live) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x0_t[(cq / 4 + i) * A + ag] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              }
+            } else if (live) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 q = x0_t[(cq / 4 + i) * A + ag];
+                v[4 * i] = q.x, v[4 * i + 1] = q.y, v[4 * i + 2] = q.z, v[4 * i + 3] = q.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            ln32(v, lp[8], lp[9]);
+            write_A(T_A, v);
+            signal_ready();  // -> Wk (ACC0), Wv (ACC1)
+            wait_gemm();
+            tc::mbar_wait(&sm.grant, n_grant & 1);
+            ++n_grant;
+            {
+              unsigned char* blk = sm.ring[*reinterpret_cast<volatile int*>(&sm.kvi_slot)];
+              float kk[16];
+              load_acc16(T_ACC0, kk);  // K[ag, ce .. ce+15]: key row ag
+#pragma unroll
+              for (int i = 0; i < 16; ++i) kk[i] += lp[10][ce + i];
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                uint4 hi, lo;
+                tc::split8(kk + 8 * c, hi, lo);
+                const uint32_t off = (uint32_t)((ce >> 6) * 8192) + tc::sw128_off(ag, ((ce & 63) >> 3) + c);
+                *reinterpret_cast<uint4*>(blk + off) = hi;
+                *reinterpret_cast<uint4*>(blk + 16384 + off) = lo;
+              }
+              load_acc16(T_ACC1, kk);  // V[ag, ce .. ce+15] -> V^T rows d = ce + i, key column ag
+              unsigned char* vt = blk + HALF + (ag & 7) * 2;
+              const uint32_t kc = (uint32_t)(ag >> 3);
+#pragma unroll
+              for (int i = 0; i < 16; i += 2) {
+                const float v0 = kk[i] + lp[11][ce + i], v1 = kk[i + 1] + lp[11][ce + i + 1];
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+                const float2 hf = __bfloat1622float2(hh);
+                const __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int d = ce + i + e;
+                  const uint32_t off = (uint32_t)((d >> 3) * 1024 + (d & 7) * 128) + ((kc ^ (uint32_t)(d & 7)) << 4);
+                  *reinterpret_cast<__nv_bfloat16*>(vt + off) = e ? hh.y : hh.x;
+                  *reinterpret_cast<__nv_bfloat16*>(vt + 16384 + off) = e ? ll.y : ll.x;
+                }
+              }
+              tc::fence_proxy_async();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.wfill);
+          }
+          load_x(v);
+          ln32(v, lp[0], lp[1]);
+          write_A(T_A, v);
+          signal_ready();  // -> Wq
+          const bool split_layer = kind == 0 && n_cta > 1;
+          if (!split_layer) commit_params();
+          wait_gemm();
+          if ((part & 1) == upper) {  // this thread's 32 Q columns = head `part` = the head lane l needs in pass part / 2
+            const int hp = part >> 1;
+            float q[32];
+            tc::tmem_ld32(tm + T_ACC0 + cq, q);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) q[i] = (q[i] + lp[2][cq + i]) * sc;
+            float ph[16], pl[16], zz[16];
+            tc::split32_packed(q, ph, pl);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) zz[i] = 0.f;
+            tc::tmem_st16(tm + T_A + 32 * hp + 16 * upper, ph);
+            tc::tmem_st16(tm + T_A + 64 + 32 * hp + 16 * upper, pl);
+            tc::tmem_st16(tm + T_A + 32 * hp + 16 * (1 - upper), zz);
+            tc::tmem_st16(tm + T_A + 64 + 32 * hp + 16 * (1 - upper), zz);
+          }
+          signal_ready();  // -> QK^T(0, .)
+          // ---- online softmax of pass `half`; this thread: keys 32 sub .. 32 sub + 31 of every block ---------------------------
+          float m_ref = -INFINITY, l_sum = 0.f;
+          const uint32_t sbase = tm + T_ACC0 + 64 * half;
+          const uint32_t obase = tm + T_O + 64 * half + 32 * upper + 16 * sub;
+          const bool split = kind == 0 && n_cta > 1;
+          const int nblk_my = kind == 0 ? (nblk > rank ? (nblk - rank + n_cta - 1) / n_cta : 0) : nblk;
+#pragma unroll 1
+          for (int jb = 0; jb < nblk_my; ++jb) {
+            const int key0 = (kind == 0 ? rank + jb * n_cta : jb) * 64 + 32 * sub;
+            tc::mbar_wait(&sm.s[half], n_s & 1);
+            ++n_s;
+            tc::tc_fence_after();
+            float sv_[32];
+            tc::tmem_ld32(sbase + 32 * sub, sv_);
+            tc::tmem_ld_wait();
+            if (kind == 2) {
+              const unsigned en = (unsigned)((vmask & ~(1ull << ag)) >> (32 * sub));
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (!((en >> j) & 1u)) sv_[j] = -INFINITY;
+            } else if (key0 + 32 > nkey) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (key0 + j >= nkey) sv_[j] = -INFINITY;
+            }
+            float mx4[4] = {sv_[0], sv_[1], sv_[2], sv_[3]};
+#pragma unroll
+            for (int j = 4; j < 32; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], sv_[j]);
+            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            sm.mxs[part][l] = mx;
+            pair_sync(pair_id);  // both threads of the pass have loaded their logits and published their maxima
+            mx = fmaxf(mx, sm.mxs[part ^ 1][l]);
+            float alpha = 1.f;
+            bool resc = false;
+            if (mx > m_ref + 8.0f) {
+              alpha = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - mx);
+              m_ref = mx;
+              l_sum *= alpha;
+              resc = jb > 0;
+            }
+            const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+            float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              sv_[j] = ex2_approx(sv_[j] + neg_m);
+              ps4[j & 3] += sv_[j];
+            }
+            l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+            {
+              float ph[16], pl[16];
+              tc::split32_packed(sv_, ph, pl);
+              tc::tmem_st16(sbase + 16 * sub, ph);
+              tc::tmem_st16(sbase + 32 + 16 * sub, pl);
+            }
+            if (__any_sync(0xffffffffu, resc)) {
+              float o[16];
+              tc::tmem_ld16(obase, o);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] *= alpha;
+              tc::tmem_st16(obase, o);
+            }
+            tc::tmem_st_wait();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.p[half]);
+          }
+          {
+            // total softmax denominator of the (lane, pass): the two threads' partial sums
+            float* lxs = reinterpret_cast<float*>(&sm.red[0][0][0]);  // [4][128] (no LayerNorm in flight; separate from mxs)
+            lxs[part * 128 + l] = l_sum;
+            pair_sync(pair_id);
+            const float l_tot = l_sum + lxs[(part ^ 1) * 128 + l];
+            float o[16];
+            if (nblk_my > 0) {
+              tc::mbar_wait(&sm.o[half], n_o & 1);
+              ++n_o;
+              tc::tc_fence_after();
+              tc::tmem_ld16(obase, o);
+              tc::tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = 0.f;
+            }
+            float* xo_mine = &sm.xo[(64 * half + 32 * upper + 16 * sub) * MAXA + ag];  // this thread's 16 outputs, stride MAXA
+            if (split) {
+              const int nq = 4 / n_cta;  // float4 per thread and range (16 outputs = 4 float4)
+              float4* xp = reinterpret_cast<float4*>(sm.xo);                          // slots [src rank][nq][512] float4
+              float2* mls = &sm.red[0][0][0];  // [src rank][256 (lane, pass)] (m, l): the whole LayerNorm exchange area (idle here)
+              const int lp_id = half * 128 + l;
+              const uint32_t xp_addr = tc::smem_u32(xp), mls_addr = tc::smem_u32(mls);
+              cluster_sync_relaxed();
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int dst = q / nq, qq = q % nq;
+                const float4 val = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                const uint32_t off = (uint32_t)(((rank * nq + qq) * WORKERS16 + tid) * 16);
+                if (dst == rank) xp[(rank * nq + qq) * WORKERS16 + tid] = val;
+                else st_cluster_f32x4(mapa(xp_addr, (uint32_t)dst) + off, val);
+              }
+              if (sub == 0) {
+                for (int dst = 0; dst < n_cta; ++dst) {
+                  if (dst == rank) mls[rank * 256 + lp_id] = make_float2(m_ref, l_tot);
+                  else st_cluster_f32x2(mapa(mls_addr, (uint32_t)dst) + (uint32_t)((rank * 256 + lp_id) * 8), make_float2(m_ref, l_tot));
+                }
+              }
+              cluster_sync_all();
+              float m_all = -INFINITY;
+              float2 mlr[4];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                mlr[r] = r < n_cta ? mls[r * 256 + lp_id] : make_float2(-INFINITY, 0.f);
+                m_all = fmaxf(m_all, mlr[r].x);
+              }
+              float l_all = 0.f, w[4];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                w[r] = mlr[r].x == -INFINITY ? 0.f : exp2f(mlr[r].x - m_all);
+                l_all = fmaf(w[r], mlr[r].y, l_all);
+              }
+              const float inv = l_all > 0.f ? 1.0f / l_all : 0.f;
+              float4 mg[2];
+#pragma unroll
+              for (int qq = 0; qq < 2; ++qq) {
+                mg[qq] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (qq < nq) {
+#pragma unroll
+                  for (int r = 0; r < 4; ++r) {
+                    if (r < n_cta) {
+                      const float4 pv = xp[(r * nq + qq) * WORKERS16 + tid];
+                      mg[qq].x = fmaf(w[r], pv.x, mg[qq].x);
+                      mg[qq].y = fmaf(w[r], pv.y, mg[qq].y);
+                      mg[qq].z = fmaf(w[r], pv.z, mg[qq].z);
+                      mg[qq].w = fmaf(w[r], pv.w, mg[qq].w);
+                    }
+                  }
+                  mg[qq].x *= inv, mg[qq].y *= inv, mg[qq].z *= inv, mg[qq].w *= inv;
+                }
+              }
+              cluster_sync_relaxed();
+#pragma unroll
+              for (int qq = 0; qq < 2; ++qq) {
+                if (qq < nq) {
+                  const uint32_t off = (uint32_t)((((rank * nq + qq) * WORKERS16) + tid) * 16);
+                  for (int dst = 0; dst < n_cta; ++dst) {
+                    if (dst == rank) xp[(rank * nq + qq) * WORKERS16 + tid] = mg[qq];
+                    else st_cluster_f32x4(mapa(xp_addr, (uint32_t)dst) + off, mg[qq]);
+                  }
+                }
+              }
+              cluster_sync_all();
+              commit_params();
+            } else {
+              const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) xo_mine[j * MAXA] = o[j] * inv;
+            }
+          }
+          worker_sync16();
+          if (split) {  // merged outputs as [float4 q][worker thread]; my columns cq..cq+31 = head `part` of agent ag
+            const float4* xp = reinterpret_cast<const float4*>(sm.xo);
+            const int l_src = ag + 64 * (part & 1);  // lane that held head `part`: lower lanes hold even heads
+#pragma unroll
+            for (int sb = 0; sb < 2; ++sb) {
+              const int src_tid = (((2 * (part >> 1) + sb) * 4 + (l_src >> 5)) << 5) + (l_src & 31);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 t4 = xp[q * WORKERS16 + src_tid];
+                v[16 * sb + 4 * q] = t4.x, v[16 * sb + 4 * q + 1] = t4.y, v[16 * sb + 4 * q + 2] = t4.z, v[16 * sb + 4 * q + 3] = t4.w;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = sm.xo[(cq + i) * MAXA + ag];
+          }
+          write_A(T_A, v);
+          signal_ready();  // -> Wo
+          wait_gemm();
+          {
+            float o16[16];
+            load_acc16(T_ACC0, o16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) xs_at(ce + i) += o16[i] + lp[3][ce + i];
+          }
+          worker_sync16();
+        } else {
+          commit_params();
+        }
+        load_x(v);
+        ln32(v, lp[4], lp[5]);
+        write_A(T_A, v);
+        signal_ready();  // -> W1
+        wait_gemm();
+        load_acc(T_ACC0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + lp[6][cq + i], 0.f);
+        write_A(T_A, v);
+        signal_ready();  // -> W2
+        wait_gemm();
+        {
+          float y[16];
+          load_acc16(T_ACC0, y);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) xs_at(ce + i) = valid ? xs_at(ce + i) + y[i] + lp[7][ce + i] : 0.f;
+        }
+        ++n_lp;
+      }
+      mark();
+
+      // ---- agent_temporal: 3-layer GRU -------------------------------------------------------------------------------------------
+#pragma unroll 1
+      for (int L = 0; L < 3; ++L) {
+        worker_sync16();
+        const float (*lp)[128] = sm.lp[n_lp & 1];
+        fetch_params(10 + L);
+        float4* hid = hid_t + (size_t)L * B * 32 * A + ag;
+        {
+          float x[32];
+          load_x(x);
+          write_A(T_A, x);
+          if (live) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 q = hid[(cq / 4 + i) * A];
+              x[4 * i] = q.x, x[4 * i + 1] = q.y, x[4 * i + 2] = q.z, x[4 * i + 3] = q.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = 0.f;
+          }
+          write_A(T_A2, x);
+        }
+        signal_ready();
+        commit_params();
+        wait_gemm();
+        {
+          float r[16], rh[16];
+          tc::tmem_ld16(tm + T_ACC0 + ce, r);
+          tc::tmem_ld16(tm + T_ACC1 + ce, rh);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float rg = fast_sigmoid(r[i] + lp[0][ce + i] + lp[3][ce + i]);
+            sm.xo[(ce + i) * MAXA + ag] = rg * (rh[i] + lp[5][ce + i]);
+          }
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.ready);
+        wait_gemm();
+        {
+          float z[16], n[16];
+          tc::tmem_ld16(tm + T_ACC0 + ce, z);
+          tc::tmem_ld16(tm + T_ACC1 + ce, n);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 hp4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) hp4 = hid[(ce / 4 + i) * A];
+            const float hp_[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
+            float hn_[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = ce + 4 * i + e;
+              const float zg = fast_sigmoid(z[4 * i + e] + lp[1][c] + lp[4][c]);
+              const float ng = fast_tanh(n[4 * i + e] + lp[2][c] + sm.xo[c * MAXA + ag]);
+              hn_[e] = (1.0f - zg) * ng + zg * hp_[e];
+            }
+            if (live) hid[(ce / 4 + i) * A] = valid ? make_float4(hn_[0], hn_[1], hn_[2], hn_[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) xs_at(ce + 4 * i + e) = (L == 2 && !valid) ? 0.f : hn_[e];
+          }
+        }
+        ++n_lp;
+      }
+      mark();
+
+      // ---- add_goal, add_latent ----------------------------------------------------------------------------------------------------
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j) {
+        worker_sync16();
+        const float (*lp)[128] = sm.lp[n_lp & 1];
+        fetch_params(13 + j);
+        const bool zv = j == 0 ? (sm.goal_valid[ag] != 0) : valid;
+        const float4* zin = (j == 0 ? goal_in_t : latent_in_t) + (cq / 4) * A + ag;
+        {
+          float z[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live && zv) q = __ldg(zin + i * A);
+            z[4 * i] = fmaxf(q.x, 0.f), z[4 * i + 1] = fmaxf(q.y, 0.f), z[4 * i + 2] = fmaxf(q.z, 0.f), z[4 * i + 3] = fmaxf(q.w, 0.f);
+          }
+          write_A(T_A2, z);
+          load_x(z);
+          write_A(T_A, z);
+        }
+        signal_ready();
+        commit_params();
+        wait_gemm();
+        {
+          float h1[32];
+          load_acc(T_ACC0, h1);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) h1[i] = fmaxf(h1[i] + lp[0][cq + i], 0.f);
+          write_A(T_A, h1);
+        }
+        signal_ready();
+        wait_gemm();
+        {
+          float h2[16];
+          load_acc16(T_ACC0, h2);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float hz = fmaxf(h2[i] + lp[1][ce + i], 0.f);
+            xs_at(ce + i) = valid ? (zv ? hz : 0.f) + xs_at(ce + i) : 0.f;
+          }
+        }
+        ++n_lp;
+      }
+      // ---- action head ----------------------------------------------------------------------------------------------------------------
+      const bool tail_thread = part == 0 && upper == 0 && live;
+      const bool out_w = rank == 0;
+      const bool has_gt = t < Tg;
+      const size_t gidx = ((size_t)s * Tg + (has_gt ? t : 0)) * A + ag;
+      float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
+      float2 g_vel = make_float2(0.f, 0.f);
+      float g_acc = 0.f, g_yr = 0.f;
+      bool ovr = false, gt_valid = false;
+      {
+        worker_sync16();
+        const float (*lp)[128] = sm.lp[n_lp & 1];
+        fetch_params(0);
+        {
+          float x[32];
+          load_x(x);
+          write_A(T_A, x);
+          if (a.out.trace_policy_feature && writer) {
+            float* dst = a.out.trace_policy_feature + ((ba * T) + (t - 1)) * D + cq;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+          }
+        }
+        signal_ready();
+        if (tail_thread && has_gt) {
+          ovr = in.tf_mask[gidx] != 0;
+          gt_valid = in.gt_valid[gidx] != 0;
+          gs = make_float4(in.gt_pos[gidx * 2], in.gt_pos[gidx * 2 + 1], in.gt_yaw[gidx], in.gt_spd[gidx]);
+          g_vel = make_float2(in.gt_vel[gidx * 2], in.gt_vel[gidx * 2 + 1]);
+          g_acc = in.gt_acc[gidx];
+          g_yr = in.gt_yaw_rate[gidx];
+        }
+        commit_params();
+        wait_gemm();
+        {
+          float m0 = 0.f, m1 = 0.f;
+#pragma unroll 1
+          for (int c3 = 0; c3 < 3; ++c3) {
+            float hdn[16];
+            tc::tmem_ld16(tm + 128 * c3 + ce, hdn);
+            tc::tmem_ld_wait();
+            const bool on = sm.type[ag][c3] && valid;
+            const float* w2 = &lp[3 + 2 * c3][0];
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float hv = fmaxf(hdn[i] + lp[c3][ce + i], 0.f);
+              const int k = ce + i;
+              s0 = fmaf(hv, w2[((k >> 2) * 2 + 0) * 4 + (k & 3)], s0);
+              s1 = fmaf(hv, w2[((k >> 2) * 2 + 1) * 4 + (k & 3)], s1);
+            }
+            if (on) {
+              m0 += s0;
+              m1 += s1;
+            }
+          }
+          sm.mean_part[2 * part + upper][ag][0] = m0;
+          sm.mean_part[2 * part + upper][ag][1] = m1;
+        }
+        ++n_lp;
+        worker_sync16();
+      }
+      mark();
+
+      // ---- per-agent tail ------------------------------------------------------------------------------------------------------------
+      if (tail_thread) {
+        float mean0 = 0.f, mean1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          mean0 += sm.mean_part[k][ag][0];
+          mean1 += sm.mean_part[k][ag][1];
+        }
+        if (valid) {
+          mean0 += sm.tailc[0][ag];
+          mean1 += sm.tailc[1][ag];
+        }
+        const bool ty0 = sm.type[ag][0], ty1 = sm.type[ag][1], ty2 = sm.type[ag][2];
+        const bool k_has_type = ty0 || ty1 || ty2;
+        const float k_max_acc = (ty0 ? 5.0f : 0.f) + (ty1 ? 7.0f : 0.f) + (ty2 ? 6.0f : 0.f);
+        const float k_max_yr = (ty0 ? 1.5f : 0.f) + (ty1 ? 7.0f : 0.f) + (ty2 ? 3.0f : 0.f);
+        const float a_acc = valid ? tanhf(mean0) * k_max_acc : 0.f;
+        const float a_yr = valid ? tanhf(mean1) * k_max_yr : 0.f;
+        const float4 st = sm.pose[ag];
+        const float v_t = st.w + 0.05f * a_acc, th_t = st.z + 0.05f * a_yr;
+        float4 pred = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && k_has_type) {
+          pred.x = st.x + 0.1f * (v_t * cosf(th_t));
+          pred.y = st.y + 0.1f * (v_t * sinf(th_t));
+          pred.z = st.z + 0.1f * a_yr;
+          pred.w = st.w + 0.1f * a_acc;
+        }
+        const size_t o = ba * T + (t - 1);
+        if (out_w) {
+          *reinterpret_cast<float4*>(a.out.preds + o * 4) = pred;
+          a.out.valid[o] = valid;
+          a.out.action_log_probs[o] = valid ? sm.tailc[2][ag] : 0.f;
+          a.out.latent_log_probs[o] = sm.tailc[3][ag];
+          if (a.out.trace_action_mean) {
+            a.out.trace_action_mean[o * 2] = mean0;
+            a.out.trace_action_mean[o * 2 + 1] = mean1;
+          }
+        }
+        bool killed = sm.killed[ag] != 0;
+        const bool m = ovr && !killed;
+        bool nvalid = valid || m;
+        float4 ns = pred;
+        if (m) {
+          ns = gs;
+          sm.vel[ag] = g_vel;
+          sm.acc[ag] = g_acc;
+          sm.yaw_rate[ag] = g_yr;
+        }
+        if (out_w) a.out.override_masks[o] = ovr;
+        const bool out_t = nvalid && (ns.x > sm.map_boundary[1] || ns.x < sm.map_boundary[0] || ns.y > sm.map_boundary[3] || ns.y < sm.map_boundary[2]);
+        bool outside = sm.sticky[0][ag] != 0, goal_r = sm.sticky[1][ag] != 0, dest_r = sm.sticky[2][ag] != 0;
+        outside |= out_t;
+        bool goal_t = false;
+        if (in.goal_gt) {
+          const float dx = ns.x - sm.tailc[4][ag], dy = ns.y - sm.tailc[5][ag];
+          const bool pos_ok = sqrtf(dx * dx + dy * dy) < sm.tailc[7][ag];
+          const float PI_F = 3.14159265358979323846f, TWO_PI_F = 6.28318530717958647692f;
+          float w = fmodf(ns.z - sm.tailc[6][ag] + PI_F, TWO_PI_F);
+          if (w < 0.f) w += TWO_PI_F;
+          const bool rot_ok = fabsf(w - PI_F) < 0.26179938779914943654f;
+          goal_t = pos_ok && rot_ok && nvalid && !goal_r;
+        }
+        goal_r |= goal_t;
+        bool pos_reached = false, rot_reached = false;
+        const float k_dest_thresh = sm.tailc[8][ag];
+        const bool k_lane_t = (sm.tflag[ag] & 1) != 0, k_edge_t = (sm.tflag[ag] & 2) != 0;
+        const float hx = cosf(ns.z), hy = sinf(ns.z);
+        const float4* dn = a.sv.dest_nodes + (size_t)b * TB_PL_NODE * A + ag;
+#pragma unroll
+        for (int n0 = 0; n0 < TB_PL_NODE; n0 += 10) {
+          float4 nd[10];
+#pragma unroll
+          for (int n = 0; n < 10; ++n) nd[n] = __ldg(dn + (n0 + n) * A);
+#pragma unroll
+          for (int n = 0; n < 10; ++n) {
+            const float dx = ns.x - nd[n].x, dy = ns.y - nd[n].y;
+            pos_reached |= sqrtf(dx * dx + dy * dy) < k_dest_thresh;
+            rot_reached |= (hx * nd[n].z + hy * nd[n].w) > 0.86602540378443864676f;
+          }
+        }
+        const bool dest_t = !dest_r && nvalid && ((k_lane_t && pos_reached && rot_reached) || (k_edge_t && pos_reached));
+        dest_r |= dest_t;
+        if (out_w) {
+          const size_t vs = BA * T;
+          a.out.violations[0 * vs + o] = outside;
+          a.out.violations[1 * vs + o] = out_t;
+          a.out.violations[2 * vs + o] = goal_r;
+          a.out.violations[3 * vs + o] = goal_t;
+          a.out.violations[4 * vs + o] = dest_r;
+          a.out.violations[5 * vs + o] = dest_t;
+        }
+        const bool kill = out_t && !gt_valid;
+        killed |= kill;
+        nvalid = nvalid && !kill;
+        const bool gv = sm.goal_valid[ag] && nvalid && !dest_r;
+        float reward = 0.f;
+        bool rv = valid;
+        if (has_gt) {
+          rv = valid && gt_valid;
+          if (rv) {
+            const float e_pos = smooth_l1(gs.x - pred.x) + smooth_l1(gs.y - pred.y);
+            const float e_rot = 0.5f * (1.0f - cosf(gs.z - pred.z));
+            const float e_spd = smooth_l1(gs.w - pred.w);
+            reward = 0.0f - (0.1f * e_pos + 10.0f * e_rot + 0.1f * e_spd);
+          }
+        }
+        if (out_w) {
+          a.out.diffbar_rewards[o] = reward;
+          a.out.diffbar_rewards_valid[o] = rv;
+        }
+        sm.pose[ag] = ns;
+        sm.valid[ag] = nvalid;
+        sm.killed[ag] = killed;
+        sm.goal_valid[ag] = gv;
+        sm.sticky[0][ag] = outside;
+        sm.sticky[1][ag] = goal_r;
+        sm.sticky[2][ag] = dest_r;
+      }
+      worker_sync16();
+    }
+    mark();
+    worker_sync16();
+    if (rank == 0) {
+      for (int L = 0; L < 3; ++L) {
+        float4* dst = reinterpret_cast<float4*>(a.sv.hidden + ((size_t)L * BA + (size_t)b * A) * D);
+        const float4* src = hid_t + (size_t)L * B * 32 * A;
+        for (int i = tid; i < A * 32; i += WORKERS16) {
+          const int ag_ = i / 32, c4 = i % 32;
+          dst[ag_ * 32 + c4] = __ldcg(src + c4 * A + ag_);
+        }
+      }
+    }
+    if (part == 0 && writer) {
+      *reinterpret_cast<float4*>(a.sv.agent_state + ba * 4) = sm.pose[ag];
+      a.sv.vel[ba * 2] = sm.vel[ag].x;
+      a.sv.vel[ba * 2 + 1] = sm.vel[ag].y;
+      a.sv.acc[ba] = sm.acc[ag];
+      a.sv.yaw_rate[ba] = sm.yaw_rate[ag];
+      a.sv.valid[(size_t)((a.t_last + 1) & 1) * BA + ba] = sm.valid[ag];
+      a.sv.killed[ba] = sm.killed[ag];
+      a.sv.goal_valid[ba] = sm.goal_valid[ag];
+      for (int i = 0; i < 3; ++i) a.sv.sticky[(size_t)i * BA + ba] = sm.sticky[i][ag];
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(sm.tmem_base, 512);
+  cluster_sync_all();
+}
+
 }  // namespace pr
 }  // namespace tb
 
@@ -1528,10 +2477,18 @@ int tb::launch_rollout_tc(const TbDims& d, const TbRolloutIn& in, const float* p
   }
   pr::Args a{d, in, packed, tc_blob(packed), sv, out, t_first, t_last, g_debug_trace};
   const int n_cta = rollout_tc_cluster_size(d);
+  const char* w8 = getenv("TB_ROLLOUT_8WARP");  // A/B: the 8-worker-warp kernel
+  const bool use16 = !(w8 && w8[0] == '1');
+  static bool attr16_set = false;
+  const int smem16 = (int)sizeof(pr::Smem16) + 1024;
+  if (use16 && !attr16_set) {
+    if (cudaFuncSetAttribute(pr::k_rollout_tc16, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16) != cudaSuccess) return TB_ERR_LAUNCH;
+    attr16_set = true;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(d.n_scene * d.n_mode * n_cta);
-  cfg.blockDim = dim3(pr::THREADS);
-  cfg.dynamicSmemBytes = smem;
+  cfg.blockDim = dim3(use16 ? pr::THREADS16 : pr::THREADS);
+  cfg.dynamicSmemBytes = use16 ? smem16 : smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1540,7 +2497,7 @@ int tb::launch_rollout_tc(const TbDims& d, const TbRolloutIn& in, const float* p
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, pr::k_rollout_tc, a) != cudaSuccess) return TB_ERR_LAUNCH;
+  if ((use16 ? cudaLaunchKernelEx(&cfg, pr::k_rollout_tc16, a) : cudaLaunchKernelEx(&cfg, pr::k_rollout_tc, a)) != cudaSuccess) return TB_ERR_LAUNCH;
   count_launch();
   return launch_status();
 }
