@@ -254,3 +254,27 @@ def test_rollout_two_kernel_path_agrees(monkeypatch):
     feat = eng.encode_scene(_cuda(batch))
     out, ref = _run_jfp(eng, sd, batch, meta, feat)
     _compare_rollout(out, ref, meta["S"], meta["K"])
+
+
+def test_rollout_8_worker_warp_kernel_agrees(monkeypatch):
+    """`TB_ROLLOUT_8WARP=1` selects the first persistent decode kernel (8 worker warps, two threads per TMEM lane)."""
+    from golden_util import load_case
+    monkeypatch.setenv("TB_ROLLOUT_8WARP", "1")
+    gold, sd, batch, meta = load_case("s1_a64_p1024_k1")
+    eng = _engine(sd)
+    feat = eng.encode_scene(_cuda(batch))
+    out, ref = _run_jfp(eng, sd, batch, meta, feat)
+    _compare_rollout(out, ref, meta["S"], meta["K"])
+
+
+def test_encode_scene_polyline_v1_agrees(monkeypatch):
+    """`TB_POLYLINE_V1=1` selects the first tensor-core polyline encoder (one thread per node row)."""
+    import trafficbots_oracle as orc
+    from golden_util import load_case
+    monkeypatch.setenv("TB_POLYLINE_V1", "1")
+    gold, sd, batch, meta = load_case("s3_a8_p64_k2")
+    eng = _engine(sd)
+    feat = eng.encode_scene(_cuda(batch))
+    ref = orc.encode_scene(sd, batch)
+    assert torch.equal(feat["map_feature_valid"].cpu(), ref["map_feature_valid"])
+    assert _maxdiff(feat["map_feature"], ref["map_feature"]) <= 1e-4
