@@ -424,6 +424,8 @@ extern "C" int32_t tb_kv_project(int32_t block, int32_t layer, const float* tgt,
   if (!tgt || !packed || !kv) return TB_ERR_NULL;
   if (block_base(block) < 0 || layer < 0 || layer >= block_layers(block) || n_row < 1) return TB_ERR_BAD_SHAPE;
   if (!aligned16(tgt) || !aligned16(packed) || !aligned16(kv)) return TB_ERR_ALIGN;
+  if (tc_enabled() && n_row >= 128)  // tensor-core kernel for everything but tiny inputs
+    return launch_kv_project_tc(block, layer, tgt, n_row, packed, kv, (cudaStream_t)stream);
   return launch_kv_project<ROW_TILE>(tgt, n_row, packed + block_base(block) + layer * tfl::STRIDE, kv, (cudaStream_t)stream);
 }
 

@@ -58,6 +58,7 @@ int launch_xlayer_tc(int block, int layer, const float* src, const uint8_t* src_
                      const unsigned char* blocks, const int32_t* n_key, int n_key_max, int kv_share, const float* packed, float* dst,
                      cudaStream_t st);
 
+int launch_kv_project_tc(int block, int layer, const float* tgt, long n_row, const float* packed, float* kv, cudaStream_t st);
 int launch_dest_pairs_tc(const float* U, const float* V, int n_scene, int n_agent, int n_pl, const float* packed, float* logits,
                          cudaStream_t st);
 

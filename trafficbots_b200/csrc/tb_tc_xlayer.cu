@@ -642,3 +642,168 @@ int tb::launch_dest_pairs_tc(const float* U, const float* V, int n_scene, int n_
   count_launch();
   return launch_status();
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// K|V projection on the tensor pipe: kv[row] = LN_tgt(tgt[row]) W_kv^T + b_kv  (transformer.py:192 + attention.py:86).
+// Persistent CTAs of 512 threads (4 threads per row, 128-row tiles); the two 128x128 weight blocks (Wk, Wv) stay resident in
+// shared memory; A operand in tensor memory, two accumulators.
+// ------------------------------------------------------------------------------------------------------------
+namespace tb {
+namespace kvp {
+
+constexpr int THREADS = 512;
+constexpr uint32_t T_K = 0, T_V = 128, T_A = 256;
+struct Smem {
+  unsigned char w[2][tc::BLOCK_BYTES];
+  float2 red[2][4][128];
+  float lp[4][128];  // norm_tgt weight, bias, K bias, V bias
+  uint64_t bar_w, bar_mma;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) k_kv_project_tc(const float* __restrict__ tgt, long n_row, const float* __restrict__ lw,
+                                                              const unsigned char* __restrict__ wkv_blocks, float* __restrict__ kv) {
+  extern __shared__ unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tc::uniform(tid >> 5), lane = tid & 31;
+  const int quad = warp & 3, part = warp >> 2, r = quad * 32 + lane, cq = 32 * part;
+  const long n_tile = (n_row + 127) / 128;
+  if (tid == 0) {
+    tc::mbar_init(&sm.bar_w, 1);
+    tc::mbar_init(&sm.bar_mma, 1);
+    tc::fence_mbar_init();
+    tc::mbar_expect_tx(&sm.bar_w, 2 * tc::BLOCK_BYTES);
+    tc::bulk_g2s(sm.w[0], wkv_blocks, tc::BLOCK_BYTES, &sm.bar_w);                    // Wk = block 1 of in_proj
+    tc::bulk_g2s(sm.w[1], wkv_blocks + tc::BLOCK_BYTES, tc::BLOCK_BYTES, &sm.bar_w);  // Wv = block 2
+  }
+  if (warp == 0) tc::tmem_alloc(&sm.tmem_base, 512);
+  {
+    const int off[4] = {tfl::NORMT_W, tfl::NORMT_B, tfl::IN_B + 128, tfl::IN_B + 256};
+    sm.lp[tid >> 7][tid & 127] = __ldg(lw + off[tid >> 7] + (tid & 127));
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tm0 = (uint32_t)tc::uniform((int)sm.tmem_base);
+  const uint32_t tm = tm0 + ((uint32_t)(quad * 32) << 16);
+  const uint32_t idesc = tc::make_idesc_bf16(128, 128);
+  uint32_t n_mma = 0, n_ln = 0;
+  bool w_ready = false;
+  for (long tile = blockIdx.x; tile < n_tile; tile += gridDim.x) {
+    const long row = tile * 128 + r;
+    const bool live = row < n_row;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) q = __ldg(reinterpret_cast<const float4*>(tgt + row * D + cq) + i);
+      v[4 * i] = q.x, v[4 * i + 1] = q.y, v[4 * i + 2] = q.z, v[4 * i + 3] = q.w;
+    }
+    {  // LayerNorm over the row held by 4 threads
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 32; ++i) s4[i & 3] += v[i];
+      const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      const float mloc = sum * (1.0f / 32);
+      float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float d = v[i] - mloc;
+        q[i & 3] = fmaf(d, d, q[i & 3]);
+      }
+      const int buf = n_ln & 1;
+      ++n_ln;
+      sm.red[buf][part][r] = make_float2(sum, (q[0] + q[1]) + (q[2] + q[3]));
+      __syncthreads();
+      const float2 p0 = sm.red[buf][0][r], p1 = sm.red[buf][1][r], p2 = sm.red[buf][2][r], p3 = sm.red[buf][3][r];
+      const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.0f / 128);
+      const float d0 = p0.x * (1.0f / 32) - mean, d1 = p1.x * (1.0f / 32) - mean, d2 = p2.x * (1.0f / 32) - mean, d3 = p3.x * (1.0f / 32) - mean;
+      const float m2 = ((p0.y + p1.y) + (p2.y + p3.y)) + 32.0f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+      const float rstd = 1.0f / sqrtf(m2 * (1.0f / 128) + LN_EPS);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd * sm.lp[0][cq + i] + sm.lp[1][cq + i];
+    }
+    {
+      float ph[16], pl[16];
+      tc::split32_packed(v, ph, pl);
+      tc::tmem_st16(tm + T_A + cq / 2, ph);
+      tc::tmem_st16(tm + T_A + 64 + cq / 2, pl);
+    }
+    tc::tmem_st_wait();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc::tc_fence_after();
+      if (!w_ready) tc::mbar_wait(&sm.bar_w, 0);
+      tc::tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t wh = tc::smem_u32(sm.w[j]);
+        const uint64_t dh = tc::make_desc_sw128(wh), dl = tc::make_desc_sw128(wh + 2 * tc::KB_BYTES_128);
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {
+            const uint32_t ta = tm0 + T_A + (term == 1 ? 64 : 0);
+            const uint64_t db = term == 2 ? dl : dh;
+#pragma unroll
+            for (int k = 0; k < 128; k += 16)
+              tc::mma_bf16_ts(tm0 + (j ? T_V : T_K), ta + k / 2, db + (uint64_t)(((k >> 6) * tc::KB_BYTES_128 + (k & 63) * 2) >> 4), idesc,
+                              (term > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+      }
+      if (tc::elect_one()) tc::mma_commit(&sm.bar_mma);
+      __syncwarp();
+    }
+    w_ready = true;
+    tc::mbar_wait(&sm.bar_mma, n_mma & 1);
+    ++n_mma;
+    tc::tc_fence_after();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      tc::tmem_ld32(tm + (j ? T_V : T_K) + cq, v);
+      tc::tmem_ld_wait();
+      if (live) {
+        float* dst = kv + row * 256 + 128 * j + cq;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i] + sm.lp[2 + j][cq + 4 * i], v[4 * i + 1] + sm.lp[2 + j][cq + 4 * i + 1],
+                                                          v[4 * i + 2] + sm.lp[2 + j][cq + 4 * i + 2], v[4 * i + 3] + sm.lp[2 + j][cq + 4 * i + 3]);
+      }
+    }
+    tc::tc_fence_before();  // the accumulators and the A operand are rewritten by the next tile
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(sm.tmem_base, 512);
+}
+
+}  // namespace kvp
+}  // namespace tb
+
+static int tc_in_proj_first_block(int block, int layer) {
+  switch (block) {
+    case TB_BLOCK_MAP_DENSETNT: return tbb::model_map_encoder_transformer_densetnt_layers_0_attn_in_proj_weight + 6 * layer;
+    case TB_BLOCK_LATENT_PRIOR_INT: return tbb::model_latent_encoder_agent_interaction_prior_transformer_layers_0_attn_in_proj_weight + 6 * layer;
+    case TB_BLOCK_LATENT_POST_INT: return tbb::model_latent_encoder_agent_interaction_post_transformer_layers_0_attn_in_proj_weight + 6 * layer;
+    default: return tc_layer_first_block(block, layer);
+  }
+}
+
+int tb::launch_kv_project_tc(int block, int layer, const float* tgt, long n_row, const float* packed, float* kv, cudaStream_t st) {
+  const int first = tc_in_proj_first_block(block, layer);
+  if (first < 0) return TB_ERR_UNSUPPORTED;
+  static bool attr_set = false;
+  const int smem = (int)sizeof(kvp::Smem) + 1024;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kvp::k_kv_project_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return TB_ERR_LAUNCH;
+    attr_set = true;
+  }
+  const long n_tile = (n_row + 127) / 128;
+  const int grid = (int)(n_tile < 148 ? n_tile : 148);
+  kvp::k_kv_project_tc<<<grid, kvp::THREADS, smem, st>>>(tgt, n_row, packed + block_base(block) + layer * tfl::STRIDE,
+                                                        tc_blob(packed) + (size_t)(first + 1) * tc::BLOCK_BYTES, kv);
+  count_launch();
+  return launch_status();
+}
