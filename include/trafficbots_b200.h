@@ -267,9 +267,12 @@ typedef enum tb_gru {
  *   mode 0: `TemporalAggregate` max_valid (agent_temporal.py:31-32,43-44)            -> latent encoder (latent_encoder.py:131-137)
  *   mode 1: last valid frame of (GRU output + input)  (goal_manager.py:298-300, last_valid)  -> destination predictor
  * x [n_batch, n_frame, n_agent, 128], valid [n_batch, n_frame, n_agent]; every t_stride-th frame is used.
- * out [n_batch, n_agent, 128], out_valid [n_batch, n_agent] = valid.any(frames). */
+ * out [n_batch, n_agent, 128], out_valid [n_batch, n_agent] = valid.any(frames).
+ * workspace: tb_gru_workspace_bytes (hidden state of the tensor-core kernel), or NULL for the fp32 row-tile kernel. */
+size_t tb_gru_workspace_bytes(int32_t n_batch, int32_t n_agent);
 int32_t tb_gru_sequence(int32_t which, int32_t mode, const float* x, const uint8_t* valid, int32_t n_batch, int32_t n_frame,
-                        int32_t n_agent, int32_t t_stride, const float* packed, float* out, uint8_t* out_valid, void* stream);
+                        int32_t n_agent, int32_t t_stride, const float* packed, void* workspace, float* out, uint8_t* out_valid,
+                        void* stream);
 
 typedef enum tb_mlp {
   TB_MLP_LATENT_PRIOR_MEAN = 0, /* model.latent_encoder.latent_prior_dist.mlp_mean : 128 -> 128 -> 16 */

@@ -40,7 +40,7 @@ EXPORTS = (
     "tb_pack_weights", "tb_encode_workspace_bytes", "tb_encode_scene", "tb_kv_project", "tb_xlayer",
     "tb_rollout_state_bytes", "tb_rollout_state_offset", "tb_rollout_init", "tb_rollout_steps", "tb_step_front", "tb_step_back", "tb_rollout",
     "tb_launch_count", "tb_kv_tc_bytes", "tb_tc_block_count", "tb_tc_first_block", "tb_tc_selftest",
-    "tb_gru_sequence", "tb_mlp_head", "tb_dest_workspace_bytes", "tb_dest_logits", "tb_xlayer_tc",
+    "tb_gru_sequence", "tb_gru_workspace_bytes", "tb_mlp_head", "tb_dest_workspace_bytes", "tb_dest_logits", "tb_xlayer_tc",
 )
 
 
@@ -168,7 +168,9 @@ def lib() -> C.CDLL:
                                C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.tb_gru_sequence.restype = C.c_int32
     L.tb_gru_sequence.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.tb_gru_workspace_bytes.restype = C.c_size_t
+    L.tb_gru_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
     L.tb_mlp_head.restype = C.c_int32
     L.tb_mlp_head.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.tb_dest_workspace_bytes.restype = C.c_size_t

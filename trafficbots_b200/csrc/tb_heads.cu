@@ -251,13 +251,22 @@ static int gru_base(int which) {
   return -1;
 }
 
+extern "C" size_t tb_gru_workspace_bytes(int32_t n_batch, int32_t n_agent) {
+  if (n_batch < 1 || n_agent < 1) return 0;
+  const size_t n_cta = ((size_t)n_batch * n_agent + 127) / 128;
+  return n_cta * 3 * 128 * 128 * sizeof(float);  // hidden state of the 3 layers, 128 rows per CTA
+}
+
 extern "C" int32_t tb_gru_sequence(int32_t which, int32_t mode, const float* x, const uint8_t* valid, int32_t n_batch,
-                                   int32_t n_frame, int32_t n_agent, int32_t t_stride, const float* packed, float* out,
-                                   uint8_t* out_valid, void* stream) {
+                                   int32_t n_frame, int32_t n_agent, int32_t t_stride, const float* packed, void* workspace,
+                                   float* out, uint8_t* out_valid, void* stream) {
   if (!x || !valid || !packed || !out || !out_valid) return TB_ERR_NULL;
   if (gru_base(which) < 0 || (mode != 0 && mode != 1) || n_batch < 1 || n_batch > 65535 || n_frame < 1 || n_agent < 1 || t_stride < 1)
     return TB_ERR_BAD_SHAPE;
-  if (!aligned16(x) || !aligned16(packed) || !aligned16(out)) return TB_ERR_ALIGN;
+  if (!aligned16(x) || !aligned16(packed) || !aligned16(out) || (workspace && !aligned16(workspace))) return TB_ERR_ALIGN;
+  if (workspace && tc_enabled())  // tensor-core kernel (tb_tc_xlayer.cu); without a workspace: the fp32 row-tile kernel
+    return launch_gru_seq_tc(which, mode, x, valid, n_batch, n_frame, n_agent, t_stride, packed, gru_base(which), workspace, out,
+                             out_valid, (cudaStream_t)stream);
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_gru_seq<HR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GruSmem));

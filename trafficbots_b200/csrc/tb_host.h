@@ -59,6 +59,8 @@ int launch_xlayer_tc(int block, int layer, const float* src, const uint8_t* src_
                      cudaStream_t st);
 
 int launch_kv_project_tc(int block, int layer, const float* tgt, long n_row, const float* packed, float* kv, cudaStream_t st);
+int launch_gru_seq_tc(int which, int mode, const float* x, const uint8_t* valid, int n_batch, int n_frame, int n_agent, int t_stride,
+                      const float* packed, int gru_base_offset, void* workspace, float* out, uint8_t* out_valid, cudaStream_t st);
 int launch_dest_pairs_tc(const float* U, const float* V, int n_scene, int n_agent, int n_pl, const float* packed, float* logits,
                          cudaStream_t st);
 

@@ -807,3 +807,270 @@ int tb::launch_kv_project_tc(int block, int layer, const float* tgt, long n_row,
   count_launch();
   return launch_status();
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// 3-layer GRU over the frames of a sequence on the tensor pipe (MultiAgentGRULoop 3-D branch + temporal aggregation, see
+// tb_gru_sequence in the header).  A CTA owns 128 rows (flattened batch x agent) for the whole sequence; 512 threads, four
+// per row; x and h of a layer are two TMEM A operands; gates r and W_hn h in one MMA batch, z and W_in x in the next
+// (the same schedule as the decode kernel); the hidden state of the 3 layers lives in a global scratch in row-minor layout.
+// ------------------------------------------------------------------------------------------------------------
+namespace tb {
+namespace gq {
+
+constexpr int THREADS = 512;
+constexpr uint32_t T_ACC0 = 0, T_ACC1 = 128, T_A2 = 256, T_A = 384;
+struct Smem {
+  unsigned char w[2][tc::BLOCK_BYTES];
+  float agg[128 * 128];  // temporal aggregate, [col][row]
+  float lp[2][6][128];   // b_ih (r, z, n), b_hh (r, z, n) of the current layer
+  uint64_t bar_w[2], bar_free[2], bar_mma;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  return __fdividef(1.0f, 1.0f + e);
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_gru_seq_tc(const float* __restrict__ x, const uint8_t* __restrict__ valid, int T_all,
+                                                           int A, long n_rows, int t_stride, int n_t, const float* __restrict__ gw0,
+                                                           const unsigned char* __restrict__ tcw, int blk_ih0, int blk_hh0, int mode,
+                                                           float4* __restrict__ hscratch, float* __restrict__ out,
+                                                           uint8_t* __restrict__ out_valid) {
+  extern __shared__ unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tc::uniform(tid >> 5), lane = tid & 31;
+  const int quad = warp & 3, part = warp >> 2, r = quad * 32 + lane, cq = 32 * part;
+  const long row = (long)blockIdx.x * 128 + r;
+  const bool live = row < n_rows;
+  const long bb = live ? row / A : 0;
+  const int aa = live ? (int)(row % A) : 0;
+  if (tid == 0) {
+    tc::mbar_init(&sm.bar_w[0], 1);
+    tc::mbar_init(&sm.bar_w[1], 1);
+    tc::mbar_init(&sm.bar_free[0], 1);
+    tc::mbar_init(&sm.bar_free[1], 1);
+    tc::mbar_init(&sm.bar_mma, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&sm.tmem_base, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tm0 = (uint32_t)tc::uniform((int)sm.tmem_base);
+  const uint32_t tm = tm0 + ((uint32_t)(quad * 32) << 16);
+  const uint32_t idesc = tc::make_idesc_bf16(128, 128);
+  float4* hs = hscratch + (size_t)blockIdx.x * 3 * 32 * 128 + r;  // layer L, column quad c4: hs[(L * 32 + c4) * 128]
+
+  // weight stage s of the repeating 18-stage schedule (6 per layer): Wih_r, Whh_r, Whh_n | Wih_z, Whh_z, Wih_n
+  auto stage_block = [&](uint32_t s) -> int {
+    const int L = (s % 18) / 6, j = s % 6;
+    const int ih[6] = {1, 0, 0, 1, 0, 1}, gate[6] = {0, 0, 2, 1, 1, 2};
+    return (ih[j] ? blk_ih0 : blk_hh0) + 6 * L + gate[j];
+  };
+  // Weight ring (2 x 64 KB) driven by warp 0: stage j lives in slot j & 1.  A batch = 3 chains (stages s, s+1, s+2); the
+  // third reuses the slot of the first, so every chain's completion is tracked on its slot's bar_free and the refill is
+  // issued as soon as the slot is free.  All threads wait on bar_mma (committed after the last chain of a batch).
+  uint32_t s_next = 0, n_w[2] = {0, 0}, n_free[2] = {0, 0}, n_mma = 0;
+  auto load_stage = [&](uint32_t stage) {  // warp 0, converged
+    const uint32_t buf = stage & 1;
+    if (tc::elect_one()) {
+      tc::mbar_expect_tx(&sm.bar_w[buf], tc::BLOCK_BYTES);
+      tc::bulk_g2s(sm.w[buf], tcw + (size_t)stage_block(stage) * tc::BLOCK_BYTES, tc::BLOCK_BYTES, &sm.bar_w[buf]);
+    }
+    __syncwarp();
+  };
+  auto issue_chain = [&](uint32_t stage, uint32_t dst, uint32_t asel, bool accum, uint64_t* done_bar) {  // warp 0, converged
+    const uint32_t buf = stage & 1;
+    tc::mbar_wait(&sm.bar_w[buf], n_w[buf] & 1);
+    ++n_w[buf];
+    tc::tc_fence_after();
+    const uint32_t wh = tc::smem_u32(sm.w[buf]);
+    const uint64_t dh = tc::make_desc_sw128(wh), dl = tc::make_desc_sw128(wh + 2 * tc::KB_BYTES_128);
+    if (tc::elect_one()) {
+#pragma unroll
+      for (int term = 0; term < 3; ++term) {
+        const uint32_t ta = tm0 + asel + (term == 1 ? 64 : 0);
+        const uint64_t db = term == 2 ? dl : dh;
+#pragma unroll
+        for (int k = 0; k < 128; k += 16)
+          tc::mma_bf16_ts(tm0 + dst, ta + k / 2, db + (uint64_t)(((k >> 6) * tc::KB_BYTES_128 + (k & 63) * 2) >> 4), idesc,
+                          (accum || term > 0 || k > 0) ? 1u : 0u);
+      }
+      tc::mma_commit(done_bar);
+    }
+    __syncwarp();
+  };
+  auto wait_free = [&](uint32_t buf) {
+    tc::mbar_wait(&sm.bar_free[buf], n_free[buf] & 1);
+    ++n_free[buf];
+  };
+  // batch of 3 chains: (dst column, A operand column) x 3; the second accumulates onto the first
+  auto run_batch = [&](uint32_t d0, uint32_t a0, uint32_t d1, uint32_t a1, uint32_t d2, uint32_t a2) {
+    tc::tmem_st_wait();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc::tc_fence_after();
+      const uint32_t s0 = s_next, ba = s0 & 1, bb2 = ba ^ 1;
+      issue_chain(s0, d0, a0, false, &sm.bar_free[ba]);
+      issue_chain(s0 + 1, d1, a1, true, &sm.bar_free[bb2]);
+      wait_free(ba);
+      load_stage(s0 + 2);
+      issue_chain(s0 + 2, d2, a2, false, &sm.bar_mma);
+      wait_free(bb2);
+      load_stage(s0 + 3);
+    }
+    tc::mbar_wait(&sm.bar_mma, n_mma & 1);
+    ++n_mma;
+    tc::tc_fence_after();
+    if (warp == 0) load_stage(s_next + 4);  // slot of the batch's first / third chain is free again
+    s_next += 3;
+  };
+  auto write_A = [&](uint32_t col, const float (&v)[32]) {
+    float ph[16], pl[16];
+    tc::split32_packed(v, ph, pl);
+    tc::tmem_st16(tm + col + cq / 2, ph);
+    tc::tmem_st16(tm + col + 64 + cq / 2, pl);
+  };
+  if (warp == 0) {
+    load_stage(0);
+    load_stage(1);
+  }
+  for (int i = tid; i < 128 * 128; i += THREADS) sm.agg[i] = mode == 0 ? -1e3f : 0.f;
+  bool any = false;
+  float xv[32];
+#pragma unroll 1
+  for (int it = 0; it < n_t; ++it) {
+    const int t = it * t_stride;
+    const bool v_t = live && valid[(bb * T_all + t) * A + aa] != 0;
+    const float* xrow = x + ((bb * T_all + t) * A + aa) * (long)D + cq;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) q = __ldg(reinterpret_cast<const float4*>(xrow) + i);
+      xv[4 * i] = q.x, xv[4 * i + 1] = q.y, xv[4 * i + 2] = q.z, xv[4 * i + 3] = q.w;
+    }
+#pragma unroll 1
+    for (int L = 0; L < 3; ++L) {
+      const float* gw = gw0 + L * gru::STRIDE;
+      float (*lp)[128] = sm.lp[L & 1];
+      if (tid < 384) {
+        lp[tid >> 7][tid & 127] = __ldg(gw + gru::B_IH + tid);        // b_ih r, z, n
+        lp[3 + (tid >> 7)][tid & 127] = __ldg(gw + gru::B_HH + tid);  // b_hh r, z, n
+      }
+      write_A(T_A, xv);
+      {
+        float hv[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (it > 0) q = hs[(L * 32 + cq / 4 + i) * 128];
+          hv[4 * i] = q.x, hv[4 * i + 1] = q.y, hv[4 * i + 2] = q.z, hv[4 * i + 3] = q.w;
+        }
+        write_A(T_A2, hv);
+      }
+      run_batch(T_ACC0, T_A, T_ACC0, T_A2, T_ACC1, T_A2);  // r (ACC0), W_hn h (ACC1)
+      float rh[32];
+      {
+        float rr[32];
+        tc::tmem_ld32(tm + T_ACC0 + cq, rr);
+        tc::tmem_ld32(tm + T_ACC1 + cq, rh);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rh[i] = fast_sigmoid(rr[i] + lp[0][cq + i] + lp[3][cq + i]) * (rh[i] + lp[5][cq + i]);
+      }
+      run_batch(T_ACC0, T_A, T_ACC0, T_A2, T_ACC1, T_A);  // z (ACC0), W_in x (ACC1)
+      {
+        float zz[32], nn[32];
+        tc::tmem_ld32(tm + T_ACC0 + cq, zz);
+        tc::tmem_ld32(tm + T_ACC1 + cq, nn);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          float4 hq = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (it > 0) hq = hs[(L * 32 + cq / 4 + i4) * 128];
+          const float hp_[4] = {hq.x, hq.y, hq.z, hq.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = 4 * i4 + e;
+            const float zg = fast_sigmoid(zz[i] + lp[1][cq + i] + lp[4][cq + i]);
+            const float ng = 2.0f * fast_sigmoid(2.0f * (nn[i] + lp[2][cq + i] + rh[i])) - 1.0f;
+            xv[i] = (1.0f - zg) * ng + zg * hp_[e];  // the next layer sees the unmasked output
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          hs[(L * 32 + cq / 4 + i) * 128] = v_t ? make_float4(xv[4 * i], xv[4 * i + 1], xv[4 * i + 2], xv[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    // output of the frame (zero where invalid) -> temporal aggregate
+    if (mode == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sm.agg[(cq + i) * 128 + r] = fmaxf(sm.agg[(cq + i) * 128 + r], v_t ? xv[i] : -1e3f);
+    } else if (v_t) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(xrow) + i);
+        sm.agg[(cq + 4 * i) * 128 + r] = xv[4 * i] + q.x;
+        sm.agg[(cq + 4 * i + 1) * 128 + r] = xv[4 * i + 1] + q.y;
+        sm.agg[(cq + 4 * i + 2) * 128 + r] = xv[4 * i + 2] + q.z;
+        sm.agg[(cq + 4 * i + 3) * 128 + r] = xv[4 * i + 3] + q.w;
+      }
+    }
+    any = any || v_t;
+  }
+  if (live) {
+    float* dst = out + row * D + cq;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 q = make_float4(sm.agg[(cq + 4 * i) * 128 + r], sm.agg[(cq + 4 * i + 1) * 128 + r], sm.agg[(cq + 4 * i + 2) * 128 + r],
+                             sm.agg[(cq + 4 * i + 3) * 128 + r]);
+      if (!any) q = make_float4(0.f, 0.f, 0.f, 0.f);
+      reinterpret_cast<float4*>(dst)[i] = q;
+    }
+    if (part == 0) out_valid[row] = any;
+  }
+  if (warp == 0) {  // the two prefetched stages beyond the last batch must land before the CTA exits
+    tc::mbar_wait(&sm.bar_w[0], n_w[0] & 1);
+    tc::mbar_wait(&sm.bar_w[1], n_w[1] & 1);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(sm.tmem_base, 512);
+}
+
+}  // namespace gq
+}  // namespace tb
+
+int tb::launch_gru_seq_tc(int which, int mode, const float* x, const uint8_t* valid, int n_batch, int n_frame, int n_agent, int t_stride,
+                          const float* packed, int gru_base_offset, void* workspace, float* out, uint8_t* out_valid, cudaStream_t st) {
+  int blk_ih0, blk_hh0;
+  switch (which) {
+    case TB_GRU_POLICY: blk_ih0 = tbb::model_agent_temporal_rnn_weight_ih_l0, blk_hh0 = tbb::model_agent_temporal_rnn_weight_hh_l0; break;
+    case TB_GRU_LATENT_PRIOR:
+      blk_ih0 = tbb::model_latent_encoder_agent_temporal_prior_rnn_weight_ih_l0, blk_hh0 = tbb::model_latent_encoder_agent_temporal_prior_rnn_weight_hh_l0;
+      break;
+    case TB_GRU_LATENT_POST:
+      blk_ih0 = tbb::model_latent_encoder_agent_temporal_post_rnn_weight_ih_l0, blk_hh0 = tbb::model_latent_encoder_agent_temporal_post_rnn_weight_hh_l0;
+      break;
+    case TB_GRU_DEST:
+      blk_ih0 = tbb::model_goal_manager_goal_predictor_gru_as_rnn_weight_ih_l0, blk_hh0 = tbb::model_goal_manager_goal_predictor_gru_as_rnn_weight_hh_l0;
+      break;
+    default: return TB_ERR_BAD_SHAPE;
+  }
+  static bool attr_set = false;
+  const int smem = (int)sizeof(gq::Smem) + 1024;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gq::k_gru_seq_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return TB_ERR_LAUNCH;
+    attr_set = true;
+  }
+  const long n_rows = (long)n_batch * n_agent;
+  const int n_t = (n_frame + t_stride - 1) / t_stride;
+  const int grid = (int)((n_rows + 127) / 128);
+  gq::k_gru_seq_tc<<<grid, gq::THREADS, smem, st>>>(x, valid, n_frame, n_agent, n_rows, t_stride, n_t, packed + gru_base_offset, tc_blob(packed),
+                                                   blk_ih0, blk_hh0, mode, reinterpret_cast<float4*>(workspace), out, out_valid);
+  count_launch();
+  return launch_status();
+}

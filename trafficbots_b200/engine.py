@@ -165,11 +165,12 @@ class Engine:
         B, T, A, _ = x.shape
         out = torch.empty(B, A, 128, device=self.device)
         ov = torch.empty(B, A, dtype=torch.bool, device=self.device)
+        ws = torch.empty(self.lib.tb_gru_workspace_bytes(B, A), dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
             nt.check(self.lib.tb_gru_sequence(which, mode, nt.dev_ptr(x, "f32", (B, T, A, 128), "x"),
                                               nt.dev_ptr(valid, "u8", (B, T, A), "valid"), B, T, A, t_stride,
-                                              self.packed.data_ptr(), out.data_ptr(), ov.data_ptr(), nt.current_stream_ptr()),
-                     "tb_gru_sequence")
+                                              self.packed.data_ptr(), ws.data_ptr(), out.data_ptr(), ov.data_ptr(),
+                                              nt.current_stream_ptr()), "tb_gru_sequence")
         return out, ov
 
     def latent_encoder(self, feat: Mapping[str, Tensor], posterior: bool = False, temporal_down_sample_rate: int = 5):
