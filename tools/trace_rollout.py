@@ -58,7 +58,7 @@ def main():
     print(f"  {'step':28s} {sum(tot) / steps:10.0f} cycles/step")
 
 
-    for name, base in (("group 0 leader (tid 0)", 1024), ("group 1 leader (tid 128)", 1024 + 1400)):
+    for name, base in (("group 0 leader (tid 0)", 1024), ("group 1 leader (tid 128 or 256)", 1024 + 1400)):
         d = full[base:base + 1400]
         pairs = [(d[2 * i], d[2 * i + 1]) for i in range(700) if d[2 * i]]
         print(f"detailed marks, {name}: id:+cycles since previous mark")

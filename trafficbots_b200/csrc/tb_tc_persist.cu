@@ -1649,6 +1649,18 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
     auto mark = [&]() {
       if (a.trace && blockIdx.x == 0 && tid == 0 && n_mark < 1000) a.trace[n_mark++] = clock64();
     };
+#ifdef TB_TRACE_DETAIL
+    int n_dmark = 0, t_cur = 0;
+    auto dmark = [&](int id) {
+      if (a.trace && blockIdx.x == 0 && (tid == 0 || tid == 256) && t_cur == a.t_first + 3 && n_dmark < 700) {
+        long long* dst = a.trace + 1024 + (tid == 256 ? 1400 : 0) + 2 * n_dmark++;
+        dst[0] = id;
+        dst[1] = clock64();
+      }
+    };
+#else
+    auto dmark = [](int) {};
+#endif
     auto signal_ready = [&]() {
       tc::tmem_st_wait();
       tc::tc_fence_before();
@@ -1751,6 +1763,9 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
     for (int t = a.t_first; t <= a.t_last; ++t) {
       const int tl_t = min(t - 1, Th - 1);
       const int nkey_tl = uniform(in.n_key_tl[(size_t)s * Th + tl_t]);
+#ifdef TB_TRACE_DETAIL
+      t_cur = t;
+#endif
       mark();
       const bool valid = sm.valid[ag] != 0;
       const unsigned vm_lo = __ballot_sync(0xffffffffu, sm.valid[lane] != 0);
@@ -1821,6 +1836,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
         const int nkey = kind == 0 ? nkey_map : kind == 1 ? nkey_tl : (n_valid > 0 ? MAXA : 0);
         const int nblk = (nkey + 63) / 64;
         worker_sync16();
+        dmark(100 + Lx * 10);
         const float (*lp)[128] = sm.lp[n_lp & 1];
         {
           int pn = Lx + 1;
@@ -1849,7 +1865,9 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
             ln32(v, lp[8], lp[9]);
             write_A(T_A, v);
             signal_ready();  // -> Wk (ACC0), Wv (ACC1)
+            dmark(500 + Lx);
             wait_gemm();
+            dmark(510 + Lx);
             tc::mbar_wait(&sm.grant, n_grant & 1);
             ++n_grant;
             {
@@ -1887,14 +1905,17 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.wfill);
+            dmark(540 + Lx);
           }
           load_x(v);
           ln32(v, lp[0], lp[1]);
           write_A(T_A, v);
           signal_ready();  // -> Wq
+          dmark(101 + Lx * 10);
           const bool split_layer = kind == 0 && n_cta > 1;
           if (!split_layer) commit_params();
           wait_gemm();
+          dmark(102 + Lx * 10);
           if ((part & 1) == upper) {  // this thread's 32 Q columns = head `part` = the head lane l needs in pass part / 2
             const int hp = part >> 1;
             float q[32];
@@ -1912,6 +1933,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
             tc::tmem_st16(tm + T_A + 64 + 32 * hp + 16 * (1 - upper), zz);
           }
           signal_ready();  // -> QK^T(0, .)
+          dmark(103 + Lx * 10);
           // ---- online softmax of pass `half`; this thread: keys 32 sub .. 32 sub + 31 of every block ---------------------------
           float m_ref = -INFINITY, l_sum = 0.f;
           const uint32_t sbase = tm + T_ACC0 + 64 * half;
@@ -1979,6 +2001,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.p[half]);
           }
+          dmark(104 + Lx * 10);
           {
             // total softmax denominator of the (lane, pass): the two threads' partial sums
             float* lxs = reinterpret_cast<float*>(&sm.red[0][0][0]);  // [4][128] (no LayerNorm in flight; separate from mxs)
@@ -2089,7 +2112,9 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
           }
           write_A(T_A, v);
           signal_ready();  // -> Wo
+          dmark(105 + Lx * 10);
           wait_gemm();
+          dmark(106 + Lx * 10);
           {
             float o16[16];
             load_acc16(T_ACC0, o16);
@@ -2104,13 +2129,17 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
         ln32(v, lp[4], lp[5]);
         write_A(T_A, v);
         signal_ready();  // -> W1
+        dmark(107 + Lx * 10);
         wait_gemm();
+        dmark(108 + Lx * 10);
         load_acc(T_ACC0, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + lp[6][cq + i], 0.f);
         write_A(T_A, v);
         signal_ready();  // -> W2
+        dmark(109 + Lx * 10);
         wait_gemm();
+        dmark(190 + Lx);
         {
           float y[16];
           load_acc16(T_ACC0, y);
@@ -2126,6 +2155,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
       for (int L = 0; L < 3; ++L) {
         worker_sync16();
         const float (*lp)[128] = sm.lp[n_lp & 1];
+        dmark(200 + L * 10);
         fetch_params(10 + L);
         float4* hid = hid_t + (size_t)L * B * 32 * A + ag;
         {
@@ -2145,8 +2175,10 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
           write_A(T_A2, x);
         }
         signal_ready();
+        dmark(201 + L * 10);
         commit_params();
         wait_gemm();
+        dmark(202 + L * 10);
         {
           float r[16], rh[16];
           tc::tmem_ld16(tm + T_ACC0 + ce, r);
@@ -2161,7 +2193,9 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.ready);
+        dmark(203 + L * 10);
         wait_gemm();
+        dmark(204 + L * 10);
         {
           float z[16], n[16];
           tc::tmem_ld16(tm + T_ACC0 + ce, z);
@@ -2296,6 +2330,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
       }
       mark();
 
+      dmark(400);
       // ---- per-agent tail ------------------------------------------------------------------------------------------------------------
       if (tail_thread) {
         float mean0 = 0.f, mean1 = 0.f;
@@ -2414,7 +2449,9 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
         sm.sticky[1][ag] = goal_r;
         sm.sticky[2][ag] = dest_r;
       }
+      dmark(401);
       worker_sync16();
+      dmark(402);
     }
     mark();
     worker_sync16();
