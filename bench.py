@@ -323,7 +323,7 @@ def run_ours(args):
         # CPU baseline: the oracle port on a bounded sample (about 10-30 s of CPU work)
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        n_cpu = 4
+        n_cpu = 32  # the whole batch of the GPU arm: ~10 s on 16 cores
         cpu_rate, cpu_s = cpu_reference_rate(n_cpu)
         line = {
             "metric": METRIC, "value": world * S * args.steps / (ms * 1e-3), "unit": "scenes/s", "n_gpus": world,

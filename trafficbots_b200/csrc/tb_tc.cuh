@@ -185,16 +185,17 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 // ---- bf16x3 operand split and swizzled tile stores -------------------------------------------------------------------------
 // 8 consecutive K elements of one row -> one 16-byte chunk of the hi tile and one of the lo tile
+// bf16x3 split of two floats: h = packed RN-bf16 (v0 low half, v1 high half), l = packed RN-bf16 of the residuals.  Raw
+// cvt / shift / mask (6 instructions per pair): the cuda_bf16.hpp struct accessors cost two extra PRMTs per conversion.
+__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& h, uint32_t& l) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(v1), "f"(v0));
+  const float r0 = v0 - __uint_as_float(h << 16), r1 = v1 - __uint_as_float(h & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(r1), "f"(r0));
+}
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    const float2 hf = __bfloat1622float2(hh);
-    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
-    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
-  }
+  for (int i = 0; i < 4; ++i) split_pair(v[2 * i], v[2 * i + 1], h[i], l[i]);
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
@@ -202,11 +203,10 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
 __device__ __forceinline__ void split32_packed(const float (&v)[32], float (&hi)[16], float (&lo)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    const float2 hf = __bfloat1622float2(hh);
-    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
-    hi[i] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&hh));
-    lo[i] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&ll));
+    uint32_t h, l;
+    split_pair(v[2 * i], v[2 * i + 1], h, l);
+    hi[i] = __uint_as_float(h);
+    lo[i] = __uint_as_float(l);
   }
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {

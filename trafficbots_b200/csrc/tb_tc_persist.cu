@@ -868,15 +868,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {
                 const float v0 = kk[i] + lp[11][cs + i], v1 = kk[i + 1] + lp[11][cs + i + 1];
-                const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
-                const float2 hf = __bfloat1622float2(hh);
-                const __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+                uint32_t hh, ll;
+                tc::split_pair(v0, v1, hh, ll);
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                   const int d = cs + i + e;
                   const uint32_t off = (uint32_t)((d >> 3) * 1024 + (d & 7) * 128) + ((kc ^ (uint32_t)(d & 7)) << 4);
-                  *reinterpret_cast<__nv_bfloat16*>(vt + off) = e ? hh.y : hh.x;
-                  *reinterpret_cast<__nv_bfloat16*>(vt + 16384 + off) = e ? ll.y : ll.x;
+                  *reinterpret_cast<unsigned short*>(vt + off) = (unsigned short)(e ? hh >> 16 : hh & 0xffffu);
+                  *reinterpret_cast<unsigned short*>(vt + 16384 + off) = (unsigned short)(e ? ll >> 16 : ll & 0xffffu);
                 }
               }
               tc::fence_proxy_async();
@@ -1890,15 +1889,14 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
 #pragma unroll
               for (int i = 0; i < 16; i += 2) {
                 const float v0 = kk[i] + lp[11][ce + i], v1 = kk[i + 1] + lp[11][ce + i + 1];
-                const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
-                const float2 hf = __bfloat1622float2(hh);
-                const __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+                uint32_t hh, ll;
+                tc::split_pair(v0, v1, hh, ll);
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                   const int d = ce + i + e;
                   const uint32_t off = (uint32_t)((d >> 3) * 1024 + (d & 7) * 128) + ((kc ^ (uint32_t)(d & 7)) << 4);
-                  *reinterpret_cast<__nv_bfloat16*>(vt + off) = e ? hh.y : hh.x;
-                  *reinterpret_cast<__nv_bfloat16*>(vt + 16384 + off) = e ? ll.y : ll.x;
+                  *reinterpret_cast<unsigned short*>(vt + off) = (unsigned short)(e ? hh >> 16 : hh & 0xffffu);
+                  *reinterpret_cast<unsigned short*>(vt + 16384 + off) = (unsigned short)(e ? ll >> 16 : ll & 0xffffu);
                 }
               }
               tc::fence_proxy_async();
