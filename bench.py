@@ -337,16 +337,17 @@ def run_ours(args):
             "e2e": {"value": world * S * args.steps / (ms_e2e * 1e-3), "unit": "scenes/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": 1e3 * wall_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "k_rollout_tc (persistent decode kernel: 90 steps x (embed, 9 attention layers, 3 GRU layers, "
-                                   "add_goal, add_latent, action head, dynamics/rule-check tail), one CTA per scene-mode)",
+            "roofline": {"kernel": "k_rollout_tc16 (persistent decode kernel: 90 steps x (embed, 9 attention layers, 3 GRU layers, "
+                                   "add_goal, add_latent, action head, dynamics/rule-check tail), one 4-CTA cluster per scene-mode)",
                          "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                         "traffic": 11.24e9 if (world == 1 and S == 32) else None,
-                         "traffic_note": "dram read 9.78 GB + write 1.46 GB per launch, ncu --set full (profiles/r1d_k_rollout_tc.txt): "
-                                         "the 100 MB of key blocks stream from HBM at every one of the 90 steps",
+                         "traffic": 11.66e9 if (world == 1 and S == 32) else None,
+                         "traffic_note": "dram read 10.14 GB + write 1.52 GB per launch, ncu --set full (profiles/r1k_k_rollout_tc16.txt: tensor pipe "
+                                         "active 30.6 %, issue active 32 %, L2 hit 67.5 %): the 88 MB of key blocks stream through L2 at every one "
+                                         "of the 90 steps; 550 GB/s = 7 % of HBM peak, the kernel is bound by its serial GEMM -> epilogue chain",
                          "peak_source": peak_src, "flops_per_launch": f_roll,
                          "avg_launch_ms": rollout_ms, "whole_step_tflops": f_total / (ms / args.steps * 1e-3) / 1e12,
                          "note": "algorithmic fp32-equivalent FLOPs (SURVEY 8d); the kernel issues 3 bf16 MMAs per logical "
-                                 "product (bf16x3) on M=128 tiles holding 64 agents, and runs on B of the 148 SMs"},
+                                 "product (bf16x3) on M=128 tiles holding 64 agents, on 4 x B = 128 of the 148 SMs"},
             "cpu_baseline": {"value": cpu_rate, "unit": "scenes/s", "cores": cores, "kind": "port",
                              "sample": f"{n_cpu} scenes of the same workload, 1 pass ({cpu_s:.1f} s), torch CPU fp32"},
             "clocks": clocks,

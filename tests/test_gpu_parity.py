@@ -172,6 +172,24 @@ def test_rollout_matches_oracle_and_golden(case):
     assert _maxdiff(out["hidden"], gold["jfp/hidden"]) <= TOL_CLOSED
 
 
+@pytest.mark.parametrize("S,A,P,K", [(1, 128, 2048, 1), (2, 100, 1500, 1), (2, 37, 300, 2)])
+def test_rollout_other_shapes_match_oracle(S, A, P, K):
+    """shapes without a golden file, checked against the oracle on the spot: BASELINE.json configs[4] (128 agents, 2048
+    polylines: two-kernel path, n_agent > 64), a ragged shape on the same path, and a ragged shape on the persistent kernel."""
+    import trafficbots_oracle as orc
+    from trafficbots_b200 import synthetic, weights
+    sd = weights.init_state_dict(2023)
+    batch = synthetic.make_batch(S, n_agent=A, n_pl=P, seed=77 + A)
+    eng = _engine(sd)
+    feat = eng.encode_scene(_cuda(batch))
+    ref_enc = orc.encode_scene(sd, batch)
+    assert torch.equal(feat["map_feature_valid"].cpu(), ref_enc["map_feature_valid"])
+    for k in ("map_feature", "agent_feature", "tl_feature"):
+        assert _maxdiff(feat[k], ref_enc[k]) <= 1e-4, k
+    out, ref = _run_jfp(eng, sd, batch, dict(K=K, sseed=5, S=S), feat)
+    _compare_rollout(out, ref, S, K)
+
+
 def test_rollout_test_mode_11_gt_frames():
     """test_step semantics: only the 11 history frames exist as GT (waymo_motion.py:923-924), no goal check."""
     from golden_util import load_case
