@@ -263,28 +263,34 @@ def run_ours(args):
     host_res["violations"] = torch.empty(6, S * K, A, T, dtype=torch.bool).pin_memory()
     d2h = sum(v.numel() * v.element_size() for v in host_res.values())
 
-    def e2e_step():
-        cbe = host.batch_to_device(host_batch, dev)
+    stager = host.SceneStager(dev)
+
+    def e2e_step(last):
+        cbe = stager.get()  # this step's inputs: pinned host -> device, queued on the staging stream
+        stager.submit(host_batch)  # the next step's inputs travel while this step computes (one copy per step, steady state)
         buf = run_step_public(module, cbe, None)  # RolloutBuffer after flatten_repeat: [S, A, K, T, ...]
-        for name in ("preds", "valid", "override_masks", "diffbar_rewards", "diffbar_rewards_valid", "action_log_probs",
-                     "latent_log_probs"):
-            host_res[name].copy_(getattr(buf, name).squeeze(2), non_blocking=True)
-        for i, name in enumerate(E.VIOLATION_KEYS):
-            host_res["violations"][i].copy_(buf.violations[name].squeeze(2), non_blocking=True)
+        pairs = [(host_res[name], getattr(buf, name).squeeze(2)) for name in
+                 ("preds", "valid", "override_masks", "diffbar_rewards", "diffbar_rewards_valid", "action_log_probs",
+                  "latent_log_probs")]
+        pairs += [(host_res["violations"][i], buf.violations[name].squeeze(2)) for i, name in enumerate(E.VIOLATION_KEYS)]
+        stager.read_back(pairs)  # results -> pinned host, overlapping the next step's kernels
         if world > 1:  # the metrics reduction: one packed all-gather per step
             local = parallel.pack_scene_metrics(buf.preds, buf.valid, buf.violations, buf.diffbar_rewards, cbe["agent/pos"],
                                                 cbe["agent/valid"])
             parallel.all_gather_scenes(local, world * S)
+        if last:
+            stager.join()  # the last step's read-back (and the copy it started) end inside its timed region
         return buf
-    for _ in range(2):
-        e2e_step()
+    stager.submit(host_batch)
+    for i in range(2):
+        e2e_step(False)
     barrier()
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)
         ev2[i][0].record()
-        e2e_step()
+        e2e_step(i == args.steps - 1)
         ev2[i][1].record()
     barrier()
     wall_e2e = time.perf_counter() - t_wall0
@@ -333,6 +339,9 @@ def run_ours(args):
                                    "closed-loop rollout (BASELINE.json configs[1]), incl. the pre-rollout heads (prior latent encoder, "
                                    "destination predictor; the K = 1 mode is the deterministic one)",
                        "l2": "256 MiB flush write between timed iterations", "timing": "CUDA events per step, summed, max over ranks",
+                       "e2e_staging": "double-buffered (host.SceneStager): the pinned-host -> device copy of step i+1 and the device -> "
+                                      "pinned-host read-back of step i-1 run on a side stream under step i's kernels; every step's "
+                                      "copies are issued and completed inside the timed steps",
                        "weights": "seeded random init (no checkpoint distributable)"},
             "e2e": {"value": world * S * args.steps / (ms_e2e * 1e-3), "unit": "scenes/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": 1e3 * wall_e2e / args.steps},
@@ -346,6 +355,10 @@ def run_ours(args):
                                          "of the 90 steps; 550 GB/s = 7 % of HBM peak, the kernel is bound by its serial GEMM -> epilogue chain",
                          "peak_source": peak_src, "flops_per_launch": f_roll,
                          "avg_launch_ms": rollout_ms, "whole_step_tflops": f_total / (ms / args.steps * 1e-3) / 1e12,
+                         "whole_step_frac": f_total / (ms / args.steps * 1e-3) / 1e12 / peak_tf,
+                         "attention_frac": 4.0 * A * (P + 40 + A) * 128 * 3 * B * T / (rollout_ms * 1e-3) / 1e12 / peak_tf,
+                         "hbm_frac": (11.66e9 / (rollout_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbps", 6553.6)))
+                                     if (world == 1 and S == 32) else None,
                          "note": "algorithmic fp32-equivalent FLOPs (SURVEY 8d); the kernel issues 3 bf16 MMAs per logical "
                                  "product (bf16x3) on M=128 tiles holding 64 agents, on 4 x B = 128 of the 148 SMs"},
             "cpu_baseline": {"value": cpu_rate, "unit": "scenes/s", "cores": cores, "kind": "port",
