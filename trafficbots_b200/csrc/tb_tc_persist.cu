@@ -357,7 +357,9 @@ struct IssuerT {
     ++n_ready;
     tc::tc_fence_after();
   }
-  __device__ __forceinline__ void gemm_begin() { wait_ready(); }
+  bool need_ready = false;
+  // the wait for the workers' operand is deferred into the first chain(): weight-slot wait and descriptor set-up come first
+  __device__ __forceinline__ void gemm_begin() { need_ready = true; }
   __device__ __forceinline__ void gemm_end() {
     if (elect_one()) tc::mma_commit(&sm.mma);
     __syncwarp();
@@ -371,6 +373,10 @@ struct IssuerT {
     const uint32_t wh = tc::smem_u32(sm.ring[slot]);
     const uint64_t dh = tc::make_desc_sw128(wh), dl = tc::make_desc_sw128(wh + 2 * tc::KB_BYTES_128);
     const uint32_t idesc = tc::make_idesc_bf16(128, 128);
+    if (need_ready) {
+      wait_ready();
+      need_ready = false;
+    }
     if (elect_one()) {
 #pragma unroll
       for (int term = 0; term < 3; ++term) {
@@ -1711,8 +1717,9 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
       const float d0 = p0.x * (1.0f / 32) - mean, d1 = p1.x * (1.0f / 32) - mean, d2 = p2.x * (1.0f / 32) - mean, d3 = p3.x * (1.0f / 32) - mean;
       const float m2 = ((p0.y + p1.y) + (p2.y + p3.y)) + 32.0f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
       const float rstd = 1.0f / sqrtf(m2 * (1.0f / 128) + LN_EPS);
+      const float nmr = -mean * rstd;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd * g[cq + i] + bt[cq + i];
+      for (int i = 0; i < 32; ++i) v[i] = fmaf(fmaf(v[i], rstd, nmr), g[cq + i], bt[cq + i]);
     };
     float4 pf0 = make_float4(0.f, 0.f, 0.f, 0.f);
     auto fetch_params = [&](int p) {
