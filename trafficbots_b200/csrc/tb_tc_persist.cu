@@ -433,8 +433,10 @@ struct IssuerT {
     }
   }
   __device__ __forceinline__ void att(bool kvi_keys, int nblk, const unsigned char*, size_t) {
-    wait_ready();  // stacked queries written
-    if (nblk == 0) return;  // (a cluster rank without key blocks of its own)
+    if (nblk == 0) {  // (a cluster rank without key blocks of its own)
+      wait_ready();
+      return;
+    }
     const uint32_t g0 = kvi_keys ? kvi_slot : g;  // slot parity of block jb = (g0 + jb) & 1
     if (kvi_keys) {
       tc::mbar_wait(&sm.wfill, n_kvi & 1);
@@ -442,7 +444,7 @@ struct IssuerT {
     } else {
       tc::mbar_wait(&sm.full[g0 & 1][0], nf[g0 & 1] & 1);
     }
-    tc::tc_fence_after();
+    wait_ready();  // stacked queries written (the key block is normally there long before)
     if (elect_one()) {
       issue_qk(g0 & 1, 0);
       issue_qk(g0 & 1, 1);
@@ -453,19 +455,16 @@ struct IssuerT {
       const uint32_t slot = (g0 + jb) & 1, slotn = slot ^ 1;
 #pragma unroll
       for (int hp = 0; hp < 2; ++hp) {
-        tc::mbar_wait(&sm.p[hp], n_p[hp] & 1);
-        ++n_p[hp];
-        tc::tc_fence_after();
+        // operand blocks first (prefetched: these waits normally fall through), then the probabilities of this pass
         if (hp == 0 && !kvi_keys) {
           tc::mbar_wait(&sm.full[slot][1], nf[slot] & 1);
           ++nf[slot];
-          tc::tc_fence_after();
         }
         const bool more = jb + 1 < nblk;
-        if (more && hp == 0) {
-          tc::mbar_wait(&sm.full[slotn][0], nf[slotn] & 1);
-          tc::tc_fence_after();
-        }
+        if (more && hp == 0) tc::mbar_wait(&sm.full[slotn][0], nf[slotn] & 1);
+        tc::mbar_wait(&sm.p[hp], n_p[hp] & 1);
+        ++n_p[hp];
+        tc::tc_fence_after();
         if (elect_one()) {
           issue_pv(slot, hp, jb > 0);
           if (hp == 1) tc::mma_commit(&sm.free_[slot][1]);
