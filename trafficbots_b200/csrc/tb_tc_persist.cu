@@ -54,6 +54,7 @@ struct Smem {
   uint8_t tflag[MAXA];  // bit 0: destination is a lane (types 0-3), bit 1: destination is a road edge (type 4)
   // barriers
   uint64_t full[2][2], free_[2][2], grant, wfill, ready, mma, cfg, s[2], p[2], o[2];
+  static constexpr int kMergeBarriers = 4;  // cluster barriers per merge of the split agent->map attention
   uint32_t tmem_base;
   int n_valid, kvi_slot;
 };
@@ -107,6 +108,8 @@ __device__ __forceinline__ void cluster_sync_all() {  // every thread of every C
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_relaxed() {  // rendezvous only: the caller publishes no data
   asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
@@ -139,6 +142,34 @@ __device__ __forceinline__ float2 ld_cluster_f32x2(uint32_t cluster_addr) {
   float2 v;
   asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(cluster_addr) : "memory");
   return v;
+}
+// asynchronous remote stores: the data lands in CTA `rank`'s shared memory and completes `bytes` on THAT CTA's mbarrier, so
+// the receiver waits on a local barrier for exactly its data instead of the whole cluster fencing (barrier.cluster release /
+// acquire = MEMBAR.ALL.GPU on every thread)
+__device__ __forceinline__ void st_async_f32x4(uint32_t cluster_addr, float4 v, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(cluster_addr),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(cluster_bar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_f32x2(uint32_t cluster_addr, float2 v, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(cluster_addr), "f"(v.x),
+               "f"(v.y), "r"(cluster_bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // acquire at cluster scope (remote st.async data)
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(tc::smem_u32(bar)), "r"(parity), "r"(1000000u)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
 }
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -337,7 +368,7 @@ struct LoaderT {  // run by a whole (converged) warp; one elected lane issues th
   __device__ __forceinline__ void csync_before_wo() {}
   __device__ __forceinline__ void csync_after_wo() {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) cluster_sync_relaxed();
+    for (int i = 0; i < SM::kMergeBarriers; ++i) cluster_sync_relaxed();
   }
 };
 
@@ -399,7 +430,7 @@ struct IssuerT {
   }
   __device__ __forceinline__ void csync_before_wo() {  // the issuer joins the merge's four cluster barriers right away
 #pragma unroll
-    for (int i = 0; i < 4; ++i) cluster_sync_relaxed();
+    for (int i = 0; i < SM::kMergeBarriers; ++i) cluster_sync_relaxed();
   }
   __device__ __forceinline__ void csync_after_wo() {}
   // QK^T of pass hp against the K half of the block in `slot`:  S_hp[128 x 64 keys] = A_hp[128 x 64 dims] K_hp^T
@@ -1530,6 +1561,8 @@ struct Smem16 {
   float map_boundary[4];
   uint8_t tflag[MAXA];
   uint64_t full[2][2], free_[2][2], grant, wfill, ready, mma, cfg, s[2], p[2], o[2];
+  uint64_t rs_bar, ag_bar;  // merge of the cluster partials: bytes of the reduce-scatter / all-gather stage landed here
+  static constexpr int kMergeBarriers = 2;
   uint32_t tmem_base;
   int n_valid, kvi_slot;
 };
@@ -1561,6 +1594,8 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
     tc::mbar_init(&sm.grant, 1);
     tc::mbar_init(&sm.wfill, 16);
     tc::mbar_init(&sm.ready, 16);
+    tc::mbar_init(&sm.rs_bar, 1);
+    tc::mbar_init(&sm.ag_bar, 1);
     tc::mbar_init(&sm.mma, 1);
     tc::mbar_init(&sm.cfg, 1);
     for (int i = 0; i < 2; ++i) {
@@ -1648,7 +1683,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
     const size_t ba = (size_t)b * A + (live ? ag : 0), sa = (size_t)s * A + (live ? ag : 0);
     const uint32_t tm = tm0 + ((uint32_t)(quad * 32) << 16);
     const int pair_id = 2 + quad * 2 + half;  // named barrier of the two warps (quad, 2 half) and (quad, 2 half + 1)
-    uint32_t n_mma = 0, n_s = 0, n_o = 0, n_grant = 0, n_ln = 0, n_lp = 0;
+    uint32_t n_mma = 0, n_s = 0, n_o = 0, n_grant = 0, n_ln = 0, n_lp = 0, n_merge = 0;
     int n_mark = 0;
     auto mark = [&]() {
       if (a.trace && blockIdx.x == 0 && tid == 0 && n_mark < 1000) a.trace[n_mark++] = clock64();
@@ -1917,6 +1952,9 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
           signal_ready();  // -> Wq
           dmark(101 + Lx * 10);
           const bool split_layer = kind == 0 && n_cta > 1;
+          // split layer: from here to the merge this CTA touches neither the LayerNorm exchange area nor the exchange buffer,
+          // so it already arrives at the "exchange buffers free" barrier of the merge (the wait sits right before the pushes)
+          if (split_layer) cluster_arrive_relaxed();
           if (!split_layer) commit_params();
           wait_gemm();
           dmark(102 + Lx * 10);
@@ -2008,7 +2046,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
           dmark(104 + Lx * 10);
           {
             // total softmax denominator of the (lane, pass): the two threads' partial sums
-            float* lxs = reinterpret_cast<float*>(&sm.red[0][0][0]);  // [4][128] (no LayerNorm in flight; separate from mxs)
+            float* lxs = &sm.mean_part[0][0][0];  // [4][128] (the action-head partials are idle here; separate from mxs and from the merge's areas)
             lxs[part * 128 + l] = l_sum;
             pair_sync(pair_id);
             const float l_tot = l_sum + lxs[(part ^ 1) * 128 + l];
@@ -2030,27 +2068,36 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
               float2* mls = &sm.red[0][0][0];  // [src rank][256 (lane, pass)] (m, l): the whole LayerNorm exchange area (idle here)
               const int lp_id = half * 128 + l;
               const uint32_t xp_addr = tc::smem_u32(xp), mls_addr = tc::smem_u32(mls);
-              cluster_sync_relaxed();
+              const uint32_t rs_addr = tc::smem_u32(&sm.rs_bar), ag_addr = tc::smem_u32(&sm.ag_bar);
+              dmark(600);
+              cluster_wait();  // (arrived after LayerNorm 1) every CTA is done with its previous use of the exchange buffers
+              dmark(601);
+              if (tid == 0) {  // what this CTA receives: one range + the (m, l) pairs from every peer; one merged range from every peer
+                tc::mbar_expect_tx(&sm.rs_bar, (uint32_t)((n_cta - 1) * (nq * WORKERS16 * 16 + 256 * 8)));
+                tc::mbar_expect_tx(&sm.ag_bar, (uint32_t)((n_cta - 1) * nq * WORKERS16 * 16));
+              }
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const int dst = q / nq, qq = q % nq;
                 const float4 val = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
                 const uint32_t off = (uint32_t)(((rank * nq + qq) * WORKERS16 + tid) * 16);
                 if (dst == rank) xp[(rank * nq + qq) * WORKERS16 + tid] = val;
-                else st_cluster_f32x4(mapa(xp_addr, (uint32_t)dst) + off, val);
+                else st_async_f32x4(mapa(xp_addr, (uint32_t)dst) + off, val, mapa(rs_addr, (uint32_t)dst));
               }
               if (sub == 0) {
-                for (int dst = 0; dst < n_cta; ++dst) {
-                  if (dst == rank) mls[rank * 256 + lp_id] = make_float2(m_ref, l_tot);
-                  else st_cluster_f32x2(mapa(mls_addr, (uint32_t)dst) + (uint32_t)((rank * 256 + lp_id) * 8), make_float2(m_ref, l_tot));
-                }
+                for (int dst = 0; dst < n_cta; ++dst)
+                  if (dst != rank)
+                    st_async_f32x2(mapa(mls_addr, (uint32_t)dst) + (uint32_t)((rank * 256 + lp_id) * 8), make_float2(m_ref, l_tot),
+                                   mapa(rs_addr, (uint32_t)dst));
               }
-              cluster_sync_all();
+              dmark(602);
+              mbar_wait_cluster(&sm.rs_bar, n_merge & 1);  // the peers' partials of my range have landed
+              dmark(603);
               float m_all = -INFINITY;
               float2 mlr[4];
 #pragma unroll
               for (int r = 0; r < 4; ++r) {
-                mlr[r] = r < n_cta ? mls[r * 256 + lp_id] : make_float2(-INFINITY, 0.f);
+                mlr[r] = r == rank ? make_float2(m_ref, l_tot) : r < n_cta ? mls[r * 256 + lp_id] : make_float2(-INFINITY, 0.f);
                 m_all = fmaxf(m_all, mlr[r].x);
               }
               float l_all = 0.f, w[4];
@@ -2078,18 +2125,23 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
                   mg[qq].x *= inv, mg[qq].y *= inv, mg[qq].z *= inv, mg[qq].w *= inv;
                 }
               }
-              cluster_sync_relaxed();
+              dmark(604);
+              cluster_sync_relaxed();  // every CTA has consumed its slots: the exchange buffer becomes the merged output
+              dmark(605);
 #pragma unroll
               for (int qq = 0; qq < 2; ++qq) {
                 if (qq < nq) {
                   const uint32_t off = (uint32_t)((((rank * nq + qq) * WORKERS16) + tid) * 16);
                   for (int dst = 0; dst < n_cta; ++dst) {
                     if (dst == rank) xp[(rank * nq + qq) * WORKERS16 + tid] = mg[qq];
-                    else st_cluster_f32x4(mapa(xp_addr, (uint32_t)dst) + off, mg[qq]);
+                    else st_async_f32x4(mapa(xp_addr, (uint32_t)dst) + off, mg[qq], mapa(ag_addr, (uint32_t)dst));
                   }
                 }
               }
-              cluster_sync_all();
+              dmark(606);
+              mbar_wait_cluster(&sm.ag_bar, n_merge & 1);  // the merged attention output is complete in this CTA
+              dmark(607);
+              ++n_merge;
               commit_params();
             } else {
               const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
