@@ -172,10 +172,11 @@ def test_rollout_matches_oracle_and_golden(case):
     assert _maxdiff(out["hidden"], gold["jfp/hidden"]) <= TOL_CLOSED
 
 
-@pytest.mark.parametrize("S,A,P,K", [(1, 128, 2048, 1), (2, 100, 1500, 1), (2, 37, 300, 2)])
+@pytest.mark.parametrize("S,A,P,K", [(1, 128, 2048, 1), (2, 100, 1500, 1), (2, 37, 300, 2), (2, 64, 1024, 6)])
 def test_rollout_other_shapes_match_oracle(S, A, P, K):
     """shapes without a golden file, checked against the oracle on the spot: BASELINE.json configs[4] (128 agents, 2048
-    polylines: two-kernel path, n_agent > 64), a ragged shape on the same path, and a ragged shape on the persistent kernel."""
+    polylines: two-kernel path, n_agent > 64), a ragged shape on the same path, a ragged shape on the persistent kernel, and the
+    per-scene shape of configs[2] (64 agents, 1024 polylines, K = 6 modes sharing the scene's key blocks)."""
     import trafficbots_oracle as orc
     from trafficbots_b200 import synthetic, weights
     sd = weights.init_state_dict(2023)
@@ -188,6 +189,48 @@ def test_rollout_other_shapes_match_oracle(S, A, P, K):
         assert _maxdiff(feat[k], ref_enc[k]) <= 1e-4, k
     out, ref = _run_jfp(eng, sd, batch, dict(K=K, sseed=5, S=S), feat)
     _compare_rollout(out, ref, S, K)
+
+
+def test_full_batch_equals_single_scenes():
+    """BASELINE.json configs[1] at full size (32 scenes x 64 agents x 1024 polylines x 90 steps): scenes are independent, so
+    every scene of the batch must come out bit-identical to the same scene encoded and rolled out alone (same kernels, same
+    cluster size), and two of them are checked against the oracle."""
+    import trafficbots_oracle as orc
+    from trafficbots_b200 import engine as E, host, synthetic, weights
+    sd = weights.init_state_dict(2023)
+    eng = _engine(sd)
+    S, A, P = 32, 64, 1024
+    batch = synthetic.make_batch(S, n_agent=A, n_pl=P, seed=4100)
+
+    def run(b):
+        cb = _cuda(b)
+        n = b["agent/type"].shape[0]
+        feat = eng.encode_scene(cb)
+        lat, _ = eng.latent_encoder(feat)
+        dest = eng.dest_predictor(feat, cb["agent/type"], cb["map/type"])[0].argmax(-1)
+        gt = E.gt_from_batch(cb)
+        tf = host.teacher_forcing_mask(gt["valid"], 10, 10)
+        out = eng.rollout(feat, gt, tf, cb["agent/type"], cb["agent/size"], E.raw_map_from_batch(cb), lat,
+                          torch.zeros(n, A, device="cuda"), dest, cb["history/agent/valid"].any(1), cb["agent/goal"], n_mode=1,
+                          n_step=90)
+        return {k: v.clone() for k, v in out.items() if isinstance(v, torch.Tensor)}, lat, dest
+
+    full, lat_f, dest_f = run(batch)
+    for i in (0, 13, 31):
+        one = {k: v[i:i + 1] for k, v in batch.items()}
+        single, lat_s, dest_s = run(one)
+        assert torch.equal(dest_s[0], dest_f[i])
+        assert torch.equal(lat_s[0], lat_f[i])
+        for k in ("preds", "valid", "override_masks", "diffbar_rewards", "violations/dest_reached", "violations/outside_map"):
+            assert torch.equal(single[k][0], full[k][i]), (i, k)
+    # oracle on two scenes of the batch (same latent / destination as the GPU heads chose)
+    for i in (5, 31):
+        one = {k: v[i:i + 1] for k, v in batch.items()}
+        ref = orc.joint_future_pred(sd, one, k=1, sample_seed=0)
+        assert torch.equal(ref["goal_sample"][0, :, 0], dest_f[i].cpu())
+        p = full["preds"][i].cpu()
+        assert float((p - ref["preds"][0, :, 0]).abs().max()) <= TOL_CLOSED
+        assert torch.equal(full["valid"][i].cpu(), ref["valid"][0, :, 0])
 
 
 def test_rollout_test_mode_11_gt_frames():
