@@ -1817,11 +1817,12 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
         __threadfence_block();
         mbar_arrive(&sm.cfg);
       }
-      // ---- state embedding: 8 threads per agent, 16 of the 128 features each (32 MLP outputs, then 96 PE values) --------
+      // ---- state embedding: 8 threads per agent; each computes 4 hidden units, then (after one barrier) 4 MLP outputs and 12 of
+      // the 96 PE values = ONE function of one coordinate for the 12 frequencies of its group (same arithmetic order as before) --
       {
         const int fidx = 2 * part + upper;
         const float4 st = sm.pose[ag];
-        if (fidx < 2) {
+        {
           float at[12];
           at[0] = sm.vel[ag].x, at[1] = sm.vel[ag].y, at[2] = st.w, at[3] = sm.yaw_rate[ag], at[4] = sm.acc[ag];
 #pragma unroll
@@ -1830,18 +1831,39 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
             at[8 + i] = sm.type[ag][i] ? 1.f : 0.f;
           }
           at[11] = 0.f;
-          float h[32];
 #pragma unroll
-          for (int o = 0; o < 32; ++o) {
+          for (int u = 0; u < 4; ++u) {
+            const int o = 4 * fidx + u;
             float acc = sm.emb_b1[o];
 #pragma unroll
-            for (int k = 0; k < 12; ++k) acc = fmaf(at[k], sm.emb_w1[((k >> 2) * 32 + o) * 4 + (k & 3)], acc);
-            h[o] = fmaxf(acc, 0.f);
+            for (int k4 = 0; k4 < 3; ++k4) {
+              const float4 w = *reinterpret_cast<const float4*>(&sm.emb_w1[(k4 * 32 + o) * 4]);
+              acc = fmaf(at[4 * k4 + 3], w.w, fmaf(at[4 * k4 + 2], w.z, fmaf(at[4 * k4 + 1], w.y, fmaf(at[4 * k4], w.x, acc))));
+            }
+            sm.xo[o * MAXA + ag] = fmaxf(acc, 0.f);
           }
-          const float* w2 = packed + tbw::model_agent_encoder_mlp_fc_layers_3_weight;  // Wt4[8][32][4], through L1
+        }
+        // PE while the hidden units of the other threads land: [cos(x f) | sin(x f) | cos(y f) | sin(y f) | cos(yaw g) 24 | sin(yaw g) 24]
+        {
+          const bool is_sin = fidx == 1 || fidx == 3 || fidx >= 6;
+          const float arg = fidx < 2 ? st.x : fidx < 4 ? st.y : st.z;
+          const float* ft = fidx < 4 ? &sm.f_xy[is_sin ? 1 : 0] : &sm.f_yaw[(is_sin ? 1 : 0) + ((fidx & 1) ? 24 : 0)];
 #pragma unroll 4
-          for (int oo = 0; oo < 16; ++oo) {
-            const int o = 16 * fidx + oo;
+          for (int i = 0; i < 12; ++i) {
+            const float ph = arg * ft[2 * i];
+            const float v = is_sin ? sinf(ph) : cosf(ph);
+            sm.xs[(32 + 12 * fidx + i) * MAXA + ag] = valid ? v : 0.f;
+          }
+        }
+        worker_sync16();
+        {
+          float h[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) h[k] = sm.xo[k * MAXA + ag];
+          const float* w2 = packed + tbw::model_agent_encoder_mlp_fc_layers_3_weight;  // Wt4[8][32][4], through L1
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int o = 4 * fidx + u;
             float acc = sm.emb_b2[o];
 #pragma unroll
             for (int k4 = 0; k4 < 8; ++k4) {
@@ -1849,19 +1871,6 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
               acc = fmaf(h[4 * k4 + 3], w.w, fmaf(h[4 * k4 + 2], w.z, fmaf(h[4 * k4 + 1], w.y, fmaf(h[4 * k4], w.x, acc))));
             }
             sm.xs[o * MAXA + ag] = valid ? acc : 0.f;
-          }
-        } else {
-#pragma unroll 4
-          for (int i = 0; i < 16; ++i) {
-            const int j = 16 * (fidx - 2) + i;  // PE element 0..95
-            float v;
-            if (j < 12) v = cosf(st.x * sm.f_xy[2 * j]);
-            else if (j < 24) v = sinf(st.x * sm.f_xy[2 * (j - 12) + 1]);
-            else if (j < 36) v = cosf(st.y * sm.f_xy[2 * (j - 24)]);
-            else if (j < 48) v = sinf(st.y * sm.f_xy[2 * (j - 36) + 1]);
-            else if (j < 72) v = cosf(st.z * sm.f_yaw[2 * (j - 48)]);
-            else v = sinf(st.z * sm.f_yaw[2 * (j - 72) + 1]);
-            sm.xs[(32 + j) * MAXA + ag] = valid ? v : 0.f;
           }
         }
       }
