@@ -2332,7 +2332,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
         ++n_lp;
       }
       // ---- action head ----------------------------------------------------------------------------------------------------------------
-      const bool tail_thread = part == 0 && upper == 0 && live;
+      const bool tail_thread = upper == 0 && live;  // the four column-part threads of an agent share the tail (below)
       const bool out_w = rank == 0;
       const bool has_gt = t < Tg;
       const size_t gidx = ((size_t)s * Tg + (has_gt ? t : 0)) * A + ag;
@@ -2396,7 +2396,13 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
       mark();
 
       dmark(400);
-      // ---- per-agent tail ------------------------------------------------------------------------------------------------------------
+      // ---- per-agent tail: the 4 threads (part 0..3, lower lane) of an agent all integrate the dynamics (same inputs, same
+      // arithmetic), then split the rest: part 0 outputs / override / map boundary / kill, part 1 goal check + reward, parts 2
+      // and 3 ten destination nodes each; part 0 combines the flags after one barrier --------------------------------------
+      float4 ns = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool nvalid = false, killed = false, outside = false, out_t = false;
+      const size_t o = ba * T + (t - 1);
+      uint8_t* tflags = reinterpret_cast<uint8_t*>(&sm.mxs[0][0]);  // [4 parts][MAXA] result flags (the softmax exchange area is idle here)
       if (tail_thread) {
         float mean0 = 0.f, mean1 = 0.f;
 #pragma unroll
@@ -2423,59 +2429,82 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
           pred.z = st.z + 0.1f * a_yr;
           pred.w = st.w + 0.1f * a_acc;
         }
-        const size_t o = ba * T + (t - 1);
-        if (out_w) {
-          *reinterpret_cast<float4*>(a.out.preds + o * 4) = pred;
-          a.out.valid[o] = valid;
-          a.out.action_log_probs[o] = valid ? sm.tailc[2][ag] : 0.f;
-          a.out.latent_log_probs[o] = sm.tailc[3][ag];
-          if (a.out.trace_action_mean) {
-            a.out.trace_action_mean[o * 2] = mean0;
-            a.out.trace_action_mean[o * 2 + 1] = mean1;
-          }
-        }
-        bool killed = sm.killed[ag] != 0;
+        killed = sm.killed[ag] != 0;
         const bool m = ovr && !killed;
-        bool nvalid = valid || m;
-        float4 ns = pred;
-        if (m) {
-          ns = gs;
-          sm.vel[ag] = g_vel;
-          sm.acc[ag] = g_acc;
-          sm.yaw_rate[ag] = g_yr;
-        }
-        if (out_w) a.out.override_masks[o] = ovr;
-        const bool out_t = nvalid && (ns.x > sm.map_boundary[1] || ns.x < sm.map_boundary[0] || ns.y > sm.map_boundary[3] || ns.y < sm.map_boundary[2]);
-        bool outside = sm.sticky[0][ag] != 0, goal_r = sm.sticky[1][ag] != 0, dest_r = sm.sticky[2][ag] != 0;
-        outside |= out_t;
-        bool goal_t = false;
-        if (in.goal_gt) {
-          const float dx = ns.x - sm.tailc[4][ag], dy = ns.y - sm.tailc[5][ag];
-          const bool pos_ok = sqrtf(dx * dx + dy * dy) < sm.tailc[7][ag];
-          const float PI_F = 3.14159265358979323846f, TWO_PI_F = 6.28318530717958647692f;
-          float w = fmodf(ns.z - sm.tailc[6][ag] + PI_F, TWO_PI_F);
-          if (w < 0.f) w += TWO_PI_F;
-          const bool rot_ok = fabsf(w - PI_F) < 0.26179938779914943654f;
-          goal_t = pos_ok && rot_ok && nvalid && !goal_r;
-        }
-        goal_r |= goal_t;
-        bool pos_reached = false, rot_reached = false;
-        const float k_dest_thresh = sm.tailc[8][ag];
-        const bool k_lane_t = (sm.tflag[ag] & 1) != 0, k_edge_t = (sm.tflag[ag] & 2) != 0;
-        const float hx = cosf(ns.z), hy = sinf(ns.z);
-        const float4* dn = a.sv.dest_nodes + (size_t)b * TB_PL_NODE * A + ag;
-#pragma unroll
-        for (int n0 = 0; n0 < TB_PL_NODE; n0 += 10) {
+        nvalid = valid || m;
+        ns = m ? gs : pred;
+        if (part == 0) {
+          if (out_w) {
+            *reinterpret_cast<float4*>(a.out.preds + o * 4) = pred;
+            a.out.valid[o] = valid;
+            a.out.action_log_probs[o] = valid ? sm.tailc[2][ag] : 0.f;
+            a.out.latent_log_probs[o] = sm.tailc[3][ag];
+            if (a.out.trace_action_mean) {
+              a.out.trace_action_mean[o * 2] = mean0;
+              a.out.trace_action_mean[o * 2 + 1] = mean1;
+            }
+            a.out.override_masks[o] = ovr;
+          }
+          out_t = nvalid && (ns.x > sm.map_boundary[1] || ns.x < sm.map_boundary[0] || ns.y > sm.map_boundary[3] || ns.y < sm.map_boundary[2]);
+          outside = (sm.sticky[0][ag] != 0) || out_t;
+        } else if (part == 1) {
+          bool goal_t = false;
+          if (in.goal_gt) {
+            const float dx = ns.x - sm.tailc[4][ag], dy = ns.y - sm.tailc[5][ag];
+            const bool pos_ok = sqrtf(dx * dx + dy * dy) < sm.tailc[7][ag];
+            const float PI_F = 3.14159265358979323846f, TWO_PI_F = 6.28318530717958647692f;
+            float w = fmodf(ns.z - sm.tailc[6][ag] + PI_F, TWO_PI_F);
+            if (w < 0.f) w += TWO_PI_F;
+            const bool rot_ok = fabsf(w - PI_F) < 0.26179938779914943654f;
+            goal_t = pos_ok && rot_ok && nvalid && !(sm.sticky[1][ag] != 0);
+          }
+          tflags[1 * MAXA + ag] = goal_t;
+          float reward = 0.f;
+          bool rv = valid;
+          if (has_gt) {
+            rv = valid && gt_valid;
+            if (rv) {
+              const float e_pos = smooth_l1(gs.x - pred.x) + smooth_l1(gs.y - pred.y);
+              const float e_rot = 0.5f * (1.0f - cosf(gs.z - pred.z));
+              const float e_spd = smooth_l1(gs.w - pred.w);
+              reward = 0.0f - (0.1f * e_pos + 10.0f * e_rot + 0.1f * e_spd);
+            }
+          }
+          if (out_w) {
+            a.out.diffbar_rewards[o] = reward;
+            a.out.diffbar_rewards_valid[o] = rv;
+          }
+        } else {
+          bool pos_reached = false, rot_reached = false;
+          const float k_dest_thresh = sm.tailc[8][ag];
+          const float hx = cosf(ns.z), hy = sinf(ns.z);
+          const float4* dn = a.sv.dest_nodes + ((size_t)b * TB_PL_NODE + 10 * (part - 2)) * A + ag;
           float4 nd[10];
 #pragma unroll
-          for (int n = 0; n < 10; ++n) nd[n] = __ldg(dn + (n0 + n) * A);
+          for (int n = 0; n < 10; ++n) nd[n] = __ldg(dn + n * A);
 #pragma unroll
           for (int n = 0; n < 10; ++n) {
             const float dx = ns.x - nd[n].x, dy = ns.y - nd[n].y;
             pos_reached |= sqrtf(dx * dx + dy * dy) < k_dest_thresh;
             rot_reached |= (hx * nd[n].z + hy * nd[n].w) > 0.86602540378443864676f;
           }
+          tflags[part * MAXA + ag] = (uint8_t)((pos_reached ? 1 : 0) | (rot_reached ? 2 : 0));
         }
+      }
+      worker_sync16();
+      if (tail_thread && part == 0) {
+        const bool m = ovr && !killed;
+        if (m) {
+          sm.vel[ag] = g_vel;
+          sm.acc[ag] = g_acc;
+          sm.yaw_rate[ag] = g_yr;
+        }
+        bool goal_r = sm.sticky[1][ag] != 0, dest_r = sm.sticky[2][ag] != 0;
+        const bool goal_t = tflags[1 * MAXA + ag] != 0;
+        goal_r |= goal_t;
+        const uint8_t f23 = tflags[2 * MAXA + ag] | tflags[3 * MAXA + ag];
+        const bool pos_reached = (f23 & 1) != 0, rot_reached = (f23 & 2) != 0;
+        const bool k_lane_t = (sm.tflag[ag] & 1) != 0, k_edge_t = (sm.tflag[ag] & 2) != 0;
         const bool dest_t = !dest_r && nvalid && ((k_lane_t && pos_reached && rot_reached) || (k_edge_t && pos_reached));
         dest_r |= dest_t;
         if (out_w) {
@@ -2491,21 +2520,6 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
         killed |= kill;
         nvalid = nvalid && !kill;
         const bool gv = sm.goal_valid[ag] && nvalid && !dest_r;
-        float reward = 0.f;
-        bool rv = valid;
-        if (has_gt) {
-          rv = valid && gt_valid;
-          if (rv) {
-            const float e_pos = smooth_l1(gs.x - pred.x) + smooth_l1(gs.y - pred.y);
-            const float e_rot = 0.5f * (1.0f - cosf(gs.z - pred.z));
-            const float e_spd = smooth_l1(gs.w - pred.w);
-            reward = 0.0f - (0.1f * e_pos + 10.0f * e_rot + 0.1f * e_spd);
-          }
-        }
-        if (out_w) {
-          a.out.diffbar_rewards[o] = reward;
-          a.out.diffbar_rewards_valid[o] = rv;
-        }
         sm.pose[ag] = ns;
         sm.valid[ag] = nvalid;
         sm.killed[ag] = killed;
