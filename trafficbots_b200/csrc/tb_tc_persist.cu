@@ -2218,25 +2218,22 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
       // ---- agent_temporal: 3-layer GRU -------------------------------------------------------------------------------------------
 #pragma unroll 1
       for (int L = 0; L < 3; ++L) {
+        // h_{t-1} of this layer (written one step ago) is requested before the barrier: its L2 latency hides behind the barrier and
+        // the x operand
+        float4* hid = hid_t + (size_t)L * B * 32 * A + ag;
+        float4 hq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hq[i] = live ? hid[(cq / 4 + i) * A] : make_float4(0.f, 0.f, 0.f, 0.f);
         worker_sync16();
         const float (*lp)[128] = sm.lp[n_lp & 1];
         dmark(200 + L * 10);
         fetch_params(10 + L);
-        float4* hid = hid_t + (size_t)L * B * 32 * A + ag;
         {
           float x[32];
           load_x(x);
           write_A(T_A, x);
-          if (live) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 q = hid[(cq / 4 + i) * A];
-              x[4 * i] = q.x, x[4 * i + 1] = q.y, x[4 * i + 2] = q.z, x[4 * i + 3] = q.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = 0.f;
-          }
+          for (int i = 0; i < 8; ++i) x[4 * i] = hq[i].x, x[4 * i + 1] = hq[i].y, x[4 * i + 2] = hq[i].z, x[4 * i + 3] = hq[i].w;
           write_A(T_A2, x);
         }
         signal_ready();
@@ -2259,6 +2256,9 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.ready);
         dmark(203 + L * 10);
+        float4 hp4v[4];  // this thread's 16 columns of h_{t-1}, in flight during the second MMA batch
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hp4v[i] = live ? hid[(ce / 4 + i) * A] : make_float4(0.f, 0.f, 0.f, 0.f);
         wait_gemm();
         dmark(204 + L * 10);
         {
@@ -2268,9 +2268,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
           tc::tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            float4 hp4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) hp4 = hid[(ce / 4 + i) * A];
-            const float hp_[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
+            const float hp_[4] = {hp4v[i].x, hp4v[i].y, hp4v[i].z, hp4v[i].w};
             float hn_[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -2291,22 +2289,23 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
       // ---- add_goal, add_latent ----------------------------------------------------------------------------------------------------
 #pragma unroll 1
       for (int j = 0; j < 2; ++j) {
+        // the (step-invariant) goal / latent feature is requested before the barrier; the x operand goes first
+        const bool zv = j == 0 ? (sm.goal_valid[ag] != 0) : valid;
+        const float4* zin = (j == 0 ? goal_in_t : latent_in_t) + (cq / 4) * A + ag;
+        float4 zq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) zq[i] = (live && zv) ? __ldg(zin + i * A) : make_float4(0.f, 0.f, 0.f, 0.f);
         worker_sync16();
         const float (*lp)[128] = sm.lp[n_lp & 1];
         fetch_params(13 + j);
-        const bool zv = j == 0 ? (sm.goal_valid[ag] != 0) : valid;
-        const float4* zin = (j == 0 ? goal_in_t : latent_in_t) + (cq / 4) * A + ag;
         {
           float z[32];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live && zv) q = __ldg(zin + i * A);
-            z[4 * i] = fmaxf(q.x, 0.f), z[4 * i + 1] = fmaxf(q.y, 0.f), z[4 * i + 2] = fmaxf(q.z, 0.f), z[4 * i + 3] = fmaxf(q.w, 0.f);
-          }
-          write_A(T_A2, z);
           load_x(z);
           write_A(T_A, z);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            z[4 * i] = fmaxf(zq[i].x, 0.f), z[4 * i + 1] = fmaxf(zq[i].y, 0.f), z[4 * i + 2] = fmaxf(zq[i].z, 0.f), z[4 * i + 3] = fmaxf(zq[i].w, 0.f);
+          write_A(T_A2, z);
         }
         signal_ready();
         commit_params();
