@@ -55,6 +55,7 @@ struct Smem {
   // barriers
   uint64_t full[2][2], free_[2][2], grant, wfill, ready, mma, cfg, s[2], p[2], o[2];
   static constexpr int kMergeBarriers = 4;  // cluster barriers per merge of the split agent->map attention
+  static constexpr uint32_t kInteractionQ = T_ACC0;  // accumulator of the interaction layers' Q projection
   uint32_t tmem_base;
   int n_valid, kvi_slot;
 };
@@ -265,7 +266,7 @@ __device__ __forceinline__ void enumerate_step(const Args& a, const StepCfg& c, 
         r.kvi();
       }
       r.gemm_begin();
-      r.chain(W(w0, 0), T_ACC0, T_A, false);
+      r.chain(W(w0, 0), kind == 2 ? R::kInteractionQ : T_ACC0, T_A, false);
       r.gemm_end();
       r.att(kind == 2, nblk_my, kind == 0 ? c.kv_map + L * c.kv_map_layer_stride + (size_t)c.rank * BLK : c.kv_tl + L * c.kv_tl_layer_stride,
             kind == 0 ? (size_t)c.n_cta * BLK : (size_t)BLK);
@@ -320,6 +321,7 @@ __device__ __forceinline__ void enumerate_step(const Args& a, const StepCfg& c, 
 
 template <class SM>
 struct LoaderT {  // run by a whole (converged) warp; one elected lane issues the copies
+  static constexpr uint32_t kInteractionQ = SM::kInteractionQ;
   SM& sm;
   uint32_t g = 0, n_cfg = 0;
   __device__ LoaderT(SM& s) : sm(s) {}
@@ -374,6 +376,7 @@ struct LoaderT {  // run by a whole (converged) warp; one elected lane issues th
 
 template <class SM>
 struct IssuerT {
+  static constexpr uint32_t kInteractionQ = SM::kInteractionQ;
   SM& sm;
   uint32_t tm0;
   uint32_t g = 0, nf[2] = {0, 0}, n_ready = 0, n_cfg = 0, n_p[2] = {0, 0}, n_kvi = 0, kvi_slot = 0;
@@ -1563,6 +1566,7 @@ struct Smem16 {
   uint64_t full[2][2], free_[2][2], grant, wfill, ready, mma, cfg, s[2], p[2], o[2];
   uint64_t rs_bar, ag_bar;  // merge of the cluster partials: bytes of the reduce-scatter / all-gather stage landed here
   static constexpr int kMergeBarriers = 2;
+  static constexpr uint32_t kInteractionQ = T_ACC2;  // Q of the interaction layers lands beside K | V (their epilogue overlaps it)
   uint32_t tmem_base;
   int n_valid, kvi_slot;
 };
@@ -1915,8 +1919,14 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
             write_A(T_A, v);
             signal_ready();  // -> Wk (ACC0), Wv (ACC1)
             dmark(500 + Lx);
+            // LayerNorm 1 of the query side while the K | V MMAs run; its operand replaces the key-side one as soon as they are
+            // done, and the Q projection (-> ACC2) then runs under the K | V epilogue below
+            load_x(v);
+            ln32(v, lp[0], lp[1]);
             wait_gemm();
             dmark(510 + Lx);
+            write_A(T_A, v);
+            signal_ready();  // -> Wq (ACC2)
             tc::mbar_wait(&sm.grant, n_grant & 1);
             ++n_grant;
             {
@@ -1954,11 +1964,12 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.wfill);
             dmark(540 + Lx);
+          } else {
+            load_x(v);
+            ln32(v, lp[0], lp[1]);
+            write_A(T_A, v);
+            signal_ready();  // -> Wq
           }
-          load_x(v);
-          ln32(v, lp[0], lp[1]);
-          write_A(T_A, v);
-          signal_ready();  // -> Wq
           dmark(101 + Lx * 10);
           const bool split_layer = kind == 0 && n_cta > 1;
           // split layer: from here to the merge this CTA touches neither the LayerNorm exchange area nor the exchange buffer,
@@ -1970,7 +1981,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
           if ((part & 1) == upper) {  // this thread's 32 Q columns = head `part` = the head lane l needs in pass part / 2
             const int hp = part >> 1;
             float q[32];
-            tc::tmem_ld32(tm + T_ACC0 + cq, q);
+            tc::tmem_ld32(tm + (kind == 2 ? T_ACC2 : T_ACC0) + cq, q);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) q[i] = (q[i] + lp[2][cq + i]) * sc;
