@@ -49,7 +49,9 @@ def flops_front(A, P, TL, D=128):
 def flops_back(A, D=128):
     inter = 3 * (4 * A * D * D + 4 * A * A * D + 4 * A * D * D)
     gru = 3 * 12 * A * D * D
-    add = 2 * 6 * A * D * D
+    # add_goal / add_latent mlp_out: Linear(256,128) + Linear(128,128); the z half of the first Linear is step-invariant and is
+    # computed once per rollout by k_rollout_init, so it is NOT counted per step (SURVEY 8d's F_step counts it: 6AD^2 each)
+    add = 2 * (6 - 2) * A * D * D
     head = 3 * 2 * A * (D * D + 2 * D)
     return inter + gru + add + head
 

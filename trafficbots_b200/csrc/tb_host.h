@@ -42,6 +42,8 @@ struct StateView {
   float4* x0_t;        // [n_cluster][B][32][A]     input of the interaction block
   float4* goal_in_t;   // [B][32][A]   = goal_in
   float4* latent_in_t; // [B][32][A]   = latent_in
+  float4* goal_c_t;    // [B][32][A]   = W_out0[:, 128:256] relu(goal_in): step-invariant half of add_goal.mlp_out layer 0
+  float4* latent_c_t;  // [B][32][A]   = the same for add_latent
   float4* dest_nodes;  // [B][20][A]   destination polyline nodes (x, y, unit direction), invalid nodes at 1e30
 };
 

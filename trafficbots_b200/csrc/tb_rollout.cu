@@ -16,7 +16,7 @@ static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct StateLayout {
   size_t off[TB_STATE_N_FIELD];
-  size_t x0, kv_int, goal_in, latent_in, dest_nodes, hidden_t, x0_t, goal_in_t, latent_in_t, total;
+  size_t x0, kv_int, goal_in, latent_in, dest_nodes, hidden_t, x0_t, goal_in_t, latent_in_t, goal_c_t, latent_c_t, total;
 };
 
 static StateLayout state_layout(const TbDims& d) {
@@ -47,6 +47,8 @@ static StateLayout state_layout(const TbDims& d) {
   L.x0_t = put(n_cta * BA * D * sizeof(float));
   L.goal_in_t = put(BA * D * sizeof(float));
   L.latent_in_t = put(BA * D * sizeof(float));
+  L.goal_c_t = put(BA * D * sizeof(float));
+  L.latent_c_t = put(BA * D * sizeof(float));
   L.total = o;
   return L;
 }
@@ -73,6 +75,8 @@ StateView state_view(const TbDims& d, void* base) {
   v.x0_t = reinterpret_cast<float4*>(p + L.x0_t);
   v.goal_in_t = reinterpret_cast<float4*>(p + L.goal_in_t);
   v.latent_in_t = reinterpret_cast<float4*>(p + L.latent_in_t);
+  v.goal_c_t = reinterpret_cast<float4*>(p + L.goal_c_t);
+  v.latent_c_t = reinterpret_cast<float4*>(p + L.latent_c_t);
   return v;
 }
 
@@ -185,6 +189,18 @@ __global__ void __launch_bounds__(NT) k_rollout_init(TbDims dm, TbRolloutIn in, 
     if (r < nrow) sv.goal_in_t[((size_t)b * (D / 4) + c4) * A + a0 + r] = reinterpret_cast<const float4*>(sm.x + r * D)[c4];
   }
   __syncthreads();
+  // step-invariant half of add_goal.mlp_out layer 0: W[:, 128:256] relu(goal_in)  (cat[x, z] @ W^T = x-half + z-half,
+  // add_latent_goal.py:64-77; the persistent kernel adds it in the epilogue where goal_valid(t) holds)
+  for (int i = tid; i < R * D; i += NT) sm.t[i] = fmaxf(sm.x[i], 0.f);
+  __syncthreads();
+  gemm128<RPT>(packed + tbw::model_add_goal_mlp_out_fc_layers_0_weight + (size_t)(D / 4) * D * 4, D, 0, D / 4, sm.t, D,
+               [&](int r, int c, float v) { sm.q[r * D + c] = v; });
+  __syncthreads();
+  for (int i = tid; i < R * (D / 4); i += NT) {
+    const int r = i % R, c4 = i / R;
+    if (r < nrow) sv.goal_c_t[((size_t)b * (D / 4) + c4) * A + a0 + r] = reinterpret_cast<const float4*>(sm.q + r * D)[c4];
+  }
+  __syncthreads();
 
   // ---- add_latent.mlp_in(latent_sample): Linear(16,128)-ReLU-Linear(128,128) -----------------------------------------
   for (int i = tid; i < R * TB_LATENT; i += NT) {
@@ -204,6 +220,16 @@ __global__ void __launch_bounds__(NT) k_rollout_init(TbDims dm, TbRolloutIn in, 
   for (int i = tid; i < R * (D / 4); i += NT) {
     const int r = i % R, c4 = i / R;
     if (r < nrow) sv.latent_in_t[((size_t)b * (D / 4) + c4) * A + a0 + r] = reinterpret_cast<const float4*>(sm.x + r * D)[c4];
+  }
+  __syncthreads();
+  for (int i = tid; i < R * D; i += NT) sm.t[i] = fmaxf(sm.x[i], 0.f);
+  __syncthreads();
+  gemm128<RPT>(packed + tbw::model_add_latent_mlp_out_fc_layers_0_weight + (size_t)(D / 4) * D * 4, D, 0, D / 4, sm.t, D,
+               [&](int r, int c, float v) { sm.q[r * D + c] = v; });
+  __syncthreads();
+  for (int i = tid; i < R * (D / 4); i += NT) {
+    const int r = i % R, c4 = i / R;
+    if (r < nrow) sv.latent_c_t[((size_t)b * (D / 4) + c4) * A + a0 + r] = reinterpret_cast<const float4*>(sm.q + r * D)[c4];
   }
 }
 

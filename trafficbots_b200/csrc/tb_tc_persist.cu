@@ -56,6 +56,7 @@ struct Smem {
   uint64_t full[2][2], free_[2][2], grant, wfill, ready, mma, cfg, s[2], p[2], o[2];
   static constexpr int kMergeBarriers = 4;  // cluster barriers per merge of the split agent->map attention
   static constexpr uint32_t kInteractionQ = T_ACC0;  // accumulator of the interaction layers' Q projection
+  static constexpr bool kAddHalfHoisted = false;     // add_goal / add_latent: the z half of mlp_out layer 0 is a GEMM of the step
   uint32_t tmem_base;
   int n_valid, kvi_slot;
 };
@@ -305,7 +306,7 @@ __device__ __forceinline__ void enumerate_step(const Args& a, const StepCfg& c, 
     for (int j = 0; j < 2; ++j) {
       r.gemm_begin();
       r.chain(W(w[j][0], 0), T_ACC0, T_A, false);
-      r.chain(W(w[j][0], 1), T_ACC0, T_A2, true);
+      if (!R::kAddHalfHoisted) r.chain(W(w[j][0], 1), T_ACC0, T_A2, true);
       r.gemm_end();
       r.gemm_begin();
       r.chain(W(w[j][1], 0), T_ACC0, T_A, false);
@@ -322,6 +323,7 @@ __device__ __forceinline__ void enumerate_step(const Args& a, const StepCfg& c, 
 template <class SM>
 struct LoaderT {  // run by a whole (converged) warp; one elected lane issues the copies
   static constexpr uint32_t kInteractionQ = SM::kInteractionQ;
+  static constexpr bool kAddHalfHoisted = SM::kAddHalfHoisted;
   SM& sm;
   uint32_t g = 0, n_cfg = 0;
   __device__ LoaderT(SM& s) : sm(s) {}
@@ -377,6 +379,7 @@ struct LoaderT {  // run by a whole (converged) warp; one elected lane issues th
 template <class SM>
 struct IssuerT {
   static constexpr uint32_t kInteractionQ = SM::kInteractionQ;
+  static constexpr bool kAddHalfHoisted = SM::kAddHalfHoisted;
   SM& sm;
   uint32_t tm0;
   uint32_t g = 0, nf[2] = {0, 0}, n_ready = 0, n_cfg = 0, n_p[2] = {0, 0}, n_kvi = 0, kvi_slot = 0;
@@ -1567,6 +1570,7 @@ struct Smem16 {
   uint64_t rs_bar, ag_bar;  // merge of the cluster partials: bytes of the reduce-scatter / all-gather stage landed here
   static constexpr int kMergeBarriers = 2;
   static constexpr uint32_t kInteractionQ = T_ACC2;  // Q of the interaction layers lands beside K | V (their epilogue overlaps it)
+  static constexpr bool kAddHalfHoisted = true;      // ... is precomputed per rollout (k_rollout_init) and added in the epilogue
   uint32_t tmem_base;
   int n_valid, kvi_slot;
 };
@@ -1635,8 +1639,8 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
   }
   float4* const hid_t = a.sv.hidden_t + ((size_t)rank * 3 * B + b) * 32 * A;
   float4* const x0_t = a.sv.x0_t + ((size_t)rank * B + b) * 32 * A;
-  const float4* const goal_in_t = a.sv.goal_in_t + (size_t)b * 32 * A;
-  const float4* const latent_in_t = a.sv.latent_in_t + (size_t)b * 32 * A;
+  const float4* const goal_c_t = a.sv.goal_c_t + (size_t)b * 32 * A;
+  const float4* const latent_c_t = a.sv.latent_c_t + (size_t)b * 32 * A;
   for (int L = 0; L < 3; ++L) {
     const float4* src = reinterpret_cast<const float4*>(a.sv.hidden + ((size_t)L * BA + (size_t)b * A) * D);
     float4* dst = hid_t + (size_t)L * B * 32 * A;
@@ -2300,12 +2304,13 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
       // ---- add_goal, add_latent ----------------------------------------------------------------------------------------------------
 #pragma unroll 1
       for (int j = 0; j < 2; ++j) {
-        // the (step-invariant) goal / latent feature is requested before the barrier; the x operand goes first
+        // z half of mlp_out layer 0 (W[:, 128:256] relu(z), step-invariant, from k_rollout_init): requested before the barrier, added
+        // in the epilogue where z is valid
         const bool zv = j == 0 ? (sm.goal_valid[ag] != 0) : valid;
-        const float4* zin = (j == 0 ? goal_in_t : latent_in_t) + (cq / 4) * A + ag;
+        const float4* zc = (j == 0 ? goal_c_t : latent_c_t) + (cq / 4) * A + ag;
         float4 zq[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) zq[i] = (live && zv) ? __ldg(zin + i * A) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 8; ++i) zq[i] = (live && zv) ? __ldg(zc + i * A) : make_float4(0.f, 0.f, 0.f, 0.f);
         worker_sync16();
         const float (*lp)[128] = sm.lp[n_lp & 1];
         fetch_params(13 + j);
@@ -2313,10 +2318,6 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
           float z[32];
           load_x(z);
           write_A(T_A, z);
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            z[4 * i] = fmaxf(zq[i].x, 0.f), z[4 * i + 1] = fmaxf(zq[i].y, 0.f), z[4 * i + 2] = fmaxf(zq[i].z, 0.f), z[4 * i + 3] = fmaxf(zq[i].w, 0.f);
-          write_A(T_A2, z);
         }
         signal_ready();
         commit_params();
@@ -2325,7 +2326,12 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
           float h1[32];
           load_acc(T_ACC0, h1);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) h1[i] = fmaxf(h1[i] + lp[0][cq + i], 0.f);
+          for (int i = 0; i < 8; ++i) {
+            h1[4 * i] = fmaxf(h1[4 * i] + zq[i].x + lp[0][cq + 4 * i], 0.f);
+            h1[4 * i + 1] = fmaxf(h1[4 * i + 1] + zq[i].y + lp[0][cq + 4 * i + 1], 0.f);
+            h1[4 * i + 2] = fmaxf(h1[4 * i + 2] + zq[i].z + lp[0][cq + 4 * i + 2], 0.f);
+            h1[4 * i + 3] = fmaxf(h1[4 * i + 3] + zq[i].w + lp[0][cq + 4 * i + 3], 0.f);
+          }
           write_A(T_A, h1);
         }
         signal_ready();
