@@ -2261,15 +2261,17 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
           tc::tmem_ld16(tm + T_ACC0 + ce, r);
           tc::tmem_ld16(tm + T_ACC1 + ce, rh);
           tc::tmem_ld_wait();
+          // both accumulators are in registers: the second MMA batch (same operands, z and n gates) may overwrite them now and
+          // runs under the gate math below
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.ready);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float rg = fast_sigmoid(r[i] + lp[0][ce + i] + lp[3][ce + i]);
             sm.xo[(ce + i) * MAXA + ag] = rg * (rh[i] + lp[5][ce + i]);
           }
         }
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.ready);
         dmark(203 + L * 10);
         float4 hp4v[4];  // this thread's 16 columns of h_{t-1}, in flight during the second MMA batch
 #pragma unroll
