@@ -351,15 +351,15 @@ def run_ours(args):
             "roofline": {"kernel": "k_rollout_tc16 (persistent decode kernel: 90 steps x (embed, 9 attention layers, 3 GRU layers, "
                                    "add_goal, add_latent, action head, dynamics/rule-check tail), one 4-CTA cluster per scene-mode)",
                          "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                         "traffic": 11.66e9 if (world == 1 and S == 32) else None,
-                         "traffic_note": "dram read 10.14 GB + write 1.52 GB per launch, ncu --set full (profiles/r1k_k_rollout_tc16.txt: tensor pipe "
-                                         "active 30.6 %, issue active 32 %, L2 hit 67.5 %): the 88 MB of key blocks stream through L2 at every one "
-                                         "of the 90 steps; 550 GB/s = 7 % of HBM peak, the kernel is bound by its serial GEMM -> epilogue chain",
+                         "traffic": 11.64e9 if (world == 1 and S == 32) else None,
+                         "traffic_note": "dram read 10.12 GB + write 1.52 GB per launch, ncu --set full (profiles/r1o_k_rollout_tc16.txt: 17.9 ms, tensor "
+                                         "pipe active 35.3 %, issue active 34.9 %, L2 hit 67.9 %): the 88 MB of key blocks stream through L2 at every "
+                                         "one of the 90 steps; ~650 GB/s = 10 % of HBM peak, the kernel is bound by its serial GEMM -> epilogue chain",
                          "peak_source": peak_src, "flops_per_launch": f_roll,
                          "avg_launch_ms": rollout_ms, "whole_step_tflops": f_total / (ms / args.steps * 1e-3) / 1e12,
                          "whole_step_frac": f_total / (ms / args.steps * 1e-3) / 1e12 / peak_tf,
                          "attention_frac": 4.0 * A * (P + 40 + A) * 128 * 3 * B * T / (rollout_ms * 1e-3) / 1e12 / peak_tf,
-                         "hbm_frac": (11.66e9 / (rollout_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbps", 6553.6)))
+                         "hbm_frac": (11.64e9 / (rollout_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbps", 6553.6)))
                                      if (world == 1 and S == 32) else None,
                          "note": "algorithmic fp32-equivalent FLOPs (SURVEY 8d); the kernel issues 3 bf16 MMAs per logical "
                                  "product (bf16x3) on M=128 tiles holding 64 agents, on 4 x B = 128 of the 148 SMs"},
