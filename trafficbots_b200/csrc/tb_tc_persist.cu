@@ -1739,16 +1739,23 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
       tc::tmem_ld_wait();
     };
     auto ln32 = [&](float (&v)[32], const float* g, const float* bt) {
+      // packed pairs: lanes (0, 1) and (2, 3) of the former four-way accumulators, same order of operations per lane
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < 32; ++i) s4[i & 3] += v[i];
+      for (int i = 0; i < 32; i += 4) {
+        tc::add2(s4[0], s4[1], s4[0], s4[1], v[i], v[i + 1]);
+        tc::add2(s4[2], s4[3], s4[2], s4[3], v[i + 2], v[i + 3]);
+      }
       const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
       const float mloc = sum * (1.0f / 32);
       float q[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float d = v[i] - mloc;
-        q[i & 3] = fmaf(d, d, q[i & 3]);
+      for (int i = 0; i < 32; i += 4) {
+        float d0, d1, d2, d3;
+        tc::sub2(d0, d1, v[i], v[i + 1], mloc, mloc);
+        tc::sub2(d2, d3, v[i + 2], v[i + 3], mloc, mloc);
+        tc::fma2(q[0], q[1], d0, d1, d0, d1, q[0], q[1]);
+        tc::fma2(q[2], q[3], d2, d3, d2, d3, q[2], q[3]);
       }
       const int buf = n_ln & 1;
       ++n_ln;
@@ -1761,7 +1768,11 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
       const float rstd = 1.0f / sqrtf(m2 * (1.0f / 128) + LN_EPS);
       const float nmr = -mean * rstd;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = fmaf(fmaf(v[i], rstd, nmr), g[cq + i], bt[cq + i]);
+      for (int i = 0; i < 32; i += 2) {
+        float t0, t1;
+        tc::fma2(t0, t1, v[i], v[i + 1], rstd, rstd, nmr, nmr);
+        tc::fma2(v[i], v[i + 1], t0, t1, g[cq + i], g[cq + i + 1], bt[cq + i], bt[cq + i + 1]);
+      }
     };
     float4 pf0 = make_float4(0.f, 0.f, 0.f, 0.f);
     auto fetch_params = [&](int p) {
