@@ -215,6 +215,13 @@ __device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, f
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
 }
+__device__ __forceinline__ void mul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  unsigned long long a, b, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
 __device__ __forceinline__ void sub2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
   unsigned long long a, b, d;
   asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));

@@ -1949,7 +1949,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
               float kk[16];
               load_acc16(T_ACC0, kk);  // K[ag, ce .. ce+15]: key row ag
 #pragma unroll
-              for (int i = 0; i < 16; ++i) kk[i] += lp[10][ce + i];
+              for (int i = 0; i < 16; i += 2) tc::add2(kk[i], kk[i + 1], kk[i], kk[i + 1], lp[10][ce + i], lp[10][ce + i + 1]);
 #pragma unroll
               for (int c = 0; c < 2; ++c) {
                 uint4 hi, lo;
@@ -1963,7 +1963,8 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
               const uint32_t kc = (uint32_t)(ag >> 3);
 #pragma unroll
               for (int i = 0; i < 16; i += 2) {
-                const float v0 = kk[i] + lp[11][ce + i], v1 = kk[i + 1] + lp[11][ce + i + 1];
+                float v0, v1;
+                tc::add2(v0, v1, kk[i], kk[i + 1], lp[11][ce + i], lp[11][ce + i + 1]);
                 uint32_t hh, ll;
                 tc::split_pair(v0, v1, hh, ll);
 #pragma unroll
@@ -1999,7 +2000,10 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
             tc::tmem_ld32(tm + (kind == 2 ? T_ACC2 : T_ACC0) + cq, q);
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) q[i] = (q[i] + lp[2][cq + i]) * sc;
+            for (int i = 0; i < 32; i += 2) {
+              tc::add2(q[i], q[i + 1], q[i], q[i + 1], lp[2][cq + i], lp[2][cq + i + 1]);
+              tc::mul2(q[i], q[i + 1], q[i], q[i + 1], sc, sc);
+            }
             float ph[16], pl[16], zz[16];
             tc::split32_packed(q, ph, pl);
 #pragma unroll
@@ -2054,9 +2058,13 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
             const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
             float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              sv_[j] = ex2_approx(sv_[j] + neg_m);
-              ps4[j & 3] += sv_[j];
+            for (int j = 0; j < 32; j += 4) {
+              tc::add2(sv_[j], sv_[j + 1], sv_[j], sv_[j + 1], neg_m, neg_m);
+              tc::add2(sv_[j + 2], sv_[j + 3], sv_[j + 2], sv_[j + 3], neg_m, neg_m);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) sv_[j + e] = ex2_approx(sv_[j + e]);
+              tc::add2(ps4[0], ps4[1], ps4[0], ps4[1], sv_[j], sv_[j + 1]);
+              tc::add2(ps4[2], ps4[3], ps4[2], ps4[3], sv_[j + 2], sv_[j + 3]);
             }
             l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
             {
@@ -2151,10 +2159,8 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
                   for (int r = 0; r < 4; ++r) {
                     if (r < n_cta) {
                       const float4 pv = xp[(r * nq + qq) * WORKERS16 + tid];
-                      mg[qq].x = fmaf(w[r], pv.x, mg[qq].x);
-                      mg[qq].y = fmaf(w[r], pv.y, mg[qq].y);
-                      mg[qq].z = fmaf(w[r], pv.z, mg[qq].z);
-                      mg[qq].w = fmaf(w[r], pv.w, mg[qq].w);
+                      tc::fma2(mg[qq].x, mg[qq].y, w[r], w[r], pv.x, pv.y, mg[qq].x, mg[qq].y);
+                      tc::fma2(mg[qq].z, mg[qq].w, w[r], w[r], pv.z, pv.w, mg[qq].z, mg[qq].w);
                     }
                   }
                   mg[qq].x *= inv, mg[qq].y *= inv, mg[qq].z *= inv, mg[qq].w *= inv;
@@ -2181,7 +2187,12 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
             } else {
               const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) xo_mine[j * MAXA] = o[j] * inv;
+              for (int j = 0; j < 16; j += 2) {
+                float t0, t1;
+                tc::mul2(t0, t1, o[j], o[j + 1], inv, inv);
+                xo_mine[j * MAXA] = t0;
+                xo_mine[(j + 1) * MAXA] = t1;
+              }
             }
           }
           worker_sync16();
@@ -2210,7 +2221,11 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
             float o16[16];
             load_acc16(T_ACC0, o16);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) xs_at(ce + i) += o16[i] + lp[3][ce + i];
+            for (int i = 0; i < 16; i += 2) {
+              float t0, t1;
+              tc::add2(t0, t1, o16[i], o16[i + 1], lp[3][ce + i], lp[3][ce + i + 1]);
+              tc::add2(xs_at(ce + i), xs_at(ce + i + 1), xs_at(ce + i), xs_at(ce + i + 1), t0, t1);
+            }
           }
           worker_sync16();
         } else {
@@ -2225,7 +2240,10 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
         dmark(108 + Lx * 10);
         load_acc(T_ACC0, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + lp[6][cq + i], 0.f);
+        for (int i = 0; i < 32; i += 2) {
+          tc::add2(v[i], v[i + 1], v[i], v[i + 1], lp[6][cq + i], lp[6][cq + i + 1]);
+          v[i] = fmaxf(v[i], 0.f), v[i + 1] = fmaxf(v[i + 1], 0.f);
+        }
         write_A(T_A, v);
         signal_ready();  // -> W2
         dmark(109 + Lx * 10);
@@ -2235,7 +2253,12 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
           float y[16];
           load_acc16(T_ACC0, y);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) xs_at(ce + i) = valid ? xs_at(ce + i) + y[i] + lp[7][ce + i] : 0.f;
+          for (int i = 0; i < 16; i += 2) {
+            float t0, t1;
+            tc::add2(t0, t1, xs_at(ce + i), xs_at(ce + i + 1), y[i], y[i + 1]);
+            tc::add2(t0, t1, t0, t1, lp[7][ce + i], lp[7][ce + i + 1]);
+            xs_at(ce + i) = valid ? t0 : 0.f, xs_at(ce + i + 1) = valid ? t1 : 0.f;
+          }
         }
         ++n_lp;
       }
@@ -2278,9 +2301,14 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm.ready);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float rg = fast_sigmoid(r[i] + lp[0][ce + i] + lp[3][ce + i]);
-            sm.xo[(ce + i) * MAXA + ag] = rg * (rh[i] + lp[5][ce + i]);
+          for (int i = 0; i < 16; i += 2) {
+            float a0, a1, h0, h1;
+            tc::add2(a0, a1, r[i], r[i + 1], lp[0][ce + i], lp[0][ce + i + 1]);
+            tc::add2(a0, a1, a0, a1, lp[3][ce + i], lp[3][ce + i + 1]);
+            tc::add2(h0, h1, rh[i], rh[i + 1], lp[5][ce + i], lp[5][ce + i + 1]);
+            tc::mul2(h0, h1, fast_sigmoid(a0), fast_sigmoid(a1), h0, h1);
+            sm.xo[(ce + i) * MAXA + ag] = h0;
+            sm.xo[(ce + i + 1) * MAXA + ag] = h1;
           }
         }
         dmark(203 + L * 10);
@@ -2299,11 +2327,16 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
             const float hp_[4] = {hp4v[i].x, hp4v[i].y, hp4v[i].z, hp4v[i].w};
             float hn_[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < 4; e += 2) {
               const int c = ce + 4 * i + e;
-              const float zg = fast_sigmoid(z[4 * i + e] + lp[1][c] + lp[4][c]);
-              const float ng = fast_tanh(n[4 * i + e] + lp[2][c] + sm.xo[c * MAXA + ag]);
-              hn_[e] = (1.0f - zg) * ng + zg * hp_[e];
+              float z0, z1, n0, n1;
+              tc::add2(z0, z1, z[4 * i + e], z[4 * i + e + 1], lp[1][c], lp[1][c + 1]);
+              tc::add2(z0, z1, z0, z1, lp[4][c], lp[4][c + 1]);
+              tc::add2(n0, n1, n[4 * i + e], n[4 * i + e + 1], lp[2][c], lp[2][c + 1]);
+              tc::add2(n0, n1, n0, n1, sm.xo[c * MAXA + ag], sm.xo[(c + 1) * MAXA + ag]);
+              const float zg0 = fast_sigmoid(z0), zg1 = fast_sigmoid(z1), ng0 = fast_tanh(n0), ng1 = fast_tanh(n1);
+              hn_[e] = (1.0f - zg0) * ng0 + zg0 * hp_[e];
+              hn_[e + 1] = (1.0f - zg1) * ng1 + zg1 * hp_[e + 1];
             }
             if (live) hid[(ce / 4 + i) * A] = valid ? make_float4(hn_[0], hn_[1], hn_[2], hn_[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -2340,10 +2373,12 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
           load_acc(T_ACC0, h1);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            h1[4 * i] = fmaxf(h1[4 * i] + zq[i].x + lp[0][cq + 4 * i], 0.f);
-            h1[4 * i + 1] = fmaxf(h1[4 * i + 1] + zq[i].y + lp[0][cq + 4 * i + 1], 0.f);
-            h1[4 * i + 2] = fmaxf(h1[4 * i + 2] + zq[i].z + lp[0][cq + 4 * i + 2], 0.f);
-            h1[4 * i + 3] = fmaxf(h1[4 * i + 3] + zq[i].w + lp[0][cq + 4 * i + 3], 0.f);
+            tc::add2(h1[4 * i], h1[4 * i + 1], h1[4 * i], h1[4 * i + 1], zq[i].x, zq[i].y);
+            tc::add2(h1[4 * i + 2], h1[4 * i + 3], h1[4 * i + 2], h1[4 * i + 3], zq[i].z, zq[i].w);
+            tc::add2(h1[4 * i], h1[4 * i + 1], h1[4 * i], h1[4 * i + 1], lp[0][cq + 4 * i], lp[0][cq + 4 * i + 1]);
+            tc::add2(h1[4 * i + 2], h1[4 * i + 3], h1[4 * i + 2], h1[4 * i + 3], lp[0][cq + 4 * i + 2], lp[0][cq + 4 * i + 3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h1[4 * i + e] = fmaxf(h1[4 * i + e], 0.f);
           }
           write_A(T_A, h1);
         }
@@ -2408,8 +2443,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
             for (int i = 0; i < 16; ++i) {
               const float hv = fmaxf(hdn[i] + lp[c3][ce + i], 0.f);
               const int k = ce + i;
-              s0 = fmaf(hv, w2[((k >> 2) * 2 + 0) * 4 + (k & 3)], s0);
-              s1 = fmaf(hv, w2[((k >> 2) * 2 + 1) * 4 + (k & 3)], s1);
+              tc::fma2(s0, s1, hv, hv, w2[((k >> 2) * 2 + 0) * 4 + (k & 3)], w2[((k >> 2) * 2 + 1) * 4 + (k & 3)], s0, s1);
             }
             if (on) {
               m0 += s0;
