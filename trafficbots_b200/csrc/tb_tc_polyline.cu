@@ -105,16 +105,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
   };
   // LayerNorm over the 128 columns of a row held by 4 threads (32 columns each): one exchange of {sum, M2}
   auto ln32 = [&](float (&v)[32], const float* g, const float* bt) {  // g, bt: shared-memory vectors, read after the barrier
-    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};  // packed pairs (FADD2 / FFMA2): lanes (0, 1) and (2, 3) of the four-way accumulators
 #pragma unroll
-    for (int i = 0; i < 32; ++i) s4[i & 3] += v[i];
+    for (int i = 0; i < 32; i += 4) {
+      tc::add2(s4[0], s4[1], s4[0], s4[1], v[i], v[i + 1]);
+      tc::add2(s4[2], s4[3], s4[2], s4[3], v[i + 2], v[i + 3]);
+    }
     const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
     const float mloc = sum * (1.0f / 32);
     float q[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float d = v[i] - mloc;
-      q[i & 3] = fmaf(d, d, q[i & 3]);
+    for (int i = 0; i < 32; i += 4) {
+      float e0, e1, e2, e3;
+      tc::sub2(e0, e1, v[i], v[i + 1], mloc, mloc);
+      tc::sub2(e2, e3, v[i + 2], v[i + 3], mloc, mloc);
+      tc::fma2(q[0], q[1], e0, e1, e0, e1, q[0], q[1]);
+      tc::fma2(q[2], q[3], e2, e3, e2, e3, q[2], q[3]);
     }
     const int buf = n_ln & 1;
     ++n_ln;
@@ -126,7 +132,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
     const float m2 = ((p0.y + p1.y) + (p2.y + p3.y)) + 32.0f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));  // Chan
     const float rstd = 1.0f / sqrtf(m2 * (1.0f / 128) + LN_EPS);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd * g[c0 + i] + bt[c0 + i];
+    for (int i = 0; i < 32; i += 2) {
+      float t0, t1;
+      tc::sub2(t0, t1, v[i], v[i + 1], mean, mean);
+      tc::mul2(t0, t1, t0, t1, rstd, rstd);
+      tc::fma2(v[i], v[i + 1], t0, t1, g[c0 + i], g[c0 + i + 1], bt[c0 + i], bt[c0 + i + 1]);
+    }
   };
   auto write_A = [&](const float (&v)[32]) {
     float ph[16], pl[16];
@@ -270,8 +281,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
 #pragma unroll
           for (int i = 0; i < 8; i += 2) {
             const float4 k4 = reinterpret_cast<const float4*>(kr)[i], k5 = reinterpret_cast<const float4*>(kr)[i + 1];
-            a0 = fmaf(t[4 * i + 3], k4.w, fmaf(t[4 * i + 2], k4.z, fmaf(t[4 * i + 1], k4.y, fmaf(t[4 * i], k4.x, a0))));
-            a1 = fmaf(t[4 * i + 7], k5.w, fmaf(t[4 * i + 6], k5.z, fmaf(t[4 * i + 5], k5.y, fmaf(t[4 * i + 4], k5.x, a1))));
+            tc::fma2(a0, a1, t[4 * i], t[4 * i + 4], k4.x, k5.x, a0, a1);  // two independent chains, one packed FMA per step
+            tc::fma2(a0, a1, t[4 * i + 1], t[4 * i + 5], k4.y, k5.y, a0, a1);
+            tc::fma2(a0, a1, t[4 * i + 2], t[4 * i + 6], k4.z, k5.z, a0, a1);
+            tc::fma2(a0, a1, t[4 * i + 3], t[4 * i + 7], k4.w, k5.w, a0, a1);
           }
           pj[j] = sm.row_valid[p * N + j] ? (a0 + a1) * 0.17677669529663687f : -INFINITY;
           mx = fmaxf(mx, pj[j]);
@@ -308,10 +321,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 v4 = reinterpret_cast<const float4*>(vr)[i];
-            t[4 * i] = fmaf(pj[j], v4.x, t[4 * i]);
-            t[4 * i + 1] = fmaf(pj[j], v4.y, t[4 * i + 1]);
-            t[4 * i + 2] = fmaf(pj[j], v4.z, t[4 * i + 2]);
-            t[4 * i + 3] = fmaf(pj[j], v4.w, t[4 * i + 3]);
+            tc::fma2(t[4 * i], t[4 * i + 1], pj[j], pj[j], v4.x, v4.y, t[4 * i], t[4 * i + 1]);
+            tc::fma2(t[4 * i + 2], t[4 * i + 3], pj[j], pj[j], v4.z, v4.w, t[4 * i + 2], t[4 * i + 3]);
           }
         }
 #pragma unroll
