@@ -60,6 +60,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifndef TB_WATCHDOG_CYCLES
+#define TB_WATCHDOG_CYCLES 4000000000LL  // ~2 s; raise it (-DTB_WATCHDOG_CYCLES=...) under tools that slow kernels by orders of magnitude
+#endif
 // Bounded wait: a protocol bug must trap (fail the launch) instead of hanging the GPU.  The poll carries a suspend-time hint, so
 // a waiting warp sleeps in hardware until the phase completes instead of spinning: measured on the decode kernel against a
 // plain try_wait spin, -2.4 % step time (spinning roles steal issue / shared-memory slots from the working warps; a
@@ -79,7 +82,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait_hint(bar, parity, 1000000u))
-    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: far beyond any legitimate wait
+    if (clock64() - t0 > TB_WATCHDOG_CYCLES) __trap();  // ~2 s: far beyond any legitimate wait
 }
 
 // ---- bulk async copy global -> shared (TMA linear mode), completes `bytes` on the mbarrier ---------------------------
