@@ -1,12 +1,22 @@
 """Benchmark of the TrafficBots hot path on B200 (contract: see the task statement / DESIGN.md "Measurement").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|4] [--depth D]
 
 One "step" = one pass of the hot path over one batch of synthetic scenes (a "scene" = encode + prior
 latent + destination prediction + K rollouts): scene encoding (`tb_encode_scene`), the pre-rollout heads (prior latent
-encoder, destination predictor) and the 90-step closed-loop rollout of every scene-mode (`tb_rollout`).  Workload at N=1 = BASELINE.json
-configs[1]: 32 scenes, 64 agents, 1024 map polylines, 91 frames, K=1.  With N>1 GPUs every rank processes its
-own batch of 32 scenes (scene sharding, weak scaling, no data-path collective).
+encoder, destination predictor) and the 90-step closed-loop rollout of every scene-mode (`tb_rollout`).
+
+`--config` selects the BASELINE.json configuration (1-based index into `configs`, default 1):
+  1  batch = 32 scenes, 64 agents, 1024 polylines, K = 1 (the configuration the metric is quoted on)
+  2  the per-GPU slice of configs[2]: 32 scenes x K = 6 sampled modes (256 scenes over 8 GPUs)
+  4  the stress shape: 148 scenes x 128 agents x 2048 polylines
+With N > 1 GPUs every rank processes its own batches (scene sharding, weak scaling, no data-path collective; the metrics
+table of every batch is all-gathered over NCCL on a side stream).
+
+Schedule: the eval loop is a stream of independent batches, so `depth` batches are kept in flight on separate CUDA streams
+(`trafficbots_b200.pipeline.ScenePipeline`; 1-CTA clusters in the decode kernel): K timed steps = K batches submitted round
+robin, timed from the first submission to the completion of the last one.  `--depth 1` is the round-1 schedule (one batch
+at a time, 4-CTA clusters).
 
 `--impl reference` times the reference's CPU implementation of the same path (the oracle port,
 `oracle/trafficbots_oracle.py`, which is pinned to the unmodified reference) on the host cores.
@@ -30,15 +40,23 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 import torch  # noqa: E402
 
 METRIC = "scenes/sec (64 agents, 91-step closed-loop rollout)"
-WORKLOAD = dict(n_scene=32, n_agent=64, n_pl=1024, n_mode=1, n_step=90)
+CONFIGS = {
+    1: dict(n_scene=32, n_agent=64, n_pl=1024, n_mode=1, n_step=90, depth=6, cpu_scenes=32,
+            name="BASELINE.json configs[1]: batch = 32 scenes, 64 agents, 1024 map polylines, 91 frames, K = 1"),
+    2: dict(n_scene=32, n_agent=64, n_pl=1024, n_mode=6, n_step=90, depth=2, cpu_scenes=6,
+            name="BASELINE.json configs[2], per-GPU slice: 32 scenes x K = 6 sampled joint futures (256 scenes over 8 GPUs)"),
+    4: dict(n_scene=148, n_agent=128, n_pl=2048, n_mode=1, n_step=90, depth=2, cpu_scenes=4,
+            name="BASELINE.json configs[4], stress: 148 scenes x 128 agents x 2048 map polylines, K = 1"),
+}
+WORKLOAD = CONFIGS[1]  # tools/ import this name
 
 
 # ----------------------------------------------------------------------------------------------------------
 # algorithmic work, D = F = 128
 # ----------------------------------------------------------------------------------------------------------
 def flops_front(A, P, TL, D=128):
-    """k_step_front per scene-mode and step: agent encoder + 3 agent->map layers + 3 agent->TL layers (their K|V are
-    pre-projected) + the interaction K|V projection of the step."""
+    """per scene-mode and step: agent encoder + 3 agent->map layers + 3 agent->TL layers (their K|V are pre-projected)
+    + the interaction K|V projection of the step."""
     enc = 2 * A * (11 * 32 + 32 * 32)
     as2pl = 3 * (4 * A * D * D + 4 * A * P * D + 4 * A * D * D)
     as2tl = 3 * (4 * A * D * D + 4 * A * TL * D + 4 * A * D * D)
@@ -126,7 +144,8 @@ USED_KEYS = ("map/valid", "map/type", "map/pos", "map/dir", "map/boundary", "age
 
 def run_step(eng, cb, ex, n_mode, n_step, out=None):
     """device-resident step through the thin C-ABI driver: encode -> prior latent -> destination -> rollout.  With K = 1
-    the single mode is the deterministic one (prior mean, arg-max destination: waymo_motion.py:489-500)."""
+    the single mode is the deterministic one (prior mean, arg-max destination: waymo_motion.py:489-500).  (K = 1 only;
+    tools/ and tests use it -- the bench arms go through the public `WaymoMotion` surface.)"""
     from trafficbots_b200 import engine as E, host
     feat = eng.encode_scene(cb)
     lat_mean, _ = eng.latent_encoder(feat)
@@ -140,7 +159,7 @@ def run_step(eng, cb, ex, n_mode, n_step, out=None):
                        goal_valid, cb["agent/goal"], n_mode=n_mode, n_step=n_step, out=out)
 
 
-def run_step_public(module, cb, ex):
+def run_step_public(module, cb, ex=None):
     """the call sequence a user of the reference makes (validation_step's joint_future_pred leg, waymo_motion.py:581-598)
     through the `WaymoMotion` surface: encode_input_features -> latent_encoder -> pred_goal -> joint_future_pred."""
     feat = module.model.encode_input_features(cb)
@@ -152,20 +171,18 @@ def run_step_public(module, cb, ex):
 
 
 # ----------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(n_scene, repeats=1, seed=1234):
-    """the oracle port of the reference's CPU path (encode_scene + latent prior + destination predictor + rollout as the
-    reference implements them: K|V re-projected every step) on `n_scene` scenes of the bench workload; returns scenes/s
-    and seconds."""
+def cpu_reference_rate(cfg, n_scene, repeats=1, seed=1234):
+    """the oracle port of the reference's CPU path (encode_scene + latent prior + destination predictor + K rollouts as the
+    reference implements them: K|V re-projected every step) on `n_scene` scenes of the workload; returns scenes/s and s."""
     import trafficbots_oracle as orc
     from trafficbots_b200 import weights
-    W = WORKLOAD
     sd = weights.init_state_dict(2023)
-    batch, _ = make_inputs(n_scene, W["n_agent"], W["n_pl"], 1, seed)
+    batch, _ = make_inputs(n_scene, cfg["n_agent"], cfg["n_pl"], 1, seed)
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        with torch.no_grad():  # encode -> prior latent -> destination predictor -> rollout (K = 1: the deterministic mode)
-            orc.joint_future_pred(sd, batch, k=1, sample_seed=0, step_end=W["n_step"])
+        with torch.no_grad():  # encode -> prior latent -> destination predictor -> K rollouts (mode 0 deterministic)
+            orc.joint_future_pred(sd, batch, k=cfg["n_mode"], sample_seed=0, step_end=cfg["n_step"])
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return n_scene / best, best
@@ -175,26 +192,32 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cfg = CONFIGS[args.config]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    # size the per-step sample so that (steps + warmup) samples finish in ~2 minutes
-    rate1, t1 = cpu_reference_rate(1)
-    budget = 120.0 / max(1, args.steps + args.warmup)
-    n = int(max(1, min(WORKLOAD["n_scene"], budget / max(t1, 1e-3) * 0.8)))
+    # every step = the FULL batch of the GPU arm when (steps + warmup) such passes fit ~15 minutes on this host (config 1 on
+    # 16 cores: 7.3 s per pass); otherwise a bounded sample of the batch, and the line says so
+    _, t1 = cpu_reference_rate(cfg, 1)
+    passes = max(1, args.steps + args.warmup)
+    budget = 900.0 / passes
+    full = cfg["n_scene"]
+    n = full if t1 * full * 0.6 <= budget else int(max(1, min(full, budget / max(t1, 1e-3))))
     for _ in range(args.warmup):
-        cpu_reference_rate(n)
+        cpu_reference_rate(cfg, n)
     times = []
     for _ in range(args.steps):
-        _, dt = cpu_reference_rate(n)
+        _, dt = cpu_reference_rate(cfg, n)
         times.append(dt)
     total = sum(times)
     value = n * args.steps / total
+    sample = (f"the full {full}-scene batch per step" if n == full else f"{n} scenes per step (bounded sample of the {full}-scene batch)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{n} scenes/step (bounded sample of the 32-scene batch), 64 agents, 1024 polylines, K=1, "
-                               "encode + prior latent + destination predictor + 90-step closed-loop rollout, reference CPU algorithm (oracle port)"},
+        "config": {"workload": f"{cfg['name']}; {sample}; encode + prior latent + destination predictor + K x {cfg['n_step']}-step "
+                               "closed-loop rollout, reference CPU algorithm (oracle port, pinned to the unmodified reference)",
+                   "baseline_config": args.config, "scenes_per_step": n},
         "cpu_baseline": {"value": value, "unit": "scenes/s", "cores": cores, "kind": "port",
                          "sample": f"{n} scenes x {args.steps} steps, torch {torch.__version__} CPU fp32, {cores} threads"},
         "e2e": {"value": value, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -203,9 +226,83 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------------
+def load_traffic(config_id, depth):
+    """dram traffic of the dominant kernel per launch, from the committed ncu capture of THIS build's kernel
+    (profiles/traffic.json, written by tools/ncu_summary.py --traffic from a `ncu --set full` report)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+    except (OSError, ValueError):
+        return None, None
+    e = t.get(f"config{config_id}")
+    if not e:
+        return None, None
+    return float(e["dram_bytes_read"]) + float(e["dram_bytes_write"]), e
+
+
+def time_decode_kernels(pipe_slots, module, cbs, cfg, flush, repeats=3):
+    """The dominant kernel in the regime it runs in: one persistent decode launch (`tb_rollout_steps(1..T)`) per in-flight
+    batch, all `depth` launches started together on their streams; returns (span ms from the common start to the last
+    completion, mean duration of the individual launches).  `tb_rollout_init`, encoding and the heads run before the
+    timed region; L2 is flushed before every repeat."""
+    from trafficbots_b200 import engine as E
+    dev = pipe_slots[0].eng.device
+    main = torch.cuda.current_stream(dev)
+    ctxs = []
+    K, T = cfg["n_mode"], cfg["n_step"]
+    for slot, cb in zip(pipe_slots, cbs):
+        with torch.cuda.stream(slot.stream):
+            module.use_engine(slot.eng)
+            try:
+                feat = module.model.encode_input_features(cb)
+                latent = module.model.latent_encoder(**feat)
+                goal = module.model.goal_manager.pred_goal(agent_type=cb["agent/type"], map_type=cb["map/type"], agent_state=None, **feat)
+            finally:
+                module.use_engine(None)
+            S, A = cb["history/agent/valid"].shape[0], cb["history/agent/valid"].shape[2]
+            lat = latent.mean.repeat_interleave(K, 0).contiguous()
+            dest = goal.probs.argmax(-1).repeat_interleave(K, 0).contiguous()
+            gt = E.gt_from_batch(cb)
+            tf = module.teacher_forcing_joint_future_pred.get(gt["valid"], 0)
+            gv = cb["history/agent/valid"].any(1).repeat_interleave(K, 0).contiguous()
+            ctx = slot.eng.begin_rollout(feat, gt, tf, cb["agent/type"], cb["agent/size"], E.raw_map_from_batch(cb), lat,
+                                         torch.zeros(S * K, A, device=dev), dest, gv, cb["agent/goal"], n_mode=K, n_step=T)
+            ctxs.append(ctx)
+    torch.cuda.synchronize(dev)
+    spans, singles = [], []
+    for _ in range(repeats):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        per = []
+        e0.record(main)
+        for slot, ctx in zip(pipe_slots, ctxs):
+            slot.stream.wait_event(e0)
+            with torch.cuda.stream(slot.stream):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                slot.eng.last_t = 0
+                slot.eng.steps(ctx, 1, T)
+                b.record()
+                per.append((a, b))
+        for slot in pipe_slots:
+            main.wait_stream(slot.stream)
+        e1.record(main)
+        torch.cuda.synchronize(dev)
+        spans.append(e0.elapsed_time(e1))
+        singles.append(sum(a.elapsed_time(b) for a, b in per) / len(per))
+        # re-arm: the next repeat starts from the initial state again
+        for slot, ctx in zip(pipe_slots, ctxs):
+            with torch.cuda.stream(slot.stream):
+                slot.eng.reinit(ctx)
+        torch.cuda.synchronize(dev)
+    return sum(spans) / len(spans), sum(singles) / len(singles)
+
+
 def run_ours(args):
     import torch.distributed as dist
-    from trafficbots_b200 import _native as nt, engine as E, host, weights
+    from trafficbots_b200 import config as tb_config, host, parallel, weights
+    from trafficbots_b200.pipeline import ScenePipeline, joint_future_step
+    from trafficbots_b200.pl_modules.waymo_motion import WaymoMotion
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -220,95 +317,125 @@ def run_ours(args):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
-    W = WORKLOAD
-    S, A, P, K, T = W["n_scene"], W["n_agent"], W["n_pl"], W["n_mode"], W["n_step"]
+    cfg = CONFIGS[args.config]
+    S, A, P, K, T = cfg["n_scene"], cfg["n_agent"], cfg["n_pl"], cfg["n_mode"], cfg["n_step"]
+    depth = args.depth if args.depth > 0 else cfg["depth"]
+    steps, warmup = args.steps, max(args.warmup, 3)
     sd = weights.init_state_dict(2023)
-    eng = E.Engine(sd, dev)
-    batch, ex = make_inputs(S, A, P, K, seed=1000 + 100 * rank)
-    host_batch = host.pin_batch({k: batch[k] for k in USED_KEYS})
-    cb = host.batch_to_device(host_batch, dev)
-    cex = {"latent_logp": torch.zeros(S * K, A, device=dev)}  # log-prob of the deterministic latent: not part of the timed math
-    out = eng.alloc_outputs(S * K, A, T)
+    module = WaymoMotion(**tb_config.default_config(n_joint_future=K))
+    module.load_state_dict(sd)
+    module = module.to(dev).eval()
+    eng = module.engine()
+    torch.manual_seed(1234 + rank)
+
+    # `depth` distinct synthetic batches (pinned host + resident device copies), used round robin
+    n_distinct = max(depth, 2)
+    host_batches, dev_batches = [], []
+    for i in range(n_distinct):
+        batch, _ = make_inputs(S, A, P, K, seed=1000 + 100 * rank + i)
+        hb = host.pin_batch({k: batch[k] for k in USED_KEYS})
+        host_batches.append(hb)
+        dev_batches.append(host.batch_to_device(hb, dev))
+    h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    h2d = sum(v.numel() * v.element_size() for v in host_batch.values())
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput ---------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        run_step(eng, cb, cex, K, T, out)
+    def run_batches(pipe, batches, n):
+        """n batches through the pipeline, collecting each result `depth` submissions later (steady state: `depth` in flight)."""
+        tickets = []
+        for i in range(n):
+            if i >= pipe.depth:
+                pipe.result(tickets[i - pipe.depth])
+            tickets.append(pipe.submit(batches[i % len(batches)]))
+        for t in tickets[max(0, n - pipe.depth):]:
+            pipe.result(t)
+
+    # ---- device-resident throughput: inputs already in HBM, results stay in HBM -------------------------------------
+    pipe = ScenePipeline(module, depth=depth, read_back=False)
+    run_batches(pipe, dev_batches, max(warmup, depth))
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     n0 = eng.lib.tb_launch_count()
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)  # evict L2 between timed iterations
-        ev[i][0].record()
-        run_step(eng, cb, cex, K, T, out)
-        ev[i][1].record()
+    flush.fill_(0)  # cold L2 at the start; afterwards the in-flight batches' own working set (> L2) evicts it continuously
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in pipe.slots:
+        s.stream.wait_event(e0)
+    run_batches(pipe, dev_batches, steps)
+    for s in pipe.slots:
+        torch.cuda.current_stream().wait_stream(s.stream)
+    e1.record()
     barrier()
     launches = eng.lib.tb_launch_count() - n0
-    ms = sum(a.elapsed_time(b) for a, b in ev)
+    ms = e0.elapsed_time(e1)
+    lat_dev = sorted(pipe.latencies[-steps:])
 
-    # ---- end to end: pinned host buffers in, results back to the host, through the same public call ---------
-    from trafficbots_b200 import config as tb_config, parallel
-    from trafficbots_b200.pl_modules.waymo_motion import WaymoMotion
-    module = WaymoMotion(**tb_config.default_config(n_joint_future=K))
-    module.load_state_dict(sd)
-    module = module.to(dev).eval()
-    host_res = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items() if not k.startswith("_")}
-    host_res["violations"] = torch.empty(6, S * K, A, T, dtype=torch.bool).pin_memory()
-    d2h = sum(v.numel() * v.element_size() for v in host_res.values())
+    # ---- end to end: pinned host buffers in, every result tensor back to pinned host memory, same public calls --------
+    comm = torch.cuda.Stream(dev) if world > 1 else None
+    gathered = []
 
-    stager = host.SceneStager(dev)
+    def step_fn(mod, cb):
+        out = joint_future_step(mod, cb)
+        if world > 1:  # the metrics reduction of this batch: packed per-scene table, all-gathered on the side stream below
+            out["_metrics"] = parallel.pack_scene_metrics(out["preds"], out["valid"], {k[11:]: v for k, v in out.items() if k.startswith("violations/")},
+                                                          out["diffbar_rewards"], cb["agent/pos"], cb["agent/valid"])
+        return out
 
-    def e2e_step(last):
-        cbe = stager.get()  # this step's inputs: pinned host -> device, queued on the staging stream
-        stager.submit(host_batch)  # the next step's inputs travel while this step computes (one copy per step, steady state)
-        buf = run_step_public(module, cbe, None)  # RolloutBuffer after flatten_repeat: [S, A, K, T, ...]
-        pairs = [(host_res[name], getattr(buf, name).squeeze(2)) for name in
-                 ("preds", "valid", "override_masks", "diffbar_rewards", "diffbar_rewards_valid", "action_log_probs",
-                  "latent_log_probs")]
-        pairs += [(host_res["violations"][i], buf.violations[name].squeeze(2)) for i, name in enumerate(E.VIOLATION_KEYS)]
-        stager.read_back(pairs)  # results -> pinned host, overlapping the next step's kernels
-        if world > 1:  # the metrics reduction: one packed all-gather per step
-            local = parallel.pack_scene_metrics(buf.preds, buf.valid, buf.violations, buf.diffbar_rewards, cbe["agent/pos"],
-                                                cbe["agent/valid"])
-            parallel.all_gather_scenes(local, world * S)
-        if last:
-            stager.join()  # the last step's read-back (and the copy it started) end inside its timed region
-        return buf
-    stager.submit(host_batch)
-    for i in range(2):
-        e2e_step(False)
+    pipe2 = ScenePipeline(module, depth=depth, step_fn=step_fn, read_back=True)
+
+    def run_e2e(n):
+        tickets = []
+
+        def collect(t):
+            slot = pipe2.slot_of(t)
+            if world > 1:  # NCCL calls are issued in batch order on ONE side stream on every rank; compute streams never wait for them
+                comm.wait_event(slot.done)
+                with torch.cuda.stream(comm):
+                    gathered.append(parallel.all_gather_scenes(slot.keep["_metrics"], world * S))
+            pipe2.result(t)
+
+        for i in range(n):
+            if i >= depth:
+                collect(tickets[i - depth])
+            tickets.append(pipe2.submit(host_batches[i % len(host_batches)]))
+        for t in tickets[max(0, n - depth):]:
+            collect(t)
+        if world > 1:
+            torch.cuda.current_stream().wait_stream(comm)
+
+    run_e2e(max(3, depth))
+    gathered.clear()
     barrier()
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    flush.fill_(0)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)
-        ev2[i][0].record()
-        e2e_step(i == args.steps - 1)
-        ev2[i][1].record()
+    f0.record()
+    for s in pipe2.slots:
+        s.stream.wait_event(f0)
+    run_e2e(steps)
+    for s in pipe2.slots:
+        torch.cuda.current_stream().wait_stream(s.stream)
+    f1.record()
     barrier()
     wall_e2e = time.perf_counter() - t_wall0
-    ms_e2e = sum(a.elapsed_time(b) for a, b in ev2)
+    ms_e2e = f0.elapsed_time(f1)
+    lat_e2e = sorted(pipe2.latencies[-steps:])
+    d2h = pipe2.d2h_bytes()
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- dominant kernel: the persistent decode kernel (all 90 steps of every scene-mode in ONE launch), timed alone ---
-    feat = eng.encode_scene(cb)
-    gt = E.gt_from_batch(cb)
-    tf = host.teacher_forcing_mask(gt["valid"], 10, 10)
-    lat_mean, _ = eng.latent_encoder(feat)
-    dest = eng.dest_predictor(feat, cb["agent/type"], cb["map/type"])[0].argmax(-1)
-    rollout_ms = eng.profile_rollout(feat, gt, tf, cb["agent/type"], cb["agent/size"], E.raw_map_from_batch(cb),
-                                     lat_mean, cex["latent_logp"], dest, cb["history/agent/valid"].any(1),
-                                     cb["agent/goal"], n_mode=K, n_step=T, out=out)
-    torch.cuda.synchronize()
+    # ---- dominant kernel: the persistent decode kernel, `depth` launches in flight as in the timed region -----------
+    persistent = A <= 64
+    span_ms = single_ms = None
+    if persistent:
+        # as many launches as are co-resident in the timed region: one CTA per scene-mode and SM
+        n_conc = max(1, min(depth, 148 // (S * K)))
+        span_ms, single_ms = time_decode_kernels(pipe.slots[:n_conc], module, dev_batches, cfg, flush)
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -323,50 +450,69 @@ def run_ours(args):
         except OSError:
             pass
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+        hbm_gbs = float(peaks.get("hbm_gbs", 6500.0))
+        peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained (the kernel runs inside a long step)" if peaks
+                    else "fallback of B200_PROFILING.md: 1.4 PFLOP/s sustained dense bf16")
         B = S * K
-        f_roll = (flops_front(A, P, 40) + flops_back(A)) * B * T  # per launch: all scene-modes of this rank, all steps
-        ach = f_roll / (rollout_ms * 1e-3) / 1e12
-        f_total = (flops_front(A, P, 40) + flops_back(A)) * B * T + flops_map_encoder(P) * S
-        # CPU baseline: the oracle port on a bounded sample (about 10-30 s of CPU work)
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        n_cpu = 32  # the whole batch of the GPU arm: ~10 s on 16 cores
-        if world == 1:
-            cpu_rate, cpu_s = cpu_reference_rate(n_cpu)
+        f_launch = (flops_front(A, P, 40) + flops_back(A)) * B * T  # one decode launch: all scene-modes of a batch, all steps
+        f_total = f_launch + flops_map_encoder(P) * S
+        ms_step = ms / steps
+        roof = {"bound": "tensor", "peak": peak_tf, "unit": "TFLOP/s", "peak_source": peak_src, "flops_per_launch": f_launch,
+                "whole_step_tflops": f_total / (ms_step * 1e-3) / 1e12, "whole_step_frac": f_total / (ms_step * 1e-3) / 1e12 / peak_tf,
+                "note": "algorithmic fp32-equivalent FLOPs (SURVEY 8d: K|V projected once per scene, mlp_in hoisted); the kernel issues 3 "
+                        "bf16 MMAs per logical product (bf16x3) on M = 128 tiles holding 64 agents"}
+        if persistent:
+            traffic, tsrc = load_traffic(args.config, depth)
+            ach = n_conc * f_launch / (span_ms * 1e-3) / 1e12
+            roof.update({
+                "kernel": f"k_rollout_tc16 (persistent decode kernel: {T} steps x (embed, 9 attention layers, 3 GRU layers, add_goal, "
+                          f"add_latent, action head, dynamics / rule-check tail); one CTA per scene-mode, {n_conc} launches of {B} CTAs "
+                          "co-resident on separate streams as in the timed region)",
+                "achieved": ach, "frac": ach / peak_tf, "launches_in_flight": n_conc, "avg_launch_ms": single_ms,
+                "concurrent_span_ms": span_ms,
+                "achieved_definition": "launches_in_flight x flops_per_launch / span from the common start to the last completion (CUDA "
+                                       "events on the launching streams, L2 flushed before each repeat); avg_launch_ms is the mean "
+                                       "duration of one of the concurrent launches",
+                "attention_frac": n_conc * 4.0 * A * (P + 40 + A) * 128 * 3 * B * T / (span_ms * 1e-3) / 1e12 / peak_tf,
+                "traffic": traffic, "traffic_source": tsrc,
+                "hbm_frac": (traffic / (single_ms * 1e-3) / 1e9 * n_conc / hbm_gbs) if traffic else None})
+        else:
+            roof.update({"kernel": "k_step_front_tc + k_step_back (two-kernel path for 64 < n_agent <= 128): whole-step figures only",
+                         "achieved": roof["whole_step_tflops"], "frac": roof["whole_step_frac"], "traffic": None})
+        cpu = None
+        if world == 1:  # CPU baseline: the oracle port on a bounded sample, timed at N = 1 only
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            n_cpu = cfg["cpu_scenes"]
+            cpu_rate, cpu_s = cpu_reference_rate(cfg, n_cpu)
+            cpu = {"value": cpu_rate, "unit": "scenes/s", "cores": cores, "kind": "port",
+                   "sample": f"{n_cpu} scenes of the same workload (K = {K}), 1 pass ({cpu_s:.1f} s), torch CPU fp32"}
+        med = lambda xs: xs[len(xs) // 2] if xs else None  # noqa: E731
         line = {
-            "metric": METRIC, "value": world * S * args.steps / (ms * 1e-3), "unit": "scenes/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "metric": METRIC, "value": world * S * steps / (ms * 1e-3), "unit": "scenes/s", "n_gpus": world,
+            "steps": steps, "warmup": max(warmup, depth), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (bf16x3 split operands on tcgen05, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": f"{S} scenes/GPU/step, {A} agents, {P} map polylines, 40 TL, K={K}, encode_scene + {T}-step "
-                                   "closed-loop rollout (BASELINE.json configs[1]), incl. the pre-rollout heads (prior latent encoder, "
-                                   "destination predictor; the K = 1 mode is the deterministic one)",
-                       "l2": "256 MiB flush write between timed iterations", "timing": "CUDA events per step, summed, max over ranks",
-                       "e2e_staging": "double-buffered (host.SceneStager): the pinned-host -> device copy of step i+1 and the device -> "
-                                      "pinned-host read-back of step i-1 run on a side stream under step i's kernels; every step's "
-                                      "copies are issued and completed inside the timed steps",
+            "config": {"workload": f"{cfg['name']}; per step and GPU: {S} scenes x K = {K}, {A} agents, {P} map polylines, 40 TL: encode_scene + "
+                                   f"prior latent encoder + destination predictor + {T}-step closed-loop rollout (with K = 1 the mode is the "
+                                   "deterministic one)",
+                       "baseline_config": args.config, "in_flight_depth": depth, "scene_modes_per_step": B,
+                       "schedule": f"{depth} batches in flight on {depth} CUDA streams (ScenePipeline), each with its own engine state; decode "
+                                   f"kernel with {pipe.rollout_cluster or 'library-chosen'} CTA(s) per scene-mode; K timed steps = K batches "
+                                   "submitted round robin, timed from the first submission to the last completion",
+                       "batch_latency_ms": {"device_resident_median": med(lat_dev), "device_resident_max": lat_dev[-1] if lat_dev else None,
+                                            "e2e_median": med(lat_e2e), "e2e_max": lat_e2e[-1] if lat_e2e else None},
+                       "l2": f"inputs larger than L2: the {depth} in-flight batches keep {depth} x ~{(2 * 3 * S * P * 256 * 4 + 3 * S * P * 1024) >> 20} MiB of K|V caches "
+                             "+ features live (126 MB L2); one 256 MiB flush write before the timed region",
+                       "timing": "CUDA events around the K steps on the launching stream (all slot streams fork from / join into it), "
+                                 "barrier + synchronize on both sides, max over ranks",
+                       "e2e_staging": "every batch: pinned host -> device copy, the step, device -> pinned host read-back of all result "
+                                      "tensors, queued on the batch's own stream inside the timed region (copies overlap other slots' kernels)",
                        "weights": "seeded random init (no checkpoint distributable)"},
-            "e2e": {"value": world * S * args.steps / (ms_e2e * 1e-3), "unit": "scenes/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": 1e3 * wall_e2e / args.steps},
+            "e2e": {"value": world * S * steps / (ms_e2e * 1e-3), "unit": "scenes/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / steps, "wall_ms_per_step": 1e3 * wall_e2e / steps},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "k_rollout_tc16 (persistent decode kernel: 90 steps x (embed, 9 attention layers, 3 GRU layers, "
-                                   "add_goal, add_latent, action head, dynamics/rule-check tail), one 4-CTA cluster per scene-mode)",
-                         "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                         "traffic": 11.64e9 if (world == 1 and S == 32) else None,
-                         "traffic_note": "dram read 10.12 GB + write 1.52 GB per launch, ncu --set full (profiles/r1o_k_rollout_tc16.txt: 17.9 ms, tensor "
-                                         "pipe active 35.3 %, issue active 34.9 %, L2 hit 67.9 %): the 88 MB of key blocks stream through L2 at every "
-                                         "one of the 90 steps; ~650 GB/s = 10 % of HBM peak, the kernel is bound by its serial GEMM -> epilogue chain",
-                         "peak_source": peak_src, "flops_per_launch": f_roll,
-                         "avg_launch_ms": rollout_ms, "whole_step_tflops": f_total / (ms / args.steps * 1e-3) / 1e12,
-                         "whole_step_frac": f_total / (ms / args.steps * 1e-3) / 1e12 / peak_tf,
-                         "attention_frac": 4.0 * A * (P + 40 + A) * 128 * 3 * B * T / (rollout_ms * 1e-3) / 1e12 / peak_tf,
-                         "hbm_frac": (11.64e9 / (rollout_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbps", 6553.6)))
-                                     if (world == 1 and S == 32) else None,
-                         "note": "algorithmic fp32-equivalent FLOPs (SURVEY 8d); the kernel issues 3 bf16 MMAs per logical "
-                                 "product (bf16x3) on M=128 tiles holding 64 agents, on 4 x B = 128 of the 148 SMs"},
-            "cpu_baseline": ({"value": cpu_rate, "unit": "scenes/s", "cores": cores, "kind": "port",
-                              "sample": f"{n_cpu} scenes of the same workload, 1 pass ({cpu_s:.1f} s), torch CPU fp32"}
-                             if world == 1 else None),  # timed at N = 1 only
+            "roofline": roof,
+            "cpu_baseline": cpu,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -377,11 +523,18 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None, help="default: 24 (ours), 3 (reference: one full batch per step)")
+    ap.add_argument("--warmup", type=int, default=None, help="default: 6 (ours), 1 (reference)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS))
+    ap.add_argument("--depth", type=int, default=0, help="batches in flight (0 = the configuration's default)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    ref = args.impl == "reference"
+    if args.steps is None:
+        args.steps = 3 if ref else 24
+    if args.warmup is None:
+        args.warmup = 1 if ref else 6
+    if ref:
         run_reference(args)
     else:
         run_ours(args)

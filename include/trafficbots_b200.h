@@ -10,10 +10,13 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless it says "host"; all tensors are dense, row-major, in the
  *     reference's batch schema (`data_modules/data_h5_womd.py:85-173`); `bool` tensors are 1 byte per element.
- *   - the caller owns and allocates every buffer; the library keeps no global mutable state and never
+ *   - the caller owns and allocates every buffer; the library keeps no global mutable state that affects results (a launch
+ *     counter for diagnostics, `tb_launch_count`, is the only process-wide variable) and never
  *     allocates device memory; every call is asynchronous on the `stream` argument (a `cudaStream_t`).
  *   - return value: TB_OK or a negative tb_status; nothing is thrown across the ABI.
- *   - all arithmetic is fp32 (the reference's eval-mode dtype).
+ *   - inputs, outputs and accumulation are fp32 (the reference's eval-mode dtype); contractions on the tensor pipe use
+ *     bf16x3 split operands (x = hi + lo, three bf16 MMAs per product, fp32 accumulate in tensor memory): ~2^-17 relative
+ *     error per product; the 90-step closed loop stays within 2e-3 m of the fp32 reference (tests/test_gpu_parity.py).
  */
 #ifndef TRAFFICBOTS_B200_H_
 #define TRAFFICBOTS_B200_H_
@@ -54,6 +57,10 @@ typedef struct TbDims {
   int32_t n_step_hist; /* history frames = time_step_current + 1 (11); also the number of TL frames */
   int32_t n_step_gt;   /* frames in the GT tensors used for overriding: 91 (train/val) or 11 (test) */
   int32_t n_step;      /* decode steps stored in the outputs = time_step_end (90) */
+  int32_t n_cta_per_mode; /* CTAs (one thread-block cluster) per scene-mode in the persistent decode kernel: 1, 2 or 4;
+                             0 = chosen from the batch size so that one launch fills the GPU.  Callers that keep several
+                             batches in flight on separate streams pass 1 (no redundant work between cluster ranks).
+                             tb_rollout_state_bytes depends on it: use the same value for every call on one state buffer. */
 } TbDims;
 
 /* ---------------------------------------------------------------- parameters ------------------------- */

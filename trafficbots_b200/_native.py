@@ -50,7 +50,7 @@ class TbError(RuntimeError):
 
 class TbDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
-                ("n_scene", "n_mode", "n_agent", "n_pl", "n_tl", "n_step_hist", "n_step_gt", "n_step")]
+                ("n_scene", "n_mode", "n_agent", "n_pl", "n_tl", "n_step_hist", "n_step_gt", "n_step", "n_cta_per_mode")]
 
 
 def _ptr_struct(name, fields):
@@ -89,17 +89,41 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """nvcc cross-compiles for sm_100a (works without a GPU).  Output: trafficbots_b200/libtrafficbots_b200.so"""
+    """nvcc cross-compiles for sm_100a (works without a GPU).  Output: trafficbots_b200/libtrafficbots_b200.so.
+    Every translation unit is compiled to `build/<name>.o` (in parallel, only when older than the sources / headers or
+    when the flags changed) and the objects are linked into the shared library."""
     if not force and not needs_build():
         return LIB_PATH
+    import concurrent.futures as cf
+    import hashlib
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("TB_NVCC_FLAGS", "").split()  # e.g. -DTB_TRACE_DETAIL (tools/trace_rollout.py)
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    cflags = [f for f in NVCC_FLAGS if f != "--shared"] + extra + (["-Xptxas", "-v"] if verbose else [])
+    tag = hashlib.sha1((" ".join(cflags) + "|" + os.path.basename(LIB_PATH)).encode()).hexdigest()[:10]
+    obj_dir = os.path.join(PKG_DIR, "build", tag)
+    os.makedirs(obj_dir, exist_ok=True)
+    headers = glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        glob.glob(os.path.join(ROOT, "include", "*.h"))
+    t_hdr = max(os.path.getmtime(h) for h in headers)
+
+    def compile_one(src: str):
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.isfile(obj) and os.path.getmtime(obj) > max(t_hdr, os.path.getmtime(src)):
+            return obj, ""
+        cmd = [nvcc] + cflags + ["-c", "-o", obj, src]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise TbError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        done = list(ex.map(compile_one, sources()))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH] + [o for o, _ in done]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise TbError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        raise TbError("nvcc link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        print("".join(log for _, log in done))
     return LIB_PATH
 
 

@@ -393,6 +393,7 @@ static int check_dims(const TbDims* d) {
       d->n_step_gt < 1 || d->n_step < 1)
     return TB_ERR_BAD_SHAPE;
   if ((long)d->n_scene * d->n_mode > 65535) return TB_ERR_BAD_SHAPE;  // gridDim.y
+  if (d->n_cta_per_mode != 0 && d->n_cta_per_mode != 1 && d->n_cta_per_mode != 2 && d->n_cta_per_mode != 4) return TB_ERR_BAD_SHAPE;
   return TB_OK;
 }
 int tb::check_dims_host(const TbDims* d) { return check_dims(d); }
@@ -409,10 +410,10 @@ extern "C" size_t tb_encode_workspace_bytes(const TbDims* d) {
 
 template <int R>
 static int launch_kv_project(const float* tgt, long n_row, const float* lw, float* kv, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_kv_project<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<R>));
-    attr_set = true;
+  static std::atomic<uint64_t> attr_set{0};
+  if (!smem_attr_done(attr_set)) {
+    if (!set_max_smem(k_kv_project<R>, (int)sizeof(TileSmem<R>))) return TB_ERR_LAUNCH;
+    smem_attr_mark(attr_set);
   }
   k_kv_project<R><<<(unsigned)((n_row + R - 1) / R), NT, sizeof(TileSmem<R>), st>>>(tgt, n_row, lw, kv);
   count_launch();
@@ -438,10 +439,10 @@ extern "C" int32_t tb_xlayer(int32_t block, int32_t layer, const float* src, con
     return TB_ERR_BAD_SHAPE;
   if (!aligned16(src) || !aligned16(kv) || !aligned16(packed) || !aligned16(dst)) return TB_ERR_ALIGN;
   constexpr int R = ROW_TILE;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_xlayer<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<R>));
-    attr_set = true;
+  static std::atomic<uint64_t> attr_set{0};
+  if (!smem_attr_done(attr_set)) {
+    if (!set_max_smem(k_xlayer<R>, (int)sizeof(TileSmem<R>))) return TB_ERR_LAUNCH;
+    smem_attr_mark(attr_set);
   }
   dim3 grid((n_src + R - 1) / R, n_batch);
   k_xlayer<R><<<grid, NT, sizeof(TileSmem<R>), (cudaStream_t)stream>>>(src, src_valid, n_src, kv, key_valid, n_key, kv_share,
@@ -472,12 +473,12 @@ extern "C" int32_t tb_encode_scene(const TbDims* dims, const TbSceneIn* in, cons
   float* pl_feature = reinterpret_cast<float*>(workspace);
   float* kv_self = pl_feature + n_pl * D;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_map_polyline, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MapSmem));
-    cudaFuncSetAttribute(k_encode_agent_hist<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<R>));
-    cudaFuncSetAttribute(k_encode_tl<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<R>));
-    attr_set = true;
+  static std::atomic<uint64_t> attr_set{0};
+  if (!smem_attr_done(attr_set)) {
+    if (!set_max_smem(k_map_polyline, (int)sizeof(MapSmem))) return TB_ERR_LAUNCH;
+    if (!set_max_smem(k_encode_agent_hist<R>, (int)sizeof(TileSmem<R>))) return TB_ERR_LAUNCH;
+    if (!set_max_smem(k_encode_tl<R>, (int)sizeof(TileSmem<R>))) return TB_ERR_LAUNCH;
+    smem_attr_mark(attr_set);
   }
   // 1. polyline encoder: tcgen05 kernel; TB_DISABLE_TC=1 selects the fp32 CUDA-core kernel (verification aid)
   if (tc_enabled()) {

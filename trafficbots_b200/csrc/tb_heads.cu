@@ -267,10 +267,10 @@ extern "C" int32_t tb_gru_sequence(int32_t which, int32_t mode, const float* x, 
   if (workspace && tc_enabled())  // tensor-core kernel (tb_tc_xlayer.cu); without a workspace: the fp32 row-tile kernel
     return launch_gru_seq_tc(which, mode, x, valid, n_batch, n_frame, n_agent, t_stride, packed, gru_base(which), workspace, out,
                              out_valid, (cudaStream_t)stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_gru_seq<HR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GruSmem));
-    attr_set = true;
+  static std::atomic<uint64_t> attr_set{0};
+  if (!smem_attr_done(attr_set)) {
+    if (!set_max_smem(k_gru_seq<HR>, (int)sizeof(GruSmem))) return TB_ERR_LAUNCH;
+    smem_attr_mark(attr_set);
   }
   const int n_t = (n_frame + t_stride - 1) / t_stride;
   dim3 grid((n_agent + HR - 1) / HR, n_batch);
@@ -332,10 +332,10 @@ extern "C" int32_t tb_dest_logits(int32_t n_scene, int32_t n_agent, int32_t n_pl
     const int rc = launch_dest_pairs_tc(U, V, n_scene, n_agent, n_pl, packed, logp, st);
     if (rc != TB_OK) return rc;
   } else {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(k_dest_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairSmem));
-      attr_set = true;
+    static std::atomic<uint64_t> attr_set{0};
+    if (!smem_attr_done(attr_set)) {
+      if (!set_max_smem(k_dest_pairs, (int)sizeof(PairSmem))) return TB_ERR_LAUNCH;
+      smem_attr_mark(attr_set);
     }
     dim3 grid((n_pl + PR - 1) / PR, n_agent, n_scene);
     k_dest_pairs<<<grid, NT, sizeof(PairSmem), st>>>(U, V, n_pl, n_agent, packed, logp);

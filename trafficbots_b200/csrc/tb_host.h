@@ -21,6 +21,21 @@ inline int launch_status() { return cudaGetLastError() == cudaSuccess ? TB_OK : 
 
 int check_dims_host(const TbDims* d);
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: every launcher keeps one bit per device ordinal
+// (thread-safe; setting the attribute twice is harmless) instead of a process-wide "already set" flag.
+inline uint64_t device_bit() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return 1ull << (dev & 63);
+}
+inline bool smem_attr_done(const std::atomic<uint64_t>& m) { return (m.load(std::memory_order_acquire) & device_bit()) != 0; }
+inline void smem_attr_mark(std::atomic<uint64_t>& m) { m.fetch_or(device_bit(), std::memory_order_release); }
+template <class K>
+inline bool set_max_smem(K* kernel, int bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+}
+
+
 struct StateView {
   float* agent_state;  // [B,A,4]
   uint8_t* valid;      // [2,B,A]

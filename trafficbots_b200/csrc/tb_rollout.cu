@@ -643,13 +643,14 @@ static int check_rollout_in(const TbRolloutIn* in) {
 }
 
 template <int R>
-static void set_rollout_attrs() {
-  static bool done = false;
-  if (done) return;
-  cudaFuncSetAttribute(k_rollout_init<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<R>));
-  cudaFuncSetAttribute(k_step_front<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<R>));
-  cudaFuncSetAttribute(k_step_back<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BackSmem<R>));
-  done = true;
+static int set_rollout_attrs() {
+  static std::atomic<uint64_t> done{0};
+  if (smem_attr_done(done)) return TB_OK;
+  if (!set_max_smem(k_rollout_init<R>, (int)sizeof(TileSmem<R>))) return TB_ERR_LAUNCH;
+  if (!set_max_smem(k_step_front<R>, (int)sizeof(TileSmem<R>))) return TB_ERR_LAUNCH;
+  if (!set_max_smem(k_step_back<R>, (int)sizeof(BackSmem<R>))) return TB_ERR_LAUNCH;
+  smem_attr_mark(done);
+  return TB_OK;
 }
 
 extern "C" int32_t tb_rollout_init(const TbDims* dims, const TbRolloutIn* in, const float* packed, void* state, void* stream) {
@@ -660,7 +661,7 @@ extern "C" int32_t tb_rollout_init(const TbDims* dims, const TbRolloutIn* in, co
   if (!packed || !state) return TB_ERR_NULL;
   if (!aligned16(packed) || (reinterpret_cast<uintptr_t>(state) & 255u)) return TB_ERR_ALIGN;
   constexpr int R = ROW_TILE;
-  set_rollout_attrs<R>();
+  if (set_rollout_attrs<R>() != TB_OK) return TB_ERR_LAUNCH;
   const TbDims d = *dims;
   dim3 grid((d.n_agent + R - 1) / R, d.n_scene * d.n_mode);
   k_rollout_init<R><<<grid, NT, sizeof(TileSmem<R>), (cudaStream_t)stream>>>(d, *in, packed, state_view(d, state));
@@ -686,7 +687,7 @@ static int rollout_steps_impl(const TbDims* dims, const TbRolloutIn* in, const f
   if (!aligned16(packed) || (reinterpret_cast<uintptr_t>(state) & 255u)) return TB_ERR_ALIGN;
   if (t_first < 1 || t_last > dims->n_step || t_first > t_last) return TB_ERR_BAD_SHAPE;
   constexpr int R = ROW_TILE;
-  set_rollout_attrs<R>();
+  if (set_rollout_attrs<R>() != TB_OK) return TB_ERR_LAUNCH;
   const TbDims d = *dims;
   const StateView sv = state_view(d, state);
   dim3 grid((d.n_agent + R - 1) / R, d.n_scene * d.n_mode);

@@ -451,10 +451,10 @@ extern "C" int32_t tb_tc_selftest(const float* a, int32_t block, const float* pa
   if (!a || !packed || !d) return TB_ERR_NULL;
   if (block < 0 || block >= TB_N_TC_BLOCKS) return TB_ERR_BAD_SHAPE;
   if (!aligned16(a) || !aligned16(packed) || !aligned16(d)) return TB_ERR_ALIGN;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelftestSmem) + 1024);
-    attr_set = true;
+  static std::atomic<uint64_t> attr_set{0};
+  if (!smem_attr_done(attr_set)) {
+    if (!set_max_smem(k_tc_selftest, (int)sizeof(SelftestSmem) + 1024)) return TB_ERR_LAUNCH;
+    smem_attr_mark(attr_set);
   }
   k_tc_selftest<<<1, 128, sizeof(SelftestSmem) + 1024, (cudaStream_t)stream>>>(a, tc_blob(packed) + (size_t)block * tc::BLOCK_BYTES, d, mode);
   count_launch();
@@ -466,11 +466,11 @@ size_t tb::map_tc_scratch_bytes(int n_cta) { return (size_t)n_cta * 128 * 128 * 
 
 int tb::launch_map_polyline_tc(const TbDims& d, const TbSceneIn& in, const float* packed, float* x0_scratch, int n_cta,
                                float* pl_feature, uint8_t* pl_valid, cudaStream_t st) {
-  static bool attr_set = false;
+  static std::atomic<uint64_t> attr_set{0};
   const int smem = (int)sizeof(MapTcSmem) + 1024;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_map_polyline_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_set = true;
+  if (!smem_attr_done(attr_set)) {
+    if (!set_max_smem(k_map_polyline_tc, smem)) return TB_ERR_LAUNCH;
+    smem_attr_mark(attr_set);
   }
   const long n_pl = (long)d.n_scene * d.n_pl;
   const int n_tiles = (int)((n_pl + MT_NP - 1) / MT_NP);

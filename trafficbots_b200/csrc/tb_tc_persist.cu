@@ -2642,27 +2642,28 @@ int tb::rollout_tc_cluster_size(const TbDims& d) {
   const char* env = getenv("TB_CLUSTER");  // development / test override
   const int forced = env ? atoi(env) : 0;
   if (forced == 1 || forced == 2 || forced == 4) return forced;
+  if (d.n_cta_per_mode == 1 || d.n_cta_per_mode == 2 || d.n_cta_per_mode == 4) return d.n_cta_per_mode;
   const int B = d.n_scene * d.n_mode;
   return B * 4 <= 148 ? 4 : (B * 2 <= 148 ? 2 : 1);
 }
 
 int tb::launch_rollout_tc(const TbDims& d, const TbRolloutIn& in, const float* packed, const StateView& sv, const TbRolloutOut& out,
                           int t_first, int t_last, cudaStream_t st) {
-  static bool attr_set = false;
+  static std::atomic<uint64_t> attr_set{0};
   const int smem = (int)sizeof(pr::Smem) + 1024;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(pr::k_rollout_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return TB_ERR_LAUNCH;
-    attr_set = true;
+  if (!smem_attr_done(attr_set)) {
+    if (!set_max_smem(pr::k_rollout_tc, smem)) return TB_ERR_LAUNCH;
+    smem_attr_mark(attr_set);
   }
   pr::Args a{d, in, packed, tc_blob(packed), sv, out, t_first, t_last, g_debug_trace};
   const int n_cta = rollout_tc_cluster_size(d);
   const char* w8 = getenv("TB_ROLLOUT_8WARP");  // A/B: the 8-worker-warp kernel
   const bool use16 = !(w8 && w8[0] == '1');
-  static bool attr16_set = false;
+  static std::atomic<uint64_t> attr16_set{0};
   const int smem16 = (int)sizeof(pr::Smem16) + 1024;
-  if (use16 && !attr16_set) {
-    if (cudaFuncSetAttribute(pr::k_rollout_tc16, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16) != cudaSuccess) return TB_ERR_LAUNCH;
-    attr16_set = true;
+  if (use16 && !smem_attr_done(attr16_set)) {
+    if (!set_max_smem(pr::k_rollout_tc16, smem16)) return TB_ERR_LAUNCH;
+    smem_attr_mark(attr16_set);
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(d.n_scene * d.n_mode * n_cta);

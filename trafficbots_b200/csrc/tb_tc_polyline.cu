@@ -382,11 +382,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
 
 int tb::launch_map_polyline_tc2(const TbDims& d, const TbSceneIn& in, const float* packed, float* x0_scratch, int n_cta,
                                 float* pl_feature, uint8_t* pl_valid, cudaStream_t st) {
-  static bool attr_set = false;
+  static std::atomic<uint64_t> attr_set{0};
   const int smem = (int)sizeof(pl2::Smem) + 1024;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(pl2::k_map_polyline_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return TB_ERR_LAUNCH;
-    attr_set = true;
+  if (!smem_attr_done(attr_set)) {
+    if (!set_max_smem(pl2::k_map_polyline_tc2, smem)) return TB_ERR_LAUNCH;
+    smem_attr_mark(attr_set);
   }
   const long n_pl = (long)d.n_scene * d.n_pl;
   const int n_tiles = (int)((n_pl + pl2::NP - 1) / pl2::NP);

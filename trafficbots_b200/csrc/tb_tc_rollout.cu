@@ -664,11 +664,11 @@ bool tb::front_tc_supported(const TbDims& d, const TbRolloutIn& in) {
 
 int tb::launch_step_front_tc(const TbDims& d, const TbRolloutIn& in, const float* packed, const StateView& sv, int t,
                              cudaStream_t st) {
-  static bool attr_set = false;
+  static std::atomic<uint64_t> attr_set{0};
   const int smem = (int)sizeof(FrontTcSmem) + 1024;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_step_front_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_set = true;
+  if (!smem_attr_done(attr_set)) {
+    if (!set_max_smem(k_step_front_tc, smem)) return TB_ERR_LAUNCH;
+    smem_attr_mark(attr_set);
   }
   FrontArgs a{d, in, packed, tc_blob(packed), sv, t, g_debug_trace};
   k_step_front_tc<<<d.n_scene * d.n_mode, FRONT_THREADS, smem, st>>>(a);

@@ -438,11 +438,11 @@ int tb::launch_xlayer_tc(int block, int layer, const float* src, const uint8_t* 
   if (first < 0) return TB_ERR_UNSUPPORTED;
   const int nT = (n_key_max + xl::KVT_KEYS - 1) / xl::KVT_KEYS;
   if (nT + 4 > xl::MAX_STAGE) return TB_ERR_BAD_SHAPE;
-  static bool attr_set = false;
+  static std::atomic<uint64_t> attr_set{0};
   const int smem = (int)sizeof(xl::Smem) + 1024;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(xl::k_xlayer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return TB_ERR_LAUNCH;
-    attr_set = true;
+  if (!smem_attr_done(attr_set)) {
+    if (!set_max_smem(xl::k_xlayer_tc, smem)) return TB_ERR_LAUNCH;
+    smem_attr_mark(attr_set);
   }
   xl::Args a{src, src_valid, dst, n_src, blocks, n_key, nT, kv_share, packed + block_base(block) + layer * tfl::STRIDE,
              tc_blob(packed) + (size_t)first * tc::BLOCK_BYTES};
@@ -627,11 +627,11 @@ __global__ void __launch_bounds__(THREADS, 2) k_dest_pairs_tc(const float* __res
 
 int tb::launch_dest_pairs_tc(const float* U, const float* V, int n_scene, int n_agent, int n_pl, const float* packed, float* logits,
                              cudaStream_t st) {
-  static bool attr_set = false;
+  static std::atomic<uint64_t> attr_set{0};
   const int smem = (int)sizeof(dp::Smem) + 1024;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(dp::k_dest_pairs_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return TB_ERR_LAUNCH;
-    attr_set = true;
+  if (!smem_attr_done(attr_set)) {
+    if (!set_max_smem(dp::k_dest_pairs_tc, smem)) return TB_ERR_LAUNCH;
+    smem_attr_mark(attr_set);
   }
   const int n_sa = n_scene * n_agent;
   const long n_tile = (long)n_sa * ((n_pl + 127) / 128);
@@ -794,11 +794,11 @@ static int tc_in_proj_first_block(int block, int layer) {
 int tb::launch_kv_project_tc(int block, int layer, const float* tgt, long n_row, const float* packed, float* kv, cudaStream_t st) {
   const int first = tc_in_proj_first_block(block, layer);
   if (first < 0) return TB_ERR_UNSUPPORTED;
-  static bool attr_set = false;
+  static std::atomic<uint64_t> attr_set{0};
   const int smem = (int)sizeof(kvp::Smem) + 1024;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kvp::k_kv_project_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return TB_ERR_LAUNCH;
-    attr_set = true;
+  if (!smem_attr_done(attr_set)) {
+    if (!set_max_smem(kvp::k_kv_project_tc, smem)) return TB_ERR_LAUNCH;
+    smem_attr_mark(attr_set);
   }
   const long n_tile = (n_row + 127) / 128;
   const int grid = (int)(n_tile < 148 ? n_tile : 148);
@@ -1060,11 +1060,11 @@ int tb::launch_gru_seq_tc(int which, int mode, const float* x, const uint8_t* va
       break;
     default: return TB_ERR_BAD_SHAPE;
   }
-  static bool attr_set = false;
+  static std::atomic<uint64_t> attr_set{0};
   const int smem = (int)sizeof(gq::Smem) + 1024;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(gq::k_gru_seq_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return TB_ERR_LAUNCH;
-    attr_set = true;
+  if (!smem_attr_done(attr_set)) {
+    if (!set_max_smem(gq::k_gru_seq_tc, smem)) return TB_ERR_LAUNCH;
+    smem_attr_mark(attr_set);
   }
   const long n_rows = (long)n_batch * n_agent;
   const int n_t = (n_frame + t_stride - 1) / t_stride;

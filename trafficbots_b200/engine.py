@@ -32,17 +32,33 @@ class SceneFeatures(dict):
 
 
 class Engine:
-    def __init__(self, state_dict: Mapping[str, Tensor], device: Optional[torch.device] = None):
+    def __init__(self, state_dict: Optional[Mapping[str, Tensor]], device: Optional[torch.device] = None,
+                 packed: Optional[Tensor] = None, rollout_cluster: int = 0):
+        """`packed`: share the packed parameter blob of another Engine (see `fork`); otherwise `state_dict` is packed.
+        `rollout_cluster`: CTAs per scene-mode of the persistent decode kernel (`TbDims.n_cta_per_mode`; 0 = chosen by the
+        library from the batch size, 1 when several batches are kept in flight on separate streams)."""
         self.lib = nt.lib()
         if not torch.cuda.is_available():
             raise nt.TbError("no CUDA device: trafficbots_b200 has no CPU implementation of the hot path")
         self.device = torch.device(device if device is not None else "cuda")
-        self.packed = torch.empty(self.lib.tb_packed_weight_bytes() // 4, dtype=torch.float32, device=self.device)
-        self.load_state_dict(state_dict)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.rollout_cluster = int(rollout_cluster)
+        if packed is not None:
+            self.packed = packed
+        else:
+            self.packed = torch.empty(self.lib.tb_packed_weight_bytes() // 4, dtype=torch.float32, device=self.device)
+            self.load_state_dict(state_dict)
         self._enc_ws: Optional[Tensor] = None
         self._state: Optional[Tensor] = None
         self._state_dims = None
         self.last_t = 0
+
+    def fork(self, rollout_cluster: Optional[int] = None) -> "Engine":
+        """a second Engine on the SAME packed parameters with its own workspaces / simulation state: one per batch kept in
+        flight (`pipeline.ScenePipeline`).  Re-packing through either engine updates both."""
+        return Engine(None, self.device, packed=self.packed,
+                      rollout_cluster=self.rollout_cluster if rollout_cluster is None else rollout_cluster)
 
     # ------------------------------------------------------------------------------------------------ parameters
     def load_state_dict(self, state_dict: Mapping[str, Tensor]) -> None:
@@ -62,13 +78,14 @@ class Engine:
             keep.append(t)
             ptrs[i] = t.data_ptr()
         with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)  # forked engines may still be reading the blob on other streams
             nt.check(self.lib.tb_pack_weights(ptrs, self.packed.data_ptr(), nt.current_stream_ptr()), "tb_pack_weights")
-            torch.cuda.current_stream().synchronize()  # `keep` may be freed after this
+            # `keep` may be freed after this, and forked engines on other streams must see the new blob
+            torch.cuda.synchronize(self.device)
 
     # ------------------------------------------------------------------------------------------------ encoding
-    @staticmethod
-    def _dims(S, K, A, P, TL, Th, Tg, T) -> nt.TbDims:
-        return nt.TbDims(S, K, A, P, TL, Th, Tg, T)
+    def _dims(self, S, K, A, P, TL, Th, Tg, T) -> nt.TbDims:
+        return nt.TbDims(S, K, A, P, TL, Th, Tg, T, self.rollout_cluster)
 
     def encode_scene(self, batch: Mapping[str, Tensor], prefix: str = "history/") -> SceneFeatures:
         """batch: reference batch dict (CUDA tensors). Uses map/* and `{prefix}agent/*`, `{prefix}tl_stop/*`."""
@@ -273,6 +290,8 @@ class Engine:
 
     def _ensure_state(self, dims: nt.TbDims) -> Tensor:
         need = self.lib.tb_rollout_state_bytes(C.byref(dims))
+        if need == 0:
+            raise nt.TbError("tb_rollout_state_bytes: unsupported dimensions")
         if self._state is None or self._state.numel() < need:
             self._state = torch.empty(need, dtype=torch.uint8, device=self.device)
         self._state_dims = dims
@@ -344,6 +363,21 @@ class Engine:
         self.last_t = t
         return t
 
+    def steps(self, ctx: Dict, t_first: int, t_last: int) -> None:
+        """decode steps t_first..t_last of an opened rollout in one library call (`tb_rollout_steps`)."""
+        with torch.cuda.device(self.device):
+            nt.check(self.lib.tb_rollout_steps(C.byref(ctx["dims"]), C.byref(ctx["rin"]), self.packed.data_ptr(),
+                                               self._state.data_ptr(), C.byref(ctx["rout"]), t_first, t_last,
+                                               nt.current_stream_ptr()), "tb_rollout_steps")
+        self.last_t = t_last
+
+    def reinit(self, ctx: Dict) -> None:
+        """`tb_rollout_init` again on an opened rollout (back to frame 0): measurement aid."""
+        with torch.cuda.device(self.device):
+            nt.check(self.lib.tb_rollout_init(C.byref(ctx["dims"]), C.byref(ctx["rin"]), self.packed.data_ptr(),
+                                              self._state.data_ptr(), nt.current_stream_ptr()), "tb_rollout_init")
+        self.last_t = 0
+
     def profile_rollout(self, *args, n_mode: int = 1, n_step: int = 90, out=None, repeats: int = 3, **kw):
         """Times the decode loop alone (`tb_rollout_steps(1..n_step)`: ONE launch of the persistent tensor-core kernel when
         n_agent <= 64) with CUDA events on the launching stream; `tb_rollout_init` runs outside the timed region.
@@ -371,13 +405,15 @@ class Engine:
         res = {k: v for k, v in out.items() if not k.startswith("_")}
         for i, k in enumerate(VIOLATION_KEYS):
             res[f"violations/{k}"] = out["_violations"][i]
-        res["hidden"] = self.state_field(nt.STATE_HIDDEN)
-        res["final_state"] = self.state_field(nt.STATE_AGENT_STATE)
-        res["final_valid"] = self.state_field(nt.STATE_VALID)
+        # copies: the state buffer is reused (overwritten in place) by the next rollout on this engine
+        res["hidden"] = self.state_field(nt.STATE_HIDDEN).clone()
+        res["final_state"] = self.state_field(nt.STATE_AGENT_STATE).clone()
+        res["final_valid"] = self.state_field(nt.STATE_VALID).clone()
         return res
 
     def state_field(self, field: int) -> Tensor:
-        """typed view into the simulation-state buffer (see `tb_state_field` in the header)."""
+        """typed VIEW into the simulation-state buffer (see `tb_state_field` in the header): valid until the next rollout
+        on this engine starts; clone it to keep it."""
         d = self._state_dims
         B, A = d.n_scene * d.n_mode, d.n_agent
         off = self.lib.tb_rollout_state_offset(C.byref(d), field)

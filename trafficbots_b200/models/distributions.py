@@ -23,11 +23,14 @@ class DiagGaussian:
         if self.valid is not None:
             self.valid = self.valid.repeat_interleave(repeats, dim)
 
+    def _rsample(self) -> Tensor:
+        # the reference's draw (`Independent(Normal(mean, std), 1).rsample()`, distributions.py:26,49): same generator calls
+        return torch.distributions.Normal(self.mean, self.stddev, validate_args=False).rsample()
+
     def sample(self, deterministic: Union[bool, Tensor]) -> Tensor:
         if isinstance(deterministic, Tensor):
-            rnd = self.mean + torch.randn_like(self.mean) * self.stddev
-            return torch.where(deterministic.unsqueeze(-1), self.mean, rnd)
-        return self.mean if deterministic else self.mean + torch.randn_like(self.mean) * self.stddev
+            return torch.where(deterministic.unsqueeze(-1), self.mean, self._rsample())
+        return self.mean if deterministic else self._rsample()
 
     def log_prob(self, sample: Tensor) -> Tensor:
         var = self.stddev ** 2

@@ -103,26 +103,66 @@ class WaymoMotion(_Base):
         self.teacher_forcing_reactive_replay = TeacherForcing(**(teacher_forcing_reactive_replay or {"step_spawn_agent": 90}))
         self.teacher_forcing_joint_future_pred = TeacherForcing(**(teacher_forcing_joint_future_pred or {}))
         self._eng: Optional[Engine] = None
+        self._eng_slot: Optional[Engine] = None
         self._packed_version = None
+        self._params_dirty = True
+        self._param_list = None
+        self._param_ptrs = None
         self._step_ctx = None
 
     # ------------------------------------------------------------------------------------------------ engine / parameters
     def _param_version(self):
-        return tuple((p.data_ptr(), p._version) for p in self.state_dict(keep_vars=True).values())
+        """(tensor identities, version counters) of the 483 state_dict entries.  The tensor list is cached (rebuilt whenever
+        `_apply` / `load_state_dict` / `mark_params_dirty` flag a change), so the per-call cost is one attribute read per
+        tensor, not a `state_dict()` rebuild."""
+        if self._param_list is None or self._params_dirty:
+            self._param_list = list(self.state_dict(keep_vars=True).values())
+            self._param_ptrs = tuple(p.data_ptr() for p in self._param_list)
+        return self._param_ptrs, tuple(p._version for p in self._param_list)
+
+    def mark_params_dirty(self) -> None:
+        """Call after writing parameters in a way autograd's version counters do not see (`p.data.copy_()`, EMA updates
+        through `.data`, raw pointer writes): the next `engine()` call re-packs the kernel weight blob.  `load_state_dict`,
+        `.to()` / `.cuda()` and in-place updates (optimizer steps, `p.add_()`, `p.copy_()`) are detected automatically."""
+        self._params_dirty = True
+
+    def _apply(self, fn, *a, **kw):
+        self._params_dirty = True
+        return super()._apply(fn, *a, **kw)
+
+    def _load_from_state_dict(self, *a, **kw):
+        self._params_dirty = True
+        return super()._load_from_state_dict(*a, **kw)
+
+    def load_state_dict(self, *a, **kw):
+        self._params_dirty = True
+        return super().load_state_dict(*a, **kw)
 
     def engine(self) -> Engine:
-        """the CUDA engine with the CURRENT parameters packed (re-packs after load_state_dict / optimizer steps / .to())."""
+        """the CUDA engine with the CURRENT parameters packed: autograd's version counters of the (cached) parameter list are
+        compared on every call -- except inside an open stepwise rollout -- and the blob is re-packed when they moved (see
+        `mark_params_dirty` for writes the counters do not see).  Inside `pipeline.ScenePipeline` slots the slot's forked
+        engine (same packed blob, own workspaces) is returned."""
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise nt.TbError("trafficbots_b200.WaymoMotion must live on a CUDA device (no CPU implementation of the hot path)")
-        ver = self._param_version()
-        if self._eng is None or self._eng.device != dev:
+        if self._eng is None or self._eng.device != torch.device(dev.type, dev.index if dev.index is not None else torch.cuda.current_device()):
             self._eng = Engine(self.state_dict(), dev)
-            self._packed_version = ver
-        elif ver != self._packed_version:
-            self._eng.load_state_dict(self.state_dict())
-            self._packed_version = ver
-        return self._eng
+            self._packed_version = self._param_version()
+            self._params_dirty = False
+            self._eng_slot = None
+        elif self._step_ctx is None:
+            ver = self._param_version()
+            if ver != self._packed_version or self._params_dirty:
+                self._eng.load_state_dict(self.state_dict())
+                self._packed_version = ver
+            self._params_dirty = False
+        return self._eng_slot if self._eng_slot is not None else self._eng
+
+    def use_engine(self, eng: Optional[Engine]) -> None:
+        """route the next calls through a forked engine (`Engine.fork`) -- used by `pipeline.ScenePipeline`; None restores
+        the module's own engine."""
+        self._eng_slot = eng
 
     # ------------------------------------------------------------------------------------------------ encoding
     def encode(self, batch: Mapping[str, Tensor]):
@@ -164,19 +204,35 @@ class WaymoMotion(_Base):
         out = eng.rollout(*args, n_mode=n_mode, n_step=step_end)
         return RolloutBuffer(step_start, step_end, self.tb_hparams["time_step_current"], out)
 
-    def forward(self, *args, **kwargs):
-        """One decode step (waymo_motion.py:108-203) of the rollout opened with `rollout(features | {"_stepwise": True}, ...)`.
-        The reference passes the step's map / traffic-light features, goal feature and state overrides as arguments; in the
-        fused path they are bound when the rollout is opened (K|V caches, GT tensors and the teacher-forcing mask), so the
-        arguments are accepted for signature compatibility and ignored.  Returns (state [B,A,4], valid [B,A], train_dict,
-        vis_dict) like the reference; `train_dict` holds this step's pre-override prediction."""
+    def forward(self, map_feature: Optional[Tensor] = None, map_valid: Optional[Tensor] = None,
+                tl_feature: Optional[Tensor] = None, tl_valid: Optional[Tensor] = None, goal_feature: Optional[Tensor] = None,
+                goal_valid: Optional[Tensor] = None, action_override: Optional[Tensor] = None,
+                mask_action_override: Optional[Tensor] = None, state_override: Optional[Mapping] = None,
+                mask_state_override: Optional[Tensor] = None, deterministic_action: bool = True,
+                require_train_dict: bool = True, require_vis_dict: bool = False):
+        """One decode step (signature of waymo_motion.py:108-123) of the rollout opened with
+        `rollout(features | {"_stepwise": True}, ...)`.  The reference passes the step's map / traffic-light features and the
+        goal feature as arguments; in the fused path they are BOUND when the rollout is opened (K|V caches, goal features,
+        `goal_valid` bookkeeping live in the engine state), so the first six arguments are accepted and not re-read.  The
+        state override of step t is `GT[t]` under `mask_teacher_forcing[:, t]` -- what the reference's `rollout()` passes
+        (:300-309) -- also bound at opening.  A caller that passes overrides of its own (`action_override`,
+        `state_override`, `mask_state_override`), stochastic actions or asks for attention maps gets `UnsupportedConfig`
+        instead of a silently different result.  Returns (state [B,A,4], valid [B,A], train_dict, vis_dict); `train_dict`
+        holds this step's pre-override prediction under the reference's keys (:181-188)."""
         if self._step_ctx is None:
             raise nt.TbError("forward(): open a rollout first (features['_stepwise'] = True)")
+        if action_override is not None or mask_action_override is not None or state_override is not None or \
+                mask_state_override is not None:
+            raise tb_config.UnsupportedConfig("forward(): per-call action / state overrides are not supported by the fused step; the "
+                                              "overrides are the GT tensors and `mask_teacher_forcing` bound by rollout()")
+        if require_vis_dict or not deterministic_action:
+            raise tb_config.UnsupportedConfig("forward(): require_vis_dict / stochastic actions are not supported by the fused step")
         eng = self.engine()
         t = eng.step(self._step_ctx)
         o = self._step_ctx["out"]
-        train = {"pred_state": o["preds"][:, :, t - 1], "pred_valid": o["valid"][:, :, t - 1],
-                 "latent_logp": o["latent_log_probs"][:, :, t - 1], "action_logp": o["action_log_probs"][:, :, t - 1]}
+        train = {} if not require_train_dict else {
+            "latent_log_prob": o["latent_log_probs"][:, :, t - 1], "action_log_prob": o["action_log_probs"][:, :, t - 1],
+            "pred_valid": o["valid"][:, :, t - 1], "pred_state": o["preds"][:, :, t - 1]}
         return eng.state_field(nt.STATE_AGENT_STATE), eng.state_field(nt.STATE_VALID), train, {}
 
     def finish_rollout(self) -> RolloutBuffer:
