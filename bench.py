@@ -41,7 +41,7 @@ import torch  # noqa: E402
 
 METRIC = "scenes/sec (64 agents, 91-step closed-loop rollout)"
 CONFIGS = {
-    1: dict(n_scene=32, n_agent=64, n_pl=1024, n_mode=1, n_step=90, depth=6, cpu_scenes=32,
+    1: dict(n_scene=32, n_agent=64, n_pl=1024, n_mode=1, n_step=90, depth=4, cpu_scenes=32,
             name="BASELINE.json configs[1]: batch = 32 scenes, 64 agents, 1024 map polylines, 91 frames, K = 1"),
     2: dict(n_scene=32, n_agent=64, n_pl=1024, n_mode=6, n_step=90, depth=2, cpu_scenes=6,
             name="BASELINE.json configs[2], per-GPU slice: 32 scenes x K = 6 sampled joint futures (256 scenes over 8 GPUs)"),
