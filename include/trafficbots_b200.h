@@ -45,6 +45,7 @@ typedef enum tb_status {
 #define TB_PL_NODE 20
 #define TB_PL_TYPE 11
 #define TB_TL_STATE 5
+#define TB_N_OPT_VIOLATION 8 /* tb_rule_checks */
 #define TB_N_VIOLATION 6 /* outside_map, outside_map_this_step, goal_reached, goal_reached_this_step,
                             dest_reached, dest_reached_this_step (utils/traffic_rule_checker.py:499-515) */
 
@@ -301,6 +302,56 @@ size_t tb_dest_workspace_bytes(int32_t n_scene, int32_t n_agent, int32_t n_pl);
 int32_t tb_dest_logits(int32_t n_scene, int32_t n_agent, int32_t n_pl, const float* map_feature,
                        const uint8_t* map_feature_valid, const uint8_t* map_type, const float* tgt, const uint8_t* tgt_valid,
                        const uint8_t* agent_type, const float* packed, void* workspace, float* logp, float* probs, void* stream);
+
+/* ---------------------------------------------------------------- optional rule checks ---- */
+
+/* The four OPTIONAL checks of `TrafficRuleChecker.check` (utils/traffic_rule_checker.py:122-335,420-472: collided,
+ * run_road_edge, run_red_light, passive; `enable_check_*` in configs/model/traffic_bots.yaml:240-244) and the collision
+ * term of `DifferentiableReward.get` (utils/rewards.py:49-115, `w_collision` > 0).  None of them feeds back into the
+ * simulation (only outside_map kills, only goal / dest_reached disable goals), so they are evaluated AFTER the rollout, in
+ * parallel over all (scene-mode, step) pairs, from the rollout's outputs: the post-override state the reference checks at
+ * step t is `override_masks & ~killed ? GT[t] : preds[t]` with `killed` = running OR of
+ * `outside_map_this_step & ~gt_valid` (dynamics.py:132-167).  Results equal the reference's per-step evaluation. */
+typedef struct TbRuleIn {
+  /* outputs of tb_rollout for the same dims */
+  const float* preds;                    /* [B,A,T,4] */
+  const uint8_t* valid;                  /* [B,A,T]   */
+  const uint8_t* override_masks;         /* [B,A,T]   */
+  const uint8_t* outside_map_this_step;  /* [B,A,T] = violations[1] */
+  /* ground truth used for overriding (as in TbRolloutIn) */
+  const uint8_t* gt_valid;               /* [S,Tg,A]   */
+  const float* gt_pos;                   /* [S,Tg,A,2] */
+  const float* gt_yaw;                   /* [S,Tg,A,1] */
+  const float* gt_spd;                   /* [S,Tg,A,1] */
+  const uint8_t* agent_type;             /* [S,A,3] */
+  const float* agent_size;               /* [S,A,3] */
+  const uint8_t* map_valid;              /* [S,P,20] */
+  const uint8_t* map_type;               /* [S,P,11] */
+  const float* map_pos;                  /* [S,P,20,2] */
+  const float* map_dir;                  /* [S,P,20,2] */
+  /* traffic-light stop points handed to the rule checker: the full episode in reactive_replay (waymo_motion.py:439-441),
+   * the history frames in joint_future_pred (:523-525); step t reads frame min(t, n_tl_frame - 1) */
+  const uint8_t* tl_valid;               /* [S,n_tl_frame,TL]   */
+  const float* tl_pos;                   /* [S,n_tl_frame,TL,2] */
+  const uint8_t* tl_state;               /* [S,n_tl_frame,TL,5] */
+  int32_t n_tl_frame;
+  int32_t enable_mask;                   /* bit 0 collided, 1 run_road_edge, 2 run_red_light, 3 passive (needs bit 2: in the
+                                            reference `enable_check_passive` alone is a NameError, :441-442,:457-464) */
+  float collision_size_scale;            /* 1.1 (traffic_rule_checker.py:28) */
+  float w_collision;                     /* differentiable_reward.w_collision; 0 = off */
+  int32_t reduce_collision_with_max;     /* differentiable_reward.reduce_collsion_with_max */
+} TbRuleIn;
+
+typedef struct TbRuleOut {
+  uint8_t* violations;                   /* [8][B,A,T]: collided, collided_this_step, run_road_edge, run_road_edge_this_step,
+                                            run_red_light, run_red_light_this_step, passive, passive_this_step */
+  float* diffbar_rewards;                /* [B,A,T] in/out (may be NULL when w_collision == 0): the collision term is added to
+                                            the imitation reward written by tb_rollout */
+  const uint8_t* diffbar_rewards_valid;  /* [B,A,T] (tb_rollout output) */
+} TbRuleOut;
+
+size_t tb_rule_workspace_bytes(const TbDims* dims);
+int32_t tb_rule_checks(const TbDims* dims, const TbRuleIn* in, const TbRuleOut* out, void* workspace, void* stream);
 
 /* Self-test of the tensor-core GEMM machinery (tcgen05.mma, TMEM, bulk-async weight staging, bf16x3 operand split):
  * d[128,128] = a[128,128] @ W^T for packed tensor-core weight block `block` (0 <= block < tb_tc_block_count());

@@ -31,6 +31,16 @@ CASES = {
     "s3_a8_p64_k2": (3, 8, 64, 2, 100, 2023, 7),  # + zero-TL scene, single-valid-agent scene, K>1 sampling
     "s1_a64_p1024_k1": (1, 64, 1024, 1, 500, 2023, 7),  # BASELINE.json configs[1] per-scene shape
 }
+# the four optional traffic-rule checks and the collision reward switched ON in the reference, dense scenes
+# (area_scale 0.25) so that collisions / road-edge crossings / red-light / passive events really occur
+RULE_CASES = {
+    # name: (n_scene, n_agent, n_pl, K, scene_seed, weight_seed, sample_seed, area_scale, w_collision, reduce_with_max)
+    "s2_a16_p96_k2_rules": (2, 16, 96, 2, 900, 2023, 7, 0.25, 0.5, True),
+    "s2_a12_p64_k1_rules_sum": (2, 12, 64, 1, 950, 2023, 7, 0.2, 1.0, False),
+}
+RULES_ON = {"enable_check_collided": True, "enable_check_run_road_edge": True, "enable_check_run_red_light": True,
+            "enable_check_passive": True}
+RULE_BUF = tuple(f"violations/{k}{s}" for k in ("collided", "run_road_edge", "run_red_light", "passive") for s in ("", "_this_step"))
 
 KEEP = (
     "enc/map_feature", "enc/map_feature_valid", "enc/agent_feature", "enc/tl_feature", "dest/probs",
@@ -53,7 +63,8 @@ def checksum(tensors) -> float:
 def main() -> None:
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
-    for name, (S, A, P, K, seed, wseed, sseed) in CASES.items():
+    only_rules = "--rules-only" in sys.argv  # keeps the existing fixtures byte-identical
+    for name, (S, A, P, K, seed, wseed, sseed) in ({} if only_rules else CASES).items():
         model = ref_loader.build_reference(n_agent=A, n_pl=P, n_joint_future=K)
         sd = weights.init_state_dict(wseed)
         model.load_state_dict(sd, strict=True)
@@ -70,6 +81,27 @@ def main() -> None:
         path = os.path.join(out_dir, name + ".npz")
         np.savez_compressed(path, **arrays)
         print(name, "->", path, f"{os.path.getsize(path) / 1024:.0f} KiB")
+    for name, (S, A, P, K, seed, wseed, sseed, area, wcol, rmax) in RULE_CASES.items():
+        model = ref_loader.build_reference(n_agent=A, n_pl=P, n_joint_future=K, overrides={
+            "traffic_rule_checker": dict(RULES_ON),
+            "differentiable_reward": {"w_collision": wcol, "reduce_collsion_with_max": rmax}})
+        sd = weights.init_state_dict(wseed)
+        model.load_state_dict(sd, strict=True)
+        batch = synthetic.make_batch(S, n_agent=A, n_pl=P, seed=seed, special_scenes=False, area_scale=area, plant_red_light=True)
+        res = ref_run.run_reference(model, batch, k_futures=K, sample_seed=sseed)
+        keep = {k: res[k] for k in ("jfp/goal_sample", "jfp/latent_sample", "latent_post/mean")}
+        for leg in ("jfp", "replay"):
+            for b in BUF + RULE_BUF:
+                keep[f"{leg}/{b}"] = res[f"{leg}/{b}"]
+        arrays = {k.replace("/", "__"): v.numpy() for k, v in keep.items()}
+        arrays["meta__case"] = np.array([S, A, P, K, seed, wseed, sseed], dtype=np.int64)
+        arrays["meta__rules"] = np.array([area, wcol, float(rmax)], dtype=np.float64)
+        arrays["meta__checksum_batch"] = np.array(checksum(batch))
+        arrays["meta__checksum_weights"] = np.array(checksum(sd))
+        path = os.path.join(out_dir, name + ".npz")
+        np.savez_compressed(path, **arrays)
+        events = {k.split("/")[-1]: int(res[f"replay/{k}"].sum()) for k in RULE_BUF if not k.endswith("_this_step")}
+        print(name, "->", path, f"{os.path.getsize(path) / 1024:.0f} KiB", "sticky-flag counts (replay):", events)
 
 
 if __name__ == "__main__":

@@ -290,15 +290,26 @@ def default_config(time_step_end: int = 90, n_joint_future: int = 6) -> Dict[str
     )
 
 
+def _deep_update(dst: Dict[str, Any], src: Dict[str, Any]) -> None:
+    for k, v in src.items():
+        if isinstance(v, dict) and isinstance(dst.get(k), dict):
+            _deep_update(dst[k], v)
+        else:
+            dst[k] = v
+
+
 def build_reference(n_agent: int = 64, n_pl: int = 1024, time_step_end: int = 90, n_joint_future: int = 6,
-                    seed: int = 2023):
+                    seed: int = 2023, overrides: Dict[str, Any] = None):
     """Instantiate the unmodified reference `WaymoMotion` with default init under `torch.manual_seed(seed)`
     (`configs/run.yaml:17`), in eval mode."""
     install_stubs()
     from pl_modules.waymo_motion import WaymoMotion  # noqa: the reference's own class
 
     torch.manual_seed(seed)
-    cfg = _wrap(default_config(time_step_end=time_step_end, n_joint_future=n_joint_future))
+    plain = default_config(time_step_end=time_step_end, n_joint_future=n_joint_future)
+    if overrides:  # e.g. {"traffic_rule_checker": {"enable_check_collided": True}, "differentiable_reward": {"w_collision": 1.0}}
+        _deep_update(plain, overrides)
+    cfg = _wrap(plain)
     model = WaymoMotion(data_size=_wrap(data_size(n_agent=n_agent, n_pl=n_pl)), **cfg)
     model.eval()
     return model

@@ -408,11 +408,17 @@ def rollout(sd: SD, *, map_feature: Tensor, map_valid: Tensor, tl_feature: Tenso
             agent_type: Tensor, agent_size: Tensor, tf_mask: Tensor, latent_sample: Tensor, latent_logp: Tensor,
             dest: Tensor, goal_valid: Tensor, goal_gt: Optional[Tensor], map_boundary: Tensor,
             raw_map_valid: Tensor, raw_map_type: Tensor, raw_map_pos: Tensor, raw_map_dir: Tensor,
-            step_start: int = 1, step_end: int = 90, return_trace: bool = False) -> Dict[str, Tensor]:
+            step_start: int = 1, step_end: int = 90, return_trace: bool = False,
+            rules: Optional[Dict] = None, w_collision: float = 0.0, reduce_collision_with_max: bool = True
+            ) -> Dict[str, Tensor]:
     """`WaymoMotion.rollout` + `.forward` in eval mode with the default config (pl_modules/waymo_motion.py:108-354),
     including `Dynamics` (utils/dynamics.py:29-167), `MultiPathPP` (:187-228), the always-on checks of
     `TrafficRuleChecker` (utils/traffic_rule_checker.py:82-119,338-516), `disable_goal_reached`
     (models/goal_manager.py:155-161) and the IL part of `DifferentiableReward.get` (utils/rewards.py:117-131).
+
+    `rules` (optional checks): dict(enable={collided, run_road_edge, run_red_light, passive: bool}, tl_valid,
+    tl_pos, tl_state [B,T_tl,TL,..]) -> `rule_checks_oracle.check_optional` every step; `w_collision` > 0 adds the collision
+    term of the reward (`rule_checks_oracle.collision_term`).
 
     Every tensor's leading dim is B = n_scene * K scene-modes (the reference `repeat_interleave`s everything,
     waymo_motion.py:547-548).  gt_* have T_gt frames (91 for train/val, 11 for test); tl_* have T_tl frames.
@@ -452,6 +458,14 @@ def rollout(sd: SD, *, map_feature: Tensor, map_valid: Tensor, tl_feature: Tenso
             "action_log_probs", "outside_map", "outside_map_this_step", "goal_reached", "goal_reached_this_step",
             "dest_reached", "dest_reached_this_step")
     out = {k: [] for k in keys}
+    rs = None
+    if rules is not None:
+        import rule_checks_oracle as rco
+        rs = rco.init_rules(agent_type, agent_size, raw_map_valid, raw_map_type, raw_map_pos, raw_map_dir, rules["tl_valid"],
+                            rules["tl_pos"], rules["tl_state"], rules["enable"])
+        for k in rco.OPTIONAL_KEYS:
+            out[k] = []
+            out[k + "_this_step"] = []
     trace = {"policy_feature": [], "action_mean": [], "goal_valid": [], "agent_valid_post": []}
     zeros_b = torch.zeros_like(valid)
 
@@ -513,6 +527,9 @@ def rollout(sd: SD, *, map_feature: Tensor, map_valid: Tensor, tl_feature: Tenso
         edge = dest_type[:, :, 4]
         dest_t = ~dest_reached & valid & ((lane & pos_reached & rot_reached) | (edge & pos_reached))
         dest_reached = dest_reached | dest_t
+        if rs is not None:  # optional checks see the same post-override state / valid (traffic_rule_checker.py:420-472)
+            for k, v in rco.check_optional(rs, t, valid, state).items():
+                out[k].append(v)
 
         # ---- Dynamics.kill (dynamics.py:161-167), disable_goal_reached (goal_manager.py:155-161) ----
         kill = out_t & ~gt_valid[:, t] if t < T_gt else out_t
@@ -520,7 +537,12 @@ def rollout(sd: SD, *, map_feature: Tensor, map_valid: Tensor, tl_feature: Tenso
         valid = valid & ~kill
         goal_valid = goal_valid & valid & ~dest_reached
 
-        # ---- DifferentiableReward.get, IL part (rewards.py:117-131) ----
+        # ---- DifferentiableReward.get: collision term (rewards.py:49-115), IL part (:117-131) ----
+        reward0 = torch.zeros_like(px)
+        if w_collision > 0:
+            import rule_checks_oracle as rco2
+            col = rco2.collision_term(pred_valid, pred_state, agent_size, reduce_collision_with_max)
+            reward0 = reward0 - w_collision * col.masked_fill(~pred_valid, 0.0)
         if t < T_gt:
             rv = pred_valid & gt_valid[:, t]
             gs = gt_state[:, t].masked_fill(~rv.unsqueeze(-1), 0.0)
@@ -528,10 +550,10 @@ def rollout(sd: SD, *, map_feature: Tensor, map_valid: Tensor, tl_feature: Tenso
             e_pos = F.smooth_l1_loss(gs[..., :2], ps[..., :2], reduction="none").sum(-1)
             e_rot = 0.5 * (1 - torch.cos(gs[..., 2] - ps[..., 2]))
             e_spd = F.smooth_l1_loss(gs[..., 3], ps[..., 3], reduction="none")
-            reward = (0.0 - (0.1 * e_pos + 10.0 * e_rot + 0.1 * e_spd)).masked_fill(~rv, 0.0)
+            reward = (reward0 - (0.1 * e_pos + 10.0 * e_rot + 0.1 * e_spd)).masked_fill(~rv, 0.0)
         else:
             rv = pred_valid
-            reward = torch.zeros_like(px)
+            reward = reward0.masked_fill(~rv, 0.0)
 
         for k, v in (("preds", pred_state), ("valid", pred_valid), ("override_masks", ovr),
                      ("diffbar_rewards", reward), ("diffbar_rewards_valid", rv), ("latent_log_probs", latent_logp),
@@ -579,7 +601,8 @@ def rollout_inputs(batch: Dict[str, Tensor], feat: Dict[str, Tensor], k: int, te
 @torch.no_grad()
 def joint_future_pred(sd: SD, batch: Dict[str, Tensor], k: int = 6, sample_seed: Optional[int] = 7,
                       step_end: int = 90, test_mode: bool = False, feat: Optional[Dict[str, Tensor]] = None,
-                      return_trace: bool = False) -> Dict[str, Tensor]:
+                      return_trace: bool = False, rules_enable: Optional[Dict[str, bool]] = None, w_collision: float = 0.0,
+                      reduce_collision_with_max: bool = True) -> Dict[str, Tensor]:
     """encode -> prior latent -> dest prediction -> K-mode closed-loop rollout, as `validation_step`'s
     joint_future_pred leg (waymo_motion.py:581-598,683-690) / `test_step` (:905-934).
     Output layout after `flatten_repeat` (utils/buffer.py:92-123): [S, A, K, T, ...]."""
@@ -598,9 +621,15 @@ def joint_future_pred(sd: SD, batch: Dict[str, Tensor], k: int = 6, sample_seed:
     tf_mask = teacher_forcing_mask(rin["gt_valid"], 10, 10)  # teacher_forcing_joint_future_pred
     lat_sample, lat_logp = sample_latent(prior["mean"].repeat_interleave(k, 0), prior["std"].repeat_interleave(k, 0), det)
     goal_gt = None if "agent/goal" not in batch or test_mode else batch["agent/goal"].repeat_interleave(k, 0)
+    rules = None
+    if rules_enable is not None:  # the history traffic lights (waymo_motion.py:523-525): frozen after frame 10
+        rules = dict(enable=rules_enable, tl_valid=batch["history/tl_stop/valid"].repeat_interleave(k, 0),
+                     tl_pos=batch["history/tl_stop/pos"].repeat_interleave(k, 0),
+                     tl_state=batch["history/tl_stop/state"].repeat_interleave(k, 0))
     res = rollout(sd, **rin, tf_mask=tf_mask, latent_sample=lat_sample, latent_logp=lat_logp, dest=dest_sample,
                   goal_valid=goal_valid.repeat_interleave(k, 0), goal_gt=goal_gt, step_end=step_end,
-                  return_trace=return_trace)
+                  return_trace=return_trace, rules=rules, w_collision=w_collision,
+                  reduce_collision_with_max=reduce_collision_with_max)
     out = {}
     for name, v in res.items():
         if name in ("hidden", "final_state", "final_valid"):
@@ -617,7 +646,9 @@ def joint_future_pred(sd: SD, batch: Dict[str, Tensor], k: int = 6, sample_seed:
 
 @torch.no_grad()
 def reactive_replay(sd: SD, batch: Dict[str, Tensor], step_end: int = 90,
-                    feat: Optional[Dict[str, Tensor]] = None, return_trace: bool = False) -> Dict[str, Tensor]:
+                    feat: Optional[Dict[str, Tensor]] = None, return_trace: bool = False,
+                    rules_enable: Optional[Dict[str, bool]] = None, w_collision: float = 0.0,
+                    reduce_collision_with_max: bool = True) -> Dict[str, Tensor]:
     """`validation_step`'s reactive-replay leg (waymo_motion.py:597-611): posterior latent (deterministic = mean),
     GT destination, agents spawn over the whole episode (teacher_forcing_reactive_replay)."""
     if feat is None:
@@ -636,8 +667,13 @@ def reactive_replay(sd: SD, batch: Dict[str, Tensor], step_end: int = 90,
     rin = rollout_inputs(batch, feat, 1)
     tf_mask = teacher_forcing_mask(rin["gt_valid"], 90, 10)
     lat_logp = diag_gauss_log_prob(post["mean"], post["mean"], post["std"])
+    rules = None
+    if rules_enable is not None:  # the full-episode traffic lights (waymo_motion.py:439-441)
+        rules = dict(enable=rules_enable, tl_valid=batch["tl_stop/valid"], tl_pos=batch["tl_stop/pos"],
+                     tl_state=batch["tl_stop/state"])
     res = rollout(sd, **rin, tf_mask=tf_mask, latent_sample=post["mean"], latent_logp=lat_logp,
                   dest=batch["agent/dest"], goal_valid=goal_valid, goal_gt=batch["agent/goal"], step_end=step_end,
-                  return_trace=return_trace)
+                  return_trace=return_trace, rules=rules, w_collision=w_collision,
+                  reduce_collision_with_max=reduce_collision_with_max)
     res["latent_post_mean"] = post["mean"]
     return res

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 import trafficbots_oracle as orc
-from golden_util import CASES, load_case
+from golden_util import CASES, RULE_CASES, RULE_KEYS, RULES_ON, load_case
 
 BOOL_KEYS = ("valid", "override_masks", "diffbar_rewards_valid", "outside_map", "outside_map_this_step",
              "goal_reached", "goal_reached_this_step", "dest_reached", "dest_reached_this_step")
@@ -49,3 +49,23 @@ def test_golden_covers_corner_cases():
     # late spawn: some agent invalid at t=0 becomes valid through an override
     v = gold["jfp/valid"][0, :, 0]
     assert (~v[:, 0] & v[:, -1]).any()
+
+
+@pytest.mark.parametrize("case", RULE_CASES)
+def test_oracle_optional_rule_checks_match_reference_golden(case):
+    """the reference ran with the four optional checks and the collision reward ON (dense scenes with
+    collisions, road-edge crossings, planted red-light events, passive vehicles): the oracle's restatement
+    (`oracle/rule_checks_oracle.py`) reproduces its 8 extra violation maps bit for bit and the reward."""
+    gold, sd, batch, meta = load_case(case)
+    kw = dict(rules_enable=RULES_ON, w_collision=meta["w_collision"], reduce_collision_with_max=meta["reduce_with_max"])
+    jfp = orc.joint_future_pred(sd, batch, k=meta["K"], sample_seed=meta["sseed"], **kw)
+    rep = orc.reactive_replay(sd, batch, **kw)
+    seen = set()
+    for leg, res in (("jfp", jfp), ("replay", rep)):
+        for k in BOOL_KEYS + RULE_KEYS:
+            assert torch.equal(res[k], _g(gold, leg, k)), (leg, k)
+            if k in RULE_KEYS and res[k].any():
+                seen.add(k.replace("_this_step", ""))
+        assert (res["preds"] - gold[f"{leg}/preds"]).abs().max() <= 5e-4, leg
+        assert (res["diffbar_rewards"] - gold[f"{leg}/diffbar_rewards"]).abs().max() <= 5e-4, leg
+    assert {"collided", "run_red_light"} <= seen  # the fixtures really contain events

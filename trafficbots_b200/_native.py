@@ -41,6 +41,7 @@ EXPORTS = (
     "tb_rollout_state_bytes", "tb_rollout_state_offset", "tb_rollout_init", "tb_rollout_steps", "tb_step_front", "tb_step_back", "tb_rollout",
     "tb_launch_count", "tb_kv_tc_bytes", "tb_tc_block_count", "tb_tc_first_block", "tb_tc_selftest",
     "tb_gru_sequence", "tb_gru_workspace_bytes", "tb_mlp_head", "tb_dest_workspace_bytes", "tb_dest_logits", "tb_xlayer_tc",
+    "tb_rule_workspace_bytes", "tb_rule_checks",
 )
 
 
@@ -73,6 +74,20 @@ TbSceneIn = _ptr_struct("TbSceneIn", SCENE_IN_FIELDS)
 TbSceneOut = _ptr_struct("TbSceneOut", SCENE_OUT_FIELDS)
 TbRolloutIn = _ptr_struct("TbRolloutIn", ROLLOUT_IN_FIELDS)
 TbRolloutOut = _ptr_struct("TbRolloutOut", ROLLOUT_OUT_FIELDS)
+
+
+class TbRuleIn(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("preds", "valid", "override_masks", "outside_map_this_step", "gt_valid", "gt_pos", "gt_yaw", "gt_spd",
+                 "agent_type", "agent_size", "map_valid", "map_type", "map_pos", "map_dir", "tl_valid", "tl_pos", "tl_state")] + \
+               [("n_tl_frame", C.c_int32), ("enable_mask", C.c_int32), ("collision_size_scale", C.c_float),
+                ("w_collision", C.c_float), ("reduce_collision_with_max", C.c_int32)]
+
+
+TbRuleOut = _ptr_struct("TbRuleOut", ("violations", "diffbar_rewards", "diffbar_rewards_valid"))
+RULE_BITS = {"collided": 1, "run_road_edge": 2, "run_red_light": 4, "passive": 8}
+OPT_VIOLATION_KEYS = ("collided", "collided_this_step", "run_road_edge", "run_road_edge_this_step", "run_red_light",
+                      "run_red_light_this_step", "passive", "passive_this_step")
 
 
 def sources():
@@ -201,6 +216,10 @@ def lib() -> C.CDLL:
     L.tb_dest_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     L.tb_dest_logits.restype = C.c_int32
     L.tb_dest_logits.argtypes = [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 11
+    L.tb_rule_workspace_bytes.restype = C.c_size_t
+    L.tb_rule_workspace_bytes.argtypes = [C.POINTER(TbDims)]
+    L.tb_rule_checks.restype = C.c_int32
+    L.tb_rule_checks.argtypes = [C.POINTER(TbDims), C.POINTER(TbRuleIn), C.POINTER(TbRuleOut), C.c_void_p, C.c_void_p]
     _lib = L
     return L
 

@@ -70,17 +70,15 @@ REQUIRED: Dict[str, Any] = {
     "dynamics.cyc.max_yaw_rate": 3,
     "dynamics.ped.max_acc": 7,
     "dynamics.ped.max_yaw_rate": 7,
-    "differentiable_reward.w_collision": 0,
     "differentiable_reward.use_il_loss": True,
     "differentiable_reward.l_pos.weight": 1e-1,
     "differentiable_reward.l_rot.weight": 1e1,
     "differentiable_reward.l_rot.angular_type": "cosine",
     "differentiable_reward.l_spd.weight": 1e-1,
-    "traffic_rule_checker.enable_check_collided": False,
-    "traffic_rule_checker.enable_check_run_road_edge": False,
-    "traffic_rule_checker.enable_check_run_red_light": False,
-    "traffic_rule_checker.enable_check_passive": False,
 }
+# free keys of the hot path (every value is implemented): traffic_rule_checker.enable_check_{collided, run_road_edge,
+# run_red_light, passive} and differentiable_reward.{w_collision, reduce_collsion_with_max} -> `tb_rule_checks`;
+# enable_check_passive without enable_check_run_red_light is rejected like the reference does (NameError there).
 REQUIRED_SUFFIX = {  # `_target_` class names (module prefix may be the reference's or ours)
     "model.agent_temporal._target_": "MultiAgentGRULoop",
     "dynamics.veh._target_": "MultiPathPP",
@@ -122,15 +120,21 @@ def check_supported(cfg: Mapping) -> None:
         got = _lookup(cfg, path)
         if got is not _MISSING and not str(got).endswith(want):
             bad.append(f"{path}={got!r} (supported: *.{want})")
+    trc = _lookup(cfg, "traffic_rule_checker")
+    if isinstance(trc, Mapping) and trc.get("enable_check_passive") and not trc.get("enable_check_run_red_light"):
+        bad.append("traffic_rule_checker.enable_check_passive=True needs enable_check_run_red_light=True (the reference raises a "
+                   "NameError for this combination: utils/traffic_rule_checker.py:441-442,457-464)")
     if bad:
         raise UnsupportedConfig("trafficbots_b200 implements the default TrafficBots configuration only; unsupported: "
                                 + "; ".join(bad))
 
 
-def default_config(time_step_end: int = 90, n_joint_future: int = 6) -> Dict[str, Any]:
-    """constructor kwargs of `WaymoMotion` for the default model (everything the hot path reads)."""
+def default_config(time_step_end: int = 90, n_joint_future: int = 6, rule_checks: bool = False, w_collision: float = 0.0,
+                   reduce_collision_with_max: bool = True) -> Dict[str, Any]:
+    """constructor kwargs of `WaymoMotion` for the default model (everything the hot path reads); `rule_checks` switches the
+    four optional traffic-rule checks on, `w_collision` the collision reward."""
     cur = 10
-    return dict(
+    cfg = dict(
         time_step_current=cur, time_step_gt=90, time_step_end=time_step_end, time_step_sim_start=1, hidden_dim=128,
         n_joint_future=n_joint_future,
         pre_processing={"input": {"pe_dim": 96, "pose_pe": dict(_PE), "dropout_p_history": -1},
@@ -141,6 +145,8 @@ def default_config(time_step_end: int = 90, n_joint_future: int = 6) -> Dict[str
         teacher_forcing_training={"step_spawn_agent": cur, "step_warm_start": cur},
         teacher_forcing_reactive_replay={"step_spawn_agent": 90, "step_warm_start": cur},
         teacher_forcing_joint_future_pred={"step_spawn_agent": cur, "step_warm_start": cur},
-        traffic_rule_checker={"enable_check_collided": False, "enable_check_run_road_edge": False,
-                              "enable_check_run_red_light": False, "enable_check_passive": False},
+        traffic_rule_checker={"enable_check_collided": rule_checks, "enable_check_run_road_edge": rule_checks,
+                              "enable_check_run_red_light": rule_checks, "enable_check_passive": rule_checks},
+        differentiable_reward={"w_collision": w_collision, "reduce_collsion_with_max": reduce_collision_with_max, "use_il_loss": True},
     )
+    return cfg

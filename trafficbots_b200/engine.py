@@ -343,6 +343,54 @@ class Engine:
         self.last_t = n_step
         return self._finish(out)
 
+    def rule_checks(self, out: Dict[str, Tensor], gt: Mapping[str, Tensor], agent_type: Tensor, agent_size: Tensor,
+                    raw_map: Mapping[str, Tensor], tl: Optional[Mapping[str, Tensor]], enable: Mapping[str, bool], n_mode: int = 1,
+                    w_collision: float = 0.0, reduce_collision_with_max: bool = True, collision_size_scale: float = 1.1
+                    ) -> Dict[str, Tensor]:
+        """`tb_rule_checks`: the optional traffic-rule checks and the collision reward on the finished rollout
+        `out` (the dict returned by `rollout`).  `tl`: dict(valid [S,Ttl,TL], pos [S,Ttl,TL,2], state [S,Ttl,TL,5]) -- the
+        tensors the reference hands to `TrafficRuleChecker`.  Adds `violations/<key>` for the 8 optional keys to `out` and
+        updates `diffbar_rewards` in place when `w_collision` > 0."""
+        B, A, T = out["valid"].shape
+        S, P = raw_map["valid"].shape[:2]
+        Tg = gt["valid"].shape[1]
+        mask = sum(bit for k, bit in nt.RULE_BITS.items() if enable.get(k))
+        if (mask & 8) and not (mask & 4):
+            raise nt.TbError("enable_check_passive needs enable_check_run_red_light (in the reference the combination raises a "
+                             "NameError: traffic_rule_checker.py:441-442,457-464)")
+        need_tl = bool(mask & 12)
+        if need_tl and tl is None:
+            raise nt.TbError("rule_checks: traffic-light tensors are required for run_red_light / passive")
+        TL = tl["valid"].shape[2] if tl is not None else 1
+        Ttl = tl["valid"].shape[1] if tl is not None else 1
+        dims = self._dims(S, n_mode, A, P, TL, Tg, Tg, T)
+        if B != S * n_mode:
+            raise nt.TbError(f"rule_checks: {B} scene-modes, expected {S} x {n_mode}")
+        p = nt.dev_ptr
+        viol = torch.empty(8, B, A, T, dtype=torch.bool, device=self.device)
+        rin = nt.TbRuleIn(
+            p(out["preds"], "f32", (B, A, T, 4), "preds"), p(out["valid"], "u8", (B, A, T), "valid"),
+            p(out["override_masks"], "u8", (B, A, T), "override_masks"),
+            p(out["violations/outside_map_this_step"], "u8", (B, A, T), "outside_map_this_step"),
+            p(gt["valid"], "u8", (S, Tg, A), "gt valid"), p(gt["pos"], "f32", (S, Tg, A, 2), "gt pos"),
+            p(gt["yaw_bbox"], "f32", (S, Tg, A, 1), "gt yaw_bbox"), p(gt["spd"], "f32", (S, Tg, A, 1), "gt spd"),
+            p(agent_type, "u8", (S, A, 3), "agent_type"), p(agent_size, "f32", (S, A, 3), "agent_size"),
+            p(raw_map["valid"], "u8", (S, P, 20), "map/valid"), p(raw_map["type"], "u8", (S, P, 11), "map/type"),
+            p(raw_map["pos"], "f32", (S, P, 20, 2), "map/pos"), p(raw_map["dir"], "f32", (S, P, 20, 2), "map/dir"),
+            p(tl["valid"], "u8", (S, Ttl, TL), "tl valid") if tl is not None else None,
+            p(tl["pos"], "f32", (S, Ttl, TL, 2), "tl pos") if tl is not None else None,
+            p(tl["state"], "u8", (S, Ttl, TL, 5), "tl state") if tl is not None else None,
+            Ttl, mask, collision_size_scale, float(w_collision), int(bool(reduce_collision_with_max)))
+        rout = nt.TbRuleOut(viol.data_ptr(), out["diffbar_rewards"].data_ptr() if w_collision > 0 else None,
+                            out["diffbar_rewards_valid"].data_ptr())
+        ws = torch.empty(self.lib.tb_rule_workspace_bytes(C.byref(dims)), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            nt.check(self.lib.tb_rule_checks(C.byref(dims), C.byref(rin), C.byref(rout), ws.data_ptr(), nt.current_stream_ptr()),
+                     "tb_rule_checks")
+        for i, k in enumerate(nt.OPT_VIOLATION_KEYS):
+            out["violations/" + k] = viol[i]
+        return out
+
     def begin_rollout(self, *args, n_mode: int = 1, n_step: int = 90, **kw) -> Dict:
         """`tb_rollout_init` only; the steps are then driven one by one with `step(ctx)` (per-step `forward` use)."""
         dims, rin = self._rollout_structs(*args, n_mode, n_step, **kw)

@@ -47,16 +47,30 @@ class TeacherForcing:
 
 
 class TrafficRuleChecker:
-    """Carrier of the raw tensors the fused rule checks read (constructor signature of
-    utils/traffic_rule_checker.py:16-44; the checks themselves run inside `tb_step_back`)."""
+    """Carrier of the raw tensors the rule checks read, with the constructor signature of
+    utils/traffic_rule_checker.py:16-44.  The always-on checks (outside_map, goal / dest reached) run inside the fused decode
+    step; the four optional ones (`enable_check_*`) are evaluated right after the rollout by `tb_rule_checks`, which gives
+    the same result because none of them feeds back into the simulation."""
 
-    def __init__(self, map_boundary, map_valid, map_type, map_pos, map_dir, tl_valid=None, tl_pos=None, tl_state=None,
-                 agent_type=None, agent_size=None, agent_goal=None, agent_dest=None, enable_check_collided=False,
-                 enable_check_run_road_edge=False, enable_check_run_red_light=False, enable_check_passive=False) -> None:
-        if enable_check_collided or enable_check_run_road_edge or enable_check_run_red_light or enable_check_passive:
-            raise tb_config.UnsupportedConfig("optional traffic-rule checks are not implemented in the fused step (SURVEY 8f-2)")
+    def __init__(self, map_boundary, map_valid, map_type, map_pos, map_dir, tl_stop_valid=None, tl_stop_pos=None,
+                 tl_stop_state=None, agent_type=None, agent_size=None, agent_goal=None, agent_dest=None,
+                 enable_check_collided=False, enable_check_run_road_edge=False, enable_check_run_red_light=False,
+                 enable_check_passive=False, collision_size_scale: float = 1.1) -> None:
+        if enable_check_passive and not enable_check_run_red_light:
+            raise tb_config.UnsupportedConfig("enable_check_passive without enable_check_run_red_light raises a NameError in the "
+                                              "reference (traffic_rule_checker.py:441-442,457-464)")
         self.raw_map = {"boundary": map_boundary, "valid": map_valid, "type": map_type, "pos": map_pos, "dir": map_dir}
         self.agent_goal, self.agent_dest = agent_goal, agent_dest
+        self.enable = {"collided": bool(enable_check_collided), "run_road_edge": bool(enable_check_run_road_edge),
+                       "run_red_light": bool(enable_check_run_red_light), "passive": bool(enable_check_passive)}
+        self.tl = None
+        if tl_stop_valid is not None:
+            self.tl = {"valid": tl_stop_valid, "pos": tl_stop_pos, "state": tl_stop_state}
+        self.collision_size_scale = collision_size_scale
+
+    @property
+    def any_optional(self) -> bool:
+        return any(self.enable.values())
 
 
 class WaymoMotion(_Base):
@@ -83,7 +97,9 @@ class WaymoMotion(_Base):
             raise tb_config.UnsupportedConfig("detach_state_policy=False")
         self.tb_hparams = dict(time_step_current=time_step_current, time_step_gt=time_step_gt, time_step_end=time_step_end,
                                time_step_sim_start=time_step_sim_start, n_joint_future=n_joint_future,
-                               traffic_rule_checker=dict(traffic_rule_checker or {}))
+                               traffic_rule_checker=dict(traffic_rule_checker or {}),
+                               w_collision=float((differentiable_reward or {}).get("w_collision", 0) or 0),
+                               reduce_collision_with_max=bool((differentiable_reward or {}).get("reduce_collsion_with_max", True)))
         spec = weights.state_dict_spec()
         self.pre_processing = nn.Module()
         register_param_tree(self.pre_processing, spec, "pre_processing.", buffers=True)
@@ -198,11 +214,24 @@ class WaymoMotion(_Base):
                 feat[k] = features[k]
         args = (feat, gt, mask_teacher_forcing, features["agent_type"], features["agent_size"], rule_checker.raw_map,
                 self.model.latent_sample, self.model.latent_logp, goal.contiguous(), goal_valid.contiguous(), rule_checker.agent_goal)
+        post = dict(gt=gt, agent_type=features["agent_type"], agent_size=features["agent_size"], rc=rule_checker, n_mode=n_mode)
         if features.get("_stepwise", False):  # caller drives the steps through forward()
             self._step_ctx = eng.begin_rollout(*args, n_mode=n_mode, n_step=step_end)
+            self._step_ctx["post"] = post
             return None
-        out = eng.rollout(*args, n_mode=n_mode, n_step=step_end)
+        out = self._optional_checks(eng, eng.rollout(*args, n_mode=n_mode, n_step=step_end), post)
         return RolloutBuffer(step_start, step_end, self.tb_hparams["time_step_current"], out)
+
+    def _optional_checks(self, eng: Engine, out: Dict[str, Tensor], post: Mapping) -> Dict[str, Tensor]:
+        """optional traffic-rule checks + collision reward on the finished rollout (`tb_rule_checks`)."""
+        rc: TrafficRuleChecker = post["rc"]
+        w = self.tb_hparams["w_collision"]
+        if not rc.any_optional and w <= 0:
+            return out
+        return eng.rule_checks(out, post["gt"], post["agent_type"], post["agent_size"], rc.raw_map, rc.tl, rc.enable,
+                               n_mode=post["n_mode"], w_collision=w,
+                               reduce_collision_with_max=self.tb_hparams["reduce_collision_with_max"],
+                               collision_size_scale=rc.collision_size_scale)
 
     def forward(self, map_feature: Optional[Tensor] = None, map_valid: Optional[Tensor] = None,
                 tl_feature: Optional[Tensor] = None, tl_valid: Optional[Tensor] = None, goal_feature: Optional[Tensor] = None,
@@ -238,7 +267,8 @@ class WaymoMotion(_Base):
     def finish_rollout(self) -> RolloutBuffer:
         ctx, self._step_ctx = self._step_ctx, None
         eng = self.engine()
-        return RolloutBuffer(1, ctx["n_step"], self.tb_hparams["time_step_current"], eng._finish(ctx["out"]))
+        out = self._optional_checks(eng, eng._finish(ctx["out"]), ctx["post"])
+        return RolloutBuffer(1, ctx["n_step"], self.tb_hparams["time_step_current"], out)
 
     def _features(self, batch: Mapping[str, Tensor], f: Mapping[str, Tensor], n_mode: int, n_gt: Optional[int] = None) -> Dict:
         gt = gt_from_batch(batch, n_gt)
@@ -253,8 +283,9 @@ class WaymoMotion(_Base):
                         deterministic_action: bool, require_vis_dict: bool = False) -> RolloutBuffer:
         """waymo_motion.py:420-476: one rollout per scene with GT destination, spawning over the whole episode."""
         rc = TrafficRuleChecker(batch["map/boundary"], batch["map/valid"], batch["map/type"], batch["map/pos"], batch["map/dir"],
+                                batch.get("tl_stop/valid"), batch.get("tl_stop/pos"), batch.get("tl_stop/state"),
                                 agent_goal=batch.get("agent/goal"), agent_dest=batch.get("agent/dest"),
-                                **self.tb_hparams["traffic_rule_checker"])
+                                **self.tb_hparams["traffic_rule_checker"])  # full-episode traffic lights (:439-441)
         feats = self._features(batch, input_feature_dict, 1)
         return self.rollout(feats, latent=latent, goal=goal, goal_valid=goal_valid, mask_teacher_forcing=mask_teacher_forcing,
                             rule_checker=rc, step_start=self.tb_hparams["time_step_sim_start"],
@@ -277,6 +308,8 @@ class WaymoMotion(_Base):
         goal_log_probs = goal.log_prob(goal_sample)
         gvalid = goal_valid.repeat_interleave(K, 0)
         rc = TrafficRuleChecker(batch["map/boundary"], batch["map/valid"], batch["map/type"], batch["map/pos"], batch["map/dir"],
+                                batch.get("history/tl_stop/valid"), batch.get("history/tl_stop/pos"),
+                                batch.get("history/tl_stop/state"),  # history traffic lights, frozen after frame 10 (:523-525)
                                 agent_goal=batch.get("agent/goal"), agent_dest=goal_sample, **self.tb_hparams["traffic_rule_checker"])
         feats = self._features(batch, input_feature_dict, K)
         tf = self.teacher_forcing_joint_future_pred.get(feats["agent_valid"], 0)

@@ -19,7 +19,8 @@ N_PL_TYPE = 11
 DT = 0.1
 
 
-def _scene(seed: int, n_agent: int, n_pl: int, n_step: int, n_tl: int, zero_tl: bool, single_agent: bool):
+def _scene(seed: int, n_agent: int, n_pl: int, n_step: int, n_tl: int, zero_tl: bool, single_agent: bool,
+           area_scale: float = 1.0):
     g = torch.Generator(device="cpu")
     g.manual_seed(seed)
 
@@ -31,7 +32,7 @@ def _scene(seed: int, n_agent: int, n_pl: int, n_step: int, n_tl: int, zero_tl: 
 
     out: Dict[str, torch.Tensor] = {}
     # ---------------- map: straight polylines, 20 nodes 1 m apart ----------------
-    start = U((n_pl, 1, 2), -100.0, 100.0)
+    start = U((n_pl, 1, 2), -100.0, 100.0) * area_scale
     heading = U((n_pl, 1), -math.pi, math.pi)
     step = torch.stack([heading.cos(), heading.sin()], dim=-1)  # [P,1,2] unit step
     k = torch.arange(N_PL_NODE, dtype=torch.float32).view(1, N_PL_NODE, 1)
@@ -49,7 +50,7 @@ def _scene(seed: int, n_agent: int, n_pl: int, n_step: int, n_tl: int, zero_tl: 
     out["map/boundary"] = torch.stack([vpos[:, 0].min(), vpos[:, 0].max(), vpos[:, 1].min(), vpos[:, 1].max()])
 
     # ---------------- agents: constant acc / yaw-rate ground truth ----------------
-    p0 = U((n_agent, 2), -80.0, 80.0)
+    p0 = U((n_agent, 2), -80.0, 80.0) * area_scale
     p0[0] = U((2,), -1.0, 1.0)
     yaw0 = U((n_agent,), -math.pi, math.pi)
     spd0 = U((n_agent,), 0.0, 10.0)
@@ -113,18 +114,35 @@ def _scene(seed: int, n_agent: int, n_pl: int, n_step: int, n_tl: int, zero_tl: 
         tl_valid[:] = False
     out["tl_stop/valid"] = tl_valid
     out["tl_stop/state"] = torch.nn.functional.one_hot(RI((n_step, n_tl), 0, 5), 5).bool()
-    out["tl_stop/pos"] = U((1, n_tl, 2), -80.0, 80.0).expand(n_step, -1, -1).contiguous()
+    out["tl_stop/pos"] = (U((1, n_tl, 2), -80.0, 80.0) * area_scale).expand(n_step, -1, -1).contiguous()
     tl_yaw = U((1, n_tl), -math.pi, math.pi).expand(n_step, -1)
     out["tl_stop/dir"] = torch.stack([tl_yaw.cos(), tl_yaw.sin()], dim=-1).contiguous()
     return out
 
 
+def _plant_red_light_events(batch: Dict[str, torch.Tensor], frame: int = 5, n_event: int = 3) -> None:
+    """moves the first `n_event` stop points of every scene 1 m behind the centre of a fast vehicle at `frame` (a teacher-forced
+    frame, so the simulated agent is exactly there) and makes them valid + red at that frame: the vehicle's front box contains
+    the stop point now and not 0.1 s later = a run-red-light event (traffic_rule_checker.py:199-258).  No RNG involved."""
+    S = batch["agent/valid"].shape[0]
+    for s in range(S):
+        ok = batch["agent/valid"][s, frame] & batch["agent/type"][s, :, 0] & (batch["agent/spd"][s, frame, :, 0] >= 4.0)
+        for j, a in enumerate(ok.nonzero().flatten()[:n_event].tolist()):
+            yaw = batch["agent/yaw_bbox"][s, frame, a, 0]
+            back = torch.stack([yaw.cos(), yaw.sin()]) * 1.0
+            batch["tl_stop/pos"][s, :, j] = batch["agent/pos"][s, frame, a] - back
+            batch["tl_stop/valid"][s, frame, j] = True
+            batch["tl_stop/state"][s, frame, j] = torch.tensor([False, True, False, False, False])
+
+
 def make_batch(n_scene: int, n_agent: int = 64, n_pl: int = 1024, seed: int = 0, n_step: int = 91,
-               n_step_hist: int = 11, n_tl: int = 40, special_scenes: bool = True) -> Dict[str, torch.Tensor]:
+               n_step_hist: int = 11, n_tl: int = 40, special_scenes: bool = True, area_scale: float = 1.0,
+               plant_red_light: bool = False) -> Dict[str, torch.Tensor]:
     """A validation-style batch (`agent/*` = 91 frames of GT, `history/*` = first 11 frames) of CPU tensors.
 
     With `special_scenes`, scene 1 has no valid traffic light at all and scene 2 has exactly one valid agent
-    (the two masking corner cases called out in SURVEY.md §8a "parity hazards").
+    (the two masking corner cases called out in SURVEY.md §8a "parity hazards").  `area_scale` < 1 packs agents, map and
+    traffic lights into a smaller area (dense scenes: collisions, road-edge crossings and red-light events occur).
     """
     scenes = [
         _scene(seed + i, n_agent, n_pl, n_step, n_tl, zero_tl=special_scenes and i == 1,
@@ -132,6 +150,8 @@ def make_batch(n_scene: int, n_agent: int = 64, n_pl: int = 1024, seed: int = 0,
         for i in range(n_scene)
     ]
     batch = {k: torch.stack([s[k] for s in scenes], dim=0) for k in scenes[0]}
+    if plant_red_light:
+        _plant_red_light_events(batch)
     for k in ("valid", "pos", "z", "vel", "spd", "acc", "yaw_bbox", "yaw_rate"):
         batch[f"history/agent/{k}"] = batch[f"agent/{k}"][:, :n_step_hist].contiguous()
     for k in ("type", "role", "size", "object_id"):
