@@ -353,6 +353,72 @@ typedef struct TbRuleOut {
 size_t tb_rule_workspace_bytes(const TbDims* dims);
 int32_t tb_rule_checks(const TbDims* dims, const TbRuleIn* in, const TbRuleOut* out, void* workspace, void* stream);
 
+/* ---------------------------------------------------------------- post-processing + WOMD packing ---- */
+
+/* `WaymoPostProcessing` hyper-parameters (configs/model/traffic_bots.yaml:179-186).  `aggr_thresh` (k-means aggregation) is
+ * not implemented: the Python mirror raises for a non-empty list. */
+typedef struct TbPostCfg {
+  int32_t k_pred;            /* 6 */
+  float score_temperature;   /* 1e2; <= 0: off */
+  int32_t use_ade;           /* distance between modes: average over the future steps (1) or final displacement (0) */
+  int32_t n_mtr;             /* 0 or 3 */
+  float mtr_nms_thresh[3];   /* metres, by agent type veh / ped / cyc */
+  int32_t n_mpa;             /* 0 or 3 */
+  float mpa_nms_thresh[3];
+} TbPostCfg;
+
+/* `WaymoPostProcessing.forward` (data_modules/waymo_post_processing.py:33-81) incl. `mtr_nms` (:126-171), `traj_topk`
+ * (:173-193; returned in descending score order, the reference's order is unspecified) and `mpa_nms` (:83-124).
+ * trajs: element (s, a, mode, t) = 4 floats (x, y, yaw, spd) at trajs + s*stride_scene + a*stride_agent + mode*stride_mode + 4t
+ * (strides in floats) -- so the rollout's own [S*K, A, T, 4] output is read in place (stride_scene = K*A*T*4, stride_mode =
+ * A*T*4, stride_agent = T*4, trajs = preds + 4*step_future_start) as well as a dense [S,A,n_pred,Tf,4] tensor.
+ * scores [S,A,n_pred] (not normalised), valid [S,A], agent_type [S,A,3];  k = min(k_pred, n_pred).
+ * -> waymo_trajs [S,Tf,A,k,2], waymo_yaw / waymo_spd [S,Tf,A,k,1] (may be NULL), waymo_scores [S,A,k],
+ *    mode_idx [S,A,k] int32 (may be NULL): the input mode each output slot was taken from. */
+int32_t tb_post_process(int32_t n_scene, int32_t n_agent, int32_t n_pred, int32_t n_step, const float* trajs,
+                        int64_t stride_scene, int64_t stride_agent, int64_t stride_mode, const float* scores,
+                        const uint8_t* valid, const uint8_t* agent_type, const TbPostCfg* cfg, float* waymo_trajs,
+                        float* waymo_yaw, float* waymo_spd, float* waymo_scores, int32_t* mode_idx, void* stream);
+
+/* `WOMDMetrics.update` (models/metrics/womd.py:60-145, interactive_challenge = False): the per-scene Python loop (:124-138)
+ * becomes one CTA per scene.  Every scene's six tensors are written into ONE fixed-size record
+ *   [prediction_trajectory [m_joint,K,1,n_ds,2] f32 | prediction_score [m_joint,K] f32 | ground_truth_trajectory [A,step_gt+1,7] f32 |
+ *    object_type [A] f32 | ground_truth_is_valid [A,step_gt+1] u8 | prediction_ground_truth_indices_mask [m_joint,1] u8]
+ * so that the metrics reduction over the GPUs is a single all-gather of [n_scene, record] bytes (replaces torchmetrics' six
+ * per-state gathers, womd.py:23,44-49).  tb_womd_record_bytes returns the record size and the byte offset of each of the six
+ * sections, in the order of the reference's states: prediction_trajectory, prediction_score, ground_truth_trajectory,
+ * ground_truth_is_valid, prediction_ground_truth_indices_mask, object_type. */
+typedef struct TbWomdIn {
+  const uint8_t* agent_role;   /* [S,A,3]; [...,2] = agent to predict */
+  const uint8_t* agent_valid;  /* [S,n_step_gt_frames,A] */
+  const float* agent_pos;      /* [S,n_step_gt_frames,A,2] */
+  const float* agent_size;     /* [S,A,3] */
+  const float* agent_yaw;      /* [S,n_step_gt_frames,A,1] */
+  const float* agent_vel;      /* [S,n_step_gt_frames,A,2] */
+  const uint8_t* agent_type;   /* [S,A,3] */
+  const float* waymo_trajs;    /* [S,n_step_future,A,K,2] (tb_post_process output) */
+  const float* waymo_scores;   /* [S,A,K] or NULL (= uniform 1/K, womd.py:105-106) */
+  int32_t n_agent, n_pred, n_step_future, n_step_gt_frames;
+  int32_t step_gt, step_current; /* 90, 10 */
+  int32_t m_joint;             /* 8 (womd.py:41) */
+} TbWomdIn;
+
+typedef struct TbWomdOut {
+  float* prediction_trajectory;  /* section pointers of scene 0; scene s lives scene_stride_bytes * s further */
+  float* prediction_score;
+  float* ground_truth_trajectory;
+  uint8_t* ground_truth_is_valid;
+  uint8_t* prediction_ground_truth_indices_mask;
+  float* object_type;
+  int64_t scene_stride_bytes;    /* = tb_womd_record_bytes(...) */
+  int32_t* overflow;             /* optional device counter: scenes with more than m_joint agents to predict (the reference
+                                    fails with a shape error there); the first m_joint are kept */
+} TbWomdOut;
+
+size_t tb_womd_record_bytes(int32_t n_agent, int32_t n_pred, int32_t step_gt, int32_t step_current, int32_t m_joint,
+                            int64_t* offsets6);
+int32_t tb_womd_pack(int32_t n_scene, const TbWomdIn* in, const TbWomdOut* out, void* stream);
+
 /* Self-test of the tensor-core GEMM machinery (tcgen05.mma, TMEM, bulk-async weight staging, bf16x3 operand split):
  * d[128,128] = a[128,128] @ W^T for packed tensor-core weight block `block` (0 <= block < tb_tc_block_count());
  * mode 0: A operand staged in shared memory, mode 1: A operand in tensor memory. */

@@ -38,6 +38,15 @@ RULE_CASES = {
     "s2_a16_p96_k2_rules": (2, 16, 96, 2, 900, 2023, 7, 0.25, 0.5, True),
     "s2_a12_p64_k1_rules_sum": (2, 12, 64, 1, 950, 2023, 7, 0.2, 1.0, False),
 }
+# WaymoPostProcessing.forward + WOMDMetrics.update of the reference on seeded multi-modal trajectories
+POST_CASES = {
+    # name: (n_scene, n_agent, n_pred, scene_seed, traj_seed, mtr_nms_thresh, mpa_nms_thresh, use_ade)
+    "default": (3, 12, 6, 77, 5, [], [], True),
+    "mtr_nms": (3, 12, 14, 77, 5, [2.5, 1.0, 1.5], [], True),
+    "mpa_nms": (3, 12, 6, 77, 5, [], [2.5, 1.0, 1.5], True),
+    "mtr_mpa_fde": (3, 12, 10, 77, 5, [3.0, 1.5, 2.0], [4.0, 2.0, 3.0], False),
+    "a64_k6": (1, 64, 6, 300, 9, [], [2.5, 1.0, 1.5], True),
+}
 RULES_ON = {"enable_check_collided": True, "enable_check_run_road_edge": True, "enable_check_run_red_light": True,
             "enable_check_passive": True}
 RULE_BUF = tuple(f"violations/{k}{s}" for k in ("collided", "run_road_edge", "run_red_light", "passive") for s in ("", "_this_step"))
@@ -63,6 +72,9 @@ def checksum(tensors) -> float:
 def main() -> None:
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if "--post-only" in sys.argv:
+        make_post_goldens(out_dir)
+        return
     only_rules = "--rules-only" in sys.argv  # keeps the existing fixtures byte-identical
     for name, (S, A, P, K, seed, wseed, sseed) in ({} if only_rules else CASES).items():
         model = ref_loader.build_reference(n_agent=A, n_pl=P, n_joint_future=K)
@@ -102,6 +114,36 @@ def main() -> None:
         np.savez_compressed(path, **arrays)
         events = {k.split("/")[-1]: int(res[f"replay/{k}"].sum()) for k in RULE_BUF if not k.endswith("_this_step")}
         print(name, "->", path, f"{os.path.getsize(path) / 1024:.0f} KiB", "sticky-flag counts (replay):", events)
+    make_post_goldens(out_dir)
+
+
+def make_post_goldens(out_dir: str) -> None:
+    ref_loader.install_stubs()
+    from data_modules.waymo_post_processing import WaymoPostProcessing  # noqa: the reference's own classes
+    from models.metrics.womd import WOMDMetrics
+    arrays = {}
+    for name, (S, A, n, seed, tseed, mtr, mpa, ade) in POST_CASES.items():
+        batch = synthetic.make_batch(S, n_agent=A, n_pl=16, seed=seed)
+        valid, scores, trajs = synthetic.make_mode_trajectories(S, A, n, seed=tseed)
+        pp = WaymoPostProcessing(k_pred=6, score_temperature=1e2, mpa_nms_thresh=mpa, mtr_nms_thresh=mtr, aggr_thresh=[], n_iter_em=3,
+                                 use_ade=ade)
+        ref = pp(valid=valid, scores=scores.clone(), trajs=trajs.clone(), agent_type=batch["agent/type"])
+        m = WOMDMetrics("val", step_gt=90, step_current=10, interactive_challenge=False)
+        m.update(batch, ref["waymo_trajs"], ref["waymo_scores"])
+        for k in ("waymo_trajs", "waymo_yaw_bbox", "waymo_spd", "waymo_scores"):
+            arrays[f"{name}__{k}"] = ref[k].contiguous().numpy()
+        for k in ("prediction_trajectory", "prediction_score", "ground_truth_trajectory", "ground_truth_is_valid",
+                  "prediction_ground_truth_indices_mask", "object_type"):
+            arrays[f"{name}__{k}"] = getattr(m, k + "_gpu")[0].numpy()
+        arrays[f"{name}__meta"] = np.array([S, A, n, seed, tseed, int(ade)], dtype=np.int64)
+        arrays[f"{name}__mtr"] = np.array(mtr, dtype=np.float64)
+        arrays[f"{name}__mpa"] = np.array(mpa, dtype=np.float64)
+        arrays[f"{name}__checksum"] = np.array(checksum({"s": scores, "t": trajs, "v": valid.float()}))
+        uniform = torch.softmax(torch.log(scores / scores.sum(-1, keepdim=True)) / 1e2, -1)
+        print("post", name, "scores changed by NMS:", bool(n != 6 or (ref["waymo_scores"] - uniform).abs().max() > 1e-4))
+    path = os.path.join(out_dir, "post_cases.npz")
+    np.savez_compressed(path, **arrays)
+    print("post ->", path, f"{os.path.getsize(path) / 1024:.0f} KiB")
 
 
 if __name__ == "__main__":

@@ -69,3 +69,28 @@ def test_oracle_optional_rule_checks_match_reference_golden(case):
         assert (res["preds"] - gold[f"{leg}/preds"]).abs().max() <= 5e-4, leg
         assert (res["diffbar_rewards"] - gold[f"{leg}/diffbar_rewards"]).abs().max() <= 5e-4, leg
     assert {"collided", "run_red_light"} <= seen  # the fixtures really contain events
+
+
+@pytest.mark.parametrize("name", ["default", "mtr_nms", "mpa_nms", "mtr_mpa_fde", "a64_k6"])
+def test_post_oracle_matches_reference_golden(name):
+    """`oracle/post_oracle.py` reproduces what the reference's `WaymoPostProcessing.forward` and
+    `WOMDMetrics.update` produced for the seeded multi-modal trajectories (`oracle/make_golden.py`, POST_CASES)."""
+    import os
+
+    import numpy as np
+
+    import post_oracle as po
+    from golden_util import GOLDEN_DIR
+    from trafficbots_b200 import synthetic
+    z = np.load(os.path.join(GOLDEN_DIR, "post_cases.npz"))
+    S, A, n, seed, tseed, ade = [int(x) for x in z[f"{name}__meta"]]
+    batch = synthetic.make_batch(S, n_agent=A, n_pl=16, seed=seed)
+    valid, scores, trajs = synthetic.make_mode_trajectories(S, A, n, seed=tseed)
+    got = po.post_process(valid, scores, trajs, batch["agent/type"], 6, 1e2, list(z[f"{name}__mpa"]), list(z[f"{name}__mtr"]), bool(ade))
+    for k in ("waymo_trajs", "waymo_yaw_bbox", "waymo_spd"):
+        assert torch.equal(got[k], torch.from_numpy(z[f"{name}__{k}"])), k
+    assert (got["waymo_scores"] - torch.from_numpy(z[f"{name}__waymo_scores"])).abs().max() <= 1e-7
+    packed = po.womd_pack(batch, got["waymo_trajs"], got["waymo_scores"])
+    for k, v in packed.items():
+        w = torch.from_numpy(z[f"{name}__{k}"])
+        assert (torch.equal(v, w) if v.dtype == torch.bool else (v - w).abs().max() <= 1e-7), k

@@ -41,7 +41,7 @@ EXPORTS = (
     "tb_rollout_state_bytes", "tb_rollout_state_offset", "tb_rollout_init", "tb_rollout_steps", "tb_step_front", "tb_step_back", "tb_rollout",
     "tb_launch_count", "tb_kv_tc_bytes", "tb_tc_block_count", "tb_tc_first_block", "tb_tc_selftest",
     "tb_gru_sequence", "tb_gru_workspace_bytes", "tb_mlp_head", "tb_dest_workspace_bytes", "tb_dest_logits", "tb_xlayer_tc",
-    "tb_rule_workspace_bytes", "tb_rule_checks",
+    "tb_rule_workspace_bytes", "tb_rule_checks", "tb_post_process", "tb_womd_record_bytes", "tb_womd_pack",
 )
 
 
@@ -82,6 +82,23 @@ class TbRuleIn(C.Structure):
                  "agent_type", "agent_size", "map_valid", "map_type", "map_pos", "map_dir", "tl_valid", "tl_pos", "tl_state")] + \
                [("n_tl_frame", C.c_int32), ("enable_mask", C.c_int32), ("collision_size_scale", C.c_float),
                 ("w_collision", C.c_float), ("reduce_collision_with_max", C.c_int32)]
+
+
+class TbPostCfg(C.Structure):
+    _fields_ = [("k_pred", C.c_int32), ("score_temperature", C.c_float), ("use_ade", C.c_int32), ("n_mtr", C.c_int32),
+                ("mtr_nms_thresh", C.c_float * 3), ("n_mpa", C.c_int32), ("mpa_nms_thresh", C.c_float * 3)]
+
+
+class TbWomdIn(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("agent_role", "agent_valid", "agent_pos", "agent_size", "agent_yaw", "agent_vel",
+                                          "agent_type", "waymo_trajs", "waymo_scores")] + \
+               [(n, C.c_int32) for n in ("n_agent", "n_pred", "n_step_future", "n_step_gt_frames", "step_gt", "step_current", "m_joint")]
+
+
+class TbWomdOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("prediction_trajectory", "prediction_score", "ground_truth_trajectory",
+                                          "ground_truth_is_valid", "prediction_ground_truth_indices_mask", "object_type")] + \
+               [("scene_stride_bytes", C.c_int64), ("overflow", C.c_void_p)]
 
 
 TbRuleOut = _ptr_struct("TbRuleOut", ("violations", "diffbar_rewards", "diffbar_rewards_valid"))
@@ -220,6 +237,14 @@ def lib() -> C.CDLL:
     L.tb_rule_workspace_bytes.argtypes = [C.POINTER(TbDims)]
     L.tb_rule_checks.restype = C.c_int32
     L.tb_rule_checks.argtypes = [C.POINTER(TbDims), C.POINTER(TbRuleIn), C.POINTER(TbRuleOut), C.c_void_p, C.c_void_p]
+    L.tb_post_process.restype = C.c_int32
+    L.tb_post_process.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.POINTER(TbPostCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]
+    L.tb_womd_record_bytes.restype = C.c_size_t
+    L.tb_womd_record_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
+    L.tb_womd_pack.restype = C.c_int32
+    L.tb_womd_pack.argtypes = [C.c_int32, C.POINTER(TbWomdIn), C.POINTER(TbWomdOut), C.c_void_p]
     _lib = L
     return L
 

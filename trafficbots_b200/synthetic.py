@@ -171,3 +171,27 @@ def make_batch(n_scene: int, n_agent: int = 64, n_pl: int = 1024, seed: int = 0,
     batch["history/agent_no_sim/size"] = zf(n_ns, 3)
     batch["history/agent_no_sim/object_id"] = torch.zeros(n_scene, n_ns, dtype=torch.int64)
     return batch
+
+
+def make_mode_trajectories(n_scene: int, n_agent: int, n_pred: int, seed: int, n_step: int = 80, n_cluster: int = 4):
+    """Synthetic multi-modal predictions for the post-processing tests: every agent has `n_cluster` distinct futures and each
+    of its `n_pred` modes is one of them plus a small perturbation, so that NMS thresholds of ~1-3 m really merge modes.
+    Returns (valid [S,A] bool, scores [S,A,n_pred] unnormalised > 0, trajs [S,A,n_pred,n_step,4] = x, y, yaw, spd)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    S, A, n, T = n_scene, n_agent, n_pred, n_step
+    p0 = (torch.rand(S, A, 1, 1, 2, generator=g) - 0.5) * 100.0
+    yaw0 = (torch.rand(S, A, n_cluster, 1, generator=g) - 0.5) * 2 * math.pi
+    spd = torch.rand(S, A, n_cluster, 1, generator=g) * 12.0
+    yaw_rate = (torch.rand(S, A, n_cluster, 1, generator=g) - 0.5) * 0.3
+    pick = torch.randint(0, n_cluster, (S, A, n), generator=g)
+    t = torch.arange(1, T + 1, dtype=torch.float32).view(1, 1, 1, T) * DT
+    take = lambda x: torch.gather(x.expand(S, A, n_cluster, 1), 2, pick.unsqueeze(-1))  # noqa: E731
+    yaw = take(yaw0) + take(yaw_rate) * t  # [S,A,n,T]
+    v = take(spd).expand(-1, -1, -1, T)
+    step = torch.stack([v * yaw.cos(), v * yaw.sin()], -1) * DT
+    xy = p0 + torch.cumsum(step, dim=3) + torch.randn(S, A, n, 1, 2, generator=g) * 0.4
+    trajs = torch.cat([xy, yaw.unsqueeze(-1), v.unsqueeze(-1)], dim=-1).contiguous()
+    scores = torch.rand(S, A, n, generator=g) + 0.05
+    valid = torch.rand(S, A, generator=g) < 0.85
+    return valid, scores, trajs
