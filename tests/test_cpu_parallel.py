@@ -1,5 +1,5 @@
 """world_size-2 gloo test of the scene-sharding host logic: every scene is owned by exactly one rank, and the packed
-metrics all-gather reproduces the single-process table in scene order (including uneven shards)."""
+metrics all-gather (WOMD records, one per scene) reproduces the single-process table in scene order (including uneven shards)."""
 import os
 import socket
 
@@ -17,15 +17,22 @@ def _free_port():
     return p
 
 
-def _fake_rollout(n_scene, seed=0, A=6, K=3, T=20):
-    g = torch.Generator().manual_seed(seed)
-    preds = torch.randn(n_scene, A, K, T, 4, generator=g)
-    valid = torch.rand(n_scene, A, K, T, generator=g) < 0.8
-    viol = {k: torch.rand(n_scene, A, K, T, generator=g) < 0.2 for k in ("outside_map", "goal_reached", "dest_reached")}
-    rew = -torch.rand(n_scene, A, K, T, generator=g)
-    gt_pos = torch.randn(n_scene, T + 1, A, 2, generator=g)
-    gt_valid = torch.rand(n_scene, T + 1, A, generator=g) < 0.9
-    return preds, valid, viol, rew, gt_pos, gt_valid
+def _records(n_scene, A=6, K=3):
+    """per-scene WOMD records built on the CPU from the oracle's packing (the CUDA kernel writes the same layout)."""
+    import post_oracle as po
+    from trafficbots_b200 import synthetic
+    from trafficbots_b200.models.metrics.womd import WOMDMetrics
+    batch = synthetic.make_batch(n_scene, n_agent=A, n_pl=8, seed=3)
+    _v, scores, trajs = synthetic.make_mode_trajectories(n_scene, A, K, seed=4)
+    traj = trajs.movedim(3, 1)[..., :2].contiguous()
+    sc = scores / scores.sum(-1, keepdim=True)
+    six = po.womd_pack(batch, traj, sc)
+    m = WOMDMetrics()
+    nbytes, _off = m.record_layout(A, K)
+    rec = torch.zeros(n_scene, nbytes, dtype=torch.uint8)
+    for k, v in m.views(rec, A, K).items():
+        v.copy_(six[k])
+    return m, rec, six
 
 
 def _worker(rank, world, port, n_scene, q):
@@ -33,34 +40,41 @@ def _worker(rank, world, port, n_scene, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    preds, valid, viol, rew, gt_pos, gt_valid = _fake_rollout(n_scene)
+    m, rec, _six = _records(n_scene)
     b, e = parallel.scene_shard(n_scene, rank, world)
-    local = parallel.pack_scene_metrics(preds[b:e], valid[b:e], {k: v[b:e] for k, v in viol.items()}, rew[b:e], gt_pos[b:e],
-                                        gt_valid[b:e], step_current=5)
-    table = parallel.all_gather_scenes(local, n_scene)
-    q.put((rank, table))
+    table = parallel.all_gather_scenes(rec[b:e].contiguous(), n_scene)  # uneven shards
+    even = None
+    if n_scene % world == 0:  # the fixed-size path the bench uses: WOMDMetrics.gather
+        even = m.gather(rec[b:e].contiguous(), side_stream=False)
+    q.put((rank, table, even))
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("n_scene", [4, 5])
 def test_two_rank_gather_matches_single_process(n_scene):
-    from trafficbots_b200 import parallel
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n_scene, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=120) for _ in range(2))
+    got = {}
+    for _ in range(2):
+        r, table, even = q.get(timeout=120)
+        got[r] = (table, even)
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    preds, valid, viol, rew, gt_pos, gt_valid = _fake_rollout(n_scene)
-    ref = parallel.pack_scene_metrics(preds, valid, viol, rew, gt_pos, gt_valid, step_current=5)
-    assert ref.shape == (n_scene, len(parallel.METRIC_FIELDS))
+    m, rec, six = _records(n_scene)
     for r in range(2):
-        assert torch.allclose(got[r], ref, atol=1e-6), r
+        table, even = got[r]
+        assert torch.equal(table, rec), r  # every rank holds all scenes' records, in scene order
+        views = m.views(table, 6, 3)
+        for k, v in six.items():
+            assert torch.equal(views[k], v), (r, k)  # ... and they decode to the six tensors of WOMDMetrics.update
+        if even is not None:
+            assert torch.equal(even, rec)
 
 
 def test_scene_shard_partitions():
@@ -86,7 +100,7 @@ def test_mirror_state_dict_and_config_surface():
     b = getattr(m.model.transformer_as2pl.layers, "0").norm1.weight
     assert a.data_ptr() == b.data_ptr()
     for bad in ({"model": {"tf_cfg": {"n_head": 8}}}, {"model": {"agent_temporal": {"_target_": "x.MultiAgentGRUCell"}}},
-                {"traffic_rule_checker": {"enable_check_collided": True}}, {"dynamics": {"veh": {"max_acc": 4}}},
+                {"traffic_rule_checker": {"enable_check_passive": True}}, {"dynamics": {"veh": {"max_acc": 4}}},
                 {"model": {"goal_manager": {"goal_attr_mode": "goal_xy"}}}):
         with pytest.raises(config.UnsupportedConfig):
             WaymoMotion(**{**config.default_config(), **bad})

@@ -112,6 +112,8 @@ class ScenePipeline:
                 self.module.use_engine(None)
             if self.read_back:
                 for k, v in res.items():
+                    if k.startswith("_"):  # device-only results (e.g. the WOMD records that are all-gathered over NCCL)
+                        continue
                     h = slot.host_out.get(k)
                     if h is None or h.shape != v.shape or h.dtype != v.dtype:
                         h = torch.empty(v.shape, dtype=v.dtype).pin_memory()
