@@ -394,7 +394,7 @@ def run_ours(args):
         sc = torch.exp(out["latent_log_probs"][..., 0] + out["goal_log_probs"])
         pd = post(valid=out["valid"][:, :, 0].any(-1), scores=sc, trajs=out["preds"][:, :, :, 10:], agent_type=cb["agent/type"])
         out["_womd_records"] = womd.update(cb, pd["waymo_trajs"], pd["waymo_scores"])
-        womd.reset()
+        womd.clear()
         return out
 
     pipe2 = ScenePipeline(module, depth=depth, step_fn=step_fn, read_back=True)

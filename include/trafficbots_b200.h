@@ -129,6 +129,9 @@ size_t tb_encode_workspace_bytes(const TbDims* dims);
  * models/traffic_bots.py:109-151, models/modules/map_encoder.py:58-115, input_pe_encoder.py:41-61). */
 int32_t tb_encode_scene(const TbDims* dims, const TbSceneIn* in, const float* packed, const TbSceneOut* out,
                         void* workspace, void* stream);
+/* With `in->map_valid == NULL` only the agent / traffic-light halves run (map outputs untouched): the reference encodes the
+ * same map up to three times per step on aliased inputs (`input/`, `latent_prior/`, `latent_post/`; sc_latent.py:143-148,
+ * waymo_motion.py:581-583); callers encode it once and re-use map_feature / kv_map for the posterior pass. */
 
 /* ---------------------------------------------------------------- building blocks --------------------- */
 

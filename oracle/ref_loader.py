@@ -24,7 +24,17 @@ from typing import Any, Dict
 import torch
 from torch import nn
 
-REF_SRC = os.environ.get("TRAFFICBOTS_REF", "/root/reference/src")
+def _find_reference() -> str:
+    """`TRAFFICBOTS_REF`, else the read-only checkout of the build container, else the git-ignored copy that travels to the
+    GPU box with the repo snapshot (`tools/install_reference.sh` -> baseline/_ref/src; used for the GPU-vs-GPU baseline)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("TRAFFICBOTS_REF"), "/root/reference/src", os.path.join(here, "baseline", "_ref", "src")):
+        if cand and os.path.isfile(os.path.join(cand, "pl_modules", "waymo_motion.py")):
+            return cand
+    return os.environ.get("TRAFFICBOTS_REF", "/root/reference/src")
+
+
+REF_SRC = _find_reference()
 
 
 def reference_available() -> bool:

@@ -18,7 +18,8 @@ def pytest_collection_modifyitems(config, items):
     import torch
 
     has_gpu = torch.cuda.is_available()
-    has_ref = os.path.isdir(os.environ.get("TRAFFICBOTS_REF", "/root/reference/src"))
+    import ref_loader
+    has_ref = ref_loader.reference_available()  # /root/reference (build container) or baseline/_ref/src (shipped copy)
     for item in items:
         if "gpu" in item.keywords and not has_gpu:
             item.add_marker(pytest.mark.skip(reason="no CUDA device"))

@@ -457,15 +457,21 @@ extern "C" int32_t tb_encode_scene(const TbDims* dims, const TbSceneIn* in, cons
   int rc = check_dims(dims);
   if (rc != TB_OK) return rc;
   if (!in || !packed || !out || !workspace) return TB_ERR_NULL;
-  const void* req[] = {in->map_valid,  in->map_type,  in->map_pos,     in->map_dir,   in->agent_valid,    in->agent_pos,
-                       in->agent_yaw,  in->agent_vel, in->agent_spd,   in->agent_yaw_rate, in->agent_acc, in->agent_size,
-                       in->agent_type, in->tl_valid,  in->tl_state,    in->tl_pos,    in->tl_dir,         out->map_feature,
-                       out->map_feature_valid, out->agent_feature, out->tl_feature, out->kv_map, out->kv_tl};
+  // in->map_valid == NULL: agents / traffic lights only (the map part of the scene was encoded by an earlier call, e.g. the
+  // posterior pass over the full episode re-uses the map features and K|V caches of the history pass, sc_latent.py:143-148)
+  const bool do_map = in->map_valid != nullptr;
+  const void* req[] = {in->agent_valid, in->agent_pos, in->agent_yaw, in->agent_vel, in->agent_spd, in->agent_yaw_rate, in->agent_acc,
+                       in->agent_size,  in->agent_type, in->tl_valid, in->tl_state, in->tl_pos,  in->tl_dir, out->agent_feature,
+                       out->tl_feature, out->kv_tl};
   for (const void* p : req)
     if (!p) return TB_ERR_NULL;
-  if (!aligned16(packed) || !aligned16(workspace) || !aligned16(out->map_feature) || !aligned16(out->agent_feature) ||
-      !aligned16(out->tl_feature) || !aligned16(out->kv_map) || !aligned16(out->kv_tl))
+  const void* req_map[] = {in->map_type, in->map_pos, in->map_dir, out->map_feature, out->map_feature_valid, out->kv_map};
+  if (do_map)
+    for (const void* p : req_map)
+      if (!p) return TB_ERR_NULL;
+  if (!aligned16(packed) || !aligned16(workspace) || !aligned16(out->agent_feature) || !aligned16(out->tl_feature) || !aligned16(out->kv_tl))
     return TB_ERR_ALIGN;
+  if (do_map && (!aligned16(out->map_feature) || !aligned16(out->kv_map))) return TB_ERR_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   const TbDims d = *dims;
   constexpr int R = ROW_TILE;
@@ -480,6 +486,7 @@ extern "C" int32_t tb_encode_scene(const TbDims* dims, const TbSceneIn* in, cons
     if (!set_max_smem(k_encode_tl<R>, (int)sizeof(TileSmem<R>))) return TB_ERR_LAUNCH;
     smem_attr_mark(attr_set);
   }
+  if (do_map) {
   // 1. polyline encoder: tcgen05 kernel; TB_DISABLE_TC=1 selects the fp32 CUDA-core kernel (verification aid)
   if (tc_enabled()) {
     const char* v1 = getenv("TB_POLYLINE_V1");  // A/B: the first version (one thread per node row)
@@ -518,6 +525,7 @@ extern "C" int32_t tb_encode_scene(const TbDims* dims, const TbSceneIn* in, cons
     rc = launch_pack_kv_tc(out->kv_map, out->map_feature_valid, 3 * d.n_scene, d.n_scene, d.n_pl, out->kv_map_tc, out->n_key_map, st);
     if (rc != TB_OK) return rc;
   }
+  }  // do_map
   // 4. agent / traffic-light history encoders
   const long n_ag = (long)d.n_scene * d.n_step_hist * d.n_agent;
   k_encode_agent_hist<R><<<(unsigned)((n_ag + R - 1) / R), NT, sizeof(TileSmem<R>), st>>>(d, *in, packed, out->agent_feature);

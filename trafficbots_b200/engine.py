@@ -87,43 +87,57 @@ class Engine:
     def _dims(self, S, K, A, P, TL, Th, Tg, T) -> nt.TbDims:
         return nt.TbDims(S, K, A, P, TL, Th, Tg, T, self.rollout_cluster)
 
-    def encode_scene(self, batch: Mapping[str, Tensor], prefix: str = "history/") -> SceneFeatures:
-        """batch: reference batch dict (CUDA tensors). Uses map/* and `{prefix}agent/*`, `{prefix}tl_stop/*`."""
+    def encode_scene(self, batch: Mapping[str, Tensor], prefix: str = "history/", share_map: Optional[Mapping[str, Tensor]] = None
+                     ) -> SceneFeatures:
+        """batch: reference batch dict (CUDA tensors). Uses map/* and `{prefix}agent/*`, `{prefix}tl_stop/*`.
+        `share_map`: features of an earlier `encode_scene` of the SAME scenes: the map is not encoded again (its features
+        and K|V caches are taken from there), only the agent / traffic-light tensors under `prefix` are."""
         mv = batch["map/valid"]
         S, P, N = mv.shape
         if N != 20:
             raise nt.TbError("n_pl_node must be 20")
-        av = batch[prefix + "agent/valid"]
+        if prefix == "sc/":  # the re-keyed history tensors of SceneCentricPreProcessing (`sc/agent_*`, `sc/tl_*`)
+            ak, tk = (lambda k: f"sc/agent_{k}"), (lambda k: f"sc/tl_{k}")
+        else:
+            ak, tk = (lambda k: f"{prefix}agent/{k}"), (lambda k: f"{prefix}tl_stop/{k}")
+        av = batch[ak("valid")]
         Th, A = av.shape[1], av.shape[2]
-        TL = batch[prefix + "tl_stop/valid"].shape[2]
+        TL = batch[tk("valid")].shape[2]
         dims = self._dims(S, 1, A, P, TL, Th, Th, 1)
         g = lambda k: batch[k]  # noqa: E731
-        a = prefix + "agent/"
-        tl = prefix + "tl_stop/"
+        p = nt.dev_ptr
         sin = nt.TbSceneIn(
-            nt.dev_ptr(mv, "u8", (S, P, 20), "map/valid"), nt.dev_ptr(g("map/type"), "u8", (S, P, 11), "map/type"),
-            nt.dev_ptr(g("map/pos"), "f32", (S, P, 20, 2), "map/pos"), nt.dev_ptr(g("map/dir"), "f32", (S, P, 20, 2), "map/dir"),
-            nt.dev_ptr(av, "u8", (S, Th, A), a + "valid"), nt.dev_ptr(g(a + "pos"), "f32", (S, Th, A, 2), a + "pos"),
-            nt.dev_ptr(g(a + "yaw_bbox"), "f32", (S, Th, A, 1), a + "yaw_bbox"),
-            nt.dev_ptr(g(a + "vel"), "f32", (S, Th, A, 2), a + "vel"), nt.dev_ptr(g(a + "spd"), "f32", (S, Th, A, 1), a + "spd"),
-            nt.dev_ptr(g(a + "yaw_rate"), "f32", (S, Th, A, 1), a + "yaw_rate"),
-            nt.dev_ptr(g(a + "acc"), "f32", (S, Th, A, 1), a + "acc"), nt.dev_ptr(g(a + "size"), "f32", (S, A, 3), a + "size"),
-            nt.dev_ptr(g(a + "type"), "u8", (S, A, 3), a + "type"), nt.dev_ptr(g(tl + "valid"), "u8", (S, Th, TL), tl + "valid"),
-            nt.dev_ptr(g(tl + "state"), "u8", (S, Th, TL, 5), tl + "state"),
-            nt.dev_ptr(g(tl + "pos"), "f32", (S, Th, TL, 2), tl + "pos"), nt.dev_ptr(g(tl + "dir"), "f32", (S, Th, TL, 2), tl + "dir"))
+            p(mv, "u8", (S, P, 20), "map/valid") if share_map is None else None,
+            p(g("map/type"), "u8", (S, P, 11), "map/type"),
+            p(g("map/pos"), "f32", (S, P, 20, 2), "map/pos"), p(g("map/dir"), "f32", (S, P, 20, 2), "map/dir"),
+            p(av, "u8", (S, Th, A), ak("valid")), p(g(ak("pos")), "f32", (S, Th, A, 2), ak("pos")),
+            p(g(ak("yaw_bbox")), "f32", (S, Th, A, 1), ak("yaw_bbox")),
+            p(g(ak("vel")), "f32", (S, Th, A, 2), ak("vel")), p(g(ak("spd")), "f32", (S, Th, A, 1), ak("spd")),
+            p(g(ak("yaw_rate")), "f32", (S, Th, A, 1), ak("yaw_rate")),
+            p(g(ak("acc")), "f32", (S, Th, A, 1), ak("acc")), p(g(ak("size")), "f32", (S, A, 3), ak("size")),
+            p(g(ak("type")), "u8", (S, A, 3), ak("type")), p(g(tk("valid")), "u8", (S, Th, TL), tk("valid")),
+            p(g(tk("state")), "u8", (S, Th, TL, 5), tk("state")),
+            p(g(tk("pos")), "f32", (S, Th, TL, 2), tk("pos")), p(g(tk("dir")), "f32", (S, Th, TL, 2), tk("dir")))
         dev = self.device
         f = SceneFeatures()
-        f["map_feature"] = torch.empty(S, P, 128, device=dev)
-        f["map_feature_valid"] = torch.empty(S, P, dtype=torch.bool, device=dev)
+        map_keys = ("map_feature", "map_feature_valid", "_kv_map", "_kv_map_tc", "_n_key_map")
+        if share_map is not None:
+            for k in map_keys:
+                f[k] = share_map[k]
+            if tuple(f["map_feature"].shape) != (S, P, 128):
+                raise nt.TbError("encode_scene: share_map comes from a different batch shape")
+        else:
+            f["map_feature"] = torch.empty(S, P, 128, device=dev)
+            f["map_feature_valid"] = torch.empty(S, P, dtype=torch.bool, device=dev)
+            f["_kv_map"] = torch.empty(3, S, P, 256, device=dev)
+            f["_kv_map_tc"] = torch.empty(self.lib.tb_kv_tc_bytes(C.byref(dims), 0), dtype=torch.uint8, device=dev)
+            f["_n_key_map"] = torch.empty(S, dtype=torch.int32, device=dev)
         f["agent_feature"] = torch.empty(S, Th, A, 128, device=dev)
         f["agent_feature_valid"] = av
         f["tl_feature"] = torch.empty(S, Th, TL, 128, device=dev)
-        f["tl_feature_valid"] = batch[tl + "valid"]
-        f["_kv_map"] = torch.empty(3, S, P, 256, device=dev)
+        f["tl_feature_valid"] = batch[tk("valid")]
         f["_kv_tl"] = torch.empty(3, S, Th, TL, 256, device=dev)
-        f["_kv_map_tc"] = torch.empty(self.lib.tb_kv_tc_bytes(C.byref(dims), 0), dtype=torch.uint8, device=dev)
         f["_kv_tl_tc"] = torch.empty(self.lib.tb_kv_tc_bytes(C.byref(dims), 1), dtype=torch.uint8, device=dev)
-        f["_n_key_map"] = torch.empty(S, dtype=torch.int32, device=dev)
         f["_n_key_tl"] = torch.empty(S, Th, dtype=torch.int32, device=dev)
         sout = nt.TbSceneOut(f["map_feature"].data_ptr(), f["map_feature_valid"].data_ptr(), f["agent_feature"].data_ptr(),
                              f["tl_feature"].data_ptr(), f["_kv_map"].data_ptr(), f["_kv_tl"].data_ptr(),

@@ -126,6 +126,10 @@ class WOMDMetrics:
         if self._comm is not None:
             torch.cuda.current_stream().wait_stream(self._comm)
 
+    def aggregate_on_cpu(self, records: Tensor) -> None:
+        """reference womd.py:165-175 copies the six gathered tensors to the host after every step; here the packed records
+        stay on the device (`self.records`) until `compute()` -- nothing to do per step."""
+
     def compute(self) -> Dict[str, List[Tensor]]:
         """the motion-metrics op inputs, as the reference's `compute()` returns them (:153-163): one entry per update()."""
         A, K = self._shape
@@ -136,4 +140,8 @@ class WOMDMetrics:
         return out
 
     def reset(self) -> None:
+        """the reference resets its per-step torchmetrics states after `aggregate_on_cpu` (waymo_motion.py:659-660); the records
+        of the epoch are kept until `clear()`."""
+
+    def clear(self) -> None:
         self.records = []

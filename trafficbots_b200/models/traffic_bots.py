@@ -62,6 +62,11 @@ class LatentEncoder(_Head):
 
 
 class GoalManager(_Head):
+    @torch.no_grad()
+    def get_gt_goal(self, agent_valid: Tensor, gt_goal: Tensor, gt_dest: Tensor):
+        """goal_manager.py:49-74, goal_attr_mode "dest": the GT destination index, valid for agents seen in the history."""
+        return gt_dest, agent_valid.any(1)
+
     def pred_goal(self, agent_type: Tensor, map_type: Tensor, agent_state: Tensor = None, **feat) -> DestCategorical:
         """`GoalManager.pred_goal` -> `DestPredictor.forward`, mode mlp (src/models/goal_manager.py:77-81,202-333)."""
         probs, _logp, valid = self._model()._engine().dest_predictor(feat, agent_type, map_type)
@@ -102,12 +107,29 @@ class TrafficBots(nn.Module):
         import weakref
         self.__dict__["_owner"] = weakref.ref(owner)
 
-    def encode_input_features(self, batch: Mapping[str, Tensor] = None, prefix: str = "history/", **kw) -> SceneFeatures:
+    def encode_input_features(self, batch: Mapping[str, Tensor] = None, prefix: str = "history/", raw=None, **kw) -> SceneFeatures:
         """SceneCentricInput + encode_input_features (sc_input.py:98-140, traffic_bots.py:109-151) fused: consumes the
-        RAW scene tensors (`map/*`, `{prefix}agent/*`, `{prefix}tl_stop/*`); positional encodings are computed inside the
-        kernels instead of being materialised (`input/map_pe` alone is 252 MB at 32 scenes in the reference).
+        RAW scene tensors; positional encodings are computed inside the kernels instead of being materialised
+        (`input/map_pe` alone is 252 MB at 32 scenes in the reference).  Two call forms:
+          * the reference's, `encode_input_features(**input_dict)` with the dict built from the `input/` / `latent_prior/` /
+            `latent_post/` keys of `pre_processing(batch)` (waymo_motion.py:577-583): the `raw` entry is the `RawScene` handle
+            of that group.  A handle that was already encoded returns its cached features (`latent_prior` aliases `input` in
+            eval mode), and a handle with `map_from` re-uses that group's map features (the posterior pass);
+          * `encode_input_features(batch, prefix=...)` on a raw batch dict (`map/*`, `{prefix}agent/*`, `{prefix}tl_stop/*`).
         Returns the reference's feature dict (+ private K|V caches)."""
+        if raw is not None:
+            if raw.features is None:
+                share = None
+                if raw.map_from is not None:
+                    if raw.map_from.features is None:
+                        raw.map_from.features = self._engine().encode_scene(raw.map_from.batch, raw.map_from.prefix)
+                    share = raw.map_from.features
+                raw.features = self._engine().encode_scene(raw.batch, raw.prefix, share_map=share)
+            return raw.features
         if batch is None:
+            if "agent_attr" in kw or "map_pe" in kw:
+                raise nt.TbError("encode_input_features: got materialised attr / pe tensors; use trafficbots_b200's pre_processing "
+                                 "modules (data_modules/scene_centric.py), which pass the raw tensors through a `raw` handle")
             batch = kw
         return self._engine().encode_scene(batch, prefix)
 

@@ -13,6 +13,7 @@ If pytorch_lightning is importable the class derives from `LightningModule`, oth
 """
 from __future__ import annotations
 
+from collections import OrderedDict
 from typing import Dict, Mapping, Optional, Tuple, Union
 
 import torch
@@ -21,7 +22,10 @@ from torch import Tensor, nn
 from .. import _native as nt
 from .. import config as tb_config
 from .. import host, weights
+from ..data_modules.scene_centric import SceneCentricInput, SceneCentricLatent, SceneCentricPreProcessing
+from ..data_modules.waymo_post_processing import WaymoPostProcessing
 from ..engine import Engine, gt_from_batch, raw_map_from_batch
+from ..models.metrics.womd import WOMDMetrics
 from ..models.distributions import DestCategorical, DiagGaussian
 from ..models.traffic_bots import TrafficBots, register_param_tree
 from ..utils.buffer import RolloutBuffer
@@ -30,6 +34,28 @@ try:  # pragma: no cover - Lightning is optional in this image
     from pytorch_lightning import LightningModule as _Base
 except Exception:  # noqa: BLE001
     _Base = nn.Module
+
+
+class _Recorder:
+    """default stand-in for the reference's torchmetrics / submission objects (`err_metrics_*`, `rule_metrics_*`,
+    `train_metrics_*`, `sub_womd_*`): remembers the keyword tensors of the last call.  Replace the attribute with the
+    reference's own object to get its behaviour -- the call sites pass exactly the reference's keywords."""
+
+    def __init__(self, name: str) -> None:
+        self.name, self.last, self.n_call = name, None, 0
+
+    def __call__(self, *args, **kw):
+        self.last, self.n_call = (args, kw), self.n_call + 1
+        return {}
+
+    add_to_submissions = __call__
+
+    def reset(self) -> None:
+        pass
+
+
+class _HParams(dict):
+    __getattr__ = dict.__getitem__
 
 
 class TeacherForcing:
@@ -101,15 +127,15 @@ class WaymoMotion(_Base):
                                w_collision=float((differentiable_reward or {}).get("w_collision", 0) or 0),
                                reduce_collision_with_max=bool((differentiable_reward or {}).get("reduce_collsion_with_max", True)))
         spec = weights.state_dict_spec()
-        self.pre_processing = nn.Module()
-        register_param_tree(self.pre_processing, spec, "pre_processing.", buffers=True)
-        for pp in ("input", "latent"):
-            m = getattr(self.pre_processing, pp)
-            m.pl_node_ohe.copy_(torch.eye(weights.N_PL_NODE))
-            for who in ("agent", "map", "tl"):
-                pe = getattr(m, f"pose_pe_{who}")
-                pe.pe_xy.freqs.copy_(weights.pe_freqs_xy())
-                pe.pe_yaw.freqs.copy_(weights.pe_freqs_yaw())
+        # pre_processing: the reference's Sequential of three modules, under the same names (state_dict keys
+        # `pre_processing.{input,latent}.*`), waymo_motion.py:66-72
+        pp = dict(pre_processing or {})
+        drop = ("_target_", "_recursive_", "_convert_")
+        ppk = lambda name: {k: v for k, v in dict(pp.get(name) or {}).items() if k not in drop}  # noqa: E731
+        self.pre_processing = nn.Sequential(OrderedDict([
+            ("scene_centric", SceneCentricPreProcessing(time_step_current=time_step_current, data_size=data_size)),
+            ("input", SceneCentricInput(time_step_current=time_step_current, data_size=data_size, **ppk("input"))),
+            ("latent", SceneCentricLatent(time_step_current=time_step_current, data_size=data_size, **ppk("latent")))]))
         mcfg = {k: v for k, v in dict(model or {}).items() if k not in ("_target_", "hidden_dim")}
         self.model = TrafficBots(hidden_dim=hidden_dim, **mcfg)
         self.model.set_owner(self)
@@ -118,6 +144,26 @@ class WaymoMotion(_Base):
         self.teacher_forcing_training = TeacherForcing(**(teacher_forcing_training or {}))
         self.teacher_forcing_reactive_replay = TeacherForcing(**(teacher_forcing_reactive_replay or {"step_spawn_agent": 90}))
         self.teacher_forcing_joint_future_pred = TeacherForcing(**(teacher_forcing_joint_future_pred or {}))
+        wpp = {k: v for k, v in dict(waymo_post_processing or {}).items() if k not in ("_target_",)}
+        self.waymo_post_processing = WaymoPostProcessing(**wpp)
+        self.womd_metrics_reactive_replay = WOMDMetrics("reactive_replay", time_step_end, time_step_current, interactive_challenge)
+        self.womd_metrics_joint_future_pred = WOMDMetrics("joint_future_pred", time_step_end, time_step_current, interactive_challenge)
+        # optional consumers a caller may attach (the reference's torchmetrics / submission objects are outside the hot path):
+        # callables `sink(name, **tensors)` invoked by validation_step / test_step with what the reference passes to
+        # err_metrics / rule_metrics / train_metrics / sub_womd (waymo_motion.py:613-668,691-733,936-944)
+        self.metric_sinks = []
+        for leg in ("reactive_replay", "joint_future_pred"):
+            setattr(self, f"err_metrics_{leg}", _Recorder(f"err_metrics_{leg}"))
+            setattr(self, f"rule_metrics_{leg}", _Recorder(f"rule_metrics_{leg}"))
+            setattr(self, f"sub_womd_{leg}", _Recorder(f"sub_womd_{leg}"))
+        self.train_metrics_reactive_replay = _Recorder("train_metrics_reactive_replay")
+        if _Base is nn.Module:  # what LightningModule would provide; the reference's step methods read them
+            self.__dict__["hparams"] = _HParams(time_step_current=time_step_current, time_step_gt=time_step_gt, time_step_end=time_step_end,
+                                                time_step_sim_start=time_step_sim_start, n_video_batch=n_video_batch,
+                                                n_joint_future=n_joint_future, interactive_challenge=interactive_challenge)
+            self.__dict__["current_epoch"] = 0
+            self.__dict__["global_rank"] = 0
+            self.__dict__["logger"] = None
         self._eng: Optional[Engine] = None
         self._eng_slot: Optional[Engine] = None
         self._packed_version = None
@@ -318,3 +364,109 @@ class WaymoMotion(_Base):
                            deterministic_latent=det, deterministic_action=True, require_vis_dict=require_vis_dict)
         buf.flatten_repeat(K)
         return buf, goal_sample.view(S, K, A).transpose(1, 2), goal_log_probs.view(S, K, A).transpose(1, 2)
+
+    # ------------------------------------------------------------------------------------------------ eval loop
+    def _split(self, batch: Mapping, group: str) -> Dict:
+        return {k.split(group + "/")[-1]: v for k, v in batch.items() if (group + "/") in k}
+
+    def _emit(self, name: str, **tensors) -> None:
+        for sink in self.metric_sinks:
+            sink(name, **tensors)
+
+    @torch.no_grad()
+    def validation_step(self, batch: Dict[str, Tensor], batch_idx: int = 0) -> Dict:
+        """waymo_motion.py:574-733 without the video logging: pre_processing, the three `encode_input_features` calls (the
+        aliased ones are served from the first), GT / predicted destination, posterior / prior latent, `reactive_replay`,
+        `joint_future_pred`, Waymo post-processing and the WOMD packing of both legs.  Returns what the reference feeds its
+        metric objects; the same tensors are pushed to `self.metric_sinks`."""
+        batch = self.pre_processing(batch)
+        input_dict, post_dict, prior_dict = self._split(batch, "input"), self._split(batch, "latent_post"), self._split(batch, "latent_prior")
+        input_feature_dict = self.model.encode_input_features(**input_dict)
+        latent_post_feature_dict = self.model.encode_input_features(**post_dict)
+        latent_prior_feature_dict = self.model.encode_input_features(**prior_dict)
+        goal_gt, goal_valid = self.model.goal_manager.get_gt_goal(agent_valid=input_dict["agent_valid"], gt_dest=batch["gt/dest"],
+                                                                  gt_goal=batch["gt/goal"])
+        goal_pred = self.model.goal_manager.pred_goal(agent_type=batch["ref/agent_type"], map_type=batch["ref/map_type"],
+                                                      agent_state=batch["ref/agent_state"], **input_feature_dict)
+        latent_post = self.model.latent_encoder(posterior=True, **latent_post_feature_dict)
+        latent_prior = self.model.latent_encoder(**latent_prior_feature_dict)
+        t0 = self.tb_hparams["time_step_sim_start"]
+        gt_valid = batch["gt/valid"][:, t0:].transpose(1, 2)
+        gt_states = batch["gt/state"][:, t0:].transpose(1, 2)
+        out: Dict = {"goal_pred": goal_pred, "goal_gt": goal_gt, "goal_valid": goal_valid, "latent_post": latent_post,
+                     "latent_prior": latent_prior}
+
+        # ! reactive_replay: scene reconstruction given the complete episode (:597-668)
+        buf = self.reactive_replay(batch=batch, input_feature_dict=input_feature_dict,
+                                   mask_teacher_forcing=self.teacher_forcing_reactive_replay.get(batch["gt/valid"], 0),
+                                   latent=latent_post, goal=goal_gt, goal_valid=goal_valid, deterministic_latent=True,
+                                   deterministic_action=True, require_vis_dict=False)
+        buf.flatten_repeat(1)
+        self._emit("err_metrics_reactive_replay", pred_valid=buf.valid, pred_states=buf.preds, gt_valid=gt_valid, gt_states=gt_states,
+                   override_masks=buf.override_masks, agent_role=batch["ref/agent_role"])
+        self._emit("rule_metrics_reactive_replay", valid=buf.valid, override_masks=buf.override_masks, agent_type=batch["ref/agent_type"],
+                   **{k: buf.violations[k] for k in ("outside_map", "collided", "run_road_edge", "run_red_light", "passive",
+                                                     "goal_reached", "dest_reached")})
+        self._emit("train_metrics_reactive_replay", pred_valid=buf.valid.squeeze(2), diffbar_rewards_valid=buf.diffbar_rewards_valid.squeeze(2),
+                   diffbar_rewards=buf.diffbar_rewards.squeeze(2), override_masks=buf.override_masks.squeeze(2),
+                   agent_role=batch["ref/agent_role"], goal_valid=goal_valid, goal_pred=goal_pred, goal_gt=goal_gt,
+                   latent_post=latent_post, latent_prior=latent_prior)
+        pred_dict = self.waymo_post_processing(valid=buf.valid[:, :, 0].any(-1), scores=torch.ones_like(buf.preds[:, :, :, 0, 0]),
+                                               trajs=buf.preds[:, :, :, buf.step_future_start:], agent_type=batch["ref/agent_type"])
+        out["womd_records_reactive_replay"] = self.womd_metrics_reactive_replay.update(batch, pred_dict["waymo_trajs"], pred_dict["waymo_scores"])
+        out["reactive_replay"], out["pred_dict_reactive_replay"] = buf, pred_dict
+
+        # ! joint_future_pred (:683-722)
+        buf, goal_sample, goal_log_probs = self.joint_future_pred(batch=batch, input_feature_dict=input_feature_dict, latent=latent_prior,
+                                                                  goal=goal_pred, goal_valid=goal_valid, require_vis_dict=False)
+        self._emit("err_metrics_joint_future_pred", pred_valid=buf.valid, pred_states=buf.preds, gt_valid=gt_valid, gt_states=gt_states,
+                   override_masks=buf.override_masks, agent_role=batch["ref/agent_role"])
+        self._emit("rule_metrics_joint_future_pred", valid=buf.valid, override_masks=buf.override_masks, agent_type=batch["ref/agent_type"],
+                   **{k: buf.violations[k] for k in ("outside_map", "collided", "run_road_edge", "run_red_light", "passive",
+                                                     "goal_reached", "dest_reached")})
+        pred_dict = self.waymo_post_processing(valid=buf.valid[:, :, 0].any(-1),
+                                               scores=torch.exp(buf.latent_log_probs[..., 0] + goal_log_probs),
+                                               trajs=buf.preds[:, :, :, buf.step_future_start:], agent_type=batch["ref/agent_type"])
+        out["womd_records_joint_future_pred"] = self.womd_metrics_joint_future_pred.update(batch, pred_dict["waymo_trajs"],
+                                                                                           pred_dict["waymo_scores"])
+        self._emit("sub_womd_joint_future_pred", waymo_trajs=pred_dict["waymo_trajs"], waymo_scores=pred_dict["waymo_scores"],
+                   mask_pred=batch["history/agent/role"][..., 2] if "history/agent/role" in batch else None)
+        out["joint_future_pred"], out["pred_dict_joint_future_pred"] = buf, pred_dict
+        out["goal_sample"], out["goal_log_probs"] = goal_sample, goal_log_probs
+        return out
+
+    @torch.no_grad()
+    def test_step(self, batch: Dict[str, Tensor], batch_idx: int = 0) -> Dict:
+        """waymo_motion.py:902-944: only the history is available; K joint futures from the prior latent and the predicted
+        destination, post-processed for the submission writer (attach one through `metric_sinks`)."""
+        batch = self.pre_processing(batch)
+        input_dict, prior_dict = self._split(batch, "input"), self._split(batch, "latent_prior")
+        input_feature_dict = self.model.encode_input_features(**input_dict)
+        latent_prior_feature_dict = self.model.encode_input_features(**prior_dict)
+        goal_valid = input_dict["agent_valid"].any(1)
+        goal_pred = self.model.goal_manager.pred_goal(agent_type=batch["ref/agent_type"], map_type=batch["ref/map_type"],
+                                                      agent_state=batch["ref/agent_state"], **input_feature_dict)
+        latent_prior = self.model.latent_encoder(**latent_prior_feature_dict)
+        for k in ("valid", "vel", "acc", "yaw_rate", "pos", "yaw_bbox", "spd", "size"):
+            batch[f"agent/{k}"] = batch[f"history/agent/{k}"]
+        buf, goal_sample, goal_log_probs = self.joint_future_pred(batch=batch, input_feature_dict=input_feature_dict, latent=latent_prior,
+                                                                  goal=goal_pred, goal_valid=goal_valid, require_vis_dict=False)
+        pred_dict = self.waymo_post_processing(valid=buf.valid[:, :, 0].any(-1),
+                                               scores=torch.exp(buf.latent_log_probs[..., 0] + goal_log_probs),
+                                               trajs=buf.preds[:, :, :, buf.step_future_start:], agent_type=batch["ref/agent_type"])
+        self._emit("sub_womd_joint_future_pred", waymo_trajs=pred_dict["waymo_trajs"], waymo_scores=pred_dict["waymo_scores"],
+                   mask_pred=batch["history/agent/role"][..., 2] if "history/agent/role" in batch else None,
+                   object_id=batch.get("history/agent/object_id"), scenario_center=batch.get("scenario_center"),
+                   scenario_yaw=batch.get("scenario_yaw"), scenario_id=batch.get("scenario_id"))
+        return {"joint_future_pred": buf, "pred_dict": pred_dict, "goal_sample": goal_sample, "goal_log_probs": goal_log_probs}
+
+    def training_step(self, batch: Dict[str, Tensor], batch_idx: int = 0):
+        """waymo_motion.py:356-418.  The forward of the training step runs on this path (posterior latent, teacher-forced then
+        closed-loop `reactive_replay`), but back-propagation through the fused rollout (`tb_rollout_backward`) is
+        not implemented: parameters are `requires_grad=False` and training must use the reference implementation."""
+        raise tb_config.UnsupportedConfig("training_step: the fused rollout has no backward pass (BASELINE.json configs[3] is out of "
+                                          "this implementation's scope); train with the reference, evaluate / test with this module")
+
+    def configure_optimizers(self):
+        raise tb_config.UnsupportedConfig("configure_optimizers: inference-only module (see training_step)")
+
