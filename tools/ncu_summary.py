@@ -2,6 +2,10 @@
 
   python tools/ncu_summary.py launches <launches.csv>        per-kernel totals / shares of a launch list
   python tools/ncu_summary.py report <file.ncu-rep>          key metrics of every captured launch (`--set full`)
+  python tools/ncu_summary.py traffic <file.ncu-rep> <key> <summary file> [json]
+                                                             dram bytes per launch of the FIRST captured launch -> entry `key`
+                                                             (e.g. config1) of profiles/traffic.json, which bench.py reads for
+                                                             `roofline.traffic`
 """
 from __future__ import annotations
 
@@ -65,5 +69,36 @@ def report(path: str) -> None:
                 print(f"   {k:88s} {row[i]:>16s} {units[i]}")
 
 
+def traffic(path: str, key: str, summary: str, out: str = "profiles/traffic.json") -> None:
+    import json
+    import os
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, row = rows[0], rows[1], rows[2]
+
+    def val(name):
+        i = hdr.index(name)
+        v = float(row[i].replace(",", ""))
+        u = units[i].lower()
+        scale = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "ns": 1e-6, "nsecond": 1e-6, "us": 1e-3, "usecond": 1e-3,
+                 "ms": 1.0, "msecond": 1.0, "%": 1.0}.get(u, 1.0)
+        return v * scale
+
+    entry = {"kernel": row[hdr.index("Kernel Name")].split("(")[0], "grid": row[hdr.index("Grid Size")],
+             "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
+             "duration_ms_under_ncu": val("gpu__time_duration.sum"),
+             "tensor_pipe_active_pct": val("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+             "l2_hit_pct": val("lts__t_sector_hit_rate.pct"), "source": summary,
+             "how": "ncu --set full --clock-control none, first captured launch; per launch like roofline.achieved"}
+    data = {}
+    if os.path.isfile(out):
+        with open(out) as f:
+            data = json.load(f)
+    data[key] = entry
+    with open(out, "w") as f:
+        json.dump(data, f, indent=1)
+    print(json.dumps(entry))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "report": report, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])

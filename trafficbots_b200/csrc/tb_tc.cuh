@@ -61,8 +61,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 #ifndef TB_WATCHDOG_CYCLES
-#define TB_WATCHDOG_CYCLES 4000000000LL  // ~2 s; raise it (-DTB_WATCHDOG_CYCLES=...) under tools that slow kernels by orders of magnitude
+// Limit of the bounded mbarrier waits in SM clock cycles: ~60 s at 1.965 GHz.  Legitimate waits are microseconds; the bound is
+// there so that a protocol bug fails the launch instead of hanging the GPU forever, and it is far above anything a
+// time-sliced context (a GPU shared with another process) or a stopped debugger session of reasonable length adds.
+// -DTB_WATCHDOG_CYCLES=0 compiles the check out (release builds that prefer a hang to a poisoned context);
+// larger values for compute-sanitizer runs, which slow the persistent kernels by orders of magnitude.
+#define TB_WATCHDOG_CYCLES 120000000000LL
 #endif
+__device__ __forceinline__ void watchdog_check(long long t0) {
+#if TB_WATCHDOG_CYCLES > 0
+  if (clock64() - t0 > TB_WATCHDOG_CYCLES) __trap();  // the host sees TB_ERR_LAUNCH on the next call (sticky CUDA error)
+#endif
+}
 // Bounded wait: a protocol bug must trap (fail the launch) instead of hanging the GPU.  The poll carries a suspend-time hint, so
 // a waiting warp sleeps in hardware until the phase completes instead of spinning: measured on the decode kernel against a
 // plain try_wait spin, -2.4 % step time (spinning roles steal issue / shared-memory slots from the working warps; a
@@ -82,7 +92,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait_hint(bar, parity, 1000000u))
-    if (clock64() - t0 > TB_WATCHDOG_CYCLES) __trap();  // ~2 s: far beyond any legitimate wait
+    watchdog_check(t0);
 }
 
 // ---- bulk async copy global -> shared (TMA linear mode), completes `bytes` on the mbarrier ---------------------------

@@ -170,7 +170,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "r"(tc::smem_u32(bar)), "r"(parity), "r"(1000000u)
         : "memory");
     if (ok) return;
-    if (clock64() - t0 > TB_WATCHDOG_CYCLES) __trap();
+    tc::watchdog_check(t0);
   }
 }
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
