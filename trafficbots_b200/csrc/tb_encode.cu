@@ -405,7 +405,8 @@ extern "C" size_t tb_encode_workspace_bytes(const TbDims* d) {
   // key blocks and key counts of the map self-attention layer
   const size_t nT = (d->n_pl + 63) / 64;
   return rows * D * sizeof(float) + rows * 256 * sizeof(float) + map_tc_scratch_bytes(MAP_TC_MAX_CTA) + 1024 +
-         (size_t)d->n_scene * nT * tc::BLOCK_BYTES + (size_t)d->n_scene * sizeof(int32_t) + 256;
+         (size_t)d->n_scene * nT * tc::BLOCK_BYTES + (((size_t)d->n_scene * sizeof(int32_t) + 255) & ~(size_t)255) + 256 +
+         map_plan_bytes((long)rows);
 }
 
 template <int R>
@@ -452,6 +453,16 @@ extern "C" int32_t tb_xlayer(int32_t block, int32_t layer, const float* src, con
   return launch_status();
 }
 
+// the compacted-tile plan of the polyline encoder lives behind the key blocks / key counts of the map self-attention
+static int32_t* map_plan_ws(const TbDims& d, void* workspace) {
+  const size_t rows = (size_t)d.n_scene * d.n_pl, nT = (d.n_pl + 63) / 64;
+  uintptr_t p = reinterpret_cast<uintptr_t>(workspace) + rows * D * sizeof(float) + rows * 256 * sizeof(float) +
+                map_tc_scratch_bytes(MAP_TC_MAX_CTA);
+  p = (p + 1023) & ~(uintptr_t)1023;
+  p += (size_t)d.n_scene * nT * tc::BLOCK_BYTES + (((size_t)d.n_scene * sizeof(int32_t) + 255) & ~(size_t)255);
+  return reinterpret_cast<int32_t*>((p + 255) & ~(uintptr_t)255);
+}
+
 extern "C" int32_t tb_encode_scene(const TbDims* dims, const TbSceneIn* in, const float* packed, const TbSceneOut* out,
                                    void* workspace, void* stream) {
   int rc = check_dims(dims);
@@ -492,7 +503,8 @@ extern "C" int32_t tb_encode_scene(const TbDims* dims, const TbSceneIn* in, cons
     const char* v1 = getenv("TB_POLYLINE_V1");  // A/B: the first version (one thread per node row)
     rc = (v1 && v1[0] == '1')
              ? launch_map_polyline_tc(d, *in, packed, kv_self + n_pl * 256, MAP_TC_MAX_CTA, pl_feature, out->map_feature_valid, st)
-             : launch_map_polyline_tc2(d, *in, packed, kv_self + n_pl * 256, MAP_TC_MAX_CTA, pl_feature, out->map_feature_valid, st);
+             : launch_map_polyline_tc2(d, *in, packed, kv_self + n_pl * 256, MAP_TC_MAX_CTA, pl_feature, out->map_feature_valid,
+                                       map_plan_ws(d, workspace), st);
     if (rc != TB_OK) return rc;
   } else {
     k_map_polyline<<<(unsigned)((n_pl + MAP_NP - 1) / MAP_NP), NT, sizeof(MapSmem), st>>>(d, *in, packed, pl_feature,

@@ -82,8 +82,10 @@ int launch_dest_pairs_tc(const float* U, const float* V, int n_scene, int n_agen
                          cudaStream_t st);
 
 // second version of the tensor-core polyline encoder: 4 threads per node row (tb_tc_polyline.cu)
+// plan_ws: map_plan_bytes(n_scene * n_pl) bytes = [live_pl | row_start (+1) | plan] int32 (compacted-tile plan, k_map_plan)
+size_t map_plan_bytes(long n_pl_total);
 int launch_map_polyline_tc2(const TbDims& d, const TbSceneIn& in, const float* packed, float* x0_scratch, int n_cta,
-                            float* pl_feature, uint8_t* pl_valid, cudaStream_t st);
+                            float* pl_feature, uint8_t* pl_valid, int32_t* plan_ws, cudaStream_t st);
 
 // tensor-core decode step (tb_tc_rollout.cu)
 int launch_pack_kv_tc(const float* kv, const uint8_t* key_valid, int n_set, int n_set_valid, int T, unsigned char* blocks,

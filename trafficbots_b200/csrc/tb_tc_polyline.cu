@@ -7,13 +7,23 @@
 //   TMEM: Q [0,128) (also Wo / W1 / W2 accumulator) | K [128,256) | V [256,384) | A operand [384,512) (bf16x2 hi | lo);
 //   every Linear = bf16x3 tcgen05 GEMM with the A operand in tensor memory, weights through a 2 x 64 KB bulk-copy ring;
 //   K of all 4 heads is staged in shared memory for the logits, then V in the same buffer for the weighted sum.
+//
+// Compacted tiles (round 2): invalid nodes are dead weight in the reference -- as keys they are masked, as queries their rows
+// are zeroed (transformer.py:236-237) and excluded from the max-pool (map_encoder.py:95-97) -- and in the data most polylines
+// have fewer than 20 valid nodes.  `k_map_plan` lists the non-empty polylines with the running count of their valid nodes;
+// a tile is the run of polylines whose first valid-node row falls into [108 t, 108 t + 108) of that compacted row space
+// (at most 108 + 19 = 127 rows of the 128-row MMA tile), so only valid nodes occupy rows, every key of a row's polyline is
+// valid (no masking), and the per-head key loop is cut at the longest polyline of the warp.  Results are bit-identical to the
+// dense 6 x 20 layout: rows are independent in every GEMM, and a masked key contributes an exact zero.
 #include "tb_host.h"
 
 namespace tb {
 namespace pl2 {
 
 constexpr int THREADS = 512;
-constexpr int NP = 6, N = TB_PL_NODE, ROWS = NP * N;  // 120
+constexpr int N = TB_PL_NODE, ROWS = 128;  // MMA tile height
+constexpr int FILL = 108;                  // compacted rows per tile before the last polyline's overhang (108 + 19 < 128)
+constexpr int PLAN_THREADS = 1024;
 constexpr int KVS = 132;                              // staging row stride (floats)
 constexpr uint32_t TQ = 0, TK = 128, TV = 256, TA = 384;
 
@@ -24,9 +34,77 @@ struct Smem {
   float lp[2][12][128];   // per-layer bias / LayerNorm vectors (double-buffered by layer parity)
   uint64_t bar_w[2], bar_mma;
   uint32_t tmem_base;
-  uint8_t row_valid[128];
-  uint8_t pl_valid[8];
+  int32_t seg_pl[128];      // polyline index of every segment (= non-empty polyline) of the tile
+  uint8_t seg_start[128];   // first row of the segment
+  uint8_t seg_cnt[128];     // valid nodes (= rows) of the segment
+  uint8_t row_seg[128];     // segment of every row
+  uint8_t row_node[128];    // node index (0..19) of every row inside its polyline
+  int32_t n_seg, n_rows, j0;
 };
+
+// ---- plan: non-empty polylines and the prefix sum of their valid-node counts ------------------------------------------------
+// k_map_count (one thread per polyline): valid-node count; empty polylines get their (all-zero, invalid) pooled feature here.
+// k_map_plan (one CTA): live_pl[j] = index of the j-th non-empty polyline, row_start[j] = valid nodes before it
+// (row_start[n_live] = total), plan = {n_live, total_rows}.
+__global__ void __launch_bounds__(256) k_map_count(long n_pl_total, const uint8_t* __restrict__ map_valid, uint8_t* __restrict__ counts,
+                                                   float* __restrict__ pl_feature, uint8_t* __restrict__ pl_valid_out) {
+  const long pl = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pl >= n_pl_total) return;
+  const uint32_t* v = reinterpret_cast<const uint32_t*>(map_valid + pl * N);  // 20 bytes, 4-byte aligned
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < N / 4; ++i) {
+    const uint32_t w = v[i];
+    c += ((w & 0xffu) != 0) + ((w & 0xff00u) != 0) + ((w & 0xff0000u) != 0) + ((w & 0xff000000u) != 0);
+  }
+  counts[pl] = (uint8_t)c;
+  if (c == 0) {
+    pl_valid_out[pl] = 0;
+    float4* f = reinterpret_cast<float4*>(pl_feature + pl * 128);
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(PLAN_THREADS) k_map_plan(long n_pl_total, const uint8_t* __restrict__ counts, int32_t* __restrict__ live_pl,
+                                                           int32_t* __restrict__ row_start, int32_t* __restrict__ plan) {
+  __shared__ int w_live[PLAN_THREADS / 32], w_rows[PLAN_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long chunk = (n_pl_total + PLAN_THREADS - 1) / PLAN_THREADS;
+  const long p0 = (long)tid * chunk, p1 = p0 + chunk < n_pl_total ? p0 + chunk : n_pl_total;
+  int my_live = 0, my_rows = 0;
+  for (long pl = p0; pl < p1; ++pl) {
+    const int c = counts[pl];
+    my_live += c > 0;
+    my_rows += c;
+  }
+  // block-wide exclusive scan of (live, rows)
+  int sl = my_live, sr = my_rows;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, sl, o), b = __shfl_up_sync(0xffffffffu, sr, o);
+    if (lane >= o) sl += a, sr += b;
+  }
+  if (lane == 31) w_live[warp] = sl, w_rows[warp] = sr;
+  __syncthreads();
+  int base_l = 0, base_r = 0;
+  for (int k = 0; k < warp; ++k) base_l += w_live[k], base_r += w_rows[k];
+  int j = base_l + sl - my_live, row = base_r + sr - my_rows;
+  for (long pl = p0; pl < p1; ++pl) {
+    const int c = counts[pl];
+    if (c > 0) {
+      live_pl[j] = (int32_t)pl;
+      row_start[j] = row;
+      ++j;
+      row += c;
+    }
+  }
+  if (tid == PLAN_THREADS - 1) {
+    plan[0] = j;
+    plan[1] = row;
+    row_start[j] = row;
+  }
+}
 
 __device__ __forceinline__ int stage_block(uint32_t s) {  // stage s of the repeating 18-stage weight schedule
   const int L = (s % 18) / 6, j = s % 6;
@@ -37,13 +115,15 @@ __device__ __forceinline__ int stage_block(uint32_t s) {  // stage s of the repe
 __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSceneIn in, const float* __restrict__ packed,
                                                                  const unsigned char* __restrict__ tcw, float* __restrict__ x0_scratch,
                                                                  float* __restrict__ pl_feature, uint8_t* __restrict__ pl_valid_out,
-                                                                 int n_tiles) {
+                                                                 const int32_t* __restrict__ live_pl, const int32_t* __restrict__ row_start,
+                                                                 const int32_t* __restrict__ plan) {
   extern __shared__ unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tc::uniform(tid >> 5), lane = tid & 31;
   const int quad = warp & 3, q4 = warp >> 2;
   const int r = quad * 32 + lane, c0 = 32 * q4;
-  const long n_pl_total = (long)dm.n_scene * dm.n_pl;
+  const int n_live = plan[0];
+  const int n_tiles = (plan[1] + FILL - 1) / FILL;
 
   if (tid == 0) {
     tc::mbar_init(&sm.bar_w[0], 1);
@@ -152,10 +232,49 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
   if (tid == 0) prefetch();
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long pl0 = (long)tile * NP;
-    const int p = r / N, n = r % N;
-    const long pl = pl0 + p;
-    const bool live = r < ROWS && pl < n_pl_total;
+    // ---- tile plan: the live polylines whose first row lies in [FILL tile, FILL tile + FILL) --------------------------------
+    if (tid == 0) {
+      const int lo = tile * FILL;
+      int a = 0, b = n_live;  // first j with row_start[j] >= lo
+      while (a < b) {
+        const int m = (a + b) >> 1;
+        if (row_start[m] < lo) a = m + 1; else b = m;
+      }
+      sm.j0 = a;
+      sm.n_seg = 0;  // a tail tile may hold no polyline start at all (its rows belong to the previous tile's last polyline)
+      sm.n_rows = 0;
+    }
+    __syncthreads();
+    if (tid < 128) {
+      const int j = sm.j0 + tid, hi = tile * FILL + FILL;
+      const bool own = j < n_live && row_start[j] < hi;
+      const bool last = own && !(j + 1 < n_live && row_start[j + 1] < hi);
+      if (own) {
+        const int base = row_start[sm.j0], st = row_start[j] - base, cnt = row_start[j + 1] - row_start[j];
+        const int pl = live_pl[j];
+        sm.seg_pl[tid] = pl;
+        sm.seg_start[tid] = (uint8_t)st;
+        sm.seg_cnt[tid] = (uint8_t)cnt;
+        const uint8_t* v = in.map_valid + (long)pl * N;
+        int k = 0;
+        for (int n = 0; n < N; ++n)
+          if (v[n]) {
+            sm.row_seg[st + k] = (uint8_t)tid;
+            sm.row_node[st + k] = (uint8_t)n;
+            ++k;
+          }
+        if (last) {
+          sm.n_seg = tid + 1;
+          sm.n_rows = st + cnt;
+        }
+      }
+    }
+    __syncthreads();
+    const int n_rows = sm.n_rows;
+    const bool live = r < n_rows;
+    const int p = live ? sm.row_seg[r] : 0, n = live ? sm.row_node[r] : 0;
+    const long pl = live ? sm.seg_pl[p] : 0;
+    const int ks = live ? sm.seg_start[p] : 0, kc = live ? sm.seg_cnt[p] : 0;  // key rows of this row's polyline
     float x[32];  // residual stream: columns c0 .. c0+31 of row r
     // ---- node features: InputPeEncoder([type | onehot(node)], PE(pos, atan2(dir)))  (sc_input.py:124-134) ---------
     bool valid = false;
@@ -163,8 +282,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
     for (int i = 0; i < 32; ++i) x[i] = 0.f;
     if (live) {
       const long node = pl * N + n;
-      valid = in.map_valid[node] != 0;
-      if (valid) {
+      valid = true;  // compacted tiles hold valid nodes only
+      {
         if (q4 == 0) {
           const float* w1 = packed + tbw::model_map_encoder_input_pe_encoder_mlp_fc_layers_0_weight;  // Wt4[8][32][4]
           float h[32];
@@ -206,20 +325,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
         }
       }
     }
-    if (q4 == 0) sm.row_valid[r] = valid;
     // initial node features = the attention target of all 3 layers: per-CTA scratch, row-minor [32 column quads][128 rows]
     float4* x0col = reinterpret_cast<float4*>(x0_scratch) + (size_t)blockIdx.x * 32 * 128 + (size_t)(8 * q4) * 128 + r;
 #pragma unroll
     for (int i = 0; i < 8; ++i) x0col[i * 128] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-    __syncthreads();
-    if (tid < 8) {
-      bool any = false;
-      if (tid < NP)
-        for (int j = 0; j < N; ++j) any |= sm.row_valid[tid * N + j] != 0;
-      sm.pl_valid[tid] = any;
-    }
-    __syncthreads();
-    const bool pvalid = sm.pl_valid[p < 8 ? p : 7] != 0;
+    const bool pvalid = live;
 
 #pragma unroll 1
     for (int L = 0; L < 3; ++L) {
@@ -270,13 +380,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
       float pj[N];
       float inv = 0.f;
       load_acc(TQ, t);
-      if (r < ROWS) {
+      const int kmax = __reduce_max_sync(0xffffffffu, kc);  // longest polyline of the warp: later keys are skipped warp-wide
+      if (live) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) t[i] += lp[P_BQ][c0 + i];
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-          const float* kr = sm.kv + (p * N + j) * KVS + c0;
+          if (j >= kmax) {
+            pj[j] = -INFINITY;
+            continue;
+          }
+          const float* kr = sm.kv + (ks + (j < kc ? j : 0)) * KVS + c0;
           float a0 = 0.f, a1 = 0.f;
 #pragma unroll
           for (int i = 0; i < 8; i += 2) {
@@ -286,7 +401,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
             tc::fma2(a0, a1, t[4 * i + 2], t[4 * i + 6], k4.z, k5.z, a0, a1);
             tc::fma2(a0, a1, t[4 * i + 3], t[4 * i + 7], k4.w, k5.w, a0, a1);
           }
-          pj[j] = sm.row_valid[p * N + j] ? (a0 + a1) * 0.17677669529663687f : -INFINITY;
+          pj[j] = j < kc ? (a0 + a1) * 0.17677669529663687f : -INFINITY;
           mx = fmaxf(mx, pj[j]);
         }
         if (mx != -INFINITY) {
@@ -314,10 +429,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
       __syncthreads();
 #pragma unroll
       for (int i = 0; i < 32; ++i) t[i] = 0.f;
-      if (r < ROWS) {
+      if (live) {
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-          const float* vr = sm.kv + (p * N + j) * KVS + c0;
+          if (j >= kmax) continue;
+          const float* vr = sm.kv + (ks + (j < kc ? j : 0)) * KVS + c0;  // pj[j] = 0 for j >= kc
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 v4 = reinterpret_cast<const float4*>(vr)[i];
@@ -353,22 +469,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
     }
     // ---- masked max-pool over the valid nodes of each polyline (map_encoder.py:95-97,105-106) ------------------------------
     {
-      float* stage = sm.kv;  // [col][row], 128 x 120 floats
+      float* stage = sm.kv;  // [col][row], 128 x 128 floats
       __syncthreads();
-      if (r < ROWS) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) stage[(c0 + i) * ROWS + r] = x[i];
-      }
+      for (int i = 0; i < 32; ++i) stage[(c0 + i) * ROWS + r] = x[i];
       __syncthreads();
-      for (int idx = tid; idx < NP * 128; idx += THREADS) {
+      const int n_seg = sm.n_seg;
+      for (int idx = tid; idx < n_seg * 128; idx += THREADS) {
         const int pp = idx >> 7, c = idx & 127;
-        if (pl0 + pp >= n_pl_total) continue;
+        const int st = sm.seg_start[pp], cnt = sm.seg_cnt[pp];
         float mx = -INFINITY;
-        for (int j = 0; j < N; ++j)
-          if (sm.row_valid[pp * N + j]) mx = fmaxf(mx, stage[c * ROWS + pp * N + j]);
-        pl_feature[(pl0 + pp) * 128 + c] = sm.pl_valid[pp] ? mx : 0.f;
+        for (int j = 0; j < cnt; ++j) mx = fmaxf(mx, stage[c * ROWS + st + j]);
+        pl_feature[(long)sm.seg_pl[pp] * 128 + c] = mx;
       }
-      if (tid < NP && pl0 + tid < n_pl_total) pl_valid_out[pl0 + tid] = sm.pl_valid[tid];
+      if (tid < n_seg) pl_valid_out[sm.seg_pl[tid]] = 1;
       __syncthreads();
     }
   }
@@ -380,8 +494,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
 }  // namespace pl2
 }  // namespace tb
 
+size_t tb::map_plan_bytes(long n_pl_total) {  // [live_pl | row_start (+1) | plan (4)] int32 + counts u8
+  return ((size_t)(2 * n_pl_total + 1 + 4) * sizeof(int32_t) + (size_t)n_pl_total + 255) & ~(size_t)255;
+}
+
 int tb::launch_map_polyline_tc2(const TbDims& d, const TbSceneIn& in, const float* packed, float* x0_scratch, int n_cta,
-                                float* pl_feature, uint8_t* pl_valid, cudaStream_t st) {
+                                float* pl_feature, uint8_t* pl_valid, int32_t* plan_ws, cudaStream_t st) {
   static std::atomic<uint64_t> attr_set{0};
   const int smem = (int)sizeof(pl2::Smem) + 1024;
   if (!smem_attr_done(attr_set)) {
@@ -389,9 +507,16 @@ int tb::launch_map_polyline_tc2(const TbDims& d, const TbSceneIn& in, const floa
     smem_attr_mark(attr_set);
   }
   const long n_pl = (long)d.n_scene * d.n_pl;
-  const int n_tiles = (int)((n_pl + pl2::NP - 1) / pl2::NP);
-  const int grid = n_tiles < n_cta ? n_tiles : n_cta;
-  pl2::k_map_polyline_tc2<<<grid, pl2::THREADS, smem, st>>>(d, in, packed, tc_blob(packed), x0_scratch, pl_feature, pl_valid, n_tiles);
+  uint8_t* counts = reinterpret_cast<uint8_t*>(plan_ws + 2 * n_pl + 1 + 4);
+  pl2::k_map_count<<<(unsigned)((n_pl + 255) / 256), 256, 0, st>>>(n_pl, in.map_valid, counts, pl_feature, pl_valid);
+  count_launch();
+  pl2::k_map_plan<<<1, pl2::PLAN_THREADS, 0, st>>>(n_pl, counts, plan_ws, plan_ws + n_pl, plan_ws + 2 * n_pl + 1);
+  count_launch();
+  // persistent CTAs; the tile count is a device value (plan[1]): surplus CTAs exit at once
+  const long max_tiles = (n_pl * pl2::N + pl2::FILL - 1) / pl2::FILL;
+  const int grid = (int)(max_tiles < n_cta ? max_tiles : n_cta);
+  pl2::k_map_polyline_tc2<<<grid, pl2::THREADS, smem, st>>>(d, in, packed, tc_blob(packed), x0_scratch, pl_feature, pl_valid, plan_ws,
+                                                          plan_ws + n_pl, plan_ws + 2 * n_pl + 1);
   count_launch();
   return launch_status();
 }
