@@ -172,11 +172,15 @@ def test_rollout_matches_oracle_and_golden(case):
     assert _maxdiff(out["hidden"], gold["jfp/hidden"]) <= TOL_CLOSED
 
 
-@pytest.mark.parametrize("S,A,P,K", [(1, 128, 2048, 1), (2, 100, 1500, 1), (2, 37, 300, 2), (2, 64, 1024, 6)])
+@pytest.mark.parametrize("S,A,P,K", [(1, 128, 2048, 1), (2, 100, 1500, 1), (2, 37, 300, 2), (2, 64, 1024, 6), (3, 65, 200, 2),
+                                     (3, 96, 256, 1)])
 def test_rollout_other_shapes_match_oracle(S, A, P, K):
     """shapes without a golden file, checked against the oracle on the spot: BASELINE.json configs[4] (128 agents, 2048
-    polylines: two-kernel path, n_agent > 64), a ragged shape on the same path, a ragged shape on the persistent kernel, and the
-    per-scene shape of configs[2] (64 agents, 1024 polylines, K = 6 modes sharing the scene's key blocks)."""
+    polylines: the persistent kernel in its two-CTA "agent halves" mode, 64 < n_agent <= 128), ragged shapes on the same path
+    (100, 96 and 65 agents -- a second half with a single agent; the 3-scene batches contain a scene without traffic lights and a
+    scene with exactly ONE valid agent, i.e. the interaction bypass decided across the two halves), a ragged shape on the
+    one-CTA persistent kernel, and the per-scene shape of configs[2] (64 agents, 1024 polylines, K = 6 modes sharing the scene's
+    key blocks)."""
     import trafficbots_oracle as orc
     from trafficbots_b200 import synthetic, weights
     sd = weights.init_state_dict(2023)
@@ -317,25 +321,3 @@ def test_rollout_two_kernel_path_agrees(monkeypatch):
     _compare_rollout(out, ref, meta["S"], meta["K"])
 
 
-def test_rollout_8_worker_warp_kernel_agrees(monkeypatch):
-    """`TB_ROLLOUT_8WARP=1` selects the first persistent decode kernel (8 worker warps, two threads per TMEM lane)."""
-    from golden_util import load_case
-    monkeypatch.setenv("TB_ROLLOUT_8WARP", "1")
-    gold, sd, batch, meta = load_case("s1_a64_p1024_k1")
-    eng = _engine(sd)
-    feat = eng.encode_scene(_cuda(batch))
-    out, ref = _run_jfp(eng, sd, batch, meta, feat)
-    _compare_rollout(out, ref, meta["S"], meta["K"])
-
-
-def test_encode_scene_polyline_v1_agrees(monkeypatch):
-    """`TB_POLYLINE_V1=1` selects the first tensor-core polyline encoder (one thread per node row)."""
-    import trafficbots_oracle as orc
-    from golden_util import load_case
-    monkeypatch.setenv("TB_POLYLINE_V1", "1")
-    gold, sd, batch, meta = load_case("s3_a8_p64_k2")
-    eng = _engine(sd)
-    feat = eng.encode_scene(_cuda(batch))
-    ref = orc.encode_scene(sd, batch)
-    assert torch.equal(feat["map_feature_valid"].cpu(), ref["map_feature_valid"])
-    assert _maxdiff(feat["map_feature"], ref["map_feature"]) <= 1e-4

@@ -500,11 +500,8 @@ extern "C" int32_t tb_encode_scene(const TbDims* dims, const TbSceneIn* in, cons
   if (do_map) {
   // 1. polyline encoder: tcgen05 kernel; TB_DISABLE_TC=1 selects the fp32 CUDA-core kernel (verification aid)
   if (tc_enabled()) {
-    const char* v1 = getenv("TB_POLYLINE_V1");  // A/B: the first version (one thread per node row)
-    rc = (v1 && v1[0] == '1')
-             ? launch_map_polyline_tc(d, *in, packed, kv_self + n_pl * 256, MAP_TC_MAX_CTA, pl_feature, out->map_feature_valid, st)
-             : launch_map_polyline_tc2(d, *in, packed, kv_self + n_pl * 256, MAP_TC_MAX_CTA, pl_feature, out->map_feature_valid,
-                                       map_plan_ws(d, workspace), st);
+    rc = launch_map_polyline_tc2(d, *in, packed, kv_self + n_pl * 256, MAP_TC_MAX_CTA, pl_feature, out->map_feature_valid,
+                                 map_plan_ws(d, workspace), st);
     if (rc != TB_OK) return rc;
   } else {
     k_map_polyline<<<(unsigned)((n_pl + MAP_NP - 1) / MAP_NP), NT, sizeof(MapSmem), st>>>(d, *in, packed, pl_feature,

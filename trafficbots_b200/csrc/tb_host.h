@@ -60,15 +60,17 @@ struct StateView {
   float4* goal_c_t;    // [B][32][A]   = W_out0[:, 128:256] relu(goal_in): step-invariant half of add_goal.mlp_out layer 0
   float4* latent_c_t;  // [B][32][A]   = the same for add_latent
   float4* dest_nodes;  // [B][20][A]   destination polyline nodes (x, y, unit direction), invalid nodes at 1e30
+  // 64 < n_agent <= 128: the two CTAs of a scene-mode (64 agents each) exchange their valid masks and the readiness of their
+  // interaction key blocks through 16 ints per scene-mode: [0..3] valid mask (lo, hi) of rank 0, 1; [4,5] step counters;
+  // [6,7] key-block counters.  Zeroed by tb_rollout_init.
+  int32_t* xch;
 };
 
 StateView state_view(const TbDims& d, void* base);
 
-// tensor-core polyline encoder (tb_tc_kernels.cu)
+// tensor-core polyline encoder: per-CTA scratch of the initial node features (tb_tc_kernels.cu)
 constexpr int MAP_TC_MAX_CTA = 148;
 size_t map_tc_scratch_bytes(int n_cta);
-int launch_map_polyline_tc(const TbDims& d, const TbSceneIn& in, const float* packed, float* x0_scratch, int n_cta,
-                           float* pl_feature, uint8_t* pl_valid, cudaStream_t st);
 
 // generic tensor-core cross-attention layer on compacted key blocks (tb_tc_xlayer.cu)
 int launch_xlayer_tc(int block, int layer, const float* src, const uint8_t* src_valid, int n_batch, int n_src,
@@ -81,7 +83,7 @@ int launch_gru_seq_tc(int which, int mode, const float* x, const uint8_t* valid,
 int launch_dest_pairs_tc(const float* U, const float* V, int n_scene, int n_agent, int n_pl, const float* packed, float* logits,
                          cudaStream_t st);
 
-// second version of the tensor-core polyline encoder: 4 threads per node row (tb_tc_polyline.cu)
+// tensor-core polyline encoder: 4 threads per node row, compacted tiles (tb_tc_polyline.cu)
 // plan_ws: map_plan_bytes(n_scene * n_pl) bytes = [live_pl | row_start (+1) | plan] int32 (compacted-tile plan, k_map_plan)
 size_t map_plan_bytes(long n_pl_total);
 int launch_map_polyline_tc2(const TbDims& d, const TbSceneIn& in, const float* packed, float* x0_scratch, int n_cta,
@@ -93,9 +95,9 @@ int launch_pack_kv_tc(const float* kv, const uint8_t* key_valid, int n_set, int 
 bool front_tc_supported(const TbDims& d, const TbRolloutIn& in);
 int launch_step_front_tc(const TbDims& d, const TbRolloutIn& in, const float* packed, const StateView& sv, int t, cudaStream_t st);
 extern long long* g_debug_trace;  // development aid (tb_debug_set_trace)
-// persistent tensor-core rollout (tb_tc_persist.cu): all decode steps t_first..t_last in one launch, n_agent <= 64
+// persistent tensor-core rollout (tb_tc_persist.cu): all decode steps t_first..t_last in one launch, n_agent <= 128
 bool rollout_tc_supported(const TbDims& d, const TbRolloutIn& in);
-int rollout_tc_cluster_size(const TbDims& d);  // CTAs per scene-mode (1, 2 or 4)
+int rollout_tc_cluster_size(const TbDims& d);  // CTAs per scene-mode (1, 2 or 4; always 2 for 64 < n_agent <= 128: agent halves)
 int launch_rollout_tc(const TbDims& d, const TbRolloutIn& in, const float* packed, const StateView& sv, const TbRolloutOut& out,
                       int t_first, int t_last, cudaStream_t st);
 inline bool persist_enabled() {  // read per call: tests toggle it

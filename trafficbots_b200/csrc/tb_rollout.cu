@@ -16,7 +16,7 @@ static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct StateLayout {
   size_t off[TB_STATE_N_FIELD];
-  size_t x0, kv_int, goal_in, latent_in, dest_nodes, hidden_t, x0_t, goal_in_t, latent_in_t, goal_c_t, latent_c_t, total;
+  size_t x0, kv_int, goal_in, latent_in, dest_nodes, hidden_t, x0_t, goal_in_t, latent_in_t, goal_c_t, latent_c_t, xch, total;
 };
 
 static StateLayout state_layout(const TbDims& d) {
@@ -38,17 +38,20 @@ static StateLayout state_layout(const TbDims& d) {
   L.off[TB_STATE_STICKY] = put(3 * BA);
   L.off[TB_STATE_HIDDEN] = put(3 * BA * D * sizeof(float));
   L.x0 = put(BA * D * sizeof(float));
-  L.kv_int = put(3 * BA * 256 * sizeof(float));
+  // (with 64 < n_agent <= 128 the persistent kernel keeps its exchanged interaction key blocks here: [3][B][2] x 64 KB)
+  const size_t a_kv = d.n_agent > 64 && d.n_agent < 128 ? 128 : (size_t)d.n_agent;
+  L.kv_int = put(3 * (size_t)d.n_scene * d.n_mode * a_kv * 256 * sizeof(float));
   L.goal_in = put(BA * D * sizeof(float));
   L.latent_in = put(BA * D * sizeof(float));
   L.dest_nodes = put(BA * TB_PL_NODE * 4 * sizeof(float));
-  const size_t n_cta = d.n_agent <= 64 ? (size_t)rollout_tc_cluster_size(d) : 0;  // persistent-kernel scratch
+  const size_t n_cta = d.n_agent <= 128 ? (size_t)rollout_tc_cluster_size(d) : 0;  // persistent-kernel scratch
   L.hidden_t = put(n_cta * 3 * BA * D * sizeof(float));
   L.x0_t = put(n_cta * BA * D * sizeof(float));
   L.goal_in_t = put(BA * D * sizeof(float));
   L.latent_in_t = put(BA * D * sizeof(float));
   L.goal_c_t = put(BA * D * sizeof(float));
   L.latent_c_t = put(BA * D * sizeof(float));
+  L.xch = put((size_t)d.n_scene * d.n_mode * 64);
   L.total = o;
   return L;
 }
@@ -77,6 +80,7 @@ StateView state_view(const TbDims& d, void* base) {
   v.latent_in_t = reinterpret_cast<float4*>(p + L.latent_in_t);
   v.goal_c_t = reinterpret_cast<float4*>(p + L.goal_c_t);
   v.latent_c_t = reinterpret_cast<float4*>(p + L.latent_c_t);
+  v.xch = reinterpret_cast<int32_t*>(p + L.xch);
   return v;
 }
 
@@ -664,7 +668,9 @@ extern "C" int32_t tb_rollout_init(const TbDims* dims, const TbRolloutIn* in, co
   if (set_rollout_attrs<R>() != TB_OK) return TB_ERR_LAUNCH;
   const TbDims d = *dims;
   dim3 grid((d.n_agent + R - 1) / R, d.n_scene * d.n_mode);
-  k_rollout_init<R><<<grid, NT, sizeof(TileSmem<R>), (cudaStream_t)stream>>>(d, *in, packed, state_view(d, state));
+  const StateView sv0 = state_view(d, state);
+  if (cudaMemsetAsync(sv0.xch, 0, (size_t)d.n_scene * d.n_mode * 64, (cudaStream_t)stream) != cudaSuccess) return TB_ERR_LAUNCH;
+  k_rollout_init<R><<<grid, NT, sizeof(TileSmem<R>), (cudaStream_t)stream>>>(d, *in, packed, sv0);
   count_launch();
   return launch_status();
 }

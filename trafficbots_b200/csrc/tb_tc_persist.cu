@@ -35,34 +35,6 @@ constexpr uint32_t BLK = 65536, HALF = 32768;
 constexpr uint32_t T_ACC0 = 0, T_ACC1 = 128, T_ACC2 = 256, T_A2 = 256, T_O = 256, T_A = 384;
 // parameter-vector sets ("phases"): 0-8 attention layers, 9-11 GRU layers, 12 add_goal, 13 add_latent, 14 head
 
-struct Smem {
-  unsigned char ring[2][BLK];
-  float xs[128 * MAXA];  // residual stream, [col][agent]
-  float xo[128 * MAXA];  // exchange buffer, [col][agent] (attention output; scratch of the state embedding)
-  float lp[2][16][128];  // parameter vectors of the current / next phase
-  float emb_w1[384], emb_w2[1024], emb_b1[32], emb_b2[32], f_xy[24], f_yaw[48];
-  float2 red[2][2][128];  // LayerNorm partials {sum, M2} [buffer][half][lane]
-  float mean_part[4][MAXA][2];  // action-mean partial sums of the 4 column quarters
-  // simulation state of the scene-mode
-  float4 pose[MAXA];  // x, y, yaw, spd
-  float2 vel[MAXA];
-  float acc[MAXA], yaw_rate[MAXA];
-  uint8_t valid[MAXA], killed[MAXA], goal_valid[MAXA], sticky[3][MAXA], type[MAXA][4];
-  // per-rollout constants of the tail: [field][agent]; fields: b2.x, b2.y, logp, latent logp, goal x, y, yaw, goal thresh, dest thresh
-  float tailc[9][MAXA];
-  float map_boundary[4];
-  uint8_t tflag[MAXA];  // bit 0: destination is a lane (types 0-3), bit 1: destination is a road edge (type 4)
-  // barriers
-  uint64_t full[2][2], free_[2][2], grant, wfill, ready, mma, cfg, s[2], p[2], o[2];
-  static constexpr int kMergeBarriers = 4;  // cluster barriers per merge of the split agent->map attention
-  static constexpr uint32_t kInteractionQ = T_ACC0;  // accumulator of the interaction layers' Q projection
-  static constexpr bool kAddHalfHoisted = false;     // add_goal / add_latent: the z half of mlp_out layer 0 is a GEMM of the step
-  uint32_t tmem_base;
-  int n_valid, kvi_slot;
-};
-
-static_assert(sizeof(Smem) + 1024 <= 232448, "shared memory budget (227 KB per CTA)");
-
 struct Args {
   TbDims dm;
   TbRolloutIn in;
@@ -235,6 +207,13 @@ struct StepCfg {
   const unsigned char* kv_map;  // + (L * S) * nT_map * BLK per layer
   const unsigned char* kv_tl;
   size_t kv_map_layer_stride, kv_tl_layer_stride;
+  // 64 < n_agent <= 128 ("halves"): the scene-mode is shared by the 2 CTAs of a cluster, 64 agents each; the interaction key blocks
+  // of both are exchanged through global memory (`kvx`: [layer][scene-mode][cluster rank] x 64 KB) and streamed like map keys
+  bool halves;
+  int crank, t;
+  const unsigned char* kvx;  // + ((L * B + b) * 2) * BLK: block of rank 0, then of rank 1
+  size_t kvx_layer_stride;
+  int* xflag;                // this scene-mode's key-block counters [2] (StateView::xch + 6)
 };
 
 template <class R>
@@ -264,13 +243,17 @@ __device__ __forceinline__ void enumerate_step(const Args& a, const StepCfg& c, 
         r.chain(W(w0, 1), T_ACC0, T_A, false);
         r.chain(W(w0, 2), T_ACC1, T_A, false);
         r.gemm_end();
-        r.kvi();
+        if (c.halves) r.kvx(c, L);
+        else r.kvi();
       }
       r.gemm_begin();
       r.chain(W(w0, 0), kind == 2 ? R::kInteractionQ : T_ACC0, T_A, false);
       r.gemm_end();
-      r.att(kind == 2, nblk_my, kind == 0 ? c.kv_map + L * c.kv_map_layer_stride + (size_t)c.rank * BLK : c.kv_tl + L * c.kv_tl_layer_stride,
-            kind == 0 ? (size_t)c.n_cta * BLK : (size_t)BLK);
+      if (kind == 2 && c.halves)
+        r.att(false, 2, c.kvx + L * c.kvx_layer_stride, (size_t)BLK);
+      else
+        r.att(kind == 2, nblk_my, kind == 0 ? c.kv_map + L * c.kv_map_layer_stride + (size_t)c.rank * BLK : c.kv_tl + L * c.kv_tl_layer_stride,
+              kind == 0 ? (size_t)c.n_cta * BLK : (size_t)BLK);
       const bool split = kind == 0 && c.n_cta > 1;
       if (split) r.csync_before_wo();
       r.gemm_begin();
@@ -364,6 +347,29 @@ struct LoaderT {  // run by a whole (converged) warp; one elected lane issues th
     __syncwarp();
     ++g;
   }
+  // halves mode: this CTA's key block of layer L is complete in global memory once all 16 worker warps arrived at `wfill`;
+  // publish it (release), wait for the peer's (acquire), then the two blocks are loaded like any other key block
+  uint32_t n_kvx = 0;
+  __device__ __forceinline__ void kvx(const StepCfg& c, int L) {
+    tc::mbar_wait(&sm.wfill, n_kvx & 1);
+    ++n_kvx;
+    if (elect_one()) {
+      const int want = (c.t - 1) * 3 + L + 1;
+      asm volatile("fence.proxy.async;" ::: "memory");
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(c.xflag + c.crank), "r"(want) : "memory");
+      const long long t0 = clock64();
+      int got;
+      do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(c.xflag + (c.crank ^ 1)) : "memory");
+        if (got < want) {
+          __nanosleep(64);
+          tc::watchdog_check(t0);
+        }
+      } while (got < want);
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncwarp();
+  }
   __device__ __forceinline__ void att(bool kvi_keys, int nblk, const unsigned char* blocks, size_t stride) {
     if (kvi_keys) return;
     for (int j = 0; j < nblk; ++j) load(blocks + (size_t)j * stride);
@@ -434,6 +440,7 @@ struct IssuerT {
     kvi_slot = g & 1;
     ++g;
   }
+  __device__ __forceinline__ void kvx(const StepCfg&, int) {}  // the exchanged key blocks arrive through the ring like map keys
   __device__ __forceinline__ void csync_before_wo() {  // the issuer joins the merge's four cluster barriers right away
 #pragma unroll
     for (int i = 0; i < SM::kMergeBarriers; ++i) cluster_sync_relaxed();
@@ -520,1032 +527,12 @@ struct IssuerT {
 };
 
 // =============================================================================================================================
-__global__ void __launch_bounds__(THREADS, 1) k_rollout_tc(Args a) {
-  extern __shared__ unsigned char smem_raw[];
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
-  const TbDims& dm = a.dm;
-  const TbRolloutIn& in = a.in;
-  const float* __restrict__ packed = a.packed;
-  const int A = dm.n_agent, K = dm.n_mode, S = dm.n_scene, B = S * K, Th = dm.n_step_hist, T = dm.n_step, Tg = dm.n_step_gt;
-  const int nT_map = (dm.n_pl + 63) / 64, nT_tl = (dm.n_tl + 63) / 64;
-  const int rank = (int)cluster_ctarank(), n_cta = (int)cluster_nctarank();  // CTAs of a cluster share one scene-mode
-  const int b = blockIdx.x / n_cta, s = b / K;
-  const int tid = threadIdx.x, warp = uniform(tid >> 5), lane = tid & 31;
-  const size_t BA = (size_t)B * A;
-  const int nkey_map = uniform(in.n_key_map[s]);
-
-  if (tid == 0) {
-    for (int i = 0; i < 2; ++i)
-      for (int j = 0; j < 2; ++j) {
-        tc::mbar_init(&sm.full[i][j], 1);
-        tc::mbar_init(&sm.free_[i][j], 1);
-      }
-    tc::mbar_init(&sm.grant, 1);
-    tc::mbar_init(&sm.wfill, 8);
-    tc::mbar_init(&sm.ready, 8);
-    tc::mbar_init(&sm.mma, 1);
-    tc::mbar_init(&sm.cfg, 1);
-    for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&sm.s[i], 1);
-      tc::mbar_init(&sm.p[i], 4);
-      tc::mbar_init(&sm.o[i], 1);
-    }
-    tc::fence_mbar_init();
-  }
-  if (warp == 0) tc::tmem_alloc(&sm.tmem_base, 512);
-  // persistent tables: state-embedding MLP (agent_encoder) and the positional-encoding frequencies
-  for (int i = tid; i < 384; i += THREADS) sm.emb_w1[i] = __ldg(packed + tbw::model_agent_encoder_mlp_fc_layers_0_weight + i);
-  for (int i = tid; i < 1024; i += THREADS) sm.emb_w2[i] = __ldg(packed + tbw::model_agent_encoder_mlp_fc_layers_3_weight + i);
-  if (tid < 32) {
-    sm.emb_b1[tid] = __ldg(packed + tbw::model_agent_encoder_mlp_fc_layers_0_bias + tid);
-    sm.emb_b2[tid] = __ldg(packed + tbw::model_agent_encoder_mlp_fc_layers_3_bias + tid);
-  }
-  if (tid < 24) sm.f_xy[tid] = __ldg(packed + tbw::pre_processing_input_pose_pe_agent_pe_xy_freqs + tid);
-  if (tid < 48) sm.f_yaw[tid] = __ldg(packed + tbw::pre_processing_input_pose_pe_agent_pe_yaw_freqs + tid);
-  // simulation state -> shared memory
-  if (tid < MAXA) {
-    const int ag = tid;
-    const bool live = ag < A;
-    const size_t ba = (size_t)b * A + (live ? ag : 0), sa = (size_t)s * A + (live ? ag : 0);
-    sm.pose[ag] = live ? *reinterpret_cast<const float4*>(a.sv.agent_state + ba * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    sm.vel[ag] = live ? make_float2(a.sv.vel[ba * 2], a.sv.vel[ba * 2 + 1]) : make_float2(0.f, 0.f);
-    sm.acc[ag] = live ? a.sv.acc[ba] : 0.f;
-    sm.yaw_rate[ag] = live ? a.sv.yaw_rate[ba] : 0.f;
-    sm.valid[ag] = live ? a.sv.valid[(size_t)(a.t_first & 1) * BA + ba] : (uint8_t)0;
-    sm.killed[ag] = live ? a.sv.killed[ba] : (uint8_t)0;
-    sm.goal_valid[ag] = live ? a.sv.goal_valid[ba] : (uint8_t)0;
-    for (int i = 0; i < 3; ++i) {
-      sm.sticky[i][ag] = live ? a.sv.sticky[(size_t)i * BA + ba] : (uint8_t)0;
-      sm.type[ag][i] = live ? in.agent_type[sa * 3 + i] : (uint8_t)0;
-    }
-  }
-  // Mutable global scratch (GRU hidden state, x0) is private to every CTA of a cluster and kept in agent-minor layout
-  // [32 column quads][A] float4: lane = agent, so a warp reads / writes 512 contiguous bytes per instruction.
-  float4* const hid_t = a.sv.hidden_t + ((size_t)rank * 3 * B + b) * 32 * A;  // + L * B * 32 * A per layer
-  float4* const x0_t = a.sv.x0_t + ((size_t)rank * B + b) * 32 * A;
-  const float4* const goal_in_t = a.sv.goal_in_t + (size_t)b * 32 * A;
-  const float4* const latent_in_t = a.sv.latent_in_t + (size_t)b * 32 * A;
-  for (int L = 0; L < 3; ++L) {  // hidden state of the previous launch (or zeros after tb_rollout_init) -> working copy
-    const float4* src = reinterpret_cast<const float4*>(a.sv.hidden + ((size_t)L * BA + (size_t)b * A) * D);
-    float4* dst = hid_t + (size_t)L * B * 32 * A;
-    for (int i = tid; i < A * 32; i += THREADS) {
-      const int ag_ = i % A, c4 = i / A;
-      dst[c4 * A + ag_] = src[ag_ * 32 + c4];
-    }
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  cluster_sync_all();  // barriers initialised and working copies taken in every CTA of the cluster
-  const uint32_t tm0 = (uint32_t)uniform((int)sm.tmem_base);
-
-  StepCfg cfg;
-  cfg.nblk_map = (nkey_map + 63) / 64;
-  cfg.rank = rank;
-  cfg.n_cta = n_cta;
-  cfg.kv_map = in.kv_map_tc + (size_t)s * nT_map * BLK;
-  cfg.kv_map_layer_stride = (size_t)S * nT_map * BLK;
-  cfg.kv_tl_layer_stride = (size_t)S * Th * nT_tl * BLK;
-
-  if (warp == 9) {
-    // ========================================================================================================== loader
-    {
-      LoaderT<Smem> ld(sm);
-      for (int t = a.t_first; t <= a.t_last; ++t) {
-        const int tl_t = min(t - 1, Th - 1);
-        cfg.nblk_tl = (uniform(in.n_key_tl[(size_t)s * Th + tl_t]) + 63) / 64;
-        cfg.kv_tl = in.kv_tl_tc + ((size_t)s * Th + tl_t) * nT_tl * BLK;
-        enumerate_step(a, cfg, ld);
-      }
-    }
-  } else if (warp == 8) {
-    // ========================================================================================================== issuer
-    {  // the whole warp runs the issue program (so that every operand is provably warp-uniform); one elected lane issues
-      IssuerT<Smem> is(sm, tm0);
-      for (int t = a.t_first; t <= a.t_last; ++t) {
-        const int tl_t = min(t - 1, Th - 1);
-        cfg.nblk_tl = (uniform(in.n_key_tl[(size_t)s * Th + tl_t]) + 63) / 64;
-        cfg.kv_tl = nullptr;
-        enumerate_step(a, cfg, is);
-      }
-    }
-  } else {
-    // ========================================================================================================== workers
-    const int quad = warp & 3, half = warp >> 2;
-    const int l = quad * 32 + lane;  // TMEM lane
-    const int ag = l & 63, upper = l >> 6;
-    const int c0 = half * 64;
-    const bool live = ag < A;
-    const bool writer = upper == 0 && live && rank == 0;  // the lane that owns the global outputs of agent `ag`
-    const bool scratch_writer = upper == 0 && live;       // ... and this CTA's private scratch (x0)
-    // Rows a + 64 duplicate rows a.  Only the query projection needs the duplicate (head-stacked attention), so the warps of
-    // the upper lanes skip every other epilogue and just keep the barrier / mbarrier arrival counts.
-    const int cs = c0 + 32 * upper;  // first of the 32 columns this thread owns in split epilogues
-    const size_t ba = (size_t)b * A + (live ? ag : 0), sa = (size_t)s * A + (live ? ag : 0);
-    const uint32_t tm = tm0 + ((uint32_t)(quad * 32) << 16);
-    uint32_t n_mma = 0, n_s = 0, n_o = 0, n_grant = 0, n_ln = 0, n_lp = 0;
-    int n_mark = 0;
-    auto mark = [&]() {
-      if (a.trace && blockIdx.x == 0 && tid == 0 && n_mark < 1000) a.trace[n_mark++] = clock64();
-    };
-#ifdef TB_TRACE_DETAIL
-    int n_dmark = 0, t_cur = 0;
-    auto dmark = [&](int id) {  // detailed (id, clock) pairs of one warm step, both softmax groups' leaders
-      if (a.trace && blockIdx.x == 0 && (tid == 0 || tid == 128) && t_cur == a.t_first + 3 && n_dmark < 700) {
-        long long* dst = a.trace + 1024 + (tid == 128 ? 1400 : 0) + 2 * n_dmark++;
-        dst[0] = id;
-        dst[1] = clock64();
-      }
-    };
-#else
-    auto dmark = [](int) {};  // (build with -DTB_TRACE_DETAIL for per-phase marks, tools/trace_rollout.py)
-#endif
-
-    auto signal_ready = [&]() {  // TMEM operand written / accumulator consumed -> issuer
-      tc::tmem_st_wait();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.ready);
-    };
-    auto wait_gemm = [&]() {
-      tc::mbar_wait(&sm.mma, n_mma & 1);
-      tc::tc_fence_after();
-      ++n_mma;
-    };
-    auto xs_at = [&](int c) -> float& { return sm.xs[c * MAXA + ag]; };
-    auto load_x = [&](float (&v)[64]) {
-#pragma unroll
-      for (int i = 0; i < 64; ++i) v[i] = xs_at(c0 + i);
-    };
-    auto write_A = [&](uint32_t col, const float (&v)[64]) {  // columns c0 .. c0+63 of a K = 128 operand
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        float ph[16], pl[16];
-        tc::split32_packed(*reinterpret_cast<const float(*)[32]>(&v[32 * j]), ph, pl);
-        tc::tmem_st16(tm + col + (c0 + 32 * j) / 2, ph);
-        tc::tmem_st16(tm + col + 64 + (c0 + 32 * j) / 2, pl);
-      }
-    };
-    auto load_acc = [&](uint32_t col, float (&v)[64]) {
-      tc::tmem_ld32(tm + col + c0, *reinterpret_cast<float(*)[32]>(&v[0]));
-      tc::tmem_ld32(tm + col + c0 + 32, *reinterpret_cast<float(*)[32]>(&v[32]));
-      tc::tmem_ld_wait();
-    };
-    // LayerNorm over the 128 columns of a row held by the thread pair (l, half 0 / 1): one exchange of {sum, M2}
-    auto layernorm64 = [&](float (&v)[64], const float* g, const float* bt, bool active = true) {
-      if (!active) {  // a warp that skips this LayerNorm still takes part in the exchange barrier
-        ++n_ln;
-        worker_sync();
-        return;
-      }
-      float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int i = 0; i < 64; ++i) s4[i & 3] += v[i];
-      const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-      const float mloc = sum * (1.0f / 64);
-      float q4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        const float d = v[i] - mloc;
-        q4[i & 3] = fmaf(d, d, q4[i & 3]);
-      }
-      const float m2 = (q4[0] + q4[1]) + (q4[2] + q4[3]);
-      const int buf = n_ln & 1;
-      ++n_ln;
-      sm.red[buf][half][l] = make_float2(sum, m2);
-      worker_sync();
-      const float2 o = sm.red[buf][half ^ 1][l];
-      const float mean = (sum + o.x) * (1.0f / 128);
-      const float dm_ = (o.x - sum) * (1.0f / 64);  // difference of the two half means
-      const float var = (m2 + o.y + dm_ * dm_ * 32.0f) * (1.0f / 128);  // Chan: + n_a n_b / (n_a + n_b) * delta^2
-      const float rstd = 1.0f / sqrtf(var + LN_EPS);
-#pragma unroll
-      for (int i = 0; i < 64; ++i) v[i] = (v[i] - mean) * rstd * g[c0 + i] + bt[c0 + i];
-    };
-    // parameter vectors: the set of phase `p` is fetched into registers, committed to lp[n_lp & 1] later in the same phase
-    float4 pf0 = make_float4(0.f, 0.f, 0.f, 0.f), pf1 = pf0;
-    auto fetch_params = [&](int p) {
-      const int o0 = phase_vec(p, warp), o1 = phase_vec(p, warp + 8);
-      if (o0 >= 0) pf0 = __ldg(reinterpret_cast<const float4*>(packed + o0) + lane);
-      if (o1 >= 0) pf1 = __ldg(reinterpret_cast<const float4*>(packed + o1) + lane);
-    };
-    auto commit_params = [&]() {  // into the buffer that the NEXT phase reads
-      float (*dst)[128] = sm.lp[(n_lp + 1) & 1];
-      reinterpret_cast<float4*>(dst[warp])[lane] = pf0;
-      reinterpret_cast<float4*>(dst[warp + 8])[lane] = pf1;
-    };
-    fetch_params(0);
-    {
-      float (*dst)[128] = sm.lp[0];
-      reinterpret_cast<float4*>(dst[warp])[lane] = pf0;
-      reinterpret_cast<float4*>(dst[warp + 8])[lane] = pf1;
-    }
-    worker_sync();
-
-    const float sc = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e): softmax in base 2
-
-    // per-rollout constants of the tail -> shared memory (in every CTA of the cluster)
-    if (half == 0 && upper == 0 && live) {
-      const int b2o[3] = {tbw::action_head_mlp_mean_0_fc_layers_2_bias, tbw::action_head_mlp_mean_1_fc_layers_2_bias,
-                          tbw::action_head_mlp_mean_2_fc_layers_2_bias};
-      const int lso[3] = {tbw::action_head_log_std_0, tbw::action_head_log_std_1, tbw::action_head_log_std_2};
-      float b2x = 0.f, b2y = 0.f, ls[2] = {0.f, 0.f};
-      for (int c3 = 0; c3 < 3; ++c3)
-        if (sm.type[ag][c3]) {
-          b2x += __ldg(packed + b2o[c3]);
-          b2y += __ldg(packed + b2o[c3] + 1);
-          ls[0] += __ldg(packed + lso[c3]);
-          ls[1] += __ldg(packed + lso[c3] + 1);
-        }
-      float logp = 0.f;
-      for (int d = 0; d < 2; ++d) logp += -logf(expf(ls[d])) - 0.91893853320467267f;
-      sm.tailc[0][ag] = b2x;
-      sm.tailc[1][ag] = b2y;
-      sm.tailc[2][ag] = logp;
-      sm.tailc[3][ag] = in.latent_logp[ba];
-      for (int i = 0; i < 3; ++i) sm.tailc[4 + i][ag] = in.goal_gt ? in.goal_gt[sa * 4 + i] : 0.f;
-      sm.tailc[7][ag] = in.agent_size[sa * 3] * 8.0f;
-      long dst = in.dest[ba];
-      dst = dst < 0 ? 0 : (dst >= dm.n_pl ? dm.n_pl - 1 : dst);
-      const uint8_t* dtype = in.map_type + ((size_t)s * dm.n_pl + dst) * TB_PL_TYPE;
-      const bool lane_t = dtype[0] || dtype[1] || dtype[2] || dtype[3], edge_t = dtype[4] != 0;
-      sm.tailc[8][ag] = 50.0f * (1.0f - (edge_t ? 1.0f : 0.f) * 0.8f);
-      sm.tflag[ag] = (uint8_t)((lane_t ? 1 : 0) | (edge_t ? 2 : 0));
-      if (ag == 0)
-        for (int i = 0; i < 4; ++i) sm.map_boundary[i] = in.map_boundary[(size_t)s * 4 + i];
-    }
-
-#pragma unroll 1
-    for (int t = a.t_first; t <= a.t_last; ++t) {
-      const int tl_t = min(t - 1, Th - 1);
-      const int nkey_tl = uniform(in.n_key_tl[(size_t)s * Th + tl_t]);
-#ifdef TB_TRACE_DETAIL
-      t_cur = t;
-#endif
-      mark();
-      // ---- validity of this step; interaction bypass decision -> issuer / loader ----------------------------------------
-      const bool valid = sm.valid[ag] != 0;
-      const unsigned vm_lo = __ballot_sync(0xffffffffu, sm.valid[lane] != 0);
-      const unsigned vm_hi = __ballot_sync(0xffffffffu, sm.valid[lane + 32] != 0);
-      const unsigned long long vmask = ((unsigned long long)vm_hi << 32) | vm_lo;
-      const int n_valid = __popc(vm_lo) + __popc(vm_hi);
-      if (tid == 0) {
-        *reinterpret_cast<volatile int*>(&sm.n_valid) = n_valid;
-        __threadfence_block();
-        mbar_arrive(&sm.cfg);  // loader and issuer both wait for this phase
-      }
-      // ---- state embedding: get_agent_attr_and_pe + agent_encoder (sc_input.py:142-165, input_pe_encoder.py:41-61) -----------
-      {
-        const int part = tid >> 6;  // features [32 part, 32 part + 32) of agent ag
-        const float4 st = sm.pose[ag];
-        if (part == 0) {
-          float at[12];
-          at[0] = sm.vel[ag].x, at[1] = sm.vel[ag].y, at[2] = st.w, at[3] = sm.yaw_rate[ag], at[4] = sm.acc[ag];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            at[5 + i] = in.agent_size[sa * 3 + i];
-            at[8 + i] = sm.type[ag][i] ? 1.f : 0.f;
-          }
-          at[11] = 0.f;
-          float h[32];
-#pragma unroll
-          for (int o = 0; o < 32; ++o) {
-            float acc = sm.emb_b1[o];
-#pragma unroll
-            for (int k = 0; k < 12; ++k) acc = fmaf(at[k], sm.emb_w1[((k >> 2) * 32 + o) * 4 + (k & 3)], acc);
-            h[o] = fmaxf(acc, 0.f);
-          }
-#pragma unroll 4
-          for (int o = 0; o < 32; ++o) {
-            float acc = sm.emb_b2[o];
-#pragma unroll
-            for (int k = 0; k < 32; ++k) acc = fmaf(h[k], sm.emb_w2[((k >> 2) * 32 + o) * 4 + (k & 3)], acc);
-            sm.xs[o * MAXA + ag] = valid ? acc : 0.f;
-          }
-        } else {
-#pragma unroll 4
-          for (int i = 0; i < 32; ++i) {
-            const int j = 32 * (part - 1) + i;  // PE element 0..95
-            float v;
-            if (j < 12) v = cosf(st.x * sm.f_xy[2 * j]);
-            else if (j < 24) v = sinf(st.x * sm.f_xy[2 * (j - 12) + 1]);
-            else if (j < 36) v = cosf(st.y * sm.f_xy[2 * (j - 24)]);
-            else if (j < 48) v = sinf(st.y * sm.f_xy[2 * (j - 36) + 1]);
-            else if (j < 72) v = cosf(st.z * sm.f_yaw[2 * (j - 48)]);
-            else v = sinf(st.z * sm.f_yaw[2 * (j - 72) + 1]);
-            sm.xs[(32 + j) * MAXA + ag] = valid ? v : 0.f;
-          }
-        }
-      }
-      mark();
-
-      // ---- 9 pre-LN cross-attention layers ------------------------------------------------------------------------------------
-      const bool bypass = n_valid == 1;
-#pragma unroll 1
-      for (int Lx = 0; Lx < 9; ++Lx) {
-        const int kind = Lx / 3;
-        if (kind == 2 && bypass) break;
-        const int nkey = kind == 0 ? nkey_map : kind == 1 ? nkey_tl : (n_valid > 0 ? MAXA : 0);
-        const int nblk = (nkey + 63) / 64;
-        worker_sync();  // xs / lp of this phase complete
-        dmark(100 + Lx * 10);
-        const float (*lp)[128] = sm.lp[n_lp & 1];
-        {  // next phase's parameters
-          int pn = Lx + 1;
-          if (pn == 6 && bypass) pn = 9;
-          fetch_params(pn);
-        }
-        float v[64];
-        if (nblk > 0) {
-          if (kind == 2) {
-            // K|V of the block input x0 (agent_interaction.py:52: tgt = attn_to_map_aware_feature for all 3 layers)
-            // (both lanes of an agent write the operand, so both accumulator rows are valid and each lane converts 32 of the
-            // agent's 64 columns of its column half into the key block)
-            float tg[64];
-            if (Lx == 6) {
-              load_x(tg);
-              if (scratch_writer) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) x0_t[(c0 / 4 + i) * A + ag] = make_float4(tg[4 * i], tg[4 * i + 1], tg[4 * i + 2], tg[4 * i + 3]);
-              }
-            } else if (live) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {  // written at Lx == 6 by the lower lane of this agent (CTA barriers since)
-                const float4 q = x0_t[(c0 / 4 + i) * A + ag];
-                tg[4 * i] = q.x, tg[4 * i + 1] = q.y, tg[4 * i + 2] = q.z, tg[4 * i + 3] = q.w;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 64; ++i) tg[i] = 0.f;
-            }
-            layernorm64(tg, lp[8], lp[9]);
-            write_A(T_A, tg);
-            signal_ready();  // -> Wk (ACC0), Wv (ACC1)
-            dmark(500 + Lx);
-            wait_gemm();
-            dmark(510 + Lx);
-            tc::mbar_wait(&sm.grant, n_grant & 1);
-            ++n_grant;
-            dmark(520 + Lx);
-            {
-              unsigned char* blk = sm.ring[*reinterpret_cast<volatile int*>(&sm.kvi_slot)];
-              float kk[32];
-              tc::tmem_ld32(tm + T_ACC0 + cs, kk);  // K[ag, cs .. cs+31]: key row ag of K-block `half`
-              tc::tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) kk[i] += lp[10][cs + i];
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                uint4 hi, lo;
-                tc::split8(kk + 8 * c, hi, lo);
-                const uint32_t off = half * 8192 + tc::sw128_off(ag, 4 * upper + c);
-                *reinterpret_cast<uint4*>(blk + off) = hi;
-                *reinterpret_cast<uint4*>(blk + 16384 + off) = lo;
-              }
-              dmark(530 + Lx);
-              tc::tmem_ld32(tm + T_ACC1 + cs, kk);  // V[ag, cs .. cs+31] -> V^T rows d = cs + i, key column ag
-              tc::tmem_ld_wait();
-              unsigned char* vt = blk + HALF + (ag & 7) * 2;
-              const uint32_t kc = (uint32_t)(ag >> 3);
-#pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                const float v0 = kk[i] + lp[11][cs + i], v1 = kk[i + 1] + lp[11][cs + i + 1];
-                uint32_t hh, ll;
-                tc::split_pair(v0, v1, hh, ll);
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const int d = cs + i + e;
-                  const uint32_t off = (uint32_t)((d >> 3) * 1024 + (d & 7) * 128) + ((kc ^ (uint32_t)(d & 7)) << 4);
-                  *reinterpret_cast<unsigned short*>(vt + off) = (unsigned short)(e ? hh >> 16 : hh & 0xffffu);
-                  *reinterpret_cast<unsigned short*>(vt + 16384 + off) = (unsigned short)(e ? ll >> 16 : ll & 0xffffu);
-                }
-              }
-              tc::fence_proxy_async();
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.wfill);
-            dmark(540 + Lx);
-          }
-          load_x(v);
-          layernorm64(v, lp[0], lp[1]);
-          write_A(T_A, v);
-          signal_ready();  // -> Wq
-          dmark(101 + Lx * 10);
-          // (layers whose attention is split over the cluster use the next-phase parameter buffer as merge scratch first)
-          const bool split_layer = kind == 0 && n_cta > 1;
-          if (!split_layer) commit_params();
-          wait_gemm();
-          dmark(102 + Lx * 10);
-          {  // stacked query operand of pass `half`: own head's 32 dims, zeros in the twin head's dims
-            float q[32];
-            tc::tmem_ld32(tm + T_ACC0 + c0 + 32 * upper, q);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) q[i] = (q[i] + lp[2][c0 + 32 * upper + i]) * sc;
-            float ph[16], pl[16], zz[16];
-            tc::split32_packed(q, ph, pl);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) zz[i] = 0.f;
-            tc::tmem_st16(tm + T_A + 32 * half + 16 * upper, ph);
-            tc::tmem_st16(tm + T_A + 64 + 32 * half + 16 * upper, pl);
-            tc::tmem_st16(tm + T_A + 32 * half + 16 * (1 - upper), zz);
-            tc::tmem_st16(tm + T_A + 64 + 32 * half + 16 * (1 - upper), zz);
-          }
-          signal_ready();  // -> QK^T(0, .)
-          dmark(103 + Lx * 10);
-          // ---- online softmax of pass `half` over the key blocks (lazy rescaling) -----------------------------------------------
-          float m_ref = -INFINITY, l_sum = 0.f;
-          const uint32_t sbase = tm + T_ACC0 + 64 * half;
-          const uint32_t obase = tm + T_O + 64 * half + 32 * upper;
-          // the agent->map attention is split over the cluster: this CTA owns key blocks rank, rank + n_cta, ...
-          const bool split = kind == 0 && n_cta > 1;
-          const int nblk_my = kind == 0 ? (nblk > rank ? (nblk - rank + n_cta - 1) / n_cta : 0) : nblk;
-#pragma unroll 1
-          for (int jb = 0; jb < nblk_my; ++jb) {
-            const int key0 = (kind == 0 ? rank + jb * n_cta : jb) * 64;  // first key of this block
-            tc::mbar_wait(&sm.s[half], n_s & 1);
-            ++n_s;
-            tc::tc_fence_after();
-            if (Lx == 0 && jb < 8) dmark(1000 + jb * 4);
-            float sv_[64];
-            tc::tmem_ld32(sbase, *reinterpret_cast<float(*)[32]>(&sv_[0]));
-            tc::tmem_ld32(sbase + 32, *reinterpret_cast<float(*)[32]>(&sv_[32]));
-            tc::tmem_ld_wait();
-            if (Lx == 0 && jb < 8) dmark(1001 + jb * 4);
-            if (kind == 2) {
-              const unsigned long long en = vmask & ~(1ull << ag);
-#pragma unroll
-              for (int j = 0; j < 64; ++j)
-                if (!((en >> j) & 1ull)) sv_[j] = -INFINITY;
-            } else if (key0 + 64 > nkey) {
-#pragma unroll
-              for (int j = 0; j < 64; ++j)
-                if (key0 + j >= nkey) sv_[j] = -INFINITY;
-            }
-            float mx4[4] = {sv_[0], sv_[1], sv_[2], sv_[3]};
-#pragma unroll
-            for (int j = 4; j < 64; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], sv_[j]);
-            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-            float alpha = 1.f;
-            bool resc = false;
-            if (mx > m_ref + 8.0f) {
-              alpha = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - mx);
-              m_ref = mx;
-              l_sum *= alpha;
-              resc = jb > 0;
-            }
-            const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
-            float ps4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int j = 0; j < 64; ++j) {
-              sv_[j] = ex2_approx(sv_[j] + neg_m);
-              ps4[j & 3] += sv_[j];
-            }
-            l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
-            {
-              float ph[16], pl[16];
-              tc::split32_packed(*reinterpret_cast<const float(*)[32]>(&sv_[0]), ph, pl);
-              tc::tmem_st16(sbase, ph);
-              tc::tmem_st16(sbase + 32, pl);
-              tc::split32_packed(*reinterpret_cast<const float(*)[32]>(&sv_[32]), ph, pl);
-              tc::tmem_st16(sbase + 16, ph);
-              tc::tmem_st16(sbase + 48, pl);
-            }
-            if (__any_sync(0xffffffffu, resc)) {  // PV(jb-1) is complete (its commit precedes QK^T(jb)'s): O is quiescent
-              float o[32];
-              tc::tmem_ld32(obase, o);
-              tc::tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) o[j] *= alpha;
-              tc::tmem_st32(obase, o);
-            }
-            if (Lx == 0 && jb < 8) dmark(1002 + jb * 4);
-            tc::tmem_st_wait();
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.p[half]);  // -> PV(jb, half), QK^T(jb+1, half)
-            if (Lx == 0 && jb < 8) dmark(1003 + jb * 4);
-          }
-          dmark(104 + Lx * 10);
-          {
-            float o[32];
-            if (nblk_my > 0) {
-              tc::mbar_wait(&sm.o[half], n_o & 1);
-              ++n_o;
-              tc::tc_fence_after();
-              tc::tmem_ld32(obase, o);
-              tc::tmem_ld_wait();
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) o[j] = 0.f;
-            }
-            float* xo_mine = &sm.xo[(c0 + 32 * upper) * MAXA + ag];  // this thread's 32 outputs: stride MAXA
-            if (split) {
-              // Merge of the online-softmax partials (O, m, l) of the cluster's CTAs, all traffic as remote STORES into
-              // distributed shared memory: reduce-scatter (CTA r receives everyone's partial of column range r and merges it),
-              // then all-gather of the merged, normalised ranges straight into every CTA's exchange buffer.
-              const int nq = 8 / n_cta;  // float4 per thread and range (the 32 outputs of a thread = 8 float4)
-              float4* xp = reinterpret_cast<float4*>(sm.xo);                        // slots [src rank][nq][256] float4
-              float2* mls = reinterpret_cast<float2*>(&sm.lp[(n_lp + 1) & 1][0][0]);  // [src rank][256] (m, l)
-              const uint32_t xp_addr = tc::smem_u32(xp), mls_addr = tc::smem_u32(mls), xo_addr = tc::smem_u32(sm.xo);
-              dmark(600 + Lx);
-              cluster_sync_relaxed();  // every CTA is done with its previous use of the exchange buffer
-              dmark(610 + Lx);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const int dst = q / nq, qq = q % nq;
-                const float4 val = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-                const uint32_t off = (uint32_t)(((rank * nq + qq) * WORKERS + tid) * 16);
-                if (dst == rank) xp[(rank * nq + qq) * WORKERS + tid] = val;
-                else st_cluster_f32x4(mapa(xp_addr, (uint32_t)dst) + off, val);
-              }
-              for (int dst = 0; dst < n_cta; ++dst) {
-                if (dst == rank) mls[rank * WORKERS + tid] = make_float2(m_ref, l_sum);
-                else st_cluster_f32x2(mapa(mls_addr, (uint32_t)dst) + (uint32_t)((rank * WORKERS + tid) * 8), make_float2(m_ref, l_sum));
-              }
-              dmark(620 + Lx);
-              cluster_sync_all();  // release / acquire: all partials of my range have landed
-              dmark(630 + Lx);
-              float m_all = -INFINITY;
-              float2 mlr[4];
-#pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                mlr[r] = r < n_cta ? mls[r * WORKERS + tid] : make_float2(-INFINITY, 0.f);
-                m_all = fmaxf(m_all, mlr[r].x);
-              }
-              float l_all = 0.f, w[4];
-#pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                w[r] = mlr[r].x == -INFINITY ? 0.f : exp2f(mlr[r].x - m_all);
-                l_all = fmaf(w[r], mlr[r].y, l_all);
-              }
-              const float inv = l_all > 0.f ? 1.0f / l_all : 0.f;
-              float4 mg[4];  // merged outputs 4 * (rank * nq + qq) + e of this thread's (lane, pass)
-#pragma unroll
-              for (int qq = 0; qq < 4; ++qq) {
-                mg[qq] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (qq < nq) {
-#pragma unroll
-                  for (int r = 0; r < 4; ++r) {
-                    if (r < n_cta) {
-                      const float4 pv = xp[(r * nq + qq) * WORKERS + tid];
-                      mg[qq].x = fmaf(w[r], pv.x, mg[qq].x);
-                      mg[qq].y = fmaf(w[r], pv.y, mg[qq].y);
-                      mg[qq].z = fmaf(w[r], pv.z, mg[qq].z);
-                      mg[qq].w = fmaf(w[r], pv.w, mg[qq].w);
-                    }
-                  }
-                  mg[qq].x *= inv, mg[qq].y *= inv, mg[qq].z *= inv, mg[qq].w *= inv;
-                }
-              }
-              dmark(640 + Lx);
-              cluster_sync_relaxed();  // every CTA has consumed its slots: the exchange buffer becomes the merged output
-              dmark(650 + Lx);
-              // merged output of (lane, pass) thread `tid`, float4 q, at xp[q * 256 + tid] in EVERY CTA (16-byte remote stores)
-#pragma unroll
-              for (int qq = 0; qq < 4; ++qq) {
-                if (qq < nq) {
-                  const uint32_t off = (uint32_t)((((rank * nq + qq) * WORKERS) + tid) * 16);
-                  for (int dst = 0; dst < n_cta; ++dst) {
-                    if (dst == rank) xp[(rank * nq + qq) * WORKERS + tid] = mg[qq];
-                    else st_cluster_f32x4(mapa(xp_addr, (uint32_t)dst) + off, mg[qq]);
-                  }
-                }
-              }
-              dmark(660 + Lx);
-              cluster_sync_all();  // release / acquire: the merged attention output is complete in every CTA
-              dmark(670 + Lx);
-              commit_params();
-            } else {
-              const float inv = l_sum > 0.f ? 1.0f / l_sum : 0.f;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) xo_mine[j * MAXA] = o[j] * inv;
-            }
-          }
-          worker_sync();
-          // From here to the end of the layer the two lanes of an agent (rows a and a + 64) both write complete A operands, so
-          // both accumulator rows are valid and the epilogues that end in shared memory are split between them: the thread of
-          // lane l handles the 32 columns cs .. cs + 31 of its column half.
-          if (split) {  // merged outputs live as [float4 q][worker thread]: heads 2 half / 2 half + 1 of agent ag
-            const float4* xp = reinterpret_cast<const float4*>(sm.xo);
-#pragma unroll
-            for (int which = 0; which < 2; ++which) {
-              const int src_tid = half * 128 + 64 * which + ag;
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 t4 = xp[q * WORKERS + src_tid];
-                v[32 * which + 4 * q] = t4.x, v[32 * which + 4 * q + 1] = t4.y, v[32 * which + 4 * q + 2] = t4.z, v[32 * which + 4 * q + 3] = t4.w;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = sm.xo[(c0 + i) * MAXA + ag];
-          }
-          write_A(T_A, v);
-          signal_ready();  // -> Wo
-          dmark(105 + Lx * 10);
-          wait_gemm();
-          dmark(106 + Lx * 10);
-          {  // x += attention output (all rows have at least one enabled key here)
-            float o32[32];
-            tc::tmem_ld32(tm + T_ACC0 + cs, o32);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) xs_at(cs + i) += o32[i] + lp[3][cs + i];
-          }
-          worker_sync();
-        } else {
-          commit_params();
-        }
-        {
-          float x2[64];
-          load_x(x2);
-          layernorm64(x2, lp[4], lp[5]);
-          write_A(T_A, x2);
-        }
-        signal_ready();  // -> W1
-        dmark(107 + Lx * 10);
-        wait_gemm();
-        dmark(108 + Lx * 10);
-        {
-          float h1[64];
-          load_acc(T_ACC0, h1);
-#pragma unroll
-          for (int i = 0; i < 64; ++i) h1[i] = fmaxf(h1[i] + lp[6][c0 + i], 0.f);
-          write_A(T_A, h1);
-        }
-        signal_ready();  // -> W2
-        dmark(109 + Lx * 10);
-        wait_gemm();
-        dmark(190 + Lx);
-        {  // x = valid ? x + FFN : 0
-          float y[32];
-          tc::tmem_ld32(tm + T_ACC0 + cs, y);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) xs_at(cs + i) = valid ? xs_at(cs + i) + y[i] + lp[7][cs + i] : 0.f;
-        }
-        ++n_lp;
-      }
-      mark();
-
-      // ---- agent_temporal: 3-layer GRU, one time step (agent_temporal.py:147-153) -------------------------------------------------
-#pragma unroll 1
-      for (int L = 0; L < 3; ++L) {
-        worker_sync();
-        const float (*lp)[128] = sm.lp[n_lp & 1];
-        dmark(200 + L * 10);
-        fetch_params(10 + L);  // 10, 11 = GRU layers 1, 2; 12 = add_goal
-        float4* hid = hid_t + (size_t)L * B * 32 * A + ag;  // column quad c4 of this agent at hid[c4 * A]
-        {  // both lanes of an agent write the operands x and h (valid accumulator rows for the split epilogues)
-          float x[64];
-          load_x(x);
-          write_A(T_A, x);
-          if (live) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float4 q = hid[(c0 / 4 + i) * A];
-              x[4 * i] = q.x, x[4 * i + 1] = q.y, x[4 * i + 2] = q.z, x[4 * i + 3] = q.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 64; ++i) x[i] = 0.f;
-          }
-          write_A(T_A2, x);
-        }
-        signal_ready();  // -> r (ACC0), W_hn h (ACC1)
-        dmark(201 + L * 10);
-        commit_params();
-        wait_gemm();
-        dmark(202 + L * 10);
-        {  // r * (W_hn h + b_hn) of this thread's 32 columns, parked in the exchange buffer (free during the GRU)
-          float r[32], rh[32];
-          tc::tmem_ld32(tm + T_ACC0 + cs, r);
-          tc::tmem_ld32(tm + T_ACC1 + cs, rh);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float rg = fast_sigmoid(r[i] + lp[0][cs + i] + lp[3][cs + i]);
-            sm.xo[(cs + i) * MAXA + ag] = rg * (rh[i] + lp[5][cs + i]);
-          }
-        }
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.ready);  // accumulators consumed -> z (ACC0), W_in x (ACC1)
-        dmark(203 + L * 10);
-        wait_gemm();
-        dmark(204 + L * 10);
-        {
-          float z[32], n[32];
-          tc::tmem_ld32(tm + T_ACC0 + cs, z);
-          tc::tmem_ld32(tm + T_ACC1 + cs, n);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 hp4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) hp4 = hid[(cs / 4 + i) * A];
-            const float hp_[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
-            float hn_[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = cs + 4 * i + e;
-              const float zg = fast_sigmoid(z[4 * i + e] + lp[1][c] + lp[4][c]);
-              const float ng = fast_tanh(n[4 * i + e] + lp[2][c] + sm.xo[c * MAXA + ag]);
-              hn_[e] = (1.0f - zg) * ng + zg * hp_[e];
-            }
-            // h[:, ~valid] = 0; the next GRU layer sees the unmasked output, after the last layer x[~valid] = 0
-            if (live)
-              hid[(cs / 4 + i) * A] = valid ? make_float4(hn_[0], hn_[1], hn_[2], hn_[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) xs_at(cs + 4 * i + e) = (L == 2 && !valid) ? 0.f : hn_[e];
-          }
-        }
-        ++n_lp;
-      }
-      mark();
-
-      // ---- add_goal, add_latent (add_latent_goal.py:57-77, mode cat, res_add) ---------------------------------------------------------
-#pragma unroll 1
-      for (int j = 0; j < 2; ++j) {
-        worker_sync();
-        const float (*lp)[128] = sm.lp[n_lp & 1];
-        dmark(300 + j * 10);
-        fetch_params(13 + j);  // 13 = add_latent, 14 = head
-        const bool zv = j == 0 ? (sm.goal_valid[ag] != 0) : valid;
-        const float4* zin = (j == 0 ? goal_in_t : latent_in_t) + (c0 / 4) * A + ag;
-        {
-          float x[64], z[64];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live && zv) q = __ldg(zin + i * A);
-            z[4 * i] = fmaxf(q.x, 0.f), z[4 * i + 1] = fmaxf(q.y, 0.f), z[4 * i + 2] = fmaxf(q.z, 0.f), z[4 * i + 3] = fmaxf(q.w, 0.f);
-          }
-          write_A(T_A2, z);
-          load_x(x);
-          write_A(T_A, x);
-        }
-        signal_ready();
-        dmark(301 + j * 10);
-        commit_params();
-        wait_gemm();
-        dmark(302 + j * 10);
-        {
-          float h1[64];
-          load_acc(T_ACC0, h1);
-#pragma unroll
-          for (int i = 0; i < 64; ++i) h1[i] = fmaxf(h1[i] + lp[0][c0 + i], 0.f);
-          write_A(T_A, h1);
-        }
-        signal_ready();
-        dmark(303 + j * 10);
-        wait_gemm();
-        dmark(304 + j * 10);
-        {  // split epilogue: this thread's 32 columns
-          float h2[32];
-          tc::tmem_ld32(tm + T_ACC0 + cs, h2);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float hz = fmaxf(h2[i] + lp[1][cs + i], 0.f);
-            xs_at(cs + i) = valid ? (zv ? hz : 0.f) + xs_at(cs + i) : 0.f;
-          }
-        }
-        ++n_lp;
-      }
-      // ---- action head (action_head.py:70-87): per-type MLP 128 -> 128 -> 2, masked by type & valid, summed -------------------------------
-      // the tail's ground-truth operands of this step are fetched now, so that their latency hides behind the head GEMMs
-      const bool tail_thread = half == 0 && upper == 0 && live;  // runs in every CTA of the cluster (state stays replicated)
-      const bool out_w = rank == 0;                              // ... but only rank 0 writes the global outputs
-      const bool has_gt = t < Tg;
-      const size_t gidx = ((size_t)s * Tg + (has_gt ? t : 0)) * A + ag;
-      float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
-      float2 g_vel = make_float2(0.f, 0.f);
-      float g_acc = 0.f, g_yr = 0.f;
-      bool ovr = false, gt_valid = false;
-      {
-        worker_sync();
-        const float (*lp)[128] = sm.lp[n_lp & 1];
-        dmark(320);
-        fetch_params(0);
-        {
-          float x[64];
-          load_x(x);
-          write_A(T_A, x);
-          if (a.out.trace_policy_feature && writer) {
-            float* dst = a.out.trace_policy_feature + ((ba * T) + (t - 1)) * D + c0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-          }
-        }
-        signal_ready();
-        dmark(321);
-        if (tail_thread && has_gt) {
-          ovr = in.tf_mask[gidx] != 0;
-          gt_valid = in.gt_valid[gidx] != 0;
-          gs = make_float4(in.gt_pos[gidx * 2], in.gt_pos[gidx * 2 + 1], in.gt_yaw[gidx], in.gt_spd[gidx]);
-          g_vel = make_float2(in.gt_vel[gidx * 2], in.gt_vel[gidx * 2 + 1]);
-          g_acc = in.gt_acc[gidx];
-          g_yr = in.gt_yaw_rate[gidx];
-        }
-        commit_params();
-        wait_gemm();
-        dmark(322);
-        {  // split epilogue: partial dot products of this thread's 32 hidden columns (tcgen05.ld is warp-collective: every
-           // lane loads all three accumulators and masks the contribution)
-          float m0 = 0.f, m1 = 0.f;
-#pragma unroll 1
-          for (int c3 = 0; c3 < 3; ++c3) {
-            float hdn[32];
-            tc::tmem_ld32(tm + 128 * c3 + cs, hdn);
-            tc::tmem_ld_wait();
-            const bool on = sm.type[ag][c3] && valid;
-            const float* w2 = &lp[3 + 2 * c3][0];  // Wt4[32][2][4]: (k, d) at ((k >> 2) * 2 + d) * 4 + (k & 3); 256 contiguous floats
-            float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float hv = fmaxf(hdn[i] + lp[c3][cs + i], 0.f);
-              const int k = cs + i;
-              s0 = fmaf(hv, w2[((k >> 2) * 2 + 0) * 4 + (k & 3)], s0);
-              s1 = fmaf(hv, w2[((k >> 2) * 2 + 1) * 4 + (k & 3)], s1);
-            }
-            if (on) {
-              m0 += s0;
-              m1 += s1;
-            }
-          }
-          sm.mean_part[2 * half + upper][ag][0] = m0;
-          sm.mean_part[2 * half + upper][ag][1] = m1;
-        }
-        ++n_lp;
-        worker_sync();
-      }
-      mark();
-
-      dmark(400);
-      // ---- per-agent tail: dynamics, override, rule checks, kill, goal_valid, reward, outputs ----------------------------------------------
-      if (tail_thread) {
-        float mean0 = (sm.mean_part[0][ag][0] + sm.mean_part[1][ag][0]) + (sm.mean_part[2][ag][0] + sm.mean_part[3][ag][0]);
-        float mean1 = (sm.mean_part[0][ag][1] + sm.mean_part[1][ag][1]) + (sm.mean_part[2][ag][1] + sm.mean_part[3][ag][1]);
-        if (valid) {
-          mean0 += sm.tailc[0][ag];
-          mean1 += sm.tailc[1][ag];
-        }
-        // MultiPathPP.process_action / update (dynamics.py:187-228); type order of the parameter tuples: veh, ped, cyc
-        const bool ty0 = sm.type[ag][0], ty1 = sm.type[ag][1], ty2 = sm.type[ag][2];
-        const bool k_has_type = ty0 || ty1 || ty2;
-        const float k_max_acc = (ty0 ? 5.0f : 0.f) + (ty1 ? 7.0f : 0.f) + (ty2 ? 6.0f : 0.f);
-        const float k_max_yr = (ty0 ? 1.5f : 0.f) + (ty1 ? 7.0f : 0.f) + (ty2 ? 3.0f : 0.f);
-        const float a_acc = valid ? tanhf(mean0) * k_max_acc : 0.f;
-        const float a_yr = valid ? tanhf(mean1) * k_max_yr : 0.f;
-        const float4 st = sm.pose[ag];
-        const float v_t = st.w + 0.05f * a_acc, th_t = st.z + 0.05f * a_yr;
-        float4 pred = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid && k_has_type) {
-          pred.x = st.x + 0.1f * (v_t * cosf(th_t));
-          pred.y = st.y + 0.1f * (v_t * sinf(th_t));
-          pred.z = st.z + 0.1f * a_yr;
-          pred.w = st.w + 0.1f * a_acc;
-        }
-        const size_t o = ba * T + (t - 1);
-        if (out_w) {
-          *reinterpret_cast<float4*>(a.out.preds + o * 4) = pred;
-          a.out.valid[o] = valid;
-          a.out.action_log_probs[o] = valid ? sm.tailc[2][ag] : 0.f;  // DiagGaussian log-prob of the deterministic sample, dynamics.py:77-80
-          a.out.latent_log_probs[o] = sm.tailc[3][ag];
-          if (a.out.trace_action_mean) {
-            a.out.trace_action_mean[o * 2] = mean0;
-            a.out.trace_action_mean[o * 2 + 1] = mean1;
-          }
-        }
-        // Dynamics.override_states (dynamics.py:121-149)
-        bool killed = sm.killed[ag] != 0;
-        const bool m = ovr && !killed;
-        bool nvalid = valid || m;
-        float4 ns = pred;
-        if (m) {
-          ns = gs;
-          sm.vel[ag] = g_vel;
-          sm.acc[ag] = g_acc;
-          sm.yaw_rate[ag] = g_yr;
-        }
-        if (out_w) a.out.override_masks[o] = ovr;
-        // TrafficRuleChecker.check, always-on subset (traffic_rule_checker.py:101-119,338-410,423-424,474-496)
-        const bool out_t = nvalid && (ns.x > sm.map_boundary[1] || ns.x < sm.map_boundary[0] || ns.y > sm.map_boundary[3] || ns.y < sm.map_boundary[2]);
-        bool outside = sm.sticky[0][ag] != 0, goal_r = sm.sticky[1][ag] != 0, dest_r = sm.sticky[2][ag] != 0;
-        outside |= out_t;
-        bool goal_t = false;
-        if (in.goal_gt) {
-          const float dx = ns.x - sm.tailc[4][ag], dy = ns.y - sm.tailc[5][ag];
-          const bool pos_ok = sqrtf(dx * dx + dy * dy) < sm.tailc[7][ag];
-          // cast_rad (transform_utils.py:10-12): (a + pi) % (2 pi) - pi with Python's sign-of-divisor modulo
-          const float PI_F = 3.14159265358979323846f, TWO_PI_F = 6.28318530717958647692f;
-          float w = fmodf(ns.z - sm.tailc[6][ag] + PI_F, TWO_PI_F);
-          if (w < 0.f) w += TWO_PI_F;
-          const bool rot_ok = fabsf(w - PI_F) < 0.26179938779914943654f;
-          goal_t = pos_ok && rot_ok && nvalid && !goal_r;
-        }
-        goal_r |= goal_t;
-        bool pos_reached = false, rot_reached = false;
-        const float k_dest_thresh = sm.tailc[8][ag];
-        const bool k_lane_t = (sm.tflag[ag] & 1) != 0, k_edge_t = (sm.tflag[ag] & 2) != 0;
-        const float hx = cosf(ns.z), hy = sinf(ns.z);
-        const float4* dn = a.sv.dest_nodes + (size_t)b * TB_PL_NODE * A + ag;
-#pragma unroll
-        for (int n0 = 0; n0 < TB_PL_NODE; n0 += 10) {
-          float4 nd[10];
-#pragma unroll
-          for (int n = 0; n < 10; ++n) nd[n] = __ldg(dn + (n0 + n) * A);
-#pragma unroll
-          for (int n = 0; n < 10; ++n) {
-            const float dx = ns.x - nd[n].x, dy = ns.y - nd[n].y;
-            pos_reached |= sqrtf(dx * dx + dy * dy) < k_dest_thresh;
-            rot_reached |= (hx * nd[n].z + hy * nd[n].w) > 0.86602540378443864676f;  // NaN (zero-length dir) compares false
-          }
-        }
-        const bool dest_t = !dest_r && nvalid && ((k_lane_t && pos_reached && rot_reached) || (k_edge_t && pos_reached));
-        dest_r |= dest_t;
-        if (out_w) {
-          const size_t vs = BA * T;
-          a.out.violations[0 * vs + o] = outside;
-          a.out.violations[1 * vs + o] = out_t;
-          a.out.violations[2 * vs + o] = goal_r;
-          a.out.violations[3 * vs + o] = goal_t;
-          a.out.violations[4 * vs + o] = dest_r;
-          a.out.violations[5 * vs + o] = dest_t;
-        }
-        // Dynamics.kill (dynamics.py:151-167): outside_map_this_step & ~gt_valid
-        const bool kill = out_t && !gt_valid;
-        killed |= kill;
-        nvalid = nvalid && !kill;
-        // disable_goal_reached (goal_manager.py:155-161)
-        const bool gv = sm.goal_valid[ag] && nvalid && !dest_r;
-        // DifferentiableReward.get, imitation part (rewards.py:117-131)
-        float reward = 0.f;
-        bool rv = valid;
-        if (has_gt) {
-          rv = valid && gt_valid;
-          if (rv) {
-            const float e_pos = smooth_l1(gs.x - pred.x) + smooth_l1(gs.y - pred.y);
-            const float e_rot = 0.5f * (1.0f - cosf(gs.z - pred.z));
-            const float e_spd = smooth_l1(gs.w - pred.w);
-            reward = 0.0f - (0.1f * e_pos + 10.0f * e_rot + 0.1f * e_spd);
-          }
-        }
-        if (out_w) {
-          a.out.diffbar_rewards[o] = reward;
-          a.out.diffbar_rewards_valid[o] = rv;
-        }
-        // state for the next step
-        sm.pose[ag] = ns;
-        sm.valid[ag] = nvalid;
-        sm.killed[ag] = killed;
-        sm.goal_valid[ag] = gv;
-        sm.sticky[0][ag] = outside;
-        sm.sticky[1][ag] = goal_r;
-        sm.sticky[2][ag] = dest_r;
-      }
-      dmark(401);
-      worker_sync();
-      dmark(402);
-    }
-    mark();
-    // ---- simulation state back to global memory (chunked stepping, final-state outputs) -------------------------------------------
-    worker_sync();
-    if (rank == 0) {  // GRU hidden state: working copy -> the ABI's [3, B*A, 128] layout
-      for (int L = 0; L < 3; ++L) {
-        float4* dst = reinterpret_cast<float4*>(a.sv.hidden + ((size_t)L * BA + (size_t)b * A) * D);
-        const float4* src = hid_t + (size_t)L * B * 32 * A;
-        for (int i = tid; i < A * 32; i += WORKERS) {
-          const int ag_ = i / 32, c4 = i % 32;
-          dst[ag_ * 32 + c4] = __ldcg(src + c4 * A + ag_);
-        }
-      }
-    }
-    if (half == 0 && writer) {
-      *reinterpret_cast<float4*>(a.sv.agent_state + ba * 4) = sm.pose[ag];
-      a.sv.vel[ba * 2] = sm.vel[ag].x;
-      a.sv.vel[ba * 2 + 1] = sm.vel[ag].y;
-      a.sv.acc[ba] = sm.acc[ag];
-      a.sv.yaw_rate[ba] = sm.yaw_rate[ag];
-      a.sv.valid[(size_t)((a.t_last + 1) & 1) * BA + ba] = sm.valid[ag];
-      a.sv.killed[ba] = sm.killed[ag];
-      a.sv.goal_valid[ba] = sm.goal_valid[ag];
-      for (int i = 0; i < 3; ++i) a.sv.sticky[(size_t)i * BA + ba] = sm.sticky[i][ag];
-    }
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(sm.tmem_base, 512);
-  cluster_sync_all();  // no CTA leaves while a peer may still read its shared memory or arrive on its barrier
-}
-
-// =============================================================================================================================
 // 16-worker-warp variant: FOUR threads per TMEM lane.  Thread (lane l, part 0..3) owns columns [32 part, 32 part + 32) of
 // lane l in every operand write (both lanes of an agent write complete A operands), and 16 columns [32 part + 16 upper, +16)
 // of the agent in the epilogues that end in shared / global memory.  In the attention the pass of a lane is shared by the
 // two threads part = 2 hp, 2 hp + 1: each takes 32 of the block's 64 keys, and they agree on the running maximum through
-// shared memory (one 64-thread named barrier per key block).  Same issuer / loader programs as the 8-warp kernel.
+// shared memory (one 64-thread named barrier per key block).  The first version of this kernel (8 worker
+// warps, two threads per lane: 25.5 vs 21.7 ms per rollout, profiles/r1j_*) was removed in round 2.
 // =============================================================================================================================
 constexpr int WORKERS16 = 512;
 constexpr int THREADS16 = WORKERS16 + 64;
@@ -1573,6 +560,7 @@ struct Smem16 {
   static constexpr bool kAddHalfHoisted = true;      // ... is precomputed per rollout (k_rollout_init) and added in the epilogue
   uint32_t tmem_base;
   int n_valid, kvi_slot;
+  unsigned peer_vm[2];  // halves mode: valid mask (lo, hi) of the peer CTA's 64 agents at this step
 };
 static_assert(sizeof(Smem16) + 1024 <= 232448, "shared memory budget (227 KB per CTA)");
 
@@ -1587,8 +575,14 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
   const float* __restrict__ packed = a.packed;
   const int A = dm.n_agent, K = dm.n_mode, S = dm.n_scene, B = S * K, Th = dm.n_step_hist, T = dm.n_step, Tg = dm.n_step_gt;
   const int nT_map = (dm.n_pl + 63) / 64, nT_tl = (dm.n_tl + 63) / 64;
-  const int rank = (int)cluster_ctarank(), n_cta = (int)cluster_nctarank();
-  const int b = blockIdx.x / n_cta, s = b / K;
+  // cluster: either the split of the agent->map attention over 1 / 2 / 4 CTAs (n_agent <= 64), or -- "halves", 64 < n_agent <= 128
+  // -- two CTAs that each own 64 agents of the scene-mode (rows 0..63 of every per-agent array belong to cluster rank 0)
+  const int crank = (int)cluster_ctarank(), n_cl = (int)cluster_nctarank();
+  const bool halves = A > MAXA;
+  const int rank = halves ? 0 : crank, n_cta = halves ? 1 : n_cl;  // rank / size of the attention split
+  const int a0 = halves ? crank * MAXA : 0;                        // first agent of this CTA
+  const int A_loc = min(MAXA, A - a0);
+  const int b = blockIdx.x / n_cl, s = b / K;
   const int tid = threadIdx.x, warp = uniform(tid >> 5), lane = tid & 31;
   const size_t BA = (size_t)B * A;
   const int nkey_map = uniform(in.n_key_map[s]);
@@ -1623,8 +617,8 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
   if (tid < 48) sm.f_yaw[tid] = __ldg(packed + tbw::pre_processing_input_pose_pe_agent_pe_yaw_freqs + tid);
   if (tid < MAXA) {
     const int ag = tid;
-    const bool live = ag < A;
-    const size_t ba = (size_t)b * A + (live ? ag : 0), sa = (size_t)s * A + (live ? ag : 0);
+    const bool live = a0 + ag < A;
+    const size_t ba = (size_t)b * A + (live ? a0 + ag : 0), sa = (size_t)s * A + (live ? a0 + ag : 0);
     sm.pose[ag] = live ? *reinterpret_cast<const float4*>(a.sv.agent_state + ba * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     sm.vel[ag] = live ? make_float2(a.sv.vel[ba * 2], a.sv.vel[ba * 2 + 1]) : make_float2(0.f, 0.f);
     sm.acc[ag] = live ? a.sv.acc[ba] : 0.f;
@@ -1644,8 +638,8 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
   for (int L = 0; L < 3; ++L) {
     const float4* src = reinterpret_cast<const float4*>(a.sv.hidden + ((size_t)L * BA + (size_t)b * A) * D);
     float4* dst = hid_t + (size_t)L * B * 32 * A;
-    for (int i = tid; i < A * 32; i += THREADS16) {
-      const int ag_ = i % A, c4 = i / A;
+    for (int i = tid; i < A_loc * 32; i += THREADS16) {
+      const int ag_ = a0 + i % A_loc, c4 = i / A_loc;
       dst[c4 * A + ag_] = src[ag_ * 32 + c4];
     }
   }
@@ -1662,6 +656,12 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
   cfg.kv_map = in.kv_map_tc + (size_t)s * nT_map * BLK;
   cfg.kv_map_layer_stride = (size_t)S * nT_map * BLK;
   cfg.kv_tl_layer_stride = (size_t)S * Th * nT_tl * BLK;
+  cfg.halves = halves;
+  cfg.crank = crank;
+  cfg.t = 0;
+  cfg.kvx = reinterpret_cast<const unsigned char*>(a.sv.kv_int) + (size_t)b * 2 * BLK;
+  cfg.kvx_layer_stride = (size_t)B * 2 * BLK;
+  cfg.xflag = a.sv.xch + (size_t)b * 16 + 6;
 
   if (warp == 17) {
     LoaderT<Smem16> ld(sm);
@@ -1669,6 +669,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
       const int tl_t = min(t - 1, Th - 1);
       cfg.nblk_tl = (uniform(in.n_key_tl[(size_t)s * Th + tl_t]) + 63) / 64;
       cfg.kv_tl = in.kv_tl_tc + ((size_t)s * Th + tl_t) * nT_tl * BLK;
+      cfg.t = t;
       enumerate_step(a, cfg, ld);
     }
   } else if (warp == 16) {
@@ -1677,6 +678,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
       const int tl_t = min(t - 1, Th - 1);
       cfg.nblk_tl = (uniform(in.n_key_tl[(size_t)s * Th + tl_t]) + 63) / 64;
       cfg.kv_tl = nullptr;
+      cfg.t = t;
       enumerate_step(a, cfg, is);
     }
   } else {
@@ -1686,9 +688,10 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
     const int ag = l & 63, upper = l >> 6;
     const int cq = 32 * part;             // operand columns of this thread
     const int ce = cq + 16 * upper;       // epilogue columns of this thread (16)
-    const bool live = ag < A;
+    const bool live = a0 + ag < A;
+    const int agg = live ? a0 + ag : 0;  // agent index inside the scene (global arrays, [..][A] scratch layouts)
     const bool writer = upper == 0 && live && rank == 0;
-    const size_t ba = (size_t)b * A + (live ? ag : 0), sa = (size_t)s * A + (live ? ag : 0);
+    const size_t ba = (size_t)b * A + agg, sa = (size_t)s * A + agg;
     const uint32_t tm = tm0 + ((uint32_t)(quad * 32) << 16);
     const int pair_id = 2 + quad * 2 + half;  // named barrier of the two warps (quad, 2 half) and (quad, 2 half + 1)
     uint32_t n_mma = 0, n_s = 0, n_o = 0, n_grant = 0, n_ln = 0, n_lp = 0, n_merge = 0;
@@ -1830,8 +833,37 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
       const unsigned vm_lo = __ballot_sync(0xffffffffu, sm.valid[lane] != 0);
       const unsigned vm_hi = __ballot_sync(0xffffffffu, sm.valid[lane + 32] != 0);
       const unsigned long long vmask = ((unsigned long long)vm_hi << 32) | vm_lo;
-      const int n_valid = __popc(vm_lo) + __popc(vm_hi);
-      if (tid == 0) {
+      int n_valid = __popc(vm_lo) + __popc(vm_hi);  // valid agents of the SCENE (decides the interaction bypass)
+      unsigned long long vmask_peer = 0ull;
+      if (halves) {
+        // exchange the valid masks of the two agent halves through global memory: [parity][rank] (lo, hi) + a step counter per rank
+        if (tid == 0) {
+          int* x = a.sv.xch + (size_t)b * 16;
+          volatile unsigned* vm = reinterpret_cast<volatile unsigned*>(x) + 4 * (t & 1);
+          vm[2 * crank] = vm_lo;
+          vm[2 * crank + 1] = vm_hi;
+          __threadfence();
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(x + 8 + crank), "r"(t) : "memory");
+          const long long t0 = clock64();
+          int got;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(x + 8 + (crank ^ 1)) : "memory");
+            if (got < t) {
+              __nanosleep(64);
+              tc::watchdog_check(t0);
+            }
+          } while (got < t);
+          const unsigned plo = vm[2 * (crank ^ 1)], phi = vm[2 * (crank ^ 1) + 1];
+          sm.peer_vm[0] = plo;
+          sm.peer_vm[1] = phi;
+          *reinterpret_cast<volatile int*>(&sm.n_valid) = n_valid + __popc(plo) + __popc(phi);
+          __threadfence_block();
+          mbar_arrive(&sm.cfg);
+        }
+        worker_sync16();
+        vmask_peer = ((unsigned long long)sm.peer_vm[1] << 32) | sm.peer_vm[0];
+        n_valid += __popc(sm.peer_vm[0]) + __popc(sm.peer_vm[1]);
+      } else if (tid == 0) {
         *reinterpret_cast<volatile int*>(&sm.n_valid) = n_valid;
         __threadfence_block();
         mbar_arrive(&sm.cfg);
@@ -1901,7 +933,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
       for (int Lx = 0; Lx < 9; ++Lx) {
         const int kind = Lx / 3;
         if (kind == 2 && bypass) break;
-        const int nkey = kind == 0 ? nkey_map : kind == 1 ? nkey_tl : (n_valid > 0 ? MAXA : 0);
+        const int nkey = kind == 0 ? nkey_map : kind == 1 ? nkey_tl : (n_valid > 0 ? (halves ? 2 * MAXA : MAXA) : 0);
         const int nblk = (nkey + 63) / 64;
         worker_sync16();
         dmark(100 + Lx * 10);
@@ -1918,12 +950,12 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
               load_x(v);
               if (upper == 0 && live) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x0_t[(cq / 4 + i) * A + ag] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                for (int i = 0; i < 8; ++i) x0_t[(cq / 4 + i) * A + agg] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
               }
             } else if (live) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float4 q = x0_t[(cq / 4 + i) * A + ag];
+                const float4 q = x0_t[(cq / 4 + i) * A + agg];
                 v[4 * i] = q.x, v[4 * i + 1] = q.y, v[4 * i + 2] = q.z, v[4 * i + 3] = q.w;
               }
             } else {
@@ -1942,10 +974,15 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
             dmark(510 + Lx);
             write_A(T_A, v);
             signal_ready();  // -> Wq (ACC2)
-            tc::mbar_wait(&sm.grant, n_grant & 1);
-            ++n_grant;
+            if (!halves) {
+              tc::mbar_wait(&sm.grant, n_grant & 1);
+              ++n_grant;
+            }
             {
-              unsigned char* blk = sm.ring[*reinterpret_cast<volatile int*>(&sm.kvi_slot)];
+              // the 64-key block of this CTA's agents: a ring slot granted by the loader, or (halves) global memory, from where both
+              // CTAs of the scene-mode stream it after the exchange
+              unsigned char* blk = halves ? const_cast<unsigned char*>(cfg.kvx) + (Lx - 6) * cfg.kvx_layer_stride + (size_t)crank * BLK
+                                          : sm.ring[*reinterpret_cast<volatile int*>(&sm.kvi_slot)];
               float kk[16];
               load_acc16(T_ACC0, kk);  // K[ag, ce .. ce+15]: key row ag
 #pragma unroll
@@ -1975,7 +1012,12 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
                   *reinterpret_cast<unsigned short*>(vt + 16384 + off) = (unsigned short)(e ? ll >> 16 : ll & 0xffffu);
                 }
               }
-              tc::fence_proxy_async();
+              if (halves) {
+                __threadfence();
+                asm volatile("fence.proxy.async;" ::: "memory");
+              } else {
+                tc::fence_proxy_async();
+              }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.wfill);
@@ -2031,7 +1073,9 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
             tc::tmem_ld32(sbase + 32 * sub, sv_);
             tc::tmem_ld_wait();
             if (kind == 2) {
-              const unsigned en = (unsigned)((vmask & ~(1ull << ag)) >> (32 * sub));
+              // keys = the agents of the scene (halves: block jb holds the 64 agents of cluster rank jb), without the query itself
+              const bool own = !halves || jb == crank;
+              const unsigned en = (unsigned)(((own ? vmask & ~(1ull << ag) : vmask_peer)) >> (32 * sub));
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (!((en >> j) & 1u)) sv_[j] = -INFINITY;
@@ -2269,7 +1313,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
       for (int L = 0; L < 3; ++L) {
         // h_{t-1} of this layer (written one step ago) is requested before the barrier: its L2 latency hides behind the barrier and
         // the x operand
-        float4* hid = hid_t + (size_t)L * B * 32 * A + ag;
+        float4* hid = hid_t + (size_t)L * B * 32 * A + agg;
         float4 hq[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) hq[i] = live ? hid[(cq / 4 + i) * A] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -2353,7 +1397,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
         // z half of mlp_out layer 0 (W[:, 128:256] relu(z), step-invariant, from k_rollout_init): requested before the barrier, added
         // in the epilogue where z is valid
         const bool zv = j == 0 ? (sm.goal_valid[ag] != 0) : valid;
-        const float4* zc = (j == 0 ? goal_c_t : latent_c_t) + (cq / 4) * A + ag;
+        const float4* zc = (j == 0 ? goal_c_t : latent_c_t) + (cq / 4) * A + agg;
         float4 zq[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) zq[i] = (live && zv) ? __ldg(zc + i * A) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -2399,7 +1443,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
       const bool tail_thread = upper == 0 && live;  // the four column-part threads of an agent share the tail (below)
       const bool out_w = rank == 0;
       const bool has_gt = t < Tg;
-      const size_t gidx = ((size_t)s * Tg + (has_gt ? t : 0)) * A + ag;
+      const size_t gidx = ((size_t)s * Tg + (has_gt ? t : 0)) * A + agg;
       float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
       float2 g_vel = make_float2(0.f, 0.f);
       float g_acc = 0.f, g_yr = 0.f;
@@ -2541,7 +1585,7 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
           bool pos_reached = false, rot_reached = false;
           const float k_dest_thresh = sm.tailc[8][ag];
           const float hx = cosf(ns.z), hy = sinf(ns.z);
-          const float4* dn = a.sv.dest_nodes + ((size_t)b * TB_PL_NODE + 10 * (part - 2)) * A + ag;
+          const float4* dn = a.sv.dest_nodes + ((size_t)b * TB_PL_NODE + 10 * (part - 2)) * A + agg;
           float4 nd[10];
 #pragma unroll
           for (int n = 0; n < 10; ++n) nd[n] = __ldg(dn + n * A);
@@ -2601,8 +1645,8 @@ __global__ void __launch_bounds__(THREADS16, 1) k_rollout_tc16(Args a) {
       for (int L = 0; L < 3; ++L) {
         float4* dst = reinterpret_cast<float4*>(a.sv.hidden + ((size_t)L * BA + (size_t)b * A) * D);
         const float4* src = hid_t + (size_t)L * B * 32 * A;
-        for (int i = tid; i < A * 32; i += WORKERS16) {
-          const int ag_ = i / 32, c4 = i % 32;
+        for (int i = tid; i < A_loc * 32; i += WORKERS16) {
+          const int ag_ = a0 + i / 32, c4 = i % 32;
           dst[ag_ * 32 + c4] = __ldcg(src + c4 * A + ag_);
         }
       }
@@ -2632,13 +1676,13 @@ using namespace tb;
 
 bool tb::rollout_tc_supported(const TbDims& d, const TbRolloutIn& in) {
   if (!in.kv_map_tc || !in.kv_tl_tc || !in.n_key_map || !in.n_key_tl) return false;
-  return d.n_agent <= pr::MAXA;
+  return d.n_agent <= 2 * pr::MAXA;
 }
 
 int tb::rollout_tc_cluster_size(const TbDims& d) {
   // One CTA per scene-mode leaves most of the 148 SMs idle for small batches; the agent->map attention (the largest part of
   // a step) is then split over a cluster of 2 or 4 CTAs per scene-mode.
-  if (d.n_agent > pr::MAXA) return 1;
+  if (d.n_agent > pr::MAXA) return 2;  // two CTAs per scene-mode, 64 agents each (the agent->map attention is not split)
   const char* env = getenv("TB_CLUSTER");  // development / test override
   const int forced = env ? atoi(env) : 0;
   if (forced == 1 || forced == 2 || forced == 4) return forced;
@@ -2649,26 +1693,18 @@ int tb::rollout_tc_cluster_size(const TbDims& d) {
 
 int tb::launch_rollout_tc(const TbDims& d, const TbRolloutIn& in, const float* packed, const StateView& sv, const TbRolloutOut& out,
                           int t_first, int t_last, cudaStream_t st) {
-  static std::atomic<uint64_t> attr_set{0};
-  const int smem = (int)sizeof(pr::Smem) + 1024;
-  if (!smem_attr_done(attr_set)) {
-    if (!set_max_smem(pr::k_rollout_tc, smem)) return TB_ERR_LAUNCH;
-    smem_attr_mark(attr_set);
-  }
   pr::Args a{d, in, packed, tc_blob(packed), sv, out, t_first, t_last, g_debug_trace};
   const int n_cta = rollout_tc_cluster_size(d);
-  const char* w8 = getenv("TB_ROLLOUT_8WARP");  // A/B: the 8-worker-warp kernel
-  const bool use16 = !(w8 && w8[0] == '1');
   static std::atomic<uint64_t> attr16_set{0};
   const int smem16 = (int)sizeof(pr::Smem16) + 1024;
-  if (use16 && !smem_attr_done(attr16_set)) {
+  if (!smem_attr_done(attr16_set)) {
     if (!set_max_smem(pr::k_rollout_tc16, smem16)) return TB_ERR_LAUNCH;
     smem_attr_mark(attr16_set);
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(d.n_scene * d.n_mode * n_cta);
-  cfg.blockDim = dim3(use16 ? pr::THREADS16 : pr::THREADS);
-  cfg.dynamicSmemBytes = use16 ? smem16 : smem;
+  cfg.blockDim = dim3(pr::THREADS16);
+  cfg.dynamicSmemBytes = smem16;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -2677,7 +1713,7 @@ int tb::launch_rollout_tc(const TbDims& d, const TbRolloutIn& in, const float* p
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if ((use16 ? cudaLaunchKernelEx(&cfg, pr::k_rollout_tc16, a) : cudaLaunchKernelEx(&cfg, pr::k_rollout_tc, a)) != cudaSuccess) return TB_ERR_LAUNCH;
+  if (cudaLaunchKernelEx(&cfg, pr::k_rollout_tc16, a) != cudaSuccess) return TB_ERR_LAUNCH;
   count_launch();
   return launch_status();
 }
