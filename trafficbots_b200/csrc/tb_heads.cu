@@ -202,10 +202,11 @@ __global__ void __launch_bounds__(NT) k_dest_pairs(const float* __restrict__ U, 
 }
 
 // masks + Categorical(logits=) normalisation, one warp per (scene, agent) row of P logits (goal_manager.py:328-333)
-__global__ void __launch_bounds__(NT) k_dest_finish(float* __restrict__ logits, const uint8_t* __restrict__ map_valid,
+// (`logits` and `logp` may be the same buffer: the raw logits are normalised in place)
+__global__ void __launch_bounds__(NT) k_dest_finish(float* logits, const uint8_t* __restrict__ map_valid,
                                                     const uint8_t* __restrict__ map_type, const uint8_t* __restrict__ agent_type,
                                                     const uint8_t* __restrict__ dist_valid, int S, int A, int P,
-                                                    float* __restrict__ logp, float* __restrict__ probs) {
+                                                    float* logp, float* __restrict__ probs) {
   const int row = blockIdx.x * NWARP + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= S * A) return;
   const int s = row / A;
@@ -307,7 +308,7 @@ extern "C" int32_t tb_mlp_head(int32_t which, const float* x, const uint8_t* val
 
 extern "C" size_t tb_dest_workspace_bytes(int32_t n_scene, int32_t n_agent, int32_t n_pl) {
   if (n_scene < 1 || n_agent < 1 || n_pl < 1) return 0;
-  return ((size_t)n_scene * n_pl * D + (size_t)n_scene * n_agent * D) * sizeof(float) + 512;
+  return ((size_t)n_scene * n_pl * D + (size_t)n_scene * n_agent * D) * sizeof(float) + 1024 + dest_lists_bytes(n_scene, n_pl);
 }
 
 extern "C" int32_t tb_dest_logits(int32_t n_scene, int32_t n_agent, int32_t n_pl, const float* map_feature,
@@ -329,7 +330,10 @@ extern "C" int32_t tb_dest_logits(int32_t n_scene, int32_t n_agent, int32_t n_pl
   k_row_linear<HR><<<(unsigned)((rows_v + HR - 1) / HR), NT, 0, st>>>(tgt, rows_v, w0, D, nullptr, V);
   count_launch();
   if (tc_enabled()) {  // pairwise MLP on the tensor pipe (tb_tc_xlayer.cu); raw logits staged in `logp`
-    const int rc = launch_dest_pairs_tc(U, V, n_scene, n_agent, n_pl, packed, logp, st);
+    int32_t* lists = reinterpret_cast<int32_t*>(
+        (reinterpret_cast<uintptr_t>(V + (((size_t)n_scene * n_agent * D + 63) & ~(size_t)63)) + 255) & ~(uintptr_t)255);
+    const int rc = launch_dest_pairs_tc(U, V, n_scene, n_agent, n_pl, packed, logp, map_feature_valid, map_type, agent_type, tgt_valid,
+                                        lists, st);
     if (rc != TB_OK) return rc;
   } else {
     static std::atomic<uint64_t> attr_set{0};

@@ -80,8 +80,10 @@ int launch_xlayer_tc(int block, int layer, const float* src, const uint8_t* src_
 int launch_kv_project_tc(int block, int layer, const float* tgt, long n_row, const float* packed, float* kv, cudaStream_t st);
 int launch_gru_seq_tc(int which, int mode, const float* x, const uint8_t* valid, int n_batch, int n_frame, int n_agent, int t_stride,
                       const float* packed, int gru_base_offset, void* workspace, float* out, uint8_t* out_valid, cudaStream_t st);
+size_t dest_lists_bytes(int n_scene, int n_pl);  // admissible-polyline lists per (scene, agent class) + counts
 int launch_dest_pairs_tc(const float* U, const float* V, int n_scene, int n_agent, int n_pl, const float* packed, float* logits,
-                         cudaStream_t st);
+                         const uint8_t* map_valid, const uint8_t* map_type, const uint8_t* agent_type, const uint8_t* agent_valid,
+                         int32_t* lists_ws, cudaStream_t st);
 
 // tensor-core polyline encoder: 4 threads per node row, compacted tiles (tb_tc_polyline.cu)
 // plan_ws: map_plan_bytes(n_scene * n_pl) bytes = [live_pl | row_start (+1) | plan] int32 (compacted-tile plan, k_map_plan)

@@ -487,9 +487,53 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
 
+// Admissible destinations: the reference masks every (agent, polyline) pair whose polyline is invalid / not a lane or road edge
+// (types 0-4) or does not fit the agent type (goal_manager.py:233-244,328-330) to -inf AFTER evaluating the pairwise MLP on all
+// of them; ~80 % of the pairs are masked.  k_dest_lists compacts, per scene and agent class (0 vehicle, 1 pedestrian, 2 cyclist,
+// 3 no type bit), the indices of the admissible polylines; the pair kernel only evaluates those (k_dest_finish never reads a
+// masked logit), and skips agents without a valid history altogether (their row becomes uniform, :331).
+__global__ void __launch_bounds__(256) k_dest_lists(int P, const uint8_t* __restrict__ map_valid, const uint8_t* __restrict__ map_type,
+                                                    int32_t* __restrict__ lists, int32_t* __restrict__ counts) {
+  const int s = blockIdx.x, c = blockIdx.y;
+  __shared__ int wsum[8];
+  __shared__ int base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int32_t* out = lists + ((size_t)s * 4 + c) * P;
+  for (int p0 = 0; p0 < P; p0 += 256) {
+    const int p = p0 + threadIdx.x;
+    bool ok = false;
+    if (p < P && map_valid[(size_t)s * P + p]) {
+      const uint8_t* mt = map_type + ((size_t)s * P + p) * TB_PL_TYPE;
+      const bool t012 = mt[0] | mt[1] | mt[2], t3 = mt[3], t4 = mt[4];
+      // type_mask keeps types 0-4; vehicles exclude type 3, pedestrians 0-3, cyclists 0-2 (the masks combine as written in the
+      // reference even if a polyline had several type bits set)
+      const bool any = t012 || t3 || t4;
+      ok = c == 0 ? (any && !t3) : c == 1 ? (t4 && !t012 && !t3) : c == 2 ? ((t3 || t4) && !t012) : any;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) wsum[w] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int k = 0; k < w; ++k) off += wsum[k];
+    if (ok) out[off + __popc(bal & ((1u << lane) - 1u))] = p;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int k = 0; k < 8; ++k) t += wsum[k];
+      base += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counts[s * 4 + c] = base;
+}
+
 __global__ void __launch_bounds__(THREADS, 2) k_dest_pairs_tc(const float* __restrict__ U, const float* __restrict__ V, int P, int A,
                                                               int n_sa, const float* __restrict__ packed,
-                                                              const unsigned char* __restrict__ w3_block, float* __restrict__ logits) {
+                                                              const unsigned char* __restrict__ w3_block, float* __restrict__ logits,
+                                                              const int32_t* __restrict__ lists, const int32_t* __restrict__ counts,
+                                                              const uint8_t* __restrict__ agent_type, const uint8_t* __restrict__ agent_valid) {
   extern __shared__ unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tc::uniform(tid >> 5), lane = tid & 31;
@@ -508,6 +552,16 @@ __global__ void __launch_bounds__(THREADS, 2) k_dest_pairs_tc(const float* __res
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tm0 = (uint32_t)tc::uniform((int)sm.tmem_base);
+  // tile = (scene-agent sa, j-th block of 128 admissible polylines of its class); both roles skip the same dead tiles
+  auto agent_class = [&](int sa) {
+    const uint8_t* at = agent_type + (size_t)sa * 3;
+    return at[0] ? 0 : at[1] ? 1 : at[2] ? 2 : 3;
+  };
+  auto tile_live = [&](int tile) {
+    const int sa = tile / tiles_per_sa, j = tile % tiles_per_sa;
+    if (!agent_valid[sa]) return false;
+    return j * 128 < counts[(sa / A) * 4 + agent_class(sa)];
+  };
 
   if (warp == 8) {
     tc::mbar_wait(&sm.bar_w, 0);
@@ -516,6 +570,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_dest_pairs_tc(const float* __res
     const uint32_t idesc = tc::make_idesc_bf16(128, 128);
     uint32_t n_ready = 0;
     for (int tile = blockIdx.x; tile < n_tile; tile += gridDim.x) {
+      if (!tile_live(tile)) continue;
       tc::mbar_wait(&sm.bar_ready, n_ready & 1);
       ++n_ready;
       tc::tc_fence_after();
@@ -569,10 +624,11 @@ __global__ void __launch_bounds__(THREADS, 2) k_dest_pairs_tc(const float* __res
       rstd = 1.0f / sqrtf((m2 + om + dm * dm * 32.0f) * (1.0f / 128) + LN_EPS);
     };
     for (int tile = blockIdx.x; tile < n_tile; tile += gridDim.x) {
-      const int sa = tile / tiles_per_sa, p0 = (tile % tiles_per_sa) * 128;
-      const int s = sa / A;
-      const int p = p0 + r;
-      const bool live = p < P;
+      if (!tile_live(tile)) continue;
+      const int sa = tile / tiles_per_sa, j0 = (tile % tiles_per_sa) * 128;
+      const int s = sa / A, cls = agent_class(sa);
+      const bool live = j0 + r < counts[s * 4 + cls];
+      const int p = live ? lists[((size_t)s * 4 + cls) * P + j0 + r] : 0;
       float v[64];
       {
         const float4* u4 = reinterpret_cast<const float4*>(U + ((size_t)s * P + (live ? p : 0)) * D + c0);
@@ -625,8 +681,11 @@ __global__ void __launch_bounds__(THREADS, 2) k_dest_pairs_tc(const float* __res
 }  // namespace dp
 }  // namespace tb
 
+size_t tb::dest_lists_bytes(int n_scene, int n_pl) { return (((size_t)n_scene * 4 * n_pl + (size_t)n_scene * 4) * sizeof(int32_t) + 255) & ~(size_t)255; }
+
 int tb::launch_dest_pairs_tc(const float* U, const float* V, int n_scene, int n_agent, int n_pl, const float* packed, float* logits,
-                             cudaStream_t st) {
+                             const uint8_t* map_valid, const uint8_t* map_type, const uint8_t* agent_type, const uint8_t* agent_valid,
+                             int32_t* lists_ws, cudaStream_t st) {
   static std::atomic<uint64_t> attr_set{0};
   const int smem = (int)sizeof(dp::Smem) + 1024;
   if (!smem_attr_done(attr_set)) {
@@ -636,9 +695,13 @@ int tb::launch_dest_pairs_tc(const float* U, const float* V, int n_scene, int n_
   const int n_sa = n_scene * n_agent;
   const long n_tile = (long)n_sa * ((n_pl + 127) / 128);
   const int grid = (int)(n_tile < 2 * 148 ? n_tile : 2 * 148);  // 2 CTAs per SM (66 KB shared memory, 256 TMEM columns each)
+  int32_t* counts = lists_ws + (size_t)n_scene * 4 * n_pl;
+  dp::k_dest_lists<<<dim3(n_scene, 4), 256, 0, st>>>(n_pl, map_valid, map_type, lists_ws, counts);
+  count_launch();
   dp::k_dest_pairs_tc<<<grid, dp::THREADS, smem, st>>>(
       U, V, n_pl, n_agent, n_sa, packed,
-      tc_blob(packed) + (size_t)tbb::model_goal_manager_goal_predictor_mlp_fc_layers_3_weight * tc::BLOCK_BYTES, logits);
+      tc_blob(packed) + (size_t)tbb::model_goal_manager_goal_predictor_mlp_fc_layers_3_weight * tc::BLOCK_BYTES, logits, lists_ws, counts,
+      agent_type, agent_valid);
   count_launch();
   return launch_status();
 }
