@@ -148,3 +148,43 @@ def test_scene_stager_round_trip():
     cb2 = st.get()
     torch.cuda.synchronize()
     assert torch.equal(cb2["a"].cpu(), batch["a"]) and torch.equal(cb2["b"].cpu(), batch["b"])
+
+
+def test_sampled_modes_through_the_public_surface_match_reference():
+    """All K modes -- not only the deterministic mode 0 -- of `joint_future_pred` on the public surface against the reference's
+    golden rollout: the CUDA generator cannot reproduce the reference's CPU draws, so the prior / destination objects handed to
+    `joint_future_pred` return the reference's own samples (`jfp/latent_sample`, `jfp/goal_sample` of the fixture) from
+    `.sample()`; everything downstream (log-probs, K-mode replication sharing the scene's key blocks, rollout, buffers) is the
+    product path."""
+    from golden_util import load_case
+    from trafficbots_b200.models.distributions import DestCategorical, DiagGaussian
+    gold, sd, batch, meta = load_case("s3_a8_p64_k2")
+    K, S = meta["K"], meta["S"]
+    A = batch["agent/type"].shape[1]
+    m = _module(sd, K)
+    cb = {k: v.cuda() for k, v in batch.items()}
+    feat = m.model.encode_input_features(cb)
+    latent, goal = _heads(sd, batch)
+
+    class FixedLatent(DiagGaussian):
+        def sample(self, deterministic):
+            return gold["jfp/latent_sample"].cuda()  # [S*K, A, 16], scene-major like the reference's repeat_interleave
+
+    class FixedGoal(DestCategorical):
+        def sample(self, deterministic):
+            return gold["jfp/goal_sample"].transpose(1, 2).reshape(S * K, A).cuda()  # fixture layout [S, A, K]
+
+    latent.__class__, goal.__class__ = FixedLatent, FixedGoal
+    goal_valid = cb["history/agent/valid"].any(1)
+    buf, goal_sample, goal_logp = m.joint_future_pred(cb, feat, latent, goal, goal_valid, require_vis_dict=False)
+    assert torch.equal(goal_sample.cpu(), gold["jfp/goal_sample"])
+    assert float((goal_logp.cpu() - gold["jfp/goal_log_probs"]).abs().max()) <= 1e-4
+    for k in range(K):  # every mode, sampled ones included
+        assert torch.equal(buf.valid[:, :, k].cpu(), gold["jfp/valid"][:, :, k]), k
+        assert torch.equal(buf.override_masks[:, :, k].cpu(), gold["jfp/override_masks"][:, :, k]), k
+        assert float((buf.preds[:, :, k].cpu() - gold["jfp/preds"][:, :, k]).abs().max()) <= 2e-3, k  # closed-loop tolerance
+        assert float((buf.latent_log_probs[:, :, k].cpu() - gold["jfp/latent_log_probs"][:, :, k]).abs().max()) <= 1e-3, k
+        for name in ("outside_map", "goal_reached", "dest_reached"):
+            assert torch.equal(buf.violations[name][:, :, k].cpu(), gold[f"jfp/violations/{name}"][:, :, k]), (name, k)
+    # the sampled mode really differs from the deterministic one
+    assert float((buf.preds[:, :, 1] - buf.preds[:, :, 0]).abs().max()) > 1e-2
