@@ -558,7 +558,9 @@ __global__ void __launch_bounds__(THREADS, 2) k_dest_pairs_tc(const float* __res
     return at[0] ? 0 : at[1] ? 1 : at[2] ? 2 : 3;
   };
   auto tile_live = [&](int tile) {
-    const int sa = tile / tiles_per_sa, j = tile % tiles_per_sa;
+    // block-major tile order (tile = j * n_sa + sa): with the agent-major order a CTA striding by gridDim.x = 8 x 37 would
+    // always get the same block index j, i.e. either only live or only dead tiles
+    const int sa = tile % n_sa, j = tile / n_sa;
     if (!agent_valid[sa]) return false;
     return j * 128 < counts[(sa / A) * 4 + agent_class(sa)];
   };
@@ -625,7 +627,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_dest_pairs_tc(const float* __res
     };
     for (int tile = blockIdx.x; tile < n_tile; tile += gridDim.x) {
       if (!tile_live(tile)) continue;
-      const int sa = tile / tiles_per_sa, j0 = (tile % tiles_per_sa) * 128;
+      const int sa = tile % n_sa, j0 = (tile / n_sa) * 128;
       const int s = sa / A, cls = agent_class(sa);
       const bool live = j0 + r < counts[s * 4 + cls];
       const int p = live ? lists[((size_t)s * 4 + cls) * P + j0 + r] : 0;
