@@ -97,7 +97,8 @@ def test_reference_validation_step_body_drives_the_library(case):
     assert torch.equal(kw["dest_reached"][:, :, 0].cpu(), gold["jfp/violations/dest_reached"][:, :, 0])
     args, kw = m2.sub_womd_joint_future_pred.last
     assert torch.equal(kw["waymo_trajs"], mine["pred_dict_joint_future_pred"]["waymo_trajs"])
-    assert torch.equal(m2.womd_metrics_joint_future_pred.records[0], mine["womd_records_joint_future_pred"])
+    assert torch.equal(m2.womd_metrics_joint_future_pred.ops_inputs_cpu[0], mine["womd_records_joint_future_pred"].cpu())
+    assert m2.womd_metrics_joint_future_pred.records == []  # the reference's loop reset the per-step device state
     assert m2.train_metrics_reactive_replay.n_call == 1
 
 

@@ -30,7 +30,8 @@ class WOMDMetrics:
         self.prefix, self.step_gt, self.step_current = prefix, step_gt, step_current
         self.track_future_samples = step_gt - step_current
         self.m_joint, self.n_pred = 8, 1
-        self.records: List[Tensor] = []  # one uint8 [n_scene, record_bytes] buffer per update()
+        self.records: List[Tensor] = []  # device: one uint8 [n_scene, record_bytes] buffer per update() since the last reset()
+        self.ops_inputs_cpu: List[Tensor] = []  # host: what aggregate_on_cpu() collected over the epoch
         self._shape = None  # (n_agent, K)
         self.overflow: Optional[Tensor] = None
         self._comm: Optional[torch.cuda.Stream] = None
@@ -126,22 +127,33 @@ class WOMDMetrics:
         if self._comm is not None:
             torch.cuda.current_stream().wait_stream(self._comm)
 
-    def aggregate_on_cpu(self, records: Tensor) -> None:
-        """reference womd.py:165-175 copies the six gathered tensors to the host after every step; here the packed records
-        stay on the device (`self.records`) until `compute()` -- nothing to do per step."""
+    def aggregate_on_cpu(self, records: Optional[Tensor] = None) -> None:
+        """reference womd.py:165-175: after every step the (rank-synchronised, `dist_sync_on_step=True`) states are moved to
+        the host and kept there until the end of the epoch.  Here: ONE all-gather of the packed records (if distributed), one
+        device -> host copy; the device buffer can then be dropped with `reset()` like in the reference's loop
+        (waymo_motion.py:655-660), so an epoch does not accumulate device memory."""
+        if records is None:
+            if not self.records:
+                return
+            records = self.records[-1]
+        if records.is_cuda:
+            records = self.gather(records, side_stream=False)
+        self.ops_inputs_cpu.append(records.cpu())
 
     def compute(self) -> Dict[str, List[Tensor]]:
         """the motion-metrics op inputs, as the reference's `compute()` returns them (:153-163): one entry per update()."""
         A, K = self._shape
         out: Dict[str, List[Tensor]] = {k: [] for k in STATES}
-        for rec in self.records:
+        for rec in (self.records if self.records else self.ops_inputs_cpu):
             for k, v in self.views(rec, A, K).items():
                 out[k].append(v)
         return out
 
     def reset(self) -> None:
-        """the reference resets its per-step torchmetrics states after `aggregate_on_cpu` (waymo_motion.py:659-660); the records
-        of the epoch are kept until `clear()`."""
+        """drops the per-step device records (the reference resets its torchmetrics states after `aggregate_on_cpu`,
+        waymo_motion.py:659-660); what was aggregated on the host stays until `clear()`."""
+        self.records = []
 
     def clear(self) -> None:
         self.records = []
+        self.ops_inputs_cpu = []

@@ -414,6 +414,8 @@ class WaymoMotion(_Base):
         pred_dict = self.waymo_post_processing(valid=buf.valid[:, :, 0].any(-1), scores=torch.ones_like(buf.preds[:, :, :, 0, 0]),
                                                trajs=buf.preds[:, :, :, buf.step_future_start:], agent_type=batch["ref/agent_type"])
         out["womd_records_reactive_replay"] = self.womd_metrics_reactive_replay.update(batch, pred_dict["waymo_trajs"], pred_dict["waymo_scores"])
+        self.womd_metrics_reactive_replay.aggregate_on_cpu(out["womd_records_reactive_replay"])  # like :655-660
+        self.womd_metrics_reactive_replay.reset()
         out["reactive_replay"], out["pred_dict_reactive_replay"] = buf, pred_dict
 
         # ! joint_future_pred (:683-722)
@@ -429,6 +431,8 @@ class WaymoMotion(_Base):
                                                trajs=buf.preds[:, :, :, buf.step_future_start:], agent_type=batch["ref/agent_type"])
         out["womd_records_joint_future_pred"] = self.womd_metrics_joint_future_pred.update(batch, pred_dict["waymo_trajs"],
                                                                                            pred_dict["waymo_scores"])
+        self.womd_metrics_joint_future_pred.aggregate_on_cpu(out["womd_records_joint_future_pred"])
+        self.womd_metrics_joint_future_pred.reset()
         self._emit("sub_womd_joint_future_pred", waymo_trajs=pred_dict["waymo_trajs"], waymo_scores=pred_dict["waymo_scores"],
                    mask_pred=batch["history/agent/role"][..., 2] if "history/agent/role" in batch else None)
         out["joint_future_pred"], out["pred_dict_joint_future_pred"] = buf, pred_dict
