@@ -181,6 +181,10 @@ __global__ void __launch_bounds__(NT) k_rule_step(TbDims dm, TbRuleIn in, TbRule
     for (int idx = tid; idx < A * A; idx += NT) {
       const int i = idx / A, j = idx - i * A;
       if (i == j || !sm.valid[i] || !sm.valid[j] || (sm.ped[i] && sm.ped[j])) continue;  // never collide: handled below
+      {  // boxes whose circumscribed circles are apart are separated by one of their edge lines (SAT): skipped here and below
+        const float dx = sm.x[i] - sm.x[j], dy = sm.y[i] - sm.y[j], reach = sm.cull[i] + sm.cull[j];
+        if (dx * dx + dy * dy > reach * reach) continue;
+      }
       bool sepd = false;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -276,6 +280,12 @@ __global__ void __launch_bounds__(NT) k_rule_step(TbDims dm, TbRuleIn in, TbRule
     for (int idx = tid; idx < A * A; idx += NT) {
       const int i = idx / A, j = idx - i * A;
       if (i == j || !sm.pvalid[i] || !sm.pvalid[j]) continue;
+      {  // every circle centre lies within 2 d of its agent's centre: if the agents are further apart than that plus the radii,
+         // all 25 distances exceed r_i + r_j and the relaxed overlap clamps to exactly 0
+        const float dx = sm.px[i] - sm.px[j], dy = sm.py[i] - sm.py[j];
+        const float reach = 2.f * (sm.pd[i] + sm.pd[j]) + sm.pr[i] + sm.pr[j] + 1e-2f;
+        if (dx * dx + dy * dy > reach * reach) continue;
+      }
       float dmin = 3.0e38f;
 #pragma unroll
       for (int p = 0; p < 5; ++p) {
@@ -305,6 +315,8 @@ __global__ void __launch_bounds__(NT) k_rule_step(TbDims dm, TbRuleIn in, TbRule
     if ((en & 1) && sm.valid[a]) {
       for (int j = 0; j < A; ++j) {
         if (j == a || !sm.valid[j] || (sm.ped[a] && sm.ped[j])) continue;
+        const float dx = sm.x[a] - sm.x[j], dy = sm.y[a] - sm.y[j], reach = sm.cull[a] + sm.cull[j];
+        if (dx * dx + dy * dy > reach * reach) continue;  // far apart: separated (same test as in the pair loop)
         const bool sepd = ((sm.sep[a][j >> 5] >> (j & 31)) & 1u) || ((sm.sep[j][a >> 5] >> (a & 31)) & 1u);
         collided |= !sepd;
       }

@@ -385,24 +385,31 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
 #pragma unroll
         for (int i = 0; i < 32; ++i) t[i] += lp[P_BQ][c0 + i];
         float mx = -INFINITY;
+        // keys in chunks of 4: one warp-uniform test per chunk (the longest polyline of the warp), the 4 keys of a chunk fully
+        // unrolled so that their shared-memory loads overlap
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-          if (j >= kmax) {
-            pj[j] = -INFINITY;
+        for (int j0 = 0; j0 < N; j0 += 4) {
+          if (j0 >= kmax) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pj[j0 + e] = -INFINITY;
             continue;
           }
-          const float* kr = sm.kv + (ks + (j < kc ? j : 0)) * KVS + c0;
-          float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-            const float4 k4 = reinterpret_cast<const float4*>(kr)[i], k5 = reinterpret_cast<const float4*>(kr)[i + 1];
-            tc::fma2(a0, a1, t[4 * i], t[4 * i + 4], k4.x, k5.x, a0, a1);  // two independent chains, one packed FMA per step
-            tc::fma2(a0, a1, t[4 * i + 1], t[4 * i + 5], k4.y, k5.y, a0, a1);
-            tc::fma2(a0, a1, t[4 * i + 2], t[4 * i + 6], k4.z, k5.z, a0, a1);
-            tc::fma2(a0, a1, t[4 * i + 3], t[4 * i + 7], k4.w, k5.w, a0, a1);
+          for (int e = 0; e < 4; ++e) {
+            const int j = j0 + e;
+            const float* kr = sm.kv + (ks + (j < kc ? j : 0)) * KVS + c0;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              const float4 k4 = reinterpret_cast<const float4*>(kr)[i], k5 = reinterpret_cast<const float4*>(kr)[i + 1];
+              tc::fma2(a0, a1, t[4 * i], t[4 * i + 4], k4.x, k5.x, a0, a1);  // two independent chains, one packed FMA per step
+              tc::fma2(a0, a1, t[4 * i + 1], t[4 * i + 5], k4.y, k5.y, a0, a1);
+              tc::fma2(a0, a1, t[4 * i + 2], t[4 * i + 6], k4.z, k5.z, a0, a1);
+              tc::fma2(a0, a1, t[4 * i + 3], t[4 * i + 7], k4.w, k5.w, a0, a1);
+            }
+            pj[j] = j < kc ? (a0 + a1) * 0.17677669529663687f : -INFINITY;
+            mx = fmaxf(mx, pj[j]);
           }
-          pj[j] = j < kc ? (a0 + a1) * 0.17677669529663687f : -INFINITY;
-          mx = fmaxf(mx, pj[j]);
         }
         if (mx != -INFINITY) {
           float sum = 0.f;
@@ -431,14 +438,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
       for (int i = 0; i < 32; ++i) t[i] = 0.f;
       if (live) {
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-          if (j >= kmax) continue;
-          const float* vr = sm.kv + (ks + (j < kc ? j : 0)) * KVS + c0;  // pj[j] = 0 for j >= kc
+        for (int j0 = 0; j0 < N; j0 += 4) {
+          if (j0 >= kmax) continue;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 v4 = reinterpret_cast<const float4*>(vr)[i];
-            tc::fma2(t[4 * i], t[4 * i + 1], pj[j], pj[j], v4.x, v4.y, t[4 * i], t[4 * i + 1]);
-            tc::fma2(t[4 * i + 2], t[4 * i + 3], pj[j], pj[j], v4.z, v4.w, t[4 * i + 2], t[4 * i + 3]);
+          for (int e = 0; e < 4; ++e) {
+            const int j = j0 + e;
+            const float* vr = sm.kv + (ks + (j < kc ? j : 0)) * KVS + c0;  // pj[j] = 0 for j >= kc
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 v4 = reinterpret_cast<const float4*>(vr)[i];
+              tc::fma2(t[4 * i], t[4 * i + 1], pj[j], pj[j], v4.x, v4.y, t[4 * i], t[4 * i + 1]);
+              tc::fma2(t[4 * i + 2], t[4 * i + 3], pj[j], pj[j], v4.z, v4.w, t[4 * i + 2], t[4 * i + 3]);
+            }
           }
         }
 #pragma unroll
