@@ -38,7 +38,7 @@ def _run(pipe, batches):
     return res
 
 
-@pytest.mark.parametrize("shape", [(3, 16, 128), (2, 64, 256)])
+@pytest.mark.parametrize("shape", [(3, 16, 128), (2, 64, 256), (2, 96, 192)])  # the last: two-CTA agent-halves decode mode
 def test_in_flight_equals_sequential_bit_for_bit(shape):
     from trafficbots_b200.pipeline import ScenePipeline
     S, A, P = shape

@@ -440,29 +440,6 @@ class Engine:
                                               self._state.data_ptr(), nt.current_stream_ptr()), "tb_rollout_init")
         self.last_t = 0
 
-    def profile_rollout(self, *args, n_mode: int = 1, n_step: int = 90, out=None, repeats: int = 3, **kw):
-        """Times the decode loop alone (`tb_rollout_steps(1..n_step)`: ONE launch of the persistent tensor-core kernel when
-        n_agent <= 64) with CUDA events on the launching stream; `tb_rollout_init` runs outside the timed region.
-        Returns the average ms per call.  Measurement aid for bench.py."""
-        dims, rin = self._rollout_structs(*args, n_mode, n_step, **kw)
-        B, A = dims.n_scene * dims.n_mode, dims.n_agent
-        if out is None:
-            out = self.alloc_outputs(B, A, n_step)
-        state = self._ensure_state(dims)
-        rout = self._out_struct(out)
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(repeats)]
-        with torch.cuda.device(self.device):
-            st = nt.current_stream_ptr()
-            for e0, e1 in ev:
-                nt.check(self.lib.tb_rollout_init(C.byref(dims), C.byref(rin), self.packed.data_ptr(), state.data_ptr(), st), "init")
-                e0.record()
-                nt.check(self.lib.tb_rollout_steps(C.byref(dims), C.byref(rin), self.packed.data_ptr(), state.data_ptr(),
-                                                   C.byref(rout), 1, n_step, st), "steps")
-                e1.record()
-            torch.cuda.current_stream().synchronize()
-        self.last_t = n_step
-        return sum(e0.elapsed_time(e1) for e0, e1 in ev) / repeats
-
     def _finish(self, out: Dict[str, Tensor]) -> Dict[str, Tensor]:
         res = {k: v for k, v in out.items() if not k.startswith("_")}
         for i, k in enumerate(VIOLATION_KEYS):
