@@ -170,6 +170,13 @@ def run_step_public(module, cb, ex=None):
     return buf
 
 
+def workload_string(cfg):
+    """the same text in both arms' `config.workload` (the arms differ in `schedule` / `sample`, not in the workload)."""
+    return (f"{cfg['name']}; per step and GPU: {cfg['n_scene']} scenes x K = {cfg['n_mode']}, {cfg['n_agent']} agents, {cfg['n_pl']} map "
+            f"polylines, 40 TL: encode_scene + prior latent encoder + destination predictor + {cfg['n_step']}-step closed-loop rollout "
+            "(with K = 1 the mode is the deterministic one)")
+
+
 # ----------------------------------------------------------------------------------------------------------
 def cpu_reference_rate(cfg, n_scene, repeats=1, seed=1234):
     """the oracle port of the reference's CPU path (encode_scene + latent prior + destination predictor + K rollouts as the
@@ -215,9 +222,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{cfg['name']}; {sample}; encode + prior latent + destination predictor + K x {cfg['n_step']}-step "
-                               "closed-loop rollout, reference CPU algorithm (oracle port, pinned to the unmodified reference)",
-                   "baseline_config": args.config, "scenes_per_step": n},
+        "config": {"workload": workload_string(cfg), "baseline_config": args.config, "scenes_per_step": n,
+                   "sample": f"{sample}; reference CPU algorithm (oracle port, pinned to the unmodified reference), {cores} threads"},
         "cpu_baseline": {"value": value, "unit": "scenes/s", "cores": cores, "kind": "port",
                          "sample": f"{n} scenes x {args.steps} steps, torch {torch.__version__} CPU fp32, {cores} threads"},
         "e2e": {"value": value, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -506,10 +512,8 @@ def run_ours(args):
             "metric": METRIC, "value": world * S * steps / (ms * 1e-3), "unit": "scenes/s", "n_gpus": world,
             "steps": steps, "warmup": max(warmup, depth), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (bf16x3 split operands on tcgen05, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": f"{cfg['name']}; per step and GPU: {S} scenes x K = {K}, {A} agents, {P} map polylines, 40 TL: encode_scene + "
-                                   f"prior latent encoder + destination predictor + {T}-step closed-loop rollout (with K = 1 the mode is the "
-                                   "deterministic one)",
-                       "baseline_config": args.config, "in_flight_depth": depth, "scene_modes_per_step": B,
+            "config": {"workload": workload_string(cfg), "baseline_config": args.config, "scenes_per_step": S,
+                       "in_flight_depth": depth, "scene_modes_per_step": B,
                        "schedule": f"{depth} batches in flight on {depth} CUDA streams (ScenePipeline), each with its own engine state; decode "
                                    f"kernel with {pipe.rollout_cluster or 'library-chosen'} CTA(s) per scene-mode; K timed steps = K batches "
                                    "submitted round robin, timed from the first submission to the last completion",

@@ -93,6 +93,8 @@ class ScenePipeline:
         # the module's own parameter check (re-pack if they changed) runs on the caller's stream, before the slot is entered
         self.module.use_engine(None)
         self.module.engine()
+        # work the caller queued on its own stream (e.g. producing a device-resident batch) is ordered before the slot's
+        slot.stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(slot.stream):
             slot.start.record(slot.stream)
             for k, v in host_batch.items():
@@ -135,6 +137,8 @@ class ScenePipeline:
         slot.done.synchronize()
         slot.busy = False
         self.latencies.append(slot.start.elapsed_time(slot.done))
+        if len(self.latencies) > 4096:
+            del self.latencies[:2048]
         return slot.host_out if self.read_back else slot.keep
 
     def slot_of(self, ticket: int) -> _Slot:
