@@ -1,0 +1,281 @@
+"""Reverse-mode tape over the training primitives of `csrc/tb_train.cu`.
+
+The reference trains through `torch.autograd` (Lightning backward of `training_step`, pl_modules/waymo_motion.py:356-418).
+Here every differentiable operation is one of ~20 hand-written CUDA primitives (forward kernel + hand-derived backward
+kernel, bound in `cuda_ops.CudaOps`); this module only records which primitive produced which buffer and replays the
+backward kernels in reverse order.  torch tensors are used as device memory; no torch autograd is involved.
+
+`Var` = a 2-D fp32 buffer [rows, cols] (+ its gradient buffer).  `Fn` = the recording front end used by `graph.py`.
+The primitive back end (`ops`) is injected: `CudaOps` in the product (the default; raises without the CUDA library),
+a torch restatement in the tests (`oracle/train_ops_oracle.py`), which is how the composition is validated on CPU against
+gradients of the unmodified reference.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import torch
+from torch import Tensor
+
+
+class Var:
+    __slots__ = ("data", "grad", "req", "grad_fixed", "grad_shared")
+
+    def __init__(self, data: Tensor, req: bool = False, grad: Optional[Tensor] = None) -> None:
+        self.data = data
+        self.req = req  # a gradient is wanted for this buffer
+        self.grad = grad
+        self.grad_fixed = grad is not None  # grad is a view into a parent / flat parameter buffer: accumulate in place only
+        self.grad_shared = False  # grad tensor may be referenced by another Var: never modify it in place
+
+    @property
+    def rows(self) -> int:
+        return self.data.shape[0]
+
+    @property
+    def cols(self) -> int:
+        return self.data.shape[1]
+
+    def detach(self) -> "Var":
+        return Var(self.data, False)
+
+
+class Fn:
+    """records primitives on a tape; `backward()` replays the backward kernels in reverse."""
+
+    def __init__(self, ops) -> None:
+        self.ops = ops
+        self.nodes: List[Callable[[], None]] = []
+        self.n_fwd = 0
+
+    # ------------------------------------------------------------------ tape mechanics
+    def _acc(self, v: Var, g: Optional[Tensor], owned: bool = True) -> None:
+        if g is None or not v.req:
+            return
+        if v.grad is None:
+            v.grad = g
+            v.grad_shared = not owned
+        elif v.grad_fixed:
+            self.ops.add_(v.grad, g)
+        elif v.grad_shared:
+            v.grad = self.ops.add_mask_fwd(v.grad, g, None)
+            v.grad_shared = False
+        else:
+            self.ops.add_(v.grad, g)
+
+    def _push(self, out: Var, fn: Callable[[Tensor], None]) -> None:
+        def node() -> None:
+            g = out.grad
+            if g is None:
+                return
+            fn(g)
+            if not out.grad_fixed:
+                out.grad = None  # the gradient of an intermediate buffer is dead once its producer has consumed it
+        self.nodes.append(node)
+
+    def backward(self) -> None:
+        nodes, self.nodes = self.nodes, []
+        while nodes:
+            nodes.pop()()
+
+    def const(self, t: Tensor) -> Var:
+        return Var(t, False)
+
+    def row_slice(self, v: Var, lo: int, hi: int) -> Var:
+        """rows [lo, hi) of a buffer as a Var of its own; the gradient is accumulated into the parent's (zero-initialised)."""
+        if not v.req:
+            return Var(v.data[lo:hi], False)
+        if v.grad is None:
+            v.grad = self.ops.zeros(tuple(v.data.shape), v.data)
+            v.grad_shared = False
+        elif v.grad_shared:
+            v.grad = self.ops.add_mask_fwd(v.grad, None, None).clone()
+            v.grad_shared = False
+        out = Var(v.data[lo:hi], True, v.grad[lo:hi])
+        return out
+
+    def cat_rows(self, vs: Sequence[Var]) -> Var:
+        req = any(v.req for v in vs)
+        out = Var(torch.cat([v.data for v in vs], 0), req)
+        self.n_fwd += 1
+        if req:
+            def bw(g: Tensor) -> None:
+                lo = 0
+                for v in vs:
+                    self._acc(v, g[lo:lo + v.rows], owned=False)
+                    lo += v.rows
+            self._push(out, bw)
+        return out
+
+    # ------------------------------------------------------------------ primitives
+    def linear(self, x: Var, w: Var, b: Optional[Var], relu: bool = False) -> Var:
+        bd = None if b is None else b.data.view(-1)
+        y = self.ops.linear_fwd(x.data, w.data, bd, relu)
+        self.n_fwd += 1
+        req = x.req or w.req
+        out = Var(y, req)
+        if req:
+            def bw(g: Tensor) -> None:
+                dx = self.ops.linear_bwd(g, x.data, w.data, bd, y, relu, w.grad if w.req else None,
+                                         b.grad.view(-1) if (b is not None and b.req) else None, x.req)
+                self._acc(x, dx)
+            self._push(out, bw)
+        return out
+
+    def layernorm(self, x: Var, w: Var, b: Var, relu: bool = False) -> Var:
+        wd, bd = w.data.view(-1), b.data.view(-1)
+        y, stats = self.ops.layernorm_fwd(x.data, wd, bd, relu)
+        self.n_fwd += 1
+        req = x.req or w.req
+        out = Var(y, req)
+        if req:
+            def bw(g: Tensor) -> None:
+                dx = self.ops.layernorm_bwd(g, x.data, wd, bd, stats, y, relu, w.grad.view(-1) if w.req else None,
+                                            b.grad.view(-1) if b.req else None)
+                self._acc(x, dx)
+            self._push(out, bw)
+        return out
+
+    def attention(self, q: Var, kv: Var, key_valid: Tensor, n_batch: int, n_src: int, n_tgt: int, eye: bool):
+        """q [B*S, D], kv [B*T, 2D] -> (o [B*S, D], dead [B*S] u8)."""
+        D = q.cols
+        o, p, dead = self.ops.attention_fwd(q.data.view(n_batch, n_src, D), kv.data.view(n_batch, n_tgt, 2 * D), key_valid, eye)
+        self.n_fwd += 1
+        req = q.req or kv.req
+        out = Var(o.view(n_batch * n_src, D), req)
+        if req:
+            def bw(g: Tensor) -> None:
+                dq, dkv = self.ops.attention_bwd(g.view(n_batch, n_src, D), q.data.view(n_batch, n_src, D),
+                                                 kv.data.view(n_batch, n_tgt, 2 * D), key_valid, eye, p)
+                self._acc(q, dq.view(n_batch * n_src, D))
+                self._acc(kv, dkv.view(n_batch * n_tgt, 2 * D))
+            self._push(out, bw)
+        return out, dead.view(-1)
+
+    def add_mask(self, a: Var, b: Optional[Var], keep: Optional[Tensor]) -> Var:
+        """(a + b) with the rows where keep == 0 zeroed."""
+        y = self.ops.add_mask_fwd(a.data, None if b is None else b.data, keep)
+        self.n_fwd += 1
+        req = a.req or (b is not None and b.req)
+        out = Var(y, req)
+        if req:
+            def bw(g: Tensor) -> None:
+                d = self.ops.add_mask_bwd(g, keep)
+                shared = (d is g) or (b is not None and a.req and b.req)
+                self._acc(a, d, owned=not shared)
+                if b is not None:
+                    self._acc(b, d, owned=not shared)
+            self._push(out, bw)
+        return out
+
+    def select_rows(self, mask: Tensor, a: Var, b: Var) -> Var:
+        y = self.ops.select_rows_fwd(mask, a.data, b.data)
+        self.n_fwd += 1
+        req = a.req or b.req
+        out = Var(y, req)
+        if req:
+            def bw(g: Tensor) -> None:
+                da, db = self.ops.select_rows_bwd(g, mask)
+                self._acc(a, da)
+                self._acc(b, db)
+            self._push(out, bw)
+        return out
+
+    def cat2(self, a: Var, b: Var) -> Var:
+        y = self.ops.cat2_fwd(a.data, b.data)
+        self.n_fwd += 1
+        req = a.req or b.req
+        out = Var(y, req)
+        if req:
+            ka = a.cols
+
+            def bw(g: Tensor) -> None:
+                da, db = self.ops.cat2_bwd(g, ka)
+                self._acc(a, da)
+                self._acc(b, db)
+            self._push(out, bw)
+        return out
+
+    def gru_gates(self, gi: Var, gh: Var, h: Var) -> Var:
+        y = self.ops.gru_gates_fwd(gi.data, gh.data, h.data)
+        self.n_fwd += 1
+        out = Var(y, True)
+
+        def bw(g: Tensor) -> None:
+            dgi, dgh, dh = self.ops.gru_gates_bwd(g, gi.data, gh.data, h.data)
+            self._acc(gi, dgi)
+            self._acc(gh, dgh)
+            self._acc(h, dh)
+        self._push(out, bw)
+        return out
+
+    def masked_max(self, x: Var, valid: Tensor, n_outer: int, n_red: int, n_inner: int, fill: float) -> Var:
+        D = x.cols
+        y, idx = self.ops.masked_max_fwd(x.data.view(n_outer, n_red, n_inner, D), valid.view(n_outer, n_red, n_inner), fill)
+        self.n_fwd += 1
+        out = Var(y.view(n_outer * n_inner, D), x.req)
+        if x.req:
+            def bw(g: Tensor) -> None:
+                dx = self.ops.masked_max_bwd(g.view(n_outer, n_inner, D), idx, n_red)
+                self._acc(x, dx.view(-1, D))
+            self._push(out, bw)
+        return out
+
+    def gather_rows(self, x: Var, idx: Tensor) -> Var:
+        y = self.ops.gather_rows_fwd(x.data, idx)
+        self.n_fwd += 1
+        out = Var(y, x.req)
+        if x.req:
+            n = x.rows
+
+            def bw(g: Tensor) -> None:
+                self._acc(x, self.ops.gather_rows_bwd(g, idx, n))
+            self._push(out, bw)
+        return out
+
+    def pair_add(self, u: Var, v: Var, n_scene: int, n_pl: int, n_agent: int) -> Var:
+        D = u.cols
+        y = self.ops.pair_add_fwd(u.data.view(n_scene, n_pl, D), v.data.view(n_scene, n_agent, D))
+        self.n_fwd += 1
+        req = u.req or v.req
+        out = Var(y.view(-1, D), req)
+        if req:
+            def bw(g: Tensor) -> None:
+                du, dv = self.ops.pair_add_bwd(g.view(n_scene, n_agent, n_pl, D))
+                self._acc(u, du.reshape(-1, D))
+                self._acc(v, dv.reshape(-1, D))
+            self._push(out, bw)
+        return out
+
+    def rsample(self, mean: Var, log_std: Var, eps: Tensor) -> Var:
+        z = self.ops.rsample_fwd(mean.data, log_std.data.view(-1), eps)
+        self.n_fwd += 1
+        out = Var(z, True)
+
+        def bw(g: Tensor) -> None:
+            dm = self.ops.rsample_bwd(g, eps, log_std.data.view(-1), log_std.grad.view(-1))
+            self._acc(mean, dm, owned=dm is not g)
+        self._push(out, bw)
+        return out
+
+    def dynamics(self, state: Var, mean: Var, a_type: Tensor, valid: Tensor) -> Var:
+        y = self.ops.dynamics_fwd(state.data, mean.data, a_type, valid)
+        self.n_fwd += 1
+        out = Var(y, True)
+
+        def bw(g: Tensor) -> None:
+            ds, dm = self.ops.dynamics_bwd(g, state.data, mean.data, a_type, valid)
+            self._acc(state, ds)
+            self._acc(mean, dm)
+        self._push(out, bw)
+        return out
+
+    def reward(self, pred: Var, gt: Tensor, rv: Tensor) -> Var:
+        r = self.ops.reward_fwd(pred.data, gt, rv)
+        self.n_fwd += 1
+        out = Var(r.view(-1, 1), True)
+
+        def bw(g: Tensor) -> None:
+            self._acc(pred, self.ops.reward_bwd(g.view(-1), pred.data, gt, rv))
+        self._push(out, bw)
+        return out
