@@ -429,6 +429,68 @@ int32_t tb_tc_block_count(void);
 int32_t tb_tc_first_block(int32_t weight_index); /* -1 if weight i has no tensor-core copy (N or K not multiple of 128) */
 int32_t tb_tc_selftest(const float* a, int32_t block, const float* packed, float* d, int32_t mode, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training primitives (BASELINE.json configs[3]; csrc/tb_train.cu).  The reference trains through torch.autograd
+ * (src/pl_modules/waymo_motion.py:356-418 `training_step` + Lightning backward, loss: src/models/metrics/training.py:62-158,
+ * optimizer: waymo_motion.py:955-973).  Each entry point is the forward or the hand-derived backward kernel of one
+ * differentiable operation of that step; buffers are dense row-major fp32 [rows, cols], masks uint8; "accumulated" outputs
+ * are added to, "zero-initialised by the caller" outputs receive atomic partial sums.  The host side that replays them in
+ * reverse order is trafficbots_b200/train/{tape,graph}.py.
+ *   linear      : nn.Linear (+ReLU) of models/modules/mlp.py:36-64 and the in/out projections of attention.py:85-87,142
+ *   layernorm   : nn.LayerNorm(128), eps 1e-5 (+ReLU)
+ *   attention   : softmax(QK^T masked, / sqrt(32)) V per head, dead rows (attention.py:89-141,144-146)
+ *   gru_gates   : nn.GRU cell gate math (agent_temporal.py:119-153)
+ *   masked_max  : map_encoder.py:95-97,105-106 / TemporalAggregate max_valid (agent_temporal.py:31-44)
+ *   pair_add, dest_nll : DestPredictor mlp mode (goal_manager.py:294-307,328-333) + goal NLL (metrics/training.py:138-147)
+ *   rsample, kl : DiagGaussian.rsample (distributions.py:19-50), BalancedKL with free nats (metrics/loss.py:74-77)
+ *   dynamics, reward, sim_flags : utils/dynamics.py:74-167,187-228; utils/rewards.py:117-131;
+ *                 utils/traffic_rule_checker.py:101-119,364-410 + models/goal_manager.py:155-161
+ *   sq_norm, adam_step : torch.nn.utils.clip_grad_norm_ + torch.optim.Adam on the flat parameter buffer
+ * ------------------------------------------------------------------------------------------------------------------ */
+int32_t tb_tr_linear_fwd(const float* x, int64_t M, int32_t K, const float* w, int64_t ldw, int32_t N, const float* bias, int32_t relu, float* y, void* stream);
+/* dx = (dy * relu') W; dw += (dy * relu')^T x; db += colsum(dy * relu').  dx / dw / db may be NULL (skipped). */
+int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_t ldw, const float* y, int32_t relu, int64_t M, int32_t K, int32_t N, float* dx, float* dw, int64_t lddw, float* db, void* stream);
+int32_t tb_tr_layernorm_fwd(const float* x, const float* w, const float* b, int32_t relu, int64_t M, int32_t D, float* y, float* stats, void* stream);
+int32_t tb_tr_layernorm_bwd(const float* dy, const float* x, const float* w, const float* stats, const float* y, int32_t relu, int64_t M, int32_t D, float* dx, float* dw, float* db, void* stream);
+int32_t tb_tr_attention_fwd(const float* q, const float* kv, const uint8_t* key_valid, int32_t eye, int32_t B, int32_t S, int32_t T, float* o, float* p, uint8_t* dead, void* stream);
+/* dq must be zero-initialised by the caller (partials are added atomically); dkv is overwritten */
+int32_t tb_tr_attention_bwd(const float* dout, const float* q, const float* kv, const float* p, const float* o, int32_t B, int32_t S, int32_t T, float* dq, float* dkv, void* stream);
+int32_t tb_tr_add_mask(const float* a, const float* b, const uint8_t* keep, int64_t M, int32_t N, float* y, void* stream);
+int32_t tb_tr_axpy(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t M, int32_t N, void* stream);
+int32_t tb_tr_select_rows(const uint8_t* mask, const float* a, const float* b, int64_t M, int32_t N, float* y, void* stream);
+int32_t tb_tr_select_rows_bwd(const uint8_t* mask, const float* dy, int64_t M, int32_t N, float* da, float* db, void* stream);
+int32_t tb_tr_cat2(const float* a, int32_t ka, const float* b, int32_t kb, int64_t M, float* y, void* stream);
+int32_t tb_tr_cat2_bwd(const float* dy, int32_t ka, int32_t kb, int64_t M, float* da, float* db, void* stream);
+int32_t tb_tr_gru_gates_fwd(const float* gi, const float* gh, const float* h, int64_t M, float* hn, void* stream);
+int32_t tb_tr_gru_gates_bwd(const float* dhn, const float* gi, const float* gh, const float* h, int64_t M, float* dgi, float* dgh, float* dh, void* stream);
+int32_t tb_tr_masked_max_fwd(const float* x, const uint8_t* valid, int64_t O, int32_t R, int64_t I, int32_t D, float fill, float* y, int32_t* idx, void* stream);
+int32_t tb_tr_masked_max_bwd(const float* dy, const int32_t* idx, int64_t O, int32_t R, int64_t I, int32_t D, float* dx, void* stream);
+int32_t tb_tr_gather_rows(const float* x, const int64_t* idx, int64_t M, int32_t D, float* y, void* stream);
+/* dx must be zero-initialised by the caller */
+int32_t tb_tr_scatter_add_rows(const float* dy, const int64_t* idx, int64_t M, int32_t D, float* dx, void* stream);
+int32_t tb_tr_pair_add(const float* u, const float* v, int32_t S, int32_t P, int32_t A, float* y, void* stream);
+/* dv must be zero-initialised by the caller */
+int32_t tb_tr_pair_add_bwd(const float* dy, int32_t S, int32_t P, int32_t A, float* du, float* dv, void* stream);
+/* nll_sum [1] must be zero-initialised by the caller */
+int32_t tb_tr_dest_nll(const float* logits, const uint8_t* pair_ok, const uint8_t* row_valid, const int64_t* gt, const uint8_t* loss_rows, const float* scale, int64_t n_row, int32_t P, float* nll_sum, float* dlogits, void* stream);
+int32_t tb_tr_rsample(const float* mean, const float* log_std, const float* eps, int64_t M, int32_t E, float* z, void* stream);
+int32_t tb_tr_rsample_bwd(const float* dz, const float* eps, const float* log_std, int64_t M, int32_t E, float* dlog_std, void* stream);
+/* kl_sum [1] zero-initialised by the caller; dlq / dlp are accumulated into */
+int32_t tb_tr_kl(const float* mq, const float* lq, const float* mp, const float* lp, const uint8_t* valid, float free_nats, const float* scale, int64_t M, int32_t E, float* kl_sum, float* dmq, float* dmp, float* dlq, float* dlp, void* stream);
+int32_t tb_tr_pose_pe(const float* xy, const float* yaw, const float* f_xy, int32_t n_xy, const float* f_yaw, int32_t n_yaw, int64_t M, float* pe, void* stream);
+int32_t tb_tr_dir_to_yaw(const float* d, int64_t M, float* yaw, void* stream);
+int32_t tb_tr_dynamics(const float* state, const float* mean, const uint8_t* a_type, const uint8_t* valid, int64_t M, float* pred, const float* dpred, float* dstate, float* dmean, void* stream);
+int32_t tb_tr_reward(const float* pred, const float* gt, const uint8_t* rv, int64_t M, float* r, const float* dr, float* dpred, void* stream);
+int32_t tb_tr_sim_flags(const float* state, const uint8_t* valid, const uint8_t* gt_valid, const float* boundary, const float* dest_pos, const float* dest_dir, const uint8_t* dest_valid, const uint8_t* dest_lane, const uint8_t* dest_edge, const uint8_t* killed, const uint8_t* dest_reached, const uint8_t* goal_valid, int32_t B, int32_t A, uint8_t* o_valid, uint8_t* o_killed, uint8_t* o_dest, uint8_t* o_goal, void* stream);
+/* out [1] zero-initialised by the caller */
+int32_t tb_tr_masked_sum(const float* x, const uint8_t* mask, int64_t n, float* out, void* stream);
+int32_t tb_tr_mask_scale(const uint8_t* mask, const float* scale, int64_t n, float* out, void* stream);
+int32_t tb_tr_scale(float* x, int64_t n, float alpha, void* stream);
+/* out [1] zero-initialised by the caller */
+int32_t tb_tr_sq_norm(const float* g, int64_t n, float* out, void* stream);
+int32_t tb_tr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_by_group, const int32_t* group_end, int32_t n_group, float beta1, float beta2, float eps, int32_t step, const float* sq_norm, float max_norm, void* stream);
+
 /* Kernels this library launches on a call path, for accounting (`gpu_launches` in bench.py). */
 int64_t tb_launch_count(void);
 

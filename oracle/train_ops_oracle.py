@@ -49,6 +49,9 @@ class OracleOps:
     def add_(self, dst: Tensor, src: Tensor) -> None:
         dst += src
 
+    def scale_(self, x: Tensor, alpha: float) -> None:
+        x *= alpha
+
     # ---- Linear (+ReLU) : models/modules/mlp.py, attention.py in/out projections ----
     def linear_fwd(self, x: Tensor, w: Tensor, b: Optional[Tensor], relu: bool) -> Tensor:
         y = F.linear(x, w, b)
@@ -256,11 +259,13 @@ class OracleOps:
 
     # ---- non-differentiable simulation bookkeeping of one step (pl_modules/waymo_motion.py:311-320) ----
     def sim_flags(self, state, valid, gt_valid_t, boundary, dest_pos, dest_dir, dest_valid, dest_is_lane, dest_is_edge,
-                  dest_thresh, killed, dest_reached, goal_valid):
+                  killed, dest_reached, goal_valid):
         """state [B,A,4] post-override, valid [B,A] post-override.  Always-on checks that feed back into the simulation:
         outside_map (utils/traffic_rule_checker.py:101-119) -> kill (utils/dynamics.py:151-167), dest_reached (:364-410) ->
         goal_valid (models/goal_manager.py:155-161).  Returns (valid', killed', dest_reached', goal_valid')."""
         valid, killed, dest_reached, goal_valid = valid.bool(), killed.bool(), dest_reached.bool(), goal_valid.bool()
+        dest_dir = dest_dir / torch.norm(dest_dir, dim=-1, keepdim=True)  # traffic_rule_checker.py:93
+        dest_thresh = torch.ones_like(state[..., 0]) * 50 * (1 - dest_is_edge.to(state.dtype) * 0.8)  # :95-98
         px, py = state[..., 0], state[..., 1]
         out_t = ((px > boundary[:, [1]]) | (px < boundary[:, [0]]) | (py > boundary[:, [3]]) | (py < boundary[:, [2]])) & valid
         dist = torch.norm(state[..., :2].unsqueeze(2) - dest_pos, dim=-1).masked_fill(~dest_valid.bool(), 1e4)
@@ -281,11 +286,18 @@ class OracleOps:
     def grad_sq_norm(self, g):
         return (g.double() ** 2).sum().float().reshape(1)
 
-    def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, step: int, clip_coef):
-        """clip_coef: device scalar multiplied into g (torch.nn.utils.clip_grad_norm_)."""
-        g = g * clip_coef
+    def adam_step(self, p, g, m, v, lr_by_group, group_end, beta1, beta2, eps, step: int, sq_norm, max_norm):
+        """torch.optim.Adam (defaults) on the flat buffer; g is first scaled by min(1, max_norm / (||g|| + 1e-6))
+        (torch.nn.utils.clip_grad_norm_); parameter group i covers [group_end[i-1], group_end[i])."""
+        coef = 1.0
+        if sq_norm is not None and max_norm > 0:
+            coef = torch.clamp(max_norm / (sq_norm.sqrt() + 1e-6), max=1.0)
+        g = g * coef
         m.mul_(beta1).add_(g, alpha=1 - beta1)
         v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
         bc1 = 1 - beta1 ** step
         bc2 = 1 - beta2 ** step
-        p.addcdiv_(m, (v.sqrt() / math.sqrt(bc2)).add_(eps), value=-lr / bc1)
+        lo = 0
+        for gi, hi in enumerate(group_end.tolist()):
+            p[lo:hi].addcdiv_(m[lo:hi], (v[lo:hi].sqrt() / math.sqrt(bc2)).add_(eps), value=-float(lr_by_group[gi]) / bc1)
+            lo = hi

@@ -1,0 +1,289 @@
+"""Training step (BASELINE.json configs[3]) -- GPU parity tests, through the C ABI (`tb_tr_*`).
+
+(1) every primitive: forward kernel vs the torch restatement, hand-derived backward kernel vs torch.autograd of that
+    restatement (`oracle/train_ops_oracle.py`), fp32, tolerance 2e-5 relative to the tensor's max;
+(2) the whole step: loss terms and gradients of all 385 parameters vs fingerprints of the UNMODIFIED reference's
+    `training_step` + backward (`tests/golden/train_*.npz`), tolerance 1e-3 of each gradient's scale;
+(3) a few optimizer steps reduce the loss and match the same steps done with the torch restatement on CPU.
+"""
+import pytest
+import torch
+
+from train_ops_oracle import OracleOps
+from train_util import TRAIN_CASES, compare_grads, load_train_case
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from trafficbots_b200.train.cuda_ops import CudaOps
+    return CudaOps(DEV)
+
+
+ORC = OracleOps()
+
+
+def close(a, b, tol=2e-5, what=""):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    scale = float(b.abs().max()) + 1e-12
+    err = float((a - b).abs().max())
+    assert err <= tol * scale + 1e-7, f"{what}: max|diff| {err:.3e} vs scale {scale:.3e}"
+
+
+def g(*t):
+    return [x.to(DEV) if x is not None else None for x in t]
+
+
+@pytest.mark.parametrize("M,K,N,relu,strided", [(37, 11, 32, True, False), (300, 128, 256, False, False), (1000, 256, 128, True, True),
+                                                (129, 128, 1, False, False), (64, 16, 128, True, False), (5000, 128, 384, False, False)])
+def test_linear(ops, M, K, N, relu, strided):
+    torch.manual_seed(M + K + N)
+    x = torch.randn(M, K)
+    wfull = torch.randn(N, 2 * K if strided else K) / K ** 0.5
+    w = wfull[:, K // 2: K // 2 + K] if strided else wfull
+    b = torch.randn(N) * 0.1
+    y_ref = ORC.linear_fwd(x, w, b, relu)
+    dy = torch.randn(M, N)
+    dw_ref, db_ref = torch.zeros_like(w) + 0.5, torch.zeros(N) - 0.25  # accumulate on top of existing content
+    dx_ref = ORC.linear_bwd(dy, x, w, b, y_ref, relu, dw_ref, db_ref, True)
+    xg, bg, dyg = g(x, b, dy)
+    wfg = wfull.to(DEV)
+    wg = wfg[:, K // 2: K // 2 + K] if strided else wfg
+    y = ops.linear_fwd(xg, wg, bg, relu)
+    close(y, y_ref, what="y")
+    dwf = torch.zeros_like(wfg) + 0.5
+    dwg = dwf[:, K // 2: K // 2 + K] if strided else dwf
+    dbg = torch.zeros(N, device=DEV) - 0.25
+    dx = ops.linear_bwd(dyg, xg, wg, bg, y, relu, dwg, dbg, True)
+    close(dx, dx_ref, what="dx")
+    close(dwg, dw_ref, tol=5e-5, what="dw")
+    close(dbg, db_ref, tol=5e-5, what="db")
+    if strided:  # columns outside the slice untouched
+        assert float((dwf[:, : K // 2] - 0.5).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,relu", [(5, False), (777, True)])
+def test_layernorm(ops, M, relu):
+    torch.manual_seed(M)
+    x, w, b, dy = torch.randn(M, 128) * 3 + 1, torch.rand(128) + 0.5, torch.randn(128) * 0.2, torch.randn(M, 128)
+    y_ref, st_ref = ORC.layernorm_fwd(x, w, b, relu)
+    dw_ref, db_ref = torch.ones(128), torch.ones(128)
+    dx_ref = ORC.layernorm_bwd(dy, x, w, b, st_ref, y_ref, relu, dw_ref, db_ref)
+    xg, wg, bg, dyg = g(x, w, b, dy)
+    y, st = ops.layernorm_fwd(xg, wg, bg, relu)
+    close(y, y_ref, what="y")
+    close(st, st_ref, what="stats")
+    dwg, dbg = torch.ones(128, device=DEV), torch.ones(128, device=DEV)
+    dx = ops.layernorm_bwd(dyg, xg, wg, bg, st, y, relu, dwg, dbg)
+    close(dx, dx_ref, tol=5e-5, what="dx")
+    close(dwg, dw_ref, tol=5e-5, what="dw")
+    close(dbg, db_ref, tol=5e-5, what="db")
+
+
+@pytest.mark.parametrize("B,S,T,eye", [(3, 8, 64, False), (2, 20, 20, False), (5, 8, 8, True), (2, 70, 200, False), (1, 64, 1024, False),
+                                       (4, 3, 40, False)])
+def test_attention(ops, B, S, T, eye):
+    torch.manual_seed(B * 1000 + S + T)
+    q, kv, do = torch.randn(B, S, 128), torch.randn(B, T, 256), torch.randn(B, S, 128)
+    kvalid = (torch.rand(B, T) < 0.7)
+    kvalid[0] = False  # a batch entry without any valid key: every row dead
+    if B > 1:
+        kvalid[1] = False
+        kvalid[1, 0] = True  # exactly one valid key (with eye: row 0 is dead)
+    kvalid = kvalid.to(torch.uint8)
+    o_ref, p_ref, dead_ref = ORC.attention_fwd(q, kv, kvalid, eye)
+    dq_ref, dkv_ref = ORC.attention_bwd(do, q, kv, kvalid, eye, p_ref)
+    qg, kvg, dog, kvg_valid = g(q, kv, do, kvalid)
+    o, p, dead = ops.attention_fwd(qg, kvg, kvg_valid, eye)
+    close(o, o_ref, what="o")
+    close(p[0], p_ref, what="p")
+    assert torch.equal(dead.cpu(), dead_ref)
+    dq, dkv = ops.attention_bwd(dog, qg, kvg, kvg_valid, eye, p)
+    close(dq, dq_ref, tol=5e-5, what="dq")
+    close(dkv, dkv_ref, tol=5e-5, what="dkv")
+
+
+def test_glue_ops(ops):
+    torch.manual_seed(1)
+    M = 333
+    a, b, dy = torch.randn(M, 128), torch.randn(M, 128), torch.randn(M, 128)
+    keep = (torch.rand(M) < 0.6).to(torch.uint8)
+    ag, bg, dyg, kg = g(a, b, dy, keep)
+    close(ops.add_mask_fwd(ag, bg, kg), ORC.add_mask_fwd(a, b, keep))
+    close(ops.add_mask_fwd(ag, None, kg), ORC.add_mask_fwd(a, None, keep))
+    close(ops.add_mask_fwd(ag, bg, None), ORC.add_mask_fwd(a, b, None))
+    close(ops.add_mask_bwd(dyg, kg), ORC.add_mask_bwd(dy, keep))
+    close(ops.select_rows_fwd(kg, ag, bg), ORC.select_rows_fwd(keep, a, b))
+    for x, y in zip(ops.select_rows_bwd(dyg, kg), ORC.select_rows_bwd(dy, keep)):
+        close(x, y)
+    c = torch.randn(M, 96)
+    close(ops.cat2_fwd(ag[:, :32].contiguous(), c.to(DEV)), ORC.cat2_fwd(a[:, :32], c))
+    for x, y in zip(ops.cat2_bwd(dyg, 32), ORC.cat2_bwd(dy, 32)):
+        close(x, y)
+    dst = torch.randn(M, 128)
+    dstg = dst.to(DEV)
+    ops.add_(dstg, ag)
+    close(dstg, dst + a)
+    big = torch.zeros(M, 256, device=DEV)
+    ops.add_(big[:, 64:192], ag)  # strided destination (gradient view of a column slice)
+    close(big[:, 64:192], a)
+    ops.scale_(dstg, 0.25)
+    close(dstg, (dst + a) * 0.25)
+    # GRU gates
+    gi, gh, h, dh = torch.randn(M, 384), torch.randn(M, 384), torch.randn(M, 128), torch.randn(M, 128)
+    gig, ghg, hg, dhg = g(gi, gh, h, dh)
+    close(ops.gru_gates_fwd(gig, ghg, hg), ORC.gru_gates_fwd(gi, gh, h))
+    for x, y in zip(ops.gru_gates_bwd(dhg, gig, ghg, hg), ORC.gru_gates_bwd(dh, gi, gh, h)):
+        close(x, y)
+    # gather / scatter-add
+    idx = torch.randint(0, 50, (M,))
+    src = torch.randn(50, 128)
+    close(ops.gather_rows_fwd(src.to(DEV), idx.to(DEV)), ORC.gather_rows_fwd(src, idx))
+    close(ops.gather_rows_bwd(dyg, idx.to(DEV), 50), ORC.gather_rows_bwd(dy, idx, 50), tol=5e-5)
+
+
+@pytest.mark.parametrize("O,R,I,fill", [(40, 20, 1, float("-inf")), (1, 7, 33, -1e3)])
+def test_masked_max(ops, O, R, I, fill):
+    torch.manual_seed(O)
+    x = torch.randn(O, R, I, 128)
+    valid = (torch.rand(O, R, I) < 0.5)
+    valid[0, :, 0] = False
+    valid = valid.to(torch.uint8)
+    y_ref, idx_ref = ORC.masked_max_fwd(x, valid, fill)
+    y, idx = ops.masked_max_fwd(x.to(DEV), valid.to(DEV), fill)
+    close(y, y_ref)
+    assert torch.equal(idx.cpu(), idx_ref)
+    dy = torch.randn(O, I, 128)
+    close(ops.masked_max_bwd(dy.to(DEV), idx, R), ORC.masked_max_bwd(dy, idx_ref, R))
+
+
+def test_dest_ops(ops):
+    torch.manual_seed(3)
+    S, P, A = 2, 50, 6
+    u, v, dy = torch.randn(S, P, 128), torch.randn(S, A, 128), torch.randn(S, A, P, 128)
+    close(ops.pair_add_fwd(u.to(DEV), v.to(DEV)), ORC.pair_add_fwd(u, v))
+    for x, y in zip(ops.pair_add_bwd(dy.to(DEV)), ORC.pair_add_bwd(dy)):
+        close(x, y, tol=5e-5)
+    logits = torch.randn(S, A, P) * 2
+    ok = (torch.rand(S, A, P) < 0.4)
+    ok[0, 0] = False  # a row that ends up all -inf -> reset to 0
+    gt = torch.randint(0, P, (S, A))
+    ok[torch.arange(S)[:, None], torch.arange(A)[None], gt] = True
+    ok[0, 0] = False
+    row_valid = torch.ones(S, A, dtype=torch.bool)
+    row_valid[1, 2] = False
+    loss_rows = row_valid.clone()
+    loss_rows[1, 3] = False
+    scale = torch.tensor([0.37])
+    u8 = torch.uint8
+    nll_ref, dl_ref = ORC.dest_nll(logits, ok.to(u8), row_valid.to(u8), gt, loss_rows.to(u8), scale)
+    nll, dl = ops.dest_nll(*g(logits, ok.to(u8), row_valid.to(u8), gt, loss_rows.to(u8), scale))
+    close(nll, nll_ref)
+    close(dl, dl_ref)
+
+
+def test_latent_ops(ops):
+    torch.manual_seed(4)
+    M, E = 50, 16
+    mean, ls, eps, dz = torch.randn(M, E), torch.randn(E) * 0.1 - 1, torch.randn(M, E), torch.randn(M, E)
+    close(ops.rsample_fwd(*g(mean, ls, eps)), ORC.rsample_fwd(mean, ls, eps))
+    dls_ref, dls = torch.ones(E), torch.ones(E, device=DEV)
+    ORC.rsample_bwd(dz, eps, ls, dls_ref)
+    ops.rsample_bwd(dz.to(DEV), eps.to(DEV), ls.to(DEV), dls)
+    close(dls, dls_ref, tol=5e-5)
+    mq, mp, lq, lp = torch.randn(M, E) * 0.3, torch.randn(M, E) * 0.3, torch.randn(E) * 0.1 - 1, torch.randn(E) * 0.1 - 1
+    mq[:5] = mp[:5]  # rows below the free-nats floor: no gradient
+    lq2 = lp.clone()
+    valid = (torch.rand(M) < 0.8).to(torch.uint8)
+    scale = torch.tensor([0.05])
+    for lq_ in (lq, lq2):
+        a_ref, b_ref = torch.zeros(E), torch.zeros(E)
+        ref = ORC.kl_fwd_bwd(mq, lq_, mp, lp, valid, 0.01, scale, a_ref, b_ref)
+        a, b = torch.zeros(E, device=DEV), torch.zeros(E, device=DEV)
+        out = ops.kl_fwd_bwd(*g(mq, lq_, mp, lp, valid), 0.01, scale.to(DEV), a, b)
+        for x, y in zip(out, ref):
+            close(x, y, tol=5e-5)
+        close(a, a_ref, tol=5e-5)
+        close(b, b_ref, tol=5e-5)
+    x = torch.randn(40, 9)
+    mask = (torch.rand(40, 9) < 0.5).to(torch.uint8)
+    close(ops.masked_sum(x.to(DEV), mask.to(DEV)), ORC.masked_sum(x, mask))
+    close(ops.mask_scale(mask[:, 0].contiguous().to(DEV), scale.to(DEV)), ORC.mask_scale(mask[:, 0], scale))
+
+
+def test_pose_pe_and_simulation_ops(ops):
+    from trafficbots_b200 import weights
+    torch.manual_seed(5)
+    M = 200
+    xy, yaw, d = (torch.rand(M, 2) - 0.5) * 200, (torch.rand(M) - 0.5) * 6.28, torch.randn(M, 2)
+    fx, fy = weights.pe_freqs_xy(), weights.pe_freqs_yaw()
+    close(ops.pose_pe(*g(xy, yaw, fx, fy)), ORC.pose_pe(xy, yaw, fx, fy), tol=1e-5)
+    close(ops.dir_to_yaw(d.to(DEV)), ORC.dir_to_yaw(d), tol=1e-6)
+    state = torch.cat([xy, yaw[:, None], torch.rand(M, 1) * 10], -1)
+    mean, dp = torch.randn(M, 2), torch.randn(M, 4)
+    a_type = torch.nn.functional.one_hot(torch.randint(0, 3, (M,)), 3).to(torch.uint8)
+    a_type[:3] = 0  # agents without a type
+    valid = (torch.rand(M) < 0.8).to(torch.uint8)
+    pred_ref = ORC.dynamics_fwd(state, mean, a_type, valid)
+    pred = ops.dynamics_fwd(*g(state, mean, a_type, valid))
+    close(pred, pred_ref, tol=1e-6)
+    for x, y in zip(ops.dynamics_bwd(*g(dp, state, mean, a_type, valid)), ORC.dynamics_bwd(dp, state, mean, a_type, valid)):
+        close(x, y)
+    gt = state + torch.randn(M, 4) * torch.tensor([2.0, 2.0, 0.5, 1.0])
+    rv = (torch.rand(M) < 0.7).to(torch.uint8)
+    close(ops.reward_fwd(*g(pred_ref, gt, rv)), ORC.reward_fwd(pred_ref, gt, rv))
+    dr = torch.randn(M)
+    close(ops.reward_bwd(*g(dr, pred_ref, gt, rv)), ORC.reward_bwd(dr, pred_ref, gt, rv))
+    # bookkeeping
+    B, A = 4, 50
+    st = state.view(B, A, 4).contiguous()
+    boundary = torch.tensor([[-80.0, 80.0, -80.0, 80.0]]).expand(B, 4).contiguous()
+    dest_pos = st[..., None, :2] + torch.randn(B, A, 20, 2) * 40
+    dest_dir = torch.randn(B, A, 20, 2)
+    dest_dir[0, 0, 0] = 0.0  # zero-length direction (NaN after normalisation, masked: traffic_rule_checker.py:93,400)
+    u8 = torch.uint8
+    dest_valid = (torch.rand(B, A, 20) < 0.7).to(u8)
+    lane, edge = (torch.rand(B, A) < 0.6).to(u8), (torch.rand(B, A) < 0.3).to(u8)
+    flags = [(torch.rand(B, A) < p).to(u8) for p in (0.1, 0.1, 0.8)]
+    vb, gtv = valid.view(B, A).contiguous(), (torch.rand(B, A) < 0.5).to(u8)
+    for gt_valid_t in (gtv, None):
+        ref = ORC.sim_flags(st, vb, gt_valid_t, boundary, dest_pos, dest_dir, dest_valid, lane, edge, *flags)
+        out = ops.sim_flags(*g(st, vb, gt_valid_t, boundary, dest_pos, dest_dir, dest_valid, lane, edge, *flags))
+        for x, y in zip(out, ref):
+            assert torch.equal(x.cpu(), y)
+
+
+@pytest.mark.parametrize("case", TRAIN_CASES)
+def test_training_step_matches_reference(case):
+    from trafficbots_b200.train import trainer
+    c = load_train_case(case)
+    ts = trainer.TrainState(c["sd"], device=DEV)
+    batch = {k: v.to(DEV) for k, v in c["batch"].items()}
+    n0 = ts.ops.L.tb_launch_count()
+    out = ts.forward_backward(batch, c["eps"], c["use_prior"])
+    torch.cuda.synchronize()
+    assert ts.ops.L.tb_launch_count() - n0 > 10000  # the CUDA primitives did the work
+    for k, ref in c["terms"].items():
+        assert abs(float(out[k]) - ref) <= 1e-4 * max(1.0, abs(ref)), (k, float(out[k]), ref)
+    worst = compare_grads({k: v.cpu() for k, v in ts.grads().items()}, c["grads"])
+    print(f"{case}: loss {float(out['loss']):.6f} (reference {c['terms']['loss']:.6f}), worst gradient deviation {worst:.2e}")
+
+
+def test_optimizer_steps_match_cpu_restatement():
+    from trafficbots_b200.train import trainer
+    c = load_train_case(TRAIN_CASES[0])
+    ts = trainer.TrainState(c["sd"], device=DEV, lr=1e-3)
+    ref = trainer.TrainState(c["sd"], device="cpu", ops=ORC, lr=1e-3)
+    batch = {k: v.to(DEV) for k, v in c["batch"].items()}
+    losses = []
+    for i in range(3):
+        out = ts.training_step(batch, c["eps"], c["use_prior"])
+        out_ref = ref.training_step(c["batch"], c["eps"], c["use_prior"])
+        losses.append(float(out["loss"]))
+        assert abs(losses[-1] - float(out_ref["loss"])) <= 2e-4 * abs(float(out_ref["loss"])), (i, losses[-1], float(out_ref["loss"]))
+    assert losses[-1] < losses[0]
+    for k, v in ref.params.t.items():
+        assert float((ts.params.t[k].cpu() - v).abs().max()) <= 2e-4, k

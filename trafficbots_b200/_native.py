@@ -245,8 +245,34 @@ def lib() -> C.CDLL:
     L.tb_womd_record_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
     L.tb_womd_pack.restype = C.c_int32
     L.tb_womd_pack.argtypes = [C.c_int32, C.POINTER(TbWomdIn), C.POINTER(TbWomdOut), C.c_void_p]
+    for name, argtypes in training_signatures().items():  # tb_tr_*: argtypes parsed from the header (single source)
+        if not hasattr(L, name):
+            raise TbError(f"{LIB_PATH} does not export {name}")
+        fn = getattr(L, name)
+        fn.restype = C.c_int32
+        fn.argtypes = argtypes
     _lib = L
     return L
+
+
+_CTYPE = {"int64_t": C.c_int64, "int32_t": C.c_int32, "float": C.c_float}
+
+
+def training_signatures():
+    """{name: ctypes argtypes} of every `tb_tr_*` entry point declared in include/trafficbots_b200.h."""
+    import re
+    text = open(os.path.join(ROOT, "include", "trafficbots_b200.h")).read()
+    out = {}
+    for m in re.finditer(r"int32_t (tb_tr_[a-z0-9_]+)\(([^)]*)\);", text):
+        args = []
+        for a in m.group(2).split(","):
+            a = a.strip()
+            if "*" in a:
+                args.append(C.c_void_p)
+            else:
+                args.append(_CTYPE[a.replace("const ", "").split()[0]])
+        out[m.group(1)] = args
+    return out
 
 
 def check(rc: int, what: str) -> None:

@@ -320,9 +320,7 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
     dest_valid = batch["map/valid"][bidx, goal_gt].to(U8).contiguous()
     dest_type = batch["map/type"][bidx, goal_gt]
     dest_pos = batch["map/pos"][bidx, goal_gt].contiguous()
-    dest_dir = batch["map/dir"][bidx, goal_gt]
-    dest_dir = (dest_dir / torch.norm(dest_dir, dim=-1, keepdim=True)).contiguous()
-    dest_thresh = (torch.ones(S, A, device=dev) * 50 * (1 - dest_type[:, :, 4].to(torch.float32) * 0.8)).contiguous()
+    dest_dir = batch["map/dir"][bidx, goal_gt].contiguous()  # normalised in the kernel (:93)
     dest_lane = dest_type[:, :, :4].any(-1).to(U8).contiguous()
     dest_edge = dest_type[:, :, 4].to(U8).contiguous()
     boundary = batch["map/boundary"].contiguous()
@@ -383,7 +381,7 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
         # rule check on the post-override state, kill, disable_goal_reached (:311-320)
         valid, killed, dest_reached, goal_valid = ops.sim_flags(
             state.data.view(S, A, 4), valid, gv[:, t].to(U8).contiguous() if t < T_gt else None, boundary, dest_pos, dest_dir,
-            dest_valid, dest_lane, dest_edge, dest_thresh, killed, dest_reached, goal_valid)
+            dest_valid, dest_lane, dest_edge, killed, dest_reached, goal_valid)
         # DifferentiableReward.get, IL part (utils/rewards.py:117-131)
         if t < T_gt:
             rv = (pred_valid & gv[:, t].to(U8)).reshape(-1).contiguous()

@@ -1,0 +1,116 @@
+"""`TrainState` -- flat parameter / gradient / Adam buffers + one training step (BASELINE.json configs[3]).
+
+Stands where Lightning's `training_step` -> `backward` -> DDP all-reduce -> `optimizer.step` stands in the reference
+(pl_modules/waymo_motion.py:356-418,955-973; configs/trainer/default.yaml:12 gradient clipping at 5).  All parameters live in
+ONE flat fp32 buffer (layout = the order of the reference's `named_parameters()`, goal-predictor parameters last: they form
+the second Adam parameter group, :957-966), all gradients in another: the data-parallel reduction is a single NCCL
+all-reduce of 13.6 MB and the optimizer a single fused kernel (`tb_tr_sq_norm` + `tb_tr_adam_step`).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, Mapping, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from .. import weights
+from . import graph
+from .tape import Fn
+
+
+def trainable_names(state_dict: Mapping[str, Tensor]):
+    """the reference's `named_parameters()`: every state_dict key except buffers (`pre_processing.*`) and the aliases of the
+    shared cross-attention blocks (latent_encoder.py:39-41)."""
+    names = [k for k in state_dict if not k.startswith("pre_processing.") and weights._alias_of(k) is None]
+    main = [k for k in names if "goal_predictor" not in k]
+    goal = [k for k in names if "goal_predictor" in k]
+    return main, goal
+
+
+def build_params(state_dict: Mapping[str, Tensor], device) -> Tuple[graph.Params, Tensor, Tensor, "OrderedDict[str, Tuple[int, tuple]]", int]:
+    """-> (Params over views, flat parameters, flat gradients, {name: (offset, shape)}, end of parameter group 0)."""
+    main, goal = trainable_names(state_dict)
+    layout: "OrderedDict[str, Tuple[int, tuple]]" = OrderedDict()
+    off = 0
+    for k in main + goal:
+        layout[k] = (off, tuple(state_dict[k].shape))
+        off += (state_dict[k].numel() + 3) // 4 * 4  # 16-byte aligned views
+        if k == main[-1]:
+            end_main = off
+    flat_p = torch.zeros(off, dtype=torch.float32, device=device)
+    flat_g = torch.zeros(off, dtype=torch.float32, device=device)
+    tensors, grads = {}, {}
+    for k, (o, shape) in layout.items():
+        n = state_dict[k].numel()
+        tensors[k] = flat_p[o:o + n].view(shape)
+        grads[k] = flat_g[o:o + n].view(shape)
+        tensors[k].copy_(state_dict[k])
+    buffers = {k: v.to(device=device, dtype=torch.float32).contiguous() for k, v in state_dict.items() if k.startswith("pre_processing.")}
+    return graph.Params(tensors, grads, buffers), flat_p, flat_g, layout, end_main
+
+
+class TrainState:
+    def __init__(self, state_dict: Mapping[str, Tensor], device="cuda", ops=None, lr: float = 3e-4, lr_goal: Optional[float] = None,
+                 betas=(0.9, 0.999), eps: float = 1e-8, max_grad_norm: float = 5.0, p_rollout_prior: float = 0.1) -> None:
+        if ops is None:
+            from .cuda_ops import CudaOps  # raises without the CUDA library / a CUDA device: there is no CPU training path
+            ops = CudaOps(device)
+        self.ops = ops
+        self.device = torch.device(device)
+        self.params, self.flat_p, self.flat_g, self.layout, end_main = build_params(state_dict, self.device)
+        self.m = torch.zeros_like(self.flat_p)
+        self.v = torch.zeros_like(self.flat_p)
+        self.group_end = torch.tensor([end_main, self.flat_p.numel()], dtype=torch.int32, device=self.device)
+        self.lr = torch.tensor([lr, lr if lr_goal is None else lr_goal], dtype=torch.float32, device=self.device)
+        self.betas, self.eps, self.max_grad_norm = betas, eps, max_grad_norm
+        self.p_rollout_prior = p_rollout_prior
+        self.n_step = 0
+        self.last_ops = 0
+
+    def state_dict(self) -> Dict[str, Tensor]:
+        return {k: v.detach().clone() for k, v in self.params.t.items()}
+
+    def grads(self) -> Dict[str, Tensor]:
+        return self.params.g
+
+    def draw_noise(self, n_scene: int, n_agent: int, latent_dim: int = 16) -> Tuple[bool, Tensor]:
+        """the two host-side random draws of the reference step, in its order (global torch CPU generator):
+        `torch.rand(1) < p_training_rollout_prior` (:384), then the `rsample` noise (distributions.py:30)."""
+        use_prior = bool(torch.rand(1) < self.p_rollout_prior)
+        eps = torch.empty(n_scene, n_agent, latent_dim).normal_()
+        return use_prior, eps
+
+    def forward_backward(self, batch: Mapping[str, Tensor], eps: Optional[Tensor] = None, use_prior: Optional[bool] = None,
+                         return_buffers: bool = False) -> Dict[str, Tensor]:
+        """loss terms of `training_step` (device scalars) with the gradients of all parameters left in `self.flat_g`."""
+        S, _, A = batch["agent/valid"].shape
+        if eps is None or use_prior is None:
+            use_prior, eps = self.draw_noise(S, A)
+        self.flat_g.zero_()
+        fn = Fn(self.ops)
+        out = graph.training_forward(fn, self.params, batch, eps.to(self.device), use_prior, return_buffers=return_buffers)
+        self.last_ops = fn.n_fwd
+        fn.backward()
+        return out
+
+    def all_reduce_grads(self) -> None:
+        """DDP's gradient averaging (reference: Lightning DDP, src/run.py:51-53) as ONE collective on the flat buffer."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+            self.ops.scale_(self.flat_g, 1.0 / dist.get_world_size())
+
+    def optimizer_step(self) -> Tensor:
+        """clip_grad_norm_(max_grad_norm) + Adam; returns the squared gradient norm (device scalar)."""
+        self.n_step += 1
+        sq = self.ops.grad_sq_norm(self.flat_g)
+        self.ops.adam_step(self.flat_p, self.flat_g, self.m, self.v, self.lr, self.group_end, self.betas[0], self.betas[1], self.eps,
+                           self.n_step, sq, self.max_grad_norm)
+        return sq
+
+    def training_step(self, batch: Mapping[str, Tensor], eps: Optional[Tensor] = None, use_prior: Optional[bool] = None) -> Dict[str, Tensor]:
+        out = self.forward_backward(batch, eps, use_prior)
+        self.all_reduce_grads()
+        out["grad_sq_norm"] = self.optimizer_step()
+        return out
