@@ -1,0 +1,56 @@
+"""Times the training step (BASELINE.json configs[3] per-GPU slice: 16 scenes x 64 agents x 1024 polylines, 90 steps)
+phase by phase.  Usage: python tools/bench_train.py [n_scene] [n_agent] [n_pl] [repeats]"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from trafficbots_b200 import synthetic, weights  # noqa: E402
+from trafficbots_b200.train import graph, trainer  # noqa: E402
+from trafficbots_b200.train.tape import Fn  # noqa: E402
+
+
+def main():
+    S = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    A = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    P = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+    rep = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+    dev = "cuda:0"
+    sd = weights.init_state_dict(2023)
+    ts = trainer.TrainState(sd, device=dev)
+    ts.ops.check = False
+    batch = {k: v.to(dev) for k, v in synthetic.make_batch(S, n_agent=A, n_pl=P, seed=7).items()}
+    torch.manual_seed(0)
+    L = ts.ops.L
+    for i in range(rep + 1):
+        use_prior, eps = ts.draw_noise(S, A)
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        n0 = L.tb_launch_count()
+        t0 = time.perf_counter()
+        ts.flat_g.zero_()
+        fn = Fn(ts.ops)
+        out = graph.training_forward(fn, ts.params, batch, eps.to(dev), use_prior)
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        n1 = L.tb_launch_count()
+        fn.backward()
+        t3 = time.perf_counter()
+        torch.cuda.synchronize()
+        t4 = time.perf_counter()
+        n2 = L.tb_launch_count()
+        ts.optimizer_step()
+        torch.cuda.synchronize()
+        t5 = time.perf_counter()
+        print(f"iter {i}: forward host {1e3 * (t1 - t0):.0f} ms (+{1e3 * (t2 - t1):.0f} ms GPU tail, {n1 - n0} launches, {fn.n_fwd} ops), "
+              f"backward host {1e3 * (t3 - t2):.0f} ms (+{1e3 * (t4 - t3):.0f} ms GPU tail, {n2 - n1} launches), adam {1e3 * (t5 - t4):.1f} ms, "
+              f"total {1e3 * (t5 - t0):.0f} ms = {S / (t5 - t0):.1f} scenes/s, peak memory {torch.cuda.max_memory_allocated() / 2 ** 30:.1f} GiB, "
+              f"loss {float(out['loss']):.4f}", flush=True)
+
+
+if __name__ == "__main__":
+    main()

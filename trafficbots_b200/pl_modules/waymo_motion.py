@@ -171,6 +171,23 @@ class WaymoMotion(_Base):
         self._param_list = None
         self._param_ptrs = None
         self._step_ctx = None
+        self._train_state = None
+        self.__dict__["automatic_optimization"] = True  # False: training_step leaves the gradients in p.grad and stops there
+        tm = dict(training_metrics or {})
+        defaults = dict(w_vae_kl=0.1, kl_balance_scale=-1, kl_free_nats=0.01, kl_for_unseen_agent=True, w_diffbar_reward=1.0, w_goal=1.0,
+                        w_relevant_agent=0, p_loss_for_irrelevant=-1.0, loss_for_teacher_forcing=True, step_training_start=10)
+        for k, v in defaults.items():  # the loss of train/graph.py implements the default TrainingMetrics configuration
+            if k in tm and tm[k] != v and not (isinstance(v, float) and abs(float(tm[k]) - v) < 1e-12):
+                raise tb_config.UnsupportedConfig(f"training_metrics.{k}={tm[k]!r} (supported: {v!r})")
+        if step_detach_hidden > 0 or p_drop_hidden > 0 or not training_deterministic_action:
+            raise tb_config.UnsupportedConfig("step_detach_hidden / p_drop_hidden / stochastic training actions are not supported")
+        opt, sch = dict(optimizer or {}), dict(lr_scheduler or {})
+        if opt.get("_target_", "torch.optim.Adam") != "torch.optim.Adam" or sch.get("_target_", "torch.optim.lr_scheduler.StepLR") != \
+                "torch.optim.lr_scheduler.StepLR":
+            raise tb_config.UnsupportedConfig("optimizer / lr_scheduler other than Adam / StepLR")
+        self._train_hparams = dict(lr=float(opt.get("lr", 3e-4)), lr_goal=float(lr_goal), max_grad_norm=5.0,
+                                   p_training_rollout_prior=float(p_training_rollout_prior), lr_gamma=float(sch.get("gamma", 0.5)),
+                                   lr_step_size=int(sch.get("step_size", 7)))
 
     # ------------------------------------------------------------------------------------------------ engine / parameters
     def _param_version(self):
@@ -373,6 +390,10 @@ class WaymoMotion(_Base):
         for sink in self.metric_sinks:
             sink(name, **tensors)
 
+    if _Base is nn.Module:  # LightningModule.log stand-in: the last value of every logged key (device scalars are not synchronised)
+        def log(self, name: str, value, **kw) -> None:
+            self.__dict__.setdefault("logged", {})[name] = value
+
     @torch.no_grad()
     def validation_step(self, batch: Dict[str, Tensor], batch_idx: int = 0) -> Dict:
         """waymo_motion.py:574-733 without the video logging: pre_processing, the three `encode_input_features` calls (the
@@ -464,13 +485,71 @@ class WaymoMotion(_Base):
                    scenario_yaw=batch.get("scenario_yaw"), scenario_id=batch.get("scenario_id"))
         return {"joint_future_pred": buf, "pred_dict": pred_dict, "goal_sample": goal_sample, "goal_log_probs": goal_log_probs}
 
+    # ------------------------------------------------------------------------------------------------ training
+    def train_state(self):
+        """flat parameter / gradient / Adam buffers of the training path (`train.trainer.TrainState`), created on first use
+        from the current parameters.  From then on every `nn.Parameter` of this module is a VIEW into the flat parameter buffer
+        and its `.grad` a view into the flat gradient buffer, so `state_dict()`, checkpoints, torch optimizers and the
+        inference engine all see the trained values."""
+        if self._train_state is None:
+            from ..train.trainer import TrainState
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise nt.TbError("trafficbots_b200.WaymoMotion must live on a CUDA device (no CPU implementation of the training path)")
+            hp = self._train_hparams
+            ts = TrainState(self.state_dict(), device=dev, lr=hp["lr"], lr_goal=hp["lr_goal"], max_grad_norm=hp["max_grad_norm"],
+                            p_rollout_prior=hp["p_training_rollout_prior"])
+            named = dict(self.named_parameters())
+            for k, view in ts.params.t.items():
+                named[k].data = view
+                named[k].requires_grad_(True)
+                named[k].grad = ts.params.g[k]
+            self._train_state = ts
+            self.mark_params_dirty()
+        return self._train_state
+
     def training_step(self, batch: Dict[str, Tensor], batch_idx: int = 0):
-        """waymo_motion.py:356-418.  The forward of the training step runs on this path (posterior latent, teacher-forced then
-        closed-loop `reactive_replay`), but back-propagation through the fused rollout (`tb_rollout_backward`) is
-        not implemented: parameters are `requires_grad=False` and training must use the reference implementation."""
-        raise tb_config.UnsupportedConfig("training_step: the fused rollout has no backward pass (BASELINE.json configs[3] is out of "
-                                          "this implementation's scope); train with the reference, evaluate / test with this module")
+        """waymo_motion.py:356-418 on the raw episode batch (`agent/*`, `tl_stop/*`, `map/*`, `agent/dest`, ...: the keys the
+        reference's data module delivers; the re-keying of `pre_processing` is folded into `train/graph.py`).  Runs the forward
+        AND the backward of the step (the gradients are in `p.grad` of every parameter when it returns, like after Lightning's
+        `loss.backward()`), and -- with `self.automatic_optimization` left True -- also what the Lightning trainer does next:
+        gradient averaging over the data-parallel ranks (one NCCL all-reduce of the flat buffer), `clip_grad_norm_` at
+        `gradient_clip_val` (configs/trainer/default.yaml:12) and the Adam step (:955-973).  Dropout is not implemented: the
+        step is the reference's with every dropout probability at 0.  Returns the loss (device scalar); the terms of
+        `TrainingMetrics.compute` go to `self.log` as `training/*`."""
+        ts = self.train_state()
+        out = ts.forward_backward(batch)
+        if self.automatic_optimization:
+            ts.all_reduce_grads()
+            out["grad_sq_norm"] = ts.optimizer_step()
+            self.mark_params_dirty()  # the inference engine re-packs its weight blob on its next use
+        for k in ("loss", "vae_kl", "diffbar_reward", "goal_loss"):
+            self.log(f"training/{k}", out[k], on_step=True)
+        return out["loss"]
 
     def configure_optimizers(self):
-        raise tb_config.UnsupportedConfig("configure_optimizers: inference-only module (see training_step)")
+        """waymo_motion.py:955-973: Adam with a second parameter group (`lr_goal`) for the goal predictor and StepLR per epoch.
+        Returns handles on the fused flat-buffer optimizer (the step itself runs inside `training_step`)."""
+        ts = self.train_state()
+        hp = self._train_hparams
 
+        class _FlatAdam:
+            param_groups = [{"lr": hp["lr"], "name": "model"}, {"lr": hp["lr_goal"], "name": "goal_predictor"}]
+
+            def step(self_inner):
+                ts.optimizer_step()
+                self.mark_params_dirty()
+
+            def zero_grad(self_inner, set_to_none: bool = False):
+                ts.flat_g.zero_()
+
+        class _StepLR:
+            def __init__(self_inner):
+                self_inner.epoch = 0
+
+            def step(self_inner):
+                self_inner.epoch += 1
+                if self_inner.epoch % hp["lr_step_size"] == 0:
+                    ts.ops.scale_(ts.lr, hp["lr_gamma"])
+
+        return [_FlatAdam()], [{"scheduler": _StepLR(), "monitor": "val/loss", "interval": "epoch", "frequency": 1, "strict": True}]
