@@ -52,5 +52,40 @@ def main():
               f"loss {float(out['loss']):.4f}", flush=True)
 
 
+def graph_mode():
+    S = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    A = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    P = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+    rep = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+    dev = "cuda:0"
+    ts = trainer.TrainState(weights.init_state_dict(2023), device=dev)
+    ts.ops.check = False
+    batch = {k: v.to(dev) for k, v in synthetic.make_batch(S, n_agent=A, n_pl=P, seed=7).items()}
+    torch.manual_seed(0)
+    t0 = time.perf_counter()
+    ts.capture(batch)
+    eager = ts.forward_backward(batch, torch.zeros(S, A, 16), False)
+    g_eager = ts.flat_g.clone()
+    out = ts.replay(batch, torch.zeros(S, A, 16), False)
+    torch.cuda.synchronize()
+    print(f"capture (posterior graph): {time.perf_counter() - t0:.1f} s; graph == eager: loss {float(out['loss']):.6f} vs "
+          f"{float(eager['loss']):.6f}, max grad diff {float((ts.flat_g - g_eager).abs().max()):.2e} "
+          f"(scale {float(g_eager.abs().max()):.2e}); memory reserved {torch.cuda.memory_reserved() / 2 ** 30:.1f} GiB", flush=True)
+    for i in range(rep):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        eps = torch.randn(S, A, 16)
+        e0.record()
+        out = ts.replay(batch, eps, False)
+        e1.record()
+        ts.optimizer_step()
+        e2.record()
+        torch.cuda.synchronize()
+        print(f"graph iter {i}: fwd+bwd {e0.elapsed_time(e1):.1f} ms, adam {e1.elapsed_time(e2):.2f} ms -> {S / (e0.elapsed_time(e2) * 1e-3):.1f} "
+              f"scenes/s, loss {float(out['loss']):.4f}", flush=True)
+
+
 if __name__ == "__main__":
+    if os.environ.get("TB_TRAIN_GRAPH"):
+        graph_mode()
+        sys.exit(0)
     main()

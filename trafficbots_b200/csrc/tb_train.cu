@@ -24,19 +24,21 @@ constexpr int TR_DH = 32;
 constexpr int GM = 64, GN = 64, GK = 16;
 enum { EPI_BIAS = 0, EPI_STORE = 1, EPI_ATOMIC = 2 };
 
+// `rowsum` (optional, EPI_ATOMIC tiles with tile_j == 0 only): rowsum[i] += sum_k A(i, k) -- the bias gradient of a Linear
 template <bool A_KCONTIG, bool B_JCONTIG, int EPI>
-__global__ void __launch_bounds__(256) k_tr_gemm(const float* __restrict__ a, long sai, long sak, const float* __restrict__ ym,
-                                                 const float* __restrict__ b, long sbk, long sbj, float* __restrict__ c, long ldc,
-                                                 const float* __restrict__ bias, int relu, long ni, int nj, long nk, long k_chunk) {
-  __shared__ float As[GK][GM + 4];
-  __shared__ float Bs[GK][GN + 4];
+__device__ __forceinline__ void gemm_tile(float (&As)[GK][GM + 4], float (&Bs)[GK][GN + 4], const float* __restrict__ a, long sai,
+                                          long sak, const float* __restrict__ ym, const float* __restrict__ b, long sbk, long sbj,
+                                          float* __restrict__ c, long ldc, const float* __restrict__ bias, int relu, long ni, int nj,
+                                          long nk, long k_chunk, long tile_i, int tile_j, long tile_z, float* __restrict__ rowsum) {
   const int tid = threadIdx.x;
-  const long i0 = (long)blockIdx.x * GM;
-  const int j0 = blockIdx.y * GN;
-  const long k_lo = (long)blockIdx.z * k_chunk;
+  const long i0 = tile_i * GM;
+  const int j0 = tile_j * GN;
+  const long k_lo = tile_z * k_chunk;
   const long k_hi = min(nk, k_lo + k_chunk);
   const int ti = tid / 16, tj = tid % 16;  // 16 x 16 threads, 4 x 4 outputs each
   float acc[4][4] = {};
+  float rs = 0.f;
+  const bool do_rowsum = (EPI == EPI_ATOMIC) && rowsum != nullptr && tile_j == 0;
   for (long k0 = k_lo; k0 < k_hi; k0 += GK) {
     // ---- A tile [GM x GK] ----
     if (A_KCONTIG) {
@@ -85,6 +87,10 @@ __global__ void __launch_bounds__(256) k_tr_gemm(const float* __restrict__ a, lo
       }
     }
     __syncthreads();
+    if (do_rowsum && tid < GM) {
+#pragma unroll
+      for (int kk = 0; kk < GK; ++kk) rs += As[kk][tid];
+    }
 #pragma unroll
     for (int kk = 0; kk < GK; ++kk) {
       const float4 av = *reinterpret_cast<const float4*>(&As[kk][ti * 4]);
@@ -117,20 +123,38 @@ __global__ void __launch_bounds__(256) k_tr_gemm(const float* __restrict__ a, lo
       }
     }
   }
+  if (do_rowsum && tid < GM && i0 + tid < ni) atomicAdd(&rowsum[i0 + tid], rs);
 }
 
-// column sums of dy (* relu mask) -> db (atomic)
-__global__ void __launch_bounds__(256) k_tr_colsum(const float* __restrict__ dy, const float* __restrict__ ym, long M, int N,
-                                                   float* __restrict__ db, long rows_per_block) {
-  const long m_lo = (long)blockIdx.x * rows_per_block, m_hi = min(M, m_lo + rows_per_block);
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    float s = 0.f;
-    for (long m = m_lo; m < m_hi; ++m) {
-      float v = dy[m * N + n];
-      if (ym && !(ym[m * N + n] > 0.f)) v = 0.f;
-      s += v;
-    }
-    atomicAdd(&db[n], s);
+template <bool A_KCONTIG, bool B_JCONTIG, int EPI>
+__global__ void __launch_bounds__(256) k_tr_gemm(const float* __restrict__ a, long sai, long sak, const float* __restrict__ ym,
+                                                 const float* __restrict__ b, long sbk, long sbj, float* __restrict__ c, long ldc,
+                                                 const float* __restrict__ bias, int relu, long ni, int nj, long nk, long k_chunk) {
+  __shared__ float As[GK][GM + 4];
+  __shared__ float Bs[GK][GN + 4];
+  gemm_tile<A_KCONTIG, B_JCONTIG, EPI>(As, Bs, a, sai, sak, ym, b, sbk, sbj, c, ldc, bias, relu, ni, nj, nk, k_chunk, blockIdx.x,
+                                       blockIdx.y, blockIdx.z, nullptr);
+}
+
+// backward of a Linear in ONE launch: CTAs [0, n_dx) compute tiles of dX = dY' W, the others tiles of dW += dY'^T X (rows split
+// over `nz` chunks, partial sums added atomically) and, in the first column tile, db += colsum(dY');  dY' = dY * relu'(Y)
+__global__ void __launch_bounds__(256) k_tr_linear_bwd(const float* __restrict__ dy, const float* __restrict__ x,
+                                                       const float* __restrict__ w, long ldw, const float* __restrict__ ym, long M,
+                                                       int K, int N, float* __restrict__ dx, float* __restrict__ dw, long lddw,
+                                                       float* __restrict__ db, int n_dx, int dx_tiles_j, int dw_tiles_i,
+                                                       int dw_tiles_j, long chunk) {
+  __shared__ float As[GK][GM + 4];
+  __shared__ float Bs[GK][GN + 4];
+  int t = blockIdx.x;
+  if (t < n_dx) {
+    gemm_tile<true, true, EPI_STORE>(As, Bs, dy, N, 1, ym, w, ldw, 1, dx, K, nullptr, 0, M, K, N, N, t / dx_tiles_j, t % dx_tiles_j, 0,
+                                     nullptr);
+  } else {
+    t -= n_dx;
+    const int per_z = dw_tiles_i * dw_tiles_j;
+    const int z = t / per_z, r = t % per_z;
+    gemm_tile<false, true, EPI_ATOMIC>(As, Bs, dy, 1, N, ym, x, K, 1, dw, lddw, nullptr, 0, N, K, M, chunk, r / dw_tiles_j,
+                                       r % dw_tiles_j, z, db);
   }
 }
 
@@ -948,28 +972,25 @@ int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_
   TR_CHECK(dy && x && w, TB_ERR_NULL);
   TR_CHECK(M > 0 && K > 0 && N > 0 && (!relu || y), TB_ERR_BAD_SHAPE);
   const float* ym = relu ? y : nullptr;
-  if (dx) {
-    dim3 grid((unsigned)((M + GM - 1) / GM), (K + GN - 1) / GN, 1);
-    k_tr_gemm<true, true, EPI_STORE><<<grid, 256, 0, st>>>(dy, N, 1, ym, w, ldw, 1, dx, K, nullptr, 0, M, K, N, N);
-    count_launch();
+  TR_CHECK(dw || !db, TB_ERR_BAD_SHAPE);  // the bias gradient rides on the weight-gradient tiles
+  const int dx_tiles_j = (K + GN - 1) / GN;
+  const long n_dx = dx ? ((M + GM - 1) / GM) * dx_tiles_j : 0;
+  const int dw_tiles_i = (N + GM - 1) / GM, dw_tiles_j = (K + GN - 1) / GN;
+  long nz = 0, chunk = 0;
+  if (dw) {  // enough row chunks to fill the GPU twice, at least 128 rows each
+    const long tiles = (long)dw_tiles_i * dw_tiles_j;
+    nz = (296 + tiles - 1) / tiles;
+    const long nz_max = (M + 127) / 128;
+    if (nz > nz_max) nz = nz_max;
+    if (nz < 1) nz = 1;
+    chunk = ((M + nz - 1) / nz + GK - 1) / GK * GK;
+    nz = (M + chunk - 1) / chunk;
   }
-  if (dw) {
-    // C[n, k] += sum_m dy[m, n] x[m, k]: contraction over the rows, split over gridDim.z
-    long chunk = 2048;
-    long nz = (M + chunk - 1) / chunk;
-    if (nz > 4096) {
-      chunk = ((M + 4095) / 4096 + GK - 1) / GK * GK;
-      nz = (M + chunk - 1) / chunk;
-    }
-    dim3 grid((N + GM - 1) / GM, (K + GN - 1) / GN, (unsigned)nz);
-    k_tr_gemm<false, true, EPI_ATOMIC><<<grid, 256, 0, st>>>(dy, 1, N, ym, x, K, 1, dw, lddw, nullptr, 0, N, K, M, chunk);
-    count_launch();
-  }
-  if (db) {
-    const long rows = 512;
-    k_tr_colsum<<<(unsigned)((M + rows - 1) / rows), 256, 0, st>>>(dy, ym, M, N, db, rows);
-    count_launch();
-  }
+  const long total = n_dx + nz * dw_tiles_i * dw_tiles_j;
+  TR_CHECK(total > 0 && total < 2147483647L, TB_ERR_BAD_SHAPE);
+  k_tr_linear_bwd<<<(unsigned)total, 256, 0, st>>>(dy, x, w, ldw, ym, M, K, N, dx, dw, lddw, db, (int)n_dx, dx_tiles_j, dw_tiles_i,
+                                                   dw_tiles_j, chunk);
+  count_launch();
   return launch_status();
 }
 

@@ -499,7 +499,7 @@ class WaymoMotion(_Base):
             hp = self._train_hparams
             ts = TrainState(self.state_dict(), device=dev, lr=hp["lr"], lr_goal=hp["lr_goal"], max_grad_norm=hp["max_grad_norm"],
                             p_rollout_prior=hp["p_training_rollout_prior"])
-            named = dict(self.named_parameters())
+            named = dict(self.named_parameters(remove_duplicate=False))  # shared blocks appear under both of their names
             for k, view in ts.params.t.items():
                 named[k].data = view
                 named[k].requires_grad_(True)
@@ -518,7 +518,10 @@ class WaymoMotion(_Base):
         step is the reference's with every dropout probability at 0.  Returns the loss (device scalar); the terms of
         `TrainingMetrics.compute` go to `self.log` as `training/*`."""
         ts = self.train_state()
-        out = ts.forward_backward(batch)
+        if ts._static_batch is not None and all(tuple(batch[k].shape) == tuple(v.shape) for k, v in ts._static_batch.items()):
+            out = ts.replay(batch)  # `train_state().capture(batch)` was called for this batch shape: whole-step CUDA graph
+        else:
+            out = ts.forward_backward({k: v.to(ts.device, non_blocking=True) for k, v in batch.items()})
         if self.automatic_optimization:
             ts.all_reduce_grads()
             out["grad_sq_norm"] = ts.optimizer_step()

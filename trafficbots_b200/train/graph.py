@@ -219,9 +219,9 @@ def dest_masks(batch: Dict[str, Tensor], pl_valid: Tensor) -> Tensor:
     """pair_ok [S,A,P] = not masked to -inf by `DestPredictor.forward` (models/goal_manager.py:228-246,328-329)."""
     mt, at = batch["map/type"].bool(), batch["agent/type"].bool()
     type_ok = pl_valid.bool() & mt[:, :, :5].any(-1)
-    m_veh = at[:, :, [0]] & mt[:, :, 3].unsqueeze(1)
-    m_ped = at[:, :, [1]] & mt[:, :, :4].any(-1).unsqueeze(1)
-    m_cyc = at[:, :, [2]] & mt[:, :, :3].any(-1).unsqueeze(1)
+    m_veh = at[:, :, 0:1] & mt[:, :, 3].unsqueeze(1)
+    m_ped = at[:, :, 1:2] & mt[:, :, :4].any(-1).unsqueeze(1)
+    m_cyc = at[:, :, 2:3] & mt[:, :, :3].any(-1).unsqueeze(1)
     return (type_ok.unsqueeze(1) & ~(m_veh | m_ped | m_cyc)).to(U8).contiguous()
 
 
@@ -280,23 +280,24 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
     # ---- latent encoders (:382-383) ----
     fr_prior = list(range(0, n_hist, down))
     Tp = len(fr_prior)
-    idx_p = (torch.arange(S, device=dev)[:, None, None] * n_hist + torch.tensor(fr_prior, device=dev)[None, :, None]) * A \
+    fr_p = torch.arange(0, n_hist, down, device=dev)
+    idx_p = (torch.arange(S, device=dev)[:, None, None] * n_hist + fr_p[None, :, None]) * A \
         + torch.arange(A, device=dev)[None, None, :]
     af_prior = f.gather_rows(af_hist, idx_p.reshape(-1))
-    idx_tl = (torch.tensor(fr_prior, device=dev)[None, :, None] * S + torch.arange(S, device=dev)[:, None, None]) * TL \
+    idx_tl = (fr_p[None, :, None] * S + torch.arange(S, device=dev)[:, None, None]) * TL \
         + torch.arange(TL, device=dev)[None, None, :]
     kv_tl_prior = [f.gather_rows(kv, idx_tl.reshape(-1)) for kv in kv_tl_hist]
-    prior_mean, prior_valid = m.latent_encoder("prior", af_prior, hv[:, fr_prior], kv_map, pl_valid, kv_tl_prior,
-                                               batch["tl_stop/valid"][:, fr_prior], S, Tp, A, P, TL)
+    prior_mean, prior_valid = m.latent_encoder("prior", af_prior, hv[:, ::down], kv_map, pl_valid, kv_tl_prior,
+                                               batch["tl_stop/valid"][:, 0:n_hist:down], S, Tp, A, P, TL)
     fr_post = list(range(0, T_gt, down))
     Tq = len(fr_post)
-    sel = lambda k: batch[k][:, fr_post]  # noqa: E731
+    sel = lambda k: batch[k][:, ::down]  # noqa: E731  (frames 0, 5, ..., 90)
     af_post = m.encode_agents(sel("agent/valid"), sel("agent/pos"), sel("agent/yaw_bbox"), sel("agent/vel"), sel("agent/spd"),
                               sel("agent/yaw_rate"), sel("agent/acc"), batch["agent/size"].unsqueeze(1).expand(-1, Tq, -1, -1),
                               batch["agent/type"].unsqueeze(1).expand(-1, Tq, -1, -1))
     tl_post = m.encode_tl(sel("tl_stop/valid"), sel("tl_stop/state"), sel("tl_stop/pos"), sel("tl_stop/dir"))  # [S*Tq*TL, D]
     kv_tl_post = [m.kv_project(f"model.transformer_as2tl.layers.{i}", tl_post) for i in range(3)]
-    post_mean, post_valid = m.latent_encoder("post", af_post, gv[:, fr_post], kv_map, pl_valid, kv_tl_post,
+    post_mean, post_valid = m.latent_encoder("post", af_post, gv[:, ::down], kv_map, pl_valid, kv_tl_post,
                                              sel("tl_stop/valid"), S, Tq, A, P, TL)
     ls_prior = params("model.latent_encoder.latent_prior_dist.log_std")
     ls_post = params("model.latent_encoder.latent_post_dist.log_std")
