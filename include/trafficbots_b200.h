@@ -448,15 +448,17 @@ int32_t tb_tc_selftest(const float* a, int32_t block, const float* packed, float
  *                 utils/traffic_rule_checker.py:101-119,364-410 + models/goal_manager.py:155-161
  *   sq_norm, adam_step : torch.nn.utils.clip_grad_norm_ + torch.optim.Adam on the flat parameter buffer
  * ------------------------------------------------------------------------------------------------------------------ */
-int32_t tb_tr_linear_fwd(const float* x, int64_t M, int32_t K, const float* w, int64_t ldw, int32_t N, const float* bias, int32_t relu, float* y, void* stream);
-/* dx = (dy * relu') W; dw += (dy * relu')^T x; db += colsum(dy * relu').  dx / dw / db may be NULL (skipped). */
-int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_t ldw, const float* y, int32_t relu, int64_t M, int32_t K, int32_t N, float* dx, float* dw, int64_t lddw, float* db, void* stream);
+/* y = (relu(x W^T + bias) * keep_lin[row] + res) * keep_out[row]; bias / keep_lin / res / keep_out may be NULL */
+int32_t tb_tr_linear_fwd(const float* x, int64_t M, int32_t K, const float* w, int64_t ldw, int32_t N, const float* bias, int32_t relu, const uint8_t* keep_lin, const float* res, const uint8_t* keep_out, float* y, void* stream);
+/* dx = dY' W; dw += dY'^T x; db += colsum(dY') with dY' = dy * relu'(y) * rm1[row] * rm2[row] (the forward's keep_lin / keep_out; may be NULL).  dx / dw / db may be NULL (skipped); db needs dw. */
+int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_t ldw, const float* y, int32_t relu, const uint8_t* rm1, const uint8_t* rm2, int64_t M, int32_t K, int32_t N, float* dx, float* dw, int64_t lddw, float* db, void* stream);
 int32_t tb_tr_layernorm_fwd(const float* x, const float* w, const float* b, int32_t relu, int64_t M, int32_t D, float* y, float* stats, void* stream);
 int32_t tb_tr_layernorm_bwd(const float* dy, const float* x, const float* w, const float* stats, const float* y, int32_t relu, int64_t M, int32_t D, float* dx, float* dw, float* db, void* stream);
 int32_t tb_tr_attention_fwd(const float* q, const float* kv, const uint8_t* key_valid, int32_t eye, int32_t B, int32_t S, int32_t T, float* o, float* p, uint8_t* dead, void* stream);
 /* dq must be zero-initialised by the caller (partials are added atomically); dkv is overwritten */
 int32_t tb_tr_attention_bwd(const float* dout, const float* q, const float* kv, const float* p, const float* o, int32_t B, int32_t S, int32_t T, float* dq, float* dkv, void* stream);
-int32_t tb_tr_add_mask(const float* a, const float* b, const uint8_t* keep, int64_t M, int32_t N, float* y, void* stream);
+/* y = (a * keep_a[row] + b) * keep[row]; keep_a / b / keep may be NULL */
+int32_t tb_tr_add_mask(const float* a, const uint8_t* keep_a, const float* b, const uint8_t* keep, int64_t M, int32_t N, float* y, void* stream);
 int32_t tb_tr_axpy(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t M, int32_t N, void* stream);
 int32_t tb_tr_select_rows(const uint8_t* mask, const float* a, const float* b, int64_t M, int32_t N, float* y, void* stream);
 int32_t tb_tr_select_rows_bwd(const uint8_t* mask, const float* dy, int64_t M, int32_t N, float* da, float* db, void* stream);

@@ -53,15 +53,26 @@ class OracleOps:
         x *= alpha
 
     # ---- Linear (+ReLU) : models/modules/mlp.py, attention.py in/out projections ----
-    def linear_fwd(self, x: Tensor, w: Tensor, b: Optional[Tensor], relu: bool) -> Tensor:
+    def linear_fwd(self, x: Tensor, w: Tensor, b: Optional[Tensor], relu: bool, keep_lin=None, res=None, keep_out=None) -> Tensor:
+        """y = (relu(x W^T + b) * keep_lin[row] + res) * keep_out[row] -- the optional tail is the residual / row-mask epilogue
+        of a transformer sub-layer (transformer.py:203,220,236-237; attention.py:144-146)."""
         y = F.linear(x, w, b)
-        return torch.relu(y) if relu else y
+        y = torch.relu(y) if relu else y
+        if keep_lin is not None:
+            y = y * keep_lin.to(y.dtype).unsqueeze(-1)
+        if res is not None:
+            y = y + res
+        if keep_out is not None:
+            y = y * keep_out.to(y.dtype).unsqueeze(-1)
+        return y
 
-    def linear_bwd(self, dy, x, w, b, y, relu, dw, db, need_dx: bool):
+    def linear_bwd(self, dy, x, w, b, y, relu, dw, db, need_dx: bool, keep_lin=None, keep_out=None):
+        """gradients of the Linear part (the residual's gradient is dy * keep_out, formed by the caller)."""
         x_, w_, b_ = _req(x, w, b)
-        gx, gw, gb = _grads(self.linear_fwd(x_, w_, b_, relu), [x_, w_, b_], dy)
-        dw += gw
-        if b is not None:
+        gx, gw, gb = _grads(self.linear_fwd(x_, w_, b_, relu, keep_lin, None, keep_out), [x_, w_, b_], dy)
+        if dw is not None:
+            dw += gw
+        if b is not None and db is not None:
             db += gb
         return gx if need_dx else None
 
@@ -105,12 +116,15 @@ class OracleOps:
         return gq, gkv
 
     # ---- elementwise glue ----
-    def add_mask_fwd(self, a, b, keep):
-        y = a if b is None else a + b
+    def add_mask_fwd(self, a, b, keep, keep_a=None):
+        """(a * keep_a[row] + b) * keep[row]"""
+        y = a if keep_a is None else a * keep_a.to(a.dtype).unsqueeze(-1)
+        y = y if b is None else y + b
         return y if keep is None else y * keep.to(y.dtype).unsqueeze(-1)
 
-    def add_mask_bwd(self, dy, keep):
-        return dy if keep is None else dy * keep.to(dy.dtype).unsqueeze(-1)
+    def add_mask_bwd(self, dy, keep, keep_a=None):
+        d = dy if keep is None else dy * keep.to(dy.dtype).unsqueeze(-1)
+        return d if keep_a is None else d * keep_a.to(dy.dtype).unsqueeze(-1)
 
     def select_rows_fwd(self, mask, a, b):
         return torch.where(mask.bool().unsqueeze(-1), a, b)

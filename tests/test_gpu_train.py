@@ -65,6 +65,26 @@ def test_linear(ops, M, K, N, relu, strided):
         assert float((dwf[:, : K // 2] - 0.5).abs().max()) == 0.0
 
 
+def test_linear_fused_epilogue(ops):
+    """y = (x W^T + b) * keep_lin + res) * keep_out and the row-masked backward (dead attention rows, residual, invalid rows)."""
+    torch.manual_seed(11)
+    M, K, N = 203, 128, 128
+    x, w, b, res, dy = torch.randn(M, K), torch.randn(N, K) / K ** 0.5, torch.randn(N) * 0.1, torch.randn(M, N), torch.randn(M, N)
+    kl, ko = (torch.rand(M) < 0.7).to(torch.uint8), (torch.rand(M) < 0.8).to(torch.uint8)
+    for keep_lin, r, keep_out in ((kl, res, None), (None, res, ko), (kl, res, ko), (kl, None, None)):
+        y_ref = ORC.linear_fwd(x, w, b, False, keep_lin, r, keep_out)
+        dw_ref, db_ref = torch.zeros_like(w), torch.zeros(N)
+        dx_ref = ORC.linear_bwd(dy, x, w, b, y_ref, False, dw_ref, db_ref, True, keep_lin, keep_out)
+        xg, wg, bg, dyg, klg, rg, kog = g(x, w, b, dy, keep_lin, r, keep_out)
+        y = ops.linear_fwd(xg, wg, bg, False, klg, rg, kog)
+        close(y, y_ref, what="y")
+        dwg, dbg = torch.zeros_like(wg), torch.zeros(N, device=DEV)
+        dx = ops.linear_bwd(dyg, xg, wg, bg, y, False, dwg, dbg, True, klg, kog)
+        close(dx, dx_ref, what="dx")
+        close(dwg, dw_ref, tol=5e-5, what="dw")
+        close(dbg, db_ref, tol=5e-5, what="db")
+
+
 @pytest.mark.parametrize("M,relu", [(5, False), (777, True)])
 def test_layernorm(ops, M, relu):
     torch.manual_seed(M)
@@ -116,6 +136,9 @@ def test_glue_ops(ops):
     close(ops.add_mask_fwd(ag, None, kg), ORC.add_mask_fwd(a, None, keep))
     close(ops.add_mask_fwd(ag, bg, None), ORC.add_mask_fwd(a, b, None))
     close(ops.add_mask_bwd(dyg, kg), ORC.add_mask_bwd(dy, keep))
+    keep2 = (torch.rand(M) < 0.5).to(torch.uint8)
+    close(ops.add_mask_fwd(ag, bg, kg, keep2.to(DEV)), ORC.add_mask_fwd(a, b, keep, keep2))
+    close(ops.add_mask_bwd(dyg, kg, keep2.to(DEV)), ORC.add_mask_bwd(dy, keep, keep2))
     close(ops.select_rows_fwd(kg, ag, bg), ORC.select_rows_fwd(keep, a, b))
     for x, y in zip(ops.select_rows_bwd(dyg, kg), ORC.select_rows_bwd(dy, keep)):
         close(x, y)

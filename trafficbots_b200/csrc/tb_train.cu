@@ -24,12 +24,28 @@ constexpr int TR_DH = 32;
 constexpr int GM = 64, GN = 64, GK = 16;
 enum { EPI_BIAS = 0, EPI_STORE = 1, EPI_ATOMIC = 2 };
 
-// `rowsum` (optional, EPI_ATOMIC tiles with tile_j == 0 only): rowsum[i] += sum_k A(i, k) -- the bias gradient of a Linear
+// Per-tile options.  A operand: `ym` = ReLU mask source (same indexing as A: element kept where ym > 0), `rm1` / `rm2` = row masks
+// over the M ("sample") dimension of A (uint8, element dropped where 0).  EPI_BIAS epilogue: v = acc + bias; ReLU; v *= keep_lin[i];
+// v += res[i, j]; v *= keep_out[i].  `rowsum` (EPI_ATOMIC tiles with tile_j == 0): rowsum[i] += sum_k A(i, k) (bias gradient).
+struct GemmOpt {
+  const float* ym;
+  const uint8_t* rm1;
+  const uint8_t* rm2;
+  const float* bias;
+  int relu;
+  const uint8_t* keep_lin;
+  const float* res;
+  const uint8_t* keep_out;
+  float* rowsum;
+};
+
+// The next k-slab is fetched into registers while the current one is multiplied out of shared memory (global-load latency
+// hidden behind the FMAs); 16-byte loads where the layout allows.
 template <bool A_KCONTIG, bool B_JCONTIG, int EPI>
 __device__ __forceinline__ void gemm_tile(float (&As)[GK][GM + 4], float (&Bs)[GK][GN + 4], const float* __restrict__ a, long sai,
-                                          long sak, const float* __restrict__ ym, const float* __restrict__ b, long sbk, long sbj,
-                                          float* __restrict__ c, long ldc, const float* __restrict__ bias, int relu, long ni, int nj,
-                                          long nk, long k_chunk, long tile_i, int tile_j, long tile_z, float* __restrict__ rowsum) {
+                                          long sak, const float* __restrict__ b, long sbk, long sbj, float* __restrict__ c, long ldc,
+                                          long ni, int nj, long nk, long k_chunk, long tile_i, int tile_j, long tile_z,
+                                          const GemmOpt& op) {
   const int tid = threadIdx.x;
   const long i0 = tile_i * GM;
   const int j0 = tile_j * GN;
@@ -38,55 +54,117 @@ __device__ __forceinline__ void gemm_tile(float (&As)[GK][GM + 4], float (&Bs)[G
   const int ti = tid / 16, tj = tid % 16;  // 16 x 16 threads, 4 x 4 outputs each
   float acc[4][4] = {};
   float rs = 0.f;
-  const bool do_rowsum = (EPI == EPI_ATOMIC) && rowsum != nullptr && tile_j == 0;
-  for (long k0 = k_lo; k0 < k_hi; k0 += GK) {
-    // ---- A tile [GM x GK] ----
+  const bool do_rowsum = (EPI == EPI_ATOMIC) && op.rowsum != nullptr && tile_j == 0;
+  const float* __restrict__ ym = op.ym;
+  // thread -> element mapping of the two tile loads (4 consecutive elements along the contiguous direction)
+  const int a_r = A_KCONTIG ? tid / 4 : (tid % 16) * 4;   // row (i) offset
+  const int a_k = A_KCONTIG ? (tid % 4) * 4 : tid / 16;   // k offset
+  const int b_j = B_JCONTIG ? (tid % 16) * 4 : tid / 4;
+  const int b_k = B_JCONTIG ? tid / 16 : (tid % 4) * 4;
+  const bool a_vec = A_KCONTIG ? (sak == 1 && (sai & 3) == 0) : (sai == 1 && (sak & 3) == 0);
+  const bool b_vec = B_JCONTIG ? (sbj == 1 && (sbk & 3) == 0) : (sbk == 1 && (sbj & 3) == 0);
+  const bool a_al = a_vec && ((reinterpret_cast<uintptr_t>(a) & 15) == 0) && (!ym || (reinterpret_cast<uintptr_t>(ym) & 15) == 0);
+  const bool b_al = b_vec && ((reinterpret_cast<uintptr_t>(b) & 15) == 0);
+  float ra[4], rb[4];
+
+  auto fetch = [&](long k0) {
+    // ---- A ----
     if (A_KCONTIG) {
-      const int r = tid / 4, kq = (tid % 4) * 4;
-      const long i = i0 + r;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long k = k0 + kq + u;
-        float v = 0.f;
-        if (i < ni && k < k_hi) {
-          v = a[i * sai + k * sak];
-          if (ym && !(ym[i * sai + k * sak] > 0.f)) v = 0.f;
+      const long i = i0 + a_r, k = k0 + a_k;
+      bool row_ok = i < ni;
+      if (row_ok && op.rm1 && !op.rm1[i]) row_ok = false;
+      if (row_ok && op.rm2 && !op.rm2[i]) row_ok = false;
+      if (row_ok && a_al && k + 3 < k_hi) {
+        const float4 v = *reinterpret_cast<const float4*>(a + i * sai + k);
+        ra[0] = v.x, ra[1] = v.y, ra[2] = v.z, ra[3] = v.w;
+        if (ym) {
+          const float4 m = *reinterpret_cast<const float4*>(ym + i * sai + k);
+          if (!(m.x > 0.f)) ra[0] = 0.f;
+          if (!(m.y > 0.f)) ra[1] = 0.f;
+          if (!(m.z > 0.f)) ra[2] = 0.f;
+          if (!(m.w > 0.f)) ra[3] = 0.f;
         }
-        As[kq + u][r] = v;
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float v = 0.f;
+          if (row_ok && k + u < k_hi) {
+            v = a[i * sai + (k + u) * sak];
+            if (ym && !(ym[i * sai + (k + u) * sak] > 0.f)) v = 0.f;
+          }
+          ra[u] = v;
+        }
       }
     } else {
-      const int kk = tid / 16, rq = (tid % 16) * 4;
-      const long k = k0 + kk;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long i = i0 + rq + u;
-        float v = 0.f;
-        if (i < ni && k < k_hi) {
-          v = a[i * sai + k * sak];
-          if (ym && !(ym[i * sai + k * sak] > 0.f)) v = 0.f;
+      const long i = i0 + a_r, k = k0 + a_k;
+      bool k_ok = k < k_hi;
+      if (k_ok && op.rm1 && !op.rm1[k]) k_ok = false;
+      if (k_ok && op.rm2 && !op.rm2[k]) k_ok = false;
+      if (k_ok && a_al && i + 3 < ni) {
+        const float4 v = *reinterpret_cast<const float4*>(a + i + k * sak);
+        ra[0] = v.x, ra[1] = v.y, ra[2] = v.z, ra[3] = v.w;
+        if (ym) {
+          const float4 m = *reinterpret_cast<const float4*>(ym + i + k * sak);
+          if (!(m.x > 0.f)) ra[0] = 0.f;
+          if (!(m.y > 0.f)) ra[1] = 0.f;
+          if (!(m.z > 0.f)) ra[2] = 0.f;
+          if (!(m.w > 0.f)) ra[3] = 0.f;
         }
-        As[kk][rq + u] = v;
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float v = 0.f;
+          if (k_ok && i + u < ni) {
+            v = a[(i + u) * sai + k * sak];
+            if (ym && !(ym[(i + u) * sai + k * sak] > 0.f)) v = 0.f;
+          }
+          ra[u] = v;
+        }
       }
     }
-    // ---- B tile [GK x GN] ----
+    // ---- B ----
     if (B_JCONTIG) {
-      const int kk = tid / 16, jq = (tid % 16) * 4;
-      const long k = k0 + kk;
+      const long k = k0 + b_k;
+      const int jj = j0 + b_j;
+      if (k < k_hi && b_al && jj + 3 < nj) {
+        const float4 v = *reinterpret_cast<const float4*>(b + k * sbk + jj);
+        rb[0] = v.x, rb[1] = v.y, rb[2] = v.z, rb[3] = v.w;
+      } else {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = j0 + jq + u;
-        Bs[kk][jq + u] = (j < nj && k < k_hi) ? b[k * sbk + (long)j * sbj] : 0.f;
+        for (int u = 0; u < 4; ++u) rb[u] = (k < k_hi && jj + u < nj) ? b[k * sbk + (long)(jj + u) * sbj] : 0.f;
       }
     } else {
-      const int r = tid / 4, kq = (tid % 4) * 4;
-      const int j = j0 + r;
+      const long k = k0 + b_k;
+      const int jj = j0 + b_j;
+      if (jj < nj && b_al && k + 3 < k_hi) {
+        const float4 v = *reinterpret_cast<const float4*>(b + k + (long)jj * sbj);
+        rb[0] = v.x, rb[1] = v.y, rb[2] = v.z, rb[3] = v.w;
+      } else {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long k = k0 + kq + u;
-        Bs[kq + u][r] = (j < nj && k < k_hi) ? b[k * sbk + (long)j * sbj] : 0.f;
+        for (int u = 0; u < 4; ++u) rb[u] = (jj < nj && k + u < k_hi) ? b[(k + u) * sbk + (long)jj * sbj] : 0.f;
       }
     }
+  };
+  auto stash = [&]() {
+    if (A_KCONTIG) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) As[a_k + u][a_r] = ra[u];
+    } else {
+      *reinterpret_cast<float4*>(&As[a_k][a_r]) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+    }
+    if (B_JCONTIG) {
+      *reinterpret_cast<float4*>(&Bs[b_k][b_j]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) Bs[b_k + u][b_j] = rb[u];
+    }
+  };
+
+  if (k_lo < k_hi) fetch(k_lo);
+  for (long k0 = k_lo; k0 < k_hi; k0 += GK) {
+    stash();
     __syncthreads();
+    if (k0 + GK < k_hi) fetch(k0 + GK);
     if (do_rowsum && tid < GM) {
 #pragma unroll
       for (int kk = 0; kk < GK; ++kk) rs += As[kk][tid];
@@ -107,14 +185,22 @@ __device__ __forceinline__ void gemm_tile(float (&As)[GK][GM + 4], float (&Bs)[G
   for (int x = 0; x < 4; ++x) {
     const long i = i0 + ti * 4 + x;
     if (i >= ni) continue;
+    float kl = 1.f, ko = 1.f;
+    if (EPI == EPI_BIAS) {
+      if (op.keep_lin && !op.keep_lin[i]) kl = 0.f;
+      if (op.keep_out && !op.keep_out[i]) ko = 0.f;
+    }
 #pragma unroll
     for (int y = 0; y < 4; ++y) {
       const int j = j0 + tj * 4 + y;
       if (j >= nj) continue;
       float v = acc[x][y];
       if (EPI == EPI_BIAS) {
-        if (bias) v += bias[j];
-        if (relu) v = fmaxf(v, 0.f);
+        if (op.bias) v += op.bias[j];
+        if (op.relu) v = fmaxf(v, 0.f);
+        v *= kl;
+        if (op.res) v += op.res[i * ldc + j];
+        v *= ko;
         c[i * ldc + j] = v;
       } else if (EPI == EPI_STORE) {
         c[i * ldc + j] = v;
@@ -123,38 +209,36 @@ __device__ __forceinline__ void gemm_tile(float (&As)[GK][GM + 4], float (&Bs)[G
       }
     }
   }
-  if (do_rowsum && tid < GM && i0 + tid < ni) atomicAdd(&rowsum[i0 + tid], rs);
+  if (do_rowsum && tid < GM && i0 + tid < ni) atomicAdd(&op.rowsum[i0 + tid], rs);
 }
 
 template <bool A_KCONTIG, bool B_JCONTIG, int EPI>
-__global__ void __launch_bounds__(256) k_tr_gemm(const float* __restrict__ a, long sai, long sak, const float* __restrict__ ym,
-                                                 const float* __restrict__ b, long sbk, long sbj, float* __restrict__ c, long ldc,
-                                                 const float* __restrict__ bias, int relu, long ni, int nj, long nk, long k_chunk) {
-  __shared__ float As[GK][GM + 4];
-  __shared__ float Bs[GK][GN + 4];
-  gemm_tile<A_KCONTIG, B_JCONTIG, EPI>(As, Bs, a, sai, sak, ym, b, sbk, sbj, c, ldc, bias, relu, ni, nj, nk, k_chunk, blockIdx.x,
-                                       blockIdx.y, blockIdx.z, nullptr);
+__global__ void __launch_bounds__(256) k_tr_gemm(const float* __restrict__ a, long sai, long sak, const float* __restrict__ b, long sbk,
+                                                 long sbj, float* __restrict__ c, long ldc, long ni, int nj, long nk, long k_chunk,
+                                                 GemmOpt op) {
+  __shared__ __align__(16) float As[GK][GM + 4];
+  __shared__ __align__(16) float Bs[GK][GN + 4];
+  gemm_tile<A_KCONTIG, B_JCONTIG, EPI>(As, Bs, a, sai, sak, b, sbk, sbj, c, ldc, ni, nj, nk, k_chunk, blockIdx.x, blockIdx.y, blockIdx.z,
+                                       op);
 }
 
 // backward of a Linear in ONE launch: CTAs [0, n_dx) compute tiles of dX = dY' W, the others tiles of dW += dY'^T X (rows split
-// over `nz` chunks, partial sums added atomically) and, in the first column tile, db += colsum(dY');  dY' = dY * relu'(Y)
+// over `nz` chunks, partial sums added atomically) and, in the first column tile, db += colsum(dY');
+// dY' = dY * relu'(Y) * rm1[row] * rm2[row]
 __global__ void __launch_bounds__(256) k_tr_linear_bwd(const float* __restrict__ dy, const float* __restrict__ x,
-                                                       const float* __restrict__ w, long ldw, const float* __restrict__ ym, long M,
-                                                       int K, int N, float* __restrict__ dx, float* __restrict__ dw, long lddw,
-                                                       float* __restrict__ db, int n_dx, int dx_tiles_j, int dw_tiles_i,
-                                                       int dw_tiles_j, long chunk) {
-  __shared__ float As[GK][GM + 4];
-  __shared__ float Bs[GK][GN + 4];
+                                                       const float* __restrict__ w, long ldw, long M, int K, int N,
+                                                       float* __restrict__ dx, float* __restrict__ dw, long lddw, int n_dx,
+                                                       int dx_tiles_j, int dw_tiles_i, int dw_tiles_j, long chunk, GemmOpt op) {
+  __shared__ __align__(16) float As[GK][GM + 4];
+  __shared__ __align__(16) float Bs[GK][GN + 4];
   int t = blockIdx.x;
   if (t < n_dx) {
-    gemm_tile<true, true, EPI_STORE>(As, Bs, dy, N, 1, ym, w, ldw, 1, dx, K, nullptr, 0, M, K, N, N, t / dx_tiles_j, t % dx_tiles_j, 0,
-                                     nullptr);
+    gemm_tile<true, true, EPI_STORE>(As, Bs, dy, N, 1, w, ldw, 1, dx, K, M, K, N, N, t / dx_tiles_j, t % dx_tiles_j, 0, op);
   } else {
     t -= n_dx;
     const int per_z = dw_tiles_i * dw_tiles_j;
     const int z = t / per_z, r = t % per_z;
-    gemm_tile<false, true, EPI_ATOMIC>(As, Bs, dy, 1, N, ym, x, K, 1, dw, lddw, nullptr, 0, N, K, M, chunk, r / dw_tiles_j,
-                                       r % dw_tiles_j, z, db);
+    gemm_tile<false, true, EPI_ATOMIC>(As, Bs, dy, 1, N, x, K, 1, dw, lddw, N, K, M, chunk, r / dw_tiles_j, r % dw_tiles_j, z, op);
   }
 }
 
@@ -324,6 +408,7 @@ __global__ void __launch_bounds__(128) k_tr_attn_fwd(const float* __restrict__ q
   // O = P V : thread (d, group g) handles queries g, g + 4
   const int d = tid % 32, g = tid / 32;
   float acc[AT_QT / 4] = {};
+#pragma unroll 8
   for (int j = 0; j < T; ++j) {
     const float vv = kv[((long)b * T + j) * 2 * TR_D + TR_D + h * TR_DH + d];
 #pragma unroll
@@ -429,13 +514,16 @@ __global__ void __launch_bounds__(256) k_tr_attn_bwd(const float* __restrict__ d
 // =====================================================================================================================
 // elementwise glue
 // =====================================================================================================================
-__global__ void k_tr_add_mask(const float* __restrict__ a, const float* __restrict__ b, const uint8_t* __restrict__ keep, long M,
-                              int N, float* __restrict__ y) {
+// y = (a * keep_a[row] + b) * keep[row]
+__global__ void k_tr_add_mask(const float* __restrict__ a, const uint8_t* __restrict__ keep_a, const float* __restrict__ b,
+                              const uint8_t* __restrict__ keep, long M, int N, float* __restrict__ y) {
   const long total = M * N;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const long m = e / N;
     float v = a[e];
+    if (keep_a && !keep_a[m]) v = 0.f;
     if (b) v += b[e];
-    if (keep && !keep[e / N]) v = 0.f;
+    if (keep && !keep[m]) v = 0.f;
     y[e] = v;
   }
 }
@@ -954,25 +1042,29 @@ using namespace tb;
 
 extern "C" {
 
+// y = (relu(x W^T + bias) * keep_lin[row] + res) * keep_out[row]; bias / keep_lin / res / keep_out may be NULL
 int32_t tb_tr_linear_fwd(const float* x, int64_t M, int32_t K, const float* w, int64_t ldw, int32_t N, const float* bias, int32_t relu,
-                     float* y, void* stream) {
+                         const uint8_t* keep_lin, const float* res, const uint8_t* keep_out, float* y, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TR_CHECK(x && w && y, TB_ERR_NULL);
   TR_CHECK(M > 0 && K > 0 && N > 0 && ldw >= K, TB_ERR_BAD_SHAPE);
   dim3 grid((unsigned)((M + GM - 1) / GM), (N + GN - 1) / GN, 1);
-  k_tr_gemm<true, false, EPI_BIAS><<<grid, 256, 0, st>>>(x, K, 1, nullptr, w, 1, ldw, y, N, bias, relu, M, N, K, K);
+  GemmOpt op{nullptr, nullptr, nullptr, bias, relu, keep_lin, res, keep_out, nullptr};
+  k_tr_gemm<true, false, EPI_BIAS><<<grid, 256, 0, st>>>(x, K, 1, w, 1, ldw, y, N, M, N, K, K, op);
   count_launch();
   return launch_status();
 }
 
-// dx = (dy * relu') W; dw += (dy * relu')^T x; db += colsum(dy * relu').  dx / dw / db may be NULL (skipped).
-int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_t ldw, const float* y, int32_t relu, int64_t M, int32_t K,
-                     int32_t N, float* dx, float* dw, int64_t lddw, float* db, void* stream) {
+// dx = dY' W; dw += dY'^T x; db += colsum(dY') with dY' = dy * relu'(y) * rm1[row] * rm2[row] (row masks may be NULL: the
+// keep_lin / keep_out of the forward).  dx / dw / db may be NULL (skipped); db needs dw.
+int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_t ldw, const float* y, int32_t relu, const uint8_t* rm1,
+                         const uint8_t* rm2, int64_t M, int32_t K, int32_t N, float* dx, float* dw, int64_t lddw, float* db,
+                         void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TR_CHECK(dy && x && w, TB_ERR_NULL);
   TR_CHECK(M > 0 && K > 0 && N > 0 && (!relu || y), TB_ERR_BAD_SHAPE);
-  const float* ym = relu ? y : nullptr;
   TR_CHECK(dw || !db, TB_ERR_BAD_SHAPE);  // the bias gradient rides on the weight-gradient tiles
+  if (!dx && !dw) return TB_OK;
   const int dx_tiles_j = (K + GN - 1) / GN;
   const long n_dx = dx ? ((M + GM - 1) / GM) * dx_tiles_j : 0;
   const int dw_tiles_i = (N + GM - 1) / GM, dw_tiles_j = (K + GN - 1) / GN;
@@ -988,8 +1080,9 @@ int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_
   }
   const long total = n_dx + nz * dw_tiles_i * dw_tiles_j;
   TR_CHECK(total > 0 && total < 2147483647L, TB_ERR_BAD_SHAPE);
-  k_tr_linear_bwd<<<(unsigned)total, 256, 0, st>>>(dy, x, w, ldw, ym, M, K, N, dx, dw, lddw, db, (int)n_dx, dx_tiles_j, dw_tiles_i,
-                                                   dw_tiles_j, chunk);
+  GemmOpt op{relu ? y : nullptr, rm1, rm2, nullptr, 0, nullptr, nullptr, nullptr, db};
+  k_tr_linear_bwd<<<(unsigned)total, 256, 0, st>>>(dy, x, w, ldw, M, K, N, dx, dw, lddw, (int)n_dx, dx_tiles_j, dw_tiles_i, dw_tiles_j,
+                                                   chunk, op);
   count_launch();
   return launch_status();
 }
@@ -1056,11 +1149,13 @@ int32_t tb_tr_attention_bwd(const float* dout, const float* q, const float* kv, 
   return launch_status();
 }
 
-int32_t tb_tr_add_mask(const float* a, const float* b, const uint8_t* keep, int64_t M, int32_t N, float* y, void* stream) {
+// y = (a * keep_a[row] + b) * keep[row]; keep_a / b / keep may be NULL
+int32_t tb_tr_add_mask(const float* a, const uint8_t* keep_a, const float* b, const uint8_t* keep, int64_t M, int32_t N, float* y,
+                       void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TR_CHECK(a && y, TB_ERR_NULL);
   TR_CHECK(M > 0 && N > 0, TB_ERR_BAD_SHAPE);
-  k_tr_add_mask<<<grid_for(M * N), 256, 0, st>>>(a, b, keep, M, N, y);
+  k_tr_add_mask<<<grid_for(M * N), 256, 0, st>>>(a, keep_a, b, keep, M, N, y);
   count_launch();
   return launch_status();
 }

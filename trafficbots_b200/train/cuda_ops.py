@@ -75,23 +75,24 @@ class CudaOps:
         self._run(self.L.tb_tr_scale(self._c(x), x.numel(), float(alpha), self._st()), "tb_tr_scale")
 
     # ---- Linear ----
-    def linear_fwd(self, x, w, b, relu):
+    def linear_fwd(self, x, w, b, relu, keep_lin=None, res=None, keep_out=None):
         M, K = x.shape
         N = w.shape[0]
         pw, ldw = _rows_ld(w)
         y = self.empty((M, N))
-        self._run(self.L.tb_tr_linear_fwd(self._c(x), M, K, pw, ldw, N, None if b is None else self._c(b), int(relu), y.data_ptr(),
+        self._run(self.L.tb_tr_linear_fwd(self._c(x), M, K, pw, ldw, N, None if b is None else self._c(b), int(relu),
+                                          self._u8(keep_lin), None if res is None else self._c(res), self._u8(keep_out), y.data_ptr(),
                                           self._st()), "tb_tr_linear_fwd")
         return y
 
-    def linear_bwd(self, dy, x, w, b, y, relu, dw, db, need_dx):
+    def linear_bwd(self, dy, x, w, b, y, relu, dw, db, need_dx, keep_lin=None, keep_out=None):
         M, K = x.shape
         N = w.shape[0]
         pw, ldw = _rows_ld(w)
         dx = self.empty((M, K)) if need_dx else None
         pdw, lddw = (None, 0) if dw is None else _rows_ld(dw)
-        self._run(self.L.tb_tr_linear_bwd(self._c(dy), self._c(x), pw, ldw, self._c(y), int(relu), M, K, N,
-                                          None if dx is None else dx.data_ptr(), pdw, lddw, None if db is None else self._c(db),
+        self._run(self.L.tb_tr_linear_bwd(self._c(dy), self._c(x), pw, ldw, self._c(y), int(relu), self._u8(keep_lin), self._u8(keep_out),
+                                          M, K, N, None if dx is None else dx.data_ptr(), pdw, lddw, None if db is None else self._c(db),
                                           self._st()), "tb_tr_linear_bwd")
         return dx
 
@@ -134,17 +135,17 @@ class CudaOps:
         return dq, dkv
 
     # ---- glue ----
-    def add_mask_fwd(self, a, b, keep):
+    def add_mask_fwd(self, a, b, keep, keep_a=None):
         M, N = a.shape
         y = self.empty((M, N))
-        self._run(self.L.tb_tr_add_mask(self._c(a), None if b is None else self._c(b), self._u8(keep), M, N, y.data_ptr(),
-                                        self._st()), "tb_tr_add_mask")
+        self._run(self.L.tb_tr_add_mask(self._c(a), self._u8(keep_a), None if b is None else self._c(b), self._u8(keep), M, N,
+                                        y.data_ptr(), self._st()), "tb_tr_add_mask")
         return y
 
-    def add_mask_bwd(self, dy, keep):
-        if keep is None:
+    def add_mask_bwd(self, dy, keep, keep_a=None):
+        if keep is None and keep_a is None:
             return dy
-        return self.add_mask_fwd(dy, None, keep)
+        return self.add_mask_fwd(dy, None, keep, keep_a)
 
     def select_rows_fwd(self, mask, a, b):
         M, N = a.shape

@@ -84,12 +84,13 @@ class Model:
         s2 = self.ln(src, prefix + ".norm1")
         q = f.linear(s2, self.p(prefix + ".attn.in_proj_weight", rows=(0, D)), self.p(prefix + ".attn.in_proj_bias", rows=(0, D)))
         o, dead = f.attention(q, kv, key_valid, B, S, T, eye)
-        o = f.linear(o, self.p(prefix + ".attn.out_proj_weight"), self.p(prefix + ".attn.out_proj_bias"))
-        o = f.add_mask(o, None, (dead == 0).to(U8))  # attention.py:144-146
-        src = f.add_mask(src, o, None)  # transformer.py:203
+        # out-projection, dead rows forced to 0 (attention.py:144-146), residual (transformer.py:203): one fused Linear
+        src = f.linear(o, self.p(prefix + ".attn.out_proj_weight"), self.p(prefix + ".attn.out_proj_bias"),
+                       keep_lin=(dead == 0).to(U8), res=src)
         s2 = self.ln(src, prefix + ".norm2")
-        s2 = self.lin(self.lin(s2, prefix + ".linear1", relu=True), prefix + ".linear2")
-        return f.add_mask(src, s2, src_keep)  # :220, :236-237
+        s2 = self.lin(s2, prefix + ".linear1", relu=True)
+        # second FFN Linear + residual (:220) + zeroing of the invalid source rows (:236-237)
+        return f.linear(s2, self.p(prefix + ".linear2.weight"), self.p(prefix + ".linear2.bias"), res=src, keep_out=src_keep)
 
     def tf_block(self, prefix: str, n_layer: int, src: Var, src_keep: Tensor, kvs: List[Var], key_valid: Tensor, B: int, S: int,
                  T: int, eye: bool = False) -> Var:
@@ -359,7 +360,7 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
             # AddLatentGoal.forward, mode cat, res_add (models/modules/add_latent_goal.py:57-77)
             zz = f.add_mask(zr, None, zv)
             h = m.lin(m.lin(f.cat2(x, zz), f"{name}.mlp_out.fc_layers.0", relu=True), f"{name}.mlp_out.fc_layers.3", relu=True)
-            x = f.add_mask(f.add_mask(h, None, zv), x, vflat)
+            x = f.add_mask(h, x, vflat, keep_a=zv)  # (h * z_valid + x) * x_valid
         # ActionHead.forward, branch_type (models/modules/action_head.py:70-87)
         mean = None
         for c in range(3):

@@ -108,17 +108,25 @@ class Fn:
         return out
 
     # ------------------------------------------------------------------ primitives
-    def linear(self, x: Var, w: Var, b: Optional[Var], relu: bool = False) -> Var:
+    def linear(self, x: Var, w: Var, b: Optional[Var], relu: bool = False, keep_lin: Optional[Tensor] = None,
+               res: Optional[Var] = None, keep_out: Optional[Tensor] = None) -> Var:
+        """y = (relu(x W^T + b) * keep_lin[row] + res) * keep_out[row]: a Linear with the residual / row-mask tail of a
+        transformer sub-layer fused into its epilogue (one kernel instead of three)."""
+        assert not (relu and (res is not None or keep_lin is not None or keep_out is not None))
         bd = None if b is None else b.data.view(-1)
-        y = self.ops.linear_fwd(x.data, w.data, bd, relu)
+        y = self.ops.linear_fwd(x.data, w.data, bd, relu, keep_lin, None if res is None else res.data, keep_out)
         self.n_fwd += 1
-        req = x.req or w.req
+        req = x.req or w.req or (res is not None and res.req)
         out = Var(y, req)
         if req:
             def bw(g: Tensor) -> None:
-                dx = self.ops.linear_bwd(g, x.data, w.data, bd, y, relu, w.grad if w.req else None,
-                                         b.grad.view(-1) if (b is not None and b.req) else None, x.req)
-                self._acc(x, dx)
+                if x.req or w.req:
+                    dx = self.ops.linear_bwd(g, x.data, w.data, bd, y, relu, w.grad if w.req else None,
+                                             b.grad.view(-1) if (b is not None and b.req) else None, x.req, keep_lin, keep_out)
+                    self._acc(x, dx)
+                if res is not None and res.req:
+                    d = self.ops.add_mask_bwd(g, keep_out)
+                    self._acc(res, d, owned=d is not g)
             self._push(out, bw)
         return out
 
@@ -152,19 +160,22 @@ class Fn:
             self._push(out, bw)
         return out, dead.view(-1)
 
-    def add_mask(self, a: Var, b: Optional[Var], keep: Optional[Tensor]) -> Var:
-        """(a + b) with the rows where keep == 0 zeroed."""
-        y = self.ops.add_mask_fwd(a.data, None if b is None else b.data, keep)
+    def add_mask(self, a: Var, b: Optional[Var], keep: Optional[Tensor], keep_a: Optional[Tensor] = None) -> Var:
+        """(a * keep_a[row] + b) * keep[row] (masks are row masks; a zero entry zeroes the row)."""
+        y = self.ops.add_mask_fwd(a.data, None if b is None else b.data, keep, keep_a)
         self.n_fwd += 1
         req = a.req or (b is not None and b.req)
         out = Var(y, req)
         if req:
             def bw(g: Tensor) -> None:
                 d = self.ops.add_mask_bwd(g, keep)
-                shared = (d is g) or (b is not None and a.req and b.req)
-                self._acc(a, d, owned=not shared)
                 if b is not None:
-                    self._acc(b, d, owned=not shared)
+                    self._acc(b, d, owned=False if (d is g or a.req) else True)
+                if a.req:
+                    if keep_a is None:
+                        self._acc(a, d, owned=not (d is g or (b is not None and b.req)))
+                    else:
+                        self._acc(a, self.ops.add_mask_bwd(g, keep, keep_a))
             self._push(out, bw)
         return out
 
