@@ -108,3 +108,43 @@ def test_mirror_state_dict_and_config_surface():
         from trafficbots_b200 import _native as nt
         with pytest.raises(nt.TbError):
             m.engine()
+
+
+def _train_worker(rank, world, port, q):
+    """data-parallel training (BASELINE.json configs[3]): every rank back-propagates its own scene shard, ONE all-reduce of
+    the flat gradient buffer averages them (what Lightning DDP does per bucket in the reference), identical Adam steps follow."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    from train_ops_oracle import OracleOps
+    from trafficbots_b200.train import trainer
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    sd = {"a.weight": torch.randn(6, 4), "model.goal_manager.goal_predictor.x.weight": torch.randn(5, 3), "b.bias": torch.randn(7)}
+    ts = trainer.TrainState(sd, device="cpu", ops=OracleOps(), lr=1e-2)
+    g = torch.Generator().manual_seed(100 + rank)
+    local = torch.randn(ts.flat_g.numel(), generator=g)  # this rank's "shard gradient"
+    ts.flat_g.copy_(local)
+    ts.all_reduce_grads()
+    averaged = ts.flat_g.clone()
+    ts.optimizer_step()
+    q.put((rank, local, averaged, ts.flat_p.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_all_reduce_and_identical_steps():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+    mean = (got[0][1] + got[1][1]) / 2
+    for _rank, _local, averaged, params in got:
+        assert torch.allclose(averaged, mean, atol=1e-7)
+    assert torch.equal(got[0][3], got[1][3])  # replicas stay bit-identical

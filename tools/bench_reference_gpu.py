@@ -18,6 +18,36 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
     sys.path.insert(0, p)
 
 import torch  # noqa: E402
+import torch._dynamo  # noqa: E402,F401  (torch.optim imports it lazily; must precede ref_loader's module stubs)
+
+
+def train(model, batch, dev, args):
+    """the reference's training_step + loss.backward() + Adam step on the GPU, dropout 0 (the parity configuration) -- the
+    training counterpart of the secondary baseline."""
+    import ref_train
+    model.train()
+    ref_train.zero_dropout(model)
+    model.log = lambda *a, **k: None
+    opt = torch.optim.Adam(model.parameters(), lr=3e-4)
+    b = {k: v.to(dev) for k, v in batch.items()}
+    times = []
+    with torch.autocast("cuda", dtype=torch.float16, enabled=args.amp):
+        for i in range(args.steps + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            opt.zero_grad(set_to_none=True)
+            loss = model.training_step({k: v.clone() for k, v in b.items()}, i)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
+            opt.step()
+            torch.cuda.synchronize()
+            if i > 0:
+                times.append(time.perf_counter() - t0)
+    best = min(times)
+    print(json.dumps({"impl": "reference on GPU (unmodified PyTorch training_step + backward + Adam)",
+                      "precision": "fp16 autocast" if args.amp else "fp32", "scenes": args.scenes, "agents": args.agents,
+                      "polylines": args.pl, "s_per_step": best, "scenes_per_s": args.scenes / best, "gpu": torch.cuda.get_device_name(0),
+                      "loss": float(loss), "peak_memory_gib": torch.cuda.max_memory_allocated() / 2 ** 30}))
 
 
 def main():
@@ -28,6 +58,7 @@ def main():
     ap.add_argument("--k", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--amp", action="store_true")
+    ap.add_argument("--train", action="store_true", help="training_step + backward (BASELINE.json configs[3]) instead of the eval step")
     args = ap.parse_args()
     import ref_loader
     from trafficbots_b200 import synthetic, weights
@@ -39,6 +70,8 @@ def main():
     model.load_state_dict(weights.init_state_dict(2023), strict=True)
     model = model.to(dev).eval()
     batch = synthetic.make_batch(args.scenes, n_agent=args.agents, n_pl=args.pl, seed=1000)
+    if args.train:
+        return train(model, batch, dev, args)
 
     @torch.no_grad()
     def step():

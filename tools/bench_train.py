@@ -33,7 +33,7 @@ def main():
         t0 = time.perf_counter()
         ts.flat_g.zero_()
         fn = Fn(ts.ops)
-        out = graph.training_forward(fn, ts.params, batch, eps.to(dev), use_prior)
+        out = graph.training_forward(fn, ts.params, batch, eps.to(dev), use_prior, n_step=int(os.environ.get("TB_TRAIN_STEPS", "90")))
         t1 = time.perf_counter()
         torch.cuda.synchronize()
         t2 = time.perf_counter()

@@ -68,6 +68,7 @@ class TrainState:
         self.n_step = 0
         self.last_ops = 0
         self._graphs, self._pool, self._static_batch, self._static_eps = {}, None, None, None
+        self.replayed_kernels = 0  # kernels of this library launched through graph replays (tb_launch_count sees eager launches only)
 
     def state_dict(self) -> Dict[str, Tensor]:
         return {k: v.detach().clone() for k, v in self.params.t.items()}
@@ -117,11 +118,12 @@ class TrainState:
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
+            n0 = self.ops.L.tb_launch_count()
             with torch.cuda.graph(g, pool=self._pool):
                 out = self.forward_backward(self._static_batch, self._static_eps, use_prior)
             if self._pool is None:
                 self._pool = g.pool()
-            self._graphs[use_prior] = (g, out)
+            self._graphs[use_prior] = (g, out, int(self.ops.L.tb_launch_count() - n0))  # kernels of this library in the graph
         return self._graphs[use_prior]
 
     def replay(self, batch: Mapping[str, Tensor], eps: Optional[Tensor] = None, use_prior: Optional[bool] = None) -> Dict[str, Tensor]:
@@ -129,11 +131,12 @@ class TrainState:
         S, _, A = batch["agent/valid"].shape
         if eps is None or use_prior is None:
             use_prior, eps = self.draw_noise(S, A)
-        g, out = self._graph(bool(use_prior))
+        g, out, n_kernel = self._graph(bool(use_prior))
         for k, dst in self._static_batch.items():
             dst.copy_(batch[k], non_blocking=True)
         self._static_eps.copy_(eps, non_blocking=True)
         g.replay()
+        self.replayed_kernels += n_kernel
         return out
 
     def all_reduce_grads(self) -> None:
