@@ -22,6 +22,7 @@ constexpr int TR_DH = 32;
 // GEMM:  C[i, j] (op)= sum_k A(i, k) * B(k, j),   A(i, k) = a[i * sai + k * sak] (* relu mask ym[i * sai + k * sak] > 0)
 // =====================================================================================================================
 constexpr int GM = 64, GN = 64, GK = 16;
+constexpr long SMALL_M = 8192;  // launches with at most this many rows use 32-row tiles
 enum { EPI_BIAS = 0, EPI_STORE = 1, EPI_ATOMIC = 2 };
 
 // Per-tile options.  A operand: `ym` = ReLU mask source (same indexing as A: element kept where ym > 0), `rm1` / `rm2` = row masks
@@ -41,24 +42,29 @@ struct GemmOpt {
 
 // The next k-slab is fetched into registers while the current one is multiplied out of shared memory (global-load latency
 // hidden behind the FMAs); 16-byte loads where the layout allows.
-template <bool A_KCONTIG, bool B_JCONTIG, int EPI>
+// TM = rows of the output tile (64: 4 x 4 outputs per thread; 32: 2 x 4 -- twice the CTAs for the 1 k-row launches of a decode
+// step, which are bound by the dependent k-slab iterations of a CTA, not by FLOPs)
+template <int TM, bool A_KCONTIG, bool B_JCONTIG, int EPI>
 __device__ __forceinline__ void gemm_tile(float (&As)[GK][GM + 4], float (&Bs)[GK][GN + 4], const float* __restrict__ a, long sai,
                                           long sak, const float* __restrict__ b, long sbk, long sbj, float* __restrict__ c, long ldc,
                                           long ni, int nj, long nk, long k_chunk, long tile_i, int tile_j, long tile_z,
                                           const GemmOpt& op) {
   const int tid = threadIdx.x;
-  const long i0 = tile_i * GM;
+  constexpr int RX = TM / 16;  // output rows per thread
+  const long i0 = tile_i * TM;
   const int j0 = tile_j * GN;
   const long k_lo = tile_z * k_chunk;
   const long k_hi = min(nk, k_lo + k_chunk);
   const int ti = tid / 16, tj = tid % 16;  // 16 x 16 threads, 4 x 4 outputs each
-  float acc[4][4] = {};
+  float acc[RX][4] = {};
   float rs = 0.f;
   const bool do_rowsum = (EPI == EPI_ATOMIC) && op.rowsum != nullptr && tile_j == 0;
   const float* __restrict__ ym = op.ym;
-  // thread -> element mapping of the two tile loads (4 consecutive elements along the contiguous direction)
-  const int a_r = A_KCONTIG ? tid / 4 : (tid % 16) * 4;   // row (i) offset
-  const int a_k = A_KCONTIG ? (tid % 4) * 4 : tid / 16;   // k offset
+  // thread -> element mapping of the two tile loads (4 consecutive elements along the contiguous direction); with TM = 32 the A
+  // tile has 512 elements: threads 0..127 load it
+  const bool a_thread = tid < TM * 4;
+  const int a_r = A_KCONTIG ? tid / 4 : (tid % (TM / 4)) * 4;   // row (i) offset
+  const int a_k = A_KCONTIG ? (tid % 4) * 4 : tid / (TM / 4);   // k offset
   const int b_j = B_JCONTIG ? (tid % 16) * 4 : tid / 4;
   const int b_k = B_JCONTIG ? tid / 16 : (tid % 4) * 4;
   const bool a_vec = A_KCONTIG ? (sak == 1 && (sai & 3) == 0) : (sai == 1 && (sak & 3) == 0);
@@ -69,7 +75,8 @@ __device__ __forceinline__ void gemm_tile(float (&As)[GK][GM + 4], float (&Bs)[G
 
   auto fetch = [&](long k0) {
     // ---- A ----
-    if (A_KCONTIG) {
+    if (!a_thread) {
+    } else if (A_KCONTIG) {
       const long i = i0 + a_r, k = k0 + a_k;
       bool row_ok = i < ni;
       if (row_ok && op.rm1 && !op.rm1[i]) row_ok = false;
@@ -146,7 +153,8 @@ __device__ __forceinline__ void gemm_tile(float (&As)[GK][GM + 4], float (&Bs)[G
     }
   };
   auto stash = [&]() {
-    if (A_KCONTIG) {
+    if (!a_thread) {
+    } else if (A_KCONTIG) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) As[a_k + u][a_r] = ra[u];
     } else {
@@ -165,25 +173,32 @@ __device__ __forceinline__ void gemm_tile(float (&As)[GK][GM + 4], float (&Bs)[G
     stash();
     __syncthreads();
     if (k0 + GK < k_hi) fetch(k0 + GK);
-    if (do_rowsum && tid < GM) {
+    if (do_rowsum && tid < TM) {
 #pragma unroll
       for (int kk = 0; kk < GK; ++kk) rs += As[kk][tid];
     }
 #pragma unroll
     for (int kk = 0; kk < GK; ++kk) {
-      const float4 av = *reinterpret_cast<const float4*>(&As[kk][ti * 4]);
+      float ar[RX];
+      if (RX == 4) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[kk][ti * 4]);
+        ar[0] = av.x, ar[1] = av.y, ar[RX - 2] = av.z, ar[RX - 1] = av.w;
+      } else {
+        const float2 av = *reinterpret_cast<const float2*>(&As[kk][ti * 2]);
+        ar[0] = av.x, ar[1] = av.y;
+      }
       const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tj * 4]);
-      const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+      const float br[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-      for (int x = 0; x < 4; ++x)
+      for (int x = 0; x < RX; ++x)
 #pragma unroll
         for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(ar[x], br[y], acc[x][y]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int x = 0; x < 4; ++x) {
-    const long i = i0 + ti * 4 + x;
+  for (int x = 0; x < RX; ++x) {
+    const long i = i0 + ti * RX + x;
     if (i >= ni) continue;
     float kl = 1.f, ko = 1.f;
     if (EPI == EPI_BIAS) {
@@ -209,22 +224,23 @@ __device__ __forceinline__ void gemm_tile(float (&As)[GK][GM + 4], float (&Bs)[G
       }
     }
   }
-  if (do_rowsum && tid < GM && i0 + tid < ni) atomicAdd(&op.rowsum[i0 + tid], rs);
+  if (do_rowsum && tid < TM && i0 + tid < ni) atomicAdd(&op.rowsum[i0 + tid], rs);
 }
 
-template <bool A_KCONTIG, bool B_JCONTIG, int EPI>
+template <int TM, bool A_KCONTIG, bool B_JCONTIG, int EPI>
 __global__ void __launch_bounds__(256) k_tr_gemm(const float* __restrict__ a, long sai, long sak, const float* __restrict__ b, long sbk,
                                                  long sbj, float* __restrict__ c, long ldc, long ni, int nj, long nk, long k_chunk,
                                                  GemmOpt op) {
   __shared__ __align__(16) float As[GK][GM + 4];
   __shared__ __align__(16) float Bs[GK][GN + 4];
-  gemm_tile<A_KCONTIG, B_JCONTIG, EPI>(As, Bs, a, sai, sak, b, sbk, sbj, c, ldc, ni, nj, nk, k_chunk, blockIdx.x, blockIdx.y, blockIdx.z,
-                                       op);
+  gemm_tile<TM, A_KCONTIG, B_JCONTIG, EPI>(As, Bs, a, sai, sak, b, sbk, sbj, c, ldc, ni, nj, nk, k_chunk, blockIdx.x, blockIdx.y,
+                                           blockIdx.z, op);
 }
 
 // backward of a Linear in ONE launch: CTAs [0, n_dx) compute tiles of dX = dY' W, the others tiles of dW += dY'^T X (rows split
 // over `nz` chunks, partial sums added atomically) and, in the first column tile, db += colsum(dY');
 // dY' = dY * relu'(Y) * rm1[row] * rm2[row]
+template <int TM>
 __global__ void __launch_bounds__(256) k_tr_linear_bwd(const float* __restrict__ dy, const float* __restrict__ x,
                                                        const float* __restrict__ w, long ldw, long M, int K, int N,
                                                        float* __restrict__ dx, float* __restrict__ dw, long lddw, int n_dx,
@@ -233,12 +249,12 @@ __global__ void __launch_bounds__(256) k_tr_linear_bwd(const float* __restrict__
   __shared__ __align__(16) float Bs[GK][GN + 4];
   int t = blockIdx.x;
   if (t < n_dx) {
-    gemm_tile<true, true, EPI_STORE>(As, Bs, dy, N, 1, w, ldw, 1, dx, K, M, K, N, N, t / dx_tiles_j, t % dx_tiles_j, 0, op);
+    gemm_tile<TM, true, true, EPI_STORE>(As, Bs, dy, N, 1, w, ldw, 1, dx, K, M, K, N, N, t / dx_tiles_j, t % dx_tiles_j, 0, op);
   } else {
     t -= n_dx;
     const int per_z = dw_tiles_i * dw_tiles_j;
     const int z = t / per_z, r = t % per_z;
-    gemm_tile<false, true, EPI_ATOMIC>(As, Bs, dy, 1, N, x, K, 1, dw, lddw, N, K, M, chunk, r / dw_tiles_j, r % dw_tiles_j, z, op);
+    gemm_tile<TM, false, true, EPI_ATOMIC>(As, Bs, dy, 1, N, x, K, 1, dw, lddw, N, K, M, chunk, r / dw_tiles_j, r % dw_tiles_j, z, op);
   }
 }
 
@@ -1048,9 +1064,14 @@ int32_t tb_tr_linear_fwd(const float* x, int64_t M, int32_t K, const float* w, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TR_CHECK(x && w && y, TB_ERR_NULL);
   TR_CHECK(M > 0 && K > 0 && N > 0 && ldw >= K, TB_ERR_BAD_SHAPE);
-  dim3 grid((unsigned)((M + GM - 1) / GM), (N + GN - 1) / GN, 1);
   GemmOpt op{nullptr, nullptr, nullptr, bias, relu, keep_lin, res, keep_out, nullptr};
-  k_tr_gemm<true, false, EPI_BIAS><<<grid, 256, 0, st>>>(x, K, 1, w, 1, ldw, y, N, M, N, K, K, op);
+  if (M <= SMALL_M) {
+    dim3 grid((unsigned)((M + 31) / 32), (N + GN - 1) / GN, 1);
+    k_tr_gemm<32, true, false, EPI_BIAS><<<grid, 256, 0, st>>>(x, K, 1, w, 1, ldw, y, N, M, N, K, K, op);
+  } else {
+    dim3 grid((unsigned)((M + GM - 1) / GM), (N + GN - 1) / GN, 1);
+    k_tr_gemm<GM, true, false, EPI_BIAS><<<grid, 256, 0, st>>>(x, K, 1, w, 1, ldw, y, N, M, N, K, K, op);
+  }
   count_launch();
   return launch_status();
 }
@@ -1065,9 +1086,10 @@ int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_
   TR_CHECK(M > 0 && K > 0 && N > 0 && (!relu || y), TB_ERR_BAD_SHAPE);
   TR_CHECK(dw || !db, TB_ERR_BAD_SHAPE);  // the bias gradient rides on the weight-gradient tiles
   if (!dx && !dw) return TB_OK;
+  const int TMh = M <= SMALL_M ? 32 : GM;
   const int dx_tiles_j = (K + GN - 1) / GN;
-  const long n_dx = dx ? ((M + GM - 1) / GM) * dx_tiles_j : 0;
-  const int dw_tiles_i = (N + GM - 1) / GM, dw_tiles_j = (K + GN - 1) / GN;
+  const long n_dx = dx ? ((M + TMh - 1) / TMh) * dx_tiles_j : 0;
+  const int dw_tiles_i = (N + TMh - 1) / TMh, dw_tiles_j = (K + GN - 1) / GN;
   long nz = 0, chunk = 0;
   if (dw) {  // enough row chunks to fill the GPU twice, at least 128 rows each
     const long tiles = (long)dw_tiles_i * dw_tiles_j;
@@ -1081,8 +1103,12 @@ int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_
   const long total = n_dx + nz * dw_tiles_i * dw_tiles_j;
   TR_CHECK(total > 0 && total < 2147483647L, TB_ERR_BAD_SHAPE);
   GemmOpt op{relu ? y : nullptr, rm1, rm2, nullptr, 0, nullptr, nullptr, nullptr, db};
-  k_tr_linear_bwd<<<(unsigned)total, 256, 0, st>>>(dy, x, w, ldw, M, K, N, dx, dw, lddw, (int)n_dx, dx_tiles_j, dw_tiles_i, dw_tiles_j,
-                                                   chunk, op);
+  if (TMh == 32)
+    k_tr_linear_bwd<32><<<(unsigned)total, 256, 0, st>>>(dy, x, w, ldw, M, K, N, dx, dw, lddw, (int)n_dx, dx_tiles_j, dw_tiles_i,
+                                                         dw_tiles_j, chunk, op);
+  else
+    k_tr_linear_bwd<GM><<<(unsigned)total, 256, 0, st>>>(dy, x, w, ldw, M, K, N, dx, dw, lddw, (int)n_dx, dx_tiles_j, dw_tiles_i,
+                                                         dw_tiles_j, chunk, op);
   count_launch();
   return launch_status();
 }
