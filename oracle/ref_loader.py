@@ -123,11 +123,14 @@ class _Metric(nn.Module):
 
     def add_state(self, name, default, dist_reduce_fx=None):
         self._defaults[name] = default
-        setattr(self, name, default.clone() if torch.is_tensor(default) else list(default))
+        if torch.is_tensor(default):  # like torchmetrics: the state follows the module's device, stays out of the state_dict
+            self.register_buffer(name, default.clone(), persistent=False)
+        else:
+            setattr(self, name, list(default))
 
     def reset(self):
         for k, v in self._defaults.items():
-            setattr(self, k, v.clone() if torch.is_tensor(v) else list(v))
+            setattr(self, k, v.clone().to(getattr(self, k).device) if torch.is_tensor(v) else list(v))
 
     def forward(self, *a, **kw):
         self.update(*a, **kw)

@@ -353,10 +353,10 @@ __global__ void __launch_bounds__(256) k_tr_ln_bwd(const float* __restrict__ dy,
 constexpr int AT_QT = 8;  // queries per CTA (forward)
 
 // grid (ceil(S / AT_QT), H, B), 128 threads; dynamic smem: AT_QT * T logits
-__global__ void __launch_bounds__(128) k_tr_attn_fwd(const float* __restrict__ q, const float* __restrict__ kv,
+__global__ void __launch_bounds__(128, 4) k_tr_attn_fwd(const float* __restrict__ q, const float* __restrict__ kv,
                                                      const uint8_t* __restrict__ key_valid, int eye, int S, int T,
                                                      float* __restrict__ o, float* __restrict__ p, uint8_t* __restrict__ dead) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* lg = sm;                     // [AT_QT][T]
   __shared__ float qs[AT_QT][TR_DH];
   __shared__ float rmax[AT_QT], rinv[AT_QT];
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(128) k_tr_attn_fwd(const float* __restrict__ q
       kr[u * 4] = t4.x, kr[u * 4 + 1] = t4.y, kr[u * 4 + 2] = t4.z, kr[u * 4 + 3] = t4.w;
     }
     const bool kvld = key_valid[(long)b * T + j] != 0;
-#pragma unroll
+#pragma unroll 2
     for (int qi = 0; qi < AT_QT; ++qi) {
       float dot = 0.f;
 #pragma unroll
@@ -421,32 +421,56 @@ __global__ void __launch_bounds__(128) k_tr_attn_fwd(const float* __restrict__ q
     p[(((long)b * TR_H + h) * S + s0 + qi) * T + j] = pv;
   }
   __syncthreads();
-  // O = P V : thread (d, group g) handles queries g, g + 4
+  // O = P V : thread (d, key slice g) accumulates all AT_QT queries over the keys {4 (g + 4 i) .. + 3}; the four slices are then
+  // summed through shared memory (the logits buffer is free after the barrier)
   const int d = tid % 32, g = tid / 32;
-  float acc[AT_QT / 4] = {};
-#pragma unroll 8
-  for (int j = 0; j < T; ++j) {
-    const float vv = kv[((long)b * T + j) * 2 * TR_D + TR_D + h * TR_DH + d];
+  float acc[AT_QT] = {};
+  const float* vbase = kv + (long)b * T * 2 * TR_D + TR_D + h * TR_DH + d;
+  if ((T & 3) == 0) {
+#pragma unroll 2
+    for (int j4 = g * 4; j4 < T; j4 += 16) {
+      const float v0 = vbase[(long)(j4 + 0) * 2 * TR_D], v1 = vbase[(long)(j4 + 1) * 2 * TR_D];
+      const float v2 = vbase[(long)(j4 + 2) * 2 * TR_D], v3 = vbase[(long)(j4 + 3) * 2 * TR_D];
 #pragma unroll
-    for (int u = 0; u < AT_QT / 4; ++u) acc[u] = fmaf(lg[(g + 4 * u) * T + j], vv, acc[u]);
+      for (int qi = 0; qi < AT_QT; ++qi) {
+        const float4 pq = *reinterpret_cast<const float4*>(&lg[qi * T + j4]);
+        acc[qi] = fmaf(pq.x, v0, fmaf(pq.y, v1, fmaf(pq.z, v2, fmaf(pq.w, v3, acc[qi]))));
+      }
+    }
+  } else {
+    for (int j = g; j < T; j += 4) {
+      const float vv = vbase[(long)j * 2 * TR_D];
+#pragma unroll
+      for (int qi = 0; qi < AT_QT; ++qi) acc[qi] = fmaf(lg[qi * T + j], vv, acc[qi]);
+    }
   }
+  __syncthreads();
+  float* red = lg;  // [4][AT_QT][32]
 #pragma unroll
-  for (int u = 0; u < AT_QT / 4; ++u) {
-    const int qi = g + 4 * u;
-    if (qi < nq) o[((long)b * S + s0 + qi) * TR_D + h * TR_DH + d] = acc[u];
+  for (int qi = 0; qi < AT_QT; ++qi) red[(g * AT_QT + qi) * 32 + d] = acc[qi];
+  __syncthreads();
+  for (int e = tid; e < nq * 32; e += 128) {
+    const int qi = e / 32, dd = e % 32;
+    o[((long)b * S + s0 + qi) * TR_D + h * TR_DH + dd] =
+        red[(0 * AT_QT + qi) * 32 + dd] + red[(1 * AT_QT + qi) * 32 + dd] + red[(2 * AT_QT + qi) * 32 + dd] + red[(3 * AT_QT + qi) * 32 + dd];
   }
 }
 
 // backward: CTA = (key chunk of 64, head, batch); loops over query tiles of 16.  dK / dV of its keys are complete (plain
-// stores), dQ partials are added atomically (dq zero-initialised by the caller).
+// stores), dQ partials are added atomically (dq zero-initialised by the caller).  Shared-memory rows are padded to 16-byte
+// multiples and every inner product is register-blocked over 16-byte shared loads (the first version issued one 4-byte shared
+// load per FMA and was bound by the LSU pipe).
 constexpr int AB_KC = 64, AB_QT = 16;
+constexpr int AB_LD = TR_DH + 4;   // 36: row stride of the [*, 32] tiles
+constexpr int AB_LDS = AB_KC + 4;  // 68: row stride of the [16, 64] tiles
 __global__ void __launch_bounds__(256) k_tr_attn_bwd(const float* __restrict__ dout, const float* __restrict__ q,
                                                      const float* __restrict__ kv, const float* __restrict__ p,
                                                      const float* __restrict__ o, int S, int T, float* __restrict__ dq,
                                                      float* __restrict__ dkv) {
-  __shared__ float ks[AB_KC][TR_DH + 1], vs[AB_KC][TR_DH + 1];
-  __shared__ float qs[AB_QT][TR_DH], gs[AB_QT][TR_DH], delta[AB_QT];
-  __shared__ float ps[AB_QT][AB_KC + 1], ds[AB_QT][AB_KC + 1];
+  __shared__ __align__(16) float ks[AB_KC][AB_LD], vs[AB_KC][AB_LD];
+  __shared__ __align__(16) float qs[AB_QT][AB_LD], gs[AB_QT][AB_LD];
+  __shared__ __align__(16) float ps[AB_QT][AB_LDS], ds[AB_QT][AB_LDS];
+  __shared__ float delta[AB_QT];
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * AB_KC;
   const int tid = threadIdx.x;
   const int nk = min(AB_KC, T - j0);
@@ -458,9 +482,11 @@ __global__ void __launch_bounds__(256) k_tr_attn_bwd(const float* __restrict__ d
     vs[j][d] = ok ? kv[base + TR_D] : 0.f;
   }
   const float scale = 0.17677669529663688110f;
-  // register accumulators of dK / dV: thread owns d = tid % 32 and keys jj = tid / 32 + 8 * u, u < 8
-  float adk[AB_KC / 8] = {}, adv[AB_KC / 8] = {};
+  // dK / dV accumulators: thread owns feature od and the 8 consecutive keys oj * 8 .. + 7
+  float adk[8] = {}, adv[8] = {};
   const int od = tid % 32, oj = tid / 32;
+  // dS: thread owns query sq and the keys sj + 16 u;  dQ: thread owns query sq and the features 2 sj, 2 sj + 1
+  const int sq = tid / 16, sj = tid % 16;
   for (int s0 = 0; s0 < S; s0 += AB_QT) {
     const int nq = min(AB_QT, S - s0);
     __syncthreads();
@@ -474,7 +500,7 @@ __global__ void __launch_bounds__(256) k_tr_attn_bwd(const float* __restrict__ d
       const int qi = e / AB_KC, j = e % AB_KC;
       ps[qi][j] = (qi < nq && j < nk) ? p[(((long)b * TR_H + h) * S + s0 + qi) * T + j0 + j] : 0.f;
     }
-    if (tid < AB_QT * 2) {  // delta = sum_d do * o, two half rows per query combined below
+    if (tid < AB_QT * 2) {  // delta = sum_d do * o, two half rows per query
       const int qi = tid / 2, half = tid % 2;
       float s = 0.f;
       if (qi < nq) {
@@ -485,44 +511,162 @@ __global__ void __launch_bounds__(256) k_tr_attn_bwd(const float* __restrict__ d
       if (half == 0) delta[qi] = s;
     }
     __syncthreads();
-    // dS = P * (dO V^T - delta) * scale
-    for (int e = tid; e < AB_QT * AB_KC; e += 256) {
-      const int qi = e / AB_KC, j = e % AB_KC;
-      float dp = 0.f;
+    {  // dS = P * (dO V^T - delta) * scale
+      float dp[4] = {};
 #pragma unroll
-      for (int d = 0; d < TR_DH; ++d) dp = fmaf(gs[qi][d], vs[j][d], dp);
-      ds[qi][j] = ps[qi][j] * (dp - delta[qi]) * scale;
+      for (int c = 0; c < 8; ++c) {
+        const float4 g4 = *reinterpret_cast<const float4*>(&gs[sq][c * 4]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 v4 = *reinterpret_cast<const float4*>(&vs[sj + 16 * u][c * 4]);
+          dp[u] = fmaf(g4.x, v4.x, fmaf(g4.y, v4.y, fmaf(g4.z, v4.z, fmaf(g4.w, v4.w, dp[u]))));
+        }
+      }
+      const float dl = delta[sq];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ds[sq][sj + 16 * u] = ps[sq][sj + 16 * u] * (dp[u] - dl) * scale;
     }
     __syncthreads();
-    // dQ partial: 16 x 32 outputs, 2 per thread
-    for (int e = tid; e < AB_QT * TR_DH; e += 256) {
-      const int qi = e / TR_DH, d = e % TR_DH;
-      if (qi >= nq) continue;
-      float s = 0.f;
-      for (int j = 0; j < nk; ++j) s = fmaf(ds[qi][j], ks[j][d], s);
-      atomicAdd(&dq[((long)b * S + s0 + qi) * TR_D + h * TR_DH + d], s);
+    if (sq < nq) {  // dQ partial of (sq, 2 sj .. 2 sj + 1)
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+      for (int jj = 0; jj < AB_KC; jj += 4) {
+        const float4 d4 = *reinterpret_cast<const float4*>(&ds[sq][jj]);
+        const float2 k0 = *reinterpret_cast<const float2*>(&ks[jj + 0][2 * sj]);
+        const float2 k1 = *reinterpret_cast<const float2*>(&ks[jj + 1][2 * sj]);
+        const float2 k2 = *reinterpret_cast<const float2*>(&ks[jj + 2][2 * sj]);
+        const float2 k3 = *reinterpret_cast<const float2*>(&ks[jj + 3][2 * sj]);
+        a0 = fmaf(d4.x, k0.x, fmaf(d4.y, k1.x, fmaf(d4.z, k2.x, fmaf(d4.w, k3.x, a0))));
+        a1 = fmaf(d4.x, k0.y, fmaf(d4.y, k1.y, fmaf(d4.z, k2.y, fmaf(d4.w, k3.y, a1))));
+      }
+      float* dst = dq + ((long)b * S + s0 + sq) * TR_D + h * TR_DH + 2 * sj;
+      atomicAdd(dst, a0);
+      atomicAdd(dst + 1, a1);
     }
     // dK, dV accumulation
-#pragma unroll
-    for (int u = 0; u < AB_KC / 8; ++u) {
-      const int j = oj + 8 * u;
-      float sk = 0.f, sv = 0.f;
-#pragma unroll
-      for (int qi = 0; qi < AB_QT; ++qi) {
-        sk = fmaf(ds[qi][j], qs[qi][od], sk);
-        sv = fmaf(ps[qi][j], gs[qi][od], sv);
-      }
-      adk[u] += sk;
-      adv[u] += sv;
+#pragma unroll 4
+    for (int qi = 0; qi < AB_QT; ++qi) {
+      const float qv = qs[qi][od], gv = gs[qi][od];
+      const float4 da = *reinterpret_cast<const float4*>(&ds[qi][oj * 8]), db = *reinterpret_cast<const float4*>(&ds[qi][oj * 8 + 4]);
+      const float4 pa = *reinterpret_cast<const float4*>(&ps[qi][oj * 8]), pb = *reinterpret_cast<const float4*>(&ps[qi][oj * 8 + 4]);
+      adk[0] = fmaf(da.x, qv, adk[0]), adk[1] = fmaf(da.y, qv, adk[1]), adk[2] = fmaf(da.z, qv, adk[2]), adk[3] = fmaf(da.w, qv, adk[3]);
+      adk[4] = fmaf(db.x, qv, adk[4]), adk[5] = fmaf(db.y, qv, adk[5]), adk[6] = fmaf(db.z, qv, adk[6]), adk[7] = fmaf(db.w, qv, adk[7]);
+      adv[0] = fmaf(pa.x, gv, adv[0]), adv[1] = fmaf(pa.y, gv, adv[1]), adv[2] = fmaf(pa.z, gv, adv[2]), adv[3] = fmaf(pa.w, gv, adv[3]);
+      adv[4] = fmaf(pb.x, gv, adv[4]), adv[5] = fmaf(pb.y, gv, adv[5]), adv[6] = fmaf(pb.z, gv, adv[6]), adv[7] = fmaf(pb.w, gv, adv[7]);
     }
   }
 #pragma unroll
-  for (int u = 0; u < AB_KC / 8; ++u) {
-    const int j = oj + 8 * u;
+  for (int u = 0; u < 8; ++u) {
+    const int j = oj * 8 + u;
     if (j < nk) {
       const long base = ((long)b * T + j0 + j) * 2 * TR_D + h * TR_DH + od;
       dkv[base] = adk[u];
       dkv[base + TR_D] = adv[u];
+    }
+  }
+}
+
+// ---- at most 32 keys (the 20 nodes of a polyline, map_encoder.py:72-88): one warp per (batch element, head), lane = key ----
+// K rows live in registers, V in shared memory; per query the row of Q is broadcast lane by lane (shuffles), the softmax is two
+// warp reductions, O = P V is accumulated with lane = feature.  Same arithmetic as the general kernel.
+__global__ void __launch_bounds__(128) k_tr_attn_small_fwd(const float* __restrict__ q, const float* __restrict__ kv,
+                                                           const uint8_t* __restrict__ key_valid, int eye, int S, int T,
+                                                           float* __restrict__ o, float* __restrict__ p, uint8_t* __restrict__ dead) {
+  __shared__ float vs[TR_H][32][TR_DH + 1];
+  const int b = blockIdx.x, h = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const bool has_key = lane < T;
+  float kr[TR_DH];
+  if (has_key) {
+    const float4* kp = reinterpret_cast<const float4*>(kv + ((long)b * T + lane) * 2 * TR_D + h * TR_DH);
+    const float4* vp = reinterpret_cast<const float4*>(kv + ((long)b * T + lane) * 2 * TR_D + TR_D + h * TR_DH);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float4 t4 = kp[u], v4 = vp[u];
+      kr[u * 4] = t4.x, kr[u * 4 + 1] = t4.y, kr[u * 4 + 2] = t4.z, kr[u * 4 + 3] = t4.w;
+      vs[h][lane][u * 4] = v4.x, vs[h][lane][u * 4 + 1] = v4.y, vs[h][lane][u * 4 + 2] = v4.z, vs[h][lane][u * 4 + 3] = v4.w;
+    }
+  } else {
+#pragma unroll
+    for (int d = 0; d < TR_DH; ++d) kr[d] = 0.f;
+  }
+  const bool kvld = has_key && key_valid[(long)b * T + lane] != 0;
+  __syncwarp();
+  const float scale = 0.17677669529663688110f;
+  for (int s = 0; s < S; ++s) {
+    const long row = (long)b * S + s;
+    const float qv = q[row * TR_D + h * TR_DH + lane];
+    float dot = 0.f;
+#pragma unroll
+    for (int d = 0; d < TR_DH; ++d) dot = fmaf(__shfl_sync(0xffffffffu, qv, d), kr[d], dot);
+    const bool ok = kvld && !(eye && lane == s);
+    const float lg = ok ? dot * scale : -INFINITY;
+    float m = lg;
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, of));
+    float e = (ok && m > -INFINITY) ? expf(lg - m) : 0.f;
+    float sum = e;
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, of);
+    const float pv = m > -INFINITY ? e * (1.f / sum) : 0.f;
+    if (has_key) p[(((long)b * TR_H + h) * S + s) * T + lane] = pv;
+    if (h == 0 && lane == 0) dead[row] = m > -INFINITY ? 0 : 1;
+    float acc = 0.f;
+    for (int j = 0; j < T; ++j) acc = fmaf(__shfl_sync(0xffffffffu, pv, j), vs[h][j][lane], acc);
+    o[row * TR_D + h * TR_DH + lane] = acc;
+  }
+}
+
+// backward of the same: lane = key holds its V row and the dK / dV accumulators in registers, K in shared memory; dQ of a query
+// is complete within the warp (plain stores, no atomics)
+__global__ void __launch_bounds__(128) k_tr_attn_small_bwd(const float* __restrict__ dout, const float* __restrict__ q,
+                                                           const float* __restrict__ kv, const float* __restrict__ p,
+                                                           const float* __restrict__ o, int S, int T, float* __restrict__ dq,
+                                                           float* __restrict__ dkv) {
+  __shared__ float ks[TR_H][32][TR_DH + 1];
+  const int b = blockIdx.x, h = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const bool has_key = lane < T;
+  float vr[TR_DH], dk[TR_DH], dv[TR_DH];
+#pragma unroll
+  for (int d = 0; d < TR_DH; ++d) vr[d] = 0.f, dk[d] = 0.f, dv[d] = 0.f;
+  if (has_key) {
+    const float4* kp = reinterpret_cast<const float4*>(kv + ((long)b * T + lane) * 2 * TR_D + h * TR_DH);
+    const float4* vp = reinterpret_cast<const float4*>(kv + ((long)b * T + lane) * 2 * TR_D + TR_D + h * TR_DH);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float4 t4 = kp[u], v4 = vp[u];
+      ks[h][lane][u * 4] = t4.x, ks[h][lane][u * 4 + 1] = t4.y, ks[h][lane][u * 4 + 2] = t4.z, ks[h][lane][u * 4 + 3] = t4.w;
+      vr[u * 4] = v4.x, vr[u * 4 + 1] = v4.y, vr[u * 4 + 2] = v4.z, vr[u * 4 + 3] = v4.w;
+    }
+  }
+  __syncwarp();
+  const float scale = 0.17677669529663688110f;
+  for (int s = 0; s < S; ++s) {
+    const long idx = ((long)b * S + s) * TR_D + h * TR_DH + lane;
+    const float gv = dout[idx], ov = o[idx], qv = q[idx];
+    float delta = gv * ov;
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, of);
+    float dp = 0.f;
+#pragma unroll
+    for (int d = 0; d < TR_DH; ++d) dp = fmaf(__shfl_sync(0xffffffffu, gv, d), vr[d], dp);
+    const float pj = has_key ? p[(((long)b * TR_H + h) * S + s) * T + lane] : 0.f;
+    const float dsj = pj * (dp - delta) * scale;
+#pragma unroll
+    for (int d = 0; d < TR_DH; ++d) {
+      dv[d] = fmaf(pj, __shfl_sync(0xffffffffu, gv, d), dv[d]);
+      dk[d] = fmaf(dsj, __shfl_sync(0xffffffffu, qv, d), dk[d]);
+    }
+    float acc = 0.f;
+    for (int j = 0; j < T; ++j) acc = fmaf(__shfl_sync(0xffffffffu, dsj, j), ks[h][j][lane], acc);
+    dq[idx] = acc;
+  }
+  if (has_key) {
+    float4* okp = reinterpret_cast<float4*>(dkv + ((long)b * T + lane) * 2 * TR_D + h * TR_DH);
+    float4* ovp = reinterpret_cast<float4*>(dkv + ((long)b * T + lane) * 2 * TR_D + TR_D + h * TR_DH);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      okp[u] = make_float4(dk[u * 4], dk[u * 4 + 1], dk[u * 4 + 2], dk[u * 4 + 3]);
+      ovp[u] = make_float4(dv[u * 4], dv[u * 4 + 1], dv[u * 4 + 2], dv[u * 4 + 3]);
     }
   }
 }
@@ -1142,7 +1286,12 @@ int32_t tb_tr_attention_fwd(const float* q, const float* kv, const uint8_t* key_
   TR_CHECK(q && kv && key_valid && o && p && dead, TB_ERR_NULL);
   TR_CHECK(B > 0 && S > 0 && T > 0 && T <= 6144 && (!eye || S == T) && B <= 65535 * 1024, TB_ERR_BAD_SHAPE);
   TR_CHECK(aligned16(kv), TB_ERR_ALIGN);
-  const int smem = AT_QT * T * (int)sizeof(float);
+  if (T <= 32) {  // one warp per (batch element, head)
+    k_tr_attn_small_fwd<<<B, 128, 0, st>>>(q, kv, key_valid, eye, S, T, o, p, dead);
+    count_launch();
+    return launch_status();
+  }
+  const int smem = (AT_QT * T > 4 * AT_QT * 32 ? AT_QT * T : 4 * AT_QT * 32) * (int)sizeof(float);
   static std::atomic<uint64_t> attr_set{0};
   if (smem > 48 * 1024 && !smem_attr_done(attr_set)) {
     if (!set_max_smem(k_tr_attn_fwd, 200 * 1024)) return TB_ERR_LAUNCH;
@@ -1164,6 +1313,12 @@ int32_t tb_tr_attention_bwd(const float* dout, const float* q, const float* kv, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TR_CHECK(dout && q && kv && p && o && dq && dkv, TB_ERR_NULL);
   TR_CHECK(B > 0 && S > 0 && T > 0, TB_ERR_BAD_SHAPE);
+  if (T <= 32) {
+    TR_CHECK(aligned16(kv) && aligned16(dkv), TB_ERR_ALIGN);
+    k_tr_attn_small_bwd<<<B, 128, 0, st>>>(dout, q, kv, p, o, S, T, dq, dkv);
+    count_launch();
+    return launch_status();
+  }
   for (int b0 = 0; b0 < B; b0 += 65535) {
     const int nb = B - b0 < 65535 ? B - b0 : 65535;
     dim3 grid((T + AB_KC - 1) / AB_KC, TR_H, nb);
