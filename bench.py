@@ -46,7 +46,7 @@ CONFIGS = {
     2: dict(n_scene=32, n_agent=64, n_pl=1024, n_mode=6, n_step=90, depth=2, cpu_scenes=6,
             name="BASELINE.json configs[2], per-GPU slice: 32 scenes x K = 6 sampled joint futures (256 scenes over 8 GPUs)"),
     3: dict(n_scene=16, n_agent=64, n_pl=1024, n_mode=1, n_step=90, depth=1, cpu_scenes=2, training=True,
-            name="BASELINE.json configs[3], per-GPU slice: training_step forward + backward + Adam, 16 scenes (128 over 8 GPUs), dropout 0"),
+            name="BASELINE.json configs[3], per-GPU slice: training_step forward + backward + Adam, 16 scenes (128 over 8 GPUs), dropout 0.1"),
     4: dict(n_scene=148, n_agent=128, n_pl=2048, n_mode=1, n_step=90, depth=2, cpu_scenes=4,
             name="BASELINE.json configs[4], stress: 148 scenes x 128 agents x 2048 map polylines, K = 1"),
 }
@@ -559,7 +559,8 @@ TRAIN_KEYS = ("map/valid", "map/type", "map/pos", "map/dir", "map/boundary", "ag
 def train_workload_string(cfg):
     return (f"{cfg['name']}; per step and GPU: {cfg['n_scene']} scenes, {cfg['n_agent']} agents, {cfg['n_pl']} map polylines, 40 TL: "
             "map / agent / TL encoders, destination predictor, posterior + prior latent encoders, 90-step rollout (teacher-forced to "
-            "t = 10), loss = 0.1 KL + IL reward + destination NLL, backward through all of it, gradient all-reduce, clip 5, Adam")
+            "t = 10), dropout 0.1 at every site of the reference, loss = 0.1 KL + IL reward + destination NLL, backward through all of it, "
+            "gradient all-reduce, clip 5, Adam")
 
 
 def train_flops_per_scene(cfg):
@@ -575,7 +576,7 @@ def train_flops_per_scene(cfg):
 
 
 def reference_training_rate(cfg, n_scene, seed=1234):
-    """the UNMODIFIED reference's `training_step` + backward (dropout 0) on the host cores, when its sources are reachable
+    """the UNMODIFIED reference's `training_step` + backward (as shipped: dropout 0.1) on the host cores, when its sources are reachable
     (/root/reference in the build container, baseline/_ref on the GPU box); None otherwise."""
     import ref_loader
     if not ref_loader.reference_available():
@@ -586,7 +587,7 @@ def reference_training_rate(cfg, n_scene, seed=1234):
     model.load_state_dict(weights.init_state_dict(2023), strict=True)
     batch = synthetic.make_batch(n_scene, n_agent=cfg["n_agent"], n_pl=cfg["n_pl"], seed=seed)
     t0 = time.perf_counter()
-    ref_train.run_reference_training(model, batch, seed=0)
+    ref_train.run_reference_training(model, batch, seed=0, dropout=True)
     dt = time.perf_counter() - t0
     return n_scene / dt, dt
 
@@ -616,7 +617,7 @@ def run_training_reference(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": train_workload_string(cfg), "baseline_config": 3, "scenes_per_step": n,
                        "sample": f"{n} scenes per step (bounded sample of the {cfg['n_scene']}-scene batch); unmodified reference "
-                                 f"training_step + backward, dropout 0, {cores} threads"},
+                                 f"training_step + backward as shipped (dropout 0.1), {cores} threads"},
             "cpu_baseline": {"value": value, "unit": "scenes/s", "cores": cores, "kind": "reference",
                              "sample": f"{n} scenes x {args.steps} steps, torch {torch.__version__} CPU fp32 autograd, {cores} threads"},
             "e2e": {"value": value, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -706,10 +707,13 @@ def run_training(args):
         e2e = world * S * steps / (ms_e2e * 1e-3)
         tf = 3.0 * train_flops_per_scene(cfg) * S * steps / (ms * 1e-3) / 1e12
         cpu = None
-        r = reference_training_rate(cfg, cfg["cpu_scenes"])
+        r = None
+        if world == 1:  # the CPU baseline is timed at N = 1 only (all host cores)
+            torch.set_num_threads(os.cpu_count() or 1)
+            r = reference_training_rate(cfg, cfg["cpu_scenes"])
         if r is not None:
             cpu = {"value": r[0], "unit": "scenes/s", "cores": os.cpu_count() or 1, "kind": "reference",
-                   "sample": f"{cfg['cpu_scenes']} scenes, one training_step + backward of the unmodified reference (dropout 0), "
+                   "sample": f"{cfg['cpu_scenes']} scenes, one training_step + backward of the unmodified reference (dropout 0.1), "
                              f"torch {torch.__version__} CPU fp32, {os.cpu_count()} threads"}
         line = {
             "metric": TRAIN_METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": steps, "warmup": warmup,

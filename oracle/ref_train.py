@@ -29,10 +29,12 @@ def draw_training_noise(seed: int, n_scene: int, n_agent: int, latent_dim: int =
     return use_prior, eps
 
 
-def run_reference_training(model, batch: Dict[str, torch.Tensor], seed: int, p_prior: float = 0.1):
-    """-> (loss terms dict, gradients by `named_parameters()` name, extra tensors)."""
+def run_reference_training(model, batch: Dict[str, torch.Tensor], seed: int, p_prior: float = 0.1, dropout: bool = False):
+    """-> (loss terms dict, gradients by `named_parameters()` name, extra tensors).  dropout=False: every dropout probability
+    set to 0 (the parity configuration); True: the module as shipped (p = 0.1 everywhere; used for timing only)."""
     model.train()
-    zero_dropout(model)
+    if not dropout:
+        zero_dropout(model)
     model.hparams.p_training_rollout_prior = p_prior
     for p in model.parameters():
         p.grad = None

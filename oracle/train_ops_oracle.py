@@ -30,6 +30,33 @@ def _grads(outs, ins, gouts):
     return [None if t is None else next(it) for t in ins]
 
 
+def _mix32(x: Tensor) -> Tensor:
+    """lowbias32 on int64 tensors holding uint32 values (the hash of csrc/tb_train.cu::mix32)."""
+    m = 0xFFFFFFFF
+    x = x & m
+    x = x ^ (x >> 16)
+    x = (x * 0x7feb352d) & m
+    x = x ^ (x >> 15)
+    x = (x * 0x846ca68b) & m
+    x = x ^ (x >> 16)
+    return x
+
+
+def drop_factor(drop, shape, device) -> Tensor:
+    """dropout factor tensor of a call site: drop = (seed tensor [1] int32/int64, site id, p); element index = flat index."""
+    if drop is None:
+        return None
+    seed, site, p = drop
+    n = 1
+    for d in shape:
+        n *= d
+    key = _mix32(torch.tensor([(site * 0x9E3779B9) & 0xFFFFFFFF], dtype=torch.int64, device=device) ^ (seed.to(torch.int64).to(device) & 0xFFFFFFFF))
+    h = _mix32((torch.arange(n, dtype=torch.int64, device=device) & 0xFFFFFFFF) ^ key)
+    thresh = int(float(torch.tensor(p, dtype=torch.float32)) * 4294967296.0)  # p as the fp32 value the kernel receives
+    scale = torch.tensor(1.0, dtype=torch.float32) / (torch.tensor(1.0, dtype=torch.float32) - torch.tensor(p, dtype=torch.float32))
+    return ((h >= thresh).to(torch.float32) * scale.to(device)).view(*shape)
+
+
 def _req(*ts):
     return [None if t is None else t.detach().clone().requires_grad_(True) for t in ts]
 
@@ -53,23 +80,25 @@ class OracleOps:
         x *= alpha
 
     # ---- Linear (+ReLU) : models/modules/mlp.py, attention.py in/out projections ----
-    def linear_fwd(self, x: Tensor, w: Tensor, b: Optional[Tensor], relu: bool, keep_lin=None, res=None, keep_out=None) -> Tensor:
-        """y = (relu(x W^T + b) * keep_lin[row] + res) * keep_out[row] -- the optional tail is the residual / row-mask epilogue
-        of a transformer sub-layer (transformer.py:203,220,236-237; attention.py:144-146)."""
+    def linear_fwd(self, x: Tensor, w: Tensor, b: Optional[Tensor], relu: bool, keep_lin=None, res=None, keep_out=None, drop=None) -> Tensor:
+        """y = (dropout(relu(x W^T + b) * keep_lin[row]) + res) * keep_out[row] -- the optional tail is the residual / row-mask
+        epilogue of a transformer sub-layer (transformer.py:203,220,236-237; attention.py:144-146)."""
         y = F.linear(x, w, b)
         y = torch.relu(y) if relu else y
         if keep_lin is not None:
             y = y * keep_lin.to(y.dtype).unsqueeze(-1)
+        if drop is not None:
+            y = y * drop_factor(drop, y.shape, y.device)
         if res is not None:
             y = y + res
         if keep_out is not None:
             y = y * keep_out.to(y.dtype).unsqueeze(-1)
         return y
 
-    def linear_bwd(self, dy, x, w, b, y, relu, dw, db, need_dx: bool, keep_lin=None, keep_out=None):
+    def linear_bwd(self, dy, x, w, b, y, relu, dw, db, need_dx: bool, keep_lin=None, keep_out=None, drop=None):
         """gradients of the Linear part (the residual's gradient is dy * keep_out, formed by the caller)."""
         x_, w_, b_ = _req(x, w, b)
-        gx, gw, gb = _grads(self.linear_fwd(x_, w_, b_, relu, keep_lin, None, keep_out), [x_, w_, b_], dy)
+        gx, gw, gb = _grads(self.linear_fwd(x_, w_, b_, relu, keep_lin, None, keep_out, drop), [x_, w_, b_], dy)
         if dw is not None:
             dw += gw
         if b is not None and db is not None:
@@ -77,21 +106,24 @@ class OracleOps:
         return gx if need_dx else None
 
     # ---- LayerNorm (+ReLU), eps 1e-5 ----
-    def layernorm_fwd(self, x, w, b, relu: bool):
+    def layernorm_fwd(self, x, w, b, relu: bool, drop=None):
         y = F.layer_norm(x, (x.shape[-1],), w, b, 1e-5)
         mean = x.mean(-1)
         rstd = (x.var(-1, unbiased=False) + 1e-5).rsqrt()
-        return (torch.relu(y) if relu else y), torch.stack([mean, rstd], -1)
+        y = torch.relu(y) if relu else y
+        if drop is not None:
+            y = y * drop_factor(drop, y.shape, y.device)
+        return y, torch.stack([mean, rstd], -1)
 
-    def layernorm_bwd(self, dy, x, w, b, stats, y, relu, dw, db):
+    def layernorm_bwd(self, dy, x, w, b, stats, y, relu, dw, db, drop=None):
         x_, w_, b_ = _req(x, w, b)
-        gx, gw, gb = _grads(self.layernorm_fwd(x_, w_, b_, relu)[0], [x_, w_, b_], dy)
+        gx, gw, gb = _grads(self.layernorm_fwd(x_, w_, b_, relu, drop)[0], [x_, w_, b_], dy)
         dw += gw
         db += gb
         return gx
 
     # ---- multi-head cross attention core (models/modules/attention.py:89-141), no projections ----
-    def attention_fwd(self, q: Tensor, kv: Tensor, key_valid: Tensor, eye: bool):
+    def attention_fwd(self, q: Tensor, kv: Tensor, key_valid: Tensor, eye: bool, drop=None):
         """q [B,S,D], kv [B,T,2D] (K | V), key_valid [B,T]; eye: query i may not attend key i (agent_interaction.py:57-59).
         Rows without any admissible key (attention.py:101-107,144-146): o = 0, p = 0, dead = 1."""
         B, S, D = q.shape
@@ -107,13 +139,18 @@ class OracleOps:
         vh = v.reshape(B, T, N_HEAD, dh).transpose(1, 2)
         logits = torch.matmul(qh, kh.transpose(-2, -1)).masked_fill((invalid & ~dead.unsqueeze(-1)).unsqueeze(1), float("-inf"))
         p = torch.softmax(logits / math.sqrt(dh), dim=-1).masked_fill(dead[:, None, :, None], 0.0)
-        o = torch.matmul(p, vh).transpose(1, 2).flatten(2, 3)
+        pd = p if drop is None else p * drop_factor(drop, p.shape, p.device)  # attention.py:131-132
+        o = torch.matmul(pd, vh).transpose(1, 2).flatten(2, 3)
         return o, p, dead.to(torch.uint8)
 
-    def attention_bwd(self, do, q, kv, key_valid, eye, p):
+    def attention_bwd(self, do, q, kv, key_valid, eye, p, drop=None):
         q_, kv_ = _req(q, kv)
-        gq, gkv = _grads(self.attention_fwd(q_, kv_, key_valid, eye)[0], [q_, kv_], do)
+        gq, gkv = _grads(self.attention_fwd(q_, kv_, key_valid, eye, drop)[0], [q_, kv_], do)
         return gq, gkv
+
+    def dropout(self, x, drop):
+        """x * dropout factor (nn.GRU inter-layer dropout); applied to dy it is its own backward."""
+        return x * drop_factor(drop, x.shape, x.device)
 
     # ---- elementwise glue ----
     def add_mask_fwd(self, a, b, keep, keep_a=None):

@@ -324,6 +324,8 @@ def test_public_training_step_and_inference_sees_updated_weights():
     m = WaymoMotion(**config.default_config(n_joint_future=1))
     m.load_state_dict(c["sd"], strict=True)
     m = m.cuda().train()
+    assert m.train_dropout_p == 0.1  # the reference's default; the parity fixtures were produced with dropout 0
+    m.train_dropout_p = 0.0
     batch = {k: v.to(DEV) for k, v in c["batch"].items()}
     m.automatic_optimization = False
     import ref_train
@@ -345,3 +347,113 @@ def test_public_training_step_and_inference_sees_updated_weights():
     assert float((feat1 - feat0).abs().max()) > 1e-6
     opt, sch = m.configure_optimizers()
     assert len(opt) == 1 and len(opt[0].param_groups) == 2 and sch[0]["interval"] == "epoch"
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# dropout: counter-based hash masks (seed on the device, site id, element index), regenerated in the backward kernels
+# ---------------------------------------------------------------------------------------------------------------------------
+def _drop(site, p=0.1, seed=12345):
+    return (torch.tensor([seed], dtype=torch.int32), site, p)
+
+
+def _dropg(d):
+    return (d[0].to(DEV), d[1], d[2])
+
+
+def test_dropout_mask_statistics_and_elementwise_op(ops):
+    x = torch.ones(1000, 128)
+    for site, p in ((1, 0.1), (2, 0.1), (77, 0.5)):
+        d = _drop(site, p)
+        y = ops.dropout(x.to(DEV), _dropg(d)).cpu()
+        close(y, ORC.dropout(x, d), tol=1e-7)
+        keep = float((y > 0).float().mean())
+        assert abs(keep - (1 - p)) < 0.01, (site, p, keep)
+        assert abs(float(y.mean()) - 1.0) < 0.02
+    a = ops.dropout(x.to(DEV), _dropg(_drop(1))).cpu()
+    b = ops.dropout(x.to(DEV), _dropg(_drop(2))).cpu()
+    c = ops.dropout(x.to(DEV), _dropg(_drop(1, seed=999))).cpu()
+    assert 0.7 < float(((a > 0) == (b > 0)).float().mean()) < 0.9  # different sites / seeds: independent masks
+    assert 0.7 < float(((a > 0) == (c > 0)).float().mean()) < 0.9
+
+
+def test_dropout_in_linear_layernorm_attention(ops):
+    torch.manual_seed(21)
+    M, K, N = 300, 128, 128
+    x, w, b, res, dy = torch.randn(M, K), torch.randn(N, K) / K ** 0.5, torch.randn(N) * 0.1, torch.randn(M, N), torch.randn(M, N)
+    kl, ko = (torch.rand(M) < 0.7).to(torch.uint8), (torch.rand(M) < 0.8).to(torch.uint8)
+    for relu, keep_lin, r, keep_out, site in ((True, None, None, None, 3), (False, kl, res, None, 4), (False, None, res, ko, 5)):
+        d = _drop(site)
+        y_ref = ORC.linear_fwd(x, w, b, relu, keep_lin, r, keep_out, d)
+        dw_ref, db_ref = torch.zeros_like(w), torch.zeros(N)
+        dx_ref = ORC.linear_bwd(dy, x, w, b, y_ref, relu, dw_ref, db_ref, True, keep_lin, keep_out, d)
+        xg, wg, bg, dyg, klg, rg, kog = g(x, w, b, dy, keep_lin, r, keep_out)
+        y = ops.linear_fwd(xg, wg, bg, relu, klg, rg, kog, _dropg(d))
+        close(y, y_ref, what="y")
+        dwg, dbg = torch.zeros_like(wg), torch.zeros(N, device=DEV)
+        dx = ops.linear_bwd(dyg, xg, wg, bg, y, relu, dwg, dbg, True, klg, kog, _dropg(d))
+        close(dx, dx_ref, what="dx")
+        close(dwg, dw_ref, tol=5e-5, what="dw")
+        close(dbg, db_ref, tol=5e-5, what="db")
+    # big-M path (64-row tiles) with a weight-gradient row split
+    M2 = 9000
+    x2, dy2 = torch.randn(M2, K), torch.randn(M2, N)
+    d = _drop(6)
+    y_ref = ORC.linear_fwd(x2, w, b, True, drop=d)
+    dw_ref, db_ref = torch.zeros_like(w), torch.zeros(N)
+    dx_ref = ORC.linear_bwd(dy2, x2, w, b, y_ref, True, dw_ref, db_ref, True, drop=d)
+    y = ops.linear_fwd(x2.to(DEV), w.to(DEV), b.to(DEV), True, drop=_dropg(d))
+    close(y, y_ref)
+    dwg, dbg = torch.zeros(N, K, device=DEV), torch.zeros(N, device=DEV)
+    close(ops.linear_bwd(dy2.to(DEV), x2.to(DEV), w.to(DEV), b.to(DEV), y, True, dwg, dbg, True, drop=_dropg(d)), dx_ref)
+    close(dwg, dw_ref, tol=5e-5)
+    # LayerNorm + ReLU + dropout (add_goal.mlp_in)
+    lw, lb = torch.rand(128) + 0.5, torch.randn(128) * 0.2
+    d = _drop(7)
+    y_ref, st_ref = ORC.layernorm_fwd(x, lw, lb, True, d)
+    dw_ref, db_ref = torch.zeros(128), torch.zeros(128)
+    dx_ref = ORC.layernorm_bwd(dy, x, lw, lb, st_ref, y_ref, True, dw_ref, db_ref, d)
+    y, st = ops.layernorm_fwd(x.to(DEV), lw.to(DEV), lb.to(DEV), True, _dropg(d))
+    close(y, y_ref)
+    dwg, dbg = torch.zeros(128, device=DEV), torch.zeros(128, device=DEV)
+    close(ops.layernorm_bwd(dy.to(DEV), x.to(DEV), lw.to(DEV), lb.to(DEV), st, y, True, dwg, dbg, _dropg(d)), dx_ref, tol=5e-5)
+    close(dwg, dw_ref, tol=5e-5)
+    # attention probabilities: general kernel (T = 200, two key chunks) and the warp-per-head kernel (T = 20)
+    for B, S, T, eye, site in ((2, 70, 200, False, 8), (3, 20, 20, False, 9), (4, 8, 8, True, 10)):
+        q, kv, do = torch.randn(B, S, 128), torch.randn(B, T, 256), torch.randn(B, S, 128)
+        kvalid = (torch.rand(B, T) < 0.8).to(torch.uint8)
+        d = _drop(site)
+        o_ref, p_ref, dead_ref = ORC.attention_fwd(q, kv, kvalid, eye, d)
+        dq_ref, dkv_ref = ORC.attention_bwd(do, q, kv, kvalid, eye, p_ref, d)
+        o, p, dead = ops.attention_fwd(q.to(DEV), kv.to(DEV), kvalid.to(DEV), eye, _dropg(d))
+        close(o, o_ref, what="o")
+        close(p[0], p_ref, what="p")
+        dq, dkv = ops.attention_bwd(do.to(DEV), q.to(DEV), kv.to(DEV), kvalid.to(DEV), eye, p, _dropg(d))
+        close(dq, dq_ref, tol=5e-5, what="dq", atol=1e-5)
+        close(dkv, dkv_ref, tol=5e-5, what="dkv")
+
+
+def test_training_step_with_dropout_matches_cpu_restatement():
+    """the whole step with dropout 0.1: the hash masks are a pure function of (seed, site, element), so the torch restatement on
+    the CPU draws the same masks; loss and gradients must agree (closed-loop amplification as in the dropout-free test)."""
+    from trafficbots_b200.train import trainer
+    c = load_train_case(TRAIN_CASES[0])
+    ts = trainer.TrainState(c["sd"], device=DEV, dropout_p=0.1)
+    ref = trainer.TrainState(c["sd"], device="cpu", ops=ORC, dropout_p=0.1)
+    for t in (ts, ref):
+        t.new_dropout_seed(4242)
+    batch = {k: v.to(DEV) for k, v in c["batch"].items()}
+    out = ts.forward_backward(batch, c["eps"], c["use_prior"], new_seed=False)
+    out_ref = ref.forward_backward(c["batch"], c["eps"], c["use_prior"], new_seed=False)
+    assert abs(float(out["loss"]) - float(out_ref["loss"])) <= 2e-4 * abs(float(out_ref["loss"]))
+    assert abs(float(out["loss"]) - c["terms"]["loss"]) > 1e-3  # dropout really changed the step
+    total = float(ref.flat_g.norm())
+    worst = 0.0
+    for k, gref in ref.grads().items():
+        n = gref.numel()
+        err = float((ts.grads()[k].cpu() - gref).abs().max())
+        scale = float(gref.norm()) / n ** 0.5 * 8.0 + 1e-6 * total
+        worst = max(worst, err / scale)
+    assert worst <= 5e-3, worst
+    # a second step draws new masks
+    out2 = ts.forward_backward(batch, c["eps"], c["use_prior"])
+    assert abs(float(out2["loss"]) - float(out["loss"])) > 1e-6

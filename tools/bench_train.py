@@ -58,7 +58,7 @@ def graph_mode():
     P = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
     rep = int(sys.argv[4]) if len(sys.argv) > 4 else 3
     dev = "cuda:0"
-    ts = trainer.TrainState(weights.init_state_dict(2023), device=dev)
+    ts = trainer.TrainState(weights.init_state_dict(2023), device=dev, dropout_p=float(os.environ.get("TB_TRAIN_DROPOUT", "0")))
     ts.ops.check = False
     batch = {k: v.to(dev) for k, v in synthetic.make_batch(S, n_agent=A, n_pl=P, seed=7).items()}
     torch.manual_seed(0)

@@ -255,7 +255,7 @@ def lib() -> C.CDLL:
     return L
 
 
-_CTYPE = {"int64_t": C.c_int64, "int32_t": C.c_int32, "float": C.c_float}
+_CTYPE = {"int64_t": C.c_int64, "int32_t": C.c_int32, "uint32_t": C.c_uint32, "float": C.c_float}
 
 
 def training_signatures():

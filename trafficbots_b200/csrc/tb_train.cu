@@ -28,6 +28,38 @@ enum { EPI_BIAS = 0, EPI_STORE = 1, EPI_ATOMIC = 2 };
 // Per-tile options.  A operand: `ym` = ReLU mask source (same indexing as A: element kept where ym > 0), `rm1` / `rm2` = row masks
 // over the M ("sample") dimension of A (uint8, element dropped where 0).  EPI_BIAS epilogue: v = acc + bias; ReLU; v *= keep_lin[i];
 // v += res[i, j]; v *= keep_out[i].  `rowsum` (EPI_ATOMIC tiles with tile_j == 0): rowsum[i] += sum_k A(i, k) (bias gradient).
+// Dropout (nn.Dropout in training mode: mlp.py:53-63, transformer.py:116-134, attention.py:131-132, nn.GRU inter-layer): the keep
+// mask is a counter-based hash of (per-step seed on the device, site id of the call, element index) -- reproducible in the
+// backward kernel without storing it.  seed == NULL switches it off.
+struct Drop {
+  const uint32_t* seed;
+  uint32_t site;
+  uint32_t thresh;  // element kept iff hash >= thresh (= p * 2^32)
+  float scale;      // 1 / (1 - p)
+};
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t drop_key(const Drop& d) { return d.seed ? mix32(d.site * 0x9E3779B9u ^ d.seed[0]) : 0u; }
+__device__ __forceinline__ float drop_factor(const Drop& d, uint32_t key, long idx) {
+  return mix32((uint32_t)idx ^ key) >= d.thresh ? d.scale : 0.f;
+}
+inline Drop make_drop(const uint32_t* seed, uint32_t site, float p) {
+  Drop d{nullptr, 0u, 0u, 1.f};
+  if (seed && p > 0.f) {
+    d.seed = seed;
+    d.site = site;
+    d.thresh = (uint32_t)((double)p * 4294967296.0);
+    d.scale = 1.f / (1.f - p);
+  }
+  return d;
+}
+
 struct GemmOpt {
   const float* ym;
   const uint8_t* rm1;
@@ -38,6 +70,7 @@ struct GemmOpt {
   const float* res;
   const uint8_t* keep_out;
   float* rowsum;
+  Drop drop;  // forward: applied after ReLU / keep_lin, before the residual; backward: applied to the A operand (dY)
 };
 
 // The next k-slab is fetched into registers while the current one is multiplied out of shared memory (global-load latency
@@ -72,6 +105,8 @@ __device__ __forceinline__ void gemm_tile(float (&As)[GK][GM + 4], float (&Bs)[G
   const bool a_al = a_vec && ((reinterpret_cast<uintptr_t>(a) & 15) == 0) && (!ym || (reinterpret_cast<uintptr_t>(ym) & 15) == 0);
   const bool b_al = b_vec && ((reinterpret_cast<uintptr_t>(b) & 15) == 0);
   float ra[4], rb[4];
+  const bool a_drop = EPI != EPI_BIAS && op.drop.seed != nullptr;
+  const uint32_t dkey = drop_key(op.drop);
 
   auto fetch = [&](long k0) {
     // ---- A ----
@@ -128,6 +163,11 @@ __device__ __forceinline__ void gemm_tile(float (&As)[GK][GM + 4], float (&Bs)[G
           ra[u] = v;
         }
       }
+    }
+    if (a_drop && a_thread) {  // the 4 elements are consecutive in dY: offsets off .. off + 3
+      const long off = A_KCONTIG ? (i0 + a_r) * sai + (k0 + a_k) : (i0 + a_r) + (k0 + a_k) * sak;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ra[u] *= drop_factor(op.drop, dkey, off + (A_KCONTIG ? u * sak : u * sai));
     }
     // ---- B ----
     if (B_JCONTIG) {
@@ -214,6 +254,7 @@ __device__ __forceinline__ void gemm_tile(float (&As)[GK][GM + 4], float (&Bs)[G
         if (op.bias) v += op.bias[j];
         if (op.relu) v = fmaxf(v, 0.f);
         v *= kl;
+        if (op.drop.seed) v *= drop_factor(op.drop, dkey, i * ldc + j);
         if (op.res) v += op.res[i * ldc + j];
         v *= ko;
         c[i * ldc + j] = v;
@@ -263,7 +304,7 @@ __global__ void __launch_bounds__(256) k_tr_linear_bwd(const float* __restrict__
 // =====================================================================================================================
 __global__ void __launch_bounds__(256) k_tr_ln_fwd(const float* __restrict__ x, const float* __restrict__ w,
                                                    const float* __restrict__ b, int relu, long M, float* __restrict__ y,
-                                                   float* __restrict__ stats) {
+                                                   float* __restrict__ stats, Drop drop) {
   const long row = (long)blockIdx.x * 8 + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   if (row >= M) return;
@@ -280,6 +321,12 @@ __global__ void __launch_bounds__(256) k_tr_ln_fwd(const float* __restrict__ x, 
   const float4 wv = reinterpret_cast<const float4*>(w)[lane], bv = reinterpret_cast<const float4*>(b)[lane];
   float4 o4 = make_float4(dx * rstd * wv.x + bv.x, dy * rstd * wv.y + bv.y, dz * rstd * wv.z + bv.z, dw * rstd * wv.w + bv.w);
   if (relu) o4 = make_float4(fmaxf(o4.x, 0.f), fmaxf(o4.y, 0.f), fmaxf(o4.z, 0.f), fmaxf(o4.w, 0.f));
+  if (drop.seed) {
+    const uint32_t key = drop_key(drop);
+    const long e0 = row * TR_D + lane * 4;
+    o4.x *= drop_factor(drop, key, e0), o4.y *= drop_factor(drop, key, e0 + 1), o4.z *= drop_factor(drop, key, e0 + 2),
+        o4.w *= drop_factor(drop, key, e0 + 3);
+  }
   reinterpret_cast<float4*>(y + row * TR_D)[lane] = o4;
   if (lane == 0) {
     stats[row * 2] = mean;
@@ -291,14 +338,20 @@ __global__ void __launch_bounds__(256) k_tr_ln_fwd(const float* __restrict__ x, 
 __global__ void __launch_bounds__(256) k_tr_ln_bwd(const float* __restrict__ dy, const float* __restrict__ x,
                                                    const float* __restrict__ w, const float* __restrict__ stats,
                                                    const float* __restrict__ y, int relu, long M, long rows_per_block,
-                                                   float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db) {
+                                                   float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, Drop drop) {
   __shared__ float red[2][8][TR_D];
+  const uint32_t dkey = drop_key(drop);
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const long r_lo = (long)blockIdx.x * rows_per_block, r_hi = min(M, r_lo + rows_per_block);
   const float4 wv = reinterpret_cast<const float4*>(w)[lane];
   float aw[4] = {}, ab[4] = {};
   for (long row = r_lo + warp; row < r_hi; row += 8) {
     float4 g = reinterpret_cast<const float4*>(dy + row * TR_D)[lane];
+    if (drop.seed) {
+      const long e0 = row * TR_D + lane * 4;
+      g.x *= drop_factor(drop, dkey, e0), g.y *= drop_factor(drop, dkey, e0 + 1), g.z *= drop_factor(drop, dkey, e0 + 2),
+          g.w *= drop_factor(drop, dkey, e0 + 3);
+    }
     if (relu) {
       const float4 yv = reinterpret_cast<const float4*>(y + row * TR_D)[lane];
       if (!(yv.x > 0.f)) g.x = 0.f;
@@ -355,7 +408,8 @@ constexpr int AT_QT = 8;  // queries per CTA (forward)
 // grid (ceil(S / AT_QT), H, B), 128 threads; dynamic smem: AT_QT * T logits
 __global__ void __launch_bounds__(128, 4) k_tr_attn_fwd(const float* __restrict__ q, const float* __restrict__ kv,
                                                      const uint8_t* __restrict__ key_valid, int eye, int S, int T,
-                                                     float* __restrict__ o, float* __restrict__ p, uint8_t* __restrict__ dead) {
+                                                     float* __restrict__ o, float* __restrict__ p, uint8_t* __restrict__ dead,
+                                                     Drop drop, long b_off) {
   extern __shared__ __align__(16) float sm[];
   float* lg = sm;                     // [AT_QT][T]
   __shared__ float qs[AT_QT][TR_DH];
@@ -370,6 +424,7 @@ __global__ void __launch_bounds__(128, 4) k_tr_attn_fwd(const float* __restrict_
   __syncthreads();
   const float scale = 0.17677669529663688110f;  // 1 / sqrt(32), applied after the -inf fill (attention.py:128-130)
   const float NEG = -INFINITY;
+  const uint32_t dkey = drop_key(drop);
   for (int j = tid; j < T; j += 128) {
     const float4* kp = reinterpret_cast<const float4*>(kv + ((long)b * T + j) * 2 * TR_D + h * TR_DH);
     float kr[TR_DH];
@@ -417,8 +472,9 @@ __global__ void __launch_bounds__(128, 4) k_tr_attn_fwd(const float* __restrict_
   for (int e = tid; e < nq * T; e += 128) {
     const int qi = e / T, j = e % T;
     const float pv = lg[qi * T + j] * rinv[qi];
-    lg[qi * T + j] = pv;
-    p[(((long)b * TR_H + h) * S + s0 + qi) * T + j] = pv;
+    const long pidx = (((long)b * TR_H + h) * S + s0 + qi) * T + j;
+    p[pidx] = pv;  // the un-dropped probabilities are what the backward needs; O uses the dropped ones (attention.py:131-136)
+    lg[qi * T + j] = drop.seed ? pv * drop_factor(drop, dkey, pidx + b_off) : pv;
   }
   __syncthreads();
   // O = P V : thread (d, key slice g) accumulates all AT_QT queries over the keys {4 (g + 4 i) .. + 3}; the four slices are then
@@ -466,10 +522,12 @@ constexpr int AB_LDS = AB_KC + 4;  // 68: row stride of the [16, 64] tiles
 __global__ void __launch_bounds__(256) k_tr_attn_bwd(const float* __restrict__ dout, const float* __restrict__ q,
                                                      const float* __restrict__ kv, const float* __restrict__ p,
                                                      const float* __restrict__ o, int S, int T, float* __restrict__ dq,
-                                                     float* __restrict__ dkv) {
+                                                     float* __restrict__ dkv, Drop drop, long b_off) {
   __shared__ __align__(16) float ks[AB_KC][AB_LD], vs[AB_KC][AB_LD];
   __shared__ __align__(16) float qs[AB_QT][AB_LD], gs[AB_QT][AB_LD];
   __shared__ __align__(16) float ps[AB_QT][AB_LDS], ds[AB_QT][AB_LDS];
+  __shared__ __align__(16) float pf[AB_QT][AB_LDS];  // P * dropout factor (= P without dropout): what multiplied V in the forward
+  const uint32_t dkey = drop_key(drop);
   __shared__ float delta[AB_QT];
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * AB_KC;
   const int tid = threadIdx.x;
@@ -498,7 +556,10 @@ __global__ void __launch_bounds__(256) k_tr_attn_bwd(const float* __restrict__ d
     }
     for (int e = tid; e < AB_QT * AB_KC; e += 256) {
       const int qi = e / AB_KC, j = e % AB_KC;
-      ps[qi][j] = (qi < nq && j < nk) ? p[(((long)b * TR_H + h) * S + s0 + qi) * T + j0 + j] : 0.f;
+      const long pidx = (((long)b * TR_H + h) * S + s0 + qi) * T + j0 + j;
+      const float pv = (qi < nq && j < nk) ? p[pidx] : 0.f;
+      ps[qi][j] = pv;
+      pf[qi][j] = drop.seed ? pv * drop_factor(drop, dkey, pidx + b_off) : pv;
     }
     if (tid < AB_QT * 2) {  // delta = sum_d do * o, two half rows per query
       const int qi = tid / 2, half = tid % 2;
@@ -524,7 +585,7 @@ __global__ void __launch_bounds__(256) k_tr_attn_bwd(const float* __restrict__ d
       }
       const float dl = delta[sq];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) ds[sq][sj + 16 * u] = ps[sq][sj + 16 * u] * (dp[u] - dl) * scale;
+      for (int u = 0; u < 4; ++u) ds[sq][sj + 16 * u] = (pf[sq][sj + 16 * u] * dp[u] - ps[sq][sj + 16 * u] * dl) * scale;
     }
     __syncthreads();
     if (sq < nq) {  // dQ partial of (sq, 2 sj .. 2 sj + 1)
@@ -548,7 +609,7 @@ __global__ void __launch_bounds__(256) k_tr_attn_bwd(const float* __restrict__ d
     for (int qi = 0; qi < AB_QT; ++qi) {
       const float qv = qs[qi][od], gv = gs[qi][od];
       const float4 da = *reinterpret_cast<const float4*>(&ds[qi][oj * 8]), db = *reinterpret_cast<const float4*>(&ds[qi][oj * 8 + 4]);
-      const float4 pa = *reinterpret_cast<const float4*>(&ps[qi][oj * 8]), pb = *reinterpret_cast<const float4*>(&ps[qi][oj * 8 + 4]);
+      const float4 pa = *reinterpret_cast<const float4*>(&pf[qi][oj * 8]), pb = *reinterpret_cast<const float4*>(&pf[qi][oj * 8 + 4]);
       adk[0] = fmaf(da.x, qv, adk[0]), adk[1] = fmaf(da.y, qv, adk[1]), adk[2] = fmaf(da.z, qv, adk[2]), adk[3] = fmaf(da.w, qv, adk[3]);
       adk[4] = fmaf(db.x, qv, adk[4]), adk[5] = fmaf(db.y, qv, adk[5]), adk[6] = fmaf(db.z, qv, adk[6]), adk[7] = fmaf(db.w, qv, adk[7]);
       adv[0] = fmaf(pa.x, gv, adv[0]), adv[1] = fmaf(pa.y, gv, adv[1]), adv[2] = fmaf(pa.z, gv, adv[2]), adv[3] = fmaf(pa.w, gv, adv[3]);
@@ -571,8 +632,10 @@ __global__ void __launch_bounds__(256) k_tr_attn_bwd(const float* __restrict__ d
 // warp reductions, O = P V is accumulated with lane = feature.  Same arithmetic as the general kernel.
 __global__ void __launch_bounds__(128) k_tr_attn_small_fwd(const float* __restrict__ q, const float* __restrict__ kv,
                                                            const uint8_t* __restrict__ key_valid, int eye, int S, int T,
-                                                           float* __restrict__ o, float* __restrict__ p, uint8_t* __restrict__ dead) {
+                                                           float* __restrict__ o, float* __restrict__ p, uint8_t* __restrict__ dead,
+                                                           Drop drop) {
   __shared__ float vs[TR_H][32][TR_DH + 1];
+  const uint32_t dkey = drop_key(drop);
   const int b = blockIdx.x, h = threadIdx.x / 32, lane = threadIdx.x % 32;
   const bool has_key = lane < T;
   float kr[TR_DH];
@@ -608,10 +671,12 @@ __global__ void __launch_bounds__(128) k_tr_attn_small_fwd(const float* __restri
 #pragma unroll
     for (int of = 16; of > 0; of >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, of);
     const float pv = m > -INFINITY ? e * (1.f / sum) : 0.f;
-    if (has_key) p[(((long)b * TR_H + h) * S + s) * T + lane] = pv;
+    const long pidx = (((long)b * TR_H + h) * S + s) * T + lane;
+    if (has_key) p[pidx] = pv;
     if (h == 0 && lane == 0) dead[row] = m > -INFINITY ? 0 : 1;
+    const float pd = (drop.seed && has_key) ? pv * drop_factor(drop, dkey, pidx) : pv;
     float acc = 0.f;
-    for (int j = 0; j < T; ++j) acc = fmaf(__shfl_sync(0xffffffffu, pv, j), vs[h][j][lane], acc);
+    for (int j = 0; j < T; ++j) acc = fmaf(__shfl_sync(0xffffffffu, pd, j), vs[h][j][lane], acc);
     o[row * TR_D + h * TR_DH + lane] = acc;
   }
 }
@@ -621,8 +686,9 @@ __global__ void __launch_bounds__(128) k_tr_attn_small_fwd(const float* __restri
 __global__ void __launch_bounds__(128) k_tr_attn_small_bwd(const float* __restrict__ dout, const float* __restrict__ q,
                                                            const float* __restrict__ kv, const float* __restrict__ p,
                                                            const float* __restrict__ o, int S, int T, float* __restrict__ dq,
-                                                           float* __restrict__ dkv) {
+                                                           float* __restrict__ dkv, Drop drop) {
   __shared__ float ks[TR_H][32][TR_DH + 1];
+  const uint32_t dkey = drop_key(drop);
   const int b = blockIdx.x, h = threadIdx.x / 32, lane = threadIdx.x % 32;
   const bool has_key = lane < T;
   float vr[TR_DH], dk[TR_DH], dv[TR_DH];
@@ -649,11 +715,13 @@ __global__ void __launch_bounds__(128) k_tr_attn_small_bwd(const float* __restri
     float dp = 0.f;
 #pragma unroll
     for (int d = 0; d < TR_DH; ++d) dp = fmaf(__shfl_sync(0xffffffffu, gv, d), vr[d], dp);
-    const float pj = has_key ? p[(((long)b * TR_H + h) * S + s) * T + lane] : 0.f;
-    const float dsj = pj * (dp - delta) * scale;
+    const long pidx = (((long)b * TR_H + h) * S + s) * T + lane;
+    const float pj = has_key ? p[pidx] : 0.f;
+    const float pjf = (drop.seed && has_key) ? pj * drop_factor(drop, dkey, pidx) : pj;
+    const float dsj = (pjf * dp - pj * delta) * scale;
 #pragma unroll
     for (int d = 0; d < TR_DH; ++d) {
-      dv[d] = fmaf(pj, __shfl_sync(0xffffffffu, gv, d), dv[d]);
+      dv[d] = fmaf(pjf, __shfl_sync(0xffffffffu, gv, d), dv[d]);
       dk[d] = fmaf(dsj, __shfl_sync(0xffffffffu, qv, d), dk[d]);
     }
     float acc = 0.f;
@@ -686,6 +754,13 @@ __global__ void k_tr_add_mask(const float* __restrict__ a, const uint8_t* __rest
     if (keep && !keep[m]) v = 0.f;
     y[e] = v;
   }
+}
+
+// y = x * dropout factor(site, element index): nn.GRU's inter-layer dropout; the same call is its own backward
+__global__ void k_tr_dropout(const float* __restrict__ x, long n, float* __restrict__ y, Drop drop) {
+  const uint32_t key = drop_key(drop);
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x)
+    y[e] = x[e] * drop_factor(drop, key, e);
 }
 
 __global__ void k_tr_axpy(float* __restrict__ dst, long ld_dst, const float* __restrict__ src, long ld_src, long M, int N) {
@@ -1202,13 +1277,14 @@ using namespace tb;
 
 extern "C" {
 
-// y = (relu(x W^T + bias) * keep_lin[row] + res) * keep_out[row]; bias / keep_lin / res / keep_out may be NULL
+// y = (dropout(relu(x W^T + bias) * keep_lin[row]) + res) * keep_out[row]; bias / keep_lin / res / keep_out / drop_seed may be NULL
 int32_t tb_tr_linear_fwd(const float* x, int64_t M, int32_t K, const float* w, int64_t ldw, int32_t N, const float* bias, int32_t relu,
-                         const uint8_t* keep_lin, const float* res, const uint8_t* keep_out, float* y, void* stream) {
+                         const uint8_t* keep_lin, const float* res, const uint8_t* keep_out, float* y, const uint32_t* drop_seed,
+                         uint32_t drop_site, float drop_p, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TR_CHECK(x && w && y, TB_ERR_NULL);
   TR_CHECK(M > 0 && K > 0 && N > 0 && ldw >= K, TB_ERR_BAD_SHAPE);
-  GemmOpt op{nullptr, nullptr, nullptr, bias, relu, keep_lin, res, keep_out, nullptr};
+  GemmOpt op{nullptr, nullptr, nullptr, bias, relu, keep_lin, res, keep_out, nullptr, make_drop(drop_seed, drop_site, drop_p)};
   if (M <= SMALL_M) {
     dim3 grid((unsigned)((M + 31) / 32), (N + GN - 1) / GN, 1);
     k_tr_gemm<32, true, false, EPI_BIAS><<<grid, 256, 0, st>>>(x, K, 1, w, 1, ldw, y, N, M, N, K, K, op);
@@ -1220,11 +1296,11 @@ int32_t tb_tr_linear_fwd(const float* x, int64_t M, int32_t K, const float* w, i
   return launch_status();
 }
 
-// dx = dY' W; dw += dY'^T x; db += colsum(dY') with dY' = dy * relu'(y) * rm1[row] * rm2[row] (row masks may be NULL: the
-// keep_lin / keep_out of the forward).  dx / dw / db may be NULL (skipped); db needs dw.
+// dx = dY' W; dw += dY'^T x; db += colsum(dY') with dY' = dy * relu'(y) * dropout mask * rm1[row] * rm2[row] (row masks may be
+// NULL: the keep_lin / keep_out of the forward; drop_* as in the forward).  dx / dw / db may be NULL (skipped); db needs dw.
 int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_t ldw, const float* y, int32_t relu, const uint8_t* rm1,
                          const uint8_t* rm2, int64_t M, int32_t K, int32_t N, float* dx, float* dw, int64_t lddw, float* db,
-                         void* stream) {
+                         const uint32_t* drop_seed, uint32_t drop_site, float drop_p, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TR_CHECK(dy && x && w, TB_ERR_NULL);
   TR_CHECK(M > 0 && K > 0 && N > 0 && (!relu || y), TB_ERR_BAD_SHAPE);
@@ -1246,7 +1322,7 @@ int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_
   }
   const long total = n_dx + nz * dw_tiles_i * dw_tiles_j;
   TR_CHECK(total > 0 && total < 2147483647L, TB_ERR_BAD_SHAPE);
-  GemmOpt op{relu ? y : nullptr, rm1, rm2, nullptr, 0, nullptr, nullptr, nullptr, db};
+  GemmOpt op{relu ? y : nullptr, rm1, rm2, nullptr, 0, nullptr, nullptr, nullptr, db, make_drop(drop_seed, drop_site, drop_p)};
   if (TMh == 32)
     k_tr_linear_bwd<32><<<(unsigned)total, 256, 0, st>>>(dy, x, w, ldw, M, K, N, dx, dw, lddw, (int)n_dx, dx_tiles_j, dw_tiles_i,
                                                          dw_tiles_j, chunk, op);
@@ -1258,36 +1334,40 @@ int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_
 }
 
 int32_t tb_tr_layernorm_fwd(const float* x, const float* w, const float* b, int32_t relu, int64_t M, int32_t D, float* y, float* stats,
-                        void* stream) {
+                        const uint32_t* drop_seed, uint32_t drop_site,
+                        float drop_p, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TR_CHECK(x && w && b && y && stats, TB_ERR_NULL);
   TR_CHECK(M > 0 && D == TR_D, TB_ERR_BAD_SHAPE);
   TR_CHECK(aligned16(x) && aligned16(y) && aligned16(w) && aligned16(b), TB_ERR_ALIGN);
-  k_tr_ln_fwd<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(x, w, b, relu, M, y, stats);
+  k_tr_ln_fwd<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(x, w, b, relu, M, y, stats, make_drop(drop_seed, drop_site, drop_p));
   count_launch();
   return launch_status();
 }
 
 int32_t tb_tr_layernorm_bwd(const float* dy, const float* x, const float* w, const float* stats, const float* y, int32_t relu, int64_t M,
-                        int32_t D, float* dx, float* dw, float* db, void* stream) {
+                        int32_t D, float* dx, float* dw, float* db, const uint32_t* drop_seed, uint32_t drop_site,
+                        float drop_p, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TR_CHECK(dy && x && w && stats && dx, TB_ERR_NULL);
   TR_CHECK(M > 0 && D == TR_D && (!relu || y) && ((dw == nullptr) == (db == nullptr)), TB_ERR_BAD_SHAPE);
   TR_CHECK(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(w), TB_ERR_ALIGN);
   const long rows = 64;
-  k_tr_ln_bwd<<<(unsigned)((M + rows - 1) / rows), 256, 0, st>>>(dy, x, w, stats, y, relu, M, rows, dx, dw, db);
+  k_tr_ln_bwd<<<(unsigned)((M + rows - 1) / rows), 256, 0, st>>>(dy, x, w, stats, y, relu, M, rows, dx, dw, db,
+                                                                 make_drop(drop_seed, drop_site, drop_p));
   count_launch();
   return launch_status();
 }
 
 int32_t tb_tr_attention_fwd(const float* q, const float* kv, const uint8_t* key_valid, int32_t eye, int32_t B, int32_t S, int32_t T,
-                        float* o, float* p, uint8_t* dead, void* stream) {
+                        float* o, float* p, uint8_t* dead, const uint32_t* drop_seed, uint32_t drop_site,
+                        float drop_p, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TR_CHECK(q && kv && key_valid && o && p && dead, TB_ERR_NULL);
   TR_CHECK(B > 0 && S > 0 && T > 0 && T <= 6144 && (!eye || S == T) && B <= 65535 * 1024, TB_ERR_BAD_SHAPE);
   TR_CHECK(aligned16(kv), TB_ERR_ALIGN);
   if (T <= 32) {  // one warp per (batch element, head)
-    k_tr_attn_small_fwd<<<B, 128, 0, st>>>(q, kv, key_valid, eye, S, T, o, p, dead);
+    k_tr_attn_small_fwd<<<B, 128, 0, st>>>(q, kv, key_valid, eye, S, T, o, p, dead, make_drop(drop_seed, drop_site, drop_p));
     count_launch();
     return launch_status();
   }
@@ -1301,7 +1381,8 @@ int32_t tb_tr_attention_fwd(const float* q, const float* kv, const uint8_t* key_
     const int nb = B - b0 < 65535 ? B - b0 : 65535;
     dim3 grid((S + AT_QT - 1) / AT_QT, TR_H, nb);
     k_tr_attn_fwd<<<grid, 128, smem, st>>>(q + (size_t)b0 * S * TR_D, kv + (size_t)b0 * T * 2 * TR_D, key_valid + (size_t)b0 * T, eye, S,
-                                           T, o + (size_t)b0 * S * TR_D, p + (size_t)b0 * TR_H * S * T, dead + (size_t)b0 * S);
+                                           T, o + (size_t)b0 * S * TR_D, p + (size_t)b0 * TR_H * S * T, dead + (size_t)b0 * S,
+                                           make_drop(drop_seed, drop_site, drop_p), (long)b0 * TR_H * S * T);
     count_launch();
   }
   return launch_status();
@@ -1309,13 +1390,14 @@ int32_t tb_tr_attention_fwd(const float* q, const float* kv, const uint8_t* key_
 
 // dq must be zero-initialised by the caller (partials are added atomically); dkv is overwritten
 int32_t tb_tr_attention_bwd(const float* dout, const float* q, const float* kv, const float* p, const float* o, int32_t B, int32_t S,
-                        int32_t T, float* dq, float* dkv, void* stream) {
+                        int32_t T, float* dq, float* dkv, const uint32_t* drop_seed, uint32_t drop_site,
+                        float drop_p, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TR_CHECK(dout && q && kv && p && o && dq && dkv, TB_ERR_NULL);
   TR_CHECK(B > 0 && S > 0 && T > 0, TB_ERR_BAD_SHAPE);
   if (T <= 32) {
     TR_CHECK(aligned16(kv) && aligned16(dkv), TB_ERR_ALIGN);
-    k_tr_attn_small_bwd<<<B, 128, 0, st>>>(dout, q, kv, p, o, S, T, dq, dkv);
+    k_tr_attn_small_bwd<<<B, 128, 0, st>>>(dout, q, kv, p, o, S, T, dq, dkv, make_drop(drop_seed, drop_site, drop_p));
     count_launch();
     return launch_status();
   }
@@ -1324,7 +1406,7 @@ int32_t tb_tr_attention_bwd(const float* dout, const float* q, const float* kv, 
     dim3 grid((T + AB_KC - 1) / AB_KC, TR_H, nb);
     k_tr_attn_bwd<<<grid, 256, 0, st>>>(dout + (size_t)b0 * S * TR_D, q + (size_t)b0 * S * TR_D, kv + (size_t)b0 * T * 2 * TR_D,
                                         p + (size_t)b0 * TR_H * S * T, o + (size_t)b0 * S * TR_D, S, T, dq + (size_t)b0 * S * TR_D,
-                                        dkv + (size_t)b0 * T * 2 * TR_D);
+                                        dkv + (size_t)b0 * T * 2 * TR_D, make_drop(drop_seed, drop_site, drop_p), (long)b0 * TR_H * S * T);
     count_launch();
   }
   return launch_status();
@@ -1337,6 +1419,15 @@ int32_t tb_tr_add_mask(const float* a, const uint8_t* keep_a, const float* b, co
   TR_CHECK(a && y, TB_ERR_NULL);
   TR_CHECK(M > 0 && N > 0, TB_ERR_BAD_SHAPE);
   k_tr_add_mask<<<grid_for(M * N), 256, 0, st>>>(a, keep_a, b, keep, M, N, y);
+  count_launch();
+  return launch_status();
+}
+
+// y = x * dropout factor (inter-layer dropout of nn.GRU, agent_temporal.py:116); applied to dy it is its own backward
+int32_t tb_tr_dropout(const float* x, int64_t n, float* y, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TR_CHECK(x && y && drop_seed, TB_ERR_NULL);
+  k_tr_dropout<<<grid_for(n), 256, 0, st>>>(x, n, y, make_drop(drop_seed, drop_site, drop_p));
   count_launch();
   return launch_status();
 }

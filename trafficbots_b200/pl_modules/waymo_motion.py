@@ -185,6 +185,16 @@ class WaymoMotion(_Base):
         if opt.get("_target_", "torch.optim.Adam") != "torch.optim.Adam" or sch.get("_target_", "torch.optim.lr_scheduler.StepLR") != \
                 "torch.optim.lr_scheduler.StepLR":
             raise tb_config.UnsupportedConfig("optimizer / lr_scheduler other than Adam / StepLR")
+        # dropout of the training step: the reference has ONE probability at all its sites (tf_cfg.dropout_p, *.mlp_dropout_p,
+        # mlp_*_cfg.dropout_p, agent_temporal.dropout: 0.1 in traffic_bots.yaml); set `train_dropout_p = 0` for the parity runs
+        mc = dict(model or {})
+        ps = {float((mc.get("tf_cfg") or {}).get("dropout_p", 0.1)), float((mc.get("input_pe_encoder") or {}).get("mlp_dropout_p", 0.1)),
+              float((mc.get("map_encoder") or {}).get("mlp_dropout_p", 0.1)), float((mc.get("agent_temporal") or {}).get("dropout", 0.1)),
+              float(((mc.get("add_latent") or {}).get("mlp_in_cfg") or {}).get("dropout_p", 0.1)),
+              float(((mc.get("add_goal") or {}).get("mlp_in_cfg") or {}).get("dropout_p", 0.1))}
+        if len(ps) != 1:
+            raise tb_config.UnsupportedConfig(f"different dropout probabilities at different sites are not supported: {sorted(ps)}")
+        self.__dict__["train_dropout_p"] = ps.pop()
         self._train_hparams = dict(lr=float(opt.get("lr", 3e-4)), lr_goal=float(lr_goal), max_grad_norm=5.0,
                                    p_training_rollout_prior=float(p_training_rollout_prior), lr_gamma=float(sch.get("gamma", 0.5)),
                                    lr_step_size=int(sch.get("step_size", 7)))
@@ -498,7 +508,7 @@ class WaymoMotion(_Base):
                 raise nt.TbError("trafficbots_b200.WaymoMotion must live on a CUDA device (no CPU implementation of the training path)")
             hp = self._train_hparams
             ts = TrainState(self.state_dict(), device=dev, lr=hp["lr"], lr_goal=hp["lr_goal"], max_grad_norm=hp["max_grad_norm"],
-                            p_rollout_prior=hp["p_training_rollout_prior"])
+                            p_rollout_prior=hp["p_training_rollout_prior"], dropout_p=self.train_dropout_p)
             named = dict(self.named_parameters(remove_duplicate=False))  # shared blocks appear under both of their names
             for k, view in ts.params.t.items():
                 named[k].data = view

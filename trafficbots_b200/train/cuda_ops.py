@@ -52,6 +52,18 @@ class CudaOps:
             t = t.view(U8)
         return self._c(t, U8)
 
+    def _drop(self, drop):
+        """(seed pointer, site id, p) of a dropout call site; (NULL, 0, 0) switches it off."""
+        if drop is None:
+            return None, 0, 0.0
+        seed, site, p = drop
+        return self._c(seed, torch.int32), int(site) & 0xFFFFFFFF, float(p)
+
+    def dropout(self, x, drop):
+        y = torch.empty_like(x)
+        self._run(self.L.tb_tr_dropout(self._c(x), x.numel(), y.data_ptr(), *self._drop(drop), self._st()), "tb_tr_dropout")
+        return y
+
     def _run(self, rc: int, what: str) -> None:
         if rc != nt.TB_OK:
             raise nt.TbError(f"{what} failed: {nt.STATUS.get(rc, rc)}")
@@ -75,17 +87,17 @@ class CudaOps:
         self._run(self.L.tb_tr_scale(self._c(x), x.numel(), float(alpha), self._st()), "tb_tr_scale")
 
     # ---- Linear ----
-    def linear_fwd(self, x, w, b, relu, keep_lin=None, res=None, keep_out=None):
+    def linear_fwd(self, x, w, b, relu, keep_lin=None, res=None, keep_out=None, drop=None):
         M, K = x.shape
         N = w.shape[0]
         pw, ldw = _rows_ld(w)
         y = self.empty((M, N))
         self._run(self.L.tb_tr_linear_fwd(self._c(x), M, K, pw, ldw, N, None if b is None else self._c(b), int(relu),
                                           self._u8(keep_lin), None if res is None else self._c(res), self._u8(keep_out), y.data_ptr(),
-                                          self._st()), "tb_tr_linear_fwd")
+                                          *self._drop(drop), self._st()), "tb_tr_linear_fwd")
         return y
 
-    def linear_bwd(self, dy, x, w, b, y, relu, dw, db, need_dx, keep_lin=None, keep_out=None):
+    def linear_bwd(self, dy, x, w, b, y, relu, dw, db, need_dx, keep_lin=None, keep_out=None, drop=None):
         M, K = x.shape
         N = w.shape[0]
         pw, ldw = _rows_ld(w)
@@ -93,45 +105,45 @@ class CudaOps:
         pdw, lddw = (None, 0) if dw is None else _rows_ld(dw)
         self._run(self.L.tb_tr_linear_bwd(self._c(dy), self._c(x), pw, ldw, self._c(y), int(relu), self._u8(keep_lin), self._u8(keep_out),
                                           M, K, N, None if dx is None else dx.data_ptr(), pdw, lddw, None if db is None else self._c(db),
-                                          self._st()), "tb_tr_linear_bwd")
+                                          *self._drop(drop), self._st()), "tb_tr_linear_bwd")
         return dx
 
     # ---- LayerNorm ----
-    def layernorm_fwd(self, x, w, b, relu):
+    def layernorm_fwd(self, x, w, b, relu, drop=None):
         M, D = x.shape
         y = self.empty((M, D))
         stats = self.empty((M, 2))
         self._run(self.L.tb_tr_layernorm_fwd(self._c(x), self._c(w), self._c(b), int(relu), M, D, y.data_ptr(), stats.data_ptr(),
-                                             self._st()), "tb_tr_layernorm_fwd")
+                                             *self._drop(drop), self._st()), "tb_tr_layernorm_fwd")
         return y, stats
 
-    def layernorm_bwd(self, dy, x, w, b, stats, y, relu, dw, db):
+    def layernorm_bwd(self, dy, x, w, b, stats, y, relu, dw, db, drop=None):
         M, D = x.shape
         dx = self.empty((M, D))
         self._run(self.L.tb_tr_layernorm_bwd(self._c(dy), self._c(x), self._c(w), self._c(stats), self._c(y), int(relu), M, D,
                                              dx.data_ptr(), None if dw is None else self._c(dw), None if db is None else self._c(db),
-                                             self._st()), "tb_tr_layernorm_bwd")
+                                             *self._drop(drop), self._st()), "tb_tr_layernorm_bwd")
         return dx
 
     # ---- attention ----
-    def attention_fwd(self, q, kv, key_valid, eye):
+    def attention_fwd(self, q, kv, key_valid, eye, drop=None):
         B, S, D = q.shape
         T = kv.shape[1]
         o = self.empty((B, S, D))
         p = self.empty((B, 4, S, T))
         dead = self.empty((B, S), dtype=U8)
         self._run(self.L.tb_tr_attention_fwd(self._c(q), self._c(kv), self._u8(key_valid), int(eye), B, S, T, o.data_ptr(),
-                                             p.data_ptr(), dead.data_ptr(), self._st()), "tb_tr_attention_fwd")
+                                             p.data_ptr(), dead.data_ptr(), *self._drop(drop), self._st()), "tb_tr_attention_fwd")
         return o, (p, o), dead
 
-    def attention_bwd(self, do, q, kv, key_valid, eye, p):
+    def attention_bwd(self, do, q, kv, key_valid, eye, p, drop=None):
         p, o = p
         B, S, D = q.shape
         T = kv.shape[1]
         dq = self.zeros((B, S, D))
         dkv = self.empty((B, T, 2 * D))
         self._run(self.L.tb_tr_attention_bwd(self._c(do), self._c(q), self._c(kv), self._c(p), self._c(o), B, S, T, dq.data_ptr(),
-                                             dkv.data_ptr(), self._st()), "tb_tr_attention_bwd")
+                                             dkv.data_ptr(), *self._drop(drop), self._st()), "tb_tr_attention_bwd")
         return dq, dkv
 
     # ---- glue ----

@@ -55,19 +55,31 @@ class Params:
 
 
 class Model:
-    def __init__(self, fn: Fn, params: Params) -> None:
+    def __init__(self, fn: Fn, params: Params, drop_seed: Optional[Tensor] = None, drop_p: float = 0.0) -> None:
+        """drop_seed: device int32 [1] holding this step's dropout seed; drop_p: the reference's single dropout probability
+        (traffic_bots.yaml: tf_cfg.dropout_p = *.mlp_dropout_p = *.dropout_p = agent_temporal.dropout = 0.1).  Every dropout
+        site of the forward gets the next site id; the masks are regenerated from (seed, site, element) in the backward."""
         self.f, self.p = fn, params
+        self.drop_seed, self.drop_p, self.n_site = drop_seed, float(drop_p), 0
+
+    def dp(self):
+        """the next dropout call site, or None when dropout is off."""
+        if self.drop_seed is None or self.drop_p <= 0.0:
+            return None
+        self.n_site += 1
+        return (self.drop_seed, self.n_site, self.drop_p)
 
     # ------------------------------------------------------------------ building blocks
-    def lin(self, x: Var, prefix: str, relu: bool = False) -> Var:
-        return self.f.linear(x, self.p(prefix + ".weight"), self.p(prefix + ".bias"), relu)
+    def lin(self, x: Var, prefix: str, relu: bool = False, drop=None) -> Var:
+        return self.f.linear(x, self.p(prefix + ".weight"), self.p(prefix + ".bias"), relu, drop=drop)
 
-    def ln(self, x: Var, prefix: str, relu: bool = False) -> Var:
-        return self.f.layernorm(x, self.p(prefix + ".weight"), self.p(prefix + ".bias"), relu)
+    def ln(self, x: Var, prefix: str, relu: bool = False, drop=None) -> Var:
+        return self.f.layernorm(x, self.p(prefix + ".weight"), self.p(prefix + ".bias"), relu, drop=drop)
 
     def input_pe_encoder(self, prefix: str, valid: Tensor, attr: Tensor, pe: Tensor) -> Var:
-        """`InputPeEncoder.forward`, pe_mode cat (models/modules/input_pe_encoder.py:52-59)."""
-        x = self.lin(self.lin(Var(attr), prefix + ".mlp.fc_layers.0", relu=True), prefix + ".mlp.fc_layers.3")
+        """`InputPeEncoder.forward`, pe_mode cat (models/modules/input_pe_encoder.py:52-59); MLP = Linear-Dropout-ReLU-Linear
+        (mlp.py:36-64; relu(dropout(x)) == dropout(relu(x)))."""
+        x = self.lin(self.lin(Var(attr), prefix + ".mlp.fc_layers.0", relu=True, drop=self.dp()), prefix + ".mlp.fc_layers.3")
         return self.f.add_mask(self.f.cat2(x, Var(pe)), None, valid.reshape(-1))
 
     def kv_project(self, prefix: str, tgt: Var) -> Var:
@@ -83,14 +95,15 @@ class Model:
         f = self.f
         s2 = self.ln(src, prefix + ".norm1")
         q = f.linear(s2, self.p(prefix + ".attn.in_proj_weight", rows=(0, D)), self.p(prefix + ".attn.in_proj_bias", rows=(0, D)))
-        o, dead = f.attention(q, kv, key_valid, B, S, T, eye)
-        # out-projection, dead rows forced to 0 (attention.py:144-146), residual (transformer.py:203): one fused Linear
+        o, dead = f.attention(q, kv, key_valid, B, S, T, eye, drop=self.dp())  # attention.py:131-132
+        # out-projection, dead rows forced to 0 (attention.py:144-146), dropout1 + residual (transformer.py:202-205): one Linear
         src = f.linear(o, self.p(prefix + ".attn.out_proj_weight"), self.p(prefix + ".attn.out_proj_bias"),
-                       keep_lin=(dead == 0).to(U8), res=src)
+                       keep_lin=(dead == 0).to(U8), res=src, drop=self.dp())
         s2 = self.ln(src, prefix + ".norm2")
-        s2 = self.lin(s2, prefix + ".linear1", relu=True)
-        # second FFN Linear + residual (:220) + zeroing of the invalid source rows (:236-237)
-        return f.linear(s2, self.p(prefix + ".linear2.weight"), self.p(prefix + ".linear2.bias"), res=src, keep_out=src_keep)
+        s2 = self.lin(s2, prefix + ".linear1", relu=True, drop=self.dp())  # linear2(dropout(relu(linear1))) (:214-217)
+        # second FFN Linear + dropout2 + residual (:219-222) + zeroing of the invalid source rows (:236-237)
+        return f.linear(s2, self.p(prefix + ".linear2.weight"), self.p(prefix + ".linear2.bias"), res=src, keep_out=src_keep,
+                        drop=self.dp())
 
     def tf_block(self, prefix: str, n_layer: int, src: Var, src_keep: Tensor, kvs: List[Var], key_valid: Tensor, B: int, S: int,
                  T: int, eye: bool = False) -> Var:
@@ -115,6 +128,8 @@ class Model:
             gh = f.linear(h[layer], self.p(f"{prefix}.rnn.weight_hh_l{layer}"), self.p(f"{prefix}.rnn.bias_hh_l{layer}"))
             inp = f.gru_gates(gi, gh, h[layer])
             hs.append(f.add_mask(inp, None, keep))
+            if layer < 2:
+                inp = f.dropout(inp, self.dp())  # nn.GRU(dropout=...): on the outputs of every layer but the last
         return hs[2], hs
 
     def gru_sequence(self, prefix: str, frames: List[Var], valid_tm: Tensor) -> List[Var]:
@@ -243,13 +258,17 @@ LOSS_CFG = dict(w_vae_kl=0.1, kl_free_nats=0.01, w_diffbar_reward=1.0, w_goal=1.
 
 
 def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tensor, use_prior: bool, n_step: int = 90,
-                     n_hist: int = 11, down: int = 5, loss_cfg: Dict = LOSS_CFG, return_buffers: bool = False) -> Dict[str, Tensor]:
+                     n_hist: int = 11, down: int = 5, loss_cfg: Dict = LOSS_CFG, return_buffers: bool = False,
+                     drop_seed: Optional[Tensor] = None, drop_p: float = 0.0) -> Dict[str, Tensor]:
     """forward of `training_step` + seeding of the loss gradients; call `fn.backward()` afterwards.
 
     batch: the raw episode (`agent/*` [S,91,A,..], `tl_stop/*` [S,91,TL,..], `map/*`, `agent/dest`, ...) on the device of
     the parameters.  eps [S,A,16]: the standard-normal draw of `Normal.rsample` (distributions.py:30); use_prior: the outcome of
-    `torch.rand(1) < p_training_rollout_prior` (:384-387).  Returns the loss terms as device scalars."""
-    m = Model(fn, params)
+    `torch.rand(1) < p_training_rollout_prior` (:384-387).  drop_seed (device int32 [1]) / drop_p: dropout as in the reference's
+    training mode (every nn.Dropout / nn.GRU dropout of the default config has p = 0.1); the masks come from a counter-based hash,
+    so they differ from torch's generator (same distribution, not the same samples).  One simplification: the three aliased
+    `encode_input_features` calls share one encoding, hence one set of dropout masks.  Returns the loss terms as device scalars."""
+    m = Model(fn, params, drop_seed, drop_p)
     f, ops = fn, fn.ops
     dev = batch["agent/valid"].device
     gv = batch["agent/valid"].bool()
@@ -305,14 +324,27 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
 
     # ---- rollout (:390-400 -> reactive_replay :420-476 -> rollout :205-354) ----
     z = f.rsample(prior_mean if use_prior else post_mean, ls_prior if use_prior else ls_post, eps.reshape(M, -1).contiguous())
-    lp = "model.add_latent.mlp_in.fc_layers"
-    z_lat = m.lin(m.lin(z, f"{lp}.0", relu=True), f"{lp}.3", relu=True)  # relu(mlp_in(z)); the mask commutes with ReLU
     bidx = torch.arange(S, device=dev).unsqueeze(1)
     goal_feature = f.gather_rows(map_feature, (bidx * P + goal_gt).reshape(-1))  # goal_manager.py:131-138
-    gp = "model.add_goal.mlp_in.fc_layers"
-    g = m.ln(m.lin(goal_feature, f"{gp}.0"), f"{gp}.1", relu=True)
-    g = m.ln(m.lin(g, f"{gp}.4"), f"{gp}.5", relu=True)
-    z_goal = m.ln(m.lin(g, f"{gp}.8"), f"{gp}.9", relu=True)
+
+    def mlp_in_latent() -> Var:
+        """relu(add_latent.mlp_in(z)) = Linear-Dropout-ReLU-Linear-Dropout, then mask / ReLU in MLP.forward (mlp.py:36-85): the
+        row mask and the dropout factor commute with ReLU."""
+        lp = "model.add_latent.mlp_in.fc_layers"
+        return m.lin(m.lin(z, f"{lp}.0", relu=True, drop=m.dp()), f"{lp}.3", relu=True, drop=m.dp())
+
+    def mlp_in_goal() -> Var:
+        """relu(add_goal.mlp_in(goal_feature)): 3 x [Linear, LayerNorm, Dropout] with ReLU between / after."""
+        gp = "model.add_goal.mlp_in.fc_layers"
+        g = m.ln(m.lin(goal_feature, f"{gp}.0"), f"{gp}.1", relu=True, drop=m.dp())
+        g = m.ln(m.lin(g, f"{gp}.4"), f"{gp}.5", relu=True, drop=m.dp())
+        return m.ln(m.lin(g, f"{gp}.8"), f"{gp}.9", relu=True, drop=m.dp())
+
+    # without dropout both are loop invariants of the rollout and are evaluated once; with dropout the reference draws fresh
+    # masks at every decode step, so they are evaluated per step
+    hoist = m.dp() is None
+    z_lat = mlp_in_latent() if hoist else None
+    z_goal = mlp_in_goal() if hoist else None
 
     tf_mask = teacher_forcing_mask(gv, 10, 10)  # teacher_forcing_training (traffic_bots.yaml:131-137)
     gt_state = torch.cat([batch["agent/pos"], batch["agent/yaw_bbox"], batch["agent/spd"]], -1)  # [S,T,A,4]
@@ -356,10 +388,12 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
         x = m.tf_block("model.transformer_as2tl", 3, x, vflat, kv_t, tlv_tm[tl_t].to(U8).contiguous(), S, A, TL)
         x = m.interaction("model.agent_interaction", x, valid, S, A)
         x, hidden = m.gru_layers("model.agent_temporal", x, hidden, vflat)
-        for name, zr, zv in (("model.add_goal", z_goal, goal_valid.reshape(-1)), ("model.add_latent", z_lat, vflat)):
+        for name, zr, zv in (("model.add_goal", z_goal if hoist else mlp_in_goal(), goal_valid.reshape(-1)),
+                             ("model.add_latent", z_lat if hoist else mlp_in_latent(), vflat)):
             # AddLatentGoal.forward, mode cat, res_add (models/modules/add_latent_goal.py:57-77)
             zz = f.add_mask(zr, None, zv)
-            h = m.lin(m.lin(f.cat2(x, zz), f"{name}.mlp_out.fc_layers.0", relu=True), f"{name}.mlp_out.fc_layers.3", relu=True)
+            h = m.lin(m.lin(f.cat2(x, zz), f"{name}.mlp_out.fc_layers.0", relu=True, drop=m.dp()), f"{name}.mlp_out.fc_layers.3",
+                      relu=True, drop=m.dp())
             x = f.add_mask(h, x, vflat, keep_a=zv)  # (h * z_valid + x) * x_valid
         # ActionHead.forward, branch_type (models/modules/action_head.py:70-87)
         mean = None

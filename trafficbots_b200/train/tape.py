@@ -109,12 +109,12 @@ class Fn:
 
     # ------------------------------------------------------------------ primitives
     def linear(self, x: Var, w: Var, b: Optional[Var], relu: bool = False, keep_lin: Optional[Tensor] = None,
-               res: Optional[Var] = None, keep_out: Optional[Tensor] = None) -> Var:
-        """y = (relu(x W^T + b) * keep_lin[row] + res) * keep_out[row]: a Linear with the residual / row-mask tail of a
-        transformer sub-layer fused into its epilogue (one kernel instead of three)."""
+               res: Optional[Var] = None, keep_out: Optional[Tensor] = None, drop=None) -> Var:
+        """y = (dropout(relu(x W^T + b) * keep_lin[row]) + res) * keep_out[row]: a Linear with the dropout / residual / row-mask
+        tail of a transformer sub-layer fused into its epilogue (one kernel instead of four).  drop = (seed, site, p) or None."""
         assert not (relu and (res is not None or keep_lin is not None or keep_out is not None))
         bd = None if b is None else b.data.view(-1)
-        y = self.ops.linear_fwd(x.data, w.data, bd, relu, keep_lin, None if res is None else res.data, keep_out)
+        y = self.ops.linear_fwd(x.data, w.data, bd, relu, keep_lin, None if res is None else res.data, keep_out, drop)
         self.n_fwd += 1
         req = x.req or w.req or (res is not None and res.req)
         out = Var(y, req)
@@ -122,7 +122,7 @@ class Fn:
             def bw(g: Tensor) -> None:
                 if x.req or w.req:
                     dx = self.ops.linear_bwd(g, x.data, w.data, bd, y, relu, w.grad if w.req else None,
-                                             b.grad.view(-1) if (b is not None and b.req) else None, x.req, keep_lin, keep_out)
+                                             b.grad.view(-1) if (b is not None and b.req) else None, x.req, keep_lin, keep_out, drop)
                     self._acc(x, dx)
                 if res is not None and res.req:
                     d = self.ops.add_mask_bwd(g, keep_out)
@@ -130,31 +130,31 @@ class Fn:
             self._push(out, bw)
         return out
 
-    def layernorm(self, x: Var, w: Var, b: Var, relu: bool = False) -> Var:
+    def layernorm(self, x: Var, w: Var, b: Var, relu: bool = False, drop=None) -> Var:
         wd, bd = w.data.view(-1), b.data.view(-1)
-        y, stats = self.ops.layernorm_fwd(x.data, wd, bd, relu)
+        y, stats = self.ops.layernorm_fwd(x.data, wd, bd, relu, drop)
         self.n_fwd += 1
         req = x.req or w.req
         out = Var(y, req)
         if req:
             def bw(g: Tensor) -> None:
                 dx = self.ops.layernorm_bwd(g, x.data, wd, bd, stats, y, relu, w.grad.view(-1) if w.req else None,
-                                            b.grad.view(-1) if b.req else None)
+                                            b.grad.view(-1) if b.req else None, drop)
                 self._acc(x, dx)
             self._push(out, bw)
         return out
 
-    def attention(self, q: Var, kv: Var, key_valid: Tensor, n_batch: int, n_src: int, n_tgt: int, eye: bool):
-        """q [B*S, D], kv [B*T, 2D] -> (o [B*S, D], dead [B*S] u8)."""
+    def attention(self, q: Var, kv: Var, key_valid: Tensor, n_batch: int, n_src: int, n_tgt: int, eye: bool, drop=None):
+        """q [B*S, D], kv [B*T, 2D] -> (o [B*S, D], dead [B*S] u8); drop: dropout on the attention probabilities."""
         D = q.cols
-        o, p, dead = self.ops.attention_fwd(q.data.view(n_batch, n_src, D), kv.data.view(n_batch, n_tgt, 2 * D), key_valid, eye)
+        o, p, dead = self.ops.attention_fwd(q.data.view(n_batch, n_src, D), kv.data.view(n_batch, n_tgt, 2 * D), key_valid, eye, drop)
         self.n_fwd += 1
         req = q.req or kv.req
         out = Var(o.view(n_batch * n_src, D), req)
         if req:
             def bw(g: Tensor) -> None:
                 dq, dkv = self.ops.attention_bwd(g.view(n_batch, n_src, D), q.data.view(n_batch, n_src, D),
-                                                 kv.data.view(n_batch, n_tgt, 2 * D), key_valid, eye, p)
+                                                 kv.data.view(n_batch, n_tgt, 2 * D), key_valid, eye, p, drop)
                 self._acc(q, dq.view(n_batch * n_src, D))
                 self._acc(kv, dkv.view(n_batch * n_tgt, 2 * D))
             self._push(out, bw)
@@ -176,6 +176,19 @@ class Fn:
                         self._acc(a, d, owned=not (d is g or (b is not None and b.req)))
                     else:
                         self._acc(a, self.ops.add_mask_bwd(g, keep, keep_a))
+            self._push(out, bw)
+        return out
+
+    def dropout(self, x: Var, drop) -> Var:
+        """elementwise dropout (nn.GRU's inter-layer dropout); drop None = identity."""
+        if drop is None:
+            return x
+        y = self.ops.dropout(x.data, drop)
+        self.n_fwd += 1
+        out = Var(y, x.req)
+        if x.req:
+            def bw(g: Tensor) -> None:
+                self._acc(x, self.ops.dropout(g, drop))
             self._push(out, bw)
         return out
 

@@ -52,7 +52,8 @@ def build_params(state_dict: Mapping[str, Tensor], device) -> Tuple[graph.Params
 
 class TrainState:
     def __init__(self, state_dict: Mapping[str, Tensor], device="cuda", ops=None, lr: float = 3e-4, lr_goal: Optional[float] = None,
-                 betas=(0.9, 0.999), eps: float = 1e-8, max_grad_norm: float = 5.0, p_rollout_prior: float = 0.1) -> None:
+                 betas=(0.9, 0.999), eps: float = 1e-8, max_grad_norm: float = 5.0, p_rollout_prior: float = 0.1,
+                 dropout_p: float = 0.0) -> None:
         if ops is None:
             from .cuda_ops import CudaOps  # raises without the CUDA library / a CUDA device: there is no CPU training path
             ops = CudaOps(device)
@@ -65,6 +66,9 @@ class TrainState:
         self.lr = torch.tensor([lr, lr if lr_goal is None else lr_goal], dtype=torch.float32, device=self.device)
         self.betas, self.eps, self.max_grad_norm = betas, eps, max_grad_norm
         self.p_rollout_prior = p_rollout_prior
+        # dropout of the reference's training mode (one probability for every site, traffic_bots.yaml); 0 = the parity configuration
+        self.dropout_p = float(dropout_p)
+        self.drop_seed = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.n_step = 0
         self.last_ops = 0
         self._graphs, self._pool, self._static_batch, self._static_eps = {}, None, None, None
@@ -83,15 +87,24 @@ class TrainState:
         eps = torch.empty(n_scene, n_agent, latent_dim).normal_()
         return use_prior, eps
 
+    def new_dropout_seed(self, seed: Optional[int] = None) -> None:
+        """a fresh seed for this step's dropout masks (host draw from the global torch generator unless given); the kernels
+        read it from device memory, so a captured CUDA graph sees the new value."""
+        if self.dropout_p > 0.0:
+            self.drop_seed.fill_(int(torch.randint(0, 2 ** 31 - 1, (1,))) if seed is None else int(seed))
+
     def forward_backward(self, batch: Mapping[str, Tensor], eps: Optional[Tensor] = None, use_prior: Optional[bool] = None,
-                         return_buffers: bool = False) -> Dict[str, Tensor]:
+                         return_buffers: bool = False, new_seed: bool = True) -> Dict[str, Tensor]:
         """loss terms of `training_step` (device scalars) with the gradients of all parameters left in `self.flat_g`."""
         S, _, A = batch["agent/valid"].shape
         if eps is None or use_prior is None:
             use_prior, eps = self.draw_noise(S, A)
+        if new_seed and not (self.device.type == "cuda" and torch.cuda.is_current_stream_capturing()):
+            self.new_dropout_seed()
         self.flat_g.zero_()
         fn = Fn(self.ops)
-        out = graph.training_forward(fn, self.params, batch, eps.to(self.device), use_prior, return_buffers=return_buffers)
+        out = graph.training_forward(fn, self.params, batch, eps.to(self.device), use_prior, return_buffers=return_buffers,
+                                     drop_seed=self.drop_seed if self.dropout_p > 0.0 else None, drop_p=self.dropout_p)
         self.last_ops = fn.n_fwd
         fn.backward()
         return out
@@ -135,6 +148,7 @@ class TrainState:
         for k, dst in self._static_batch.items():
             dst.copy_(batch[k], non_blocking=True)
         self._static_eps.copy_(eps, non_blocking=True)
+        self.new_dropout_seed()
         g.replay()
         self.replayed_kernels += n_kernel
         return out
