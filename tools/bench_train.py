@@ -84,7 +84,30 @@ def graph_mode():
               f"scenes/s, loss {float(out['loss']):.4f}", flush=True)
 
 
+def curve_mode(n_iter):
+    """n_iter optimizer steps (graph replay, dropout 0.1, lr 3e-4, clip 5) on two alternating synthetic batches: the loss terms."""
+    S, A, P = 16, 64, 1024
+    dev = "cuda:0"
+    ts = trainer.TrainState(weights.init_state_dict(2023), device=dev, dropout_p=0.1)
+    ts.ops.check = False
+    batches = [{k: v.to(dev) for k, v in synthetic.make_batch(S, n_agent=A, n_pl=P, seed=7 + i).items()} for i in range(2)]
+    torch.manual_seed(0)
+    ts.capture(batches[0])
+    hist = []
+    for i in range(n_iter):
+        out = ts.training_step(batches[i % 2], graph=True)
+        hist.append([float(out[k]) for k in ("loss", "vae_kl", "diffbar_reward", "goal_loss")] + [float(out["grad_sq_norm"]) ** 0.5])
+    for i, h in enumerate(hist):
+        if i < 3 or i % 10 == 9:
+            print(f"step {i + 1:3d}: loss {h[0]:.4f} = kl {h[1]:.4f} + reward {h[2]:.4f} + goal {h[3]:.4f}; |grad| {h[4]:.2f}", flush=True)
+    first, last = sum(h[0] for h in hist[:10]) / 10, sum(h[0] for h in hist[-10:]) / 10
+    print(f"mean loss of the first 10 steps {first:.4f}, of the last 10 steps {last:.4f}")
+
+
 if __name__ == "__main__":
+    if os.environ.get("TB_TRAIN_CURVE"):
+        curve_mode(int(os.environ["TB_TRAIN_CURVE"]))
+        sys.exit(0)
     if os.environ.get("TB_TRAIN_GRAPH"):
         graph_mode()
         sys.exit(0)
