@@ -586,6 +586,10 @@ def reference_training_rate(cfg, n_scene, seed=1234):
     model = ref_loader.build_reference(n_agent=cfg["n_agent"], n_pl=cfg["n_pl"], n_joint_future=1)
     model.load_state_dict(weights.init_state_dict(2023), strict=True)
     batch = synthetic.make_batch(n_scene, n_agent=cfg["n_agent"], n_pl=cfg["n_pl"], seed=seed)
+    if not getattr(reference_training_rate, "warm", False):  # thread pools / allocator: one small untimed pass per process
+        ref_train.run_reference_training(model, synthetic.make_batch(1, n_agent=cfg["n_agent"], n_pl=cfg["n_pl"], seed=seed + 1), seed=0,
+                                         dropout=True)
+        reference_training_rate.warm = True
     t0 = time.perf_counter()
     ref_train.run_reference_training(model, batch, seed=0, dropout=True)
     dt = time.perf_counter() - t0
