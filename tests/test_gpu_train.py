@@ -297,6 +297,21 @@ def test_training_step_matches_reference(case):
     print(f"{case}: loss {float(out['loss']):.6f} (reference {c['terms']['loss']:.6f}), worst gradient deviation {worst:.2e}")
 
 
+@pytest.mark.parametrize("case", TRAIN_CASES)
+def test_training_step_in_concurrent_sub_batches_matches_reference(case):
+    """n_split = 2: the scenes of a step run as two concurrent chains on side streams (1 + 1 and 1 + 2 scenes here); the loss
+    normalisers stay batch-wide, parameter gradients of both chains accumulate atomically: same loss / gradients."""
+    from trafficbots_b200.train import trainer
+    c = load_train_case(case)
+    ts = trainer.TrainState(c["sd"], device=DEV, n_split=2)
+    batch = {k: v.to(DEV) for k, v in c["batch"].items()}
+    out = ts.forward_backward(batch, c["eps"], c["use_prior"])
+    torch.cuda.synchronize()
+    for k, ref in c["terms"].items():
+        assert abs(float(out[k]) - ref) <= 1e-4 * max(1.0, abs(ref)), (k, float(out[k]), ref)
+    compare_grads({k: v.cpu() for k, v in ts.grads().items()}, c["grads"], rel=2e-3)
+
+
 def test_optimizer_steps_match_cpu_restatement():
     from trafficbots_b200.train import trainer
     c = load_train_case(TRAIN_CASES[0])

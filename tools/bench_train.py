@@ -58,7 +58,8 @@ def graph_mode():
     P = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
     rep = int(sys.argv[4]) if len(sys.argv) > 4 else 3
     dev = "cuda:0"
-    ts = trainer.TrainState(weights.init_state_dict(2023), device=dev, dropout_p=float(os.environ.get("TB_TRAIN_DROPOUT", "0")))
+    ts = trainer.TrainState(weights.init_state_dict(2023), device=dev, dropout_p=float(os.environ.get("TB_TRAIN_DROPOUT", "0")),
+                            n_split=int(os.environ.get("TB_TRAIN_SPLIT", "1")))
     ts.ops.check = False
     batch = {k: v.to(dev) for k, v in synthetic.make_batch(S, n_agent=A, n_pl=P, seed=7).items()}
     torch.manual_seed(0)
@@ -68,7 +69,7 @@ def graph_mode():
     g_eager = ts.flat_g.clone()
     out = ts.replay(batch, torch.zeros(S, A, 16), False)
     torch.cuda.synchronize()
-    print(f"capture (posterior graph): {time.perf_counter() - t0:.1f} s; graph == eager: loss {float(out['loss']):.6f} vs "
+    print(f"n_split {ts.n_split}, dropout {ts.dropout_p}: capture (posterior graph): {time.perf_counter() - t0:.1f} s; graph == eager: loss {float(out['loss']):.6f} vs "
           f"{float(eager['loss']):.6f}, max grad diff {float((ts.flat_g - g_eager).abs().max()):.2e} "
           f"(scale {float(g_eager.abs().max()):.2e}); memory reserved {torch.cuda.memory_reserved() / 2 ** 30:.1f} GiB", flush=True)
     for i in range(rep):

@@ -1027,7 +1027,7 @@ __global__ void k_tr_rsample_bwd(const float* __restrict__ dz, const float* __re
   const float sd = expf(log_std[e]);
   float acc = 0.f;
   for (long m = 0; m < M; ++m) acc += dz[m * E + e] * eps[m * E + e] * sd;
-  dlog_std[e] += acc;
+  atomicAdd(&dlog_std[e], acc);  // several sub-batches of a step may run concurrently
 }
 
 // KL(N(mq, e^lq) || N(mp, e^lp)) per row = sum_e [lp - lq + (e^2lq + (mq - mp)^2) / (2 e^2lp) - 1/2], clamped at free_nats

@@ -259,7 +259,8 @@ LOSS_CFG = dict(w_vae_kl=0.1, kl_free_nats=0.01, w_diffbar_reward=1.0, w_goal=1.
 
 def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tensor, use_prior: bool, n_step: int = 90,
                      n_hist: int = 11, down: int = 5, loss_cfg: Dict = LOSS_CFG, return_buffers: bool = False,
-                     drop_seed: Optional[Tensor] = None, drop_p: float = 0.0) -> Dict[str, Tensor]:
+                     drop_seed: Optional[Tensor] = None, drop_p: float = 0.0, defer_loss: bool = False,
+                     first_drop_site: int = 0) -> Dict[str, Tensor]:
     """forward of `training_step` + seeding of the loss gradients; call `fn.backward()` afterwards.
 
     batch: the raw episode (`agent/*` [S,91,A,..], `tl_stop/*` [S,91,TL,..], `map/*`, `agent/dest`, ...) on the device of
@@ -269,6 +270,7 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
     so they differ from torch's generator (same distribution, not the same samples).  One simplification: the three aliased
     `encode_input_features` calls share one encoding, hence one set of dropout masks.  Returns the loss terms as device scalars."""
     m = Model(fn, params, drop_seed, drop_p)
+    m.n_site = first_drop_site  # sub-batches of one step use disjoint site ranges: independent masks
     f, ops = fn, fn.ops
     dev = batch["agent/valid"].device
     gv = batch["agent/valid"].bool()
@@ -436,33 +438,42 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
     pv[:, :t0] = False
     rvs = torch.stack(rv_l, 1).bool() & pv
     any_pv = pv.any(-1)
-    one = torch.ones(1, device=dev)
-    s_r = loss_cfg["w_diffbar_reward"] / rvs.sum().to(torch.float32) * one  # device scalars; no host synchronisation
-    r_all = torch.cat([r.data for r in rewards], 1)  # [M, n_step]
-    rvs_u8 = rvs.to(U8).contiguous()
-    loss_r = -s_r * ops.masked_sum(r_all, rvs_u8)  # w * (-sum r) / count
-    for i, r in enumerate(rewards):
-        if r.req:
-            r.grad = ops.mask_scale(rvs_u8[:, i].contiguous(), -s_r)  # d loss / d r on the counted entries
     kl_valid = (post_valid.bool() & any_pv)
-    s_kl = loss_cfg["w_vae_kl"] / kl_valid.sum().to(torch.float32) * one
-    kl_sum, dmq, dmp = ops.kl_fwd_bwd(post_mean.data, ls_post.data.view(-1), prior_mean.data, ls_prior.data.view(-1),
-                                      kl_valid.to(U8).contiguous(), loss_cfg["kl_free_nats"], s_kl, ls_post.grad.view(-1),
-                                      ls_prior.grad.view(-1))
-    loss_kl = s_kl * kl_sum
-    f._acc(post_mean, dmq)
-    f._acc(prior_mean, dmp)
     goal_rows = (goal_valid0.reshape(-1) & any_pv)
-    s_g = loss_cfg["w_goal"] / goal_rows.sum().to(torch.float32) * one
-    nll_sum, dlogits = ops.dest_nll(logits.data.view(S, A, P), dest_masks(batch, pl_valid), goal_valid0.to(U8).contiguous(),
-                                    goal_gt, goal_rows.view(S, A).to(U8).contiguous(), s_g)
-    loss_g = s_g * nll_sum
-    f._acc(logits, dlogits.reshape(-1, 1))
-    out = {"loss": loss_kl + loss_r + loss_g, "vae_kl": loss_kl, "diffbar_reward": loss_r, "goal_loss": loss_g}
-    if return_buffers:
-        out["preds"] = torch.stack(preds_l, 1).view(S, A, n_step, 4)
-        out["pred_valid"] = torch.stack(pred_valid_l, 1).view(S, A, n_step)
-        out["post_mean"] = post_mean.data.view(S, A, -1)
-        out["prior_mean"] = prior_mean.data.view(S, A, -1)
-        out["map_feature"] = map_feature.data.view(S, P, D)
-    return out
+    rvs_u8 = rvs.to(U8).contiguous()
+    # the three normalisers of TrainingMetrics.compute (:150-157): counts over the WHOLE batch
+    counts = torch.stack([rvs.sum(), kl_valid.sum(), goal_rows.sum()]).to(torch.float32)
+
+    def finish(counts_total: Tensor) -> Dict[str, Tensor]:
+        """seeds the loss gradients with the given batch-wide counts [reward, kl, goal] (device tensor; no host synchronisation)
+        and returns this (sub-)batch's share of the loss terms; `fn.backward()` follows."""
+        s_r = (loss_cfg["w_diffbar_reward"] / counts_total[0]).reshape(1)
+        r_all = torch.cat([r.data for r in rewards], 1)  # [M, n_step]
+        loss_r = -s_r * ops.masked_sum(r_all, rvs_u8)  # w * (-sum r) / count
+        for i, r in enumerate(rewards):
+            if r.req:
+                r.grad = ops.mask_scale(rvs_u8[:, i].contiguous(), -s_r)  # d loss / d r on the counted entries
+        s_kl = (loss_cfg["w_vae_kl"] / counts_total[1]).reshape(1)
+        kl_sum, dmq, dmp = ops.kl_fwd_bwd(post_mean.data, ls_post.data.view(-1), prior_mean.data, ls_prior.data.view(-1),
+                                          kl_valid.to(U8).contiguous(), loss_cfg["kl_free_nats"], s_kl, ls_post.grad.view(-1),
+                                          ls_prior.grad.view(-1))
+        loss_kl = s_kl * kl_sum
+        f._acc(post_mean, dmq)
+        f._acc(prior_mean, dmp)
+        s_g = (loss_cfg["w_goal"] / counts_total[2]).reshape(1)
+        nll_sum, dlogits = ops.dest_nll(logits.data.view(S, A, P), dest_masks(batch, pl_valid), goal_valid0.to(U8).contiguous(),
+                                        goal_gt, goal_rows.view(S, A).to(U8).contiguous(), s_g)
+        loss_g = s_g * nll_sum
+        f._acc(logits, dlogits.reshape(-1, 1))
+        out = {"loss": loss_kl + loss_r + loss_g, "vae_kl": loss_kl, "diffbar_reward": loss_r, "goal_loss": loss_g}
+        if return_buffers:
+            out["preds"] = torch.stack(preds_l, 1).view(S, A, n_step, 4)
+            out["pred_valid"] = torch.stack(pred_valid_l, 1).view(S, A, n_step)
+            out["post_mean"] = post_mean.data.view(S, A, -1)
+            out["prior_mean"] = prior_mean.data.view(S, A, -1)
+            out["map_feature"] = map_feature.data.view(S, P, D)
+        return out
+
+    if defer_loss:  # the caller sums `counts` over its sub-batches first (TrainState.forward_backward with n_split > 1)
+        return {"counts": counts, "finish": finish}
+    return finish(counts)

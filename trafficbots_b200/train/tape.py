@@ -89,7 +89,7 @@ class Fn:
             v.grad = self.ops.zeros(tuple(v.data.shape), v.data)
             v.grad_shared = False
         elif v.grad_shared:
-            v.grad = self.ops.add_mask_fwd(v.grad, None, None).clone()
+            v.grad = v.grad.clone()  # memory copy: the slices below are accumulated into in place
             v.grad_shared = False
         out = Var(v.data[lo:hi], True, v.grad[lo:hi])
         return out

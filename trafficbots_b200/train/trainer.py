@@ -53,7 +53,7 @@ def build_params(state_dict: Mapping[str, Tensor], device) -> Tuple[graph.Params
 class TrainState:
     def __init__(self, state_dict: Mapping[str, Tensor], device="cuda", ops=None, lr: float = 3e-4, lr_goal: Optional[float] = None,
                  betas=(0.9, 0.999), eps: float = 1e-8, max_grad_norm: float = 5.0, p_rollout_prior: float = 0.1,
-                 dropout_p: float = 0.0) -> None:
+                 dropout_p: float = 0.0, n_split: int = 1) -> None:
         if ops is None:
             from .cuda_ops import CudaOps  # raises without the CUDA library / a CUDA device: there is no CPU training path
             ops = CudaOps(device)
@@ -69,6 +69,8 @@ class TrainState:
         # dropout of the reference's training mode (one probability for every site, traffic_bots.yaml); 0 = the parity configuration
         self.dropout_p = float(dropout_p)
         self.drop_seed = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.n_split = int(n_split)  # concurrent sub-batch chains per step (see forward_backward)
+        self._streams, self._keep = None, None
         self.n_step = 0
         self.last_ops = 0
         self._graphs, self._pool, self._static_batch, self._static_eps = {}, None, None, None
@@ -102,12 +104,51 @@ class TrainState:
         if new_seed and not (self.device.type == "cuda" and torch.cuda.is_current_stream_capturing()):
             self.new_dropout_seed()
         self.flat_g.zero_()
-        fn = Fn(self.ops)
-        out = graph.training_forward(fn, self.params, batch, eps.to(self.device), use_prior, return_buffers=return_buffers,
-                                     drop_seed=self.drop_seed if self.dropout_p > 0.0 else None, drop_p=self.dropout_p)
-        self.last_ops = fn.n_fwd
-        fn.backward()
-        return out
+        kw = dict(return_buffers=return_buffers, drop_seed=self.drop_seed if self.dropout_p > 0.0 else None, drop_p=self.dropout_p)
+        n_split = min(self.n_split, S) if self.device.type == "cuda" and not return_buffers else 1
+        if n_split <= 1:
+            fn = Fn(self.ops)
+            out = graph.training_forward(fn, self.params, batch, eps.to(self.device), use_prior, **kw)
+            self.last_ops = fn.n_fwd
+            fn.backward()
+            return out
+        # ---- scenes are independent: n_split sub-batches run as concurrent chains on side streams (inside a graph capture they
+        # become parallel branches).  At 16 scenes a launch has 1024 rows and is bound by latency, not by work: two chains of 512
+        # rows overlap almost perfectly.  The loss normalisers are batch-wide counts, so the chains meet once between forward
+        # and backward; parameter gradients of all chains accumulate atomically in the flat buffer.
+        cur = torch.cuda.current_stream(self.device)
+        if self._streams is None or len(self._streams) < n_split:
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in range(n_split)]
+        eps = eps.to(self.device)
+        bounds = [(i * S) // n_split for i in range(n_split + 1)]
+        fns, parts = [], []
+        for i in range(n_split):
+            st = self._streams[i]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                lo, hi = bounds[i], bounds[i + 1]
+                sub = {k: v[lo:hi] for k, v in batch.items()}
+                fn = Fn(self.ops)
+                parts.append(graph.training_forward(fn, self.params, sub, eps[lo:hi], use_prior, defer_loss=True,
+                                                    first_drop_site=i * 1000000, **kw))
+                fns.append(fn)
+        for st in self._streams[:n_split]:
+            cur.wait_stream(st)
+        counts = parts[0]["counts"]
+        for p_ in parts[1:]:
+            counts = counts + p_["counts"]
+        outs = []
+        for i in range(n_split):
+            st = self._streams[i]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                outs.append(parts[i]["finish"](counts))
+                fns[i].backward()
+        for st in self._streams[:n_split]:
+            cur.wait_stream(st)
+        self.last_ops = sum(fn.n_fwd for fn in fns)
+        self._keep = (outs, counts)  # tensors that crossed streams stay referenced until the next step
+        return {k: sum(o[k] for o in outs) for k in outs[0]}
 
     # ---- whole-step CUDA graph -------------------------------------------------------------------------------------
     def capture(self, batch: Mapping[str, Tensor]) -> None:
