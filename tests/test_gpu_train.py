@@ -472,3 +472,53 @@ def test_training_step_with_dropout_matches_cpu_restatement():
     # a second step draws new masks
     out2 = ts.forward_backward(batch, c["eps"], c["use_prior"])
     assert abs(float(out2["loss"]) - float(out["loss"])) > 1e-6
+
+
+@pytest.mark.reference
+def test_full_size_step_vs_reference_on_the_gpu():
+    """BASELINE.json configs[3] scene shape (64 agents, 1024 polylines, 90 steps; 2 scenes): the UNMODIFIED reference's
+    `training_step` + backward executed on the same GPU (fp32, TF32 off, dropout 0) against the CUDA step: loss terms and the
+    gradients of all 382 parameters.  Needs the reference sources on the box (tools/install_reference.sh -> baseline/_ref)."""
+    import torch._dynamo  # noqa: F401  (before ref_loader's module stubs)
+    import ref_loader
+    import ref_train
+    from trafficbots_b200 import synthetic, weights
+    from trafficbots_b200.train import trainer
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    S, A, P = 2, 64, 1024
+    sd = weights.init_state_dict(2023)
+    batch = synthetic.make_batch(S, n_agent=A, n_pl=P, seed=4321)
+    model = ref_loader.build_reference(n_agent=A, n_pl=P, n_joint_future=1)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV)
+    # the reference draws its latent noise on the device: replay the host-side protocol with a generator-independent patch
+    use_prior, eps = ref_train.draw_training_noise(11, S, A)
+    import models.modules.distributions as dist_mod
+    orig = dist_mod.MyDist.sample
+
+    def sample(self, deterministic):
+        if deterministic is False:
+            return self.distribution.mean + eps.to(DEV) * self.distribution.stddev
+        return orig(self, deterministic)
+    dist_mod.MyDist.sample = sample
+    try:
+        terms, grads, _ = ref_train.run_reference_training(model, {k: v.to(DEV) for k, v in batch.items()}, seed=11,
+                                                           p_prior=1.0 if use_prior else 0.0)
+    finally:
+        dist_mod.MyDist.sample = orig
+    ts = trainer.TrainState(sd, device=DEV)
+    out = ts.forward_backward({k: v.to(DEV) for k, v in batch.items()}, eps, use_prior)
+    for k in ("loss", "vae_kl", "diffbar_reward", "goal_loss"):
+        assert abs(float(out[k]) - float(terms[k])) <= 2e-4 * max(1.0, abs(float(terms[k]))), (k, float(out[k]), float(terms[k]))
+    total = sum(float((g_.double() ** 2).sum()) for g_ in grads.values() if g_ is not None) ** 0.5
+    worst = 0.0
+    for k, g_ in ts.grads().items():
+        if grads[k] is None:
+            assert float(g_.abs().max()) == 0.0, k
+            continue
+        err = float((g_ - grads[k]).abs().max())
+        scale = float(grads[k].norm()) / g_.numel() ** 0.5 * 8.0 + 1e-6 * total
+        worst = max(worst, err / scale)
+    print(f"full-size step vs reference on the GPU: loss {float(out['loss']):.6f} vs {float(terms['loss']):.6f}, worst gradient deviation {worst:.2e}")
+    assert worst <= 5e-3, worst
