@@ -451,19 +451,20 @@ int32_t tb_tc_selftest(const float* a, int32_t block, const float* packed, float
  *   sq_norm, adam_step : torch.nn.utils.clip_grad_norm_ + torch.optim.Adam on the flat parameter buffer
  * ------------------------------------------------------------------------------------------------------------------ */
 /* y = (dropout(relu(x W^T + bias) * keep_lin[row]) + res) * keep_out[row]; bias / keep_lin / res / keep_out / drop_seed may be NULL */
-int32_t tb_tr_linear_fwd(const float* x, int64_t M, int32_t K, const float* w, int64_t ldw, int32_t N, const float* bias, int32_t relu, const uint8_t* keep_lin, const float* res, const uint8_t* keep_out, float* y, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, void* stream);
+int32_t tb_tr_linear_fwd(const float* x, int64_t M, int32_t K, const float* w, int64_t ldw, int32_t N, const float* bias, int32_t relu, const uint8_t* keep_lin, const float* res, const uint8_t* keep_out, float* y, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, int64_t drop_offset, void* stream);
 /* dx = dY' W; dw += dY'^T x; db += colsum(dY') with dY' = dy * relu'(y) * dropout mask * rm1[row] * rm2[row] (row masks may be */
 /* NULL: the keep_lin / keep_out of the forward; drop_* as in the forward).  dx / dw / db may be NULL (skipped); db needs dw. */
-int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_t ldw, const float* y, int32_t relu, const uint8_t* rm1, const uint8_t* rm2, int64_t M, int32_t K, int32_t N, float* dx, float* dw, int64_t lddw, float* db, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, void* stream);
-int32_t tb_tr_layernorm_fwd(const float* x, const float* w, const float* b, int32_t relu, int64_t M, int32_t D, float* y, float* stats, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, void* stream);
-int32_t tb_tr_layernorm_bwd(const float* dy, const float* x, const float* w, const float* stats, const float* y, int32_t relu, int64_t M, int32_t D, float* dx, float* dw, float* db, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, void* stream);
-int32_t tb_tr_attention_fwd(const float* q, const float* kv, const uint8_t* key_valid, int32_t eye, int32_t B, int32_t S, int32_t T, float* o, float* p, uint8_t* dead, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, void* stream);
-/* dq must be zero-initialised by the caller (partials are added atomically); dkv is overwritten */
-int32_t tb_tr_attention_bwd(const float* dout, const float* q, const float* kv, const float* p, const float* o, int32_t B, int32_t S, int32_t T, float* dq, float* dkv, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, void* stream);
+int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_t ldw, const float* y, int32_t relu, const uint8_t* rm1, const uint8_t* rm2, int64_t M, int32_t K, int32_t N, float* dx, float* dw, int64_t lddw, float* db, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, int64_t drop_offset, void* stream);
+int32_t tb_tr_layernorm_fwd(const float* x, const float* w, const float* b, int32_t relu, int64_t M, int32_t D, float* y, float* stats, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, int64_t drop_offset, void* stream);
+int32_t tb_tr_layernorm_bwd(const float* dy, const float* x, const float* w, const float* stats, const float* y, int32_t relu, int64_t M, int32_t D, float* dx, float* dw, float* db, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, int64_t drop_offset, void* stream);
+int32_t tb_tr_attention_fwd(const float* q, const float* kv, const uint8_t* key_valid, int32_t eye, int32_t B, int32_t S, int32_t T, float* o, float* p, uint8_t* dead, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, int64_t drop_offset, void* stream);
+/* dq must be zero-initialised by the caller (partials are added atomically); dkv is overwritten -- or, with kv_batch > 0 (K|V of */
+/* batch element b = those of b % kv_batch; kv / dkv hold kv_batch elements), accumulated atomically into a zero-initialised buffer */
+int32_t tb_tr_attention_bwd(const float* dout, const float* q, const float* kv, const float* p, const float* o, int32_t B, int32_t S, int32_t T, int32_t kv_batch, float* dq, float* dkv, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, int64_t drop_offset, void* stream);
 /* y = (a * keep_a[row] + b) * keep[row]; keep_a / b / keep may be NULL */
 int32_t tb_tr_add_mask(const float* a, const uint8_t* keep_a, const float* b, const uint8_t* keep, int64_t M, int32_t N, float* y, void* stream);
 /* y = x * dropout factor (inter-layer dropout of nn.GRU, agent_temporal.py:116); applied to dy it is its own backward */
-int32_t tb_tr_dropout(const float* x, int64_t n, float* y, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, void* stream);
+int32_t tb_tr_dropout(const float* x, int64_t n, float* y, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, int64_t drop_offset, void* stream);
 int32_t tb_tr_axpy(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t M, int32_t N, void* stream);
 int32_t tb_tr_select_rows(const uint8_t* mask, const float* a, const float* b, int64_t M, int32_t N, float* y, void* stream);
 int32_t tb_tr_select_rows_bwd(const uint8_t* mask, const float* dy, int64_t M, int32_t N, float* da, float* db, void* stream);

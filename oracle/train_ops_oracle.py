@@ -46,12 +46,13 @@ def drop_factor(drop, shape, device) -> Tensor:
     """dropout factor tensor of a call site: drop = (seed tensor [1] int32/int64, site id, p); element index = flat index."""
     if drop is None:
         return None
-    seed, site, p = drop
+    seed, site, p = drop[:3]
+    offset = int(drop[3]) if len(drop) > 3 else 0
     n = 1
     for d in shape:
         n *= d
     key = _mix32(torch.tensor([(site * 0x9E3779B9) & 0xFFFFFFFF], dtype=torch.int64, device=device) ^ (seed.to(torch.int64).to(device) & 0xFFFFFFFF))
-    h = _mix32((torch.arange(n, dtype=torch.int64, device=device) & 0xFFFFFFFF) ^ key)
+    h = _mix32(((torch.arange(n, dtype=torch.int64, device=device) + offset) & 0xFFFFFFFF) ^ key)
     thresh = int(float(torch.tensor(p, dtype=torch.float32)) * 4294967296.0)  # p as the fp32 value the kernel receives
     scale = torch.tensor(1.0, dtype=torch.float32) / (torch.tensor(1.0, dtype=torch.float32) - torch.tensor(p, dtype=torch.float32))
     return ((h >= thresh).to(torch.float32) * scale.to(device)).view(*shape)
@@ -143,14 +144,21 @@ class OracleOps:
         o = torch.matmul(pd, vh).transpose(1, 2).flatten(2, 3)
         return o, p, dead.to(torch.uint8)
 
-    def attention_bwd(self, do, q, kv, key_valid, eye, p, drop=None):
+    def attention_bwd(self, do, q, kv, key_valid, eye, p, drop=None, kv_shared: bool = False):
         q_, kv_ = _req(q, kv)
-        gq, gkv = _grads(self.attention_fwd(q_, kv_, key_valid, eye, drop)[0], [q_, kv_], do)
+        if kv_shared:  # batch element b of q uses the keys of b % kv.shape[0]
+            rep = q.shape[0] // kv.shape[0]
+            o = self.attention_fwd(q_, kv_.repeat(rep, 1, 1), key_valid.repeat(rep, 1), eye, drop)[0]
+        else:
+            o = self.attention_fwd(q_, kv_, key_valid, eye, drop)[0]
+        gq, gkv = _grads(o, [q_, kv_], do)
         return gq, gkv
 
     def dropout(self, x, drop):
         """x * dropout factor (nn.GRU inter-layer dropout); applied to dy it is its own backward."""
         return x * drop_factor(drop, x.shape, x.device)
+
+    dropout_bwd = dropout
 
     # ---- elementwise glue ----
     def add_mask_fwd(self, a, b, keep, keep_a=None):

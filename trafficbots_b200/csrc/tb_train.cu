@@ -36,6 +36,8 @@ struct Drop {
   uint32_t site;
   uint32_t thresh;  // element kept iff hash >= thresh (= p * 2^32)
   float scale;      // 1 / (1 - p)
+  long offset;      // added to the element index: a launch that covers rows [t M, (t + 1) M) of a step-stacked buffer passes t M N,
+                    // so that ONE backward launch over the whole stacked buffer regenerates the masks of all steps
 };
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16;
@@ -47,13 +49,14 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
 }
 __device__ __forceinline__ uint32_t drop_key(const Drop& d) { return d.seed ? mix32(d.site * 0x9E3779B9u ^ d.seed[0]) : 0u; }
 __device__ __forceinline__ float drop_factor(const Drop& d, uint32_t key, long idx) {
-  return mix32((uint32_t)idx ^ key) >= d.thresh ? d.scale : 0.f;
+  return mix32((uint32_t)(idx + d.offset) ^ key) >= d.thresh ? d.scale : 0.f;
 }
-inline Drop make_drop(const uint32_t* seed, uint32_t site, float p) {
-  Drop d{nullptr, 0u, 0u, 1.f};
+inline Drop make_drop(const uint32_t* seed, uint32_t site, float p, long offset) {
+  Drop d{nullptr, 0u, 0u, 1.f, 0};
   if (seed && p > 0.f) {
     d.seed = seed;
     d.site = site;
+    d.offset = offset;
     d.thresh = (uint32_t)((double)p * 4294967296.0);
     d.scale = 1.f / (1.f - p);
   }
@@ -522,20 +525,23 @@ constexpr int AB_LDS = AB_KC + 4;  // 68: row stride of the [16, 64] tiles
 __global__ void __launch_bounds__(256) k_tr_attn_bwd(const float* __restrict__ dout, const float* __restrict__ q,
                                                      const float* __restrict__ kv, const float* __restrict__ p,
                                                      const float* __restrict__ o, int S, int T, float* __restrict__ dq,
-                                                     float* __restrict__ dkv, Drop drop, long b_off) {
+                                                     float* __restrict__ dkv, Drop drop, int b_base, int kv_batch) {
   __shared__ __align__(16) float ks[AB_KC][AB_LD], vs[AB_KC][AB_LD];
   __shared__ __align__(16) float qs[AB_QT][AB_LD], gs[AB_QT][AB_LD];
   __shared__ __align__(16) float ps[AB_QT][AB_LDS], ds[AB_QT][AB_LDS];
   __shared__ __align__(16) float pf[AB_QT][AB_LDS];  // P * dropout factor (= P without dropout): what multiplied V in the forward
   const uint32_t dkey = drop_key(drop);
   __shared__ float delta[AB_QT];
-  const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * AB_KC;
+  // kv_batch > 0: the K|V rows of batch element b are those of b % kv_batch (step-stacked queries [t][scene] against the per-scene
+  // map keys); dK / dV of a key then receive contributions from several CTAs and are added atomically (dkv zero-initialised)
+  const int b = blockIdx.z + b_base, h = blockIdx.y, j0 = blockIdx.x * AB_KC;
+  const int bk = kv_batch > 0 ? b % kv_batch : b;
   const int tid = threadIdx.x;
   const int nk = min(AB_KC, T - j0);
   for (int e = tid; e < AB_KC * TR_DH; e += 256) {
     const int j = e / TR_DH, d = e % TR_DH;
     const bool ok = j < nk;
-    const long base = ((long)b * T + j0 + j) * 2 * TR_D + h * TR_DH + d;
+    const long base = ((long)bk * T + j0 + j) * 2 * TR_D + h * TR_DH + d;
     ks[j][d] = ok ? kv[base] : 0.f;
     vs[j][d] = ok ? kv[base + TR_D] : 0.f;
   }
@@ -559,7 +565,7 @@ __global__ void __launch_bounds__(256) k_tr_attn_bwd(const float* __restrict__ d
       const long pidx = (((long)b * TR_H + h) * S + s0 + qi) * T + j0 + j;
       const float pv = (qi < nq && j < nk) ? p[pidx] : 0.f;
       ps[qi][j] = pv;
-      pf[qi][j] = drop.seed ? pv * drop_factor(drop, dkey, pidx + b_off) : pv;
+      pf[qi][j] = drop.seed ? pv * drop_factor(drop, dkey, pidx) : pv;
     }
     if (tid < AB_QT * 2) {  // delta = sum_d do * o, two half rows per query
       const int qi = tid / 2, half = tid % 2;
@@ -620,9 +626,14 @@ __global__ void __launch_bounds__(256) k_tr_attn_bwd(const float* __restrict__ d
   for (int u = 0; u < 8; ++u) {
     const int j = oj * 8 + u;
     if (j < nk) {
-      const long base = ((long)b * T + j0 + j) * 2 * TR_D + h * TR_DH + od;
-      dkv[base] = adk[u];
-      dkv[base + TR_D] = adv[u];
+      const long base = ((long)bk * T + j0 + j) * 2 * TR_D + h * TR_DH + od;
+      if (kv_batch > 0) {
+        atomicAdd(&dkv[base], adk[u]);
+        atomicAdd(&dkv[base + TR_D], adv[u]);
+      } else {
+        dkv[base] = adk[u];
+        dkv[base + TR_D] = adv[u];
+      }
     }
   }
 }
@@ -1280,11 +1291,11 @@ extern "C" {
 // y = (dropout(relu(x W^T + bias) * keep_lin[row]) + res) * keep_out[row]; bias / keep_lin / res / keep_out / drop_seed may be NULL
 int32_t tb_tr_linear_fwd(const float* x, int64_t M, int32_t K, const float* w, int64_t ldw, int32_t N, const float* bias, int32_t relu,
                          const uint8_t* keep_lin, const float* res, const uint8_t* keep_out, float* y, const uint32_t* drop_seed,
-                         uint32_t drop_site, float drop_p, void* stream) {
+                         uint32_t drop_site, float drop_p, int64_t drop_offset, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TR_CHECK(x && w && y, TB_ERR_NULL);
   TR_CHECK(M > 0 && K > 0 && N > 0 && ldw >= K, TB_ERR_BAD_SHAPE);
-  GemmOpt op{nullptr, nullptr, nullptr, bias, relu, keep_lin, res, keep_out, nullptr, make_drop(drop_seed, drop_site, drop_p)};
+  GemmOpt op{nullptr, nullptr, nullptr, bias, relu, keep_lin, res, keep_out, nullptr, make_drop(drop_seed, drop_site, drop_p, drop_offset)};
   if (M <= SMALL_M) {
     dim3 grid((unsigned)((M + 31) / 32), (N + GN - 1) / GN, 1);
     k_tr_gemm<32, true, false, EPI_BIAS><<<grid, 256, 0, st>>>(x, K, 1, w, 1, ldw, y, N, M, N, K, K, op);
@@ -1300,7 +1311,7 @@ int32_t tb_tr_linear_fwd(const float* x, int64_t M, int32_t K, const float* w, i
 // NULL: the keep_lin / keep_out of the forward; drop_* as in the forward).  dx / dw / db may be NULL (skipped); db needs dw.
 int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_t ldw, const float* y, int32_t relu, const uint8_t* rm1,
                          const uint8_t* rm2, int64_t M, int32_t K, int32_t N, float* dx, float* dw, int64_t lddw, float* db,
-                         const uint32_t* drop_seed, uint32_t drop_site, float drop_p, void* stream) {
+                         const uint32_t* drop_seed, uint32_t drop_site, float drop_p, int64_t drop_offset, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TR_CHECK(dy && x && w, TB_ERR_NULL);
   TR_CHECK(M > 0 && K > 0 && N > 0 && (!relu || y), TB_ERR_BAD_SHAPE);
@@ -1322,7 +1333,7 @@ int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_
   }
   const long total = n_dx + nz * dw_tiles_i * dw_tiles_j;
   TR_CHECK(total > 0 && total < 2147483647L, TB_ERR_BAD_SHAPE);
-  GemmOpt op{relu ? y : nullptr, rm1, rm2, nullptr, 0, nullptr, nullptr, nullptr, db, make_drop(drop_seed, drop_site, drop_p)};
+  GemmOpt op{relu ? y : nullptr, rm1, rm2, nullptr, 0, nullptr, nullptr, nullptr, db, make_drop(drop_seed, drop_site, drop_p, drop_offset)};
   if (TMh == 32)
     k_tr_linear_bwd<32><<<(unsigned)total, 256, 0, st>>>(dy, x, w, ldw, M, K, N, dx, dw, lddw, (int)n_dx, dx_tiles_j, dw_tiles_i,
                                                          dw_tiles_j, chunk, op);
@@ -1335,39 +1346,39 @@ int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_
 
 int32_t tb_tr_layernorm_fwd(const float* x, const float* w, const float* b, int32_t relu, int64_t M, int32_t D, float* y, float* stats,
                         const uint32_t* drop_seed, uint32_t drop_site,
-                        float drop_p, void* stream) {
+                        float drop_p, int64_t drop_offset, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TR_CHECK(x && w && b && y && stats, TB_ERR_NULL);
   TR_CHECK(M > 0 && D == TR_D, TB_ERR_BAD_SHAPE);
   TR_CHECK(aligned16(x) && aligned16(y) && aligned16(w) && aligned16(b), TB_ERR_ALIGN);
-  k_tr_ln_fwd<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(x, w, b, relu, M, y, stats, make_drop(drop_seed, drop_site, drop_p));
+  k_tr_ln_fwd<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(x, w, b, relu, M, y, stats, make_drop(drop_seed, drop_site, drop_p, drop_offset));
   count_launch();
   return launch_status();
 }
 
 int32_t tb_tr_layernorm_bwd(const float* dy, const float* x, const float* w, const float* stats, const float* y, int32_t relu, int64_t M,
                         int32_t D, float* dx, float* dw, float* db, const uint32_t* drop_seed, uint32_t drop_site,
-                        float drop_p, void* stream) {
+                        float drop_p, int64_t drop_offset, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TR_CHECK(dy && x && w && stats && dx, TB_ERR_NULL);
   TR_CHECK(M > 0 && D == TR_D && (!relu || y) && ((dw == nullptr) == (db == nullptr)), TB_ERR_BAD_SHAPE);
   TR_CHECK(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(w), TB_ERR_ALIGN);
   const long rows = 64;
   k_tr_ln_bwd<<<(unsigned)((M + rows - 1) / rows), 256, 0, st>>>(dy, x, w, stats, y, relu, M, rows, dx, dw, db,
-                                                                 make_drop(drop_seed, drop_site, drop_p));
+                                                                 make_drop(drop_seed, drop_site, drop_p, drop_offset));
   count_launch();
   return launch_status();
 }
 
 int32_t tb_tr_attention_fwd(const float* q, const float* kv, const uint8_t* key_valid, int32_t eye, int32_t B, int32_t S, int32_t T,
                         float* o, float* p, uint8_t* dead, const uint32_t* drop_seed, uint32_t drop_site,
-                        float drop_p, void* stream) {
+                        float drop_p, int64_t drop_offset, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TR_CHECK(q && kv && key_valid && o && p && dead, TB_ERR_NULL);
   TR_CHECK(B > 0 && S > 0 && T > 0 && T <= 6144 && (!eye || S == T) && B <= 65535 * 1024, TB_ERR_BAD_SHAPE);
   TR_CHECK(aligned16(kv), TB_ERR_ALIGN);
   if (T <= 32) {  // one warp per (batch element, head)
-    k_tr_attn_small_fwd<<<B, 128, 0, st>>>(q, kv, key_valid, eye, S, T, o, p, dead, make_drop(drop_seed, drop_site, drop_p));
+    k_tr_attn_small_fwd<<<B, 128, 0, st>>>(q, kv, key_valid, eye, S, T, o, p, dead, make_drop(drop_seed, drop_site, drop_p, drop_offset));
     count_launch();
     return launch_status();
   }
@@ -1382,31 +1393,32 @@ int32_t tb_tr_attention_fwd(const float* q, const float* kv, const uint8_t* key_
     dim3 grid((S + AT_QT - 1) / AT_QT, TR_H, nb);
     k_tr_attn_fwd<<<grid, 128, smem, st>>>(q + (size_t)b0 * S * TR_D, kv + (size_t)b0 * T * 2 * TR_D, key_valid + (size_t)b0 * T, eye, S,
                                            T, o + (size_t)b0 * S * TR_D, p + (size_t)b0 * TR_H * S * T, dead + (size_t)b0 * S,
-                                           make_drop(drop_seed, drop_site, drop_p), (long)b0 * TR_H * S * T);
+                                           make_drop(drop_seed, drop_site, drop_p, drop_offset), (long)b0 * TR_H * S * T);
     count_launch();
   }
   return launch_status();
 }
 
-// dq must be zero-initialised by the caller (partials are added atomically); dkv is overwritten
+// dq must be zero-initialised by the caller (partials are added atomically); dkv is overwritten -- or, with kv_batch > 0 (K|V of
+// batch element b = those of b % kv_batch; kv / dkv hold kv_batch elements), accumulated atomically into a zero-initialised buffer
 int32_t tb_tr_attention_bwd(const float* dout, const float* q, const float* kv, const float* p, const float* o, int32_t B, int32_t S,
-                        int32_t T, float* dq, float* dkv, const uint32_t* drop_seed, uint32_t drop_site,
-                        float drop_p, void* stream) {
+                            int32_t T, int32_t kv_batch, float* dq, float* dkv, const uint32_t* drop_seed, uint32_t drop_site,
+                            float drop_p, int64_t drop_offset, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TR_CHECK(dout && q && kv && p && o && dq && dkv, TB_ERR_NULL);
-  TR_CHECK(B > 0 && S > 0 && T > 0, TB_ERR_BAD_SHAPE);
+  TR_CHECK(B > 0 && S > 0 && T > 0 && kv_batch >= 0 && (kv_batch == 0 || B % kv_batch == 0), TB_ERR_BAD_SHAPE);
   if (T <= 32) {
+    TR_CHECK(kv_batch == 0, TB_ERR_UNSUPPORTED);
     TR_CHECK(aligned16(kv) && aligned16(dkv), TB_ERR_ALIGN);
-    k_tr_attn_small_bwd<<<B, 128, 0, st>>>(dout, q, kv, p, o, S, T, dq, dkv, make_drop(drop_seed, drop_site, drop_p));
+    k_tr_attn_small_bwd<<<B, 128, 0, st>>>(dout, q, kv, p, o, S, T, dq, dkv, make_drop(drop_seed, drop_site, drop_p, drop_offset));
     count_launch();
     return launch_status();
   }
   for (int b0 = 0; b0 < B; b0 += 65535) {
     const int nb = B - b0 < 65535 ? B - b0 : 65535;
     dim3 grid((T + AB_KC - 1) / AB_KC, TR_H, nb);
-    k_tr_attn_bwd<<<grid, 256, 0, st>>>(dout + (size_t)b0 * S * TR_D, q + (size_t)b0 * S * TR_D, kv + (size_t)b0 * T * 2 * TR_D,
-                                        p + (size_t)b0 * TR_H * S * T, o + (size_t)b0 * S * TR_D, S, T, dq + (size_t)b0 * S * TR_D,
-                                        dkv + (size_t)b0 * T * 2 * TR_D, make_drop(drop_seed, drop_site, drop_p), (long)b0 * TR_H * S * T);
+    k_tr_attn_bwd<<<grid, 256, 0, st>>>(dout, q, kv, p, o, S, T, dq, dkv, make_drop(drop_seed, drop_site, drop_p, drop_offset), b0,
+                                        kv_batch);
     count_launch();
   }
   return launch_status();
@@ -1424,10 +1436,10 @@ int32_t tb_tr_add_mask(const float* a, const uint8_t* keep_a, const float* b, co
 }
 
 // y = x * dropout factor (inter-layer dropout of nn.GRU, agent_temporal.py:116); applied to dy it is its own backward
-int32_t tb_tr_dropout(const float* x, int64_t n, float* y, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, void* stream) {
+int32_t tb_tr_dropout(const float* x, int64_t n, float* y, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, int64_t drop_offset, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TR_CHECK(x && y && drop_seed, TB_ERR_NULL);
-  k_tr_dropout<<<grid_for(n), 256, 0, st>>>(x, n, y, make_drop(drop_seed, drop_site, drop_p));
+  k_tr_dropout<<<grid_for(n), 256, 0, st>>>(x, n, y, make_drop(drop_seed, drop_site, drop_p, drop_offset));
   count_launch();
   return launch_status();
 }

@@ -34,6 +34,7 @@ class CudaOps:
         self.L = nt.lib()
         self.check = check
         self.dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.alloc_hook = None  # tape.StepStack: outputs of the forward kernels land in slices of step-stacked buffers
 
     # ---- helpers ----
     def _st(self) -> int:
@@ -53,22 +54,26 @@ class CudaOps:
         return self._c(t, U8)
 
     def _drop(self, drop):
-        """(seed pointer, site id, p) of a dropout call site; (NULL, 0, 0) switches it off."""
+        """(seed pointer, site id, p, element-index offset) of a dropout call site; (NULL, 0, 0, 0) switches it off."""
         if drop is None:
-            return None, 0, 0.0
-        seed, site, p = drop
-        return self._c(seed, torch.int32), int(site) & 0xFFFFFFFF, float(p)
+            return None, 0, 0.0, 0
+        seed, site, p = drop[:3]
+        return self._c(seed, torch.int32), int(site) & 0xFFFFFFFF, float(p), int(drop[3]) if len(drop) > 3 else 0
 
     def dropout(self, x, drop):
-        y = torch.empty_like(x)
+        y = self.empty(tuple(x.shape))
         self._run(self.L.tb_tr_dropout(self._c(x), x.numel(), y.data_ptr(), *self._drop(drop), self._st()), "tb_tr_dropout")
         return y
+
+    dropout_bwd = dropout  # the same mask applied to the gradient
 
     def _run(self, rc: int, what: str) -> None:
         if rc != nt.TB_OK:
             raise nt.TbError(f"{what} failed: {nt.STATUS.get(rc, rc)}")
 
     def empty(self, shape, like: Tensor = None, dtype=F32) -> Tensor:
+        if self.alloc_hook is not None:
+            return self.alloc_hook(tuple(shape), dtype)
         return torch.empty(shape, dtype=dtype, device=self.dev)
 
     def zeros(self, shape, like: Tensor = None, dtype=F32) -> Tensor:
@@ -136,13 +141,15 @@ class CudaOps:
                                              p.data_ptr(), dead.data_ptr(), *self._drop(drop), self._st()), "tb_tr_attention_fwd")
         return o, (p, o), dead
 
-    def attention_bwd(self, do, q, kv, key_valid, eye, p, drop=None):
+    def attention_bwd(self, do, q, kv, key_valid, eye, p, drop=None, kv_shared: bool = False):
+        """kv_shared: q / do / p hold B batch elements, kv only kv.shape[0] (element b uses the keys of b % kv.shape[0])."""
         p, o = p
         B, S, D = q.shape
-        T = kv.shape[1]
+        Bk, T = kv.shape[0], kv.shape[1]
         dq = self.zeros((B, S, D))
-        dkv = self.empty((B, T, 2 * D))
-        self._run(self.L.tb_tr_attention_bwd(self._c(do), self._c(q), self._c(kv), self._c(p), self._c(o), B, S, T, dq.data_ptr(),
+        dkv = self.zeros((Bk, T, 2 * D)) if kv_shared else self.empty((B, T, 2 * D))
+        self._run(self.L.tb_tr_attention_bwd(self._c(do), self._c(q), self._c(kv), self._c(p), self._c(o), B, S, T,
+                                             Bk if kv_shared else 0, dq.data_ptr(),
                                              dkv.data_ptr(), *self._drop(drop), self._st()), "tb_tr_attention_bwd")
         return dq, dkv
 

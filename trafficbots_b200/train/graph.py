@@ -21,7 +21,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 from torch import Tensor
 
-from .tape import Fn, Var
+from .tape import Fn, ReplayOps, StepStack, Var
 
 D = 128
 N_NODE = 20
@@ -89,13 +89,13 @@ class Model:
                              self.p(prefix + ".attn.in_proj_bias", rows=(D, 3 * D)))
 
     def xlayer(self, prefix: str, src: Var, src_keep: Tensor, kv: Var, key_valid: Tensor, B: int, S: int, T: int,
-               eye: bool = False) -> Var:
+               eye: bool = False, kv_shared: bool = False) -> Var:
         """`TransformerCrossAttention.forward`, norm_first (models/modules/transformer.py:186-237) with
         `Attention.forward` (models/modules/attention.py:79-146)."""
         f = self.f
         s2 = self.ln(src, prefix + ".norm1")
         q = f.linear(s2, self.p(prefix + ".attn.in_proj_weight", rows=(0, D)), self.p(prefix + ".attn.in_proj_bias", rows=(0, D)))
-        o, dead = f.attention(q, kv, key_valid, B, S, T, eye, drop=self.dp())  # attention.py:131-132
+        o, dead = f.attention(q, kv, key_valid, B, S, T, eye, drop=self.dp(), kv_shared=kv_shared)  # attention.py:131-132
         # out-projection, dead rows forced to 0 (attention.py:144-146), dropout1 + residual (transformer.py:202-205): one Linear
         src = f.linear(o, self.p(prefix + ".attn.out_proj_weight"), self.p(prefix + ".attn.out_proj_bias"),
                        keep_lin=(dead == 0).to(U8), res=src, drop=self.dp())
@@ -106,10 +106,20 @@ class Model:
                         drop=self.dp())
 
     def tf_block(self, prefix: str, n_layer: int, src: Var, src_keep: Tensor, kvs: List[Var], key_valid: Tensor, B: int, S: int,
-                 T: int, eye: bool = False) -> Var:
+                 T: int, eye: bool = False, kv_shared: bool = False) -> Var:
         for i in range(n_layer):
-            src = self.xlayer(f"{prefix}.layers.{i}", src, src_keep, kvs[i], key_valid, B, S, T, eye)
+            src = self.xlayer(f"{prefix}.layers.{i}", src, src_keep, kvs[i], key_valid, B, S, T, eye, kv_shared)
         return src
+
+    def decode_front(self, attr: Tensor, pe: Tensor, vflat: Tensor, valid2d: Tensor, kv_map: List[Var], map_valid: Tensor,
+                     kv_tl: List[Var], tl_valid: Tensor, B: int, A: int, P: int, TL: int, kv_shared: bool = False) -> Var:
+        """the part of a decode step in front of the GRU: state embedding (pl_modules/waymo_motion.py:136-153) and the three
+        attention blocks of `TrafficBots.forward` (models/traffic_bots.py:201-226).  Its inputs are gradient-free (the policy
+        input is detached), so its backward does not take part in the back-propagation through time."""
+        x = self.input_pe_encoder("model.agent_encoder", vflat, attr, pe)
+        x = self.tf_block("model.transformer_as2pl", 3, x, vflat, kv_map, map_valid, B, A, P, kv_shared=kv_shared)
+        x = self.tf_block("model.transformer_as2tl", 3, x, vflat, kv_tl, tl_valid, B, A, TL)
+        return self.interaction("model.agent_interaction", x, valid2d, B, A)
 
     def interaction(self, prefix: str, x: Var, valid: Tensor, B: int, A: int) -> Var:
         """`MultiAgentTF.forward` (models/modules/agent_interaction.py:51-93).  valid [B, A]."""
@@ -260,7 +270,7 @@ LOSS_CFG = dict(w_vae_kl=0.1, kl_free_nats=0.01, w_diffbar_reward=1.0, w_goal=1.
 def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tensor, use_prior: bool, n_step: int = 90,
                      n_hist: int = 11, down: int = 5, loss_cfg: Dict = LOSS_CFG, return_buffers: bool = False,
                      drop_seed: Optional[Tensor] = None, drop_p: float = 0.0, defer_loss: bool = False,
-                     first_drop_site: int = 0) -> Dict[str, Tensor]:
+                     first_drop_site: int = 0, stack_backward: Optional[bool] = None) -> Dict[str, Tensor]:
     """forward of `training_step` + seeding of the loss gradients; call `fn.backward()` afterwards.
 
     batch: the raw episode (`agent/*` [S,91,A,..], `tl_stop/*` [S,91,TL,..], `map/*`, `agent/dest`, ...) on the device of
@@ -375,6 +385,26 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
     f_xy = params.buffers["pre_processing.input.pose_pe_agent.pe_xy.freqs"]
     f_yaw = params.buffers["pre_processing.input.pose_pe_agent.pe_yaw.freqs"]
 
+    # ---- step-stacked backward of the decode front (see Model.decode_front): the forward of every step writes its buffers into
+    # row block t of step-stacked buffers; afterwards the chain is RECORDED once over the stacked buffers, so its backward is one
+    # pass with n_step x M rows per launch instead of n_step passes with M rows (the front is ~70 % of a step's launches).
+    # Needs the CUDA back end (allocation hook) and the general attention kernel for the shared map keys (P > 32).
+    if stack_backward is None:
+        stack_backward = getattr(ops, "name", "") == "cuda" and P > 32
+    pre_site = first_drop_site + 500000  # dropout sites of the front: the same ids at every step, element indices continue
+    if stack_backward:
+        stack = StepStack(ops, n_step)
+        fn_s = Fn(ops, record=False)
+        m_s = Model(fn_s, params, drop_seed, drop_p)
+        fr = torch.clamp(torch.arange(n_step, device=dev), max=n_hist - 1)  # TL frame of step t: min(t - 1, 10) (:287)
+        idx_steps = ((fr[:, None, None] * S + torch.arange(S, device=dev)[None, :, None]) * TL
+                     + torch.arange(TL, device=dev)[None, None, :]).reshape(-1)
+        kv_tl_steps = [f.gather_rows(kv, idx_steps) for kv in kv_tl_hist]  # [n_step * S * TL, 2D] (recorded: scatter-add backward)
+        tlv_steps = tlv_tm[fr].to(U8).contiguous()  # [n_step, S, TL]
+        rollout_start = len(f.nodes)
+        attr_l, pe_l, vflat_l, valid_l = [], [], [], []
+        x_front = None
+
     for t in range(1, n_step + 1):
         ovr = tf_mask[:, t].to(U8) if t < T_gt else zeros_u8
         tl_t = min(t - 1, n_hist - 1)
@@ -383,12 +413,26 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
         sd_ = state.data.view(S, A, 4)
         attr = torch.cat([vel, sd_[..., 3:4], yaw_rate, acc, size.view(S, A, 3), a_type.view(S, A, 3).to(torch.float32)], -1)
         pe = ops.pose_pe(sd_[..., :2].reshape(M, 2).contiguous(), sd_[..., 2].reshape(M).contiguous(), f_xy, f_yaw)
-        x = m.input_pe_encoder("model.agent_encoder", vflat, attr.reshape(M, 11).contiguous(), pe)
+        attr = attr.reshape(M, 11).contiguous()
         # TrafficBots.forward (models/traffic_bots.py:201-241)
-        x = m.tf_block("model.transformer_as2pl", 3, x, vflat, kv_map, pl_valid, S, A, P)
-        kv_t = [f.row_slice(kv, tl_t * S * TL, (tl_t + 1) * S * TL) for kv in kv_tl_hist]
-        x = m.tf_block("model.transformer_as2tl", 3, x, vflat, kv_t, tlv_tm[tl_t].to(U8).contiguous(), S, A, TL)
-        x = m.interaction("model.agent_interaction", x, valid, S, A)
+        if stack_backward:
+            i = t - 1
+            post_site, m_s.n_site, fn_s.stack_t = m.n_site, pre_site, i
+            stack.begin(i)
+            kv_t = [Var(kv.data[i * S * TL:(i + 1) * S * TL]) for kv in kv_tl_steps]
+            x = m_s.decode_front(attr, pe, vflat, valid, kv_map, pl_valid, kv_t, tlv_steps[i], S, A, P, TL)
+            stack.end()
+            if x_front is None:
+                x_front = Var(stack.bufs[-1].flatten(0, 1), True)  # the front's outputs of all steps
+            assert x.data.data_ptr() == x_front.data[i * M:(i + 1) * M].data_ptr()
+            x = f.row_slice(x_front, i * M, (i + 1) * M)
+            attr_l.append(attr), pe_l.append(pe), vflat_l.append(vflat), valid_l.append(valid)
+            m.n_site = post_site
+        else:  # per-step recording; the dropout sites / element indices are those of the stacked schedule (same masks)
+            kv_t = [f.row_slice(kv, tl_t * S * TL, (tl_t + 1) * S * TL) for kv in kv_tl_hist]
+            post_site, m.n_site, f.stack_t = m.n_site, pre_site, t - 1
+            x = m.decode_front(attr, pe, vflat, valid, kv_map, pl_valid, kv_t, tlv_tm[tl_t].to(U8).contiguous(), S, A, P, TL)
+            m.n_site, f.stack_t = post_site, None
         x, hidden = m.gru_layers("model.agent_temporal", x, hidden, vflat)
         for name, zr, zv in (("model.add_goal", z_goal if hoist else mlp_in_goal(), goal_valid.reshape(-1)),
                              ("model.add_latent", z_lat if hoist else mlp_in_latent(), vflat)):
@@ -431,6 +475,19 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
         rv_l.append(rv)
         if return_buffers:
             preds_l.append(pred.data)
+
+    if stack_backward:  # record the front ONCE over the stacked buffers; its nodes run after the per-step nodes in the backward
+        rops = ReplayOps(ops, stack)
+        fn_r = Fn(rops)
+        m_r = Model(fn_r, params, drop_seed, drop_p)
+        m_r.n_site = pre_site
+        out_r = m_r.decode_front(torch.cat(attr_l), torch.cat(pe_l), torch.cat(vflat_l), torch.cat(valid_l), kv_map, pl_valid,
+                                 kv_tl_steps, tlv_steps.reshape(n_step * S, TL), n_step * S, A, P, TL, kv_shared=True)
+        assert rops.done() and out_r.data.data_ptr() == x_front.data.data_ptr()
+        fn_r.ops = ops
+        out_r.grad, out_r.grad_fixed = x_front.grad, True  # filled by the GRU backward of every step (row slices)
+        f.nodes[rollout_start:rollout_start] = fn_r.nodes
+        f.n_fwd += fn_s.n_fwd
 
     # ---- TrainingMetrics.update / compute (models/metrics/training.py:62-158) ----
     t0 = loss_cfg["step_training_start"]

@@ -40,13 +40,81 @@ class Var:
         return Var(self.data, False)
 
 
+class StepStack:
+    """Allocation hook of the ops back end for a chain of forward primitives that runs once per decode step: the k-th output
+    buffer of step t is row block t of ONE buffer [n_step, rows, cols].  The backward of that chain then runs ONCE over the stacked
+    buffers (`ReplayOps`) instead of once per step: its launches see n_step x 1024 rows instead of 1024."""
+
+    def __init__(self, ops, n_step: int) -> None:
+        self.ops, self.n_step, self.bufs, self.t, self.k = ops, n_step, [], 0, 0
+
+    def begin(self, t: int) -> None:
+        self.t, self.k = t, 0
+        self.ops.alloc_hook = self._alloc
+
+    def end(self) -> None:
+        self.ops.alloc_hook = None
+        assert self.k == len(self.bufs), "every step must allocate the same sequence of buffers"
+
+    def _alloc(self, shape, dtype) -> Tensor:
+        if self.k == len(self.bufs):
+            assert self.t == 0, "allocation sequence changed between steps"
+            self.ops.alloc_hook = None
+            self.bufs.append(self.ops.empty((self.n_step,) + tuple(shape), dtype=dtype))
+            self.ops.alloc_hook = self._alloc
+        buf = self.bufs[self.k]
+        assert tuple(buf.shape[1:]) == tuple(shape) and buf.dtype == dtype, (buf.shape, shape)
+        self.k += 1
+        return buf[self.t]
+
+
+class ReplayOps:
+    """ops back end for RECORDING a chain whose forward already ran step by step into a `StepStack`: every forward primitive
+    returns the next stacked buffer(s) instead of launching; everything else (the backward kernels) is the real back end."""
+
+    def __init__(self, ops, stack: StepStack) -> None:
+        self._ops, self._bufs, self._i = ops, stack.bufs, 0
+
+    def __getattr__(self, name):
+        return getattr(self._ops, name)
+
+    def _pop(self) -> Tensor:
+        b = self._bufs[self._i]
+        self._i += 1
+        return b.flatten(0, 1)
+
+    def done(self) -> bool:
+        return self._i == len(self._bufs)
+
+    def linear_fwd(self, *a, **k):
+        return self._pop()
+
+    add_mask_fwd = select_rows_fwd = cat2_fwd = gather_rows_fwd = dropout = linear_fwd
+
+    def layernorm_fwd(self, *a, **k):
+        y = self._pop()
+        return y, self._pop()
+
+    def attention_fwd(self, *a, **k):
+        o, p, dead = self._pop(), self._pop(), self._pop()
+        return o, (p, o), dead
+
+
 class Fn:
     """records primitives on a tape; `backward()` replays the backward kernels in reverse."""
 
-    def __init__(self, ops) -> None:
+    def __init__(self, ops, record: bool = True) -> None:
         self.ops = ops
         self.nodes: List[Callable[[], None]] = []
         self.n_fwd = 0
+        self.record = record  # False: forward only (a step of a `StepStack` chain, recorded later through `ReplayOps`)
+        self.stack_t: Optional[int] = None  # step index of a `StepStack` chain: offsets the dropout element indices
+
+    def _d(self, drop, numel: int):
+        """dropout site of a launch that fills row block `stack_t` of a step-stacked buffer: element indices continue across steps."""
+        if drop is None or self.stack_t is None:
+            return drop
+        return (drop[0], drop[1], drop[2], self.stack_t * numel)
 
     # ------------------------------------------------------------------ tape mechanics
     def _acc(self, v: Var, g: Optional[Tensor], owned: bool = True) -> None:
@@ -64,6 +132,9 @@ class Fn:
             self.ops.add_(v.grad, g)
 
     def _push(self, out: Var, fn: Callable[[Tensor], None]) -> None:
+        if not self.record:
+            return
+
         def node() -> None:
             g = out.grad
             if g is None:
@@ -114,6 +185,7 @@ class Fn:
         tail of a transformer sub-layer fused into its epilogue (one kernel instead of four).  drop = (seed, site, p) or None."""
         assert not (relu and (res is not None or keep_lin is not None or keep_out is not None))
         bd = None if b is None else b.data.view(-1)
+        drop = self._d(drop, x.rows * w.data.shape[0])
         y = self.ops.linear_fwd(x.data, w.data, bd, relu, keep_lin, None if res is None else res.data, keep_out, drop)
         self.n_fwd += 1
         req = x.req or w.req or (res is not None and res.req)
@@ -132,6 +204,7 @@ class Fn:
 
     def layernorm(self, x: Var, w: Var, b: Var, relu: bool = False, drop=None) -> Var:
         wd, bd = w.data.view(-1), b.data.view(-1)
+        drop = self._d(drop, x.data.numel())
         y, stats = self.ops.layernorm_fwd(x.data, wd, bd, relu, drop)
         self.n_fwd += 1
         req = x.req or w.req
@@ -144,19 +217,23 @@ class Fn:
             self._push(out, bw)
         return out
 
-    def attention(self, q: Var, kv: Var, key_valid: Tensor, n_batch: int, n_src: int, n_tgt: int, eye: bool, drop=None):
-        """q [B*S, D], kv [B*T, 2D] -> (o [B*S, D], dead [B*S] u8); drop: dropout on the attention probabilities."""
+    def attention(self, q: Var, kv: Var, key_valid: Tensor, n_batch: int, n_src: int, n_tgt: int, eye: bool, drop=None,
+                  kv_shared: bool = False):
+        """q [B*S, D], kv [B*T, 2D] -> (o [B*S, D], dead [B*S] u8); drop: dropout on the attention probabilities.
+        kv_shared (backward of a step-stacked chain only): kv holds fewer batch elements than q, element b uses kv[b % n_kv]."""
         D = q.cols
-        o, p, dead = self.ops.attention_fwd(q.data.view(n_batch, n_src, D), kv.data.view(n_batch, n_tgt, 2 * D), key_valid, eye, drop)
+        n_kv = kv.rows // n_tgt
+        drop = self._d(drop, n_batch * 4 * n_src * n_tgt)
+        o, p, dead = self.ops.attention_fwd(q.data.view(n_batch, n_src, D), kv.data.view(n_kv, n_tgt, 2 * D), key_valid, eye, drop)
         self.n_fwd += 1
         req = q.req or kv.req
         out = Var(o.view(n_batch * n_src, D), req)
         if req:
             def bw(g: Tensor) -> None:
                 dq, dkv = self.ops.attention_bwd(g.view(n_batch, n_src, D), q.data.view(n_batch, n_src, D),
-                                                 kv.data.view(n_batch, n_tgt, 2 * D), key_valid, eye, p, drop)
+                                                 kv.data.view(n_kv, n_tgt, 2 * D), key_valid, eye, p, drop, kv_shared)
                 self._acc(q, dq.view(n_batch * n_src, D))
-                self._acc(kv, dkv.view(n_batch * n_tgt, 2 * D))
+                self._acc(kv, dkv.view(n_kv * n_tgt, 2 * D))
             self._push(out, bw)
         return out, dead.view(-1)
 
@@ -183,12 +260,13 @@ class Fn:
         """elementwise dropout (nn.GRU's inter-layer dropout); drop None = identity."""
         if drop is None:
             return x
+        drop = self._d(drop, x.data.numel())
         y = self.ops.dropout(x.data, drop)
         self.n_fwd += 1
         out = Var(y, x.req)
         if x.req:
             def bw(g: Tensor) -> None:
-                self._acc(x, self.ops.dropout(g, drop))
+                self._acc(x, self.ops.dropout_bwd(g, drop))
             self._push(out, bw)
         return out
 
