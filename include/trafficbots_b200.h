@@ -457,7 +457,8 @@ int32_t tb_tr_linear_fwd(const float* x, int64_t M, int32_t K, const float* w, i
 int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_t ldw, const float* y, int32_t relu, const uint8_t* rm1, const uint8_t* rm2, int64_t M, int32_t K, int32_t N, float* dx, float* dw, int64_t lddw, float* db, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, int64_t drop_offset, void* stream);
 int32_t tb_tr_layernorm_fwd(const float* x, const float* w, const float* b, int32_t relu, int64_t M, int32_t D, float* y, float* stats, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, int64_t drop_offset, void* stream);
 int32_t tb_tr_layernorm_bwd(const float* dy, const float* x, const float* w, const float* stats, const float* y, int32_t relu, int64_t M, int32_t D, float* dx, float* dw, float* db, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, int64_t drop_offset, void* stream);
-int32_t tb_tr_attention_fwd(const float* q, const float* kv, const uint8_t* key_valid, int32_t eye, int32_t B, int32_t S, int32_t T, float* o, float* p, uint8_t* dead, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, int64_t drop_offset, void* stream);
+/* alive[b, s] = 0 for rows without any admissible key (their o and p are 0: attention.py:101-107,144-146), else 1 */
+int32_t tb_tr_attention_fwd(const float* q, const float* kv, const uint8_t* key_valid, int32_t eye, int32_t B, int32_t S, int32_t T, float* o, float* p, uint8_t* alive, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, int64_t drop_offset, void* stream);
 /* dq must be zero-initialised by the caller (partials are added atomically); dkv is overwritten -- or, with kv_batch > 0 (K|V of */
 /* batch element b = those of b % kv_batch; kv / dkv hold kv_batch elements), accumulated atomically into a zero-initialised buffer */
 int32_t tb_tr_attention_bwd(const float* dout, const float* q, const float* kv, const float* p, const float* o, int32_t B, int32_t S, int32_t T, int32_t kv_batch, float* dq, float* dkv, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, int64_t drop_offset, void* stream);

@@ -126,7 +126,7 @@ class OracleOps:
     # ---- multi-head cross attention core (models/modules/attention.py:89-141), no projections ----
     def attention_fwd(self, q: Tensor, kv: Tensor, key_valid: Tensor, eye: bool, drop=None):
         """q [B,S,D], kv [B,T,2D] (K | V), key_valid [B,T]; eye: query i may not attend key i (agent_interaction.py:57-59).
-        Rows without any admissible key (attention.py:101-107,144-146): o = 0, p = 0, dead = 1."""
+        Rows without any admissible key (attention.py:101-107,144-146): o = 0, p = 0, alive = 0.  Returns (o, p, alive)."""
         B, S, D = q.shape
         T = kv.shape[1]
         dh = D // N_HEAD
@@ -142,7 +142,7 @@ class OracleOps:
         p = torch.softmax(logits / math.sqrt(dh), dim=-1).masked_fill(dead[:, None, :, None], 0.0)
         pd = p if drop is None else p * drop_factor(drop, p.shape, p.device)  # attention.py:131-132
         o = torch.matmul(pd, vh).transpose(1, 2).flatten(2, 3)
-        return o, p, dead.to(torch.uint8)
+        return o, p, (~dead).to(torch.uint8)
 
     def attention_bwd(self, do, q, kv, key_valid, eye, p, drop=None, kv_shared: bool = False):
         q_, kv_ = _req(q, kv)

@@ -114,13 +114,13 @@ def test_attention(ops, B, S, T, eye):
         kvalid[1] = False
         kvalid[1, 0] = True  # exactly one valid key (with eye: row 0 is dead)
     kvalid = kvalid.to(torch.uint8)
-    o_ref, p_ref, dead_ref = ORC.attention_fwd(q, kv, kvalid, eye)
+    o_ref, p_ref, alive_ref = ORC.attention_fwd(q, kv, kvalid, eye)
     dq_ref, dkv_ref = ORC.attention_bwd(do, q, kv, kvalid, eye, p_ref)
     qg, kvg, dog, kvg_valid = g(q, kv, do, kvalid)
-    o, p, dead = ops.attention_fwd(qg, kvg, kvg_valid, eye)
+    o, p, alive = ops.attention_fwd(qg, kvg, kvg_valid, eye)
     close(o, o_ref, what="o")
     close(p[0], p_ref, what="p")
-    assert torch.equal(dead.cpu(), dead_ref)
+    assert torch.equal(alive.cpu(), alive_ref) and not bool(alive_ref[0].any())  # batch element 0 has no valid key
     dq, dkv = ops.attention_bwd(dog, qg, kvg, kvg_valid, eye, p)
     close(dq, dq_ref, tol=5e-5, what="dq", atol=1e-5)  # rows with a single admissible key: dq == 0 up to rounding
     close(dkv, dkv_ref, tol=5e-5, what="dkv")
@@ -437,9 +437,9 @@ def test_dropout_in_linear_layernorm_attention(ops):
         q, kv, do = torch.randn(B, S, 128), torch.randn(B, T, 256), torch.randn(B, S, 128)
         kvalid = (torch.rand(B, T) < 0.8).to(torch.uint8)
         d = _drop(site)
-        o_ref, p_ref, dead_ref = ORC.attention_fwd(q, kv, kvalid, eye, d)
+        o_ref, p_ref, _alive_ref = ORC.attention_fwd(q, kv, kvalid, eye, d)
         dq_ref, dkv_ref = ORC.attention_bwd(do, q, kv, kvalid, eye, p_ref, d)
-        o, p, dead = ops.attention_fwd(q.to(DEV), kv.to(DEV), kvalid.to(DEV), eye, _dropg(d))
+        o, p, _alive = ops.attention_fwd(q.to(DEV), kv.to(DEV), kvalid.to(DEV), eye, _dropg(d))
         close(o, o_ref, what="o")
         close(p[0], p_ref, what="p")
         dq, dkv = ops.attention_bwd(do.to(DEV), q.to(DEV), kv.to(DEV), kvalid.to(DEV), eye, p, _dropg(d))

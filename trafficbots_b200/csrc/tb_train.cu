@@ -411,7 +411,7 @@ constexpr int AT_QT = 8;  // queries per CTA (forward)
 // grid (ceil(S / AT_QT), H, B), 128 threads; dynamic smem: AT_QT * T logits
 __global__ void __launch_bounds__(128, 4) k_tr_attn_fwd(const float* __restrict__ q, const float* __restrict__ kv,
                                                      const uint8_t* __restrict__ key_valid, int eye, int S, int T,
-                                                     float* __restrict__ o, float* __restrict__ p, uint8_t* __restrict__ dead,
+                                                     float* __restrict__ o, float* __restrict__ p, uint8_t* __restrict__ alive,
                                                      Drop drop, long b_off) {
   extern __shared__ __align__(16) float sm[];
   float* lg = sm;                     // [AT_QT][T]
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(128, 4) k_tr_attn_fwd(const float* __restrict_
     if (lane == 0) {
       rmax[qi] = m;
       rinv[qi] = m > NEG ? 1.f / s : 0.f;
-      if (h == 0 && qi < nq) dead[(long)b * S + s0 + qi] = m > NEG ? 0 : 1;
+      if (h == 0 && qi < nq) alive[(long)b * S + s0 + qi] = m > NEG ? 1 : 0;
     }
   }
   __syncthreads();
@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(256) k_tr_attn_bwd(const float* __restrict__ d
 // warp reductions, O = P V is accumulated with lane = feature.  Same arithmetic as the general kernel.
 __global__ void __launch_bounds__(128) k_tr_attn_small_fwd(const float* __restrict__ q, const float* __restrict__ kv,
                                                            const uint8_t* __restrict__ key_valid, int eye, int S, int T,
-                                                           float* __restrict__ o, float* __restrict__ p, uint8_t* __restrict__ dead,
+                                                           float* __restrict__ o, float* __restrict__ p, uint8_t* __restrict__ alive,
                                                            Drop drop) {
   __shared__ float vs[TR_H][32][TR_DH + 1];
   const uint32_t dkey = drop_key(drop);
@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(128) k_tr_attn_small_fwd(const float* __restri
     const float pv = m > -INFINITY ? e * (1.f / sum) : 0.f;
     const long pidx = (((long)b * TR_H + h) * S + s) * T + lane;
     if (has_key) p[pidx] = pv;
-    if (h == 0 && lane == 0) dead[row] = m > -INFINITY ? 0 : 1;
+    if (h == 0 && lane == 0) alive[row] = m > -INFINITY ? 1 : 0;
     const float pd = (drop.seed && has_key) ? pv * drop_factor(drop, dkey, pidx) : pv;
     float acc = 0.f;
     for (int j = 0; j < T; ++j) acc = fmaf(__shfl_sync(0xffffffffu, pd, j), vs[h][j][lane], acc);
@@ -1370,15 +1370,16 @@ int32_t tb_tr_layernorm_bwd(const float* dy, const float* x, const float* w, con
   return launch_status();
 }
 
+// alive[b, s] = 0 for rows without any admissible key (their o and p are 0: attention.py:101-107,144-146), else 1
 int32_t tb_tr_attention_fwd(const float* q, const float* kv, const uint8_t* key_valid, int32_t eye, int32_t B, int32_t S, int32_t T,
-                        float* o, float* p, uint8_t* dead, const uint32_t* drop_seed, uint32_t drop_site,
+                        float* o, float* p, uint8_t* alive, const uint32_t* drop_seed, uint32_t drop_site,
                         float drop_p, int64_t drop_offset, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  TR_CHECK(q && kv && key_valid && o && p && dead, TB_ERR_NULL);
+  TR_CHECK(q && kv && key_valid && o && p && alive, TB_ERR_NULL);
   TR_CHECK(B > 0 && S > 0 && T > 0 && T <= 6144 && (!eye || S == T) && B <= 65535 * 1024, TB_ERR_BAD_SHAPE);
   TR_CHECK(aligned16(kv), TB_ERR_ALIGN);
   if (T <= 32) {  // one warp per (batch element, head)
-    k_tr_attn_small_fwd<<<B, 128, 0, st>>>(q, kv, key_valid, eye, S, T, o, p, dead, make_drop(drop_seed, drop_site, drop_p, drop_offset));
+    k_tr_attn_small_fwd<<<B, 128, 0, st>>>(q, kv, key_valid, eye, S, T, o, p, alive, make_drop(drop_seed, drop_site, drop_p, drop_offset));
     count_launch();
     return launch_status();
   }
@@ -1392,7 +1393,7 @@ int32_t tb_tr_attention_fwd(const float* q, const float* kv, const uint8_t* key_
     const int nb = B - b0 < 65535 ? B - b0 : 65535;
     dim3 grid((S + AT_QT - 1) / AT_QT, TR_H, nb);
     k_tr_attn_fwd<<<grid, 128, smem, st>>>(q + (size_t)b0 * S * TR_D, kv + (size_t)b0 * T * 2 * TR_D, key_valid + (size_t)b0 * T, eye, S,
-                                           T, o + (size_t)b0 * S * TR_D, p + (size_t)b0 * TR_H * S * T, dead + (size_t)b0 * S,
+                                           T, o + (size_t)b0 * S * TR_D, p + (size_t)b0 * TR_H * S * T, alive + (size_t)b0 * S,
                                            make_drop(drop_seed, drop_site, drop_p, drop_offset), (long)b0 * TR_H * S * T);
     count_launch();
   }

@@ -136,10 +136,10 @@ class CudaOps:
         T = kv.shape[1]
         o = self.empty((B, S, D))
         p = self.empty((B, 4, S, T))
-        dead = self.empty((B, S), dtype=U8)
+        alive = self.empty((B, S), dtype=U8)
         self._run(self.L.tb_tr_attention_fwd(self._c(q), self._c(kv), self._u8(key_valid), int(eye), B, S, T, o.data_ptr(),
-                                             p.data_ptr(), dead.data_ptr(), *self._drop(drop), self._st()), "tb_tr_attention_fwd")
-        return o, (p, o), dead
+                                             p.data_ptr(), alive.data_ptr(), *self._drop(drop), self._st()), "tb_tr_attention_fwd")
+        return o, (p, o), alive
 
     def attention_bwd(self, do, q, kv, key_valid, eye, p, drop=None, kv_shared: bool = False):
         """kv_shared: q / do / p hold B batch elements, kv only kv.shape[0] (element b uses the keys of b % kv.shape[0])."""

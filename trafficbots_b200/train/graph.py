@@ -95,10 +95,10 @@ class Model:
         f = self.f
         s2 = self.ln(src, prefix + ".norm1")
         q = f.linear(s2, self.p(prefix + ".attn.in_proj_weight", rows=(0, D)), self.p(prefix + ".attn.in_proj_bias", rows=(0, D)))
-        o, dead = f.attention(q, kv, key_valid, B, S, T, eye, drop=self.dp(), kv_shared=kv_shared)  # attention.py:131-132
+        o, alive = f.attention(q, kv, key_valid, B, S, T, eye, drop=self.dp(), kv_shared=kv_shared)  # attention.py:131-132
         # out-projection, dead rows forced to 0 (attention.py:144-146), dropout1 + residual (transformer.py:202-205): one Linear
         src = f.linear(o, self.p(prefix + ".attn.out_proj_weight"), self.p(prefix + ".attn.out_proj_bias"),
-                       keep_lin=(dead == 0).to(U8), res=src, drop=self.dp())
+                       keep_lin=alive, res=src, drop=self.dp())
         s2 = self.ln(src, prefix + ".norm2")
         s2 = self.lin(s2, prefix + ".linear1", relu=True, drop=self.dp())  # linear2(dropout(relu(linear1))) (:214-217)
         # second FFN Linear + dropout2 + residual (:219-222) + zeroing of the invalid source rows (:236-237)

@@ -96,8 +96,8 @@ class ReplayOps:
         return y, self._pop()
 
     def attention_fwd(self, *a, **k):
-        o, p, dead = self._pop(), self._pop(), self._pop()
-        return o, (p, o), dead
+        o, p, alive = self._pop(), self._pop(), self._pop()
+        return o, (p, o), alive
 
 
 class Fn:
@@ -219,12 +219,13 @@ class Fn:
 
     def attention(self, q: Var, kv: Var, key_valid: Tensor, n_batch: int, n_src: int, n_tgt: int, eye: bool, drop=None,
                   kv_shared: bool = False):
-        """q [B*S, D], kv [B*T, 2D] -> (o [B*S, D], dead [B*S] u8); drop: dropout on the attention probabilities.
+        """q [B*S, D], kv [B*T, 2D] -> (o [B*S, D], alive [B*S] u8: 0 for rows without any admissible key); drop: dropout on the
+        attention probabilities.
         kv_shared (backward of a step-stacked chain only): kv holds fewer batch elements than q, element b uses kv[b % n_kv]."""
         D = q.cols
         n_kv = kv.rows // n_tgt
         drop = self._d(drop, n_batch * 4 * n_src * n_tgt)
-        o, p, dead = self.ops.attention_fwd(q.data.view(n_batch, n_src, D), kv.data.view(n_kv, n_tgt, 2 * D), key_valid, eye, drop)
+        o, p, alive = self.ops.attention_fwd(q.data.view(n_batch, n_src, D), kv.data.view(n_kv, n_tgt, 2 * D), key_valid, eye, drop)
         self.n_fwd += 1
         req = q.req or kv.req
         out = Var(o.view(n_batch * n_src, D), req)
@@ -235,7 +236,7 @@ class Fn:
                 self._acc(q, dq.view(n_batch * n_src, D))
                 self._acc(kv, dkv.view(n_kv * n_tgt, 2 * D))
             self._push(out, bw)
-        return out, dead.view(-1)
+        return out, alive.view(-1)
 
     def add_mask(self, a: Var, b: Optional[Var], keep: Optional[Tensor], keep_a: Optional[Tensor] = None) -> Var:
         """(a * keep_a[row] + b) * keep[row] (masks are row masks; a zero entry zeroes the row)."""
