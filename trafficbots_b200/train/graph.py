@@ -152,6 +152,40 @@ class Model:
             outs.append(y)
         return outs
 
+    def mlp_in_latent(self, z: Var) -> Var:
+        """relu(add_latent.mlp_in(z)) = Linear-Dropout-ReLU-Linear-Dropout, then mask / ReLU in MLP.forward (mlp.py:36-85): the
+        row mask and the dropout factor commute with ReLU."""
+        lp = "model.add_latent.mlp_in.fc_layers"
+        return self.lin(self.lin(z, f"{lp}.0", relu=True, drop=self.dp()), f"{lp}.3", relu=True, drop=self.dp())
+
+    def mlp_in_goal(self, goal_feature: Var) -> Var:
+        """relu(add_goal.mlp_in(goal_feature)): 3 x [Linear, LayerNorm, Dropout] with ReLU between / after."""
+        gp = "model.add_goal.mlp_in.fc_layers"
+        g = self.ln(self.lin(goal_feature, f"{gp}.0"), f"{gp}.1", relu=True, drop=self.dp())
+        g = self.ln(self.lin(g, f"{gp}.4"), f"{gp}.5", relu=True, drop=self.dp())
+        return self.ln(self.lin(g, f"{gp}.8"), f"{gp}.9", relu=True, drop=self.dp())
+
+    def decode_tail(self, x: Var, goal_in: Var, lat_in: Var, goal_valid: Tensor, vflat: Tensor, a_type: Tensor, hoisted: bool) -> Var:
+        """the part of a decode step behind the GRU: add_goal, add_latent (models/modules/add_latent_goal.py:57-77, mode cat,
+        res_add) and the action head (models/modules/action_head.py:70-87, branch_type) -> mean of the action distribution.
+        goal_in / lat_in: relu(mlp_in(.)) when hoisted (no dropout: loop invariants of the rollout), else the raw goal feature /
+        latent sample (the reference draws fresh dropout masks in mlp_in at every step).  Its backward depends on the other steps
+        only through the dynamics chain, which consumes `mean`."""
+        f = self.f
+        zg = goal_in if hoisted else self.mlp_in_goal(goal_in)
+        zl = lat_in if hoisted else self.mlp_in_latent(lat_in)
+        for name, zr, zv in (("model.add_goal", zg, goal_valid), ("model.add_latent", zl, vflat)):
+            zz = f.add_mask(zr, None, zv)
+            h = self.lin(self.lin(f.cat2(x, zz), f"{name}.mlp_out.fc_layers.0", relu=True, drop=self.dp()),
+                         f"{name}.mlp_out.fc_layers.3", relu=True, drop=self.dp())
+            x = f.add_mask(h, x, vflat, keep_a=zv)  # (h * z_valid + x) * x_valid
+        mean = None
+        for c in range(3):
+            ap = f"action_head.mlp_mean.{c}.fc_layers"
+            mc = f.add_mask(self.lin(self.lin(x, f"{ap}.0", relu=True), f"{ap}.2"), None, (a_type[:, c] & vflat).contiguous())
+            mean = mc if mean is None else f.add_mask(mean, mc, None)
+        return mean
+
     # ------------------------------------------------------------------ encoders
     def map_encoder(self, batch: Dict[str, Tensor]) -> Tuple[Var, Tensor]:
         """data_modules/sc_input.py:124-134 + `MapEncoder.forward` (models/modules/map_encoder.py:72-115)."""
@@ -339,24 +373,11 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
     bidx = torch.arange(S, device=dev).unsqueeze(1)
     goal_feature = f.gather_rows(map_feature, (bidx * P + goal_gt).reshape(-1))  # goal_manager.py:131-138
 
-    def mlp_in_latent() -> Var:
-        """relu(add_latent.mlp_in(z)) = Linear-Dropout-ReLU-Linear-Dropout, then mask / ReLU in MLP.forward (mlp.py:36-85): the
-        row mask and the dropout factor commute with ReLU."""
-        lp = "model.add_latent.mlp_in.fc_layers"
-        return m.lin(m.lin(z, f"{lp}.0", relu=True, drop=m.dp()), f"{lp}.3", relu=True, drop=m.dp())
-
-    def mlp_in_goal() -> Var:
-        """relu(add_goal.mlp_in(goal_feature)): 3 x [Linear, LayerNorm, Dropout] with ReLU between / after."""
-        gp = "model.add_goal.mlp_in.fc_layers"
-        g = m.ln(m.lin(goal_feature, f"{gp}.0"), f"{gp}.1", relu=True, drop=m.dp())
-        g = m.ln(m.lin(g, f"{gp}.4"), f"{gp}.5", relu=True, drop=m.dp())
-        return m.ln(m.lin(g, f"{gp}.8"), f"{gp}.9", relu=True, drop=m.dp())
-
-    # without dropout both are loop invariants of the rollout and are evaluated once; with dropout the reference draws fresh
-    # masks at every decode step, so they are evaluated per step
+    # without dropout relu(mlp_in(.)) of the goal feature / latent sample are loop invariants of the rollout and are evaluated
+    # once; with dropout the reference draws fresh masks at every decode step, so they are evaluated per step (Model.decode_tail)
     hoist = m.dp() is None
-    z_lat = mlp_in_latent() if hoist else None
-    z_goal = mlp_in_goal() if hoist else None
+    goal_src = m.mlp_in_goal(goal_feature) if hoist else goal_feature
+    lat_src = m.mlp_in_latent(z) if hoist else z
 
     tf_mask = teacher_forcing_mask(gv, 10, 10)  # teacher_forcing_training (traffic_bots.yaml:131-137)
     gt_state = torch.cat([batch["agent/pos"], batch["agent/yaw_bbox"], batch["agent/spd"]], -1)  # [S,T,A,4]
@@ -392,6 +413,7 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
     if stack_backward is None:
         stack_backward = getattr(ops, "name", "") == "cuda" and P > 32
     pre_site = first_drop_site + 500000  # dropout sites of the front: the same ids at every step, element indices continue
+    tail_site = first_drop_site + 700000  # ... and of the tail
     if stack_backward:
         stack = StepStack(ops, n_step)
         fn_s = Fn(ops, record=False)
@@ -401,9 +423,16 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
                      + torch.arange(TL, device=dev)[None, None, :]).reshape(-1)
         kv_tl_steps = [f.gather_rows(kv, idx_steps) for kv in kv_tl_hist]  # [n_step * S * TL, 2D] (recorded: scatter-add backward)
         tlv_steps = tlv_tm[fr].to(U8).contiguous()  # [n_step, S, TL]
+        # the same for the tail of a step (Model.decode_tail): its inputs repeated per step (recorded: scatter-add backward)
+        stack_t = StepStack(ops, n_step)
+        fn_t = Fn(ops, record=False)
+        m_t = Model(fn_t, params, drop_seed, drop_p)
+        idx_rep = torch.arange(M, device=dev).repeat(n_step)
+        goal_rep, lat_rep = f.gather_rows(goal_src, idx_rep), f.gather_rows(lat_src, idx_rep)
         rollout_start = len(f.nodes)
-        attr_l, pe_l, vflat_l, valid_l = [], [], [], []
-        x_front = None
+        attr_l, pe_l, vflat_l, valid_l, gvalid_l, x_gru_l = [], [], [], [], [], []
+        x_front = mean_all = None
+        main_nodes, gru_nodes, dyn_nodes = f.nodes, [], []
 
     for t in range(1, n_step + 1):
         ovr = tf_mask[:, t].to(U8) if t < T_gt else zeros_u8
@@ -433,20 +462,26 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
             post_site, m.n_site, f.stack_t = m.n_site, pre_site, t - 1
             x = m.decode_front(attr, pe, vflat, valid, kv_map, pl_valid, kv_t, tlv_tm[tl_t].to(U8).contiguous(), S, A, P, TL)
             m.n_site, f.stack_t = post_site, None
+        if stack_backward:
+            f.nodes = gru_nodes  # back-propagation through time: the GRU nodes of all steps, kept apart from ...
         x, hidden = m.gru_layers("model.agent_temporal", x, hidden, vflat)
-        for name, zr, zv in (("model.add_goal", z_goal if hoist else mlp_in_goal(), goal_valid.reshape(-1)),
-                             ("model.add_latent", z_lat if hoist else mlp_in_latent(), vflat)):
-            # AddLatentGoal.forward, mode cat, res_add (models/modules/add_latent_goal.py:57-77)
-            zz = f.add_mask(zr, None, zv)
-            h = m.lin(m.lin(f.cat2(x, zz), f"{name}.mlp_out.fc_layers.0", relu=True, drop=m.dp()), f"{name}.mlp_out.fc_layers.3",
-                      relu=True, drop=m.dp())
-            x = f.add_mask(h, x, vflat, keep_a=zv)  # (h * z_valid + x) * x_valid
-        # ActionHead.forward, branch_type (models/modules/action_head.py:70-87)
-        mean = None
-        for c in range(3):
-            ap = f"action_head.mlp_mean.{c}.fc_layers"
-            mc = f.add_mask(m.lin(m.lin(x, f"{ap}.0", relu=True), f"{ap}.2"), None, (a_type[:, c] & vflat).contiguous())
-            mean = mc if mean is None else f.add_mask(mean, mc, None)
+        gflat = goal_valid.reshape(-1)
+        if stack_backward:
+            i = t - 1
+            x_gru_l.append(x), gvalid_l.append(gflat)
+            post_site, m_t.n_site, fn_t.stack_t = m.n_site, tail_site, i
+            stack_t.begin(i)
+            mean = m_t.decode_tail(Var(x.data), Var(goal_src.data), Var(lat_src.data), gflat, vflat, a_type, hoist)
+            stack_t.end()
+            if mean_all is None:
+                mean_all = Var(stack_t.bufs[-1].flatten(0, 1), True)  # the action means of all steps
+            assert mean.data.data_ptr() == mean_all.data[i * M:(i + 1) * M].data_ptr()
+            mean = f.row_slice(mean_all, i * M, (i + 1) * M)
+            f.nodes = dyn_nodes  # ... the dynamics / reward nodes of all steps
+        else:
+            post_site, m.n_site, f.stack_t = m.n_site, tail_site, t - 1
+            mean = m.decode_tail(x, goal_src, lat_src, gflat, vflat, a_type, hoist)
+            m.n_site, f.stack_t = post_site, None
         # Dynamics.update / override_states (utils/dynamics.py:74-149)
         pred = f.dynamics(state, mean, a_type, vflat)
         pred_valid = valid
@@ -476,18 +511,33 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
         if return_buffers:
             preds_l.append(pred.data)
 
-    if stack_backward:  # record the front ONCE over the stacked buffers; its nodes run after the per-step nodes in the backward
+    if stack_backward:
+        # record front and tail ONCE over the stacked buffers.  Order of the backward (= reverse of the node list): dynamics /
+        # reward chain of all steps (fills the gradient of every step's action mean), tail (one pass), GRU chain of all steps
+        # (back-propagation through time; fills the gradient of every step's front output), front (one pass), everything else.
         rops = ReplayOps(ops, stack)
         fn_r = Fn(rops)
         m_r = Model(fn_r, params, drop_seed, drop_p)
         m_r.n_site = pre_site
-        out_r = m_r.decode_front(torch.cat(attr_l), torch.cat(pe_l), torch.cat(vflat_l), torch.cat(valid_l), kv_map, pl_valid,
+        vflat_all = torch.cat(vflat_l)
+        out_r = m_r.decode_front(torch.cat(attr_l), torch.cat(pe_l), vflat_all, torch.cat(valid_l), kv_map, pl_valid,
                                  kv_tl_steps, tlv_steps.reshape(n_step * S, TL), n_step * S, A, P, TL, kv_shared=True)
         assert rops.done() and out_r.data.data_ptr() == x_front.data.data_ptr()
         fn_r.ops = ops
         out_r.grad, out_r.grad_fixed = x_front.grad, True  # filled by the GRU backward of every step (row slices)
-        f.nodes[rollout_start:rollout_start] = fn_r.nodes
-        f.n_fwd += fn_s.n_fwd
+        f.nodes = cat_nodes = []
+        x_gru_all = f.cat_rows(x_gru_l)
+        rops_t = ReplayOps(ops, stack_t)
+        fn_rt = Fn(rops_t)
+        m_rt = Model(fn_rt, params, drop_seed, drop_p)
+        m_rt.n_site = tail_site
+        out_t = m_rt.decode_tail(x_gru_all, goal_rep, lat_rep, torch.cat(gvalid_l), vflat_all, a_type.repeat(n_step, 1), hoist)
+        assert rops_t.done() and out_t.data.data_ptr() == mean_all.data.data_ptr()
+        fn_rt.ops = ops
+        out_t.grad, out_t.grad_fixed = mean_all.grad, True  # filled by the dynamics backward of every step
+        assert len(main_nodes) == rollout_start
+        f.nodes = main_nodes + fn_r.nodes + gru_nodes + cat_nodes + fn_rt.nodes + dyn_nodes
+        f.n_fwd += fn_s.n_fwd + fn_t.n_fwd
 
     # ---- TrainingMetrics.update / compute (models/metrics/training.py:62-158) ----
     t0 = loss_cfg["step_training_start"]
