@@ -480,17 +480,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_map_polyline_tc2(TbDims dm, TbSc
     }
     // ---- masked max-pool over the valid nodes of each polyline (map_encoder.py:95-97,105-106) ------------------------------
     {
-      float* stage = sm.kv;  // [col][row], 128 x 128 floats
+      float* stage = sm.kv;  // [row][col] with the K|V staging stride: 16-byte row writes and column-contiguous reads are both
+                             // conflict-free (a [col][row] layout made every read of the pooling loop a 32-way bank conflict)
       __syncthreads();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) stage[(c0 + i) * ROWS + r] = x[i];
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(stage + r * KVS + c0)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
       __syncthreads();
       const int n_seg = sm.n_seg;
       for (int idx = tid; idx < n_seg * 128; idx += THREADS) {
         const int pp = idx >> 7, c = idx & 127;
         const int st = sm.seg_start[pp], cnt = sm.seg_cnt[pp];
         float mx = -INFINITY;
-        for (int j = 0; j < cnt; ++j) mx = fmaxf(mx, stage[c * ROWS + st + j]);
+        for (int j = 0; j < cnt; ++j) mx = fmaxf(mx, stage[(st + j) * KVS + c]);
         pl_feature[(long)sm.seg_pl[pp] * 128 + c] = mx;
       }
       if (tid < n_seg) pl_valid_out[sm.seg_pl[tid]] = 1;
