@@ -10,7 +10,7 @@ fixtures from oracle/make_golden_train.py).  Only tests/ may import it.
 from __future__ import annotations
 
 import math
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 import torch.nn.functional as F

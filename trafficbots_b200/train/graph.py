@@ -15,7 +15,6 @@ frame-major [T, S, A] where a recurrent loop walks over frames.
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -24,7 +23,6 @@ from torch import Tensor
 from .tape import Fn, ReplayOps, StepStack, Var
 
 D = 128
-N_NODE = 20
 U8 = torch.uint8
 
 
@@ -344,8 +342,7 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
     goal_valid0 = hv.any(1)  # get_gt_goal (goal_manager.py:64-66) == DestCategorical.valid
 
     # ---- latent encoders (:382-383) ----
-    fr_prior = list(range(0, n_hist, down))
-    Tp = len(fr_prior)
+    Tp = len(range(0, n_hist, down))  # frames 0, 5, 10
     fr_p = torch.arange(0, n_hist, down, device=dev)
     idx_p = (torch.arange(S, device=dev)[:, None, None] * n_hist + fr_p[None, :, None]) * A \
         + torch.arange(A, device=dev)[None, None, :]
@@ -355,8 +352,7 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
     kv_tl_prior = [f.gather_rows(kv, idx_tl.reshape(-1)) for kv in kv_tl_hist]
     prior_mean, prior_valid = m.latent_encoder("prior", af_prior, hv[:, ::down], kv_map, pl_valid, kv_tl_prior,
                                                batch["tl_stop/valid"][:, 0:n_hist:down], S, Tp, A, P, TL)
-    fr_post = list(range(0, T_gt, down))
-    Tq = len(fr_post)
+    Tq = len(range(0, T_gt, down))  # frames 0, 5, ..., 90
     sel = lambda k: batch[k][:, ::down]  # noqa: E731  (frames 0, 5, ..., 90)
     af_post = m.encode_agents(sel("agent/valid"), sel("agent/pos"), sel("agent/yaw_bbox"), sel("agent/vel"), sel("agent/spd"),
                               sel("agent/yaw_rate"), sel("agent/acc"), batch["agent/size"].unsqueeze(1).expand(-1, Tq, -1, -1),
