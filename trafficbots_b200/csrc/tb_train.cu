@@ -23,6 +23,7 @@ constexpr int TR_DH = 32;
 // =====================================================================================================================
 constexpr int GM = 64, GN = 64, GK = 16;
 constexpr long SMALL_M = 8192;  // launches with at most this many rows use 32-row tiles
+constexpr long TC_MIN_M = 8192; // launches with at least this many rows and 128-wide operands run on the tensor cores (tb_train_tc.cu)
 enum { EPI_BIAS = 0, EPI_STORE = 1, EPI_ATOMIC = 2 };
 
 // Per-tile options.  A operand: `ym` = ReLU mask source (same indexing as A: element kept where ym > 0), `rm1` / `rm2` = row masks
@@ -1296,6 +1297,9 @@ int32_t tb_tr_linear_fwd(const float* x, int64_t M, int32_t K, const float* w, i
   TR_CHECK(x && w && y, TB_ERR_NULL);
   TR_CHECK(M > 0 && K > 0 && N > 0 && ldw >= K, TB_ERR_BAD_SHAPE);
   GemmOpt op{nullptr, nullptr, nullptr, bias, relu, keep_lin, res, keep_out, nullptr, make_drop(drop_seed, drop_site, drop_p, drop_offset)};
+  if (M >= TC_MIN_M && K == 128 && N % 128 == 0 && (ldw & 3) == 0 && aligned16(x) && aligned16(w) && aligned16(y) && train_tc_enabled())
+    return launch_train_linear_tc_fwd(x, M, w, ldw, N, bias, relu, keep_lin, res, keep_out, y, op.drop.seed, op.drop.site,
+                                      op.drop.thresh, op.drop.scale, op.drop.offset, st);
   if (M <= SMALL_M) {
     dim3 grid((unsigned)((M + 31) / 32), (N + GN - 1) / GN, 1);
     k_tr_gemm<32, true, false, EPI_BIAS><<<grid, 256, 0, st>>>(x, K, 1, w, 1, ldw, y, N, M, N, K, K, op);
@@ -1317,6 +1321,16 @@ int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_
   TR_CHECK(M > 0 && K > 0 && N > 0 && (!relu || y), TB_ERR_BAD_SHAPE);
   TR_CHECK(dw || !db, TB_ERR_BAD_SHAPE);  // the bias gradient rides on the weight-gradient tiles
   if (!dx && !dw) return TB_OK;
+  if (M >= TC_MIN_M && K == 128 && N == 128 && (ldw & 3) == 0 && aligned16(dy) && aligned16(x) && aligned16(w) && (!dx || aligned16(dx)) &&
+      (!relu || aligned16(y)) && train_tc_enabled()) {
+    const Drop d = make_drop(drop_seed, drop_site, drop_p, drop_offset);
+    int rc = TB_OK;
+    if (dx)
+      rc = launch_train_linear_tc_dx(dy, M, w, ldw, relu ? y : nullptr, rm1, rm2, dx, d.seed, d.site, d.thresh, d.scale, d.offset, st);
+    if (rc == TB_OK && dw)
+      rc = launch_train_linear_tc_dw(dy, x, M, relu ? y : nullptr, rm1, rm2, dw, lddw, db, d.seed, d.site, d.thresh, d.scale, d.offset, st);
+    return rc;
+  }
   const int TMh = M <= SMALL_M ? 32 : GM;
   const int dx_tiles_j = (K + GN - 1) / GN;
   const long n_dx = dx ? ((M + TMh - 1) / TMh) * dx_tiles_j : 0;
