@@ -99,15 +99,19 @@ def test_linear_tensor_core_path(ops):
             y_ref = ORC.linear_fwd(x, w, b, relu, keep_lin, r, keep_out)
             y = ops.linear_fwd(*g(x, w, b), relu, *g(keep_lin, r, keep_out))
             close(y, y_ref, tol=1e-4, what=f"y N={N}")
-    w, b = torch.randn(128, K) / K ** 0.5, torch.randn(128) * 0.1
-    for relu, keep_lin, keep_out in ((True, None, None), (False, kl, ko)):
+    # backward: N = 128 (most Linears), N = 256 (K|V projection), N = 384 (GRU), K = 256 (mlp_out of add_goal / add_latent)
+    for Kb, Nb, relu, keep_lin, keep_out in ((128, 128, True, None, None), (128, 128, False, kl, ko), (128, 256, False, None, None),
+                                             (128, 384, False, None, ko), (256, 128, True, None, None)):
+        x = torch.randn(M, Kb)
+        dy = torch.randn(M, Nb)
+        w, b = torch.randn(Nb, Kb) / Kb ** 0.5, torch.randn(Nb) * 0.1
         y_ref = ORC.linear_fwd(x, w, b, relu, keep_lin, None, keep_out)
-        dw_ref, db_ref = torch.zeros_like(w) + 0.5, torch.zeros(128) - 0.25
+        dw_ref, db_ref = torch.zeros_like(w) + 0.5, torch.zeros(Nb) - 0.25
         dx_ref = ORC.linear_bwd(dy, x, w, b, y_ref, relu, dw_ref, db_ref, True, keep_lin, keep_out)
         xg, wg, bg, dyg, klg, kog = g(x, w, b, dy, keep_lin, keep_out)
         y = ops.linear_fwd(xg, wg, bg, relu, klg, None, kog)
-        close(y, y_ref, tol=1e-4, what="y")
-        dwg, dbg = torch.zeros_like(wg) + 0.5, torch.zeros(128, device=DEV) - 0.25
+        close(y, y_ref, tol=1e-4, what=f"y K={Kb} N={Nb}")
+        dwg, dbg = torch.zeros_like(wg) + 0.5, torch.zeros(Nb, device=DEV) - 0.25
         # the ReLU mask of the reference forward (outputs within rounding of 0 may have the other sign in the bf16x3 forward)
         dx = ops.linear_bwd(dyg, xg, wg, bg, y_ref.to(DEV), relu, dwg, dbg, True, klg, kog)
         close(dx, dx_ref, tol=1e-4, what="dx")

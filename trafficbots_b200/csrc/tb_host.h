@@ -113,15 +113,15 @@ inline bool tc_enabled() {
 
 // tensor-core Linear kernels of the training path (tb_train_tc.cu): launches with many rows and 128-wide operands
 bool train_tc_enabled();  // TB_TRAIN_NO_TC=1 switches them off (A/B runs)
-int launch_train_linear_tc_fwd(const float* x, long M, const float* w, long ldw, int N, const float* bias, int relu,
+int launch_train_linear_tc_fwd(const float* x, long M, int K, const float* w, long ldw, int N, const float* bias, int relu,
                                const uint8_t* keep_lin, const float* res, const uint8_t* keep_out, float* y, const uint32_t* drop_seed,
                                uint32_t drop_site, uint32_t drop_thresh, float drop_scale, long drop_offset, cudaStream_t st);
-int launch_train_linear_tc_dx(const float* dy, long M, const float* w, long ldw, const float* ym, const uint8_t* rm1, const uint8_t* rm2,
-                              float* dx, const uint32_t* drop_seed, uint32_t drop_site, uint32_t drop_thresh, float drop_scale,
-                              long drop_offset, cudaStream_t st);
-int launch_train_linear_tc_dw(const float* dy, const float* x, long M, const float* ym, const uint8_t* rm1, const uint8_t* rm2,
-                              float* dw, long lddw, float* db, const uint32_t* drop_seed, uint32_t drop_site, uint32_t drop_thresh,
+int launch_train_linear_tc_dx(const float* dy, long M, int K, int N, const float* w, long ldw, const float* ym, const uint8_t* rm1,
+                              const uint8_t* rm2, float* dx, const uint32_t* drop_seed, uint32_t drop_site, uint32_t drop_thresh,
                               float drop_scale, long drop_offset, cudaStream_t st);
+int launch_train_linear_tc_dw(const float* dy, const float* x, long M, int K, int N, const float* ym, const uint8_t* rm1,
+                              const uint8_t* rm2, float* dw, long lddw, float* db, const uint32_t* drop_seed, uint32_t drop_site,
+                              uint32_t drop_thresh, float drop_scale, long drop_offset, cudaStream_t st);
 
 // the packed parameter buffer = [fp32 blob | pad to 1 KB | tensor-core blocks]
 inline size_t tc_blob_offset_bytes() { return ((size_t)TB_PACKED_FLOATS * sizeof(float) + 1023) & ~(size_t)1023; }

@@ -1297,8 +1297,9 @@ int32_t tb_tr_linear_fwd(const float* x, int64_t M, int32_t K, const float* w, i
   TR_CHECK(x && w && y, TB_ERR_NULL);
   TR_CHECK(M > 0 && K > 0 && N > 0 && ldw >= K, TB_ERR_BAD_SHAPE);
   GemmOpt op{nullptr, nullptr, nullptr, bias, relu, keep_lin, res, keep_out, nullptr, make_drop(drop_seed, drop_site, drop_p, drop_offset)};
-  if (M >= TC_MIN_M && K == 128 && N % 128 == 0 && (ldw & 3) == 0 && aligned16(x) && aligned16(w) && aligned16(y) && train_tc_enabled())
-    return launch_train_linear_tc_fwd(x, M, w, ldw, N, bias, relu, keep_lin, res, keep_out, y, op.drop.seed, op.drop.site,
+  if (M >= TC_MIN_M && K % 128 == 0 && K <= 256 && N % 128 == 0 && (ldw & 3) == 0 && aligned16(x) && aligned16(w) && aligned16(y) &&
+      (!res || aligned16(res)) && train_tc_enabled())
+    return launch_train_linear_tc_fwd(x, M, K, w, ldw, N, bias, relu, keep_lin, res, keep_out, y, op.drop.seed, op.drop.site,
                                       op.drop.thresh, op.drop.scale, op.drop.offset, st);
   if (M <= SMALL_M) {
     dim3 grid((unsigned)((M + 31) / 32), (N + GN - 1) / GN, 1);
@@ -1321,14 +1322,16 @@ int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_
   TR_CHECK(M > 0 && K > 0 && N > 0 && (!relu || y), TB_ERR_BAD_SHAPE);
   TR_CHECK(dw || !db, TB_ERR_BAD_SHAPE);  // the bias gradient rides on the weight-gradient tiles
   if (!dx && !dw) return TB_OK;
-  if (M >= TC_MIN_M && K == 128 && N == 128 && (ldw & 3) == 0 && aligned16(dy) && aligned16(x) && aligned16(w) && (!dx || aligned16(dx)) &&
-      (!relu || aligned16(y)) && train_tc_enabled()) {
+  if (M >= TC_MIN_M && K % 128 == 0 && K <= 256 && N % 128 == 0 && N <= 384 && (ldw & 3) == 0 && aligned16(dy) && aligned16(x) &&
+      aligned16(w) && (!dx || aligned16(dx)) && (!relu || aligned16(y)) && train_tc_enabled()) {
     const Drop d = make_drop(drop_seed, drop_site, drop_p, drop_offset);
     int rc = TB_OK;
     if (dx)
-      rc = launch_train_linear_tc_dx(dy, M, w, ldw, relu ? y : nullptr, rm1, rm2, dx, d.seed, d.site, d.thresh, d.scale, d.offset, st);
+      rc = launch_train_linear_tc_dx(dy, M, K, N, w, ldw, relu ? y : nullptr, rm1, rm2, dx, d.seed, d.site, d.thresh, d.scale, d.offset,
+                                     st);
     if (rc == TB_OK && dw)
-      rc = launch_train_linear_tc_dw(dy, x, M, relu ? y : nullptr, rm1, rm2, dw, lddw, db, d.seed, d.site, d.thresh, d.scale, d.offset, st);
+      rc = launch_train_linear_tc_dw(dy, x, M, K, N, relu ? y : nullptr, rm1, rm2, dw, lddw, db, d.seed, d.site, d.thresh, d.scale,
+                                     d.offset, st);
     return rc;
   }
   const int TMh = M <= SMALL_M ? 32 : GM;

@@ -40,6 +40,12 @@ struct TcArgs {
   const uint8_t* rm1;      // backward: row masks
   const uint8_t* rm2;
   TcDrop drop;
+  // geometry of one pass (operands wider than 128 are handled as several passes over 128-wide blocks)
+  long a_ld, a_off;          // A operand: row stride and column offset (floats); the ReLU mask source and the dropout index share them
+  long w_row, w_col;         // offset into W [N, K]
+  long o_ld, o_off;          // output (and residual): row stride and column offset
+  int acc_in;                // add the partial result already stored in the output (contraction split over passes)
+  int final_pass;            // forward: apply the epilogue (last contraction pass)
 };
 
 struct LinSmem {
@@ -83,7 +89,7 @@ __device__ __forceinline__ void load_split_tile(unsigned char* hi, unsigned char
   for (int i = 0; i < 8; ++i) {
     const long m = m0 + r0 + 16 * i;
     if (m < M) {
-      const float4* q = reinterpret_cast<const float4*>(src + m * 128 + c16 * 8);
+      const float4* q = reinterpret_cast<const float4*>(src + m * p.a_ld + p.a_off + c16 * 8);
       v[i][0] = q[0];
       v[i][1] = q[1];
     } else {
@@ -100,7 +106,7 @@ __device__ __forceinline__ void load_split_tile(unsigned char* hi, unsigned char
       if (p.rm1 && !p.rm1[m]) on = false;
       if (p.rm2 && !p.rm2[m]) on = false;
       if (p.ym) {
-        const float4* q = reinterpret_cast<const float4*>(p.ym + m * 128 + c16 * 8);
+        const float4* q = reinterpret_cast<const float4*>(p.ym + m * p.a_ld + p.a_off + c16 * 8);
         const float4 y0 = q[0], y1 = q[1];
         const float yy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
 #pragma unroll
@@ -109,7 +115,7 @@ __device__ __forceinline__ void load_split_tile(unsigned char* hi, unsigned char
       }
       if (p.drop.seed) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] *= tc_drop_factor(p.drop, dkey, m * 128 + c16 * 8 + e);
+        for (int e = 0; e < 8; ++e) f[e] *= tc_drop_factor(p.drop, dkey, m * p.a_ld + p.a_off + c16 * 8 + e);
       }
       if (!on) {
 #pragma unroll
@@ -127,7 +133,7 @@ __device__ __forceinline__ void load_split_tile(unsigned char* hi, unsigned char
 // grid (row-tile CTAs, N / 128); 256 threads
 template <bool BWD>
 __global__ void __launch_bounds__(256) k_tr_lin_tc(const float* __restrict__ a, const float* __restrict__ w, long ldw,
-                                                   float* __restrict__ out, long M, int n_total, TcArgs p) {
+                                                   float* __restrict__ out, long M, TcArgs p) {
   extern __shared__ unsigned char smem_raw[];
   LinSmem& sm = lin_smem(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(256) k_tr_lin_tc(const float* __restrict__ a, 
       for (int k0 = 0; k0 < 128; k0 += 32) {
         float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = w[(long)(k0 + i) * ldw + tid];
+        for (int i = 0; i < 32; ++i) v[i] = w[(p.w_row + k0 + i) * ldw + p.w_col + tid];
         tc::store_row32_split(sm.b_hi, sm.b_lo, tid, k0, v);
       }
     }
@@ -152,7 +158,7 @@ __global__ void __launch_bounds__(256) k_tr_lin_tc(const float* __restrict__ a, 
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = r0 + 16 * i;
-      const float4* q = reinterpret_cast<const float4*>(w + (long)(j0 + r) * ldw + c16 * 8);
+      const float4* q = reinterpret_cast<const float4*>(w + (p.w_row + j0 + r) * ldw + p.w_col + c16 * 8);
       const float4 x0 = q[0], x1 = q[1];
       const float f[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
       uint4 h, l;
@@ -191,8 +197,16 @@ __global__ void __launch_bounds__(256) k_tr_lin_tc(const float* __restrict__ a, 
       tc::tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + ecol + c0, v);
       tc::tmem_ld_wait();
       if (!row_ok) continue;
-      if (!BWD) {
-        const long base = m * n_total + j0 + ecol + c0;
+      const long base = m * p.o_ld + p.o_off + j0 + ecol + c0;
+      float4* dst = reinterpret_cast<float4*>(out + base);
+      if (p.acc_in) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = dst[i];
+          v[4 * i] += t.x, v[4 * i + 1] += t.y, v[4 * i + 2] += t.z, v[4 * i + 3] += t.w;
+        }
+      }
+      if (!BWD && p.final_pass) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           float t = v[i];
@@ -204,7 +218,6 @@ __global__ void __launch_bounds__(256) k_tr_lin_tc(const float* __restrict__ a, 
           v[i] = t * ko;
         }
       }
-      float4* dst = reinterpret_cast<float4*>(out + m * n_total + j0 + ecol + c0);
 #pragma unroll
       for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     }
@@ -220,6 +233,7 @@ __global__ void __launch_bounds__(256) k_tr_lin_tc(const float* __restrict__ a, 
 // dW [128, 128] += dY'^T X over the CTA's row chunks; db += column sums of dY'.  A tile row = output feature n (warps 0-3: thread n
 // gathers column n of dY', coalesced across the warp), B tile row = input feature k (warps 4-7); the K dimension of the MMA is
 // the row index m within the chunk.
+// p.a_ld / p.a_off: row stride / column offset of dY (and its masks); p.o_ld / p.o_off: of X
 __global__ void __launch_bounds__(256) k_tr_lin_tc_dw(const float* __restrict__ dy, const float* __restrict__ x, long M,
                                                       float* __restrict__ dw, long lddw, float* __restrict__ db, long chunks_per_cta,
                                                       TcArgs p) {
@@ -240,7 +254,8 @@ __global__ void __launch_bounds__(256) k_tr_lin_tc_dw(const float* __restrict__ 
   const long c_lo = (long)blockIdx.x * chunks_per_cta, c_hi = min(n_chunks, c_lo + chunks_per_cta);
   const bool is_a = tid < 128;  // this thread fills a row of the A tile (dY' column) or of the B tile (X column)
   const int col = tid & 127;
-  const float* __restrict__ src = is_a ? dy : x;
+  const float* __restrict__ src = is_a ? dy + p.a_off : x + p.o_off;
+  const long ld = is_a ? p.a_ld : p.o_ld;
   unsigned char* t_hi = is_a ? sm.a_hi : sm.b_hi;
   unsigned char* t_lo = is_a ? sm.a_lo : sm.b_lo;
   const bool masked = p.rm1 || p.rm2 || p.ym || p.drop.seed;
@@ -253,10 +268,10 @@ __global__ void __launch_bounds__(256) k_tr_lin_tc_dw(const float* __restrict__ 
       float v[32];
       if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = src[(m0 + i0 + i) * 128 + col];
+        for (int i = 0; i < 32; ++i) v[i] = src[(m0 + i0 + i) * ld + col];
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = (m0 + i0 + i < M) ? src[(m0 + i0 + i) * 128 + col] : 0.f;
+        for (int i = 0; i < 32; ++i) v[i] = (m0 + i0 + i < M) ? src[(m0 + i0 + i) * ld + col] : 0.f;
       }
       if (is_a) {
         if (masked) {
@@ -266,8 +281,8 @@ __global__ void __launch_bounds__(256) k_tr_lin_tc_dw(const float* __restrict__ 
             if (m < M) {
               if (p.rm1 && !p.rm1[m]) v[i] = 0.f;
               if (p.rm2 && !p.rm2[m]) v[i] = 0.f;
-              if (p.ym && !(p.ym[m * 128 + col] > 0.f)) v[i] = 0.f;
-              if (p.drop.seed) v[i] *= tc_drop_factor(p.drop, dkey, m * 128 + col);
+              if (p.ym && !(p.ym[m * p.a_ld + p.a_off + col] > 0.f)) v[i] = 0.f;
+              if (p.drop.seed) v[i] *= tc_drop_factor(p.drop, dkey, m * p.a_ld + p.a_off + col);
             }
           }
         }
@@ -320,46 +335,61 @@ bool train_tc_enabled() {
   return !(e && e[0] == '1');
 }
 
-int launch_train_linear_tc_fwd(const float* x, long M, const float* w, long ldw, int N, const float* bias, int relu,
+int launch_train_linear_tc_fwd(const float* x, long M, int K, const float* w, long ldw, int N, const float* bias, int relu,
                                const uint8_t* keep_lin, const float* res, const uint8_t* keep_out, float* y, const uint32_t* drop_seed,
                                uint32_t drop_site, uint32_t drop_thresh, float drop_scale, long drop_offset, cudaStream_t st) {
   static std::atomic<uint64_t> flag{0};
   if (!ensure_smem(k_tr_lin_tc<false>, flag)) return TB_ERR_LAUNCH;
-  TcArgs p{bias, relu, keep_lin, res, keep_out, nullptr, nullptr, nullptr, {drop_seed, drop_site, drop_thresh, drop_scale, drop_offset}};
   const long n_tiles = (M + 127) / 128;
-  const int n_col = N / 128;
-  long gx = 148 * 1 / n_col;  // one CTA per SM (128 KB of operand tiles)
+  const int n_col = N / 128, n_kb = K / 128;
+  long gx = 148 / n_col;  // one CTA per SM (128 KB of operand tiles)
   if (gx < 1) gx = 1;
   if (gx > n_tiles) gx = n_tiles;
-  k_tr_lin_tc<false><<<dim3((unsigned)gx, n_col), 256, LIN_SMEM, st>>>(x, w, ldw, y, M, N, p);
-  count_launch();
+  for (int kb = 0; kb < n_kb; ++kb) {  // contraction blocks: partial sums pass through the output buffer
+    TcArgs p{bias, relu, keep_lin, res, keep_out, nullptr, nullptr, nullptr, {drop_seed, drop_site, drop_thresh, drop_scale, drop_offset},
+             K, kb * 128L, 0, kb * 128L, N, 0, kb > 0, kb == n_kb - 1};
+    k_tr_lin_tc<false><<<dim3((unsigned)gx, n_col), 256, LIN_SMEM, st>>>(x, w, ldw, y, M, p);
+    count_launch();
+  }
   return launch_status();
 }
 
-int launch_train_linear_tc_dx(const float* dy, long M, const float* w, long ldw, const float* ym, const uint8_t* rm1, const uint8_t* rm2,
-                              float* dx, const uint32_t* drop_seed, uint32_t drop_site, uint32_t drop_thresh, float drop_scale,
-                              long drop_offset, cudaStream_t st) {
-  static std::atomic<uint64_t> flag{0};
-  if (!ensure_smem(k_tr_lin_tc<true>, flag)) return TB_ERR_LAUNCH;
-  TcArgs p{nullptr, 0, nullptr, nullptr, nullptr, ym, rm1, rm2, {drop_seed, drop_site, drop_thresh, drop_scale, drop_offset}};
-  const long n_tiles = (M + 127) / 128;
-  const long gx = n_tiles < 148 ? n_tiles : 148;
-  k_tr_lin_tc<true><<<dim3((unsigned)gx, 1), 256, LIN_SMEM, st>>>(dy, w, ldw, dx, M, 128, p);
-  count_launch();
-  return launch_status();
-}
-
-int launch_train_linear_tc_dw(const float* dy, const float* x, long M, const float* ym, const uint8_t* rm1, const uint8_t* rm2,
-                              float* dw, long lddw, float* db, const uint32_t* drop_seed, uint32_t drop_site, uint32_t drop_thresh,
+int launch_train_linear_tc_dx(const float* dy, long M, int K, int N, const float* w, long ldw, const float* ym, const uint8_t* rm1,
+                              const uint8_t* rm2, float* dx, const uint32_t* drop_seed, uint32_t drop_site, uint32_t drop_thresh,
                               float drop_scale, long drop_offset, cudaStream_t st) {
   static std::atomic<uint64_t> flag{0};
+  if (!ensure_smem(k_tr_lin_tc<true>, flag)) return TB_ERR_LAUNCH;
+  const long n_tiles = (M + 127) / 128;
+  const long gx = n_tiles < 148 ? n_tiles : 148;
+  for (int kb = 0; kb < K / 128; ++kb)      // block of input features (output columns of dX)
+    for (int nb = 0; nb < N / 128; ++nb) {  // contraction block
+      TcArgs p{nullptr, 0, nullptr, nullptr, nullptr, ym, rm1, rm2, {drop_seed, drop_site, drop_thresh, drop_scale, drop_offset},
+               N, nb * 128L, nb * 128L, kb * 128L, K, kb * 128L, nb > 0, 0};
+      k_tr_lin_tc<true><<<dim3((unsigned)gx, 1), 256, LIN_SMEM, st>>>(dy, w, ldw, dx, M, p);
+      count_launch();
+    }
+  return launch_status();
+}
+
+int launch_train_linear_tc_dw(const float* dy, const float* x, long M, int K, int N, const float* ym, const uint8_t* rm1,
+                              const uint8_t* rm2, float* dw, long lddw, float* db, const uint32_t* drop_seed, uint32_t drop_site,
+                              uint32_t drop_thresh, float drop_scale, long drop_offset, cudaStream_t st) {
+  static std::atomic<uint64_t> flag{0};
   if (!ensure_smem(k_tr_lin_tc_dw, flag)) return TB_ERR_LAUNCH;
-  TcArgs p{nullptr, 0, nullptr, nullptr, nullptr, ym, rm1, rm2, {drop_seed, drop_site, drop_thresh, drop_scale, drop_offset}};
   const long n_chunks = (M + 127) / 128;
-  const long per = (n_chunks + 147) / 148;
+  const int n_blk = (N / 128) * (K / 128);
+  long n_cta = 148 / n_blk;  // the blocks of one Linear are independent launches that may overlap
+  if (n_cta < 1) n_cta = 1;
+  const long per = (n_chunks + n_cta - 1) / n_cta;
   const long gx = (n_chunks + per - 1) / per;
-  k_tr_lin_tc_dw<<<(unsigned)gx, 256, LIN_SMEM, st>>>(dy, x, M, dw, lddw, db, per, p);
-  count_launch();
+  for (int nb = 0; nb < N / 128; ++nb)
+    for (int kb = 0; kb < K / 128; ++kb) {
+      TcArgs p{nullptr, 0, nullptr, nullptr, nullptr, ym, rm1, rm2, {drop_seed, drop_site, drop_thresh, drop_scale, drop_offset},
+               N, nb * 128L, 0, 0, K, kb * 128L, 0, 0};
+      k_tr_lin_tc_dw<<<(unsigned)gx, 256, LIN_SMEM, st>>>(dy, x, M, dw + nb * 128L * lddw + kb * 128L, lddw,
+                                                          (db && kb == 0) ? db + nb * 128L : nullptr, per, p);
+      count_launch();
+    }
   return launch_status();
 }
 
