@@ -1272,6 +1272,14 @@ __global__ void k_tr_adam(float* __restrict__ p, const float* __restrict__ g, fl
   }
 }
 
+inline long tc_min_m() {  // TB_TRAIN_TC_MIN_M overrides the row threshold of the tensor-core Linears (A/B runs)
+  static const long v = [] {
+    const char* e = getenv("TB_TRAIN_TC_MIN_M");
+    return e ? atol(e) : TC_MIN_M;
+  }();
+  return v;
+}
+
 inline int grid_for(long total, int block = 256) {
   long g = (total + block - 1) / block;
   return (int)(g < 1 ? 1 : (g > 148L * 16 ? 148L * 16 : g));
@@ -1297,7 +1305,7 @@ int32_t tb_tr_linear_fwd(const float* x, int64_t M, int32_t K, const float* w, i
   TR_CHECK(x && w && y, TB_ERR_NULL);
   TR_CHECK(M > 0 && K > 0 && N > 0 && ldw >= K, TB_ERR_BAD_SHAPE);
   GemmOpt op{nullptr, nullptr, nullptr, bias, relu, keep_lin, res, keep_out, nullptr, make_drop(drop_seed, drop_site, drop_p, drop_offset)};
-  if (M >= TC_MIN_M && K % 128 == 0 && K <= 256 && N % 128 == 0 && (ldw & 3) == 0 && aligned16(x) && aligned16(w) && aligned16(y) &&
+  if (M >= tc_min_m() && K % 128 == 0 && K <= 256 && N % 128 == 0 && (ldw & 3) == 0 && aligned16(x) && aligned16(w) && aligned16(y) &&
       (!res || aligned16(res)) && train_tc_enabled())
     return launch_train_linear_tc_fwd(x, M, K, w, ldw, N, bias, relu, keep_lin, res, keep_out, y, op.drop.seed, op.drop.site,
                                       op.drop.thresh, op.drop.scale, op.drop.offset, st);
@@ -1322,7 +1330,7 @@ int32_t tb_tr_linear_bwd(const float* dy, const float* x, const float* w, int64_
   TR_CHECK(M > 0 && K > 0 && N > 0 && (!relu || y), TB_ERR_BAD_SHAPE);
   TR_CHECK(dw || !db, TB_ERR_BAD_SHAPE);  // the bias gradient rides on the weight-gradient tiles
   if (!dx && !dw) return TB_OK;
-  if (M >= TC_MIN_M && K % 128 == 0 && K <= 256 && N % 128 == 0 && N <= 384 && (ldw & 3) == 0 && aligned16(dy) && aligned16(x) &&
+  if (M >= tc_min_m() && K % 128 == 0 && K <= 256 && N % 128 == 0 && N <= 384 && (ldw & 3) == 0 && aligned16(dy) && aligned16(x) &&
       aligned16(w) && (!dx || aligned16(dx)) && (!relu || aligned16(y)) && train_tc_enabled()) {
     const Drop d = make_drop(drop_seed, drop_site, drop_p, drop_offset);
     int rc = TB_OK;
