@@ -274,16 +274,36 @@ __global__ void __launch_bounds__(256) k_tr_lin_tc_dw(const float* __restrict__ 
         for (int i = 0; i < 32; ++i) v[i] = (m0 + i0 + i < M) ? src[(m0 + i0 + i) * ld + col] : 0.f;
       }
       if (is_a) {
-        if (masked) {
+        if (masked) {  // every mask source is loaded as an unconditional batch (full chunks), then applied arithmetically
+          if (p.ym) {
+            float yv[32];
+            const float* ys = p.ym + p.a_off + col;
+            if (full) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const long m = m0 + i0 + i;
-            if (m < M) {
-              if (p.rm1 && !p.rm1[m]) v[i] = 0.f;
-              if (p.rm2 && !p.rm2[m]) v[i] = 0.f;
-              if (p.ym && !(p.ym[m * p.a_ld + p.a_off + col] > 0.f)) v[i] = 0.f;
-              if (p.drop.seed) v[i] *= tc_drop_factor(p.drop, dkey, m * p.a_ld + p.a_off + col);
+              for (int i = 0; i < 32; ++i) yv[i] = ys[(m0 + i0 + i) * p.a_ld];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) yv[i] = (m0 + i0 + i < M) ? ys[(m0 + i0 + i) * p.a_ld] : 0.f;
             }
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (!(yv[i] > 0.f)) v[i] = 0.f;
+          }
+          if (p.rm1 || p.rm2) {
+            uint8_t k1[32], k2[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const long m = full ? m0 + i0 + i : min(m0 + i0 + i, M - 1);
+              k1[i] = p.rm1 ? p.rm1[m] : 1;
+              k2[i] = p.rm2 ? p.rm2[m] : 1;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (!k1[i] || !k2[i]) v[i] = 0.f;
+          }
+          if (p.drop.seed) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= tc_drop_factor(p.drop, dkey, (m0 + i0 + i) * p.a_ld + p.a_off + col);
           }
         }
 #pragma unroll
