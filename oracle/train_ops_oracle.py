@@ -67,9 +67,27 @@ class OracleOps:
 
     name = "oracle"
 
+    def __init__(self) -> None:
+        # tape.StepStack (the step-stacked backward): like CudaOps, the forward primitives a decode step runs put their outputs into
+        # buffers obtained from `empty`, in the SAME order as the CUDA wrappers allocate them (see `_out`)
+        self.alloc_hook = None
+
+    def _out(self, *tensors):
+        """outputs of a forward primitive: copied into hook-provided buffers while a StepStack is recording."""
+        if self.alloc_hook is None:
+            return tensors if len(tensors) > 1 else tensors[0]
+        outs = []
+        for t in tensors:
+            buf = self.alloc_hook(tuple(t.shape), t.dtype)
+            buf.copy_(t)
+            outs.append(buf)
+        return tuple(outs) if len(outs) > 1 else outs[0]
+
     # ---- memory helpers (plumbing) ----
-    def empty(self, shape, like: Tensor, dtype=torch.float32) -> Tensor:
-        return torch.empty(shape, dtype=dtype, device=like.device)
+    def empty(self, shape, like: Tensor = None, dtype=torch.float32) -> Tensor:
+        if self.alloc_hook is not None:
+            return self.alloc_hook(tuple(shape), dtype)
+        return torch.empty(shape, dtype=dtype, device=None if like is None else like.device)
 
     def zeros(self, shape, like: Tensor, dtype=torch.float32) -> Tensor:
         return torch.zeros(shape, dtype=dtype, device=like.device)
@@ -79,6 +97,14 @@ class OracleOps:
 
     def scale_(self, x: Tensor, alpha: float) -> None:
         x *= alpha
+
+    def _pure(self, fwd, *a, **k):
+        """a forward primitive evaluated for autograd inside a backward: never through the StepStack hook."""
+        hook, self.alloc_hook = self.alloc_hook, None
+        try:
+            return fwd(*a, **k)
+        finally:
+            self.alloc_hook = hook
 
     # ---- Linear (+ReLU) : models/modules/mlp.py, attention.py in/out projections ----
     def linear_fwd(self, x: Tensor, w: Tensor, b: Optional[Tensor], relu: bool, keep_lin=None, res=None, keep_out=None, drop=None) -> Tensor:
@@ -94,12 +120,12 @@ class OracleOps:
             y = y + res
         if keep_out is not None:
             y = y * keep_out.to(y.dtype).unsqueeze(-1)
-        return y
+        return self._out(y)
 
     def linear_bwd(self, dy, x, w, b, y, relu, dw, db, need_dx: bool, keep_lin=None, keep_out=None, drop=None):
         """gradients of the Linear part (the residual's gradient is dy * keep_out, formed by the caller)."""
         x_, w_, b_ = _req(x, w, b)
-        gx, gw, gb = _grads(self.linear_fwd(x_, w_, b_, relu, keep_lin, None, keep_out, drop), [x_, w_, b_], dy)
+        gx, gw, gb = _grads(self._pure(self.linear_fwd, x_, w_, b_, relu, keep_lin, None, keep_out, drop), [x_, w_, b_], dy)
         if dw is not None:
             dw += gw
         if b is not None and db is not None:
@@ -114,11 +140,11 @@ class OracleOps:
         y = torch.relu(y) if relu else y
         if drop is not None:
             y = y * drop_factor(drop, y.shape, y.device)
-        return y, torch.stack([mean, rstd], -1)
+        return self._out(y, torch.stack([mean, rstd], -1))
 
     def layernorm_bwd(self, dy, x, w, b, stats, y, relu, dw, db, drop=None):
         x_, w_, b_ = _req(x, w, b)
-        gx, gw, gb = _grads(self.layernorm_fwd(x_, w_, b_, relu, drop)[0], [x_, w_, b_], dy)
+        gx, gw, gb = _grads(self._pure(self.layernorm_fwd, x_, w_, b_, relu, drop)[0], [x_, w_, b_], dy)
         dw += gw
         db += gb
         return gx
@@ -142,44 +168,45 @@ class OracleOps:
         p = torch.softmax(logits / math.sqrt(dh), dim=-1).masked_fill(dead[:, None, :, None], 0.0)
         pd = p if drop is None else p * drop_factor(drop, p.shape, p.device)  # attention.py:131-132
         o = torch.matmul(pd, vh).transpose(1, 2).flatten(2, 3)
-        return o, p, (~dead).to(torch.uint8)
+        return self._out(o, p, (~dead).to(torch.uint8))
 
     def attention_bwd(self, do, q, kv, key_valid, eye, p, drop=None, kv_shared: bool = False):
         q_, kv_ = _req(q, kv)
         if kv_shared:  # batch element b of q uses the keys of b % kv.shape[0]
             rep = q.shape[0] // kv.shape[0]
-            o = self.attention_fwd(q_, kv_.repeat(rep, 1, 1), key_valid.repeat(rep, 1), eye, drop)[0]
+            o = self._pure(self.attention_fwd, q_, kv_.repeat(rep, 1, 1), key_valid.repeat(rep, 1), eye, drop)[0]
         else:
-            o = self.attention_fwd(q_, kv_, key_valid, eye, drop)[0]
+            o = self._pure(self.attention_fwd, q_, kv_, key_valid, eye, drop)[0]
         gq, gkv = _grads(o, [q_, kv_], do)
         return gq, gkv
 
     def dropout(self, x, drop):
         """x * dropout factor (nn.GRU inter-layer dropout); applied to dy it is its own backward."""
-        return x * drop_factor(drop, x.shape, x.device)
+        return self._out(x * drop_factor(drop, x.shape, x.device))
 
-    dropout_bwd = dropout
+    def dropout_bwd(self, g, drop):
+        return g * drop_factor(drop, g.shape, g.device)
 
     # ---- elementwise glue ----
     def add_mask_fwd(self, a, b, keep, keep_a=None):
         """(a * keep_a[row] + b) * keep[row]"""
         y = a if keep_a is None else a * keep_a.to(a.dtype).unsqueeze(-1)
         y = y if b is None else y + b
-        return y if keep is None else y * keep.to(y.dtype).unsqueeze(-1)
+        return self._out(y if keep is None else y * keep.to(y.dtype).unsqueeze(-1))
 
     def add_mask_bwd(self, dy, keep, keep_a=None):
         d = dy if keep is None else dy * keep.to(dy.dtype).unsqueeze(-1)
         return d if keep_a is None else d * keep_a.to(dy.dtype).unsqueeze(-1)
 
     def select_rows_fwd(self, mask, a, b):
-        return torch.where(mask.bool().unsqueeze(-1), a, b)
+        return self._out(torch.where(mask.bool().unsqueeze(-1), a, b))
 
     def select_rows_bwd(self, dy, mask):
         m = mask.bool().unsqueeze(-1)
         return dy.masked_fill(~m, 0.0), dy.masked_fill(m, 0.0)
 
     def cat2_fwd(self, a, b):
-        return torch.cat([a, b], -1)
+        return self._out(torch.cat([a, b], -1))
 
     def cat2_bwd(self, dy, ka: int):
         return dy[:, :ka].contiguous(), dy[:, ka:].contiguous()
@@ -216,7 +243,7 @@ class OracleOps:
         return dx
 
     def gather_rows_fwd(self, x, idx):
-        return x[idx]
+        return self._out(x[idx])
 
     def gather_rows_bwd(self, dy, idx, n_row: int):
         dx = torch.zeros(n_row, dy.shape[1], dtype=dy.dtype, device=dy.device)

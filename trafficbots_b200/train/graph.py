@@ -405,9 +405,9 @@ def training_forward(fn: Fn, params: Params, batch: Dict[str, Tensor], eps: Tens
     # ---- step-stacked backward of the decode front (see Model.decode_front): the forward of every step writes its buffers into
     # row block t of step-stacked buffers; afterwards the chain is RECORDED once over the stacked buffers, so its backward is one
     # pass with n_step x M rows per launch instead of n_step passes with M rows (the front is ~70 % of a step's launches).
-    # Needs the CUDA back end (allocation hook) and the general attention kernel for the shared map keys (P > 32).
+    # Needs a back end with an allocation hook and the general attention kernel for the shared map keys (P > 32).
     if stack_backward is None:
-        stack_backward = getattr(ops, "name", "") == "cuda" and P > 32
+        stack_backward = hasattr(ops, "alloc_hook") and P > 32
     pre_site = first_drop_site + 500000  # dropout sites of the front: the same ids at every step, element indices continue
     tail_site = first_drop_site + 700000  # ... and of the tail
     if stack_backward:

@@ -70,6 +70,7 @@ class TrainState:
         self.dropout_p = float(dropout_p)
         self.drop_seed = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.n_split = int(n_split)  # concurrent sub-batch chains per step (see forward_backward)
+        self.stack_backward = None  # None: step-stacked backward whenever the back end supports it (graph.training_forward)
         self._streams, self._keep = None, None
         self.n_step = 0
         self.last_ops = 0
@@ -104,7 +105,8 @@ class TrainState:
         if new_seed and not (self.device.type == "cuda" and torch.cuda.is_current_stream_capturing()):
             self.new_dropout_seed()
         self.flat_g.zero_()
-        kw = dict(return_buffers=return_buffers, drop_seed=self.drop_seed if self.dropout_p > 0.0 else None, drop_p=self.dropout_p)
+        kw = dict(return_buffers=return_buffers, drop_seed=self.drop_seed if self.dropout_p > 0.0 else None, drop_p=self.dropout_p,
+                  stack_backward=self.stack_backward)
         n_split = min(self.n_split, S) if self.device.type == "cuda" and not return_buffers else 1
         if n_split <= 1:
             fn = Fn(self.ops)
